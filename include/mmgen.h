@@ -1,0 +1,142 @@
+/* mmgen.h - C ABI of the B200-native chunk-generation path.
+ *
+ * This is the drop-in boundary for the generation entry points that the reference's chunk manager
+ * (Terrain::tick, /root/reference/src/terrain/terrain.cpp:587-960) calls on `Chunk`
+ * (/root/reference/src/terrain/chunk.hpp:100-172). The reference has no FFI layer: that C++ surface
+ * is its operator API, so every function below names the reference entry point it replaces.
+ * Plain pointers and sizes only; all functions return 0 on success, non-zero on failure, and
+ * mmgen_last_error() returns a message (the reference prints and exit()s instead,
+ * /root/reference/src/cuda/cuda_utils.cpp:5-17).
+ *
+ * Wire formats are the reference's:
+ *   origins      int32[n][2]          chunk origin in blocks (x, z)            chunk.cu:199-203
+ *   heightfield  float[n][256]        index x + 16*z                           chunk.hpp:59-61
+ *   biomeWeights float[n][24][256]    [biome][z][x]                            chunk.hpp:70-71
+ *   layers       float[n][20][256]    [material][z][x], layer START heights    chunk.hpp:64-65
+ *   caveLayers   MmgenCaveLayer[n][256][32]                                    biome.hpp:108-117
+ *   blocks       uint8[n][16][16][384] index y + 384*(x + 16*z)                biomeFuncs.hpp:25-30
+ *   features     MmgenFeaturePlacement / MmgenCaveFeaturePlacement             biome.hpp:207-212,254-260
+ *
+ * Two ways to use it:
+ *   (1) batch operators (mmgen_heightfields ... mmgen_fill): HOST pointers in, HOST pointers out,
+ *       one call per stage like the reference's static Chunk::* functions. Host<->device copies
+ *       happen inside the call; the call returns when results are in host memory.
+ *   (2) device-resident world (mmgen_world_*): a rectangular window of chunks whose intermediate
+ *       products never leave HBM between stages; this is what the headless bench drives and what
+ *       the multi-GPU tiling uses.
+ */
+#ifndef MMGEN_H
+#define MMGEN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMGEN_NUM_BIOMES 24
+#define MMGEN_NUM_MATERIALS 20
+#define MMGEN_MAX_CAVE_LAYERS 32
+#define MMGEN_MAX_FEATURES 2048       /* MAX_GATHERED_FEATURES_PER_CHUNK, biome.hpp:7 */
+#define MMGEN_MAX_CAVE_FEATURES 4096  /* MAX_GATHERED_CAVE_FEATURES_PER_CHUNK, biome.hpp:8 */
+#define MMGEN_CHUNK_BLOCKS 98304
+#define MMGEN_ZONE_SIZE 12            /* chunks per zone side, terrain.hpp:17 */
+
+typedef struct { int32_t start, end; uint8_t bottomBiome, topBiome, pad[2]; } MmgenCaveLayer;          /* 12 B */
+typedef struct { uint8_t feature, pad0[3]; int32_t x, y, z; uint8_t canReplaceBlocks, pad1[3]; } MmgenFeaturePlacement; /* 20 B */
+typedef struct { uint8_t feature, pad0[3]; int32_t x, y, z; int32_t layerHeight; uint8_t canReplaceBlocks, pad1[3]; } MmgenCaveFeaturePlacement; /* 24 B */
+
+/* stage bits for mmgen_world_generate */
+enum {
+    MMGEN_STAGE_HEIGHTFIELD = 1,   /* S1  Chunk::generateHeightfields            chunk.cu:187-229 */
+    MMGEN_STAGE_LAYERS = 2,        /* S2  gatherHeightfield + generateLayers     chunk.cu:237-302, 417-469 */
+    MMGEN_STAGE_EROSION = 4,       /* S3  Chunk::erodeZone                       chunk.cu:658-749 */
+    MMGEN_STAGE_CAVES = 8,         /* S4  Chunk::generateCaves                   chunk.cu:939-993 */
+    MMGEN_STAGE_FEATURES = 16,     /* S5  generate/gatherFeaturePlacements       chunk.cu:1147-1196 */
+    MMGEN_STAGE_FILL = 32,         /* S6  Chunk::fill incl. placeDecorators      chunk.cu:1518-1747 */
+    MMGEN_STAGE_ALL = 63
+};
+
+/* ---- lifetime: replaces BiomeUtils::init() (biomeFuncs.hpp:725) + Terrain::initCuda/freeCuda
+ *      (terrain.cpp:154-218). device = CUDA ordinal. Fails if no CUDA device is usable: there is
+ *      no CPU fallback. */
+int mmgen_init(int device);
+int mmgen_shutdown(void);
+const char* mmgen_last_error(void);
+/* number of kernel launches issued by this library since mmgen_init (bench.py's gpu_launches) */
+uint64_t mmgen_launch_count(void);
+
+/* ---- batch operators (host pointers) ---- */
+
+/* Chunk::generateHeightfields, chunk.hpp:100-108 / chunk.cu:187-229 */
+int mmgen_heightfields(int n, const int32_t* origins, float* out_heightfield, float* out_biomeWeights);
+
+/* Chunk::gatherHeightfield + Chunk::generateLayers, chunk.hpp:110-122 / chunk.cu:237-302, 322-469.
+ * heightfield18: float[n][18*18], the chunk's heightfield with the 1-block border gathered from its
+ * 8 neighbours (what otherChunkGatherHeightfield builds). Forward layers the reference leaves
+ * unwritten after its early break (chunk.cu:387-390) are written as the running height here. */
+int mmgen_layers(int n, const int32_t* origins, const float* heightfield18, const float* biomeWeights,
+                 float* out_layers);
+
+/* Chunk::erodeZone, chunk.hpp:124-129 / chunk.cu:477-749. gathered: float[9][384][384] = the 8 loose
+ * layer-start planes (materials 12..19) followed by the heightfield plane of the 24x24-chunk window
+ * around the zone, exactly what copyLayers(..., true) builds. out_eroded: float[8][384][384], the
+ * relaxed loose layer starts of the whole window (the reference keeps the centre 192x192). */
+int mmgen_erode_zone(const float* gathered, float* out_eroded, int* out_sweeps);
+
+/* Chunk::generateCaves, chunk.hpp:131-141 / chunk.cu:755-993 */
+int mmgen_caves(int n, const int32_t* origins, const float* heightfield, const float* biomeWeights,
+                MmgenCaveLayer* out_caveLayers);
+
+/* Chunk::generateFeaturePlacements, chunk.hpp:151 / chunk.cu:999-1156 (CPU in the reference).
+ * Outputs at most maxPerChunk placements per chunk in the reference's column order (z outer, x
+ * inner); out_counts[n][2] = {surface, cave} counts. */
+int mmgen_feature_placements(int n, const int32_t* origins, const float* heightfield, const float* biomeWeights,
+                             const float* layers, const MmgenCaveLayer* caveLayers, int maxPerChunk,
+                             MmgenFeaturePlacement* out_features, MmgenCaveFeaturePlacement* out_caveFeatures,
+                             int32_t* out_counts);
+
+/* Chunk::fill incl. Chunk::placeDecorators, chunk.hpp:154-172 / chunk.cu:1202-1747.
+ * features / caveFeatures: the GATHERED lists per chunk (what gatherFeaturePlacements builds,
+ * chunk.cu:1158-1196), numFeatures[n][2] = {surface, cave} list lengths (no terminator needed). */
+int mmgen_fill(int n, const int32_t* origins, const float* heightfield, const float* biomeWeights,
+               const float* layers, const MmgenCaveLayer* caveLayers,
+               const MmgenFeaturePlacement* features, const MmgenCaveFeaturePlacement* caveFeatures,
+               const int32_t* numFeatures, int featureStride, int caveFeatureStride, uint8_t* out_blocks);
+
+/* ---- device-resident world ---- */
+typedef struct MmgenWorld MmgenWorld;
+
+/* A window of nx x nz chunks whose lower corner is chunk (cx0, cz0). Every stage is run on as
+ * much of the window as its halo allows, like the reference state machine would inside it:
+ * S1 everywhere; S2 where the 3x3 chunk neighbourhood exists; S3 on zones (aligned to multiples of
+ * 12 chunks) whose 24x24 window exists; S4/S5a on eroded zones; S5b/S6 where the 7x7 neighbourhood
+ * has placements. */
+int mmgen_world_create(int cx0, int cz0, int nx, int nz, MmgenWorld** out);
+int mmgen_world_destroy(MmgenWorld* w);
+int mmgen_world_generate(MmgenWorld* w, int stageMask);
+/* blocks until all queued work of the world is done */
+int mmgen_world_sync(MmgenWorld* w);
+/* furthest completed stage per chunk (0..6), raster order i = (cz-cz0)*nx + (cx-cx0) */
+int mmgen_world_stages(MmgenWorld* w, uint8_t* out);
+/* device time of the last mmgen_world_generate per stage (ms, CUDA events), stage 1..6 */
+int mmgen_world_stage_ms(MmgenWorld* w, float* out7);
+int mmgen_world_erosion_sweeps(MmgenWorld* w, int* out);
+
+/* downloads (host pointers), raster order; any pointer may be NULL */
+int mmgen_world_download(MmgenWorld* w, float* heightfield, float* biomeWeights, float* layers,
+                         MmgenCaveLayer* caveLayers, uint8_t* blocks);
+/* per-chunk placement lists (own, not gathered): counts[n][2]; lists packed with stride maxPerChunk */
+int mmgen_world_download_features(MmgenWorld* w, int maxPerChunk, MmgenFeaturePlacement* features,
+                                  MmgenCaveFeaturePlacement* caveFeatures, int32_t* counts);
+/* device pointers of the resident planes (for zero-copy consumers such as a mesher) */
+int mmgen_world_device_ptrs(MmgenWorld* w, void** heightfield, void** biomeWeights, void** layers,
+                            void** caveLayers, void** blocks);
+/* 64-bit FNV-1a of the block volume of every filled chunk, computed on the device (cheap
+ * cross-GPU / cross-run equality check for large worlds) */
+int mmgen_world_block_checksum(MmgenWorld* w, uint64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMGEN_H */

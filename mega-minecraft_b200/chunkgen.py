@@ -1,0 +1,146 @@
+"""ctypes binding of libmmgen.so (include/mmgen.h).
+
+Mirrors the reference's generation entry points (static Chunk::* functions,
+/root/reference/src/terrain/chunk.hpp:100-172) with numpy arrays in the reference's wire layouts.
+There is no CPU fallback: if the CUDA library is missing or no GPU is present every call raises.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libmmgen.so")
+
+STAGE_HEIGHTFIELD, STAGE_LAYERS, STAGE_EROSION, STAGE_CAVES, STAGE_FEATURES, STAGE_FILL = 1, 2, 4, 8, 16, 32
+STAGE_ALL = 63
+
+CaveLayer = np.dtype([("start", "<i4"), ("end", "<i4"), ("bottomBiome", "u1"), ("topBiome", "u1"), ("pad", "u1", (2,))])
+FeaturePlacement = np.dtype([("feature", "u1"), ("pad0", "u1", (3,)), ("x", "<i4"), ("y", "<i4"), ("z", "<i4"),
+                             ("canReplaceBlocks", "u1"), ("pad1", "u1", (3,))])
+CaveFeaturePlacement = np.dtype([("feature", "u1"), ("pad0", "u1", (3,)), ("x", "<i4"), ("y", "<i4"), ("z", "<i4"),
+                                 ("layerHeight", "<i4"), ("canReplaceBlocks", "u1"), ("pad1", "u1", (3,))])
+assert CaveLayer.itemsize == 12 and FeaturePlacement.itemsize == 20 and CaveFeaturePlacement.itemsize == 24
+
+NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-fmad=false", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+class MmgenError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _LIB
+
+
+def build(force=False):
+    """Compile csrc/mmgen.cu for sm_100a into libmmgen.so (in-tree)."""
+    src = os.path.join(_HERE, "csrc", "mmgen.cu")
+    deps = [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc"))]
+    deps.append(os.path.join(_HERE, "..", "include", "mmgen.h"))
+    if not force and os.path.exists(_LIB) and all(os.path.getmtime(_LIB) >= os.path.getmtime(d) for d in deps):
+        return _LIB
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", _LIB, src]
+    subprocess.run(cmd, check=True)
+    return _LIB
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class ChunkGen:
+    """Batch operators with host arrays in / host arrays out (one call per stage, like Chunk::*)."""
+
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            if not os.path.exists(_LIB):
+                raise MmgenError("libmmgen.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+            L = ctypes.CDLL(_LIB)
+            L.mmgen_last_error.restype = ctypes.c_char_p
+            L.mmgen_launch_count.restype = ctypes.c_uint64
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, device=0):
+        self.L = self.lib()
+        self._check(self.L.mmgen_init(int(device)))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MmgenError(self.L.mmgen_last_error().decode())
+
+    def launch_count(self):
+        return int(self.L.mmgen_launch_count())
+
+    @staticmethod
+    def origins(chunk_coords):
+        """(n,2) chunk coordinates -> (n,2) int32 block origins."""
+        return (np.asarray(chunk_coords, dtype=np.int32).reshape(-1, 2) * 16).astype(np.int32)
+
+    def heightfields(self, origins):
+        """Chunk::generateHeightfields (chunk.cu:187-229)."""
+        origins = np.ascontiguousarray(origins, dtype=np.int32).reshape(-1, 2)
+        n = origins.shape[0]
+        h = np.empty((n, 256), np.float32)
+        w = np.empty((n, 24, 256), np.float32)
+        self._check(self.L.mmgen_heightfields(n, _ptr(origins), _ptr(h), _ptr(w)))
+        return h, w
+
+    def world(self, cx0, cz0, nx, nz):
+        return World(self, cx0, cz0, nx, nz)
+
+
+class World:
+    """Device-resident window of chunks (mmgen_world_*)."""
+
+    def __init__(self, gen, cx0, cz0, nx, nz):
+        self.gen, self.L = gen, gen.L
+        self.cx0, self.cz0, self.nx, self.nz, self.n = cx0, cz0, nx, nz, nx * nz
+        self.h = ctypes.c_void_p()
+        gen._check(self.L.mmgen_world_create(cx0, cz0, nx, nz, ctypes.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.L.mmgen_world_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def generate(self, stage_mask=STAGE_ALL):
+        self.gen._check(self.L.mmgen_world_generate(self.h, int(stage_mask)))
+
+    def sync(self):
+        self.gen._check(self.L.mmgen_world_sync(self.h))
+
+    def stages(self):
+        out = np.zeros(self.n, np.uint8)
+        self.gen._check(self.L.mmgen_world_stages(self.h, _ptr(out)))
+        return out.reshape(self.nz, self.nx)
+
+    def stage_ms(self):
+        out = np.zeros(7, np.float32)
+        self.gen._check(self.L.mmgen_world_stage_ms(self.h, _ptr(out)))
+        return out
+
+    def download(self, heightfield=False, biome_weights=False, layers=False, cave_layers=False, blocks=False):
+        res = {}
+        h = np.empty((self.n, 256), np.float32) if heightfield else None
+        w = np.empty((self.n, 24, 256), np.float32) if biome_weights else None
+        l = np.empty((self.n, 20, 256), np.float32) if layers else None
+        c = np.empty((self.n, 256, 32), CaveLayer) if cave_layers else None
+        b = np.empty((self.n, 16, 16, 384), np.uint8) if blocks else None
+        self.gen._check(self.L.mmgen_world_download(self.h, _ptr(h), _ptr(w), _ptr(l), _ptr(c), _ptr(b)))
+        for k, v in (("heightfield", h), ("biome_weights", w), ("layers", l), ("cave_layers", c), ("blocks", b)):
+            if v is not None:
+                res[k] = v
+        return res

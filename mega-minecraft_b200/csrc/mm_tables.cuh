@@ -1,0 +1,141 @@
+// Enumerations, wire structs and constant-memory tables of the generation path.
+// Values and order follow /root/reference/src/terrain/block.hpp:5-154, biome.hpp:13-260 and the
+// tables BiomeUtils::init() uploads (/root/reference/src/terrain/biomeFuncs.hpp:725-1256); here they
+// are compile-time __constant__ initialisers, so there is no init-order dependency.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mmg {
+
+constexpr int NUM_BIOMES = 24, NUM_OCEAN_BIOMES = 5, NUM_OCEAN_BEACH_BIOMES = 8;
+constexpr int NUM_CAVE_BIOMES = 5;
+constexpr int NUM_MATERIALS = 20, NUM_STRATIFIED = 12, NUM_FORWARD = 10, NUM_ERODED = 8;
+constexpr int MAX_CAVE_LAYERS = 32, MAX_FEATURES = 2048, MAX_CAVE_FEATURES = 4096;
+constexpr int SEA_LEVEL = 128, LAVA_LEVEL = 8;
+constexpr int ZONE_SIZE = 12, EROSION_SIDE = ZONE_SIZE * 2 * 16, EROSION_COLS = EROSION_SIDE * EROSION_SIDE;
+
+enum Biome : uint8_t
+{
+    CORAL_REEF, ARCHIPELAGO, WARM_OCEAN, ICEBERGS, COOL_OCEAN, ROCKY_BEACH, TROPICAL_BEACH, BEACH,
+    SAVANNA, MESA, FROZEN_WASTELAND, REDWOOD_FOREST, SHREKS_SWAMP, SPARSE_DESERT, LUSH_BIRCH_FOREST, TIANZI_MOUNTAINS,
+    JUNGLE, RED_DESERT, PURPLE_MUSHROOMS, CRYSTALS, OASIS, DESERT, PLAINS, MOUNTAINS
+};
+enum CaveBiome : uint8_t { CB_NONE, CB_CRYSTAL_CAVES, CB_LUSH_CAVES, CB_WARPED_FOREST, CB_AMBER_FOREST };
+enum Material : uint8_t
+{
+    M_BLACKSTONE, M_DEEPSLATE, M_SLATE, M_STONE, M_TUFF, M_CALCITE, M_GRANITE, M_TERRACOTTA, M_MARBLE, M_ANDESITE,
+    M_RED_SANDSTONE, M_SANDSTONE,
+    M_GRAVEL, M_CLAY, M_MUD, M_DIRT, M_RED_SAND, M_SAND, M_SMOOTH_SAND, M_SNOW
+};
+enum Feature : uint8_t
+{
+    F_NONE, F_SPHERE, F_CORAL, F_KELP, F_ICEBERG, F_ACACIA_TREE, F_REDWOOD_TREE, F_CYPRESS_TREE, F_BIRCH_TREE, F_PINE_TREE,
+    F_PINE_SHRUB, F_RAFFLESIA, F_LARGE_JUNGLE_TREE, F_SMALL_JUNGLE_TREE, F_TINY_JUNGLE_TREE, F_MEDIUM_PURPLE_MUSHROOM,
+    F_PURPLE_MUSHROOM, F_MEDIUM_CRYSTAL, F_CRYSTAL, F_PALM_TREE, F_CACTUS, NUM_FEATURES
+};
+enum CaveFeature : uint8_t
+{
+    CF_NONE, CF_TEST_GLOWSTONE_PILLAR, CF_TEST_SHROOMLIGHT_PILLAR, CF_CAVE_VINE, CF_GLOWSTONE_CLUSTER, CF_STORMLIGHT_SPHERE,
+    CF_CEILING_STORMLIGHT_SPHERE, CF_CRYSTAL_PILLAR, CF_WARPED_FUNGUS, CF_AMBER_FUNGUS, NUM_CAVE_FEATURES
+};
+
+enum Block : uint8_t
+{
+    B_AIR, B_WATER, B_LAVA, B_CAVE_VINES_MAIN, B_CAVE_VINES_GLOW_MAIN, B_CAVE_VINES_END, B_CAVE_VINES_GLOW_END, B_GRASS,
+    B_JUNGLE_GRASS, B_SAVANNA_GRASS, B_WARPED_MUSHROOM, B_WARPED_ROOTS, B_NETHER_SPROUTS, B_INFECTED_MUSHROOM, B_AMBER_ROOTS,
+    B_DANDELION, B_POPPY, B_PITCHER_BOTTOM, B_PITCHER_TOP, B_CORNFLOWER, B_BLUE_ORCHID, B_ALLIUM, B_RED_TULIP, B_ORANGE_TULIP,
+    B_WHITE_TULIP, B_PINK_TULIP, B_LILAC_BOTTOM, B_LILAC_TOP, B_PEONY_BOTTOM, B_PEONY_TOP, B_OXEYE_DAISY, B_LILY_OF_THE_VALLEY,
+    B_JUNGLE_FERN, B_SMALL_MAGENTA_CRYSTAL, B_SMALL_CYAN_CRYSTAL, B_SMALL_GREEN_CRYSTAL, B_SMALL_PURPLE_MUSHROOM, B_DEAD_BUSH,
+    B_HANGING_SMALL_MAGENTA_CRYSTAL, B_HANGING_SMALL_CYAN_CRYSTAL, B_HANGING_SMALL_GREEN_CRYSTAL, B_TALL_GRASS_BOTTOM,
+    B_TALL_GRASS_TOP, B_TALL_JUNGLE_GRASS_BOTTOM, B_TALL_JUNGLE_GRASS_TOP, B_TORCHFLOWER, B_BRAIN_CORAL, B_BUBBLE_CORAL,
+    B_FIRE_CORAL, B_HORN_CORAL, B_TUBE_CORAL, B_SEAGRASS, B_TALL_SEAGRASS_BOTTOM, B_TALL_SEAGRASS_TOP, B_KELP_MAIN, B_KELP_END,
+    B_BEDROCK,
+    B_STONE, B_DIRT, B_GRASS_BLOCK, B_SAND, B_GRAVEL, B_MYCELIUM, B_SNOW, B_SNOWY_GRASS_BLOCK, B_MUSHROOM_STEM,
+    B_MUSHROOM_UNDERSIDE, B_PURPLE_MUSHROOM_CAP, B_MARBLE, B_ANDESITE, B_CALCITE, B_BLACKSTONE, B_TUFF, B_DEEPSLATE, B_GRANITE,
+    B_SLATE, B_SANDSTONE, B_CLAY, B_RED_SAND, B_RED_SANDSTONE, B_MUD, B_JUNGLE_GRASS_BLOCK, B_RAFFLESIA_PETAL,
+    B_RAFFLESIA_CENTER, B_RAFFLESIA_SPIKES, B_RAFFLESIA_STEM, B_JUNGLE_WOOD, B_JUNGLE_LEAVES_PLAIN, B_JUNGLE_LEAVES_FRUITS,
+    B_CACTUS, B_PALM_WOOD, B_PALM_LEAVES, B_MAGENTA_CRYSTAL, B_CYAN_CRYSTAL, B_GREEN_CRYSTAL, B_SMOOTH_SAND, B_TERRACOTTA,
+    B_YELLOW_TERRACOTTA, B_ORANGE_TERRACOTTA, B_PURPLE_TERRACOTTA, B_RED_TERRACOTTA, B_WHITE_TERRACOTTA, B_QUARTZ, B_ICE,
+    B_PACKED_ICE, B_BLUE_ICE, B_SAVANNA_GRASS_BLOCK, B_BIRCH_WOOD, B_BIRCH_LEAVES, B_YELLOW_BIRCH_LEAVES, B_ORANGE_BIRCH_LEAVES,
+    B_ACACIA_WOOD, B_ACACIA_LEAVES, B_SMOOTH_SANDSTONE, B_PINE_WOOD, B_PINE_LEAVES_1, B_PINE_LEAVES_2, B_REDWOOD_WOOD,
+    B_REDWOOD_LEAVES, B_CYPRESS_WOOD, B_CYPRESS_LEAVES, B_GLOWSTONE, B_SHROOMLIGHT, B_WARPED_DEEPSLATE, B_WARPED_BLACKSTONE,
+    B_MOSS, B_AMBER_DEEPSLATE, B_AMBER_BLACKSTONE, B_WARPED_STEM, B_WARPED_WART, B_AMBER_STEM, B_AMBER_WART, B_COBBLESTONE,
+    B_COBBLED_DEEPSLATE, B_BRAIN_CORAL_BLOCK, B_BUBBLE_CORAL_BLOCK, B_FIRE_CORAL_BLOCK, B_HORN_CORAL_BLOCK, B_TUBE_CORAL_BLOCK,
+    B_SEA_LANTERN, NUM_BLOCKS
+};
+static_assert(NUM_BLOCKS == 140 && B_KELP_END == 55 && B_BEDROCK == 56, "block.hpp:153-154");
+constexpr int NUM_NON_SOLID_BLOCKS = B_KELP_END + 1;
+
+// wire structs (biome.hpp:108-117, 207-212, 254-260); sizes 12 / 20 / 24 bytes
+struct CaveLayer { int32_t start, end; uint8_t bottomBiome, topBiome; uint8_t pad[2]; };
+struct FeaturePlacement { uint8_t feature; uint8_t pad0[3]; int32_t x, y, z; uint8_t canReplaceBlocks; uint8_t pad1[3]; };
+struct CaveFeaturePlacement { uint8_t feature; uint8_t pad0[3]; int32_t x, y, z; int32_t layerHeight; uint8_t canReplaceBlocks; uint8_t pad1[3]; };
+static_assert(sizeof(CaveLayer) == 12 && sizeof(FeaturePlacement) == 20 && sizeof(CaveFeaturePlacement) == 24, "wire layout");
+
+// biome noise sign table, biomeFuncs.hpp:733-762: 0 ignore, 1 positive (w *= n), 2 negative (w *= 1-n)
+// columns: ocean, beach, rocky, magic, temperature, moisture
+__constant__ const uint8_t c_biomeNoiseWeights[NUM_BIOMES][6] = {
+    {1, 2, 1, 1, 0, 0}, {1, 2, 1, 2, 0, 0}, {1, 2, 2, 0, 1, 0}, {1, 2, 2, 1, 2, 0}, {1, 2, 2, 2, 2, 0},
+    {1, 1, 1, 0, 0, 0}, {1, 1, 2, 0, 1, 0}, {1, 1, 2, 0, 2, 0},
+    {2, 0, 1, 1, 1, 1}, {2, 0, 1, 1, 1, 2}, {2, 0, 1, 1, 2, 1}, {2, 0, 1, 1, 2, 2},
+    {2, 0, 1, 2, 1, 1}, {2, 0, 1, 2, 1, 2}, {2, 0, 1, 2, 2, 1}, {2, 0, 1, 2, 2, 2},
+    {2, 0, 2, 1, 1, 1}, {2, 0, 2, 1, 1, 2}, {2, 0, 2, 1, 2, 1}, {2, 0, 2, 1, 2, 2},
+    {2, 0, 2, 2, 1, 1}, {2, 0, 2, 2, 1, 2}, {2, 0, 2, 2, 2, 1}, {2, 0, 2, 2, 2, 2}};
+// cave biome table, biomeFuncs.hpp:767-776; columns: none, shallow, warped, rocky
+__constant__ const uint8_t c_caveBiomeNoiseWeights[NUM_CAVE_BIOMES][4] = {
+    {1, 0, 0, 0}, {2, 1, 0, 1}, {2, 1, 0, 2}, {0, 2, 1, 0}, {0, 2, 2, 0}};
+
+// grass block per biome, biomeFuncs.hpp:786-801 (default DIRT)
+__constant__ const uint8_t c_biomeGrassBlock[NUM_BIOMES] = {
+    B_DIRT, B_DIRT, B_DIRT, B_DIRT, B_DIRT, B_DIRT, B_JUNGLE_GRASS_BLOCK, B_DIRT,
+    B_SAVANNA_GRASS_BLOCK, B_DIRT, B_SNOWY_GRASS_BLOCK, B_GRASS_BLOCK, B_JUNGLE_GRASS_BLOCK, B_DIRT, B_GRASS_BLOCK, B_GRASS_BLOCK,
+    B_JUNGLE_GRASS_BLOCK, B_DIRT, B_MYCELIUM, B_DIRT, B_JUNGLE_GRASS_BLOCK, B_DIRT, B_GRASS_BLOCK, B_GRASS_BLOCK};
+
+
+// material infos (biomeFuncs.hpp:808-847). For the 8 eroded materials v1 is tan(angle of repose):
+// the reference evaluates tanf(radians(angle)) with the HOST libm (55,40,45,40,30,35,65,45 degrees);
+// the bit patterns below are those values (glibc 2.39, identical on the GPU box image).
+struct MaterialInfo { uint8_t block; float thickness, v1, v2; };
+__constant__ const MaterialInfo c_materialInfos[NUM_MATERIALS] = {
+    {B_BLACKSTONE, 32.f, 32.f, 0.0030f}, {B_DEEPSLATE, 66.f, 20.f, 0.0045f}, {B_SLATE, 6.f, 24.f, 0.0062f},
+    {B_STONE, 40.f, 30.f, 0.0050f}, {B_TUFF, 24.f, 42.f, 0.0060f}, {B_CALCITE, 20.f, 30.f, 0.0040f},
+    {B_GRANITE, 18.f, 36.f, 0.0034f}, {B_TERRACOTTA, 32.f, 16.f, 0.0020f}, {B_MARBLE, 28.f, 56.f, 0.0050f},
+    {B_ANDESITE, 24.f, 48.f, 0.0030f},
+    {B_RED_SANDSTONE, 3.0f, 2.0f, 0.0035f}, {B_SANDSTONE, 3.5f, 1.5f, 0.0025f},
+    {B_GRAVEL, 2.5f, 1.42814791f, 1.8f}, {B_CLAY, 2.7f, 0.839099586f, 1.8f}, {B_MUD, 2.3f, 1.0f, 1.6f},
+    {B_DIRT, 4.2f, 0.839099586f, 1.2f}, {B_RED_SAND, 3.5f, 0.577350318f, 1.5f}, {B_SAND, 3.8f, 0.700207531f, 1.4f},
+    {B_SMOOTH_SAND, 4.5f, 2.14450693f, 4.0f}, {B_SNOW, 2.5f, 1.0f, 1.5f}};
+
+// biome -> material weights [biome][material] (biomeFuncs.hpp:856-962)
+__constant__ const float c_biomeMaterialWeights[NUM_BIOMES][NUM_MATERIALS] = {
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.7f, 0.8f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 0.3f, 0.f, 0.f, 0.f, 0.f, 0.8f, 0.f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.7f, 0.f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 0.5f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 0.5f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f},
+    {1.f, 1.f, 1.f, 0.6f, 0.15f, 0.f, 0.2f, 3.2f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 0.f, 0.8f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 0.f, 1.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.6f, 0.f, 0.f, 0.f, 1.1f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 0.f, 1.7f, 2.2f, 0.6f, 0.f, 0.f, 0.f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 2.f, 0.5f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.4f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 1.f, 1.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 0.f, 1.f, 1.f, 0.5f, 0.f, 0.f, 0.f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 1.f, 1.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 0.4f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 0.3f, 1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 0.15f, 0.2f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 1.f, 1.f, 0.f, 1.f, 0.f, 0.4f, 0.f, 0.6f, 0.f, 0.4f, 0.f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 1.f, 1.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f},
+    {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.f, 1.f, 1.f, 0.f, 0.f, 1.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f}
+};
+
+// dirVecs2d, util/enums.hpp:32-41 (N, NE, E, SE, S, SW, W, NW)
+__constant__ const int c_dirVecs2d[8][2] = {{0, 1}, {1, 1}, {1, 0}, {1, -1}, {0, -1}, {-1, -1}, {-1, 0}, {-1, 1}};
+
+}  // namespace mmg
