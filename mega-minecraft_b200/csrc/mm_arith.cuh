@@ -78,11 +78,16 @@ __device__ __forceinline__ float sx_permute(float x) { return sx_mod289(fmaf(x, 
 
 // returns dot(m, g) BEFORE the final *130: callers that add to the result fuse that multiply
 // (fma(raw, 130, c)); everything else uses 130*raw rounded.
+// SKEW_X selects which product of the skew dot(v, C.yy) the reference build fused: most inlined
+// copies compute fma(v.y, C1, v.x*C1) (false); the copies listed in DESIGN.md (direct simplex()
+// calls hoisted in front of the biome loop) compute fma(v.x, C1, v.y*C1) (true). The value only
+// feeds floor(), so the two differ only when v + s lands within an ulp of an integer.
+template <bool SKEW_X = false>
 __device__ __forceinline__ float simplex2_raw(float vx, float vy)
 {
     const float C0 = 0.211324865405187f, C1 = 0.366025403784439f, C2 = -0.577350269189626f, C3 = 0.024390243902439f;
     // i = floor(v + dot(v, C.yy)); dot = fma(v.y, C1, v.x*C1)
-    float s = fmaf(vy, C1, vx * C1);
+    float s = SKEW_X ? fmaf(vx, C1, vy * C1) : fmaf(vy, C1, vx * C1);
     float ix = floorf(vx + s), iy = floorf(vy + s);
     // x0 = v - i + dot(i, C.xx); dot = fma(i.x, C0, i.y*C0)
     float t = fmaf(ix, C0, iy * C0);
@@ -118,7 +123,8 @@ __device__ __forceinline__ float simplex2_raw(float vx, float vy)
     // 130 * dot(m, g): mul on .y, fma .x, fma .z
     return fmaf(g2, m2, fmaf(g0, m0, g1 * m1));
 }
-__device__ __forceinline__ float simplex2(float vx, float vy) { return 130.0f * simplex2_raw(vx, vy); }
+template <bool SKEW_X = false>
+__device__ __forceinline__ float simplex2(float vx, float vy) { return 130.0f * simplex2_raw<SKEW_X>(vx, vy); }
 
 // ---------------------------------------------------------------- simplex 3-D
 // returns the dot BEFORE the final *42 (same reason as simplex2_raw)
@@ -188,7 +194,7 @@ __device__ __forceinline__ float simplex3_raw(float vx, float vy, float vz)
 __device__ __forceinline__ float simplex3(float vx, float vy, float vz) { return simplex3_raw(vx, vy, vz) * 42.0f; }
 
 // ---------------------------------------------------------------- fbm (rng.hpp:166-191)
-template <int OCT>
+template <int OCT, bool SKEW_X = false>
 __device__ __forceinline__ float fbm2(float x, float y)
 {
     float f = 0.0f, amp = 1.0f;
@@ -196,7 +202,7 @@ __device__ __forceinline__ float fbm2(float x, float y)
     for (int i = 0; i < OCT; ++i)
     {
         amp *= 0.5f;
-        f = fmaf(simplex2(x, y), amp, f);
+        f = fmaf(simplex2<SKEW_X>(x, y), amp, f);
         x = x + x; y = y + y;
     }
     return f;

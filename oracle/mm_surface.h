@@ -14,7 +14,8 @@
 namespace mmo {
 
 // 130*simplex2 as a rounded product (the form fbm and most call sites use)
-static inline float sx2(float x, float y) { return 130.0f * simplex2_raw(x, y); }
+template <bool SKEW_X>
+static inline float sx2(float x, float y) { return 130.0f * simplex2_raw<SKEW_X>(x, y); }
 
 // ------------------------------------------------------------------ Worley 2-D (rng.hpp:193-233)
 // hash (rng.hpp:123-129): dot(v, K) compiles to fma(v.x, K.x, v.y*K.y) at every stage-1 call site;
@@ -64,7 +65,7 @@ struct BiomeNoise { float v[6]; };  // ocean, beach, rocky, magic, temperature, 
 static inline float single_biome_noise(float bx, float by, float scale, float ox, float oy, float th)
 {
     // smoothstep(-th, th, simplex(pos*scale + offset)): x - e0 = fma(raw, 130, th)
-    float raw = simplex2_raw(fmaf(bx, scale, ox), fmaf(by, scale, oy));
+    float raw = simplex2_raw<true>(fmaf(bx, scale, ox), fmaf(by, scale, oy));
     float t = g_clamp01(fmaf(raw, 130.0f, th) / (th - (-th)));
     return (t * t) * (3.0f - (t + t));
 }
@@ -72,10 +73,10 @@ static inline float single_biome_noise(float bx, float by, float scale, float ox
 static inline BiomeNoise biome_noise(float wx, float wz)
 {
     const float px = wx * 0.0150f, pz = wz * 0.0150f;
-    const float offx = fbm2<3>(px, pz), offz = fbm2<3>(px + 5923.45f, pz + 4129.42f);
+    const float offx = fbm2<3>(px, pz), offz = fbm2<3, true>(px + 5923.45f, pz + 4129.42f);
     const float bx = fmaf(offx, 20.0f, wx) * 0.32f, bz = fmaf(offz, 20.0f, wz) * 0.32f;
     BiomeNoise n;
-    const float oraw = simplex2_raw(fmaf(bx, 0.0007f, 2853.49f), fmaf(bz, 0.0007f, -9481.42f));
+    const float oraw = simplex2_raw<true>(fmaf(bx, 0.0007f, 2853.49f), fmaf(bz, 0.0007f, -9481.42f));
     {
         float t = g_clamp01(fmaf(oraw, 130.0f, -0.01f) / (-0.02f - 0.01f));
         n.v[0] = (t * t) * (3.0f - (t + t));
@@ -135,9 +136,9 @@ static inline float biome_height(int biome, float wx, float wz)
         const float npx = fmaf(fbm2<5>(ox, oz), 100.f, wx);
         const float npz = fmaf(fbm2<5>(ox + 5923.45f, oz + 4129.42f), 100.f, wz);
         float p1 = worley2(npx * 0.0070f, npz * 0.0070f).d1;
-        p1 = fmaf(sx2(npx * 0.0100f, npz * 0.0100f), 0.3f, 1.f) * ss_t((p1 + -0.30f) / (0.20f - 0.30f));
+        p1 = fmaf(sx2<true>(npx * 0.0100f, npz * 0.0100f), 0.3f, 1.f) * ss_t((p1 + -0.30f) / (0.20f - 0.30f));
         float p2 = worley2((npx + -3910.12f) * 0.0045f, (npz + -9012.34f) * 0.0045f).d1;
-        p2 = fmaf(sx2(npx * 0.0130f, npz * 0.0130f), 0.2f, 1.f) * ss_t((p2 + -0.16f) / (0.08f - 0.16f));
+        p2 = fmaf(sx2<true>(npx * 0.0130f, npz * 0.0130f), 0.2f, 1.f) * ss_t((p2 + -0.16f) / (0.08f - 0.16f));
         const float plateau = fmaf(p1, 14.f, p2 * 9.f);
         return plateau + fmaf(fbm2<4>(wx * 0.0080f, wz * 0.0080f), 9.f, 136.f);
     }
@@ -151,7 +152,7 @@ static inline float biome_height(int biome, float wx, float wz)
         float base = fmaf(ss_t(river / 0.05f), 10.f, 122.f);
         const float f4 = fbm2<4>(fmaf(wx, 0.7f, offx * 0.02f) * 0.0300f, fmaf(wz, 0.7f, offz * 0.02f) * 0.0300f);
         base = fmaf(ss_t((river + -0.07f) / (0.22f - 0.07f)), fmaf(f4, 5.0f, 37.5f), base);
-        return fmaf(sx2(px * 0.0250f, pz * 0.0250f), 6.f, base);
+        return fmaf(sx2<true>(px * 0.0250f, pz * 0.0250f), 6.f, base);
     }
     case FROZEN_WASTELAND: return plain_height(wx, wz, 136.f, 16.f, 0.0035f);
     case REDWOOD_FOREST: return plain_height(wx, wz, 134.f, 8.f, 0.0120f);
@@ -159,38 +160,38 @@ static inline float biome_height(int biome, float wx, float wz)
     case SPARSE_DESERT:
     {
         const float ox = wx * 0.0080f, oz = wz * 0.0080f;
-        const float npx = fmaf(sx2(ox, oz), 20.0f, wx) * 0.0160f;
-        const float npz = fmaf(sx2(ox + 5923.45f, oz + 4129.42f), 20.0f, wz) * 0.0160f;
+        const float npx = fmaf(sx2<true>(ox, oz), 20.0f, wx) * 0.0160f;
+        const float npz = fmaf(sx2<true>(ox + 5923.45f, oz + 4129.42f), 20.0f, wz) * 0.0160f;
         const float dunes = dm_powf(worley2(npx, npz).d1, 2.f);
         return fmaf(dunes, 18.f, fmaf(fbm2<4>(wx * 0.0070f, wz * 0.0070f), 4.f, 132.f));
     }
     case LUSH_BIRCH_FOREST:
     {
-        const float hills = fmaf(simplex2_raw(wx * 0.0012f, wz * 0.0012f), 130.f, 0.8f);
+        const float hills = fmaf(simplex2_raw<true>(wx * 0.0012f, wz * 0.0012f), 130.f, 0.8f);
         return fmaf(hills, 20.f, plain_height(wx, wz, 135.f, 8.f, 0.0090f));
     }
     case TIANZI_MOUNTAINS:
     {
         const float ox = wx * 0.0800f, oz = wz * 0.0800f;
-        const float npx = fmaf(sx2(ox, oz), 3.0f, wx) * 0.0150f;
-        const float npz = fmaf(sx2(ox + 5923.45f, oz + 4129.42f), 3.0f, wz) * 0.0150f;
+        const float npx = fmaf(sx2<true>(ox, oz), 3.0f, wx) * 0.0150f;
+        const float npz = fmaf(sx2<true>(ox + 5923.45f, oz + 4129.42f), 3.0f, wz) * 0.0150f;
         const float w1 = ss_t((worley2(npx, npz).d1 + -0.45f) / (0.35f - 0.45f));
         const float w2 = ss_t((worley2(fmaf(npx, 1.4f, 4292.12f), fmaf(npz, 1.4f, 9183.27f)).d1 + -0.45f) / (0.35f - 0.45f));
         const float wsum = fmaf(w1, 1.2f, w2 * 0.6f);
         const float mscale = fmaf(fbm2<3>(npx * 1.7f, npz * 1.7f), 7.f, 54.f);
-        const float hills = fmaf(sx2(wx * 0.0150f, wz * 0.0150f), 16.f, 128.f);
+        const float hills = fmaf(sx2<false>(wx * 0.0150f, wz * 0.0150f), 16.f, 128.f);
         return fmaf(wsum, mscale, fmaf(fbm2<3>(wx * 0.0070f, wz * 0.0070f), 9.f, hills));
     }
     case JUNGLE:
     {
-        const float hills = fmaf(simplex2_raw(wx * 0.0030f, wz * 0.0030f), 130.f, 0.5f);
+        const float hills = fmaf(simplex2_raw<true>(wx * 0.0030f, wz * 0.0030f), 130.f, 0.5f);
         return fmaf(hills, 25.f, plain_height(wx, wz, 139.f, 8.f, 0.0120f));
     }
     case RED_DESERT: return plain_height(wx, wz, 137.f, 13.f, 0.0075f);
     case PURPLE_MUSHROOMS: return plain_height(wx, wz, 136.f, 9.f, 0.0140f);
     case CRYSTALS:
     {
-        const float raw = simplex2_raw(wx * 0.0030f, wz * 0.0030f);
+        const float raw = simplex2_raw<true>(wx * 0.0030f, wz * 0.0030f);
         const Worley2 w = worley2(wx * 0.0700f, wz * 0.0700f);
         float tw = ss_t(fmaf(w.d2 - w.d1, 0.5f, -0.10f) / (0.15f - 0.10f));
         const float colorR = hash_fract(MMO_HDOT2(w.cpx, 238.68f, w.cpy, 491.28f));   // rand3From2(closestPoint).x
