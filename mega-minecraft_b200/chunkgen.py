@@ -92,6 +92,24 @@ class ChunkGen:
         self._check(self.L.mmgen_heightfields(n, _ptr(origins), _ptr(h), _ptr(w)))
         return h, w
 
+    def layers(self, origins, h18, weights):
+        """Chunk::generateLayers on gathered 18x18 heightfields (chunk.cu:417-469)."""
+        origins = np.ascontiguousarray(origins, dtype=np.int32).reshape(-1, 2)
+        n = origins.shape[0]
+        h18 = np.ascontiguousarray(h18, np.float32).reshape(n, 324)
+        weights = np.ascontiguousarray(weights, np.float32).reshape(n, 24, 256)
+        out = np.empty((n, 20, 256), np.float32)
+        self._check(self.L.mmgen_layers(n, _ptr(origins), _ptr(h18), _ptr(weights), _ptr(out)))
+        return out
+
+    def erode_zone(self, gathered):
+        """Chunk::erodeZone's relaxation (chunk.cu:658-709): (9,384,384) -> ((8,384,384), sweeps)."""
+        g = np.ascontiguousarray(gathered, np.float32).reshape(9, 384, 384)
+        out = np.empty((8, 384, 384), np.float32)
+        sweeps = ctypes.c_int(0)
+        self._check(self.L.mmgen_erode_zone(_ptr(g), _ptr(out), ctypes.byref(sweeps)))
+        return out, sweeps.value
+
     def world(self, cx0, cz0, nx, nz):
         return World(self, cx0, cz0, nx, nz)
 
@@ -131,6 +149,11 @@ class World:
         out = np.zeros(7, np.float32)
         self.gen._check(self.L.mmgen_world_stage_ms(self.h, _ptr(out)))
         return out
+
+    def erosion_sweeps(self):
+        v = ctypes.c_int(0)
+        self.gen._check(self.L.mmgen_world_erosion_sweeps(self.h, ctypes.byref(v)))
+        return v.value
 
     def download(self, heightfield=False, biome_weights=False, layers=False, cave_layers=False, blocks=False):
         res = {}

@@ -1,0 +1,193 @@
+// Stage 2 (terrain layers) and stage 3 (zone erosion) kernels.
+// Replace kernGenerateLayers + the CPU heightfield gather (/root/reference/src/terrain/chunk.cu:237-302,
+// 308-415) and kernDoErosion / copyLayers / fixBackwardStratifiedLayers (chunk.cu:477-749).
+//
+// S2: one CTA per chunk; the 18x18 bordered heightfield is staged in shared memory straight from the
+//     resident height planes of the 3x3 chunk neighbourhood (no host gather, no 18x18 copy in HBM).
+//     FP32-bound (<= 55 simplex per column); algorithmic bytes 46 360 B/chunk.
+// S3: Jacobi relaxation over a 384x384 zone window, 34x34 shared tiles, 144 CTAs = one wave on 148
+//     SMs. Convergence is detected on the device (one flag per sweep) and polled once per batch of
+//     sweeps instead of after every sweep. Pure max/min/sub: bound by L2 bandwidth and launch latency;
+//     algorithmic bytes per sweep 3 planes x 589 824 B.
+#pragma once
+#include "mm_common.cuh"
+#include "mm_arith.cuh"
+#include "mm_tables.cuh"
+
+namespace mmg {
+
+constexpr float kSqrt2 = 1.41421356237309504880168872420f;
+
+// ---------------------------------------------------------------- S2
+// WORLD=true : heightfield is the world's plane array [chunk][256]; the border comes from the
+//              neighbouring chunks (all 8 must exist: the host only lists such chunks).
+// WORLD=false: h18 holds one 18x18 tile per listed chunk (the reference's gathered layout).
+template <bool WORLD>
+__global__ void __launch_bounds__(256) k_layers(const int* __restrict__ chunkList, const int2* __restrict__ origins,
+                                                const float* __restrict__ heightOrH18, const float* __restrict__ biomeWeights,
+                                                float* __restrict__ layersOut, int nx)
+{
+    __shared__ float sh[18 * 18];
+    const int li = blockIdx.x;
+    const int chunk = chunkList ? chunkList[li] : li;
+    const int idx = threadIdx.x, x = idx & 15, z = idx >> 4;
+    if (WORLD)
+    {
+        for (int t = idx; t < 18 * 18; t += 256)
+        {
+            const int tx = t % 18 - 1, tz = t / 18 - 1;            // -1..16
+            const int dcx = (tx < 0) ? -1 : (tx > 15 ? 1 : 0), dcz = (tz < 0) ? -1 : (tz > 15 ? 1 : 0);
+            const int nchunk = chunk + dcx + dcz * nx;
+            sh[t] = heightOrH18[(size_t)nchunk * 256 + ((tx - 16 * dcx) + 16 * (tz - 16 * dcz))];
+        }
+    }
+    else
+    {
+        for (int t = idx; t < 18 * 18; t += 256) sh[t] = heightOrH18[(size_t)li * 324 + t];
+    }
+    __syncthreads();
+
+    const int2 o = origins[chunk];
+    const float fx = (float)(o.x + x), fz = (float)(o.y + z);
+    const float* cw = biomeWeights + (size_t)chunk * (NUM_BIOMES * 256) + idx;
+    float w[NUM_BIOMES];
+#pragma unroll
+    for (int b = 0; b < NUM_BIOMES; ++b) w[b] = cw[b * 256];
+
+    const float maxHeight = sh[(x + 1) + 18 * (z + 1)];
+    float slope = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+    {
+        const float nh = sh[(x + 1 + c_dirVecs2d[i][0]) + 18 * (z + 1 + c_dirVecs2d[i][1])];
+        const float d = fabsf(nh - maxHeight);
+        slope = fmaxf(slope, (i & 1) ? d * kSqrt2 : d);
+    }
+    auto matWeight = [&](int m) -> float {
+        float acc = 0.0f;
+#pragma unroll
+        for (int b = 0; b < NUM_BIOMES; ++b) acc = fmaf(w[b], c_biomeMaterialWeights[b][m], acc);
+        return acc;
+    };
+    auto thickness = [&](int l, float tw) -> float {
+        if (!(tw > 0.0f)) return 0.0f;
+        const float off = (float)l * 5283.64f;
+        const MaterialInfo mi = c_materialInfos[l];
+        const float f = fbm2<5>(fmaf(mi.v2, fx, off), fmaf(mi.v2, fz, off));
+        return fmaxf(fmaf(f, mi.v1, mi.thickness), 0.0f) * tw;
+    };
+    float* out = layersOut + (size_t)chunk * (NUM_MATERIALS * 256) + idx;
+    float height = 0.0f;
+    bool stop = false;
+    for (int l = 0; l < NUM_FORWARD; ++l)
+    {
+        out[l * 256] = height;     // after the reference's break point this repeats the last height
+        if (stop || l == NUM_FORWARD - 1) continue;
+        if (height > maxHeight) { stop = true; continue; }
+        height = thickness(l, matWeight(l)) + height;
+    }
+    height = 0.0f;
+    for (int l = NUM_STRATIFIED - 1; l >= NUM_FORWARD; --l)
+    {
+        height = thickness(l, matWeight(l)) + height;
+        out[l * 256] = height;
+    }
+    height = maxHeight;
+#pragma unroll
+    for (int l = NUM_MATERIALS - 1; l >= NUM_STRATIFIED; --l)
+    {
+        const MaterialInfo mi = c_materialInfos[l];
+        const float lh = fmaxf(mi.thickness * ((mi.v2 - slope) / mi.v2), 0.0f);
+        height = fmaf(-matWeight(l), lh, height);
+        out[l * 256] = height;
+    }
+}
+
+// ---------------------------------------------------------------- S3
+constexpr int kErosionSide = 384, kErosionCols = kErosionSide * kErosionSide;
+
+// gather: zone planes[9][384][384] from chunk-major layers/height of the 24x24-chunk window whose
+// lower corner is chunk (zx0, zz0) in world raster coordinates (copyLayers(..., true), chunk.cu:603-656)
+__global__ void k_zone_gather(const float* __restrict__ layers, const float* __restrict__ height, float* __restrict__ planes,
+                              int zx0, int zz0, int nx)
+{
+    const int gx = blockIdx.x * 32 + threadIdx.x, gz = blockIdx.y * 32 + threadIdx.y;
+    const int chunk = (zx0 + (gx >> 4)) + (zz0 + (gz >> 4)) * nx;
+    const int idx = (gx & 15) + 16 * (gz & 15);
+    const int col = gx + kErosionSide * gz;
+#pragma unroll
+    for (int l = 0; l < NUM_ERODED; ++l)
+        planes[(size_t)l * kErosionCols + col] = layers[(size_t)chunk * (NUM_MATERIALS * 256) + (NUM_STRATIFIED + l) * 256 + idx];
+    planes[(size_t)NUM_ERODED * kErosionCols + col] = height[(size_t)chunk * 256 + idx];
+}
+
+// one Jacobi sweep of layer `layer`: reads start plane sIn (+ accumIn on the first sweep), writes sOut
+__global__ void __launch_bounds__(1024) k_erode_sweep(const float* __restrict__ sIn, float* __restrict__ sOut,
+                                                      const float* __restrict__ eUp, const float* __restrict__ accumIn,
+                                                      float* __restrict__ accumOut, float rep, int isFirst, int* __restrict__ changedFlag)
+{
+    __shared__ float shS[34 * 34];
+    __shared__ float shE[34 * 34];
+    const int lx = threadIdx.x, lz = threadIdx.y, lid = lx + 32 * lz;
+    const int bx0 = blockIdx.x * 32, bz0 = blockIdx.y * 32;
+    for (int t = lid; t < 34 * 34; t += 1024)
+    {
+        int gx = bx0 - 1 + (t % 34), gz = bz0 - 1 + (t / 34);
+        gx = min(max(gx, 0), kErosionSide - 1);       // clamp-to-edge halo, chunk.cu:545
+        gz = min(max(gz, 0), kErosionSide - 1);
+        const int j = gx + kErosionSide * gz;
+        const float a = isFirst ? accumIn[j] : 0.0f;
+        shS[t] = sIn[j] + a;
+        shE[t] = eUp[j] + a;
+    }
+    __syncthreads();
+    const int gx = bx0 + lx, gz = bz0 + lz, i = gx + kErosionSide * gz;
+    const int c = (lx + 1) + 34 * (lz + 1);
+    const float s0 = shS[c], e0 = shE[c];
+    const float repDiag = rep * kSqrt2;
+    float ns = s0, maxT = e0 - s0;
+#pragma unroll
+    for (int d = 0; d < 8; ++d)
+    {
+        const int j = c + c_dirVecs2d[d][0] + 34 * c_dirVecs2d[d][1];
+        const float sj = shS[j];
+        ns = fmaxf(ns, sj - ((d & 1) ? repDiag : rep));
+        maxT = fmaxf(maxT, shE[j] - sj);
+    }
+    ns = fminf(ns, e0);
+    float outS = sIn[i];
+    float acc = accumIn[i];
+    if (maxT > 0.0f)
+    {
+        outS = ns;
+        if (ns != s0)
+        {
+            acc = (ns - s0) + acc;
+            *changedFlag = 1;
+        }
+    }
+    sOut[i] = outS;
+    accumOut[i] = acc;
+}
+
+// scatter the centre 12x12 chunks back (copyLayers(..., false)) into the eroded layer set and apply
+// fixBackwardStratifiedLayers (chunk.cu:725-749); the stratified layers are copied through.
+__global__ void k_zone_scatter(const float* __restrict__ planes, const float* __restrict__ layersIn, float* __restrict__ layersOut,
+                               int zx0, int zz0, int nx)
+{
+    const int gx = 96 + blockIdx.x * 32 + threadIdx.x, gz = 96 + blockIdx.y * 32 + threadIdx.y;   // centre 192x192
+    const int chunk = (zx0 + (gx >> 4)) + (zz0 + (gz >> 4)) * nx;
+    const int idx = (gx & 15) + 16 * (gz & 15);
+    const int col = gx + kErosionSide * gz;
+    const float* in = layersIn + (size_t)chunk * (NUM_MATERIALS * 256) + idx;
+    float* out = layersOut + (size_t)chunk * (NUM_MATERIALS * 256) + idx;
+#pragma unroll
+    for (int l = 0; l < NUM_FORWARD; ++l) out[l * 256] = in[l * 256];
+    const float erodedStart = planes[col];   // loose layer 0 = material 12
+#pragma unroll
+    for (int l = NUM_FORWARD; l < NUM_STRATIFIED; ++l) out[l * 256] = erodedStart - in[l * 256];
+#pragma unroll
+    for (int l = 0; l < NUM_ERODED; ++l) out[(NUM_STRATIFIED + l) * 256] = planes[(size_t)l * kErosionCols + col];
+}
+
+}  // namespace mmg

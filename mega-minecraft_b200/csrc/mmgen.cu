@@ -10,6 +10,7 @@
 
 #include "mm_common.cuh"
 #include "mm_stage1.cuh"
+#include "mm_stage23.cuh"
 
 namespace mmg {
 
@@ -58,9 +59,15 @@ struct MmgenWorld
     int2* d_origins = nullptr;
     float* d_height = nullptr;
     float* d_weights = nullptr;
+    float* d_layers = nullptr;        // S2 output (never modified afterwards: erosion pads read it)
+    float* d_eroded = nullptr;        // S3 output: full 20-layer set of eroded chunks
+    float* d_zone = nullptr;          // 9 planes + 1 scratch plane + 2 accum planes of one zone
+    int* d_flags = nullptr;           // one "changed" flag per sweep of a batch
+    int* d_list = nullptr;            // chunk index lists
+    int erosionSweeps = 0;
     std::vector<uint8_t> stage;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[14] = {};
     float stageMs[7] = {0};
 };
 
@@ -126,6 +133,85 @@ int mmgen_heightfields(int n, const int32_t* origins, float* out_heightfield, fl
     return 0;
 }
 
+// ------------------------------------------------------------------ erosion driver
+// zone: 12 planes of 384x384 floats: [0..8] gathered planes, [9] ping-pong scratch, [10..11] accum.
+// Runs Chunk::erodeZone's loop (chunk.cu:682-705) with the convergence test on the device.
+static const float kTanRepose[NUM_ERODED] = {1.42814791f, 0.839099586f, 1.0f, 0.839099586f,
+                                             0.577350318f, 0.700207531f, 2.14450693f, 1.0f};
+constexpr int kSweepBatch = 8;
+
+static int erodeZoneDevice(float* d_zone, int* d_flags, cudaStream_t stream, int* sweepsOut)
+{
+    const size_t P = kErosionCols;
+    float* scratch = d_zone + 9 * P;
+    float* accumA = d_zone + 10 * P;
+    float* accumB = d_zone + 11 * P;
+    MMG_CUDA(cudaMemsetAsync(accumA, 0, P * sizeof(float), stream));
+    int sweeps = 0;
+    int h_flags[kSweepBatch];
+    for (int layer = NUM_ERODED - 1; layer >= 0; --layer)
+    {
+        float* plane = d_zone + (size_t)layer * P;
+        const float* eUp = d_zone + (size_t)(layer + 1) * P;
+        float* sIn = plane;
+        float* sOut = scratch;
+        bool first = true, converged = false;
+        while (!converged)
+        {
+            MMG_CUDA(cudaMemsetAsync(d_flags, 0, kSweepBatch * sizeof(int), stream));
+            for (int b = 0; b < kSweepBatch; ++b)
+            {
+                MMG_LAUNCH(k_erode_sweep, dim3(12, 12), dim3(32, 32), 0, stream, sIn, sOut, eUp, accumA, accumB,
+                           kTanRepose[layer], first ? 1 : 0, d_flags + b);
+                std::swap(sIn, sOut);
+                std::swap(accumA, accumB);
+                first = false;
+                ++sweeps;
+            }
+            MMG_CUDA(cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, stream));
+            MMG_CUDA(cudaStreamSynchronize(stream));
+            converged = (h_flags[kSweepBatch - 1] == 0);
+        }
+        if (sIn != plane) MMG_CUDA(cudaMemcpyAsync(plane, sIn, P * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    }
+    // leave the live accum in plane 10 for inspection
+    if (accumA != d_zone + 10 * P) MMG_CUDA(cudaMemcpyAsync(d_zone + 10 * P, accumA, P * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    if (sweepsOut) *sweepsOut = sweeps;
+    return 0;
+}
+
+extern "C" int mmgen_layers(int n, const int32_t* origins, const float* heightfield18, const float* biomeWeights, float* out_layers)
+{
+    if (requireReady()) return 1;
+    if (n <= 0) return 0;
+    if (g_scratch[0].ensure((size_t)n * sizeof(int2))) return 1;
+    if (g_scratch[1].ensure((size_t)n * 324 * sizeof(float))) return 1;
+    if (g_scratch[2].ensure((size_t)n * NUM_BIOMES * 256 * sizeof(float))) return 1;
+    if (g_scratch[3].ensure((size_t)n * NUM_MATERIALS * 256 * sizeof(float))) return 1;
+    MMG_CUDA(cudaMemcpyAsync(g_scratch[0].ptr, origins, (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, g_stream));
+    MMG_CUDA(cudaMemcpyAsync(g_scratch[1].ptr, heightfield18, (size_t)n * 324 * sizeof(float), cudaMemcpyHostToDevice, g_stream));
+    MMG_CUDA(cudaMemcpyAsync(g_scratch[2].ptr, biomeWeights, (size_t)n * NUM_BIOMES * 256 * sizeof(float), cudaMemcpyHostToDevice, g_stream));
+    MMG_LAUNCH(k_layers<false>, n, 256, 0, g_stream, (const int*)nullptr, (const int2*)g_scratch[0].ptr,
+               (const float*)g_scratch[1].ptr, (const float*)g_scratch[2].ptr, (float*)g_scratch[3].ptr, 0);
+    MMG_CUDA(cudaMemcpyAsync(out_layers, g_scratch[3].ptr, (size_t)n * NUM_MATERIALS * 256 * sizeof(float), cudaMemcpyDeviceToHost, g_stream));
+    MMG_CUDA(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+extern "C" int mmgen_erode_zone(const float* gathered, float* out_eroded, int* out_sweeps)
+{
+    if (requireReady()) return 1;
+    const size_t P = kErosionCols;
+    if (g_scratch[4].ensure(12 * P * sizeof(float))) return 1;
+    if (g_scratch[5].ensure(kSweepBatch * sizeof(int))) return 1;
+    float* d_zone = (float*)g_scratch[4].ptr;
+    MMG_CUDA(cudaMemcpyAsync(d_zone, gathered, 9 * P * sizeof(float), cudaMemcpyHostToDevice, g_stream));
+    if (erodeZoneDevice(d_zone, (int*)g_scratch[5].ptr, g_stream, out_sweeps)) return 1;
+    MMG_CUDA(cudaMemcpyAsync(out_eroded, d_zone, 8 * P * sizeof(float), cudaMemcpyDeviceToHost, g_stream));
+    MMG_CUDA(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
 // ------------------------------------------------------------------ world
 int mmgen_world_create(int cx0, int cz0, int nx, int nz, MmgenWorld** out)
 {
@@ -155,6 +241,11 @@ int mmgen_world_destroy(MmgenWorld* w)
     cudaFree(w->d_origins);
     cudaFree(w->d_height);
     cudaFree(w->d_weights);
+    cudaFree(w->d_layers);
+    cudaFree(w->d_eroded);
+    cudaFree(w->d_zone);
+    cudaFree(w->d_flags);
+    cudaFree(w->d_list);
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     if (w->stream) cudaStreamDestroy(w->stream);
     delete w;
@@ -173,6 +264,63 @@ int mmgen_world_generate(MmgenWorld* w, int stageMask)
         MMG_CUDA(cudaEventRecord(w->ev[1], w->stream));
         for (auto& s : w->stage) s = std::max<uint8_t>(s, 1);
     }
+    const int nx = w->nx, nz = w->nz;
+    if (stageMask & MMGEN_STAGE_LAYERS)
+    {
+        // chunks whose 3x3 neighbourhood lies inside the window (gatherHeightfield's condition)
+        std::vector<int> list;
+        for (int z = 1; z < nz - 1; ++z)
+            for (int x = 1; x < nx - 1; ++x)
+                if (w->stage[z * nx + x] >= 1) list.push_back(z * nx + x);
+        MMG_CUDA(cudaEventRecord(w->ev[2], w->stream));
+        if (!list.empty())
+        {
+            if (!w->d_layers) MMG_CUDA(cudaMalloc(&w->d_layers, (size_t)w->n * NUM_MATERIALS * 256 * sizeof(float)));
+            if (!w->d_list) MMG_CUDA(cudaMalloc(&w->d_list, (size_t)w->n * sizeof(int)));
+            MMG_CUDA(cudaMemcpyAsync(w->d_list, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, w->stream));
+            MMG_LAUNCH(k_layers<true>, (int)list.size(), 256, 0, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
+                       (const float*)w->d_height, (const float*)w->d_weights, w->d_layers, nx);
+            MMG_CUDA(cudaStreamSynchronize(w->stream));   // list buffer is reused below
+            for (int i : list) w->stage[i] = std::max<uint8_t>(w->stage[i], 2);
+        }
+        MMG_CUDA(cudaEventRecord(w->ev[3], w->stream));
+    }
+    if (stageMask & MMGEN_STAGE_EROSION)
+    {
+        MMG_CUDA(cudaEventRecord(w->ev[4], w->stream));
+        w->erosionSweeps = 0;
+        // zones are aligned to multiples of 12 chunks in WORLD chunk coordinates (terrain.cpp:259-262)
+        auto floorDiv = [](int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); };
+        for (int zz = floorDiv(w->cz0, 12) * 12; zz < w->cz0 + nz; zz += 12)
+            for (int zx = floorDiv(w->cx0, 12) * 12; zx < w->cx0 + nx; zx += 12)
+            {
+                const int lx0 = zx - 6 - w->cx0, lz0 = zz - 6 - w->cz0;   // window corner, local coords
+                if (lx0 < 0 || lz0 < 0 || lx0 + 24 > nx || lz0 + 24 > nz) continue;
+                bool ok = true;
+                for (int z = 0; z < 24 && ok; ++z)
+                    for (int x = 0; x < 24 && ok; ++x) ok = w->stage[(lz0 + z) * nx + lx0 + x] >= 2;
+                if (!ok) continue;
+                if (!w->d_zone) MMG_CUDA(cudaMalloc(&w->d_zone, 12 * (size_t)kErosionCols * sizeof(float)));
+                if (!w->d_flags) MMG_CUDA(cudaMalloc(&w->d_flags, kSweepBatch * sizeof(int)));
+                if (!w->d_eroded) MMG_CUDA(cudaMalloc(&w->d_eroded, (size_t)w->n * NUM_MATERIALS * 256 * sizeof(float)));
+                MMG_LAUNCH(k_zone_gather, dim3(12, 12), dim3(32, 32), 0, w->stream, (const float*)w->d_layers,
+                           (const float*)w->d_height, w->d_zone, lx0, lz0, nx);
+                int sweeps = 0;
+                if (erodeZoneDevice(w->d_zone, w->d_flags, w->stream, &sweeps)) return 1;
+                w->erosionSweeps += sweeps;
+                MMG_LAUNCH(k_zone_scatter, dim3(6, 6), dim3(32, 32), 0, w->stream, (const float*)w->d_zone,
+                           (const float*)w->d_layers, w->d_eroded, lx0, lz0, nx);
+                for (int z = 6; z < 18; ++z)
+                    for (int x = 6; x < 18; ++x) w->stage[(lz0 + z) * nx + lx0 + x] = 3;
+            }
+        MMG_CUDA(cudaEventRecord(w->ev[5], w->stream));
+    }
+    return 0;
+}
+
+int mmgen_world_erosion_sweeps(MmgenWorld* w, int* out)
+{
+    *out = w->erosionSweeps;
     return 0;
 }
 
@@ -192,7 +340,12 @@ int mmgen_world_stage_ms(MmgenWorld* w, float* out7)
 {
     MMG_CUDA(cudaStreamSynchronize(w->stream));
     for (int s = 0; s < 7; ++s) out7[s] = 0.f;
-    MMG_CUDA(cudaEventElapsedTime(&out7[1], w->ev[0], w->ev[1]));
+    for (int st = 1; st <= 3; ++st)
+        if (cudaEventQuery(w->ev[2 * st - 1]) == cudaSuccess && cudaEventElapsedTime(&out7[st], w->ev[2 * st - 2], w->ev[2 * st - 1]) != cudaSuccess)
+        {
+            out7[st] = 0.f;
+            cudaGetLastError();
+        }
     return 0;
 }
 
@@ -202,7 +355,17 @@ int mmgen_world_download(MmgenWorld* w, float* heightfield, float* biomeWeights,
     MMG_CUDA(cudaStreamSynchronize(w->stream));
     if (heightfield && w->d_height) MMG_CUDA(cudaMemcpy(heightfield, w->d_height, (size_t)w->n * 256 * sizeof(float), cudaMemcpyDeviceToHost));
     if (biomeWeights && w->d_weights) MMG_CUDA(cudaMemcpy(biomeWeights, w->d_weights, (size_t)w->n * NUM_BIOMES * 256 * sizeof(float), cudaMemcpyDeviceToHost));
-    (void)layers; (void)caveLayers; (void)blocks;
+    // layers: eroded set where a chunk was eroded, else the S2 output
+    if (layers && w->d_layers)
+    {
+        MMG_CUDA(cudaMemcpy(layers, w->d_layers, (size_t)w->n * NUM_MATERIALS * 256 * sizeof(float), cudaMemcpyDeviceToHost));
+        if (w->d_eroded)
+            for (int i = 0; i < w->n; ++i)
+                if (w->stage[i] >= 3)
+                    MMG_CUDA(cudaMemcpy(layers + (size_t)i * NUM_MATERIALS * 256, w->d_eroded + (size_t)i * NUM_MATERIALS * 256,
+                                        NUM_MATERIALS * 256 * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    (void)caveLayers; (void)blocks;
     return 0;
 }
 

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "mm_surface.h"
+#include "mm_layers.h"
 
 namespace {
 template <class F>
@@ -48,6 +49,28 @@ void mmo_heightfields(int n, const int32_t* origins, float* out_h, float* out_w,
             }
     });
 }
+
+// Chunk::generateLayers on gathered 18x18 heightfields (chunk.cu:322-469). Forward layers the
+// reference never writes keep the value `unwritten`.
+void mmo_layers(int n, const int32_t* origins, const float* h18, const float* weights, float* out_layers, float unwritten,
+                int nthreads)
+{
+    parallel_for(n, nthreads, [&](int c) {
+        const int ox = origins[2 * c], oz = origins[2 * c + 1];
+        float* L = out_layers + (size_t)c * (mmo::NUM_MATERIALS * 256);
+        for (int i = 0; i < mmo::NUM_FORWARD * 256; ++i) L[i] = unwritten;
+        for (int z = 0; z < 16; ++z)
+            for (int x = 0; x < 16; ++x)
+            {
+                const int idx = x + 16 * z;
+                mmo::layers_column(h18 + (size_t)c * 324, x, z, ox + x, oz + z,
+                                   weights + (size_t)c * (mmo::NUM_BIOMES * 256) + idx, 256, L + idx, 256);
+            }
+    });
+}
+
+// Chunk::erodeZone's device part (chunk.cu:658-709) on planes[9][384*384], in place; returns sweeps
+int mmo_erode_zone(float* planes) { return mmo::erode_zone(planes); }
 
 // unit probes used by tests
 float mmo_sinf(float x) { return mmo::dm_sinf(x); }

@@ -41,3 +41,52 @@ class Oracle:
         w = np.empty((n, 24, 256), np.float32)
         self.L.mmo_heightfields(n, _ptr(origins), _ptr(h), _ptr(w), self.nthreads)
         return h, w
+
+    def layers(self, origins, h18, weights, unwritten=np.nan):
+        origins = np.ascontiguousarray(origins, dtype=np.int32).reshape(-1, 2)
+        n = origins.shape[0]
+        h18 = np.ascontiguousarray(h18, np.float32).reshape(n, 324)
+        weights = np.ascontiguousarray(weights, np.float32).reshape(n, 24, 256)
+        out = np.empty((n, 20, 256), np.float32)
+        self.L.mmo_layers(n, _ptr(origins), _ptr(h18), _ptr(weights), _ptr(out), ctypes.c_float(unwritten), self.nthreads)
+        return out
+
+    def erode_zone(self, planes):
+        """planes: (9, 384, 384) float32 (8 loose layer starts + heightfield); returns (eroded copy, sweeps)."""
+        p = np.ascontiguousarray(planes, np.float32).copy()
+        sweeps = self.L.mmo_erode_zone(_ptr(p))
+        return p, sweeps
+
+
+# ---- host-side data movement of the reference, restated for tests (numpy) ----
+def gather_h18(height, nx, nz):
+    """Chunk::otherChunkGatherHeightfield (chunk.cu:237-293): height (nz*nx,256) -> dict chunk idx -> (18,18)."""
+    grid = height.reshape(nz, nx, 16, 16).transpose(0, 2, 1, 3).reshape(nz * 16, nx * 16)  # [z][x] world raster
+    out = {}
+    for cz in range(1, nz - 1):
+        for cx in range(1, nx - 1):
+            out[cz * nx + cx] = grid[cz * 16 - 1:cz * 16 + 17, cx * 16 - 1:cx * 16 + 17].copy()
+    return out
+
+
+def gather_zone(layers, height, nx, lx0, lz0):
+    """copyLayers(zone, gathered, true) (chunk.cu:603-656): -> (9, 384, 384)."""
+    planes = np.empty((9, 384, 384), np.float32)
+    for cz in range(24):
+        for cx in range(24):
+            c = (lz0 + cz) * nx + (lx0 + cx)
+            for l in range(8):
+                planes[l, cz * 16:(cz + 1) * 16, cx * 16:(cx + 1) * 16] = layers[c, 12 + l].reshape(16, 16)
+            planes[8, cz * 16:(cz + 1) * 16, cx * 16:(cx + 1) * 16] = height[c].reshape(16, 16)
+    return planes
+
+
+def scatter_zone(planes, layers, nx, lx0, lz0):
+    """copyLayers(zone, gathered, false) + fixBackwardStratifiedLayers (chunk.cu:603-656, 725-749), in place on layers."""
+    for cz in range(6, 18):
+        for cx in range(6, 18):
+            c = (lz0 + cz) * nx + (lx0 + cx)
+            for l in range(8):
+                layers[c, 12 + l] = planes[l, cz * 16:(cz + 1) * 16, cx * 16:(cx + 1) * 16].reshape(256)
+            for l in (10, 11):
+                layers[c, l] = layers[c, 12] - layers[c, l]

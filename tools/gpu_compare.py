@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 import mmgen_loader  # noqa: E402
 from oracle import oracle as orc, refcuda  # noqa: E402
 
-X0, Z0, NX, NZ = -6, -6, 24, 24
+X0, Z0, NX, NZ = -7, -7, 26, 26
 
 
 def report(name, a, b):
@@ -55,6 +55,60 @@ def main():
     report("product vs ref weights", mw, ref["biome_weights"])
     report("product vs oracle height", mh, oh)
     report("product vs oracle weights", mw, ow)
+    if last >= 2:
+        print("--- S2 ---")
+        st = ref["stage"].ravel()
+        idx = np.nonzero(st >= 2)[0]
+        rl = ref["layers"]
+        np.save(os.path.join(outdir, "layers.npy"), rl)
+        np.save(os.path.join(outdir, "stage.npy"), ref["stage"])
+        h18 = orc.gather_h18(ref["heightfield"], NX, NZ)
+        H18 = np.stack([h18[i] for i in idx])
+        ol = o.layers(origins[idx], H18, ref["biome_weights"][idx])
+        ml = gen.layers(origins[idx], H18, ref["biome_weights"][idx])
+        world = gen.world(X0, Z0, NX, NZ)
+        world.generate(mm.STAGE_HEIGHTFIELD | mm.STAGE_LAYERS | (mm.STAGE_EROSION if last >= 3 else 0))
+        wd = world.download(heightfield=True, layers=True)
+        ws = world.stages().ravel()
+        print("world stages:", np.bincount(ws), "ref stages:", np.bincount(st), "erosion sweeps", world.erosion_sweeps(), "stage ms", world.stage_ms())
+        # S2 comparison on entries the reference wrote (sentinel = NaN payload) and before erosion rewrote them
+        s2 = np.nonzero(st == 2)[0]
+        pos = {int(c): k for k, c in enumerate(idx)}
+        sel = np.array([pos[int(c)] for c in s2])
+        refl = rl[s2]
+        written = refl.view(np.uint32) != refcuda.UNWRITTEN
+        print("written fraction of S2 entries: %.4f" % written.mean())
+        report("oracle vs ref  layers(S2)", ol[sel][written], refl[written])
+        report("product vs ref layers(S2)", ml[sel][written], refl[written])
+        report("product vs oracle layers(S2)", ml[sel][written], ol[sel][written])
+        report("world vs ref   layers(S2)", wd["layers"][s2][written], refl[written])
+        for l in range(20):
+            wl = written[:, l]
+            if wl.sum():
+                d = (ol[sel][:, l][wl].view(np.uint32) != refl[:, l][wl].view(np.uint32)).sum()
+                print("   layer %2d written=%d oracle-vs-ref bitdiff=%d" % (l, wl.sum(), d))
+    if last >= 3:
+        print("--- S3 ---")
+        s3 = np.nonzero(st >= 3)[0]
+        # oracle erosion from the oracle's own S2 layers of the window around zone (0,0)
+        full = np.full((NX * NZ, 20, 256), np.nan, np.float32)
+        full[idx] = ol
+        lx0, lz0 = 0 - 6 - X0, 0 - 6 - Z0
+        planes = orc.gather_zone(full, ref["heightfield"], NX, lx0, lz0)
+        t = time.time()
+        er, sweeps = o.erode_zone(planes)
+        print("oracle erosion: %d sweeps %.2fs" % (sweeps, time.time() - t))
+        orc.scatter_zone(er, full, NX, lx0, lz0)
+        mer, msweeps = gen.erode_zone(planes)
+        report("product vs oracle eroded planes", mer, er[:8])
+        refl = rl[s3]
+        report("oracle vs ref  eroded loose layers", full[s3][:, 12:], refl[:, 12:])
+        report("oracle vs ref  backward layers", full[s3][:, 10:12], refl[:, 10:12])
+        report("world vs ref   eroded loose layers", wd["layers"][s3][:, 12:], refl[:, 12:])
+        report("world vs oracle eroded loose", wd["layers"][s3][:, 12:], full[s3][:, 12:])
+        report("world vs oracle backward", wd["layers"][s3][:, 10:12], full[s3][:, 10:12])
+        d = np.abs(full[s3][:, 12:].astype(np.float64) - refl[:, 12:])
+        print("   max abs diff oracle-vs-ref eroded: %.6g ; columns differing: %d of %d" % (d.max(), int((d.max(axis=1) > 0).sum()), d.shape[0] * 256))
     # per dominant biome breakdown of oracle-vs-ref height mismatches
     dom = ref["biome_weights"].argmax(axis=1)
     single = (ref["biome_weights"].max(axis=1) == 1.0)
