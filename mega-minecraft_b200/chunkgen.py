@@ -102,6 +102,16 @@ class ChunkGen:
         self._check(self.L.mmgen_layers(n, _ptr(origins), _ptr(h18), _ptr(weights), _ptr(out)))
         return out
 
+    def caves(self, origins, heightfield, weights):
+        """Chunk::generateCaves (chunk.cu:939-993)."""
+        origins = np.ascontiguousarray(origins, dtype=np.int32).reshape(-1, 2)
+        n = origins.shape[0]
+        h = np.ascontiguousarray(heightfield, np.float32).reshape(n, 256)
+        w = np.ascontiguousarray(weights, np.float32).reshape(n, 24, 256)
+        out = np.zeros((n, 256, 32), CaveLayer)
+        self._check(self.L.mmgen_caves(n, _ptr(origins), _ptr(h), _ptr(w), _ptr(out)))
+        return out
+
     def erode_zone(self, gathered):
         """Chunk::erodeZone's relaxation (chunk.cu:658-709): (9,384,384) -> ((8,384,384), sweeps)."""
         g = np.ascontiguousarray(gathered, np.float32).reshape(9, 384, 384)

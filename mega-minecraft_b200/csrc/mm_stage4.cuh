@@ -1,0 +1,226 @@
+// Stage 4: cave-biome noise, the per-voxel cave predicate with specialCaveNoise, and the per-column
+// compaction into CaveLayers. Replaces kernGenerateCaves / shouldGenerateCaveAtBlock / getCaveBiome
+// (/root/reference/src/terrain/chunk.cu:755-937, biomeFuncs.hpp:130-220, rng.hpp:282-320).
+//
+// Mapping: k_cave_columns computes the y-independent terms once per column (ocean+beach weight and
+// the whole ravine test: 24 simplex + a 9-cell Worley that the reference re-evaluates for every one
+// of 384 voxels); k_caves then runs one 128-thread CTA per column, three voxels per thread, skips
+// the 2/3 of voxels that are decided by y alone, packs the solid/air column into 12 ballot words,
+// extracts flips with bit scans and evaluates the <= 64 cave-biome lookups in parallel.
+// FP32-pipe bound: ~23 simplex3 + 27 hashed cells per evaluated voxel; algorithmic bytes 107 528 B/chunk.
+#pragma once
+#include "mm_surface.cuh"
+
+namespace mmg {
+
+// ---------------------------------------------------------------- cave biome (biomeFuncs.hpp:135-220)
+struct CaveBiomeNoise { float v[4]; };   // none, shallow, warped, rocky
+
+__device__ __forceinline__ CaveBiomeNoise cave_biome_noise(int x, int y, int z, float maxHeight)
+{
+    const float px = (float)x, py = (float)y, pz = (float)z;
+    const float qx = px * 0.0470f, qy = py * 0.0470f, qz = pz * 0.0470f;
+    const float cx = fmaf(fbm3<3>(qx, qy, qz), 30.f, px);
+    const float cy = fmaf(fbm3<3>(qx + 5923.45f, qy + 4129.42f, qz + 5790.48f), 24.f, py);
+    const float cz = fmaf(fbm3<3>(qx + 1765.68f, qy + 4704.36f, qz + 5692.12f), 30.f, pz);
+    const float nx = cx * 0.2000f, nz = cz * 0.2000f;
+    const float top = fmaf(maxHeight + -128.f, 0.15f, 128.f);
+    const float nsStart = fmaf(fbm2<3>(nx, nz), 23.f, top + -19.f);
+    const float nsEnd = fmaf(fbm2<3>(nx + 3821.34f, nz + 4920.32f), 3.f, nsStart + -5.f);
+    const float sdStart = fmaf(fbm2<3>(nx + -4921.34f, nz + 8402.13f), 18.f, top + -72.f);
+    const float sdEnd = fmaf(fbm2<3>(nx + 9411.32f, nz + -3921.34f), 7.f, sdStart + -10.f);
+    CaveBiomeNoise n;
+    n.v[0] = ss_t((cy - nsEnd) / (nsStart - nsEnd));
+    n.v[1] = ss_t((cy - sdEnd) / (sdStart - sdEnd));
+    n.v[2] = ss_t(fmaf(simplex3_raw<true>(fmaf(cx, 0.0030f, 5821.32f), fmaf(cy, 0.0030f, 4920.12f), fmaf(cz, 0.0030f, 7931.59f)), 42.f, 0.05f) / (0.05f - -0.05f));
+    n.v[3] = ss_t(fmaf(simplex3_raw<true>(fmaf(cx, 0.0022f, -9193.23f), fmaf(cy, 0.0022f, -6813.39f), fmaf(cz, 0.0022f, (float)-2171.23)), 42.f, 0.05f) / (0.05f - -0.05f));
+    return n;
+}
+
+__device__ __forceinline__ int cave_biome(int x, int y, int z, float maxHeight, int seed)
+{
+    const CaveBiomeNoise n = cave_biome_noise(x, y, z, maxHeight);
+    Minstd rng = make_rng4(x, y, z, seed);
+    float rand = rng.u01();
+    for (int b = 0; b < NUM_CAVE_BIOMES; ++b)
+    {
+        float w = 1.0f;
+        for (int c = 0; c < 4; ++c)
+        {
+            const uint8_t t = c_caveBiomeNoiseWeights[b][c];
+            if (t == 1) w *= n.v[c];
+            else if (t == 2) w *= 1.0f - n.v[c];
+        }
+        rand -= w;
+        if (rand <= 0.f) return b;
+    }
+    return CB_NONE;
+}
+
+// ---------------------------------------------------------------- specialCaveNoise (rng.hpp:282-320)
+// hash (rng.hpp:148-155) at this call site: fma(z, Kz, fma(x, Kx, y*Ky))
+__device__ __forceinline__ float special_cave_noise(float px, float py, float pz)
+{
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    const float nfx = fx - px, nfy = fy - py, nfz = fz - pz;
+    float d1 = FLT_MAX, d2 = FLT_MAX, d3 = FLT_MAX;
+    for (int x = -1; x <= 1; ++x)
+        for (int y = -1; y <= 1; ++y)
+            for (int z = -1; z <= 1; ++z)
+            {
+                const float cx = (float)(ix + x), cy = (float)(iy + y), cz = (float)(iz + z);
+                const float jx = hash_fract(fmaf(cz, 402.98f, fmaf(cx, 238.68f, cy * 491.28f)));
+                const float jy = hash_fract(fmaf(cz, 747.42f, fmaf(cx, 654.37f, cy * 560.45f)));
+                const float jz = hash_fract(fmaf(cz, 674.81f, fmaf(cx, 640.88f, cy * 151.81f)));
+                const float dx = nfx + (jx + (float)x), dy = nfy + (jy + (float)y), dz = nfz + (jz + (float)z);
+                const float dist = sqrtf(fmaf(dz, dz, fmaf(dx, dx, dy * dy)));
+                if (dist < d1) { d3 = d2; d2 = d1; d1 = dist; }
+                else if (dist < d2) { d3 = d2; d2 = dist; }
+                else if (dist < d3) { d3 = dist; }
+            }
+    return d3 / d1 + -1.0f;
+}
+
+// y-independent part of the ravine test (chunk.cu:785-801), hoisted per column (same values)
+struct Ravine { bool active; float top, depth; };
+
+__device__ __forceinline__ Ravine ravine_column(int wx, int wz, float obw)
+{
+    Ravine r = {false, 0.f, 0.f};
+    const float rx = (float)wx * 0.0015f, rz = (float)wz * 0.0015f;
+    const float ox = fbm2<4>(rx * 10.f, rz * 10.f), oz = fbm2<4>(rx * 10.f + 5923.45f, rz * 10.f + 4129.42f);
+    const Worley2 w = worley2(fmaf(ox, 0.03f, rx), fmaf(oz, 0.03f, rz));
+    const float thr = (1.f - obw) * 0.12f;
+    if (!(w.d1 < thr)) return r;
+    const float colorX = hash_fract(fmaf(w.cpx, 238.68f, w.cpy * 491.28f));
+    r.top = fmaf(colorX, 24.f, 120.f);
+    const float ratio = 1.f - (w.d1 / thr);
+    float depth = ss_t(ratio / 0.3f) * fmaf(fbm2<4>(fmaf(rx, 8.f, 8391.32f), fmaf(rz, 8.f, 4821.39f)), 26.f, 60.f);
+    const float waveOff = fbm2<4>(fmaf(rx, 3.f, 5129.32f), fmaf(rz, 3.f, 1392.49f)) * 4.f;
+    const float wave = sinf(fmaf(rx + rz, 15.f, waveOff));
+    depth = depth * ss_t((wave + -0.4f) / (0.6f - 0.4f));
+    r.depth = depth;
+    r.active = depth > 0.0001f;
+    return r;
+}
+
+// chunk.cu:755-810
+__device__ __forceinline__ bool cave_at_block(int wx, int y, int wz, float maxHeight, float obw, const Ravine& rav)
+{
+    if (y == 0) return false;
+    const int hi = (int)maxHeight;
+    if (y > (hi > SEA_LEVEL ? hi : SEA_LEVEL)) return true;
+    const float fy = (float)y;
+    const float npx = (float)wx * 0.0050f, npy = fy * 0.0050f, npz = (float)wz * 0.0050f;
+    const float topRatio = ss_t((fmaf(obw, 50.f, fy) + -142.f) / (95.f - 142.f));
+    const float bottomRatio = ss_t((fy + -5.f) / (20.f - 5.f));
+    const float ax = npx * 0.8000f, ay = npy * 0.8000f, az = npz * 0.8000f;
+    const float o1 = fbm3<5>(ax, ay, az);
+    const float o2 = fbm3<5>(ax + 5923.45f, ay + 4129.42f, az + 5790.48f);
+    const float o3 = fbm3<5>(ax + 1765.68f, ay + 4704.36f, az + 5692.12f);
+    const float caveNoise = special_cave_noise(fmaf(o1, 1.8f, npx), fmaf(npy, 1.6f, o2 * 1.8f), fmaf(o3, 1.8f, npz));
+    float thr = fmaf(fbm3<4>(npx * 4.f, npy * 4.f, npz * 4.f), 0.12f, 0.24f);
+    const float huge = ss_t((fbm3<4>(npx * 0.0700f, npy * 0.0700f, npz * 0.0700f) + -0.2f) / (0.4f - 0.2f));
+    thr = thr * fmaf(huge, 1.4f, 1.f);
+    thr = (fmaf(bottomRatio, 0.7f, 0.3f) * topRatio) * thr;
+    if (thr > 0.04f && caveNoise < thr) return true;
+    if (rav.active && (rav.top - rav.depth) < fy) return true;
+    return false;
+}
+
+
+struct CaveColumn { float obw, ravTop, ravDepth; int ravActive; };
+
+__global__ void __launch_bounds__(256) k_cave_columns(const int* __restrict__ chunkList, const int2* __restrict__ origins,
+                                                      const float* __restrict__ biomeWeights, CaveColumn* __restrict__ cols)
+{
+    const int li = blockIdx.x, chunk = chunkList ? chunkList[li] : li;
+    const int idx = threadIdx.x;
+    const int2 o = origins[chunk];
+    const float* cw = biomeWeights + (size_t)chunk * (NUM_BIOMES * 256) + idx;
+    float obw = 0.f;
+#pragma unroll
+    for (int b = 0; b < NUM_OCEAN_BEACH_BIOMES; ++b) obw += cw[b * 256];
+    const Ravine r = ravine_column(o.x + (idx & 15), o.y + (idx >> 4), obw);
+    CaveColumn c;
+    c.obw = obw; c.ravTop = r.top; c.ravDepth = r.depth; c.ravActive = r.active ? 1 : 0;
+    cols[(size_t)li * 256 + idx] = c;
+}
+
+__global__ void __launch_bounds__(128) k_caves(const int* __restrict__ chunkList, const int2* __restrict__ origins,
+                                               const float* __restrict__ heightfield, const CaveColumn* __restrict__ cols,
+                                               CaveLayer* __restrict__ caveLayers)
+{
+    __shared__ unsigned int shFilled[13];     // bit y = 1 if solid; word 12 = 0 (y = 384 is "not filled")
+    __shared__ int shFlips[2 * MAX_CAVE_LAYERS];
+    __shared__ int shNumFlips;
+    const int li = blockIdx.x >> 8, idx = blockIdx.x & 255;
+    const int chunk = chunkList ? chunkList[li] : li;
+    const int2 o = origins[chunk];
+    const int wx = o.x + (idx & 15), wz = o.y + (idx >> 4);
+    const float maxHeight = heightfield[(size_t)chunk * 256 + idx];
+    const CaveColumn cc = cols[(size_t)li * 256 + idx];
+    Ravine rav;
+    rav.active = cc.ravActive != 0; rav.top = cc.ravTop; rav.depth = cc.ravDepth;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) shFilled[12] = 0u;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+        const int y = tid + 128 * k;
+        const bool air = cave_at_block(wx, y, wz, maxHeight, cc.obw, rav);
+        const unsigned int bits = __ballot_sync(0xffffffffu, !air);
+        if (lane == 0) shFilled[4 * k + warp] = bits;
+    }
+    __syncthreads();
+    CaveLayer* out = caveLayers + ((size_t)chunk * 256 + idx) * MAX_CAVE_LAYERS;
+    if (warp == 0)
+    {
+        // flips: filled[y] != filled[y+1]
+        unsigned int f = 0u;
+        if (lane < 12)
+        {
+            const unsigned int w0 = shFilled[lane], w1 = shFilled[lane + 1];
+            f = w0 ^ ((w0 >> 1) | (w1 << 31));
+        }
+        const int cnt = __popc(f);
+        int base = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const int v = __shfl_up_sync(0xffffffffu, base, d);
+            if (lane >= d) base += v;
+        }
+        if (lane == 11) shNumFlips = base;
+        base -= cnt;
+        while (f)
+        {
+            const int b = __ffs(f) - 1;
+            f &= f - 1;
+            if (base < 2 * MAX_CAVE_LAYERS) shFlips[base] = 32 * lane + b;
+            ++base;
+        }
+    }
+    __syncthreads();
+    const int nflips = min(shNumFlips, 2 * MAX_CAVE_LAYERS);
+    if (tid < 2 * MAX_CAVE_LAYERS)
+    {
+        // thread t handles layer t/2, bottom (even t) or top (odd t) biome
+        const int l = tid >> 1, top = tid & 1;
+        const int start = (2 * l < nflips) ? shFlips[2 * l] : 384;
+        const int end = (2 * l + 1 < nflips) ? shFlips[2 * l + 1] : 384;
+        int biome = CB_NONE;
+        if (!top) { if (start != 384) biome = cave_biome(wx, start, wz, maxHeight, 329271348); }
+        else { if (end != 384) biome = cave_biome(wx, end + 1, wz, maxHeight, 4982921); }
+        const int other = __shfl_xor_sync(0xffffffffu, biome, 1);
+        if (!top)
+        {
+            CaveLayer cl;
+            cl.start = start; cl.end = end; cl.bottomBiome = (uint8_t)biome; cl.topBiome = (uint8_t)other; cl.pad[0] = cl.pad[1] = 0;
+            out[l] = cl;
+        }
+    }
+}
+
+}  // namespace mmg

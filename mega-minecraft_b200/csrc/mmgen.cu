@@ -11,6 +11,7 @@
 #include "mm_common.cuh"
 #include "mm_stage1.cuh"
 #include "mm_stage23.cuh"
+#include "mm_stage4.cuh"
 
 namespace mmg {
 
@@ -64,6 +65,8 @@ struct MmgenWorld
     float* d_zone = nullptr;          // 9 planes + 1 scratch plane + 2 accum planes of one zone
     int* d_flags = nullptr;           // one "changed" flag per sweep of a batch
     int* d_list = nullptr;            // chunk index lists
+    CaveLayer* d_caves = nullptr;     // [chunk][256][32]
+    CaveColumn* d_caveCols = nullptr; // per-column hoisted cave terms
     int erosionSweeps = 0;
     std::vector<uint8_t> stage;
     cudaStream_t stream = nullptr;
@@ -212,6 +215,29 @@ extern "C" int mmgen_erode_zone(const float* gathered, float* out_eroded, int* o
     return 0;
 }
 
+extern "C" int mmgen_caves(int n, const int32_t* origins, const float* heightfield, const float* biomeWeights,
+                           MmgenCaveLayer* out_caveLayers)
+{
+    if (requireReady()) return 1;
+    if (n <= 0) return 0;
+    const size_t clBytes = (size_t)n * 256 * MAX_CAVE_LAYERS * sizeof(CaveLayer);
+    if (g_scratch[0].ensure((size_t)n * sizeof(int2))) return 1;
+    if (g_scratch[1].ensure((size_t)n * 256 * sizeof(float))) return 1;
+    if (g_scratch[2].ensure((size_t)n * NUM_BIOMES * 256 * sizeof(float))) return 1;
+    if (g_scratch[3].ensure(clBytes)) return 1;
+    if (g_scratch[6].ensure((size_t)n * 256 * sizeof(CaveColumn))) return 1;
+    MMG_CUDA(cudaMemcpyAsync(g_scratch[0].ptr, origins, (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, g_stream));
+    MMG_CUDA(cudaMemcpyAsync(g_scratch[1].ptr, heightfield, (size_t)n * 256 * sizeof(float), cudaMemcpyHostToDevice, g_stream));
+    MMG_CUDA(cudaMemcpyAsync(g_scratch[2].ptr, biomeWeights, (size_t)n * NUM_BIOMES * 256 * sizeof(float), cudaMemcpyHostToDevice, g_stream));
+    MMG_LAUNCH(k_cave_columns, n, 256, 0, g_stream, (const int*)nullptr, (const int2*)g_scratch[0].ptr,
+               (const float*)g_scratch[2].ptr, (CaveColumn*)g_scratch[6].ptr);
+    MMG_LAUNCH(k_caves, n * 256, 128, 0, g_stream, (const int*)nullptr, (const int2*)g_scratch[0].ptr,
+               (const float*)g_scratch[1].ptr, (const CaveColumn*)g_scratch[6].ptr, (CaveLayer*)g_scratch[3].ptr);
+    MMG_CUDA(cudaMemcpyAsync(out_caveLayers, g_scratch[3].ptr, clBytes, cudaMemcpyDeviceToHost, g_stream));
+    MMG_CUDA(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
 // ------------------------------------------------------------------ world
 int mmgen_world_create(int cx0, int cz0, int nx, int nz, MmgenWorld** out)
 {
@@ -246,6 +272,8 @@ int mmgen_world_destroy(MmgenWorld* w)
     cudaFree(w->d_zone);
     cudaFree(w->d_flags);
     cudaFree(w->d_list);
+    cudaFree(w->d_caves);
+    cudaFree(w->d_caveCols);
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     if (w->stream) cudaStreamDestroy(w->stream);
     delete w;
@@ -315,6 +343,28 @@ int mmgen_world_generate(MmgenWorld* w, int stageMask)
             }
         MMG_CUDA(cudaEventRecord(w->ev[5], w->stream));
     }
+    if (stageMask & MMGEN_STAGE_CAVES)
+    {
+        std::vector<int> list;
+        for (int i = 0; i < w->n; ++i)
+            if (w->stage[i] == 3) list.push_back(i);
+        MMG_CUDA(cudaEventRecord(w->ev[6], w->stream));
+        if (!list.empty())
+        {
+            const int m = (int)list.size();
+            if (!w->d_caves) MMG_CUDA(cudaMalloc(&w->d_caves, (size_t)w->n * 256 * MAX_CAVE_LAYERS * sizeof(CaveLayer)));
+            if (!w->d_caveCols) MMG_CUDA(cudaMalloc(&w->d_caveCols, (size_t)w->n * 256 * sizeof(CaveColumn)));
+            if (!w->d_list) MMG_CUDA(cudaMalloc(&w->d_list, (size_t)w->n * sizeof(int)));
+            MMG_CUDA(cudaMemcpyAsync(w->d_list, list.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, w->stream));
+            MMG_LAUNCH(k_cave_columns, m, 256, 0, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
+                       (const float*)w->d_weights, w->d_caveCols);
+            MMG_LAUNCH(k_caves, m * 256, 128, 0, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
+                       (const float*)w->d_height, (const CaveColumn*)w->d_caveCols, w->d_caves);
+            MMG_CUDA(cudaStreamSynchronize(w->stream));
+            for (int i : list) w->stage[i] = 4;
+        }
+        MMG_CUDA(cudaEventRecord(w->ev[7], w->stream));
+    }
     return 0;
 }
 
@@ -340,7 +390,7 @@ int mmgen_world_stage_ms(MmgenWorld* w, float* out7)
 {
     MMG_CUDA(cudaStreamSynchronize(w->stream));
     for (int s = 0; s < 7; ++s) out7[s] = 0.f;
-    for (int st = 1; st <= 3; ++st)
+    for (int st = 1; st <= 4; ++st)
         if (cudaEventQuery(w->ev[2 * st - 1]) == cudaSuccess && cudaEventElapsedTime(&out7[st], w->ev[2 * st - 2], w->ev[2 * st - 1]) != cudaSuccess)
         {
             out7[st] = 0.f;
@@ -365,7 +415,8 @@ int mmgen_world_download(MmgenWorld* w, float* heightfield, float* biomeWeights,
                     MMG_CUDA(cudaMemcpy(layers + (size_t)i * NUM_MATERIALS * 256, w->d_eroded + (size_t)i * NUM_MATERIALS * 256,
                                         NUM_MATERIALS * 256 * sizeof(float), cudaMemcpyDeviceToHost));
     }
-    (void)caveLayers; (void)blocks;
+    if (caveLayers && w->d_caves) MMG_CUDA(cudaMemcpy(caveLayers, w->d_caves, (size_t)w->n * 256 * MAX_CAVE_LAYERS * sizeof(CaveLayer), cudaMemcpyDeviceToHost));
+    (void)blocks;
     return 0;
 }
 

@@ -132,13 +132,17 @@ static inline float simplex2(float vx, float vy) { return 130.0f * simplex2_raw<
 
 // ---------------------------------------------------------------- simplex 3-D
 // returns the dot BEFORE the final *42 (same reason as simplex2_raw)
+// SKEW_Y: which product of the skew dot(v, C.yyy) the reference build left unfused: copies inlined
+// through fbm<> compute fma(v.z, C, fma(v.y, C, v.x*C)) (false); direct simplex(vec3) calls compute
+// fma(v.z, C, fma(v.x, C, v.y*C)) (true). Only floor() sees the difference.
+template <bool SKEW_Y = false>
 static inline float simplex3_raw(float vx, float vy, float vz)
 {
     const float C = 1.0f / 3.0f, D = 1.0f / 6.0f;
     const float NZ = 0.142857142857f;           // n_
     const float NX = NZ * 2.0f;                  // ns.x = n_*D.w - D.x
     const float NY = NZ * 0.5f - 1.0f;           // ns.y = n_*D.y - D.z
-    float s = fmaf(vz, C, fmaf(vy, C, vx * C));
+    float s = SKEW_Y ? fmaf(vz, C, fmaf(vx, C, vy * C)) : fmaf(vz, C, fmaf(vy, C, vx * C));
     float ix = floorf(vx + s), iy = floorf(vy + s), iz = floorf(vz + s);
     float t = fmaf(iz, D, fmaf(ix, D, iy * D));
     float x0x = (vx - ix) + t, x0y = (vy - iy) + t, x0z = (vz - iz) + t;
@@ -192,7 +196,8 @@ static inline float simplex3_raw(float vx, float vy, float vz)
     float b = fmaf(md[3], gxk[3], md[2] * gxk[2]);
     return b + a;
 }
-static inline float simplex3(float vx, float vy, float vz) { return simplex3_raw(vx, vy, vz) * 42.0f; }
+template <bool SKEW_Y = false>
+static inline float simplex3(float vx, float vy, float vz) { return simplex3_raw<SKEW_Y>(vx, vy, vz) * 42.0f; }
 
 // ---------------------------------------------------------------- fbm (rng.hpp:166-191)
 template <int OCT, bool SKEW_X = false>
@@ -208,14 +213,14 @@ static inline float fbm2(float x, float y)
     return f;
 }
 
-template <int OCT>
+template <int OCT, bool SKEW_Y = false>
 static inline float fbm3(float x, float y, float z)
 {
     float f = 0.0f, amp = 1.0f;
     for (int i = 0; i < OCT; ++i)
     {
         amp *= 0.5f;
-        f = fmaf(simplex3(x, y, z), amp, f);
+        f = fmaf(simplex3<SKEW_Y>(x, y, z), amp, f);
         x = x + x; y = y + y; z = z + z;
     }
     return f;

@@ -13,6 +13,7 @@
 
 #include "mm_surface.h"
 #include "mm_layers.h"
+#include "mm_caves.h"
 
 namespace {
 template <class F>
@@ -71,6 +72,19 @@ void mmo_layers(int n, const int32_t* origins, const float* h18, const float* we
 
 // Chunk::erodeZone's device part (chunk.cu:658-709) on planes[9][384*384], in place; returns sweeps
 int mmo_erode_zone(float* planes) { return mmo::erode_zone(planes); }
+
+// Chunk::generateCaves (chunk.cu:939-993); out: CaveLayer[n][256][32]
+void mmo_caves(int n, const int32_t* origins, const float* heightfield, const float* weights, void* out, int nthreads)
+{
+    mmo::CaveLayer* cl = (mmo::CaveLayer*)out;
+    parallel_for(n * 256, nthreads, [&](int i) {
+        const int c = i >> 8, idx = i & 255;
+        const int ox = origins[2 * c], oz = origins[2 * c + 1];
+        mmo::caves_column(ox + (idx & 15), oz + (idx >> 4), heightfield[(size_t)c * 256 + idx],
+                          weights + (size_t)c * (mmo::NUM_BIOMES * 256) + idx, 256, cl + ((size_t)c * 256 + idx) * mmo::MAX_CAVE_LAYERS);
+    });
+}
+int mmo_cave_biome(int x, int y, int z, float maxHeight, int seed) { return mmo::cave_biome(x, y, z, maxHeight, seed); }
 
 // unit probes used by tests
 float mmo_sinf(float x) { return mmo::dm_sinf(x); }

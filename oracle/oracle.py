@@ -51,6 +51,16 @@ class Oracle:
         self.L.mmo_layers(n, _ptr(origins), _ptr(h18), _ptr(weights), _ptr(out), ctypes.c_float(unwritten), self.nthreads)
         return out
 
+    def caves(self, origins, heightfield, weights):
+        origins = np.ascontiguousarray(origins, dtype=np.int32).reshape(-1, 2)
+        n = origins.shape[0]
+        h = np.ascontiguousarray(heightfield, np.float32).reshape(n, 256)
+        w = np.ascontiguousarray(weights, np.float32).reshape(n, 24, 256)
+        from .refcuda import CaveLayer
+        out = np.zeros((n, 256, 32), CaveLayer)
+        self.L.mmo_caves(n, _ptr(origins), _ptr(h), _ptr(w), _ptr(out), self.nthreads)
+        return out
+
     def erode_zone(self, planes):
         """planes: (9, 384, 384) float32 (8 loose layer starts + heightfield); returns (eroded copy, sweeps)."""
         p = np.ascontiguousarray(planes, np.float32).copy()

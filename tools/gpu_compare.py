@@ -67,8 +67,8 @@ def main():
         ol = o.layers(origins[idx], H18, ref["biome_weights"][idx])
         ml = gen.layers(origins[idx], H18, ref["biome_weights"][idx])
         world = gen.world(X0, Z0, NX, NZ)
-        world.generate(mm.STAGE_HEIGHTFIELD | mm.STAGE_LAYERS | (mm.STAGE_EROSION if last >= 3 else 0))
-        wd = world.download(heightfield=True, layers=True)
+        world.generate(mm.STAGE_HEIGHTFIELD | mm.STAGE_LAYERS | (mm.STAGE_EROSION if last >= 3 else 0) | (mm.STAGE_CAVES if last >= 4 else 0))
+        wd = world.download(heightfield=True, layers=True, cave_layers=(last >= 4))
         ws = world.stages().ravel()
         print("world stages:", np.bincount(ws), "ref stages:", np.bincount(st), "erosion sweeps", world.erosion_sweeps(), "stage ms", world.stage_ms())
         # S2 comparison on entries the reference wrote (sentinel = NaN payload) and before erosion rewrote them
@@ -109,6 +109,23 @@ def main():
         report("world vs oracle backward", wd["layers"][s3][:, 10:12], full[s3][:, 10:12])
         d = np.abs(full[s3][:, 12:].astype(np.float64) - refl[:, 12:])
         print("   max abs diff oracle-vs-ref eroded: %.6g ; columns differing: %d of %d" % (d.max(), int((d.max(axis=1) > 0).sum()), d.shape[0] * 256))
+    if last >= 4:
+        print("--- S4 ---")
+        cidx = ref["cave_idx"]
+        rc = ref["cave_layers"]
+        np.save(os.path.join(outdir, "cave_idx.npy"), cidx)
+        np.save(os.path.join(outdir, "cave_layers.npy"), rc)
+        t = time.time()
+        oc = o.caves(origins[cidx], ref["heightfield"][cidx], ref["biome_weights"][cidx])
+        print("oracle caves: %d chunks %.2fs on %d threads" % (len(cidx), time.time() - t, o.nthreads), flush=True)
+        mc = gen.caves(origins[cidx], ref["heightfield"][cidx], ref["biome_weights"][cidx])
+        wc = wd["cave_layers"][cidx]
+        for name, a, b in (("oracle vs ref", oc, rc), ("product vs ref", mc, rc), ("product vs oracle", mc, oc), ("world vs ref", wc, rc)):
+            for f in ("start", "end", "bottomBiome", "topBiome"):
+                d = a[f] != b[f]
+                print("  %-18s %-12s different=%d of %d ; columns affected=%d" % (name, f, int(d.sum()), d.size, int(d.any(axis=2).sum())))
+        nl = (rc["start"] != 384).sum(axis=2)
+        print("  ref layers/column avg %.3f max %d" % (nl.mean(), nl.max()))
     # per dominant biome breakdown of oracle-vs-ref height mismatches
     dom = ref["biome_weights"].argmax(axis=1)
     single = (ref["biome_weights"].max(axis=1) == 1.0)
