@@ -112,6 +112,40 @@ class ChunkGen:
         self._check(self.L.mmgen_caves(n, _ptr(origins), _ptr(h), _ptr(w), _ptr(out)))
         return out
 
+    def feature_placements(self, origins, heightfield, weights, layers, cave_layers, max_per_chunk=4096):
+        """Chunk::generateFeaturePlacements (chunk.cu:1147-1156): per-chunk lists in column order."""
+        origins = np.ascontiguousarray(origins, dtype=np.int32).reshape(-1, 2)
+        n = origins.shape[0]
+        F = np.zeros((n, max_per_chunk), FeaturePlacement)
+        CF = np.zeros((n, max_per_chunk), CaveFeaturePlacement)
+        counts = np.zeros((n, 2), np.int32)
+        self._check(self.L.mmgen_feature_placements(
+            n, _ptr(origins), _ptr(np.ascontiguousarray(heightfield, np.float32)), _ptr(np.ascontiguousarray(weights, np.float32)),
+            _ptr(np.ascontiguousarray(layers, np.float32)), _ptr(np.ascontiguousarray(cave_layers)), max_per_chunk, _ptr(F), _ptr(CF),
+            _ptr(counts)))
+        return [F[i, :min(counts[i, 0], max_per_chunk)].copy() for i in range(n)], \
+               [CF[i, :min(counts[i, 1], max_per_chunk)].copy() for i in range(n)]
+
+    def fill(self, origins, heightfield, weights, layers, cave_layers, gathered, gathered_cave):
+        """Chunk::fill incl. placeDecorators (chunk.cu:1518-1747); gathered lists per chunk, untruncated."""
+        origins = np.ascontiguousarray(origins, dtype=np.int32).reshape(-1, 2)
+        n = origins.shape[0]
+        sf = max(1, max(len(g) for g in gathered))
+        scf = max(1, max(len(g) for g in gathered_cave))
+        F = np.zeros((n, sf), FeaturePlacement)
+        CF = np.zeros((n, scf), CaveFeaturePlacement)
+        counts = np.zeros((n, 2), np.int32)
+        for i in range(n):
+            F[i, :len(gathered[i])] = gathered[i]
+            CF[i, :len(gathered_cave[i])] = gathered_cave[i]
+            counts[i] = (len(gathered[i]), len(gathered_cave[i]))
+        out = np.zeros((n, 16, 16, 384), np.uint8)
+        self._check(self.L.mmgen_fill(
+            n, _ptr(origins), _ptr(np.ascontiguousarray(heightfield, np.float32)), _ptr(np.ascontiguousarray(weights, np.float32)),
+            _ptr(np.ascontiguousarray(layers, np.float32)), _ptr(np.ascontiguousarray(cave_layers)), _ptr(F), _ptr(CF), _ptr(counts),
+            sf, scf, _ptr(out)))
+        return out
+
     def erode_zone(self, gathered):
         """Chunk::erodeZone's relaxation (chunk.cu:658-709): (9,384,384) -> ((8,384,384), sweeps)."""
         g = np.ascontiguousarray(gathered, np.float32).reshape(9, 384, 384)
@@ -164,6 +198,14 @@ class World:
         v = ctypes.c_int(0)
         self.gen._check(self.L.mmgen_world_erosion_sweeps(self.h, ctypes.byref(v)))
         return v.value
+
+    def download_features(self, max_per_chunk=4096):
+        F = np.zeros((self.n, max_per_chunk), FeaturePlacement)
+        CF = np.zeros((self.n, max_per_chunk), CaveFeaturePlacement)
+        counts = np.zeros((self.n, 2), np.int32)
+        self.gen._check(self.L.mmgen_world_download_features(self.h, max_per_chunk, _ptr(F), _ptr(CF), _ptr(counts)))
+        return [F[i, :min(counts[i, 0], max_per_chunk)].copy() for i in range(self.n)], \
+               [CF[i, :min(counts[i, 1], max_per_chunk)].copy() for i in range(self.n)]
 
     def download(self, heightfield=False, biome_weights=False, layers=False, cave_layers=False, blocks=False):
         res = {}

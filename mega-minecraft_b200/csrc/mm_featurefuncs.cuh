@@ -1,0 +1,46 @@
+// Stage 5 device functions: grid test with host-libm semantics, random biome pick, gather order.
+// Behaviour: /root/reference/src/terrain/chunk.cu:999-1008, 1158-1167; biomeFuncs.hpp:39-53.
+#pragma once
+#include "mm_hostmath.cuh"
+#include "mm_arith.cuh"
+#include "mm_tables.cuh"
+
+namespace mmg {
+
+constexpr bool kCaveGridTestIgnored = true;
+
+// chunk.cu:999-1008 (host arithmetic)
+__device__ __forceinline__ bool is_feature_pos(int wx, int wz, int cell, int pad, int seed)
+{
+    const float fc = (float)cell;
+    const int gx = (int)(floorf((float)wx / fc) * fc), gz = (int)(floorf((float)wz / fc) * fc);
+    const int internal = cell - 2 * pad;
+    const float vx = (float)gx, vy = (float)gz, vz = (float)seed;
+    const float d1 = (vx * 238.68f + vy * 491.28f) + vz * 640.88f;
+    const float d2 = (vx * 654.37f + vy * 560.45f) + vz * 151.81f;
+    float r1 = hm_sinf(d1) * 39021.426f, r2 = hm_sinf(d2) * 39021.426f;
+    r1 = r1 - floorf(r1);
+    r2 = r2 - floorf(r2);
+    const int px = gx + pad + (int)floorf(r1 * (float)internal), pz = gz + pad + (int)floorf(r2 * (float)internal);
+    return wx == px && wz == pz;
+}
+
+// biomeFuncs.hpp:39-53
+__device__ __forceinline__ int random_biome(const float* w, int stride, float rand)
+{
+    for (int i = 0; i < NUM_BIOMES; ++i)
+    {
+        rand -= w[stride * i];
+        if (rand <= 0.f) return i;
+    }
+    return PLAINS;
+}
+
+// chunk.cu:1158-1167
+__constant__ const int c_gatherOffsets[49][2] = {
+    {0, 0}, {0, 1}, {1, 1}, {1, 0}, {1, -1}, {0, -1}, {-1, -1}, {-1, 0}, {-1, 1}, {2, 0}, {2, 1}, {2, 2}, {1, 2}, {0, 2},
+    {-1, 2}, {-2, 2}, {-2, 1}, {-2, 0}, {-2, -1}, {-2, -2}, {-1, -2}, {0, -2}, {1, -2}, {2, -2}, {2, -1},
+    {-3, -3}, {-2, -3}, {-1, -3}, {0, -3}, {1, -3}, {2, -3}, {3, -3}, {3, -2}, {3, -1}, {3, 0}, {3, 1}, {3, 2}, {3, 3},
+    {2, 3}, {1, 3}, {0, 3}, {-1, 3}, {-2, 3}, {-3, 3}, {-3, 2}, {-3, 1}, {-3, 0}, {-3, -1}, {-3, -2}};
+
+}  // namespace mmg

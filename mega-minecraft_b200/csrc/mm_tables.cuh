@@ -138,4 +138,128 @@ __constant__ const float c_biomeMaterialWeights[NUM_BIOMES][NUM_MATERIALS] = {
 // dirVecs2d, util/enums.hpp:32-41 (N, NE, E, SE, S, SW, W, NW)
 __constant__ const int c_dirVecs2d[8][2] = {{0, 1}, {1, 1}, {1, 0}, {1, -1}, {0, -1}, {-1, -1}, {-1, 0}, {-1, 1}};
 
+// feature height bounds, biomeFuncs.hpp:1042-1074 and 1210-1223
+__constant__ const int c_featureHeightBounds[NUM_FEATURES][2] = {
+    {0, 0}, {-6, 6}, {-3, 12}, {0, 20}, {0, 110}, {0, 15}, {-5, 75}, {-3, 50}, {0, 30}, {0, 15}, {0, 8}, {0, 10},
+    {0, 38}, {0, 17}, {0, 5}, {0, 6}, {0, 120}, {-3, 32}, {-6, 64}, {0, 28}, {0, 15}};
+__constant__ const int c_caveFeatureHeightBounds[NUM_CAVE_FEATURES][2] = {
+    {0, 0}, {-3, 3}, {-3, 3}, {0, 0}, {0, 6}, {-12, 12}, {-12, 12}, {-8, 8}, {-2, 3}, {-2, 5}};
+
+// feature / cave-feature / decorator generators (biomeFuncs.hpp:975-1040, 1081-1178, 1189-1252), flattened:
+// c_*Range[biome] = {first, count} into the generator array.
+struct FeatureGen { uint8_t feature; int cell, pad; float chance; int numTop; uint8_t topMat[2]; float topMin[2]; uint8_t canReplace; };
+__constant__ const FeatureGen c_featureGens[] = {
+    {2, 5, 0, 0.65f, 2, {18, 17}, {0.3f, 0.3f}, 1},
+    {3, 8, 0, 0.5f, 2, {18, 17}, {0.3f, 0.3f}, 1},
+    {4, 112, 6, 0.7f, 0, {0, 0}, {0.f, 0.f}, 1},
+    {19, 48, 3, 0.35f, 1, {18, 0}, {0.3f, 0.f}, 1},
+    {5, 36, 4, 0.3f, 1, {15, 0}, {0.5f, 0.f}, 1},
+    {6, 16, 2, 0.7f, 1, {15, 0}, {0.5f, 0.f}, 1},
+    {7, 18, 3, 0.6f, 2, {15, 14}, {0.5f, 0.5f}, 1},
+    {8, 16, 2, 0.15f, 1, {15, 0}, {0.4f, 0.f}, 1},
+    {8, 9, 2, 0.7f, 1, {15, 0}, {0.5f, 0.f}, 1},
+    {9, 7, 1, 0.8f, 0, {0, 0}, {0.f, 0.f}, 0},
+    {10, 6, 1, 0.8f, 0, {0, 0}, {0.f, 0.f}, 0},
+    {11, 54, 6, 0.5f, 1, {15, 0}, {0.5f, 0.f}, 1},
+    {12, 28, 3, 0.7f, 1, {15, 0}, {0.5f, 0.f}, 1},
+    {13, 10, 2, 0.82f, 1, {15, 0}, {0.5f, 0.f}, 1},
+    {14, 6, 1, 0.28f, 1, {15, 0}, {0.5f, 0.f}, 1},
+    {19, 40, 3, 0.2f, 1, {16, 0}, {0.3f, 0.f}, 1},
+    {20, 16, 2, 0.2f, 1, {16, 0}, {0.5f, 0.f}, 1},
+    {15, 10, 2, 0.5f, 1, {15, 0}, {0.3f, 0.f}, 1},
+    {16, 11, 3, 0.45f, 1, {15, 0}, {0.5f, 0.f}, 1},
+    {17, 28, 6, 0.9f, 0, {0, 0}, {0.f, 0.f}, 1},
+    {18, 52, 10, 0.8f, 0, {0, 0}, {0.f, 0.f}, 1},
+    {19, 24, 3, 0.35f, 1, {17, 0}, {0.3f, 0.f}, 1},
+    {20, 16, 2, 0.4f, 1, {17, 0}, {0.5f, 0.f}, 1},
+    {19, 64, 3, 0.3f, 1, {17, 0}, {0.3f, 0.f}, 1},
+    {20, 16, 2, 0.7f, 1, {17, 0}, {0.5f, 0.f}, 1},
+};
+__constant__ const int c_featureGenRange[NUM_BIOMES][2] = {{0, 2}, {2, 0}, {2, 0}, {2, 1}, {3, 0}, {3, 0}, {3, 1}, {4, 0}, {4, 1}, {5, 0}, {5, 0}, {5, 1}, {6, 2}, {8, 0}, {8, 1}, {9, 2}, {11, 4}, {15, 2}, {17, 2}, {19, 2}, {21, 2}, {23, 2}, {25, 0}, {25, 0}};
+struct CaveFeatureGen { uint8_t feature; int cell, pad; float chance; int minLayerHeight; uint8_t canReplace, fromCeiling, inLava; };
+__constant__ const CaveFeatureGen c_caveFeatureGens[] = {
+    {5, 32, 4, 0.8f, 4, 1, 0, 0},
+    {6, 32, 4, 0.8f, 4, 1, 1, 0},
+    {7, 28, 5, 0.6f, 10, 0, 1, 0},
+    {4, 24, 3, 0.6f, 16, 0, 1, 0},
+    {3, 4, 0, 0.4f, 4, 0, 1, 0},
+    {4, 16, 3, 0.8f, 16, 0, 1, 0},
+    {8, 7, 1, 0.75f, 6, 0, 0, 0},
+    {4, 18, 3, 0.75f, 16, 0, 1, 0},
+    {9, 5, 1, 0.6f, 9, 0, 0, 0},
+};
+__constant__ const int c_caveFeatureGenRange[NUM_CAVE_BIOMES][2] = {{0, 0}, {0, 3}, {3, 2}, {5, 2}, {7, 2}};
+struct DecoratorGen { uint8_t block; float chance; int numUnder; uint8_t under[3]; uint8_t replace, second, fromCeiling; };
+__constant__ const DecoratorGen c_decoratorGens[] = {
+    {51, 0.2f, 2, {60, 95, 0}, 1, 0, 0},
+    {52, 0.04f, 2, {60, 95, 0}, 1, 53, 0},
+    {46, 0.03f, 2, {60, 95, 0}, 1, 1, 0},
+    {47, 0.03f, 2, {60, 95, 0}, 1, 1, 0},
+    {48, 0.03f, 2, {60, 95, 0}, 1, 1, 0},
+    {49, 0.03f, 2, {60, 95, 0}, 1, 1, 0},
+    {50, 0.03f, 2, {60, 95, 0}, 1, 1, 0},
+    {7, 0.2f, 1, {59, 0, 0}, 0, 0, 0},
+    {31, 0.025f, 1, {59, 0, 0}, 0, 0, 0},
+    {8, 0.1f, 1, {81, 0, 0}, 0, 0, 0},
+    {9, 0.1f, 1, {106, 0, 0}, 0, 0, 0},
+    {7, 0.2f, 1, {59, 0, 0}, 0, 0, 0},
+    {41, 0.08f, 1, {59, 0, 0}, 0, 42, 0},
+    {30, 0.04f, 1, {59, 0, 0}, 0, 0, 0},
+    {31, 0.04f, 1, {59, 0, 0}, 0, 0, 0},
+    {28, 0.02f, 1, {59, 0, 0}, 0, 29, 0},
+    {8, 0.3f, 1, {81, 0, 0}, 0, 0, 0},
+    {32, 0.05f, 1, {81, 0, 0}, 0, 0, 0},
+    {19, 0.03f, 1, {81, 0, 0}, 0, 0, 0},
+    {20, 0.03f, 1, {81, 0, 0}, 0, 0, 0},
+    {21, 0.03f, 1, {81, 0, 0}, 0, 0, 0},
+    {7, 0.3f, 1, {59, 0, 0}, 0, 0, 0},
+    {28, 0.02f, 1, {59, 0, 0}, 0, 29, 0},
+    {26, 0.02f, 1, {59, 0, 0}, 0, 27, 0},
+    {15, 0.04f, 1, {59, 0, 0}, 0, 0, 0},
+    {8, 0.4f, 1, {81, 0, 0}, 0, 0, 0},
+    {43, 0.2f, 1, {81, 0, 0}, 0, 44, 0},
+    {17, 0.03f, 1, {81, 0, 0}, 0, 18, 0},
+    {32, 0.12f, 1, {81, 0, 0}, 0, 0, 0},
+    {20, 0.04f, 1, {81, 0, 0}, 0, 0, 0},
+    {37, 0.02f, 1, {78, 0, 0}, 0, 0, 0},
+    {36, 0.1f, 1, {62, 0, 0}, 0, 0, 0},
+    {33, 0.005f, 3, {57, 72, 70}, 0, 0, 0},
+    {34, 0.005f, 3, {57, 72, 70}, 0, 0, 0},
+    {35, 0.005f, 3, {57, 72, 70}, 0, 0, 0},
+    {36, 0.02f, 1, {62, 0, 0}, 0, 0, 0},
+    {33, 0.025f, 3, {57, 72, 70}, 0, 0, 0},
+    {34, 0.025f, 3, {57, 72, 70}, 0, 0, 0},
+    {35, 0.025f, 3, {57, 72, 70}, 0, 0, 0},
+    {8, 0.2f, 1, {81, 0, 0}, 0, 0, 0},
+    {19, 0.02f, 1, {81, 0, 0}, 0, 0, 0},
+    {37, 0.03f, 1, {78, 0, 0}, 0, 0, 0},
+    {7, 0.2f, 1, {59, 0, 0}, 0, 0, 0},
+    {22, 0.01f, 1, {59, 0, 0}, 0, 0, 0},
+    {23, 0.01f, 1, {59, 0, 0}, 0, 0, 0},
+    {24, 0.01f, 1, {59, 0, 0}, 0, 0, 0},
+    {25, 0.01f, 1, {59, 0, 0}, 0, 0, 0},
+    {15, 0.03f, 1, {59, 0, 0}, 0, 0, 0},
+    {16, 0.03f, 1, {59, 0, 0}, 0, 0, 0},
+    {7, 0.05f, 1, {59, 0, 0}, 0, 0, 0},
+    {31, 0.015f, 1, {59, 0, 0}, 0, 0, 0},
+};
+__constant__ const int c_decoratorGenRange[NUM_BIOMES][2] = {{0, 7}, {7, 2}, {9, 0}, {9, 0}, {9, 0}, {9, 0}, {9, 1}, {10, 0}, {10, 1}, {11, 0}, {11, 0}, {11, 5}, {16, 5}, {21, 0}, {21, 4}, {25, 0}, {25, 5}, {30, 1}, {31, 4}, {35, 4}, {39, 2}, {41, 1}, {42, 7}, {49, 2}};
+__constant__ const DecoratorGen c_caveDecoratorGens[] = {
+    {33, 0.015f, 0, {0, 0, 0}, 0, 0, 0},
+    {34, 0.015f, 0, {0, 0, 0}, 0, 0, 0},
+    {35, 0.015f, 0, {0, 0, 0}, 0, 0, 0},
+    {38, 0.015f, 0, {0, 0, 0}, 0, 0, 1},
+    {39, 0.015f, 0, {0, 0, 0}, 0, 0, 1},
+    {40, 0.015f, 0, {0, 0, 0}, 0, 0, 1},
+    {7, 0.1f, 1, {125, 0, 0}, 0, 0, 0},
+    {41, 0.03f, 1, {125, 0, 0}, 0, 42, 0},
+    {45, 0.02f, 1, {125, 0, 0}, 0, 0, 0},
+    {10, 0.02f, 2, {123, 124, 0}, 0, 0, 0},
+    {11, 0.06f, 2, {123, 124, 0}, 0, 0, 0},
+    {12, 0.04f, 2, {123, 124, 0}, 0, 0, 0},
+    {13, 0.02f, 2, {126, 127, 0}, 0, 0, 0},
+    {14, 0.06f, 2, {126, 127, 0}, 0, 0, 0},
+};
+__constant__ const int c_caveDecoratorGenRange[NUM_CAVE_BIOMES][2] = {{0, 0}, {0, 6}, {6, 3}, {9, 3}, {12, 2}};
+
 }  // namespace mmg

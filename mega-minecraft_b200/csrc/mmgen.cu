@@ -12,6 +12,7 @@
 #include "mm_stage1.cuh"
 #include "mm_stage23.cuh"
 #include "mm_stage4.cuh"
+#include "mm_stage56.cuh"
 
 namespace mmg {
 
@@ -67,6 +68,13 @@ struct MmgenWorld
     int* d_list = nullptr;            // chunk index lists
     CaveLayer* d_caves = nullptr;     // [chunk][256][32]
     CaveColumn* d_caveCols = nullptr; // per-column hoisted cave terms
+    FeaturePlacement* d_features = nullptr;          // own lists [chunk][kMaxOwnFeatures]
+    CaveFeaturePlacement* d_caveFeatures = nullptr;  // own lists [chunk][kMaxOwnCaveFeatures]
+    int* d_counts = nullptr;                         // [chunk][2]
+    FeaturePlacement* d_gF = nullptr;                // gathered lists of one fill batch
+    CaveFeaturePlacement* d_gCF = nullptr;
+    GatherInfo* d_info = nullptr;
+    uint8_t* d_blocks = nullptr;                     // [chunk][16][16][384]
     int erosionSweeps = 0;
     std::vector<uint8_t> stage;
     cudaStream_t stream = nullptr;
@@ -238,6 +246,83 @@ extern "C" int mmgen_caves(int n, const int32_t* origins, const float* heightfie
     return 0;
 }
 
+constexpr int kFillBatch = 512;   // chunks gathered + filled per launch group (bounds the gathered-list buffers)
+
+extern "C" int mmgen_feature_placements(int n, const int32_t* origins, const float* heightfield, const float* biomeWeights,
+                                        const float* layers, const MmgenCaveLayer* caveLayers, int maxPerChunk,
+                                        MmgenFeaturePlacement* out_features, MmgenCaveFeaturePlacement* out_caveFeatures,
+                                        int32_t* out_counts)
+{
+    if (requireReady()) return 1;
+    if (n <= 0) return 0;
+    const size_t clBytes = (size_t)n * 256 * MAX_CAVE_LAYERS * sizeof(CaveLayer);
+    Scratch* S = g_scratch;
+    if (S[0].ensure((size_t)n * sizeof(int2)) || S[1].ensure((size_t)n * 256 * 4) || S[2].ensure((size_t)n * NUM_BIOMES * 256 * 4) ||
+        S[3].ensure(clBytes) || S[4].ensure((size_t)n * NUM_MATERIALS * 256 * 4) ||
+        S[5].ensure((size_t)n * kMaxOwnFeatures * sizeof(FeaturePlacement)) ||
+        S[6].ensure((size_t)n * kMaxOwnCaveFeatures * sizeof(CaveFeaturePlacement)) || S[7].ensure((size_t)n * 2 * sizeof(int)))
+        return 1;
+    MMG_CUDA(cudaMemcpyAsync(S[0].ptr, origins, (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, g_stream));
+    MMG_CUDA(cudaMemcpyAsync(S[1].ptr, heightfield, (size_t)n * 256 * 4, cudaMemcpyHostToDevice, g_stream));
+    MMG_CUDA(cudaMemcpyAsync(S[2].ptr, biomeWeights, (size_t)n * NUM_BIOMES * 256 * 4, cudaMemcpyHostToDevice, g_stream));
+    MMG_CUDA(cudaMemcpyAsync(S[3].ptr, caveLayers, clBytes, cudaMemcpyHostToDevice, g_stream));
+    MMG_CUDA(cudaMemcpyAsync(S[4].ptr, layers, (size_t)n * NUM_MATERIALS * 256 * 4, cudaMemcpyHostToDevice, g_stream));
+    MMG_LAUNCH(k_feature_placements, n, 256, 0, g_stream, (const int*)nullptr, (const int2*)S[0].ptr, (const float*)S[1].ptr,
+               (const float*)S[2].ptr, (const float*)S[4].ptr, (const CaveLayer*)S[3].ptr, (FeaturePlacement*)S[5].ptr,
+               (CaveFeaturePlacement*)S[6].ptr, (int*)S[7].ptr);
+    std::vector<int> counts((size_t)n * 2);
+    MMG_CUDA(cudaMemcpyAsync(counts.data(), S[7].ptr, counts.size() * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    MMG_CUDA(cudaStreamSynchronize(g_stream));
+    for (int c = 0; c < n; ++c)
+    {
+        out_counts[2 * c] = counts[2 * c];
+        out_counts[2 * c + 1] = counts[2 * c + 1];
+        const int nf = std::min(counts[2 * c], maxPerChunk), nc = std::min(counts[2 * c + 1], maxPerChunk);
+        if (nf) MMG_CUDA(cudaMemcpyAsync(out_features + (size_t)c * maxPerChunk, (FeaturePlacement*)S[5].ptr + (size_t)c * kMaxOwnFeatures,
+                                         (size_t)nf * sizeof(FeaturePlacement), cudaMemcpyDeviceToHost, g_stream));
+        if (nc) MMG_CUDA(cudaMemcpyAsync(out_caveFeatures + (size_t)c * maxPerChunk, (CaveFeaturePlacement*)S[6].ptr + (size_t)c * kMaxOwnCaveFeatures,
+                                         (size_t)nc * sizeof(CaveFeaturePlacement), cudaMemcpyDeviceToHost, g_stream));
+    }
+    MMG_CUDA(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+extern "C" int mmgen_fill(int n, const int32_t* origins, const float* heightfield, const float* biomeWeights, const float* layers,
+                          const MmgenCaveLayer* caveLayers, const MmgenFeaturePlacement* features,
+                          const MmgenCaveFeaturePlacement* caveFeatures, const int32_t* numFeatures, int featureStride,
+                          int caveFeatureStride, uint8_t* out_blocks)
+{
+    if (requireReady()) return 1;
+    if (n <= 0) return 0;
+    static Scratch X[4];
+    const size_t clBytes = (size_t)n * 256 * MAX_CAVE_LAYERS * sizeof(CaveLayer);
+    Scratch* S = g_scratch;
+    if (S[0].ensure((size_t)n * sizeof(int2)) || S[1].ensure((size_t)n * 256 * 4) || S[2].ensure((size_t)n * NUM_BIOMES * 256 * 4) ||
+        S[3].ensure(clBytes) || S[4].ensure((size_t)n * NUM_MATERIALS * 256 * 4) ||
+        S[5].ensure((size_t)n * featureStride * sizeof(FeaturePlacement) + 16) ||
+        S[6].ensure((size_t)n * caveFeatureStride * sizeof(CaveFeaturePlacement) + 16) || S[7].ensure((size_t)n * 2 * sizeof(int)) ||
+        X[0].ensure((size_t)n * sizeof(GatherInfo)) || X[1].ensure((size_t)n * 98304))
+        return 1;
+    MMG_CUDA(cudaMemcpyAsync(S[0].ptr, origins, (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, g_stream));
+    MMG_CUDA(cudaMemcpyAsync(S[1].ptr, heightfield, (size_t)n * 256 * 4, cudaMemcpyHostToDevice, g_stream));
+    MMG_CUDA(cudaMemcpyAsync(S[2].ptr, biomeWeights, (size_t)n * NUM_BIOMES * 256 * 4, cudaMemcpyHostToDevice, g_stream));
+    MMG_CUDA(cudaMemcpyAsync(S[3].ptr, caveLayers, clBytes, cudaMemcpyHostToDevice, g_stream));
+    MMG_CUDA(cudaMemcpyAsync(S[4].ptr, layers, (size_t)n * NUM_MATERIALS * 256 * 4, cudaMemcpyHostToDevice, g_stream));
+    if (featureStride) MMG_CUDA(cudaMemcpyAsync(S[5].ptr, features, (size_t)n * featureStride * sizeof(FeaturePlacement), cudaMemcpyHostToDevice, g_stream));
+    if (caveFeatureStride) MMG_CUDA(cudaMemcpyAsync(S[6].ptr, caveFeatures, (size_t)n * caveFeatureStride * sizeof(CaveFeaturePlacement), cudaMemcpyHostToDevice, g_stream));
+    MMG_CUDA(cudaMemcpyAsync(S[7].ptr, numFeatures, (size_t)n * 2 * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    MMG_LAUNCH(k_gather_info, n, 256, 0, g_stream, (const FeaturePlacement*)S[5].ptr, (const CaveFeaturePlacement*)S[6].ptr,
+               (const int*)S[7].ptr, featureStride, caveFeatureStride, (GatherInfo*)X[0].ptr);
+    MMG_LAUNCH(k_fill, n * 256, 384, 0, g_stream, (const int*)nullptr, (const int2*)S[0].ptr, (const float*)S[1].ptr,
+               (const float*)S[2].ptr, (const float*)S[4].ptr, (const CaveLayer*)S[3].ptr, (const FeaturePlacement*)S[5].ptr,
+               (const CaveFeaturePlacement*)S[6].ptr, (const GatherInfo*)X[0].ptr, featureStride, caveFeatureStride, (uint8_t*)X[1].ptr);
+    MMG_LAUNCH(k_decorators, (n + 31) / 32, 32, 0, g_stream, (const int*)nullptr, n, (const int2*)S[0].ptr, (const float*)S[1].ptr,
+               (const float*)S[2].ptr, (const CaveLayer*)S[3].ptr, (uint8_t*)X[1].ptr);
+    MMG_CUDA(cudaMemcpyAsync(out_blocks, X[1].ptr, (size_t)n * 98304, cudaMemcpyDeviceToHost, g_stream));
+    MMG_CUDA(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
 // ------------------------------------------------------------------ world
 int mmgen_world_create(int cx0, int cz0, int nx, int nz, MmgenWorld** out)
 {
@@ -274,6 +359,13 @@ int mmgen_world_destroy(MmgenWorld* w)
     cudaFree(w->d_list);
     cudaFree(w->d_caves);
     cudaFree(w->d_caveCols);
+    cudaFree(w->d_features);
+    cudaFree(w->d_caveFeatures);
+    cudaFree(w->d_counts);
+    cudaFree(w->d_gF);
+    cudaFree(w->d_gCF);
+    cudaFree(w->d_info);
+    cudaFree(w->d_blocks);
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     if (w->stream) cudaStreamDestroy(w->stream);
     delete w;
@@ -365,6 +457,85 @@ int mmgen_world_generate(MmgenWorld* w, int stageMask)
         }
         MMG_CUDA(cudaEventRecord(w->ev[7], w->stream));
     }
+    if (stageMask & MMGEN_STAGE_FEATURES)
+    {
+        std::vector<int> list;
+        for (int i = 0; i < w->n; ++i)
+            if (w->stage[i] == 4) list.push_back(i);
+        MMG_CUDA(cudaEventRecord(w->ev[8], w->stream));
+        if (!list.empty())
+        {
+            const int m = (int)list.size();
+            if (!w->d_features) MMG_CUDA(cudaMalloc(&w->d_features, (size_t)w->n * kMaxOwnFeatures * sizeof(FeaturePlacement)));
+            if (!w->d_caveFeatures) MMG_CUDA(cudaMalloc(&w->d_caveFeatures, (size_t)w->n * kMaxOwnCaveFeatures * sizeof(CaveFeaturePlacement)));
+            if (!w->d_counts)
+            {
+                MMG_CUDA(cudaMalloc(&w->d_counts, (size_t)w->n * 2 * sizeof(int)));
+                MMG_CUDA(cudaMemsetAsync(w->d_counts, 0, (size_t)w->n * 2 * sizeof(int), w->stream));
+            }
+            MMG_CUDA(cudaMemcpyAsync(w->d_list, list.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, w->stream));
+            MMG_LAUNCH(k_feature_placements, m, 256, 0, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
+                       (const float*)w->d_height, (const float*)w->d_weights, (const float*)w->d_eroded, (const CaveLayer*)w->d_caves,
+                       w->d_features, w->d_caveFeatures, w->d_counts);
+            MMG_CUDA(cudaStreamSynchronize(w->stream));
+            for (int i : list) w->stage[i] = 5;
+        }
+        MMG_CUDA(cudaEventRecord(w->ev[9], w->stream));
+    }
+    if (stageMask & MMGEN_STAGE_FILL)
+    {
+        // chunks whose 7x7 neighbourhood has placements (gatherFeaturePlacements' condition)
+        std::vector<int> list;
+        for (int z = 3; z < nz - 3; ++z)
+            for (int x = 3; x < nx - 3; ++x)
+            {
+                if (w->stage[z * nx + x] != 5) continue;
+                bool ok = true;
+                for (int dz = -3; dz <= 3 && ok; ++dz)
+                    for (int dx = -3; dx <= 3 && ok; ++dx) ok = w->stage[(z + dz) * nx + x + dx] >= 5;
+                if (ok) list.push_back(z * nx + x);
+            }
+        MMG_CUDA(cudaEventRecord(w->ev[10], w->stream));
+        if (!list.empty())
+        {
+            if (!w->d_blocks) MMG_CUDA(cudaMalloc(&w->d_blocks, (size_t)w->n * 98304));
+            if (!w->d_gF) MMG_CUDA(cudaMalloc(&w->d_gF, (size_t)kFillBatch * MAX_FEATURES * sizeof(FeaturePlacement)));
+            if (!w->d_gCF) MMG_CUDA(cudaMalloc(&w->d_gCF, (size_t)kFillBatch * MAX_CAVE_FEATURES * sizeof(CaveFeaturePlacement)));
+            if (!w->d_info) MMG_CUDA(cudaMalloc(&w->d_info, (size_t)kFillBatch * sizeof(GatherInfo)));
+            MMG_CUDA(cudaMemcpyAsync(w->d_list, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, w->stream));
+            for (size_t b0 = 0; b0 < list.size(); b0 += kFillBatch)
+            {
+                const int m = (int)std::min<size_t>(kFillBatch, list.size() - b0);
+                const int* dl = w->d_list + b0;
+                MMG_LAUNCH(k_gather_features, m, 256, 0, w->stream, dl, (const FeaturePlacement*)w->d_features,
+                           (const CaveFeaturePlacement*)w->d_caveFeatures, (const int*)w->d_counts, nx, w->d_gF, w->d_gCF, w->d_info);
+                MMG_LAUNCH(k_fill, m * 256, 384, 0, w->stream, dl, (const int2*)w->d_origins, (const float*)w->d_height,
+                           (const float*)w->d_weights, (const float*)w->d_eroded, (const CaveLayer*)w->d_caves,
+                           (const FeaturePlacement*)w->d_gF, (const CaveFeaturePlacement*)w->d_gCF, (const GatherInfo*)w->d_info,
+                           MAX_FEATURES, MAX_CAVE_FEATURES, w->d_blocks);
+                MMG_LAUNCH(k_decorators, (m + 31) / 32, 32, 0, w->stream, dl, m, (const int2*)w->d_origins, (const float*)w->d_height,
+                           (const float*)w->d_weights, (const CaveLayer*)w->d_caves, w->d_blocks);
+            }
+            MMG_CUDA(cudaStreamSynchronize(w->stream));
+            for (int i : list) w->stage[i] = 6;
+        }
+        MMG_CUDA(cudaEventRecord(w->ev[11], w->stream));
+    }
+    return 0;
+}
+
+int mmgen_world_download_features(MmgenWorld* w, int maxPerChunk, MmgenFeaturePlacement* features,
+                                  MmgenCaveFeaturePlacement* caveFeatures, int32_t* counts)
+{
+    MMG_CUDA(cudaStreamSynchronize(w->stream));
+    if (!w->d_counts) { std::memset(counts, 0, (size_t)w->n * 2 * sizeof(int)); return 0; }
+    MMG_CUDA(cudaMemcpy(counts, w->d_counts, (size_t)w->n * 2 * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < w->n; ++c)
+    {
+        const int nf = std::min(counts[2 * c], maxPerChunk), nc = std::min(counts[2 * c + 1], maxPerChunk);
+        if (nf) MMG_CUDA(cudaMemcpy(features + (size_t)c * maxPerChunk, w->d_features + (size_t)c * kMaxOwnFeatures, (size_t)nf * sizeof(FeaturePlacement), cudaMemcpyDeviceToHost));
+        if (nc) MMG_CUDA(cudaMemcpy(caveFeatures + (size_t)c * maxPerChunk, w->d_caveFeatures + (size_t)c * kMaxOwnCaveFeatures, (size_t)nc * sizeof(CaveFeaturePlacement), cudaMemcpyDeviceToHost));
+    }
     return 0;
 }
 
@@ -390,7 +561,7 @@ int mmgen_world_stage_ms(MmgenWorld* w, float* out7)
 {
     MMG_CUDA(cudaStreamSynchronize(w->stream));
     for (int s = 0; s < 7; ++s) out7[s] = 0.f;
-    for (int st = 1; st <= 4; ++st)
+    for (int st = 1; st <= 6; ++st)
         if (cudaEventQuery(w->ev[2 * st - 1]) == cudaSuccess && cudaEventElapsedTime(&out7[st], w->ev[2 * st - 2], w->ev[2 * st - 1]) != cudaSuccess)
         {
             out7[st] = 0.f;
@@ -416,7 +587,7 @@ int mmgen_world_download(MmgenWorld* w, float* heightfield, float* biomeWeights,
                                         NUM_MATERIALS * 256 * sizeof(float), cudaMemcpyDeviceToHost));
     }
     if (caveLayers && w->d_caves) MMG_CUDA(cudaMemcpy(caveLayers, w->d_caves, (size_t)w->n * 256 * MAX_CAVE_LAYERS * sizeof(CaveLayer), cudaMemcpyDeviceToHost));
-    (void)blocks;
+    if (blocks && w->d_blocks) MMG_CUDA(cudaMemcpy(blocks, w->d_blocks, (size_t)w->n * 98304, cudaMemcpyDeviceToHost));
     return 0;
 }
 

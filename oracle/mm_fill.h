@@ -1,0 +1,360 @@
+// TEST INFRASTRUCTURE (CPU oracle) - never linked into the product.
+//
+// Stage 6 of the reference, restated: per-voxel block selection
+//   chunkFillPlaceBlock                       /root/reference/src/terrain/chunk.cu:1202-1380
+//   biomeBlockPreProcess / PostProcess        /root/reference/src/terrain/biomeFuncs.hpp:385-590
+//   caveBiomeBlockPostProcess                 biomeFuncs.hpp:592-707
+//   kernFill feature scan + host y-bounds     chunk.cu:1382-1510, 1555-1570
+//   placeDecorators / tryPlaceSingleDecorator chunk.cu:1634-1747
+// Feature rasterisers are in mm_placefeature.h. Rounding follows the reference's sm_100 PTX where it
+// was read (oracle/tools/ptx_expr.py); elsewhere the rule the reference build shows everywhere
+// (a product whose only consumer is an add/sub is fused into it) is applied.
+#pragma once
+#include "mm_caves.h"
+#include "mm_placefeature.h"
+
+namespace mmo {
+
+// ------------------------------------------------------------------ 3-D Worley (rng.hpp:235-278)
+// hash at the LUSH_CAVES call site (biomeFuncs.hpp:661): fma(z, Kz, fma(y, Ky, x*Kx))
+static inline float worley3_lush(float px, float py, float pz)
+{
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    const float nfx = fx - px, nfy = fy - py, nfz = fz - pz;
+    float d1 = FLT_MAX, d2 = FLT_MAX;
+    for (int x = -1; x <= 1; ++x)
+        for (int y = -1; y <= 1; ++y)
+            for (int z = -1; z <= 1; ++z)
+            {
+                const float cx = (float)(ix + x), cy = (float)(iy + y), cz = (float)(iz + z);
+                const float jx = hash_fract(fmaf(cz, 402.98f, fmaf(cy, 491.28f, cx * 238.68f)));
+                const float jy = hash_fract(fmaf(cz, 747.42f, fmaf(cy, 560.45f, cx * 654.37f)));
+                const float jz = hash_fract(fmaf(cz, 674.81f, fmaf(cy, 151.81f, cx * 640.88f)));
+                const float dx = nfx + (jx + (float)x), dy = nfy + (jy + (float)y), dz = nfz + (jz + (float)z);
+                const float dist = sqrtf(fmaf(dz, dz, fmaf(dx, dx, dy * dy)));
+                if (dist < d1) { d2 = d1; d1 = dist; }
+                else if (dist < d2) { d2 = dist; }
+            }
+    return d1;
+}
+
+// ------------------------------------------------------------------ biomeFuncs.hpp:385-406
+static inline bool biome_pre_process(uint8_t* block, int biome, int wx, int y, int wz, float height)
+{
+    if (biome == CRYSTALS && height > 176.f)
+    {
+        const float quartzStart = fmaf(fbm2<3>((float)wx * 0.0080f, (float)wz * 0.0080f), 15.f, 140.f);
+        if ((float)y > quartzStart) { *block = B_QUARTZ; return true; }
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------ biomeFuncs.hpp:408-590
+static inline bool biome_post_process(uint8_t* block, int biome, int wx, int y, int wz, float height, bool isTopBlock)
+{
+    const float fx = (float)wx, fz = (float)wz, fy = (float)y;
+    switch (biome)
+    {
+    case ARCHIPELAGO:
+    {
+        if (y < SEA_LEVEL || *block == B_WATER) return false;
+        const float dirtHeight = fmaf(fbm2<3>(fx * 0.0065f, fz * 0.0065f), 1.7f, 129.5f);
+        if (fy > dirtHeight) { *block = isTopBlock ? B_GRASS_BLOCK : B_DIRT; return true; }
+        return false;
+    }
+    case TROPICAL_BEACH:
+        if (isTopBlock && *block != B_SMOOTH_SAND && *block != B_WATER) { *block = B_SMOOTH_SAND; return true; }
+        return false;
+    case BEACH:
+        if (isTopBlock && *block != B_SAND && *block != B_WATER) { *block = B_SAND; return true; }
+        return false;
+    case MESA:
+    {
+        if (fy < 90.f || *block == B_WATER) return false;
+        const float start = fmaf(fbm2<3>(fx * 0.0040f, fz * 0.0040f), 12.f, 108.f);
+        if (fy < start) return false;
+        if (*block == B_CLAY && fy < start + 20.f) return false;
+        float sample = fmaf(simplex3<true>(fx * 0.0100f, fz * 0.0100f, fy * 0.0300f), 3.f, fy) - start;
+        sample = sample - 32.f * floorf(sample / 32.f);
+        uint8_t b;
+        if (sample < 5.f) b = B_TERRACOTTA;
+        else if (sample < 8.f) b = B_ORANGE_TERRACOTTA;
+        else if (sample < 12.f) b = B_RED_TERRACOTTA;
+        else if (sample < 14.f) b = B_WHITE_TERRACOTTA;
+        else if (sample < 20.f) b = B_TERRACOTTA;
+        else if (sample < 21.f) b = B_ORANGE_TERRACOTTA;
+        else if (sample < 26.f) b = B_YELLOW_TERRACOTTA;
+        else if (sample < 29.f) b = B_PURPLE_TERRACOTTA;
+        else b = B_TERRACOTTA;
+        *block = b;
+        return true;
+    }
+    case FROZEN_WASTELAND:
+        if (*block != B_WATER) return false;
+        *block = B_PACKED_ICE;
+        return true;
+    case SHREKS_SWAMP:
+    {
+        if (fy < 100.f) return false;
+        if (*block == B_DIRT || *block == B_JUNGLE_GRASS_BLOCK)
+        {
+            const float mudEnd = fmaf(simplex2<true>(fx * 0.0300f, fz * 0.0300f), 1.1f, 128.8f);
+            if (fy < mudEnd) { *block = B_MUD; return true; }
+        }
+        return false;
+    }
+    case TIANZI_MOUNTAINS:
+    {
+        if (fy < 90.f || *block == B_WATER || *block == B_DIRT || *block == B_GRASS_BLOCK) return false;
+        const float start = fmaf(fbm2<3>(fx * 0.0200f, fz * 0.0200f), 16.f, 112.f);
+        if (fy < start) return false;
+        *block = B_SMOOTH_SANDSTONE;
+        return true;
+    }
+    case CRYSTALS:
+    {
+        if (!isTopBlock || *block == B_QUARTZ) return false;
+        if (hash_fract(fmaf((float)(wx + 913213), 238.68f, (float)(wz + 85941) * 491.28f)) < 0.1f) { *block = B_MYCELIUM; return true; }
+        return false;
+    }
+    case MOUNTAINS:
+    {
+        if (fy < 190.f) return false;
+        const float snowStart = fmaf(fbm2<3>(fx * 0.0500f, fz * 0.0500f), 5.f, 202.f);
+        if (fy < snowStart) return false;
+        *block = B_SNOW;
+        return true;
+    }
+    default: return false;
+    }
+}
+
+// ------------------------------------------------------------------ biomeFuncs.hpp:592-707
+static inline bool cave_biome_post_process(uint8_t* block, int caveBiome, int wx, int y, int wz, int caveBottomDepth, int caveTopDepth)
+{
+    if (caveBiome == CB_NONE) return false;
+    const bool isTopBlock = caveBottomDepth == 0;
+    switch (caveBiome)
+    {
+    case CB_CRYSTAL_CAVES:
+    {
+        if (*block != B_STONE && *block != B_DEEPSLATE && *block != B_BLACKSTONE) return false;
+        const float s = (float)(wx + wz);
+        const float quartz = simplex3<true>((float)(wx + y) * 0.05f, (float)(wz + 5819323) * 0.05f, (s + s) * 0.05f);
+        if (quartz < -0.25f) { *block = B_QUARTZ; return true; }
+        if (*block == B_BLACKSTONE) return false;
+        const float chance = (*block == B_STONE) ? 0.5f : 0.4f;
+        const uint8_t cobble = (*block == B_STONE) ? B_COBBLESTONE : B_COBBLED_DEEPSLATE;
+        // rand1From3(worldBlockPos): fma(z, Kz, fma(x, Kx, y*Ky))
+        if (hash_fract(fmaf((float)wz, 640.88f, fmaf((float)wx, 238.68f, (float)y * 491.28f))) < chance) { *block = cobble; return true; }
+        return false;
+    }
+    case CB_LUSH_CAVES:
+    {
+        if (*block != B_STONE && *block != B_DEEPSLATE && *block != B_BLACKSTONE) return false;
+        const float nx = (float)wx * 0.025f, nz = (float)wz * 0.025f;
+        float ny = (float)y * 0.025f;
+        const float threshold = fmaf(simplex3<true>(nx, ny, nz), 4.5f, 1.5f);
+        const float bd = (float)caveBottomDepth, td = (float)caveTopDepth;
+        if (!(bd >= 0.f && bd <= threshold) && !(td >= 0.f && td <= threshold)) return false;
+        ny = ny + 192031.9821f;
+        const float ax = nx * 0.4f, ay = ny * 0.4f, az = nz * 0.4f;
+        const float o1 = fbm3<3, false>(ax, ay, az);
+        const float o2 = fbm3<3, true>(ax + 5923.45f, ay + 4129.42f, az + 5790.48f);
+        const float o3 = fbm3<3, true>(ax + 1765.68f, ay + 4704.36f, az + 5692.12f);
+        const float clay = worley3_lush(fmaf(o1, 2.f, nx), fmaf(o2, 2.f, ny), fmaf(o3, 2.f, nz));
+        *block = clay < 0.25f ? B_CLAY : B_MOSS;
+        return true;
+    }
+    case CB_WARPED_FOREST:
+        if (!isTopBlock) return false;
+        if (*block == B_DEEPSLATE) { *block = B_WARPED_DEEPSLATE; return true; }
+        if (*block == B_BLACKSTONE) { *block = B_WARPED_BLACKSTONE; return true; }
+        return false;
+    case CB_AMBER_FOREST:
+        if (!isTopBlock) return false;
+        if (*block == B_DEEPSLATE) { *block = B_AMBER_DEEPSLATE; return true; }
+        if (*block == B_BLACKSTONE) { *block = B_AMBER_BLACKSTONE; return true; }
+        return false;
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------ chunk.cu:1202-1380
+// weights[24], layersAndHeight[21] (20 layer starts + height), caveLayers[32] of the column
+static inline uint8_t fill_place_block(const float* weights, const float* layersAndHeight, const CaveLayer* caveLayers, int y,
+                                       float height, int wx, int wz)
+{
+    if (y == 0) return B_BEDROCK;
+    const float fy = (float)y;
+    if (fy > height && y > SEA_LEVEL) return B_AIR;
+    bool isOcean = false;
+    for (int b = 0; b < NUM_OCEAN_BIOMES; ++b)
+        if (weights[b] > 0.f) { isOcean = true; break; }
+    Minstd rng = make_rng3(wx, y, wz);
+    const int randBiome = random_biome(weights, 1, rng.u01());
+    const bool isTopBlock = fy >= height - 1.f;
+    uint8_t block = B_AIR;
+    if (fy > height && y <= SEA_LEVEL)
+    {
+        block = B_WATER;
+        biome_post_process(&block, randBiome, wx, y, wz, height, isTopBlock);
+        if (isOcean) return block;
+    }
+    int caveBottomDepth = -384, caveTopDepth = -384;
+    for (int li = 0; li < MAX_CAVE_LAYERS; ++li)
+    {
+        const CaveLayer& cl = caveLayers[li];
+        if (cl.start == 384) { caveBottomDepth = -384; break; }
+        caveBottomDepth = cl.start - y;
+        if (y <= cl.start) break;
+        if (y <= cl.end)
+        {
+            caveTopDepth = y - (cl.end + 1);
+            block = (y <= LAVA_LEVEL) ? B_LAVA : B_AIR;
+            cave_biome_post_process(&block, cave_biome(wx, y, wz, height, 190249401), wx, y, wz, caveBottomDepth, caveTopDepth);
+            return block;
+        }
+        caveTopDepth = y - (cl.end + 1);
+    }
+    if (fy > height) return block;
+    if (biome_pre_process(&block, randBiome, wx, y, wz, height))
+    {
+        biome_post_process(&block, randBiome, wx, y, wz, height, isTopBlock);
+        return block;
+    }
+    const int layerStart = (fy >= layersAndHeight[NUM_FORWARD]) ? NUM_FORWARD : 0;
+    int thisLayer = -1;
+    for (int l = layerStart; l < NUM_MATERIALS; ++l)
+        if (layersAndHeight[l] <= fy && fy < layersAndHeight[l + 1]) { thisLayer = l; break; }
+    // thisLayer == -1 reads dev_materialInfos[-1] in the reference (the bytes in front of the table);
+    // it cannot happen for y <= height when the layer stack is well-formed; treated as material 0.
+    block = material_infos()[thisLayer < 0 ? 0 : thisLayer].block;
+    if (isTopBlock && block == B_DIRT) block = kBiomeGrassBlock[randBiome];
+    biome_post_process(&block, randBiome, wx, y, wz, height, isTopBlock);
+    cave_biome_post_process(&block, cave_biome(wx, y, wz, height, 190249401), wx, y, wz, caveBottomDepth, caveTopDepth);
+    return block;
+}
+
+// ------------------------------------------------------------------ kernFill (chunk.cu:1382-1510)
+// features/caveFeatures: gathered lists (already truncated to the caps by the caller);
+// bounds: the host-side y-bounds over the UNtruncated lists (chunk.cu:1555-1570).
+static inline void fill_chunk(int ox, int oz, const float* height256, const float* weights, const float* layers,
+                              const CaveLayer* caveLayers, const FeaturePlacement* feats, int nFeats,
+                              const CaveFeaturePlacement* caveFeats, int nCaveFeats, const int fb[2], const int cfb[2],
+                              uint8_t* blocks)
+{
+    for (int z = 0; z < 16; ++z)
+        for (int x = 0; x < 16; ++x)
+        {
+            const int idx = x + 16 * z;
+            float w[NUM_BIOMES], lh[NUM_MATERIALS + 1];
+            for (int b = 0; b < NUM_BIOMES; ++b) w[b] = weights[b * 256 + idx];
+            for (int l = 0; l < NUM_MATERIALS; ++l) lh[l] = layers[l * 256 + idx];
+            lh[NUM_MATERIALS] = height256[idx];
+            const float height = lh[NUM_MATERIALS];
+            const CaveLayer* cl = caveLayers + (size_t)idx * MAX_CAVE_LAYERS;
+            const int wx = ox + x, wz = oz + z;
+            for (int y = 0; y < 384; ++y)
+            {
+                uint8_t block = fill_place_block(w, lh, cl, y, height, wx, wz);
+                uint8_t fblock = 0;
+                bool placed = false;
+                if (y >= fb[0] && y <= fb[1])
+                    for (int f = 0; f < nFeats; ++f)
+                    {
+                        const FeaturePlacement& fp = feats[f];
+                        if (fp.feature == F_NONE) break;
+                        if (block != B_AIR && !fp.canReplaceBlocks) continue;
+                        if (y < fp.y + kFeatureHeightBounds[fp.feature][0] || y > fp.y + kFeatureHeightBounds[fp.feature][1]) continue;
+                        if (place_feature(fp, wx, y, wz, &fblock)) { placed = true; break; }
+                    }
+                if (!placed && y >= cfb[0] && y <= cfb[1])
+                    for (int f = 0; f < nCaveFeats; ++f)
+                    {
+                        const CaveFeaturePlacement& cp = caveFeats[f];
+                        if (cp.feature == CF_NONE) break;
+                        if (block != B_AIR && !cp.canReplaceBlocks) continue;
+                        if (y < cp.y + kCaveFeatureHeightBounds[cp.feature][0] || y > cp.y + cp.layerHeight + kCaveFeatureHeightBounds[cp.feature][1]) continue;
+                        if (place_cave_feature(cp, wx, y, wz, &fblock)) { placed = true; break; }
+                    }
+                blocks[y + 384 * idx] = placed ? fblock : block;
+            }
+        }
+}
+
+// ------------------------------------------------------------------ decorators (chunk.cu:1634-1747)
+static inline void try_place_decorator(uint8_t* blocks, int x, int y, int z, const DecoratorGen& gen)
+{
+    const int di = y + 384 * (x + 16 * z);
+    // y may be 384 for the open-sky layer's ceiling attempt: the reference then indexes the next
+    // column (or one past the array); every such attempt returns below without writing because
+    // generatesFromCeiling decorators need y + 1 <= 383. Guard the read instead of reproducing it.
+    if (y < 0 || y > 383) return;
+    uint8_t& cur = blocks[di];
+    if (cur != gen.replace) return;                       // possibleReplaceBlocks is always one block
+    const int under = gen.fromCeiling ? 1 : -1;
+    if (y + under < 0 || y + under > 383) return;
+    const uint8_t ub = blocks[di + under];
+    if (ub < NUM_NON_SOLID_BLOCKS) return;
+    if (gen.numUnder > 0)
+    {
+        bool ok = false;
+        for (int i = 0; i < gen.numUnder; ++i) ok = ok || gen.under[i] == ub;
+        if (!ok) return;
+    }
+    if (gen.second != B_AIR)
+    {
+        const int over = -under;
+        if (y + over < 0 || y + over > 383) return;
+        uint8_t& ob = blocks[di + over];
+        if (ob != gen.replace) return;
+        ob = gen.second;
+    }
+    cur = gen.block;
+}
+
+static inline void place_decorators(int ox, int oz, const float* height256, const float* weights, const CaveLayer* caveLayers,
+                                    uint8_t* blocks)
+{
+    Minstd rng = make_rng4(ox, 0, oz, 7589341);
+    for (int z = 0; z < 16; ++z)
+        for (int x = 0; x < 16; ++x)
+        {
+            const int idx = x + 16 * z;
+            const int biome = random_biome(weights + idx, 256, rng.u01());
+            float rand = rng.u01();
+            int n;
+            const DecoratorGen* gens = biome_decorator_gens(biome, &n);
+            for (int g = 0; g < n; ++g)
+                if ((rand -= gens[g].chance) < 0.f)
+                {
+                    try_place_decorator(blocks, x, (int)height256[idx] + 1, z, gens[g]);
+                    break;
+                }
+            const CaveLayer* cl = caveLayers + (size_t)idx * MAX_CAVE_LAYERS;
+            for (int li = 0; li < MAX_CAVE_LAYERS; ++li)
+            {
+                if (cl[li].start == 384) break;
+                float bottomRand = rng.u01();
+                float topRand = rng.u01();
+                const DecoratorGen* cgens = cave_biome_decorator_gens(cl[li].bottomBiome, &n);
+                // placedTop / placedBottom are never set in the reference (chunk.cu:1718-1742): every
+                // generator whose running threshold has gone negative fires
+                for (int g = 0; g < n; ++g)
+                {
+                    if (cgens[g].fromCeiling)
+                    {
+                        if ((topRand -= cgens[g].chance) < 0.f) try_place_decorator(blocks, x, cl[li].end, z, cgens[g]);
+                    }
+                    else
+                    {
+                        if ((bottomRand -= cgens[g].chance) < 0.f) try_place_decorator(blocks, x, cl[li].start + 1, z, cgens[g]);
+                    }
+                }
+            }
+        }
+}
+
+}  // namespace mmo

@@ -14,6 +14,8 @@
 #include "mm_surface.h"
 #include "mm_layers.h"
 #include "mm_caves.h"
+#include "mm_features.h"
+#include "mm_fill.h"
 
 namespace {
 template <class F>
@@ -85,6 +87,69 @@ void mmo_caves(int n, const int32_t* origins, const float* heightfield, const fl
     });
 }
 int mmo_cave_biome(int x, int y, int z, float maxHeight, int seed) { return mmo::cave_biome(x, y, z, maxHeight, seed); }
+
+// Chunk::generateFeaturePlacements (chunk.cu:1147-1156). Lists are written with stride maxPerChunk;
+// counts[n][2] = {surface, cave} (the true counts, even if larger than maxPerChunk).
+void mmo_feature_placements(int n, const int32_t* origins, const float* heightfield, const float* weights, const float* layers,
+                            const void* caveLayers, int maxPerChunk, void* outF, void* outCF, int32_t* counts, int nthreads)
+{
+    const mmo::CaveLayer* cl = (const mmo::CaveLayer*)caveLayers;
+    mmo::FeaturePlacement* F = (mmo::FeaturePlacement*)outF;
+    mmo::CaveFeaturePlacement* CF = (mmo::CaveFeaturePlacement*)outCF;
+    parallel_for(n, nthreads, [&](int c) {
+        std::vector<mmo::FeaturePlacement> f;
+        std::vector<mmo::CaveFeaturePlacement> cf;
+        const int ox = origins[2 * c], oz = origins[2 * c + 1];
+        for (int z = 0; z < 16; ++z)
+            for (int x = 0; x < 16; ++x)
+            {
+                const int idx = x + 16 * z;
+                mmo::column_feature_placements(ox + x, oz + z, heightfield[(size_t)c * 256 + idx],
+                                               weights + (size_t)c * (mmo::NUM_BIOMES * 256) + idx, 256,
+                                               layers + (size_t)c * (mmo::NUM_MATERIALS * 256) + idx, 256,
+                                               cl + ((size_t)c * 256 + idx) * mmo::MAX_CAVE_LAYERS, f, cf);
+            }
+        counts[2 * c] = (int)f.size();
+        counts[2 * c + 1] = (int)cf.size();
+        for (size_t i = 0; i < f.size() && (int)i < maxPerChunk; ++i) F[(size_t)c * maxPerChunk + i] = f[i];
+        for (size_t i = 0; i < cf.size() && (int)i < maxPerChunk; ++i) CF[(size_t)c * maxPerChunk + i] = cf[i];
+    });
+}
+
+// Chunk::fill incl. placeDecorators (chunk.cu:1518-1632, 1679-1747). feats / caveFeats: gathered lists
+// per chunk (stride strideF / strideCF entries), numFeatures[n][2] their lengths BEFORE truncation.
+void mmo_fill(int n, const int32_t* origins, const float* heightfield, const float* weights, const float* layers,
+              const void* caveLayers, const void* feats, const void* caveFeats, const int32_t* numFeatures, int strideF,
+              int strideCF, uint8_t* out_blocks, int decorate, int nthreads)
+{
+    const mmo::CaveLayer* cl = (const mmo::CaveLayer*)caveLayers;
+    const mmo::FeaturePlacement* F = (const mmo::FeaturePlacement*)feats;
+    const mmo::CaveFeaturePlacement* CF = (const mmo::CaveFeaturePlacement*)caveFeats;
+    parallel_for(n, nthreads, [&](int c) {
+        const mmo::FeaturePlacement* f = F + (size_t)c * strideF;
+        const mmo::CaveFeaturePlacement* cf = CF + (size_t)c * strideCF;
+        const int nf = numFeatures[2 * c], ncf = numFeatures[2 * c + 1];
+        int fb[2] = {384, -1}, cfb[2] = {384, -1};
+        for (int i = 0; i < nf; ++i)
+        {
+            fb[0] = std::min(fb[0], f[i].y + mmo::kFeatureHeightBounds[f[i].feature][0]);
+            fb[1] = std::max(fb[1], f[i].y + mmo::kFeatureHeightBounds[f[i].feature][1]);
+        }
+        for (int i = 0; i < ncf; ++i)
+        {
+            cfb[0] = std::min(cfb[0], cf[i].y + mmo::kCaveFeatureHeightBounds[cf[i].feature][0]);
+            cfb[1] = std::max(cfb[1], cf[i].y + cf[i].layerHeight + mmo::kCaveFeatureHeightBounds[cf[i].feature][1]);
+        }
+        uint8_t* blocks = out_blocks + (size_t)c * 98304;
+        const float* h = heightfield + (size_t)c * 256;
+        const float* w = weights + (size_t)c * (mmo::NUM_BIOMES * 256);
+        const mmo::CaveLayer* ccl = cl + (size_t)c * 256 * mmo::MAX_CAVE_LAYERS;
+        mmo::fill_chunk(origins[2 * c], origins[2 * c + 1], h, w, layers + (size_t)c * (mmo::NUM_MATERIALS * 256), ccl, f,
+                        std::min(nf, mmo::MAX_FEATURES), cf, std::min(ncf, mmo::MAX_CAVE_FEATURES), fb, cfb, blocks);
+        if (decorate) mmo::place_decorators(origins[2 * c], origins[2 * c + 1], h, w, ccl, blocks);
+    });
+}
+float mmo_host_sinf(float x) { return mmo::hm_sinf(x); }
 
 // unit probes used by tests
 float mmo_sinf(float x) { return mmo::dm_sinf(x); }

@@ -61,6 +61,39 @@ class Oracle:
         self.L.mmo_caves(n, _ptr(origins), _ptr(h), _ptr(w), _ptr(out), self.nthreads)
         return out
 
+    def feature_placements(self, origins, heightfield, weights, layers, cave_layers, max_per_chunk=4096):
+        from .refcuda import FeaturePlacement, CaveFeaturePlacement
+        origins = np.ascontiguousarray(origins, dtype=np.int32).reshape(-1, 2)
+        n = origins.shape[0]
+        F = np.zeros((n, max_per_chunk), FeaturePlacement)
+        CF = np.zeros((n, max_per_chunk), CaveFeaturePlacement)
+        counts = np.zeros((n, 2), np.int32)
+        self.L.mmo_feature_placements(n, _ptr(origins), _ptr(np.ascontiguousarray(heightfield, np.float32)),
+                                      _ptr(np.ascontiguousarray(weights, np.float32)), _ptr(np.ascontiguousarray(layers, np.float32)),
+                                      _ptr(np.ascontiguousarray(cave_layers)), max_per_chunk, _ptr(F), _ptr(CF), _ptr(counts), self.nthreads)
+        return [F[i, :min(counts[i, 0], max_per_chunk)].copy() for i in range(n)], \
+               [CF[i, :min(counts[i, 1], max_per_chunk)].copy() for i in range(n)]
+
+    def fill(self, origins, heightfield, weights, layers, cave_layers, gathered, gathered_cave, decorate=True):
+        """gathered / gathered_cave: per-chunk lists of structured arrays (untruncated)."""
+        from .refcuda import FeaturePlacement, CaveFeaturePlacement
+        origins = np.ascontiguousarray(origins, dtype=np.int32).reshape(-1, 2)
+        n = origins.shape[0]
+        sf = max(1, max(len(g) for g in gathered))
+        scf = max(1, max(len(g) for g in gathered_cave))
+        F = np.zeros((n, sf), FeaturePlacement)
+        CF = np.zeros((n, scf), CaveFeaturePlacement)
+        counts = np.zeros((n, 2), np.int32)
+        for i in range(n):
+            F[i, :len(gathered[i])] = gathered[i]
+            CF[i, :len(gathered_cave[i])] = gathered_cave[i]
+            counts[i] = (len(gathered[i]), len(gathered_cave[i]))
+        out = np.zeros((n, 16, 16, 384), np.uint8)
+        self.L.mmo_fill(n, _ptr(origins), _ptr(np.ascontiguousarray(heightfield, np.float32)), _ptr(np.ascontiguousarray(weights, np.float32)),
+                        _ptr(np.ascontiguousarray(layers, np.float32)), _ptr(np.ascontiguousarray(cave_layers)), _ptr(F), _ptr(CF),
+                        _ptr(counts), sf, scf, _ptr(out), 1 if decorate else 0, self.nthreads)
+        return out
+
     def erode_zone(self, planes):
         """planes: (9, 384, 384) float32 (8 loose layer starts + heightfield); returns (eroded copy, sweeps)."""
         p = np.ascontiguousarray(planes, np.float32).copy()
@@ -100,3 +133,15 @@ def scatter_zone(planes, layers, nx, lx0, lz0):
                 layers[c, 12 + l] = planes[l, cz * 16:(cz + 1) * 16, cx * 16:(cx + 1) * 16].reshape(256)
             for l in (10, 11):
                 layers[c, l] = layers[c, 12] - layers[c, l]
+
+
+GATHER_OFFSETS = [(0, 0), (0, 1), (1, 1), (1, 0), (1, -1), (0, -1), (-1, -1), (-1, 0), (-1, 1), (2, 0), (2, 1), (2, 2), (1, 2), (0, 2),
+                  (-1, 2), (-2, 2), (-2, 1), (-2, 0), (-2, -1), (-2, -2), (-1, -2), (0, -2), (1, -2), (2, -2), (2, -1),
+                  (-3, -3), (-2, -3), (-1, -3), (0, -3), (1, -3), (2, -3), (3, -3), (3, -2), (3, -1), (3, 0), (3, 1), (3, 2), (3, 3),
+                  (2, 3), (1, 3), (0, 3), (-1, 3), (-2, 3), (-3, 3), (-3, 2), (-3, 1), (-3, 0), (-3, -1), (-3, -2)]
+
+
+def gather_features(lists, cx, cz, nx):
+    """Chunk::otherChunkGatherFeaturePlacements (chunk.cu:1158-1187): lists = dict chunk idx -> array."""
+    parts = [lists[(cz + dz) * nx + (cx + dx)] for dx, dz in GATHER_OFFSETS]
+    return np.concatenate(parts) if parts else None

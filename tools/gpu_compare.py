@@ -67,8 +67,8 @@ def main():
         ol = o.layers(origins[idx], H18, ref["biome_weights"][idx])
         ml = gen.layers(origins[idx], H18, ref["biome_weights"][idx])
         world = gen.world(X0, Z0, NX, NZ)
-        world.generate(mm.STAGE_HEIGHTFIELD | mm.STAGE_LAYERS | (mm.STAGE_EROSION if last >= 3 else 0) | (mm.STAGE_CAVES if last >= 4 else 0))
-        wd = world.download(heightfield=True, layers=True, cave_layers=(last >= 4))
+        world.generate(mm.STAGE_HEIGHTFIELD | mm.STAGE_LAYERS | (mm.STAGE_EROSION if last >= 3 else 0) | (mm.STAGE_CAVES if last >= 4 else 0) | (mm.STAGE_FEATURES if last >= 5 else 0) | (mm.STAGE_FILL if last >= 6 else 0))
+        wd = world.download(heightfield=True, layers=True, cave_layers=(last >= 4), blocks=(last >= 6))
         ws = world.stages().ravel()
         print("world stages:", np.bincount(ws), "ref stages:", np.bincount(st), "erosion sweeps", world.erosion_sweeps(), "stage ms", world.stage_ms())
         # S2 comparison on entries the reference wrote (sentinel = NaN payload) and before erosion rewrote them
@@ -126,6 +126,68 @@ def main():
                 print("  %-18s %-12s different=%d of %d ; columns affected=%d" % (name, f, int(d.sum()), d.size, int(d.any(axis=2).sum())))
         nl = (rc["start"] != 384).sum(axis=2)
         print("  ref layers/column avg %.3f max %d" % (nl.mean(), nl.max()))
+    def cmp_lists(name, A, B):
+        nd = sum(1 for a, b in zip(A, B) if len(a) != len(b) or (a.tobytes() != b.tobytes()))
+        print("  %-34s chunks=%d lists differing=%d ; entries %d vs %d" % (name, len(A), nd, sum(len(a) for a in A), sum(len(b) for b in B)))
+        if nd:
+            for k, (a, b) in enumerate(zip(A, B)):
+                if len(a) != len(b) or a.tobytes() != b.tobytes():
+                    m = min(len(a), len(b))
+                    j = next((i for i in range(m) if a[i].tobytes() != b[i].tobytes()), m)
+                    print("     first diff: list %d len %d vs %d at entry %d: %s | %s" % (k, len(a), len(b), j, a[j] if j < len(a) else None, b[j] if j < len(b) else None))
+                    break
+    if last >= 5:
+        print("--- S5a ---")
+        fidx = ref["feat_idx"]
+        assert (fidx == cidx).all()
+        rl5 = ref["layers"][fidx]
+        oF, oCF = o.feature_placements(origins[fidx], ref["heightfield"][fidx], ref["biome_weights"][fidx], rl5, rc)
+        mF, mCF = gen.feature_placements(origins[fidx], ref["heightfield"][fidx], ref["biome_weights"][fidx], rl5, rc)
+        wF, wCF = world.download_features()
+        cmp_lists("oracle vs ref surface features", oF, ref["features"])
+        cmp_lists("oracle vs ref cave features", oCF, ref["cave_features"])
+        cmp_lists("product vs ref surface features", mF, ref["features"])
+        cmp_lists("product vs ref cave features", mCF, ref["cave_features"])
+        cmp_lists("world vs ref surface features", [wF[i] for i in fidx], ref["features"])
+        cmp_lists("world vs ref cave features", [wCF[i] for i in fidx], [c[:4096] for c in ref["cave_features"]])
+        import pickle
+        pickle.dump({"feat_idx": fidx, "features": ref["features"], "cave_features": ref["cave_features"]}, open(os.path.join(outdir, "features.pkl"), "wb"))
+    if last >= 6:
+        print("--- S6 ---")
+        bidx = ref["block_idx"]
+        rb = ref["blocks"]
+        np.save(os.path.join(outdir, "block_idx.npy"), bidx)
+        np.save(os.path.join(outdir, "blocks.npy"), rb)
+        pickle.dump({"gf": ref["gathered_features"], "gcf": ref["gathered_cave_features"]}, open(os.path.join(outdir, "gathered.pkl"), "wb"))
+        pos5 = {int(c): k for k, c in enumerate(fidx)}
+        lists = {int(c): ref["features"][k] for k, c in enumerate(fidx)}
+        clists = {int(c): ref["cave_features"][k] for k, c in enumerate(fidx)}
+        g = [orc.gather_features(lists, int(c) % NX, int(c) // NX, NX) for c in bidx]
+        gc = [orc.gather_features(clists, int(c) % NX, int(c) // NX, NX) for c in bidx]
+        cmp_lists("test-side gather vs ref gathered", g, ref["gathered_features"])
+        cmp_lists("test-side gather vs ref gathered cave", gc, ref["gathered_cave_features"])
+        ksel = np.array([pos5[int(c)] for c in bidx])
+        t = time.time()
+        ob = o.fill(origins[bidx], ref["heightfield"][bidx], ref["biome_weights"][bidx], ref["layers"][bidx], rc[ksel], g, gc)
+        print("oracle fill: %d chunks %.2fs" % (len(bidx), time.time() - t), flush=True)
+        t = time.time()
+        mb = gen.fill(origins[bidx], ref["heightfield"][bidx], ref["biome_weights"][bidx], ref["layers"][bidx], rc[ksel], g, gc)
+        print("product fill (batch op): %.3fs" % (time.time() - t), flush=True)
+        wb = wd["blocks"][bidx]
+        names = None
+        for name, a, b in (("oracle vs ref", ob, rb), ("product vs ref", mb, rb), ("product vs oracle", mb, ob), ("world vs ref", wb, rb)):
+            d = a != b
+            print("  %-18s block mismatches=%d of %d (%.3g)" % (name, int(d.sum()), d.size, d.mean()))
+            if d.sum():
+                pairs = {}
+                for x, y in zip(a[d][:200000], b[d][:200000]):
+                    pairs[(int(x), int(y))] = pairs.get((int(x), int(y)), 0) + 1
+                top = sorted(pairs.items(), key=lambda kv: -kv[1])[:12]
+                print("     (got,ref) counts:", top)
+                w_ = np.argwhere(d)[:3]
+                for ci, z, x, y in w_:
+                    c = int(bidx[ci])
+                    print("     e.g. chunk %d (cx=%d cz=%d) local x=%d z=%d y=%d got=%d ref=%d" % (c, X0 + c % NX, Z0 + c // NX, x, z, y, a[ci, z, x, y], b[ci, z, x, y]))
     # per dominant biome breakdown of oracle-vs-ref height mismatches
     dom = ref["biome_weights"].argmax(axis=1)
     single = (ref["biome_weights"].max(axis=1) == 1.0)
