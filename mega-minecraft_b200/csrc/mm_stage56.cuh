@@ -365,4 +365,18 @@ __global__ void k_decorators(const int* __restrict__ fillList, int n, const int2
     }
 }
 
+
+// 64-bit FNV-1a of each filled column (384 bytes), for cheap equality checks of large worlds
+__global__ void k_column_hashes(const int* __restrict__ fillList, int n, const uint8_t* __restrict__ blocks, unsigned long long* __restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * 256) return;
+    const int li = t >> 8, idx = t & 255;
+    const int chunk = fillList[li];
+    const uint8_t* b = blocks + (size_t)chunk * 98304 + (size_t)idx * 384;
+    unsigned long long h = 14695981039346656037ull;
+    for (int y = 0; y < 384; ++y) { h ^= b[y]; h *= 1099511628211ull; }
+    out[t] = h;
+}
+
 }  // namespace mmg

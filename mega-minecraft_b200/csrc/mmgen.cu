@@ -524,6 +524,44 @@ int mmgen_world_generate(MmgenWorld* w, int stageMask)
     return 0;
 }
 
+int mmgen_world_device_ptrs(MmgenWorld* w, void** heightfield, void** biomeWeights, void** layers, void** caveLayers, void** blocks)
+{
+    if (heightfield) *heightfield = w->d_height;
+    if (biomeWeights) *biomeWeights = w->d_weights;
+    if (layers) *layers = w->d_eroded ? (void*)w->d_eroded : (void*)w->d_layers;
+    if (caveLayers) *caveLayers = w->d_caves;
+    if (blocks) *blocks = w->d_blocks;
+    return 0;
+}
+
+int mmgen_world_block_checksum(MmgenWorld* w, uint64_t* out)
+{
+    if (requireReady()) return 1;
+    std::vector<int> list;
+    for (int i = 0; i < w->n; ++i)
+        if (w->stage[i] == 6) list.push_back(i);
+    uint64_t h = 14695981039346656037ull;
+    if (!list.empty())
+    {
+        const int m = (int)list.size();
+        int* d_l = nullptr;
+        unsigned long long* d_h = nullptr;
+        MMG_CUDA(cudaMalloc(&d_l, (size_t)m * sizeof(int)));
+        MMG_CUDA(cudaMalloc(&d_h, (size_t)m * 256 * sizeof(unsigned long long)));
+        MMG_CUDA(cudaMemcpyAsync(d_l, list.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, w->stream));
+        MMG_LAUNCH(k_column_hashes, (m * 256 + 255) / 256, 256, 0, w->stream, (const int*)d_l, m, (const uint8_t*)w->d_blocks, d_h);
+        std::vector<unsigned long long> hs((size_t)m * 256);
+        MMG_CUDA(cudaMemcpyAsync(hs.data(), d_h, hs.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->stream));
+        MMG_CUDA(cudaStreamSynchronize(w->stream));
+        cudaFree(d_l);
+        cudaFree(d_h);
+        for (unsigned long long v : hs)
+            for (int b = 0; b < 8; ++b) { h ^= (v >> (8 * b)) & 0xff; h *= 1099511628211ull; }
+    }
+    *out = h;
+    return 0;
+}
+
 int mmgen_world_download_features(MmgenWorld* w, int maxPerChunk, MmgenFeaturePlacement* features,
                                   MmgenCaveFeaturePlacement* caveFeatures, int32_t* counts)
 {

@@ -66,6 +66,7 @@ static inline float special_cave_noise(float px, float py, float pz)
         for (int y = -1; y <= 1; ++y)
             for (int z = -1; z <= 1; ++z)
             {
+                ++op_counters().worleyCells3;
                 const float cx = (float)(ix + x), cy = (float)(iy + y), cz = (float)(iz + z);
                 const float jx = hash_fract(fmaf(cz, 402.98f, fmaf(cx, 238.68f, cy * 491.28f)));
                 const float jy = hash_fract(fmaf(cz, 747.42f, fmaf(cx, 654.37f, cy * 560.45f)));

@@ -27,6 +27,7 @@ static inline float worley3_lush(float px, float py, float pz)
         for (int y = -1; y <= 1; ++y)
             for (int z = -1; z <= 1; ++z)
             {
+                ++op_counters().worleyCells3;
                 const float cx = (float)(ix + x), cy = (float)(iy + y), cz = (float)(iz + z);
                 const float jx = hash_fract(fmaf(cz, 402.98f, fmaf(cy, 491.28f, cx * 238.68f)));
                 const float jy = hash_fract(fmaf(cz, 747.42f, fmaf(cy, 560.45f, cx * 654.37f)));

@@ -17,6 +17,15 @@
 
 namespace mmo {
 
+// Noise-primitive call counters (thread-local, summed by the API): the bench derives the ALGORITHMIC
+// FLOP count of a workload from them with the canonical costs of SURVEY.md 8(d).
+struct OpCounters { unsigned long long simplex2, simplex3, sinCalls, worleyCells2, worleyCells3; };
+inline OpCounters& op_counters()
+{
+    static thread_local OpCounters c = {0, 0, 0, 0, 0};
+    return c;
+}
+
 // ---------------------------------------------------------------- integer hash + minstd
 // rng.hpp:69-78
 static inline uint32_t hash_u32(uint32_t a)
@@ -89,6 +98,7 @@ static inline float sx_permute(float x) { return sx_mod289(fmaf(x, 34.0f, 1.0f) 
 template <bool SKEW_X = false>
 static inline float simplex2_raw(float vx, float vy)
 {
+    ++op_counters().simplex2;
     const float C0 = 0.211324865405187f, C1 = 0.366025403784439f, C2 = -0.577350269189626f, C3 = 0.024390243902439f;
     // i = floor(v + dot(v, C.yy)); dot = fma(v.y, C1, v.x*C1)
     float s = SKEW_X ? fmaf(vx, C1, vy * C1) : fmaf(vy, C1, vx * C1);
@@ -138,6 +148,7 @@ static inline float simplex2(float vx, float vy) { return 130.0f * simplex2_raw<
 template <bool SKEW_Y = false>
 static inline float simplex3_raw(float vx, float vy, float vz)
 {
+    ++op_counters().simplex3;
     const float C = 1.0f / 3.0f, D = 1.0f / 6.0f;
     const float NZ = 0.142857142857f;           // n_
     const float NX = NZ * 2.0f;                  // ns.x = n_*D.w - D.x

@@ -17,7 +17,18 @@
 #include "mm_features.h"
 #include "mm_fill.h"
 
+#include <mutex>
 namespace {
+mmo::OpCounters g_total = {0, 0, 0, 0, 0};
+std::mutex g_totalMutex;
+void flush_counters()
+{
+    mmo::OpCounters& c = mmo::op_counters();
+    std::lock_guard<std::mutex> lock(g_totalMutex);
+    g_total.simplex2 += c.simplex2; g_total.simplex3 += c.simplex3; g_total.sinCalls += c.sinCalls;
+    g_total.worleyCells2 += c.worleyCells2; g_total.worleyCells3 += c.worleyCells3;
+    c = mmo::OpCounters{0, 0, 0, 0, 0};
+}
 template <class F>
 void parallel_for(int n, int nthreads, F f)
 {
@@ -25,12 +36,14 @@ void parallel_for(int n, int nthreads, F f)
     if (nthreads == 1)
     {
         for (int i = 0; i < n; ++i) f(i);
+        flush_counters();
         return;
     }
     std::vector<std::thread> ts;
     for (int t = 0; t < nthreads; ++t)
         ts.emplace_back([=]() {
             for (int i = t; i < n; i += nthreads) f(i);
+            flush_counters();
         });
     for (auto& t : ts) t.join();
 }
@@ -150,6 +163,15 @@ void mmo_fill(int n, const int32_t* origins, const float* heightfield, const flo
     });
 }
 float mmo_host_sinf(float x) { return mmo::hm_sinf(x); }
+
+// noise-primitive call counters accumulated since the last reset: simplex2, simplex3, sin, worley cells 2-D / 3-D
+void mmo_counters(unsigned long long* out5, int reset)
+{
+    flush_counters();
+    std::lock_guard<std::mutex> lock(g_totalMutex);
+    out5[0] = g_total.simplex2; out5[1] = g_total.simplex3; out5[2] = g_total.sinCalls; out5[3] = g_total.worleyCells2; out5[4] = g_total.worleyCells3;
+    if (reset) g_total = mmo::OpCounters{0, 0, 0, 0, 0};
+}
 
 // unit probes used by tests
 float mmo_sinf(float x) { return mmo::dm_sinf(x); }

@@ -29,6 +29,7 @@ static inline float sx2(float x, float y) { return 130.0f * simplex2_raw<SKEW_X>
 #endif
 static inline float hash_fract(float d)
 {
+    ++op_counters().sinCalls;
     float r = MMO_SIN(d) * 39021.426f;
     return r - floorf(r);
 }
@@ -48,6 +49,7 @@ static inline Worley2 worley2(float px, float py)
     for (int x = -1; x <= 1; ++x)
         for (int y = -1; y <= 1; ++y)
         {
+            ++op_counters().worleyCells2;
             const float cx = (float)(ix + x), cy = (float)(iy + y);
             const float jx = hash_fract(MMO_HDOT2(cx, 238.68f, cy, 491.28f));
             const float jy = hash_fract(MMO_HDOT2(cx, 654.37f, cy, 560.45f));

@@ -34,6 +34,17 @@ class Oracle:
         self.L.mmo_hash.restype = ctypes.c_uint32
         self.L.mmo_hash.argtypes = [ctypes.c_uint32]
 
+    def counters(self, reset=False):
+        """Noise-primitive calls since the last reset: dict(simplex2, simplex3, sin, worley2_cells, worley3_cells)."""
+        out = np.zeros(5, np.uint64)
+        self.L.mmo_counters(_ptr(out), 1 if reset else 0)
+        return dict(zip(("simplex2", "simplex3", "sin", "worley2_cells", "worley3_cells"), (int(v) for v in out)))
+
+    @staticmethod
+    def flops(c):
+        """Canonical algorithmic FLOPs of SURVEY.md 8(d): simplex2 140, simplex3 330, Worley 45 / 60 per cell, sinf 20."""
+        return 140 * c["simplex2"] + 330 * c["simplex3"] + 45 * c["worley2_cells"] + 60 * c["worley3_cells"] + 20 * c["sin"]
+
     def heightfields(self, origins):
         origins = np.ascontiguousarray(origins, dtype=np.int32).reshape(-1, 2)
         n = origins.shape[0]
