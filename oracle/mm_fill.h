@@ -229,9 +229,11 @@ static inline uint8_t fill_place_block(const float* weights, const float* layers
     int thisLayer = -1;
     for (int l = layerStart; l < NUM_MATERIALS; ++l)
         if (layersAndHeight[l] <= fy && fy < layersAndHeight[l + 1]) { thisLayer = l; break; }
-    // thisLayer == -1 reads dev_materialInfos[-1] in the reference (the bytes in front of the table);
-    // it cannot happen for y <= height when the layer stack is well-formed; treated as material 0.
-    block = material_infos()[thisLayer < 0 ? 0 : thisLayer].block;
+    // thisLayer == -1 happens when y == height exactly or the layer stack is not monotone. The
+    // reference then reads dev_materialInfos[-1].block: 16 bytes in front of that table in constant
+    // memory, which in its build is dev_biomeBlocks[8].grassBlock = SAVANNA_GRASS_BLOCK (the two
+    // tables are adjacent, biomeFuncs.hpp:709-710; seen in the reference's output on a B200).
+    block = thisLayer < 0 ? (uint8_t)B_SAVANNA_GRASS_BLOCK : material_infos()[thisLayer].block;
     if (isTopBlock && block == B_DIRT) block = kBiomeGrassBlock[randBiome];
     biome_post_process(&block, randBiome, wx, y, wz, height, isTopBlock);
     cave_biome_post_process(&block, cave_biome(wx, y, wz, height, 190249401), wx, y, wz, caveBottomDepth, caveTopDepth);

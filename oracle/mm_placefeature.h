@@ -449,18 +449,21 @@ static inline bool place_feature(const FeaturePlacement& fp, int wx, int wy, int
         V3 c = pos;
         c.y = c.y - 1.f;
         c.y = c.y * 1.4f;
-        if (len3(c) - 1.f < 0.f) { *out = B_RAFFLESIA_SPIKES; return true; }
-        float sdf = fabsf(len3(c - v3(0.f, 1.f, 0.f)) - 2.0f) - 0.8f;
-        const float hole = len3(c - v3(0.f, 1.8f, 0.f)) - 1.8f;
+        // the three sphere SDFs share x*x and z*z (computed once, rounded); only the y term is fused
+        const float cx2 = c.x * c.x, cz2 = c.z * c.z;
+        if (sqrtf(cz2 + fmaf(c.y, c.y, cx2)) - 1.f < 0.f) { *out = B_RAFFLESIA_SPIKES; return true; }
+        const float y1 = c.y - 1.f, y2 = c.y - 1.8f;
+        float sdf = fabsf(sqrtf(cz2 + fmaf(y1, y1, cx2)) - 2.0f) - 0.8f;
+        const float hole = sqrtf(cz2 + fmaf(y2, y2, cx2)) - 1.8f;
         sdf = fmaxf(sdf, -hole);
         if (sdf < 0.f) { *out = c.y > 1.f ? B_RAFFLESIA_CENTER : B_RAFFLESIA_STEM; return true; }
         const float startAngle = frng.u01() * kTwoPi;
         for (int i = 0; i < 5; ++i)
         {
-            const float angle = fmaf((float)i * kTwoPi, 0.2f, startAngle);
+            const float angle = startAngle + ((float)i * kTwoPi) * 0.2f;
             float s, co;
             dm_sincosf(-angle, &s, &co);
-            V3 pp = v3(fmaf(pos.x, co, pos.z * s), pos.y - 3.2f, fmaf(-pos.x, s, pos.z * co));
+            V3 pp = v3(fmaf(pos.x, co, pos.z * s), pos.y - 3.2f, fmaf(pos.z, co, -(pos.x * s)));
             pp.y = pp.y - (float)(i % 2) * 0.53f;
             pp.y = fmaf(fminf(fmaxf((fabsf(pp.x - 3.f) - 1.5f) / 1.5f, 0.f), 1.f), 1.3f, pp.y);
             pp.x = pp.x - 3.8f;
