@@ -113,19 +113,38 @@ typedef struct MmgenWorld MmgenWorld;
  * 12 chunks) whose 24x24 window exists; S4/S5a on eroded zones; S5b/S6 where the 7x7 neighbourhood
  * has placements. */
 int mmgen_world_create(int cx0, int cz0, int nx, int nz, MmgenWorld** out);
+/* A world sized to FILL the region of rnx x rnz chunks whose lower corner is chunk (rx0, rz0), by the
+ * apron rule that follows from the reference's state machine (terrain.cpp:471-522, chunk.cu:53-136):
+ * placements on the region (+) 3 chunks, erosion of every zone that meets that, layers on those
+ * zones (+) 6 chunks, heightfields on one more ring (the layers' 1-block slope border). Stages are restricted to what the region needs; results are
+ * identical to a larger window's. This is the unit a multi-GPU tiling gives to each GPU. */
+int mmgen_world_create_for_region(int rx0, int rz0, int rnx, int rnz, MmgenWorld** out);
 int mmgen_world_destroy(MmgenWorld* w);
+/* out8 = {window cx0, cz0, nx, nz, region rx0, rz0, rnx, rnz} (region == window without a target) */
+int mmgen_world_window(MmgenWorld* w, int* out8);
+/* forget all progress (stages back to 0); buffers stay allocated */
+int mmgen_world_reset(MmgenWorld* w);
 int mmgen_world_generate(MmgenWorld* w, int stageMask);
+/* mmgen_world_generate + delivery of the block volumes into HOST memory, the reference's contract for
+ * Chunk::fill (results complete in host memory on return, chunk.cu:1621): out_blocks is
+ * uint8[rnz][rnx][98304] in region raster order (window raster order without a target region), ideally
+ * page-locked; filled batches are copied while later batches are still being filled. */
+int mmgen_world_generate_to_host(MmgenWorld* w, int stageMask, uint8_t* out_blocks);
 /* blocks until all queued work of the world is done */
 int mmgen_world_sync(MmgenWorld* w);
 /* furthest completed stage per chunk (0..6), raster order i = (cz-cz0)*nx + (cx-cx0) */
 int mmgen_world_stages(MmgenWorld* w, uint8_t* out);
 /* device time of the last mmgen_world_generate per stage (ms, CUDA events), stage 1..6 */
 int mmgen_world_stage_ms(MmgenWorld* w, float* out7);
+/* device time of the whole last mmgen_world_generate[_to_host] call (ms, CUDA events on the world's stream) */
+int mmgen_world_total_ms(MmgenWorld* w, float* out);
 int mmgen_world_erosion_sweeps(MmgenWorld* w, int* out);
 
 /* downloads (host pointers), raster order; any pointer may be NULL */
 int mmgen_world_download(MmgenWorld* w, float* heightfield, float* biomeWeights, float* layers,
                          MmgenCaveLayer* caveLayers, uint8_t* blocks);
+/* block volumes of the target region only, uint8[rnz][rnx][98304] */
+int mmgen_world_download_region_blocks(MmgenWorld* w, uint8_t* out_blocks);
 /* per-chunk placement lists (own, not gathered): counts[n][2]; lists packed with stride maxPerChunk */
 int mmgen_world_download_features(MmgenWorld* w, int maxPerChunk, MmgenFeaturePlacement* features,
                                   MmgenCaveFeaturePlacement* caveFeatures, int32_t* counts);

@@ -157,15 +157,26 @@ class ChunkGen:
     def world(self, cx0, cz0, nx, nz):
         return World(self, cx0, cz0, nx, nz)
 
+    def region_world(self, rx0, rz0, rnx, rnz):
+        """World sized by the apron rule to fill chunks [rx0,rx0+rnx) x [rz0,rz0+rnz)."""
+        return World(self, rx0, rz0, rnx, rnz, region=True)
+
 
 class World:
     """Device-resident window of chunks (mmgen_world_*)."""
 
-    def __init__(self, gen, cx0, cz0, nx, nz):
+    def __init__(self, gen, cx0, cz0, nx, nz, region=False):
         self.gen, self.L = gen, gen.L
-        self.cx0, self.cz0, self.nx, self.nz, self.n = cx0, cz0, nx, nz, nx * nz
         self.h = ctypes.c_void_p()
-        gen._check(self.L.mmgen_world_create(cx0, cz0, nx, nz, ctypes.byref(self.h)))
+        if region:
+            gen._check(self.L.mmgen_world_create_for_region(cx0, cz0, nx, nz, ctypes.byref(self.h)))
+        else:
+            gen._check(self.L.mmgen_world_create(cx0, cz0, nx, nz, ctypes.byref(self.h)))
+        win = (ctypes.c_int * 8)()
+        gen._check(self.L.mmgen_world_window(self.h, win))
+        self.cx0, self.cz0, self.nx, self.nz = win[0], win[1], win[2], win[3]
+        self.rx0, self.rz0, self.rnx, self.rnz = win[4], win[5], win[6], win[7]
+        self.n = self.nx * self.nz
 
     def close(self):
         if self.h:
@@ -180,6 +191,24 @@ class World:
 
     def generate(self, stage_mask=STAGE_ALL):
         self.gen._check(self.L.mmgen_world_generate(self.h, int(stage_mask)))
+
+    def reset(self):
+        self.gen._check(self.L.mmgen_world_reset(self.h))
+
+    def generate_to_host(self, out_blocks_ptr, stage_mask=STAGE_ALL):
+        """Generate and deliver the region's block volumes to host memory at address out_blocks_ptr
+        (uint8[rnz][rnx][98304]; pinned memory makes the copy overlap the fill)."""
+        self.gen._check(self.L.mmgen_world_generate_to_host(self.h, int(stage_mask), ctypes.c_void_p(int(out_blocks_ptr))))
+
+    def total_ms(self):
+        v = ctypes.c_float(0)
+        self.gen._check(self.L.mmgen_world_total_ms(self.h, ctypes.byref(v)))
+        return v.value
+
+    def download_region_blocks(self):
+        b = np.empty((self.rnz * self.rnx, 16, 16, 384), np.uint8)
+        self.gen._check(self.L.mmgen_world_download_region_blocks(self.h, _ptr(b)))
+        return b
 
     def sync(self):
         self.gen._check(self.L.mmgen_world_sync(self.h))

@@ -59,6 +59,7 @@ struct MmgenWorld
 {
     int cx0 = 0, cz0 = 0, nx = 0, nz = 0, n = 0;
     int2* d_origins = nullptr;
+    std::vector<int2> h_origins;
     float* d_height = nullptr;
     float* d_weights = nullptr;
     float* d_layers = nullptr;        // S2 output (never modified afterwards: erosion pads read it)
@@ -78,8 +79,16 @@ struct MmgenWorld
     int erosionSweeps = 0;
     std::vector<uint8_t> stage;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[14] = {};
-    float stageMs[7] = {0};
+    cudaStream_t copyStream = nullptr;   // device->host block copies overlapped with the fill (generate_to_host)
+    cudaEvent_t ev[14] = {};             // [2s-2, 2s-1] bracket stage s; [12, 13] bracket the whole generate
+    cudaEvent_t evBatch[2] = {};
+    // target region (mmgen_world_create_for_region): only what filling it needs is computed
+    bool hasTarget = false;
+    int tx0 = 0, tz0 = 0, tnx = 0, tnz = 0;   // window-local chunk coordinates
+    bool inTarget(int x, int z, int grow) const
+    {
+        return !hasTarget || (x >= tx0 - grow && x < tx0 + tnx + grow && z >= tz0 - grow && z < tz0 + tnz + grow);
+    }
 };
 
 extern "C" {
@@ -336,12 +345,15 @@ int mmgen_world_create(int cx0, int cz0, int nx, int nz, MmgenWorld** out)
     w->cx0 = cx0; w->cz0 = cz0; w->nx = nx; w->nz = nz; w->n = nx * nz;
     w->stage.assign(w->n, 0);
     MMG_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+    MMG_CUDA(cudaStreamCreateWithFlags(&w->copyStream, cudaStreamNonBlocking));
     for (auto& e : w->ev) MMG_CUDA(cudaEventCreate(&e));
+    for (auto& e : w->evBatch) MMG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     std::vector<int2> origins(w->n);
     for (int z = 0; z < nz; ++z)
         for (int x = 0; x < nx; ++x) origins[z * nx + x] = make_int2((cx0 + x) * 16, (cz0 + z) * 16);
     MMG_CUDA(cudaMalloc(&w->d_origins, (size_t)w->n * sizeof(int2)));
     MMG_CUDA(cudaMemcpy(w->d_origins, origins.data(), (size_t)w->n * sizeof(int2), cudaMemcpyHostToDevice));
+    w->h_origins.swap(origins);
     *out = w;
     return 0;
 }
@@ -367,14 +379,19 @@ int mmgen_world_destroy(MmgenWorld* w)
     cudaFree(w->d_info);
     cudaFree(w->d_blocks);
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : w->evBatch) if (e) cudaEventDestroy(e);
     if (w->stream) cudaStreamDestroy(w->stream);
+    if (w->copyStream) cudaStreamDestroy(w->copyStream);
     delete w;
     return 0;
 }
 
-int mmgen_world_generate(MmgenWorld* w, int stageMask)
+static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
 {
     if (requireReady()) return 1;
+    MMG_CUDA(cudaEventRecord(w->ev[12], w->stream));
+    // host-delivery calls take their only input, the chunk origins, from host memory every time
+    if (hostBlocks) MMG_CUDA(cudaMemcpyAsync(w->d_origins, w->h_origins.data(), (size_t)w->n * sizeof(int2), cudaMemcpyHostToDevice, w->stream));
     if (stageMask & MMGEN_STAGE_HEIGHTFIELD)
     {
         if (!w->d_height) MMG_CUDA(cudaMalloc(&w->d_height, (size_t)w->n * 256 * sizeof(float)));
@@ -416,6 +433,9 @@ int mmgen_world_generate(MmgenWorld* w, int stageMask)
             {
                 const int lx0 = zx - 6 - w->cx0, lz0 = zz - 6 - w->cz0;   // window corner, local coords
                 if (lx0 < 0 || lz0 < 0 || lx0 + 24 > nx || lz0 + 24 > nz) continue;
+                // with a target region only zones that meet target (+) 3 chunks are eroded
+                if (w->hasTarget && (lx0 + 18 <= w->tx0 - 3 || lx0 + 6 >= w->tx0 + w->tnx + 3 ||
+                                     lz0 + 18 <= w->tz0 - 3 || lz0 + 6 >= w->tz0 + w->tnz + 3)) continue;
                 bool ok = true;
                 for (int z = 0; z < 24 && ok; ++z)
                     for (int x = 0; x < 24 && ok; ++x) ok = w->stage[(lz0 + z) * nx + lx0 + x] >= 2;
@@ -439,7 +459,7 @@ int mmgen_world_generate(MmgenWorld* w, int stageMask)
     {
         std::vector<int> list;
         for (int i = 0; i < w->n; ++i)
-            if (w->stage[i] == 3) list.push_back(i);
+            if (w->stage[i] == 3 && w->inTarget(i % nx, i / nx, 3)) list.push_back(i);
         MMG_CUDA(cudaEventRecord(w->ev[6], w->stream));
         if (!list.empty())
         {
@@ -489,7 +509,7 @@ int mmgen_world_generate(MmgenWorld* w, int stageMask)
         for (int z = 3; z < nz - 3; ++z)
             for (int x = 3; x < nx - 3; ++x)
             {
-                if (w->stage[z * nx + x] != 5) continue;
+                if (w->stage[z * nx + x] != 5 || !w->inTarget(x, z, 0)) continue;
                 bool ok = true;
                 for (int dz = -3; dz <= 3 && ok; ++dz)
                     for (int dx = -3; dx <= 3 && ok; ++dx) ok = w->stage[(z + dz) * nx + x + dx] >= 5;
@@ -515,12 +535,109 @@ int mmgen_world_generate(MmgenWorld* w, int stageMask)
                            MAX_FEATURES, MAX_CAVE_FEATURES, w->d_blocks);
                 MMG_LAUNCH(k_decorators, (m + 31) / 32, 32, 0, w->stream, dl, m, (const int2*)w->d_origins, (const float*)w->d_height,
                            (const float*)w->d_weights, (const CaveLayer*)w->d_caves, w->d_blocks);
+                if (hostBlocks)
+                {
+                    // stream the finished batch to the host while the next batch is being filled:
+                    // one copy per run of consecutive chunks (a region row is contiguous in the window)
+                    cudaEvent_t e = w->evBatch[(b0 / kFillBatch) & 1];
+                    MMG_CUDA(cudaEventRecord(e, w->stream));
+                    MMG_CUDA(cudaStreamWaitEvent(w->copyStream, e, 0));
+                    for (int i = 0; i < m;)
+                    {
+                        int j = i + 1;
+                        while (j < m && list[b0 + j] == list[b0 + j - 1] + 1) ++j;
+                        const int c0 = list[b0 + i];
+                        const int cx = c0 % nx, cz = c0 / nx;
+                        const size_t slot = w->hasTarget ? (size_t)(cz - w->tz0) * w->tnx + (cx - w->tx0) : (size_t)c0;
+                        // runs never cross a window row, so slots of a run are consecutive too
+                        MMG_CUDA(cudaMemcpyAsync(hostBlocks + slot * 98304, w->d_blocks + (size_t)c0 * 98304, (size_t)(j - i) * 98304,
+                                                 cudaMemcpyDeviceToHost, w->copyStream));
+                        i = j;
+                    }
+                }
             }
             MMG_CUDA(cudaStreamSynchronize(w->stream));
             for (int i : list) w->stage[i] = 6;
         }
         MMG_CUDA(cudaEventRecord(w->ev[11], w->stream));
     }
+    if (hostBlocks)
+    {
+        // the whole-generate bracket includes the tail of the download
+        MMG_CUDA(cudaEventRecord(w->evBatch[0], w->copyStream));
+        MMG_CUDA(cudaStreamWaitEvent(w->stream, w->evBatch[0], 0));
+    }
+    MMG_CUDA(cudaEventRecord(w->ev[13], w->stream));
+    if (hostBlocks) MMG_CUDA(cudaStreamSynchronize(w->stream));
+    return 0;
+}
+
+int mmgen_world_generate(MmgenWorld* w, int stageMask) { return worldGenerate(w, stageMask, nullptr); }
+
+int mmgen_world_generate_to_host(MmgenWorld* w, int stageMask, uint8_t* out_blocks)
+{
+    if (!out_blocks)
+    {
+        g_lastError = "mmgen_world_generate_to_host: out_blocks is NULL";
+        return 1;
+    }
+    return worldGenerate(w, stageMask, out_blocks);
+}
+
+int mmgen_world_reset(MmgenWorld* w)
+{
+    MMG_CUDA(cudaStreamSynchronize(w->stream));
+    std::fill(w->stage.begin(), w->stage.end(), 0);
+    if (w->d_counts) MMG_CUDA(cudaMemsetAsync(w->d_counts, 0, (size_t)w->n * 2 * sizeof(int), w->stream));
+    return 0;
+}
+
+int mmgen_world_create_for_region(int rx0, int rz0, int rnx, int rnz, MmgenWorld** out)
+{
+    if (rnx <= 0 || rnz <= 0 || !out)
+    {
+        g_lastError = "mmgen_world_create_for_region: bad arguments";
+        return 1;
+    }
+    // apron rule: fill R <= placements on R(+)3 <= erosion of every zone meeting R(+)3 <= layers on those zones (+)6
+    // <= heightfields on one more ring of chunks (the 1-block slope border of the outermost layers)
+    auto floorDiv = [](int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); };
+    const int zx0 = floorDiv(rx0 - 3, 12) * 12, zx1 = floorDiv(rx0 + rnx + 2, 12) * 12 + 12;
+    const int zz0 = floorDiv(rz0 - 3, 12) * 12, zz1 = floorDiv(rz0 + rnz + 2, 12) * 12 + 12;
+    if (mmgen_world_create(zx0 - 7, zz0 - 7, zx1 - zx0 + 14, zz1 - zz0 + 14, out)) return 1;
+    MmgenWorld* w = *out;
+    w->hasTarget = true;
+    w->tx0 = rx0 - w->cx0; w->tz0 = rz0 - w->cz0; w->tnx = rnx; w->tnz = rnz;
+    return 0;
+}
+
+int mmgen_world_window(MmgenWorld* w, int* out8)
+{
+    out8[0] = w->cx0; out8[1] = w->cz0; out8[2] = w->nx; out8[3] = w->nz;
+    out8[4] = w->hasTarget ? w->cx0 + w->tx0 : w->cx0; out8[5] = w->hasTarget ? w->cz0 + w->tz0 : w->cz0;
+    out8[6] = w->hasTarget ? w->tnx : w->nx; out8[7] = w->hasTarget ? w->tnz : w->nz;
+    return 0;
+}
+
+int mmgen_world_total_ms(MmgenWorld* w, float* out)
+{
+    MMG_CUDA(cudaStreamSynchronize(w->stream));
+    MMG_CUDA(cudaEventElapsedTime(out, w->ev[12], w->ev[13]));
+    return 0;
+}
+
+int mmgen_world_download_region_blocks(MmgenWorld* w, uint8_t* out_blocks)
+{
+    MMG_CUDA(cudaStreamSynchronize(w->stream));
+    if (!w->d_blocks)
+    {
+        g_lastError = "mmgen_world_download_region_blocks: nothing filled yet";
+        return 1;
+    }
+    const int tx0 = w->hasTarget ? w->tx0 : 0, tz0 = w->hasTarget ? w->tz0 : 0;
+    const int tnx = w->hasTarget ? w->tnx : w->nx, tnz = w->hasTarget ? w->tnz : w->nz;
+    MMG_CUDA(cudaMemcpy2D(out_blocks, (size_t)tnx * 98304, w->d_blocks + ((size_t)tz0 * w->nx + tx0) * 98304, (size_t)w->nx * 98304,
+                          (size_t)tnx * 98304, tnz, cudaMemcpyDeviceToHost));
     return 0;
 }
 

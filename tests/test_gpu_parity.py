@@ -72,6 +72,43 @@ def test_world_mode_vs_reference_golden(gen, mm, golden):
     world.close()
 
 
+def test_region_world_vs_reference_golden(gen, mm, golden):
+    """The apron rule: a world created for the 6x6 target region [3,9)^2 computes exactly the C2 window
+    and delivers the same blocks, both by download and by the host-delivery call."""
+    g = golden["g"]
+    world = gen.region_world(3, 3, 6, 6)
+    assert (world.cx0, world.cz0, world.nx, world.nz) == (-7, -7, 26, 26)
+    world.generate(mm.STAGE_ALL)
+    st = world.stages()
+    assert (st == 6).sum() == 36 and (st >= 4).sum() == 144
+    blocks = world.download_region_blocks()
+    assert np.array_equal(blocks, g["blocks"])
+    host = np.zeros_like(blocks)
+    world.reset()
+    assert world.stages().max() == 0
+    world.generate_to_host(host.ctypes.data, mm.STAGE_ALL)
+    assert np.array_equal(host, g["blocks"])
+    assert world.total_ms() > 0
+    world.close()
+
+
+def test_tiles_are_bit_identical_to_one_world(gen, mm):
+    """Multi-GPU tiling property on one GPU: the tiles of a region, generated independently, reproduce
+    the region generated as one world (checksums of the block volumes and the bytes themselves)."""
+    from mega_minecraft_b200 import tiling
+    region = (-5, 20, 10, 8)
+    whole = gen.region_world(*region)
+    whole.generate(mm.STAGE_ALL)
+    ref = whole.download_region_blocks().reshape(region[3], region[2], 16, 16, 384)
+    whole.close()
+    for t in tiling.tiles(*region, 4):
+        w = gen.region_world(*t)
+        w.generate(mm.STAGE_ALL)
+        b = w.download_region_blocks().reshape(t[3], t[2], 16, 16, 384)
+        w.close()
+        assert np.array_equal(b, ref[t[1] - region[1]:t[1] - region[1] + t[3], t[0] - region[0]:t[0] - region[0] + t[2]])
+
+
 # ------------------------------------------------------------------ against the oracle, other windows
 @pytest.mark.parametrize("biome", [1, 8, 9, 13, 16, 19, 23])
 def test_stage1_all_biomes_vs_oracle(gen, oracle, biome):
