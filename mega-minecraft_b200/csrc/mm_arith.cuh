@@ -11,6 +11,14 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// The simplex bodies are ~250 (2-D) / ~450 (3-D) instructions. Inlined at every call site the
+// cave and fill kernels grow to > 500 KB of SASS and stall on instruction fetch (ncu:
+// stalled_no_instruction 13.7 per issue, profiles/r01); as real functions each kernel holds one copy
+// per skew variant and fits the instruction cache. Same operations either way: results are identical.
+#ifndef MMG_NOISE_INLINE
+#define MMG_NOISE_INLINE __noinline__
+#endif
+
 namespace mmg {
 
 // ---------------------------------------------------------------- integer hash + minstd
@@ -83,7 +91,7 @@ __device__ __forceinline__ float sx_permute(float x) { return sx_mod289(fmaf(x, 
 // calls hoisted in front of the biome loop) compute fma(v.x, C1, v.y*C1) (true). The value only
 // feeds floor(), so the two differ only when v + s lands within an ulp of an integer.
 template <bool SKEW_X = false>
-__device__ __forceinline__ float simplex2_raw(float vx, float vy)
+__device__ MMG_NOISE_INLINE float simplex2_raw(float vx, float vy)
 {
     const float C0 = 0.211324865405187f, C1 = 0.366025403784439f, C2 = -0.577350269189626f, C3 = 0.024390243902439f;
     // i = floor(v + dot(v, C.yy)); dot = fma(v.y, C1, v.x*C1)
@@ -132,7 +140,7 @@ __device__ __forceinline__ float simplex2(float vx, float vy) { return 130.0f * 
 // through fbm<> compute fma(v.z, C, fma(v.y, C, v.x*C)) (false); direct simplex(vec3) calls compute
 // fma(v.z, C, fma(v.x, C, v.y*C)) (true). Only floor() sees the difference.
 template <bool SKEW_Y = false>
-__device__ __forceinline__ float simplex3_raw(float vx, float vy, float vz)
+__device__ MMG_NOISE_INLINE float simplex3_raw(float vx, float vy, float vz)
 {
     const float C = 1.0f / 3.0f, D = 1.0f / 6.0f;
     const float NZ = 0.142857142857f;           // n_

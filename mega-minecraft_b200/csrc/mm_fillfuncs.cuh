@@ -9,14 +9,17 @@ namespace mmg {
 
 // ------------------------------------------------------------------ 3-D Worley (rng.hpp:235-278)
 // hash at the LUSH_CAVES call site (biomeFuncs.hpp:661): fma(z, Kz, fma(y, Ky, x*Kx))
-__device__ __forceinline__ float worley3_lush(float px, float py, float pz)
+__device__ MMG_NOISE_INLINE float worley3_lush(float px, float py, float pz)
 {
     const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
     const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
     const float nfx = fx - px, nfy = fy - py, nfz = fz - pz;
     float d1 = FLT_MAX, d2 = FLT_MAX;
+#pragma unroll 1
     for (int x = -1; x <= 1; ++x)
+#pragma unroll 1
         for (int y = -1; y <= 1; ++y)
+#pragma unroll 1
             for (int z = -1; z <= 1; ++z)
             {
                 const float cx = (float)(ix + x), cy = (float)(iy + y), cz = (float)(iz + z);
@@ -123,7 +126,22 @@ __device__ __forceinline__ bool biome_post_process(uint8_t* block, int biome, in
 }
 
 // ------------------------------------------------------------------ biomeFuncs.hpp:592-707
-__device__ __forceinline__ bool cave_biome_post_process(uint8_t* block, int caveBiome, int wx, int y, int wz, int caveBottomDepth, int caveTopDepth)
+// second half of the LUSH_CAVES case of caveBiomeBlockPostProcess (biomeFuncs.hpp:653-668)
+__device__ __forceinline__ uint8_t lush_block(int wx, int y, int wz)
+{
+    const float nx = (float)wx * 0.025f, nz = (float)wz * 0.025f;
+    float ny = (float)y * 0.025f;
+    ny = ny + 192031.9821f;
+    const float ax = nx * 0.4f, ay = ny * 0.4f, az = nz * 0.4f;
+    const float o1 = fbm3<3, false>(ax, ay, az);
+    const float o2 = fbm3<3, true>(ax + 5923.45f, ay + 4129.42f, az + 5790.48f);
+    const float o3 = fbm3<3, true>(ax + 1765.68f, ay + 4704.36f, az + 5692.12f);
+    const float clay = worley3_lush(fmaf(o1, 2.f, nx), fmaf(o2, 2.f, ny), fmaf(o3, 2.f, nz));
+    return clay < 0.25f ? B_CLAY : B_MOSS;
+}
+
+__device__ __forceinline__ bool cave_biome_post_process(uint8_t* block, int caveBiome, int wx, int y, int wz, int caveBottomDepth, int caveTopDepth,
+                                                        bool* pendingLush)
 {
     if (caveBiome == CB_NONE) return false;
     const bool isTopBlock = caveBottomDepth == 0;
@@ -150,14 +168,10 @@ __device__ __forceinline__ bool cave_biome_post_process(uint8_t* block, int cave
         const float threshold = fmaf(simplex3<true>(nx, ny, nz), 4.5f, 1.5f);
         const float bd = (float)caveBottomDepth, td = (float)caveTopDepth;
         if (!(bd >= 0.f && bd <= threshold) && !(td >= 0.f && td <= threshold)) return false;
-        ny = ny + 192031.9821f;
-        const float ax = nx * 0.4f, ay = ny * 0.4f, az = nz * 0.4f;
-        const float o1 = fbm3<3, false>(ax, ay, az);
-        const float o2 = fbm3<3, true>(ax + 5923.45f, ay + 4129.42f, az + 5790.48f);
-        const float o3 = fbm3<3, true>(ax + 1765.68f, ay + 4704.36f, az + 5692.12f);
-        const float clay = worley3_lush(fmaf(o1, 2.f, nx), fmaf(o2, 2.f, ny), fmaf(o3, 2.f, nz));
-        *block = clay < 0.25f ? B_CLAY : B_MOSS;
-        return true;
+        // the clay / moss decision (3 x fbm3<3> + a 27-cell Worley) is needed by a few voxels per warp only:
+        // it is deferred so that the CTA can evaluate all of its pending voxels on adjacent lanes (lush_block)
+        *pendingLush = true;
+        return false;
     }
     case CB_WARPED_FOREST:
         if (!isTopBlock) return false;
@@ -173,10 +187,17 @@ __device__ __forceinline__ bool cave_biome_post_process(uint8_t* block, int cave
     return false;
 }
 
+// caveBiomeBlockPostProcess (above) only ever rewrites STONE, DEEPSLATE or BLACKSTONE, whatever the cave
+// biome: CRYSTAL_CAVES and LUSH_CAVES return at once for any other block, WARPED_FOREST and AMBER_FOREST
+// only map DEEPSLATE / BLACKSTONE. getCaveBiome has no side effects (its RNG is its own), so for every
+// other block the ~5 kFLOP cave-biome evaluation the reference performs per voxel cannot change the result.
+__device__ __forceinline__ bool needs_cave_biome(uint8_t block) { return block == B_STONE || block == B_DEEPSLATE || block == B_BLACKSTONE; }
+
 // ------------------------------------------------------------------ chunk.cu:1202-1380
 // weights[24], layersAndHeight[21] (20 layer starts + height), caveLayers[32] of the column
+// *pendingLush: the voxel is lush-cave rock within the moss depth; its block is lush_block(wx, y, wz)
 __device__ __forceinline__ uint8_t fill_place_block(const float* weights, const float* layersAndHeight, const CaveLayer* caveLayers, int y,
-                                       float height, int wx, int wz)
+                                       float height, int wx, int wz, bool* pendingLush)
 {
     if (y == 0) return B_BEDROCK;
     const float fy = (float)y;
@@ -203,10 +224,9 @@ __device__ __forceinline__ uint8_t fill_place_block(const float* weights, const 
         if (y <= cl.start) break;
         if (y <= cl.end)
         {
-            caveTopDepth = y - (cl.end + 1);
-            block = (y <= LAVA_LEVEL) ? B_LAVA : B_AIR;
-            cave_biome_post_process(&block, cave_biome(wx, y, wz, height, 190249401), wx, y, wz, caveBottomDepth, caveTopDepth);
-            return block;
+            // the reference evaluates getCaveBiome + caveBiomeBlockPostProcess here (chunk.cu:1243-1246);
+            // no cave biome changes AIR or LAVA (see needs_cave_biome), so neither is evaluated
+            return (y <= LAVA_LEVEL) ? B_LAVA : B_AIR;
         }
         caveTopDepth = y - (cl.end + 1);
     }
@@ -227,7 +247,8 @@ __device__ __forceinline__ uint8_t fill_place_block(const float* weights, const 
     block = thisLayer < 0 ? (uint8_t)B_SAVANNA_GRASS_BLOCK : c_materialInfos[thisLayer].block;
     if (isTopBlock && block == B_DIRT) block = c_biomeGrassBlock[randBiome];
     biome_post_process(&block, randBiome, wx, y, wz, height, isTopBlock);
-    cave_biome_post_process(&block, cave_biome(wx, y, wz, height, 190249401), wx, y, wz, caveBottomDepth, caveTopDepth);
+    if (needs_cave_biome(block))
+        cave_biome_post_process(&block, cave_biome(wx, y, wz, height, 190249401), wx, y, wz, caveBottomDepth, caveTopDepth, pendingLush);
     return block;
 }
 

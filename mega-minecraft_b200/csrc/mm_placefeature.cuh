@@ -109,7 +109,7 @@ __device__ __forceinline__ uint8_t random_crystal_block(float rand)
 }
 
 // featurePlacement.hpp:147-1107. Returns true and sets *out when the voxel belongs to the feature.
-__device__ __forceinline__ bool place_feature(const FeaturePlacement& fp, int wx, int wy, int wz, uint8_t* out)
+__device__ MMG_NOISE_INLINE bool place_feature(const FeaturePlacement& fp, int wx, int wy, int wz, uint8_t* out)
 {
     const int fx = wx - fp.x, fy = wy - fp.y, fz = wz - fp.z;
     V3 pos = v3((float)fx, (float)fy, (float)fz);
@@ -623,7 +623,7 @@ __device__ __forceinline__ bool place_feature(const FeaturePlacement& fp, int wx
 }
 
 // featurePlacement.hpp:1110-1380
-__device__ __forceinline__ bool place_cave_feature(const CaveFeaturePlacement& cp, int wx, int wy, int wz, uint8_t* out)
+__device__ MMG_NOISE_INLINE bool place_cave_feature(const CaveFeaturePlacement& cp, int wx, int wy, int wz, uint8_t* out)
 {
     const int lh = cp.layerHeight;
     const int fx = wx - cp.x, fy = wy - cp.y, fz = wz - cp.z;

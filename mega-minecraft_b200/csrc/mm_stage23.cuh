@@ -5,9 +5,10 @@
 // S2: one CTA per chunk; the 18x18 bordered heightfield is staged in shared memory straight from the
 //     resident height planes of the 3x3 chunk neighbourhood (no host gather, no 18x18 copy in HBM).
 //     FP32-bound (<= 55 simplex per column); algorithmic bytes 46 360 B/chunk.
-// S3: Jacobi relaxation over a 384x384 zone window, 34x34 shared tiles, 144 CTAs = one wave on 148
-//     SMs. Convergence is detected on the device (one flag per sweep) and polled once per batch of
-//     sweeps instead of after every sweep. Pure max/min/sub: bound by L2 bandwidth and launch latency;
+// S3: Jacobi relaxation over 384x384 zone windows, 34x34 shared tiles, 144 CTAs per zone and many
+//     zones per launch (blockIdx.z), sized so the planes of a batch stay in the 126 MB L2. Convergence
+//     is detected on the device (one flag per sweep, shared by the batch) and polled once per group
+//     of sweeps instead of after every sweep of every zone. Pure max/min/sub: bound by L2 bandwidth and launch latency;
 //     algorithmic bytes per sweep 3 planes x 589 824 B.
 #pragma once
 #include "mm_common.cuh"
@@ -106,28 +107,41 @@ __global__ void __launch_bounds__(256) k_layers(const int* __restrict__ chunkLis
 // ---------------------------------------------------------------- S3
 constexpr int kErosionSide = 384, kErosionCols = kErosionSide * kErosionSide;
 
+constexpr int kZonePlanes = 12;   // per zone: [0..8] gathered planes, [9] ping-pong scratch, [10..11] accumulated heights
+
 // gather: zone planes[9][384][384] from chunk-major layers/height of the 24x24-chunk window whose
-// lower corner is chunk (zx0, zz0) in world raster coordinates (copyLayers(..., true), chunk.cu:603-656)
-__global__ void k_zone_gather(const float* __restrict__ layers, const float* __restrict__ height, float* __restrict__ planes,
-                              int zx0, int zz0, int nx)
+// lower corner is chunk zoneCorner[blockIdx.z] in window raster coordinates (copyLayers(..., true), chunk.cu:603-656)
+__global__ void k_zone_gather(const float* __restrict__ layers, const float* __restrict__ height, float* __restrict__ zones,
+                              const int2* __restrict__ zoneCorner, int nx)
 {
+    const int2 zc = zoneCorner[blockIdx.z];
+    float* planes = zones + (size_t)blockIdx.z * kZonePlanes * kErosionCols;
     const int gx = blockIdx.x * 32 + threadIdx.x, gz = blockIdx.y * 32 + threadIdx.y;
-    const int chunk = (zx0 + (gx >> 4)) + (zz0 + (gz >> 4)) * nx;
+    const int chunk = (zc.x + (gx >> 4)) + (zc.y + (gz >> 4)) * nx;
     const int idx = (gx & 15) + 16 * (gz & 15);
     const int col = gx + kErosionSide * gz;
 #pragma unroll
     for (int l = 0; l < NUM_ERODED; ++l)
         planes[(size_t)l * kErosionCols + col] = layers[(size_t)chunk * (NUM_MATERIALS * 256) + (NUM_STRATIFIED + l) * 256 + idx];
     planes[(size_t)NUM_ERODED * kErosionCols + col] = height[(size_t)chunk * 256 + idx];
+    planes[(size_t)10 * kErosionCols + col] = 0.0f;    // accumulated heights start at 0 (chunk.cu:680)
 }
 
-// one Jacobi sweep of layer `layer`: reads start plane sIn (+ accumIn on the first sweep), writes sOut
-__global__ void __launch_bounds__(1024) k_erode_sweep(const float* __restrict__ sIn, float* __restrict__ sOut,
-                                                      const float* __restrict__ eUp, const float* __restrict__ accumIn,
-                                                      float* __restrict__ accumOut, float rep, int isFirst, int* __restrict__ changedFlag)
+// one Jacobi sweep of one loose layer over every zone of the batch (blockIdx.z): reads the start plane
+// pIn (+ accumulated heights on the layer's first sweep), writes pOut. Plane roles are indices into the
+// zone's 12 planes; they swap in lockstep for all zones. A zone that has converged is a fixed point of
+// the sweep, so sweeping it again (while other zones of the batch still move) changes nothing.
+__global__ void __launch_bounds__(1024) k_erode_sweep(float* __restrict__ zones, int pIn, int pOut, int pUp, int pAccIn, int pAccOut,
+                                                      float rep, int isFirst, int* __restrict__ changedFlag)
 {
     __shared__ float shS[34 * 34];
     __shared__ float shE[34 * 34];
+    float* zone = zones + (size_t)blockIdx.z * kZonePlanes * kErosionCols;
+    const float* sIn = zone + (size_t)pIn * kErosionCols;
+    float* sOut = zone + (size_t)pOut * kErosionCols;
+    const float* eUp = zone + (size_t)pUp * kErosionCols;
+    const float* accumIn = zone + (size_t)pAccIn * kErosionCols;
+    float* accumOut = zone + (size_t)pAccOut * kErosionCols;
     const int lx = threadIdx.x, lz = threadIdx.y, lid = lx + 32 * lz;
     const int bx0 = blockIdx.x * 32, bz0 = blockIdx.y * 32;
     for (int t = lid; t < 34 * 34; t += 1024)
@@ -172,11 +186,13 @@ __global__ void __launch_bounds__(1024) k_erode_sweep(const float* __restrict__ 
 
 // scatter the centre 12x12 chunks back (copyLayers(..., false)) into the eroded layer set and apply
 // fixBackwardStratifiedLayers (chunk.cu:725-749); the stratified layers are copied through.
-__global__ void k_zone_scatter(const float* __restrict__ planes, const float* __restrict__ layersIn, float* __restrict__ layersOut,
-                               int zx0, int zz0, int nx)
+__global__ void k_zone_scatter(const float* __restrict__ zones, const float* __restrict__ layersIn, float* __restrict__ layersOut,
+                               const int2* __restrict__ zoneCorner, int nx)
 {
+    const int2 zc = zoneCorner[blockIdx.z];
+    const float* planes = zones + (size_t)blockIdx.z * kZonePlanes * kErosionCols;
     const int gx = 96 + blockIdx.x * 32 + threadIdx.x, gz = 96 + blockIdx.y * 32 + threadIdx.y;   // centre 192x192
-    const int chunk = (zx0 + (gx >> 4)) + (zz0 + (gz >> 4)) * nx;
+    const int chunk = (zc.x + (gx >> 4)) + (zc.y + (gz >> 4)) * nx;
     const int idx = (gx & 15) + 16 * (gz & 15);
     const int col = gx + kErosionSide * gz;
     const float* in = layersIn + (size_t)chunk * (NUM_MATERIALS * 256) + idx;

@@ -16,7 +16,7 @@ namespace mmg {
 // ---------------------------------------------------------------- cave biome (biomeFuncs.hpp:135-220)
 struct CaveBiomeNoise { float v[4]; };   // none, shallow, warped, rocky
 
-__device__ __forceinline__ CaveBiomeNoise cave_biome_noise(int x, int y, int z, float maxHeight)
+__device__ MMG_NOISE_INLINE CaveBiomeNoise cave_biome_noise(int x, int y, int z, float maxHeight)
 {
     const float px = (float)x, py = (float)y, pz = (float)z;
     const float qx = px * 0.0470f, qy = py * 0.0470f, qz = pz * 0.0470f;
@@ -59,14 +59,17 @@ __device__ __forceinline__ int cave_biome(int x, int y, int z, float maxHeight, 
 
 // ---------------------------------------------------------------- specialCaveNoise (rng.hpp:282-320)
 // hash (rng.hpp:148-155) at this call site: fma(z, Kz, fma(x, Kx, y*Ky))
-__device__ __forceinline__ float special_cave_noise(float px, float py, float pz)
+__device__ MMG_NOISE_INLINE float special_cave_noise(float px, float py, float pz)
 {
     const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
     const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
     const float nfx = fx - px, nfy = fy - py, nfz = fz - pz;
     float d1 = FLT_MAX, d2 = FLT_MAX, d3 = FLT_MAX;
+#pragma unroll 1
     for (int x = -1; x <= 1; ++x)
+#pragma unroll 1
         for (int y = -1; y <= 1; ++y)
+#pragma unroll 1
             for (int z = -1; z <= 1; ++z)
             {
                 const float cx = (float)(ix + x), cy = (float)(iy + y), cz = (float)(iz + z);
@@ -105,30 +108,78 @@ __device__ __forceinline__ Ravine ravine_column(int wx, int wz, float obw)
     return r;
 }
 
-// chunk.cu:755-810
-__device__ __forceinline__ bool cave_at_block(int wx, int y, int wz, float maxHeight, float obw, const Ravine& rav)
+// jitter of one Worley cell (rand3From3 of the integer cell corner, rng.hpp:148-155, 296-300)
+__device__ __forceinline__ void cave_cell_jitter(int icx, int icy, int icz, float* jx, float* jy, float* jz)
 {
-    if (y == 0) return false;
+    const float cx = (float)icx, cy = (float)icy, cz = (float)icz;
+    *jx = hash_fract(fmaf(cz, 402.98f, fmaf(cx, 238.68f, cy * 491.28f)));
+    *jy = hash_fract(fmaf(cz, 747.42f, fmaf(cx, 654.37f, cy * 560.45f)));
+    *jz = hash_fract(fmaf(cz, 674.81f, fmaf(cx, 640.88f, cy * 151.81f)));
+}
+
+// specialCaveNoise with the cell jitters taken from a table covering cells [box, box + kCaveBox)^3 that the
+// CTA filled once (a jitter depends only on the integer cell, and the voxels of one column share a few
+// dozen cells; the reference recomputes 27 x 3 sin() hashes per voxel). Cells outside the table are
+// computed in place. Same cells, same order, same comparisons as special_cave_noise.
+constexpr int kCaveBox = 6;
+__device__ __forceinline__ float special_cave_noise_cached(float px, float py, float pz, int bx, int by, int bz, const float* shJit)
+{
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    const float nfx = fx - px, nfy = fy - py, nfz = fz - pz;
+    float d1 = FLT_MAX, d2 = FLT_MAX, d3 = FLT_MAX;
+#pragma unroll 1
+    for (int x = -1; x <= 1; ++x)
+#pragma unroll 1
+        for (int y = -1; y <= 1; ++y)
+#pragma unroll
+            for (int z = -1; z <= 1; ++z)
+            {
+                const int ux = ix + x - bx, uy = iy + y - by, uz = iz + z - bz;
+                float jx, jy, jz;
+                if ((unsigned)ux < (unsigned)kCaveBox && (unsigned)uy < (unsigned)kCaveBox && (unsigned)uz < (unsigned)kCaveBox)
+                {
+                    const int c = (ux * kCaveBox + uy) * kCaveBox + uz;
+                    jx = shJit[c]; jy = shJit[c + kCaveBox * kCaveBox * kCaveBox]; jz = shJit[c + 2 * kCaveBox * kCaveBox * kCaveBox];
+                }
+                else
+                    cave_cell_jitter(ix + x, iy + y, iz + z, &jx, &jy, &jz);
+                const float dx = nfx + (jx + (float)x), dy = nfy + (jy + (float)y), dz = nfz + (jz + (float)z);
+                const float dist = sqrtf(fmaf(dz, dz, fmaf(dx, dx, dy * dy)));
+                if (dist < d1) { d3 = d2; d2 = d1; d1 = dist; }
+                else if (dist < d2) { d3 = d2; d2 = dist; }
+                else if (dist < d3) { d3 = dist; }
+            }
+    return d3 / d1 + -1.0f;
+}
+
+// chunk.cu:755-810, first half: everything up to the cave-noise threshold. Returns 0 = solid, 1 = air,
+// 2 = undecided: the warped specialCaveNoise at (*px, *py, *pz) has to be compared with *thr.
+__device__ __forceinline__ int cave_threshold(int wx, int y, int wz, float maxHeight, float obw, float* thrOut, float* px, float* py, float* pz)
+{
+    if (y == 0) return 0;
     const int hi = (int)maxHeight;
-    if (y > (hi > SEA_LEVEL ? hi : SEA_LEVEL)) return true;
+    if (y > (hi > SEA_LEVEL ? hi : SEA_LEVEL)) return 1;
     const float fy = (float)y;
     const float npx = (float)wx * 0.0050f, npy = fy * 0.0050f, npz = (float)wz * 0.0050f;
     const float topRatio = ss_t((fmaf(obw, 50.f, fy) + -142.f) / (95.f - 142.f));
     const float bottomRatio = ss_t((fy + -5.f) / (20.f - 5.f));
-    const float ax = npx * 0.8000f, ay = npy * 0.8000f, az = npz * 0.8000f;
-    const float o1 = fbm3<5>(ax, ay, az);
-    const float o2 = fbm3<5>(ax + 5923.45f, ay + 4129.42f, az + 5790.48f);
-    const float o3 = fbm3<5>(ax + 1765.68f, ay + 4704.36f, az + 5692.12f);
-    const float caveNoise = special_cave_noise(fmaf(o1, 1.8f, npx), fmaf(npy, 1.6f, o2 * 1.8f), fmaf(o3, 1.8f, npz));
     float thr = fmaf(fbm3<4>(npx * 4.f, npy * 4.f, npz * 4.f), 0.12f, 0.24f);
     const float huge = ss_t((fbm3<4>(npx * 0.0700f, npy * 0.0700f, npz * 0.0700f) + -0.2f) / (0.4f - 0.2f));
     thr = thr * fmaf(huge, 1.4f, 1.f);
     thr = (fmaf(bottomRatio, 0.7f, 0.3f) * topRatio) * thr;
-    if (thr > 0.04f && caveNoise < thr) return true;
-    if (rav.active && (rav.top - rav.depth) < fy) return true;
-    return false;
+    // the reference always evaluates the warped specialCaveNoise (15 simplex + 27 hashed cells) and then
+    // tests `thr > 0.04 && caveNoise < thr` (chunk.cu:776-783); where the threshold test alone fails
+    // (topRatio -> 0 towards y = 142 - 50 obw) the noise cannot matter and is not evaluated
+    if (!(thr > 0.04f)) return 0;
+    const float ax = npx * 0.8000f, ay = npy * 0.8000f, az = npz * 0.8000f;
+    const float o1 = fbm3<5>(ax, ay, az);
+    const float o2 = fbm3<5>(ax + 5923.45f, ay + 4129.42f, az + 5790.48f);
+    const float o3 = fbm3<5>(ax + 1765.68f, ay + 4704.36f, az + 5692.12f);
+    *px = fmaf(o1, 1.8f, npx); *py = fmaf(npy, 1.6f, o2 * 1.8f); *pz = fmaf(o3, 1.8f, npz);
+    *thrOut = thr;
+    return 2;
 }
-
 
 struct CaveColumn { float obw, ravTop, ravDepth; int ravActive; };
 
@@ -148,13 +199,15 @@ __global__ void __launch_bounds__(256) k_cave_columns(const int* __restrict__ ch
     cols[(size_t)li * 256 + idx] = c;
 }
 
-__global__ void __launch_bounds__(128) k_caves(const int* __restrict__ chunkList, const int2* __restrict__ origins,
+__global__ void __launch_bounds__(128, 8) k_caves(const int* __restrict__ chunkList, const int2* __restrict__ origins,
                                                const float* __restrict__ heightfield, const CaveColumn* __restrict__ cols,
                                                CaveLayer* __restrict__ caveLayers)
 {
     __shared__ unsigned int shFilled[13];     // bit y = 1 if solid; word 12 = 0 (y = 384 is "not filled")
     __shared__ int shFlips[2 * MAX_CAVE_LAYERS];
     __shared__ int shNumFlips;
+    __shared__ int shBox[3];
+    __shared__ float shJit[3 * kCaveBox * kCaveBox * kCaveBox];
     const int li = blockIdx.x >> 8, idx = blockIdx.x & 255;
     const int chunk = chunkList ? chunkList[li] : li;
     const int2 o = origins[chunk];
@@ -165,13 +218,47 @@ __global__ void __launch_bounds__(128) k_caves(const int* __restrict__ chunkList
     rav.active = cc.ravActive != 0; rav.top = cc.ravTop; rav.depth = cc.ravDepth;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) shFilled[12] = 0u;
-#pragma unroll
+    const int hi = (int)maxHeight, yTop = hi > SEA_LEVEL ? hi : SEA_LEVEL;   // above this every voxel is air
+#pragma unroll 1
     for (int k = 0; k < 3; ++k)
     {
+        if (128 * k > yTop)
+        {
+            if (lane == 0) shFilled[4 * k + warp] = 0u;      // the whole slab is air (chunk.cu:761-764)
+            continue;
+        }
         const int y = tid + 128 * k;
-        const bool air = cave_at_block(wx, y, wz, maxHeight, cc.obw, rav);
+        float thr = 0.f, px = 0.f, py = 0.f, pz = 0.f;
+        const int st = cave_threshold(wx, y, wz, maxHeight, cc.obw, &thr, &px, &py, &pz);
+        // cells [box, box + kCaveBox)^3 cover the 3x3x3 neighbourhoods of (nearly) all undecided voxels
+        if (tid < 3) shBox[tid] = INT_MAX;
+        __syncthreads();
+        if (st == 2)
+        {
+            atomicMin(&shBox[0], (int)floorf(px) - 1);
+            atomicMin(&shBox[1], (int)floorf(py) - 1);
+            atomicMin(&shBox[2], (int)floorf(pz) - 1);
+        }
+        __syncthreads();
+        const int bx = shBox[0], by = shBox[1], bz = shBox[2];
+        if (bx != INT_MAX)
+        {
+            constexpr int N3 = kCaveBox * kCaveBox * kCaveBox;
+            for (int c = tid; c < N3; c += 128)
+            {
+                const int uz = c % kCaveBox, uy = (c / kCaveBox) % kCaveBox, ux = c / (kCaveBox * kCaveBox);
+                float jx, jy, jz;
+                cave_cell_jitter(bx + ux, by + uy, bz + uz, &jx, &jy, &jz);
+                shJit[c] = jx; shJit[c + N3] = jy; shJit[c + 2 * N3] = jz;
+            }
+        }
+        __syncthreads();
+        bool air = st == 1;
+        if (st == 2) air = special_cave_noise_cached(px, py, pz, bx, by, bz, shJit) < thr;
+        if (st != 1 && !air) air = rav.active && (rav.top - rav.depth) < (float)y && y != 0;   // chunk.cu:785-808
         const unsigned int bits = __ballot_sync(0xffffffffu, !air);
         if (lane == 0) shFilled[4 * k + warp] = bits;
+        __syncthreads();      // shBox / shJit are reused by the next slab
     }
     __syncthreads();
     CaveLayer* out = caveLayers + ((size_t)chunk * 256 + idx) * MAX_CAVE_LAYERS;

@@ -8,10 +8,9 @@
 // S5b  k_gather_features: one CTA per chunk to fill; concatenates the 49 neighbour lists in the
 //      reference's fixed order up to the caps (2048 / 4096) and reduces the y-bounds over the whole
 //      untruncated set, as the host loop at chunk.cu:1555-1570 does.
-// S6   k_fill: one CTA per column (384 threads = 384 voxels, y fastest), column inputs staged in
-//      shared memory; a warp stores 32 consecutive block IDs. The reference launches one such grid
-//      PER CHUNK; here one launch covers every chunk of the batch.
-// S6b  k_decorators: the reference's sequential per-chunk RNG walk, one thread per chunk.
+// S6   k_fill_terrain / k_fill_lush / k_fill_features (see below). The reference launches one kernFill
+//      grid PER CHUNK; here one launch of each covers every chunk of the batch.
+// S6b  k_decorators: the reference's sequential per-chunk RNG walk, parallel over columns by minstd skip-ahead.
 #pragma once
 #include "mm_common.cuh"
 #include "mm_featurefuncs.cuh"
@@ -154,49 +153,111 @@ __global__ void __launch_bounds__(256) k_feature_placements(const int* __restric
 
 struct GatherInfo { int nF, nCF; int fb0, fb1, cfb0, cfb1; };
 
+// Position of this thread's kept entry among the kept entries of the whole CTA, in thread order
+// (= list order: the first feature in list order that contains a voxel wins, chunk.cu:1444-1500).
+// All threads of the CTA call it; *total = kept entries of the round. shWarp: one int per warp.
+__device__ __forceinline__ int block_ordered_offset(bool keep, int* shWarp, int* total)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (lane == 0) shWarp[warp] = __popc(m);
+    __syncthreads();
+    int off = 0, tot = 0;
+    for (int w = 0; w < nw; ++w)
+    {
+        const int c = shWarp[w];
+        off += (w < warp) ? c : 0;
+        tot += c;
+    }
+    __syncthreads();
+    *total = tot;
+    return off + __popc(m & ((1u << lane) - 1u));
+}
+
+// does a feature at (px, pz) with horizontal reach r touch the 16x16 footprint whose corner is (ox, oz)?
+__device__ __forceinline__ bool reach_hits_chunk(int px, int pz, int r, int ox, int oz)
+{
+    return px + r >= ox && px - r <= ox + 15 && pz + r >= oz && pz - r <= oz + 15;
+}
+
 // chunk.cu:1158-1187 + 1555-1578. fillList: chunks to gather for (world raster indices).
-__global__ void __launch_bounds__(256) k_gather_features(const int* __restrict__ fillList, const FeaturePlacement* __restrict__ features,
+// The 49 neighbour lists are concatenated in the reference's order and truncated at its caps
+// (2048 / 4096) exactly as the reference does; of that list only the placements whose horizontal
+// reach (c_featureReach) touches this chunk are kept, in order. The reference scans all of them per
+// voxel; the dropped ones cannot contain a voxel of this chunk, so the blocks are identical.
+__global__ void __launch_bounds__(256) k_gather_features(const int* __restrict__ fillList, const int2* __restrict__ origins,
+                                                         const FeaturePlacement* __restrict__ features,
                                                          const CaveFeaturePlacement* __restrict__ caveFeatures, const int* __restrict__ counts,
                                                          int nx, FeaturePlacement* __restrict__ gF, CaveFeaturePlacement* __restrict__ gCF,
                                                          GatherInfo* __restrict__ info)
 {
-    __shared__ int shMin[2], shMax[2];
+    __shared__ int shMin[2], shMax[2], shWarp[8];
     const int li = blockIdx.x, chunk = fillList[li];
     const int tid = threadIdx.x;
     if (tid < 2) { shMin[tid] = 384; shMax[tid] = -1; }
-    __syncthreads();
-    int baseF = 0, baseC = 0;
+    const int2 o = origins[chunk];
+    int baseF = 0, baseC = 0, outF = 0, outC = 0;
     int mnF = 384, mxF = -1, mnC = 384, mxC = -1;
+    FeaturePlacement* dstF = gF + (size_t)li * MAX_FEATURES;
+    CaveFeaturePlacement* dstC = gCF + (size_t)li * MAX_CAVE_FEATURES;
     for (int k = 0; k < 49; ++k)
     {
+        if (baseF >= MAX_FEATURES && baseC >= MAX_CAVE_FEATURES) break;
         const int nchunk = chunk + c_gatherOffsets[k][0] + c_gatherOffsets[k][1] * nx;
-        const int nf = counts[2 * nchunk], nc = counts[2 * nchunk + 1];
+        const int nf = min(counts[2 * nchunk], MAX_FEATURES - baseF), nc = min(counts[2 * nchunk + 1], MAX_CAVE_FEATURES - baseC);
         const FeaturePlacement* sf = features + (size_t)nchunk * kMaxOwnFeatures;
         const CaveFeaturePlacement* sc = caveFeatures + (size_t)nchunk * kMaxOwnCaveFeatures;
-        for (int i = tid; i < nf; i += 256)
+        for (int i0 = 0; i0 < nf; i0 += 256)
         {
-            const FeaturePlacement p = sf[i];
-            if (baseF + i < MAX_FEATURES) gF[(size_t)li * MAX_FEATURES + baseF + i] = p;
-            mnF = min(mnF, p.y + c_featureHeightBounds[p.feature][0]);
-            mxF = max(mxF, p.y + c_featureHeightBounds[p.feature][1]);
+            const int i = i0 + tid;
+            FeaturePlacement p;
+            bool keep = false;
+            if (i < nf)
+            {
+                p = sf[i];
+                keep = reach_hits_chunk(p.x, p.z, c_featureReach[p.feature], o.x, o.y);
+            }
+            int total;
+            const int off = block_ordered_offset(keep, shWarp, &total);
+            if (keep)
+            {
+                dstF[outF + off] = p;
+                mnF = min(mnF, p.y + c_featureHeightBounds[p.feature][0]);
+                mxF = max(mxF, p.y + c_featureHeightBounds[p.feature][1]);
+            }
+            outF += total;
         }
-        for (int i = tid; i < nc; i += 256)
+        for (int i0 = 0; i0 < nc; i0 += 256)
         {
-            const CaveFeaturePlacement p = sc[i];
-            if (baseC + i < MAX_CAVE_FEATURES) gCF[(size_t)li * MAX_CAVE_FEATURES + baseC + i] = p;
-            mnC = min(mnC, p.y + c_caveFeatureHeightBounds[p.feature][0]);
-            mxC = max(mxC, p.y + p.layerHeight + c_caveFeatureHeightBounds[p.feature][1]);
+            const int i = i0 + tid;
+            CaveFeaturePlacement p;
+            bool keep = false;
+            if (i < nc)
+            {
+                p = sc[i];
+                keep = reach_hits_chunk(p.x, p.z, c_caveFeatureReach[p.feature], o.x, o.y);
+            }
+            int total;
+            const int off = block_ordered_offset(keep, shWarp, &total);
+            if (keep)
+            {
+                dstC[outC + off] = p;
+                mnC = min(mnC, p.y + c_caveFeatureHeightBounds[p.feature][0]);
+                mxC = max(mxC, p.y + p.layerHeight + c_caveFeatureHeightBounds[p.feature][1]);
+            }
+            outC += total;
         }
-        baseF += nf;
-        baseC += nc;
+        baseF += counts[2 * nchunk];
+        baseC += counts[2 * nchunk + 1];
     }
+    __syncthreads();
     atomicMin(&shMin[0], mnF); atomicMax(&shMax[0], mxF);
     atomicMin(&shMin[1], mnC); atomicMax(&shMax[1], mxC);
     __syncthreads();
     if (tid == 0)
     {
         GatherInfo gi;
-        gi.nF = min(baseF, MAX_FEATURES); gi.nCF = min(baseC, MAX_CAVE_FEATURES);
+        gi.nF = outF; gi.nCF = outC;
         gi.fb0 = shMin[0]; gi.fb1 = shMax[0]; gi.cfb0 = shMin[1]; gi.cfb1 = shMax[1];
         info[li] = gi;
     }
@@ -210,7 +271,7 @@ __global__ void k_gather_info(const FeaturePlacement* __restrict__ gF, const Cav
     const int li = blockIdx.x, tid = threadIdx.x;
     if (tid < 2) { shMin[tid] = 384; shMax[tid] = -1; }
     __syncthreads();
-    const int nf = numFeatures[2 * li], nc = numFeatures[2 * li + 1];
+    const int nf = min(numFeatures[2 * li], MAX_FEATURES), nc = min(numFeatures[2 * li + 1], MAX_CAVE_FEATURES);
     int mnF = 384, mxF = -1, mnC = 384, mxC = -1;
     for (int i = tid; i < nf; i += blockDim.x)
     {
@@ -230,42 +291,177 @@ __global__ void k_gather_info(const FeaturePlacement* __restrict__ gF, const Cav
     if (tid == 0)
     {
         GatherInfo gi;
-        gi.nF = min(nf, MAX_FEATURES); gi.nCF = min(nc, MAX_CAVE_FEATURES);
+        gi.nF = nf; gi.nCF = nc;
         gi.fb0 = shMin[0]; gi.fb1 = shMax[0]; gi.cfb0 = shMin[1]; gi.cfb1 = shMax[1];
         info[li] = gi;
     }
 }
 
-// kernFill (chunk.cu:1382-1510). fillList[li] = chunk index into the resident planes (or li itself);
-// gathered lists are indexed by li with the given strides.
-__global__ void __launch_bounds__(384) k_fill(const int* __restrict__ fillList, const int2* __restrict__ origins,
-                                              const float* __restrict__ heightfield, const float* __restrict__ biomeWeights,
-                                              const float* __restrict__ layers, const CaveLayer* __restrict__ caveLayers,
-                                              const FeaturePlacement* __restrict__ gF, const CaveFeaturePlacement* __restrict__ gCF,
-                                              const GatherInfo* __restrict__ info, int strideF, int strideCF, uint8_t* __restrict__ blocks)
+// kernFill (chunk.cu:1382-1510) as three kernels over one batch of chunks. fillList[li] = chunk index into
+// the resident planes (or li itself); gathered lists are indexed by li with the given strides.
+//   k_fill_terrain   chunkFillPlaceBlock for every voxel: one CTA per 128-voxel segment of a column
+//                    (y fastest => a warp stores 32 consecutive block IDs), three segments per column;
+//                    segments above the terrain and the sea are stored as AIR without further work.
+//                    Voxels that need the LUSH_CAVES clay / moss decision are queued instead of decided.
+//   k_fill_lush      decides the queued voxels, one per thread (they are rare and scattered: evaluated in
+//                    place they would occupy 3-4 lanes of a warp for a 27-cell Worley + 9 simplex).
+//   k_fill_features  the placement scan: per column segment, the chunk's lists are reduced to the
+//                    placements whose horizontal reach and y range cover the segment (ordered compaction
+//                    into shared memory), so a voxel tests a few candidates instead of up to 2048 + 4096.
+// The reference decides terrain and features in one pass per voxel; the feature test only looks at
+// whether the terrain block is AIR, which the lush decision does not change, so the order
+// terrain -> lush -> features gives the same blocks.
+constexpr int kFillSeg = 128;
+constexpr int kColCapF = 512, kColCapC = 1024;   // candidates of one column segment kept in shared memory
+constexpr int kLushQueueCap = 1 << 22;           // queued voxels per fill batch (overflow is decided in place)
+
+__global__ void __launch_bounds__(kFillSeg, 8) k_fill_terrain(const int* __restrict__ fillList, const int2* __restrict__ origins,
+                                                              const float* __restrict__ heightfield, const float* __restrict__ biomeWeights,
+                                                              const float* __restrict__ layers, const CaveLayer* __restrict__ caveLayers,
+                                                              uint8_t* __restrict__ blocks, uint2* __restrict__ lushQueue, int* __restrict__ lushCount)
 {
     __shared__ float shW[NUM_BIOMES];
     __shared__ float shLH[NUM_MATERIALS + 1];
     __shared__ CaveLayer shCL[MAX_CAVE_LAYERS];
-    const int li = blockIdx.x >> 8, idx = blockIdx.x & 255;
+    const int seg = blockIdx.x % 3, col = blockIdx.x / 3;
+    const int li = col >> 8, idx = col & 255;
     const int chunk = fillList ? fillList[li] : li;
-    const int y = threadIdx.x;
-    if (y < NUM_BIOMES) shW[y] = biomeWeights[(size_t)chunk * (NUM_BIOMES * 256) + y * 256 + idx];
-    else if (y < NUM_BIOMES + NUM_MATERIALS) shLH[y - NUM_BIOMES] = layers[(size_t)chunk * (NUM_MATERIALS * 256) + (y - NUM_BIOMES) * 256 + idx];
-    else if (y == NUM_BIOMES + NUM_MATERIALS) shLH[NUM_MATERIALS] = heightfield[(size_t)chunk * 256 + idx];
-    else if (y < NUM_BIOMES + NUM_MATERIALS + 1 + MAX_CAVE_LAYERS)
-        shCL[y - (NUM_BIOMES + NUM_MATERIALS + 1)] = caveLayers[((size_t)chunk * 256 + idx) * MAX_CAVE_LAYERS + (y - (NUM_BIOMES + NUM_MATERIALS + 1))];
-    __syncthreads();
+    const int t = threadIdx.x, y0 = seg * kFillSeg, y = y0 + t;
+    const float height = heightfield[(size_t)chunk * 256 + idx];
+    uint8_t* out = blocks + (size_t)chunk * 98304 + (size_t)idx * 384 + y;
+    if ((float)y0 > height && y0 > SEA_LEVEL)
+    {
+        *out = B_AIR;      // chunkFillPlaceBlock's first exit (chunk.cu:1213-1217) for the whole segment
+        return;
+    }
+    if (t < NUM_BIOMES) shW[t] = biomeWeights[(size_t)chunk * (NUM_BIOMES * 256) + t * 256 + idx];
+    else if (t < NUM_BIOMES + NUM_MATERIALS) shLH[t - NUM_BIOMES] = layers[(size_t)chunk * (NUM_MATERIALS * 256) + (t - NUM_BIOMES) * 256 + idx];
+    else if (t == NUM_BIOMES + NUM_MATERIALS) shLH[NUM_MATERIALS] = height;
+    else if (t < NUM_BIOMES + NUM_MATERIALS + 1 + MAX_CAVE_LAYERS)
+        shCL[t - (NUM_BIOMES + NUM_MATERIALS + 1)] = caveLayers[((size_t)chunk * 256 + idx) * MAX_CAVE_LAYERS + (t - (NUM_BIOMES + NUM_MATERIALS + 1))];
     const int2 o = origins[chunk];
     const int wx = o.x + (idx & 15), wz = o.y + (idx >> 4);
-    const float height = shLH[NUM_MATERIALS];
-    uint8_t block = fill_place_block(shW, shLH, shCL, y, height, wx, wz);
+    __syncthreads();
+    bool lush = false;
+    uint8_t block = fill_place_block(shW, shLH, shCL, y, height, wx, wz, &lush);
+    // warp-aggregated append of the pending voxels
+    const unsigned m = __ballot_sync(0xffffffffu, lush);
+    if (m)
+    {
+        const int lane = t & 31, leader = __ffs(m) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(lushCount, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (lush)
+        {
+            const int slot = base + __popc(m & ((1u << lane) - 1u));
+            if (slot < kLushQueueCap) lushQueue[slot] = make_uint2((unsigned)chunk, (unsigned)(idx * 384 + y));
+            else block = lush_block(wx, y, wz);
+        }
+    }
+    *out = block;
+}
+
+__global__ void __launch_bounds__(128) k_fill_lush(const int2* __restrict__ origins, const uint2* __restrict__ lushQueue,
+                                                   const int* __restrict__ lushCount, uint8_t* __restrict__ blocks)
+{
+    const int n = min(*lushCount, kLushQueueCap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const uint2 e = lushQueue[i];
+        const int chunk = (int)e.x, idx = (int)e.y / 384, y = (int)e.y % 384;
+        const int2 o = origins[chunk];
+        blocks[(size_t)chunk * 98304 + e.y] = lush_block(o.x + (idx & 15), y, o.y + (idx >> 4));
+    }
+}
+
+// a placement that can touch this column segment: inclusive y range, index into the chunk's list
+struct Cand { short lo, hi; unsigned short idx, canReplace; };
+
+__global__ void __launch_bounds__(kFillSeg, 8) k_fill_features(const int* __restrict__ fillList, const int2* __restrict__ origins,
+                                                               const FeaturePlacement* __restrict__ gF, const CaveFeaturePlacement* __restrict__ gCF,
+                                                               const GatherInfo* __restrict__ info, int strideF, int strideCF,
+                                                               uint8_t* __restrict__ blocks)
+{
+    __shared__ Cand shCandF[kColCapF], shCandC[kColCapC];
+    __shared__ int shWarp[kFillSeg / 32];
+    const int seg = blockIdx.x % 3, col = blockIdx.x / 3;
+    const int li = col >> 8, idx = col & 255;
+    const int chunk = fillList ? fillList[li] : li;
+    const int t = threadIdx.x, y0 = seg * kFillSeg, y1 = y0 + kFillSeg - 1, y = y0 + t;
     const GatherInfo gi = info[li];
+    const bool segF = gi.nF > 0 && y0 <= gi.fb1 && y1 >= gi.fb0;
+    const bool segC = gi.nCF > 0 && y0 <= gi.cfb1 && y1 >= gi.cfb0;
+    if (!segF && !segC) return;
+    const int2 o = origins[chunk];
+    const int wx = o.x + (idx & 15), wz = o.y + (idx >> 4);
+    const FeaturePlacement* f = gF + (size_t)li * strideF;
+    const CaveFeaturePlacement* cf = gCF + (size_t)li * strideCF;
+    // candidates of this column segment, in list order. NONE ends a list scan in the reference
+    // (chunk.cu:1448-1451, 1477-1480): it is kept with an unbounded range so that the scan below ends there too.
+    int nColF = 0, nColC = 0;
+    if (segF)
+        for (int i0 = 0; i0 < gi.nF; i0 += kFillSeg)
+        {
+            const int i = i0 + t;
+            bool keep = false;
+            Cand k;
+            if (i < gi.nF)
+            {
+                const FeaturePlacement p = f[i];
+                const int r = c_featureReach[p.feature];
+                const int lo = p.y + c_featureHeightBounds[p.feature][0], hi = p.y + c_featureHeightBounds[p.feature][1];
+                const bool none = p.feature == F_NONE;
+                keep = none || (abs(wx - p.x) <= r && abs(wz - p.z) <= r && lo <= y1 && hi >= y0);
+                k.lo = none ? (short)-32768 : (short)max(lo, -32768); k.hi = none ? (short)32767 : (short)min(hi, 32767);
+                k.idx = (unsigned short)i; k.canReplace = (none || p.canReplaceBlocks) ? 1 : 0;
+            }
+            int total;
+            const int off = block_ordered_offset(keep, shWarp, &total);
+            if (keep && nColF + off < kColCapF) shCandF[nColF + off] = k;
+            nColF += total;
+        }
+    if (segC)
+        for (int i0 = 0; i0 < gi.nCF; i0 += kFillSeg)
+        {
+            const int i = i0 + t;
+            bool keep = false;
+            Cand k;
+            if (i < gi.nCF)
+            {
+                const CaveFeaturePlacement p = cf[i];
+                const int r = c_caveFeatureReach[p.feature];
+                const int lo = p.y + c_caveFeatureHeightBounds[p.feature][0], hi = p.y + p.layerHeight + c_caveFeatureHeightBounds[p.feature][1];
+                const bool none = p.feature == CF_NONE;
+                keep = none || (abs(wx - p.x) <= r && abs(wz - p.z) <= r && lo <= y1 && hi >= y0);
+                k.lo = none ? (short)-32768 : (short)max(lo, -32768); k.hi = none ? (short)32767 : (short)min(hi, 32767);
+                k.idx = (unsigned short)i; k.canReplace = (none || p.canReplaceBlocks) ? 1 : 0;
+            }
+            int total;
+            const int off = block_ordered_offset(keep, shWarp, &total);
+            if (keep && nColC + off < kColCapC) shCandC[nColC + off] = k;
+            nColC += total;
+        }
+    if (nColF == 0 && nColC == 0) return;
+    __syncthreads();
+    uint8_t* out = blocks + (size_t)chunk * 98304 + (size_t)idx * 384 + y;
+    const uint8_t block = *out;
     uint8_t fblock = 0;
     bool placed = false;
-    if (y >= gi.fb0 && y <= gi.fb1)
+    if (nColF <= kColCapF)
     {
-        const FeaturePlacement* f = gF + (size_t)li * strideF;
+        for (int c = 0; c < nColF; ++c)
+        {
+            const Cand k = shCandF[c];
+            if (y < k.lo || y > k.hi || (block != B_AIR && !k.canReplace)) continue;
+            const FeaturePlacement fp = f[k.idx];
+            if (fp.feature == F_NONE) break;
+            if (place_feature(fp, wx, y, wz, &fblock)) { placed = true; break; }
+        }
+    }
+    else
+    {
+        // more candidates than the shared list holds: the reference's own scan (chunk.cu:1444-1470)
         for (int i = 0; i < gi.nF; ++i)
         {
             const FeaturePlacement fp = f[i];
@@ -275,19 +471,32 @@ __global__ void __launch_bounds__(384) k_fill(const int* __restrict__ fillList, 
             if (place_feature(fp, wx, y, wz, &fblock)) { placed = true; break; }
         }
     }
-    if (!placed && y >= gi.cfb0 && y <= gi.cfb1)
+    if (!placed)
     {
-        const CaveFeaturePlacement* f = gCF + (size_t)li * strideCF;
-        for (int i = 0; i < gi.nCF; ++i)
+        if (nColC <= kColCapC)
         {
-            const CaveFeaturePlacement cp = f[i];
-            if (cp.feature == CF_NONE) break;
-            if (block != B_AIR && !cp.canReplaceBlocks) continue;
-            if (y < cp.y + c_caveFeatureHeightBounds[cp.feature][0] || y > cp.y + cp.layerHeight + c_caveFeatureHeightBounds[cp.feature][1]) continue;
-            if (place_cave_feature(cp, wx, y, wz, &fblock)) { placed = true; break; }
+            for (int c = 0; c < nColC; ++c)
+            {
+                const Cand k = shCandC[c];
+                if (y < k.lo || y > k.hi || (block != B_AIR && !k.canReplace)) continue;
+                const CaveFeaturePlacement cp = cf[k.idx];
+                if (cp.feature == CF_NONE) break;
+                if (place_cave_feature(cp, wx, y, wz, &fblock)) { placed = true; break; }
+            }
+        }
+        else
+        {
+            for (int i = 0; i < gi.nCF; ++i)
+            {
+                const CaveFeaturePlacement cp = cf[i];
+                if (cp.feature == CF_NONE) break;
+                if (block != B_AIR && !cp.canReplaceBlocks) continue;
+                if (y < cp.y + c_caveFeatureHeightBounds[cp.feature][0] || y > cp.y + cp.layerHeight + c_caveFeatureHeightBounds[cp.feature][1]) continue;
+                if (place_cave_feature(cp, wx, y, wz, &fblock)) { placed = true; break; }
+            }
         }
     }
-    blocks[(size_t)chunk * 98304 + (size_t)idx * 384 + y] = placed ? fblock : block;
+    if (placed) *out = fblock;
 }
 
 // tryPlaceSingleDecorator (chunk.cu:1634-1677)
@@ -317,49 +526,79 @@ __device__ __forceinline__ void try_place_decorator(uint8_t* blocks, int x, int 
     blocks[di] = gen.block;
 }
 
-// placeDecorators (chunk.cu:1679-1747): one sequential RNG stream per chunk -> one thread per chunk
-__global__ void k_decorators(const int* __restrict__ fillList, int n, const int2* __restrict__ origins,
-                             const float* __restrict__ heightfield, const float* __restrict__ biomeWeights,
-                             const CaveLayer* __restrict__ caveLayers, uint8_t* __restrict__ blocks)
+// minstd skip-ahead: a^k mod (2^31 - 1), so that a column can start from the state the reference's
+// sequential walk would have when it reaches that column
+__device__ __forceinline__ uint32_t minstd_pow(uint32_t k)
 {
-    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t r = 1, b = 48271u;
+    while (k)
+    {
+        if (k & 1u) r = (r * b) % 2147483647u;
+        b = (b * b) % 2147483647u;
+        k >>= 1;
+    }
+    return (uint32_t)r;
+}
+
+// placeDecorators (chunk.cu:1679-1747). The reference walks the 256 columns of a chunk with ONE
+// sequential RNG stream (z outer, x inner), drawing 2 numbers per column plus 2 per cave layer. The
+// number of draws of a column does not depend on any draw, so the stream position of every column
+// is a prefix sum, the state there is seed * a^position, and the columns (which only ever touch
+// their own blocks) run in parallel: one CTA per chunk, one thread per column.
+__global__ void __launch_bounds__(256) k_decorators(const int* __restrict__ fillList, int n, const int2* __restrict__ origins,
+                                                    const float* __restrict__ heightfield, const float* __restrict__ biomeWeights,
+                                                    const CaveLayer* __restrict__ caveLayers, uint8_t* __restrict__ blocks)
+{
+    __shared__ int shDraws[256];
+    const int li = blockIdx.x;
     if (li >= n) return;
     const int chunk = fillList ? fillList[li] : li;
+    const int idx = threadIdx.x, x = idx & 15, z = idx >> 4;
     const int2 o = origins[chunk];
     uint8_t* b = blocks + (size_t)chunk * 98304;
     const float* w = biomeWeights + (size_t)chunk * (NUM_BIOMES * 256);
-    Minstd rng = make_rng4(o.x, 0, o.y, 7589341);
-    for (int idx = 0; idx < 256; ++idx)
+    const CaveLayer* cl = caveLayers + ((size_t)chunk * 256 + idx) * MAX_CAVE_LAYERS;
+    int nLayers = 0;
+    while (nLayers < MAX_CAVE_LAYERS && cl[nLayers].start != 384) ++nLayers;
+    const int draws = 2 + 2 * nLayers;
+    shDraws[idx] = draws;
+    __syncthreads();
+    for (int d = 1; d < 256; d <<= 1)
     {
-        const int x = idx & 15, z = idx >> 4;
-        const int biome = random_biome(w + idx, 256, rng.u01());
-        float rand = rng.u01();
-        const int g0 = c_decoratorGenRange[biome][0], gn = c_decoratorGenRange[biome][1];
-        for (int g = 0; g < gn; ++g)
-            if ((rand -= c_decoratorGens[g0 + g].chance) < 0.f)
-            {
-                try_place_decorator(b, x, (int)heightfield[(size_t)chunk * 256 + idx] + 1, z, c_decoratorGens[g0 + g]);
-                break;
-            }
-        const CaveLayer* cl = caveLayers + ((size_t)chunk * 256 + idx) * MAX_CAVE_LAYERS;
-        for (int l = 0; l < MAX_CAVE_LAYERS; ++l)
+        const int a = idx >= d ? shDraws[idx - d] : 0;
+        __syncthreads();
+        shDraws[idx] += a;
+        __syncthreads();
+    }
+    const int before = shDraws[idx] - draws;
+    Minstd rng = make_rng4(o.x, 0, o.y, 7589341);
+    rng.x = (uint32_t)(((uint64_t)rng.x * minstd_pow((uint32_t)before)) % 2147483647u);
+
+    const int biome = random_biome(w + idx, 256, rng.u01());
+    float rand = rng.u01();
+    const int g0 = c_decoratorGenRange[biome][0], gn = c_decoratorGenRange[biome][1];
+    for (int g = 0; g < gn; ++g)
+        if ((rand -= c_decoratorGens[g0 + g].chance) < 0.f)
         {
-            const CaveLayer c = cl[l];
-            if (c.start == 384) break;
-            float bottomRand = rng.u01();
-            float topRand = rng.u01();
-            const int c0 = c_caveDecoratorGenRange[c.bottomBiome][0], cn = c_caveDecoratorGenRange[c.bottomBiome][1];
-            for (int g = 0; g < cn; ++g)
+            try_place_decorator(b, x, (int)heightfield[(size_t)chunk * 256 + idx] + 1, z, c_decoratorGens[g0 + g]);
+            break;
+        }
+    for (int l = 0; l < nLayers; ++l)
+    {
+        const CaveLayer c = cl[l];
+        float bottomRand = rng.u01();
+        float topRand = rng.u01();
+        const int c0 = c_caveDecoratorGenRange[c.bottomBiome][0], cn = c_caveDecoratorGenRange[c.bottomBiome][1];
+        for (int g = 0; g < cn; ++g)
+        {
+            const DecoratorGen& gen = c_caveDecoratorGens[c0 + g];
+            if (gen.fromCeiling)
             {
-                const DecoratorGen& gen = c_caveDecoratorGens[c0 + g];
-                if (gen.fromCeiling)
-                {
-                    if ((topRand -= gen.chance) < 0.f) try_place_decorator(b, x, c.end, z, gen);
-                }
-                else
-                {
-                    if ((bottomRand -= gen.chance) < 0.f) try_place_decorator(b, x, c.start + 1, z, gen);
-                }
+                if ((topRand -= gen.chance) < 0.f) try_place_decorator(b, x, c.end, z, gen);
+            }
+            else
+            {
+                if ((bottomRand -= gen.chance) < 0.f) try_place_decorator(b, x, c.start + 1, z, gen);
             }
         }
     }

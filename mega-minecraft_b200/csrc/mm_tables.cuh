@@ -145,6 +145,26 @@ __constant__ const int c_featureHeightBounds[NUM_FEATURES][2] = {
 __constant__ const int c_caveFeatureHeightBounds[NUM_CAVE_FEATURES][2] = {
     {0, 0}, {-3, 3}, {-3, 3}, {0, 0}, {0, 6}, {-12, 12}, {-12, 12}, {-8, 8}, {-2, 3}, {-2, 5}};
 
+// Horizontal reach of every feature type: place_feature / place_cave_feature return false for every
+// voxel with |wx - p.x| > R or |wz - p.z| > R. Each R follows from the rasteriser's OWN first
+// horizontal early-out (mm_placefeature.cuh, same tests as featurePlacement.hpp:147-1380), so culling
+// by it cannot change a block:
+//   SPHERE dot(pos,pos) > 25; CORAL hypot > 8; KELP / vines / test pillars fx = fz = 0;
+//   ICEBERG needs end >= start <=> 1 - hd/radius >= (6 f - 2)/54 with radius < 32 and |f| = |fbm2<3>| < 2.48
+//   (3 corners x 130 x max (0.5-d^2)^4 d x 0.79) => hd < 42.1; ACACIA max(|fx|,|fz|) > 15;
+//   REDWOOD hypot(pos * s) > 12 with s >= 0.6; CYPRESS hypot > 12; BIRCH max > 8; PINE / PINE_SHRUB max > 6;
+//   RAFFLESIA |pos| > 15; LARGE_JUNGLE hypot > 15; SMALL_JUNGLE hypot > 8; TINY_JUNGLE trunk or 1-block leaves;
+//   MEDIUM_PURPLE_MUSHROOM |fx|+|fz| > 8; PURPLE_MUSHROOM hypot(pos * s) > 35 with s >= 0.5;
+//   CRYSTALs max > 25; PALM |fx|+|fz| > 24; CACTUS max > 5;
+//   GLOWSTONE_CLUSTER |top * s| > 6 with s >= 1; STORMLIGHT spheres dist > radius, radius < 7.5;
+//   CRYSTAL_PILLAR hypot > 7; WARPED_FUNGUS |fx|+|fz| > 6; AMBER_FUNGUS |fx|+|fz| > 4.
+// NONE terminates a list scan (chunk.cu:1448-1451), so it is never culled.
+constexpr int kReachAll = 1 << 20;
+__constant__ const int c_featureReach[NUM_FEATURES] = {
+    kReachAll, 5, 8, 0, 43, 15, 20, 12, 8, 6, 6, 15,
+    15, 8, 1, 8, 70, 25, 25, 24, 5};
+__constant__ const int c_caveFeatureReach[NUM_CAVE_FEATURES] = {kReachAll, 0, 0, 0, 6, 7, 7, 7, 6, 4};
+
 // feature / cave-feature / decorator generators (biomeFuncs.hpp:975-1040, 1081-1178, 1189-1252), flattened:
 // c_*Range[biome] = {first, count} into the generator array.
 struct FeatureGen { uint8_t feature; int cell, pad; float chance; int numTop; uint8_t topMat[2]; float topMin[2]; uint8_t canReplace; };

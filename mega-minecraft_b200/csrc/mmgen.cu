@@ -64,7 +64,8 @@ struct MmgenWorld
     float* d_weights = nullptr;
     float* d_layers = nullptr;        // S2 output (never modified afterwards: erosion pads read it)
     float* d_eroded = nullptr;        // S3 output: full 20-layer set of eroded chunks
-    float* d_zone = nullptr;          // 9 planes + 1 scratch plane + 2 accum planes of one zone
+    float* d_zone = nullptr;          // kZoneBatch zones x (9 planes + 1 scratch plane + 2 accum planes)
+    int2* d_zoneCorners = nullptr;
     int* d_flags = nullptr;           // one "changed" flag per sweep of a batch
     int* d_list = nullptr;            // chunk index lists
     CaveLayer* d_caves = nullptr;     // [chunk][256][32]
@@ -75,6 +76,8 @@ struct MmgenWorld
     FeaturePlacement* d_gF = nullptr;                // gathered lists of one fill batch
     CaveFeaturePlacement* d_gCF = nullptr;
     GatherInfo* d_info = nullptr;
+    uint2* d_lushQueue = nullptr;                    // voxels of one fill batch waiting for the lush-cave decision
+    int* d_lushCount = nullptr;
     uint8_t* d_blocks = nullptr;                     // [chunk][16][16][384]
     int erosionSweeps = 0;
     std::vector<uint8_t> stage;
@@ -154,48 +157,43 @@ int mmgen_heightfields(int n, const int32_t* origins, float* out_heightfield, fl
 }
 
 // ------------------------------------------------------------------ erosion driver
-// zone: 12 planes of 384x384 floats: [0..8] gathered planes, [9] ping-pong scratch, [10..11] accum.
-// Runs Chunk::erodeZone's loop (chunk.cu:682-705) with the convergence test on the device.
+// zones: nZones x 12 planes of 384x384 floats (kZonePlanes). Runs Chunk::erodeZone's loop
+// (chunk.cu:682-705) for all zones of the batch in lockstep, with the convergence test on the device.
 static const float kTanRepose[NUM_ERODED] = {1.42814791f, 0.839099586f, 1.0f, 0.839099586f,
                                              0.577350318f, 0.700207531f, 2.14450693f, 1.0f};
-constexpr int kSweepBatch = 8;
+constexpr int kSweepGroup = 8;     // sweeps between two convergence polls
+constexpr int kZoneBatch = 32;     // zones per launch: 32 x 4 live planes x 590 KB = 75 MB, L2-resident
 
-static int erodeZoneDevice(float* d_zone, int* d_flags, cudaStream_t stream, int* sweepsOut)
+static int erodeZonesDevice(float* d_zones, int nZones, int* d_flags, cudaStream_t stream, int* sweepsOut)
 {
     const size_t P = kErosionCols;
-    float* scratch = d_zone + 9 * P;
-    float* accumA = d_zone + 10 * P;
-    float* accumB = d_zone + 11 * P;
-    MMG_CUDA(cudaMemsetAsync(accumA, 0, P * sizeof(float), stream));
+    int accIn = 10, accOut = 11;     // plane 10 was zeroed by the gather (or by the caller)
     int sweeps = 0;
-    int h_flags[kSweepBatch];
+    int h_flags[kSweepGroup];
     for (int layer = NUM_ERODED - 1; layer >= 0; --layer)
     {
-        float* plane = d_zone + (size_t)layer * P;
-        const float* eUp = d_zone + (size_t)(layer + 1) * P;
-        float* sIn = plane;
-        float* sOut = scratch;
+        int pIn = layer, pOut = 9;
         bool first = true, converged = false;
         while (!converged)
         {
-            MMG_CUDA(cudaMemsetAsync(d_flags, 0, kSweepBatch * sizeof(int), stream));
-            for (int b = 0; b < kSweepBatch; ++b)
+            MMG_CUDA(cudaMemsetAsync(d_flags, 0, kSweepGroup * sizeof(int), stream));
+            for (int b = 0; b < kSweepGroup; ++b)
             {
-                MMG_LAUNCH(k_erode_sweep, dim3(12, 12), dim3(32, 32), 0, stream, sIn, sOut, eUp, accumA, accumB,
+                MMG_LAUNCH(k_erode_sweep, dim3(12, 12, nZones), dim3(32, 32), 0, stream, d_zones, pIn, pOut, layer + 1, accIn, accOut,
                            kTanRepose[layer], first ? 1 : 0, d_flags + b);
-                std::swap(sIn, sOut);
-                std::swap(accumA, accumB);
+                std::swap(pIn, pOut);
+                std::swap(accIn, accOut);
                 first = false;
                 ++sweeps;
             }
             MMG_CUDA(cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, stream));
             MMG_CUDA(cudaStreamSynchronize(stream));
-            converged = (h_flags[kSweepBatch - 1] == 0);
+            converged = (h_flags[kSweepGroup - 1] == 0);
         }
-        if (sIn != plane) MMG_CUDA(cudaMemcpyAsync(plane, sIn, P * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        // an even number of sweeps per group: the result is back in the layer's own plane
+        static_assert(kSweepGroup % 2 == 0, "ping-pong must end in the layer plane");
     }
-    // leave the live accum in plane 10 for inspection
-    if (accumA != d_zone + 10 * P) MMG_CUDA(cudaMemcpyAsync(d_zone + 10 * P, accumA, P * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    (void)P;
     if (sweepsOut) *sweepsOut = sweeps;
     return 0;
 }
@@ -222,11 +220,12 @@ extern "C" int mmgen_erode_zone(const float* gathered, float* out_eroded, int* o
 {
     if (requireReady()) return 1;
     const size_t P = kErosionCols;
-    if (g_scratch[4].ensure(12 * P * sizeof(float))) return 1;
-    if (g_scratch[5].ensure(kSweepBatch * sizeof(int))) return 1;
+    if (g_scratch[4].ensure(kZonePlanes * P * sizeof(float))) return 1;
+    if (g_scratch[5].ensure(kSweepGroup * sizeof(int))) return 1;
     float* d_zone = (float*)g_scratch[4].ptr;
     MMG_CUDA(cudaMemcpyAsync(d_zone, gathered, 9 * P * sizeof(float), cudaMemcpyHostToDevice, g_stream));
-    if (erodeZoneDevice(d_zone, (int*)g_scratch[5].ptr, g_stream, out_sweeps)) return 1;
+    MMG_CUDA(cudaMemsetAsync(d_zone + 10 * P, 0, P * sizeof(float), g_stream));
+    if (erodeZonesDevice(d_zone, 1, (int*)g_scratch[5].ptr, g_stream, out_sweeps)) return 1;
     MMG_CUDA(cudaMemcpyAsync(out_eroded, d_zone, 8 * P * sizeof(float), cudaMemcpyDeviceToHost, g_stream));
     MMG_CUDA(cudaStreamSynchronize(g_stream));
     return 0;
@@ -255,7 +254,21 @@ extern "C" int mmgen_caves(int n, const int32_t* origins, const float* heightfie
     return 0;
 }
 
-constexpr int kFillBatch = 512;   // chunks gathered + filled per launch group (bounds the gathered-list buffers)
+constexpr int kFillBatch = 512;
+
+// the kernel sequence of Chunk::fill for one batch of m chunks (lists indexed by batch position)
+static int launchFill(int m, const int* d_list, const int2* d_origins, const float* d_height, const float* d_weights, const float* d_layers,
+                      const CaveLayer* d_caves, const FeaturePlacement* d_gF, const CaveFeaturePlacement* d_gCF, const GatherInfo* d_info,
+                      int strideF, int strideCF, uint8_t* d_blocks, uint2* d_lushQueue, int* d_lushCount, cudaStream_t stream)
+{
+    MMG_CUDA(cudaMemsetAsync(d_lushCount, 0, sizeof(int), stream));
+    MMG_LAUNCH(k_fill_terrain, m * 256 * 3, kFillSeg, 0, stream, d_list, d_origins, d_height, d_weights, d_layers, d_caves, d_blocks,
+               d_lushQueue, d_lushCount);
+    MMG_LAUNCH(k_fill_lush, kNumSMs * 8, 128, 0, stream, d_origins, (const uint2*)d_lushQueue, (const int*)d_lushCount, d_blocks);
+    MMG_LAUNCH(k_fill_features, m * 256 * 3, kFillSeg, 0, stream, d_list, d_origins, d_gF, d_gCF, d_info, strideF, strideCF, d_blocks);
+    MMG_LAUNCH(k_decorators, m, 256, 0, stream, d_list, m, d_origins, d_height, d_weights, d_caves, d_blocks);
+    return 0;
+}   // chunks gathered + filled per launch group (bounds the gathered-list buffers)
 
 extern "C" int mmgen_feature_placements(int n, const int32_t* origins, const float* heightfield, const float* biomeWeights,
                                         const float* layers, const MmgenCaveLayer* caveLayers, int maxPerChunk,
@@ -310,7 +323,8 @@ extern "C" int mmgen_fill(int n, const int32_t* origins, const float* heightfiel
         S[3].ensure(clBytes) || S[4].ensure((size_t)n * NUM_MATERIALS * 256 * 4) ||
         S[5].ensure((size_t)n * featureStride * sizeof(FeaturePlacement) + 16) ||
         S[6].ensure((size_t)n * caveFeatureStride * sizeof(CaveFeaturePlacement) + 16) || S[7].ensure((size_t)n * 2 * sizeof(int)) ||
-        X[0].ensure((size_t)n * sizeof(GatherInfo)) || X[1].ensure((size_t)n * 98304))
+        X[0].ensure((size_t)n * sizeof(GatherInfo)) || X[1].ensure((size_t)n * 98304) ||
+        X[2].ensure((size_t)kLushQueueCap * sizeof(uint2)) || X[3].ensure(sizeof(int)))
         return 1;
     MMG_CUDA(cudaMemcpyAsync(S[0].ptr, origins, (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, g_stream));
     MMG_CUDA(cudaMemcpyAsync(S[1].ptr, heightfield, (size_t)n * 256 * 4, cudaMemcpyHostToDevice, g_stream));
@@ -322,11 +336,10 @@ extern "C" int mmgen_fill(int n, const int32_t* origins, const float* heightfiel
     MMG_CUDA(cudaMemcpyAsync(S[7].ptr, numFeatures, (size_t)n * 2 * sizeof(int), cudaMemcpyHostToDevice, g_stream));
     MMG_LAUNCH(k_gather_info, n, 256, 0, g_stream, (const FeaturePlacement*)S[5].ptr, (const CaveFeaturePlacement*)S[6].ptr,
                (const int*)S[7].ptr, featureStride, caveFeatureStride, (GatherInfo*)X[0].ptr);
-    MMG_LAUNCH(k_fill, n * 256, 384, 0, g_stream, (const int*)nullptr, (const int2*)S[0].ptr, (const float*)S[1].ptr,
-               (const float*)S[2].ptr, (const float*)S[4].ptr, (const CaveLayer*)S[3].ptr, (const FeaturePlacement*)S[5].ptr,
-               (const CaveFeaturePlacement*)S[6].ptr, (const GatherInfo*)X[0].ptr, featureStride, caveFeatureStride, (uint8_t*)X[1].ptr);
-    MMG_LAUNCH(k_decorators, (n + 31) / 32, 32, 0, g_stream, (const int*)nullptr, n, (const int2*)S[0].ptr, (const float*)S[1].ptr,
-               (const float*)S[2].ptr, (const CaveLayer*)S[3].ptr, (uint8_t*)X[1].ptr);
+    if (launchFill(n, nullptr, (const int2*)S[0].ptr, (const float*)S[1].ptr, (const float*)S[2].ptr, (const float*)S[4].ptr,
+                   (const CaveLayer*)S[3].ptr, (const FeaturePlacement*)S[5].ptr, (const CaveFeaturePlacement*)S[6].ptr,
+                   (const GatherInfo*)X[0].ptr, featureStride, caveFeatureStride, (uint8_t*)X[1].ptr, (uint2*)X[2].ptr, (int*)X[3].ptr, g_stream))
+        return 1;
     MMG_CUDA(cudaMemcpyAsync(out_blocks, X[1].ptr, (size_t)n * 98304, cudaMemcpyDeviceToHost, g_stream));
     MMG_CUDA(cudaStreamSynchronize(g_stream));
     return 0;
@@ -367,6 +380,7 @@ int mmgen_world_destroy(MmgenWorld* w)
     cudaFree(w->d_layers);
     cudaFree(w->d_eroded);
     cudaFree(w->d_zone);
+    cudaFree(w->d_zoneCorners);
     cudaFree(w->d_flags);
     cudaFree(w->d_list);
     cudaFree(w->d_caves);
@@ -377,6 +391,8 @@ int mmgen_world_destroy(MmgenWorld* w)
     cudaFree(w->d_gF);
     cudaFree(w->d_gCF);
     cudaFree(w->d_info);
+    cudaFree(w->d_lushQueue);
+    cudaFree(w->d_lushCount);
     cudaFree(w->d_blocks);
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     for (auto& e : w->evBatch) if (e) cudaEventDestroy(e);
@@ -428,10 +444,11 @@ static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
         w->erosionSweeps = 0;
         // zones are aligned to multiples of 12 chunks in WORLD chunk coordinates (terrain.cpp:259-262)
         auto floorDiv = [](int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); };
+        std::vector<int2> corners;   // window-local corner of each erodable zone's 24x24-chunk window
         for (int zz = floorDiv(w->cz0, 12) * 12; zz < w->cz0 + nz; zz += 12)
             for (int zx = floorDiv(w->cx0, 12) * 12; zx < w->cx0 + nx; zx += 12)
             {
-                const int lx0 = zx - 6 - w->cx0, lz0 = zz - 6 - w->cz0;   // window corner, local coords
+                const int lx0 = zx - 6 - w->cx0, lz0 = zz - 6 - w->cz0;
                 if (lx0 < 0 || lz0 < 0 || lx0 + 24 > nx || lz0 + 24 > nz) continue;
                 // with a target region only zones that meet target (+) 3 chunks are eroded
                 if (w->hasTarget && (lx0 + 18 <= w->tx0 - 3 || lx0 + 6 >= w->tx0 + w->tnx + 3 ||
@@ -439,20 +456,32 @@ static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
                 bool ok = true;
                 for (int z = 0; z < 24 && ok; ++z)
                     for (int x = 0; x < 24 && ok; ++x) ok = w->stage[(lz0 + z) * nx + lx0 + x] >= 2;
-                if (!ok) continue;
-                if (!w->d_zone) MMG_CUDA(cudaMalloc(&w->d_zone, 12 * (size_t)kErosionCols * sizeof(float)));
-                if (!w->d_flags) MMG_CUDA(cudaMalloc(&w->d_flags, kSweepBatch * sizeof(int)));
-                if (!w->d_eroded) MMG_CUDA(cudaMalloc(&w->d_eroded, (size_t)w->n * NUM_MATERIALS * 256 * sizeof(float)));
-                MMG_LAUNCH(k_zone_gather, dim3(12, 12), dim3(32, 32), 0, w->stream, (const float*)w->d_layers,
-                           (const float*)w->d_height, w->d_zone, lx0, lz0, nx);
-                int sweeps = 0;
-                if (erodeZoneDevice(w->d_zone, w->d_flags, w->stream, &sweeps)) return 1;
-                w->erosionSweeps += sweeps;
-                MMG_LAUNCH(k_zone_scatter, dim3(6, 6), dim3(32, 32), 0, w->stream, (const float*)w->d_zone,
-                           (const float*)w->d_layers, w->d_eroded, lx0, lz0, nx);
-                for (int z = 6; z < 18; ++z)
-                    for (int x = 6; x < 18; ++x) w->stage[(lz0 + z) * nx + lx0 + x] = 3;
+                if (ok) corners.push_back(make_int2(lx0, lz0));
             }
+        if (!corners.empty())
+        {
+            const int batch = std::min<int>(kZoneBatch, (int)corners.size());
+            if (!w->d_zone) MMG_CUDA(cudaMalloc(&w->d_zone, (size_t)kZoneBatch * kZonePlanes * kErosionCols * sizeof(float)));
+            if (!w->d_zoneCorners) MMG_CUDA(cudaMalloc(&w->d_zoneCorners, (size_t)kZoneBatch * sizeof(int2)));
+            if (!w->d_flags) MMG_CUDA(cudaMalloc(&w->d_flags, kSweepGroup * sizeof(int)));
+            if (!w->d_eroded) MMG_CUDA(cudaMalloc(&w->d_eroded, (size_t)w->n * NUM_MATERIALS * 256 * sizeof(float)));
+            (void)batch;
+            for (size_t z0 = 0; z0 < corners.size(); z0 += kZoneBatch)
+            {
+                const int m = (int)std::min<size_t>(kZoneBatch, corners.size() - z0);
+                MMG_CUDA(cudaMemcpyAsync(w->d_zoneCorners, corners.data() + z0, (size_t)m * sizeof(int2), cudaMemcpyHostToDevice, w->stream));
+                MMG_LAUNCH(k_zone_gather, dim3(12, 12, m), dim3(32, 32), 0, w->stream, (const float*)w->d_layers,
+                           (const float*)w->d_height, w->d_zone, (const int2*)w->d_zoneCorners, nx);
+                int sweeps = 0;
+                if (erodeZonesDevice(w->d_zone, m, w->d_flags, w->stream, &sweeps)) return 1;
+                w->erosionSweeps += sweeps;
+                MMG_LAUNCH(k_zone_scatter, dim3(6, 6, m), dim3(32, 32), 0, w->stream, (const float*)w->d_zone,
+                           (const float*)w->d_layers, w->d_eroded, (const int2*)w->d_zoneCorners, nx);
+                for (int k = 0; k < m; ++k)
+                    for (int z = 6; z < 18; ++z)
+                        for (int x = 6; x < 18; ++x) w->stage[(corners[z0 + k].y + z) * nx + corners[z0 + k].x + x] = 3;
+            }
+        }
         MMG_CUDA(cudaEventRecord(w->ev[5], w->stream));
     }
     if (stageMask & MMGEN_STAGE_CAVES)
@@ -522,19 +551,19 @@ static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
             if (!w->d_gF) MMG_CUDA(cudaMalloc(&w->d_gF, (size_t)kFillBatch * MAX_FEATURES * sizeof(FeaturePlacement)));
             if (!w->d_gCF) MMG_CUDA(cudaMalloc(&w->d_gCF, (size_t)kFillBatch * MAX_CAVE_FEATURES * sizeof(CaveFeaturePlacement)));
             if (!w->d_info) MMG_CUDA(cudaMalloc(&w->d_info, (size_t)kFillBatch * sizeof(GatherInfo)));
+            if (!w->d_lushQueue) MMG_CUDA(cudaMalloc(&w->d_lushQueue, (size_t)kLushQueueCap * sizeof(uint2)));
+            if (!w->d_lushCount) MMG_CUDA(cudaMalloc(&w->d_lushCount, sizeof(int)));
             MMG_CUDA(cudaMemcpyAsync(w->d_list, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, w->stream));
             for (size_t b0 = 0; b0 < list.size(); b0 += kFillBatch)
             {
                 const int m = (int)std::min<size_t>(kFillBatch, list.size() - b0);
                 const int* dl = w->d_list + b0;
-                MMG_LAUNCH(k_gather_features, m, 256, 0, w->stream, dl, (const FeaturePlacement*)w->d_features,
+                MMG_LAUNCH(k_gather_features, m, 256, 0, w->stream, dl, (const int2*)w->d_origins, (const FeaturePlacement*)w->d_features,
                            (const CaveFeaturePlacement*)w->d_caveFeatures, (const int*)w->d_counts, nx, w->d_gF, w->d_gCF, w->d_info);
-                MMG_LAUNCH(k_fill, m * 256, 384, 0, w->stream, dl, (const int2*)w->d_origins, (const float*)w->d_height,
-                           (const float*)w->d_weights, (const float*)w->d_eroded, (const CaveLayer*)w->d_caves,
-                           (const FeaturePlacement*)w->d_gF, (const CaveFeaturePlacement*)w->d_gCF, (const GatherInfo*)w->d_info,
-                           MAX_FEATURES, MAX_CAVE_FEATURES, w->d_blocks);
-                MMG_LAUNCH(k_decorators, (m + 31) / 32, 32, 0, w->stream, dl, m, (const int2*)w->d_origins, (const float*)w->d_height,
-                           (const float*)w->d_weights, (const CaveLayer*)w->d_caves, w->d_blocks);
+                if (launchFill(m, dl, (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights, (const float*)w->d_eroded,
+                               (const CaveLayer*)w->d_caves, (const FeaturePlacement*)w->d_gF, (const CaveFeaturePlacement*)w->d_gCF,
+                               (const GatherInfo*)w->d_info, MAX_FEATURES, MAX_CAVE_FEATURES, w->d_blocks, w->d_lushQueue, w->d_lushCount, w->stream))
+                    return 1;
                 if (hostBlocks)
                 {
                     // stream the finished batch to the host while the next batch is being filled:
