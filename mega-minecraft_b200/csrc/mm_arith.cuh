@@ -78,12 +78,75 @@ __device__ __forceinline__ float g_smoothstep(float e0, float e1, float x)
     return (t * t) * fmaf(t, -2.0f, 3.0f);
 }
 
-// ---------------------------------------------------------------- simplex 2-D
+// ---------------------------------------------------------------- simplex lattice tables
+// GLM's simplex hashes every lattice corner with permute(x) = mod289((34x+1)x) chains and decodes a
+// gradient from the final value p. All of that is a function of small integers: permute() only ever sees
+// 0..579 and the normalised gradient depends on p in 0..289 alone. The reference recomputes both per
+// corner in floating point (~45 instructions, 8 of them FRND on the quarter-rate XU pipe, per corner);
+// here they are tabulated ONCE per library init by the reference's own fp32 formulas (k_init_noise_tables,
+// same -fmad=false code as before, so the quirks of the float mod289 are kept bit for bit) and every CTA
+// stages the 10 KB of tables in shared memory.
+struct NoiseTab
+{
+    float4 grad3[290];            // normalised 3-D gradient (ax, ay, az) of p   (noise.inl:676-711)
+    float4 grad2[290];            // 2-D: (a0, h, norm factor) of p              (noise.inl:622-637)
+    unsigned short perm[584];     // permute(x), x = 0..579
+};
+constexpr int kNoiseSmemBytes = (int)sizeof(NoiseTab);
+__device__ NoiseTab g_noiseTab;  // filled by k_init_noise_tables
+
+extern __shared__ float4 mmg_dyn_smem[];
+__device__ __forceinline__ const NoiseTab* noise_tab() { return reinterpret_cast<const NoiseTab*>(mmg_dyn_smem); }
+
+// every kernel that evaluates simplex noise is launched with kNoiseSmemBytes of dynamic shared memory
+// and calls this once (all threads of the CTA) before the first evaluation
+__device__ __forceinline__ void noise_tab_stage()
+{
+    const float4* src = reinterpret_cast<const float4*>(&g_noiseTab);
+    for (int i = threadIdx.x + blockDim.x * threadIdx.y; i < kNoiseSmemBytes / 16; i += blockDim.x * blockDim.y) mmg_dyn_smem[i] = src[i];
+    __syncthreads();
+}
+
 // permute(x) = mod289((34x+1)x) on small non-negative integers: every step is exact in fp32,
-// so contraction cannot change it (34*290+1 and its product with 290 are < 2^24).
+// so contraction cannot change it (34*580+1 and its product with 580 are < 2^24).
 __device__ __forceinline__ float sx_mod289(float x) { return x - floorf(x * (1.0f / 289.0f)) * 289.0f; }
 __device__ __forceinline__ float sx_permute(float x) { return sx_mod289(fmaf(x, 34.0f, 1.0f) * x); }
 
+__global__ void k_init_noise_tables()
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 584) g_noiseTab.perm[i] = (unsigned short)sx_permute((float)i);
+    if (i < 290)
+    {
+        const float p = (float)i;
+        {
+            // 3-D gradient of p (noise.inl:676-711)
+            const float NZ = 0.142857142857f, NX = NZ * 2.0f, NY = NZ * 0.5f - 1.0f;
+            const float j = p - 49.0f * floorf((p * NZ) * NZ);
+            const float x_ = floorf(j * NZ);
+            const float y_ = floorf(j - 7.0f * x_);
+            const float gx = fmaf(x_, NX, NY), gy = fmaf(y_, NX, NY);
+            const float h = (1.0f - fabsf(gx)) - fabsf(gy);
+            const float sh = (h <= 0.0f) ? -1.0f : 0.0f;
+            float ax = fmaf(fmaf(floorf(gx), 2.0f, 1.0f), sh, gx);
+            float ay = fmaf(fmaf(floorf(gy), 2.0f, 1.0f), sh, gy);
+            float az = h;
+            const float nrm = fmaf(fmaf(az, az, fmaf(ax, ax, ay * ay)), -0.85373472095314f, 1.79284291400159f);
+            g_noiseTab.grad3[i] = make_float4(ax * nrm, ay * nrm, az * nrm, 0.0f);
+        }
+        {
+            // 2-D: x = 2*fract(p*C.w) - 1 ; h = |x| - 0.5 ; a0 = x - floor(x + 0.5) ; norm = 1.79 - 0.85*(a0*a0 + h*h)
+            const float C3 = 0.024390243902439f;
+            const float q = p * C3;
+            const float gx = fmaf(q - floorf(q), 2.0f, -1.0f);
+            const float h = fabsf(gx) - 0.5f;
+            const float a0 = gx - floorf(gx + 0.5f);
+            g_noiseTab.grad2[i] = make_float4(a0, h, fmaf(fmaf(h, h, a0 * a0), -0.85373472095314f, 1.79284291400159f), 0.0f);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- simplex 2-D
 // returns dot(m, g) BEFORE the final *130: callers that add to the result fuse that multiply
 // (fma(raw, 130, c)); everything else uses 130*raw rounded.
 // SKEW_X selects which product of the skew dot(v, C.yy) the reference build fused: most inlined
@@ -93,41 +156,35 @@ __device__ __forceinline__ float sx_permute(float x) { return sx_mod289(fmaf(x, 
 template <bool SKEW_X = false>
 __device__ MMG_NOISE_INLINE float simplex2_raw(float vx, float vy)
 {
-    const float C0 = 0.211324865405187f, C1 = 0.366025403784439f, C2 = -0.577350269189626f, C3 = 0.024390243902439f;
+    const NoiseTab* T = noise_tab();
+    const float C0 = 0.211324865405187f, C1 = 0.366025403784439f, C2 = -0.577350269189626f;
     // i = floor(v + dot(v, C.yy)); dot = fma(v.y, C1, v.x*C1)
     float s = SKEW_X ? fmaf(vx, C1, vy * C1) : fmaf(vy, C1, vx * C1);
     float ix = floorf(vx + s), iy = floorf(vy + s);
     // x0 = v - i + dot(i, C.xx); dot = fma(i.x, C0, i.y*C0)
     float t = fmaf(ix, C0, iy * C0);
     float x0x = (vx - ix) + t, x0y = (vy - iy) + t;
-    float i1x = (x0x > x0y) ? 1.0f : 0.0f, i1y = (x0x > x0y) ? 0.0f : 1.0f;
+    const bool gt = x0x > x0y;
+    float i1x = gt ? 1.0f : 0.0f, i1y = gt ? 0.0f : 1.0f;
     float x1x = (x0x + C0) - i1x, x1y = (x0y + C0) - i1y;
     float x2x = x0x + C2, x2y = x0y + C2;
     // mod(i, 289) = i - 289*floor(i/289) (true division; exact for these integers)
-    float mx = ix - 289.0f * floorf(ix / 289.0f), my = iy - 289.0f * floorf(iy / 289.0f);
-    float p0 = sx_permute(sx_permute(my + 0.0f) + mx + 0.0f);
-    float p1 = sx_permute(sx_permute(my + i1y) + mx + i1x);
-    float p2 = sx_permute(sx_permute(my + 1.0f) + mx + 1.0f);
+    const int jx = (int)(ix - 289.0f * floorf(ix / 289.0f)), jy = (int)(iy - 289.0f * floorf(iy / 289.0f));
+    const int e1x = gt ? 1 : 0, e1y = gt ? 0 : 1;
+    const float4 G0 = T->grad2[T->perm[T->perm[jy] + jx]];
+    const float4 G1 = T->grad2[T->perm[T->perm[jy + e1y] + jx + e1x]];
+    const float4 G2 = T->grad2[T->perm[T->perm[jy + 1] + jx + 1]];
     float m0 = fmaxf(0.5f - fmaf(x0x, x0x, x0y * x0y), 0.0f);
     float m1 = fmaxf(0.5f - fmaf(x1x, x1x, x1y * x1y), 0.0f);
     float m2 = fmaxf(0.5f - fmaf(x2x, x2x, x2y * x2y), 0.0f);
     m0 = m0 * m0; m1 = m1 * m1; m2 = m2 * m2;
     m0 = m0 * m0; m1 = m1 * m1; m2 = m2 * m2;
-    // x = 2*fract(p*C.w) - 1 ; h = |x| - 0.5 ; ox = floor(x + 0.5) ; a0 = x - ox
-    float q0 = p0 * C3, q1 = p1 * C3, q2 = p2 * C3;
-    float gx0 = fmaf(q0 - floorf(q0), 2.0f, -1.0f);
-    float gx1 = fmaf(q1 - floorf(q1), 2.0f, -1.0f);
-    float gx2 = fmaf(q2 - floorf(q2), 2.0f, -1.0f);
-    float h0 = fabsf(gx0) - 0.5f, h1 = fabsf(gx1) - 0.5f, h2 = fabsf(gx2) - 0.5f;
-    float a0 = gx0 - floorf(gx0 + 0.5f), a1 = gx1 - floorf(gx1 + 0.5f), a2 = gx2 - floorf(gx2 + 0.5f);
-    // m *= 1.79284291400159 - 0.85373472095314 * (a0*a0 + h*h)
-    m0 = m0 * fmaf(fmaf(h0, h0, a0 * a0), -0.85373472095314f, 1.79284291400159f);
-    m1 = m1 * fmaf(fmaf(h1, h1, a1 * a1), -0.85373472095314f, 1.79284291400159f);
-    m2 = m2 * fmaf(fmaf(h2, h2, a2 * a2), -0.85373472095314f, 1.79284291400159f);
+    // m *= 1.79284291400159 - 0.85373472095314 * (a0*a0 + h*h)   (tabulated: G.z)
+    m0 = m0 * G0.z; m1 = m1 * G1.z; m2 = m2 * G2.z;
     // g = a0*x.x + h*x.y  -> fma(x.y, h, x.x*a0)
-    float g0 = fmaf(x0y, h0, x0x * a0);
-    float g1 = fmaf(x1y, h1, x1x * a1);
-    float g2 = fmaf(x2y, h2, x2x * a2);
+    float g0 = fmaf(x0y, G0.y, x0x * G0.x);
+    float g1 = fmaf(x1y, G1.y, x1x * G1.x);
+    float g2 = fmaf(x2y, G2.y, x2x * G2.x);
     // 130 * dot(m, g): mul on .y, fma .x, fma .z
     return fmaf(g2, m2, fmaf(g0, m0, g1 * m1));
 }
@@ -142,65 +199,40 @@ __device__ __forceinline__ float simplex2(float vx, float vy) { return 130.0f * 
 template <bool SKEW_Y = false>
 __device__ MMG_NOISE_INLINE float simplex3_raw(float vx, float vy, float vz)
 {
+    const NoiseTab* T = noise_tab();
     const float C = 1.0f / 3.0f, D = 1.0f / 6.0f;
-    const float NZ = 0.142857142857f;           // n_
-    const float NX = NZ * 2.0f;                  // ns.x = n_*D.w - D.x
-    const float NY = NZ * 0.5f - 1.0f;           // ns.y = n_*D.y - D.z
     float s = SKEW_Y ? fmaf(vz, C, fmaf(vx, C, vy * C)) : fmaf(vz, C, fmaf(vy, C, vx * C));
     float ix = floorf(vx + s), iy = floorf(vy + s), iz = floorf(vz + s);
     float t = fmaf(iz, D, fmaf(ix, D, iy * D));
     float x0x = (vx - ix) + t, x0y = (vy - iy) + t, x0z = (vz - iz) + t;
-    // g = step(x0.yzx, x0) ; l = 1 - g ; i1 = min(g, l.zxy) ; i2 = max(g, l.zxy)
-    float gx = (x0x < x0y) ? 0.0f : 1.0f, gy = (x0y < x0z) ? 0.0f : 1.0f, gz = (x0z < x0x) ? 0.0f : 1.0f;
-    float lx = 1.0f - gx, ly = 1.0f - gy, lz = 1.0f - gz;
-    float i1x = fminf(gx, lz), i1y = fminf(gy, lx), i1z = fminf(gz, ly);
-    float i2x = fmaxf(gx, lz), i2y = fmaxf(gy, lx), i2z = fmaxf(gz, ly);
-    float x1x = (x0x - i1x) + D, x1y = (x0y - i1y) + D, x1z = (x0z - i1z) + D;
-    float x2x = (x0x - i2x) + C, x2y = (x0y - i2y) + C, x2z = (x0z - i2z) + C;
+    // g = step(x0.yzx, x0) ; l = 1 - g ; i1 = min(g, l.zxy) ; i2 = max(g, l.zxy)   (all 0 / 1)
+    const bool gx = !(x0x < x0y), gy = !(x0y < x0z), gz = !(x0z < x0x);
+    const bool a1x = gx && !gz, a1y = gy && !gx, a1z = gz && !gy;
+    const bool a2x = gx || !gz, a2y = gy || !gx, a2z = gz || !gy;
+    float x1x = (x0x - (a1x ? 1.0f : 0.0f)) + D, x1y = (x0y - (a1y ? 1.0f : 0.0f)) + D, x1z = (x0z - (a1z ? 1.0f : 0.0f)) + D;
+    float x2x = (x0x - (a2x ? 1.0f : 0.0f)) + C, x2y = (x0y - (a2y ? 1.0f : 0.0f)) + C, x2z = (x0z - (a2z ? 1.0f : 0.0f)) + C;
     float x3x = x0x - 0.5f, x3y = x0y - 0.5f, x3z = x0z - 0.5f;
-    float mx = sx_mod289(ix), my = sx_mod289(iy), mz = sx_mod289(iz);
-    float p[4];
-    {
-        const float ez[4] = {0.0f, i1z, i2z, 1.0f}, ey[4] = {0.0f, i1y, i2y, 1.0f}, ex[4] = {0.0f, i1x, i2x, 1.0f};
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            p[k] = sx_permute(sx_permute(sx_permute(mz + ez[k]) + my + ey[k]) + mx + ex[k]);
-    }
-    float gxk[4], gyk[4], hk[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-    {
-        float j = p[k] - 49.0f * floorf((p[k] * NZ) * NZ);   // exact (integers)
-        float x_ = floorf(j * NZ);
-        float y_ = floorf(j - 7.0f * x_);
-        gxk[k] = fmaf(x_, NX, NY);
-        gyk[k] = fmaf(y_, NX, NY);
-        hk[k] = (1.0f - fabsf(gxk[k])) - fabsf(gyk[k]);
-    }
-    const float xsx[4] = {x0x, x1x, x2x, x3x}, xsy[4] = {x0y, x1y, x2y, x3y}, xsz[4] = {x0z, x1z, x2z, x3z};
-    float md[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-    {
-        // a = b + s*sh with s = floor(b)*2+1, sh = -step(h, 0)
-        float sh = (hk[k] <= 0.0f) ? -1.0f : 0.0f;
-        float ax = fmaf(fmaf(floorf(gxk[k]), 2.0f, 1.0f), sh, gxk[k]);
-        float ay = fmaf(fmaf(floorf(gyk[k]), 2.0f, 1.0f), sh, gyk[k]);
-        float az = hk[k];
-        // norm = taylorInvSqrt(dot(p,p)); dot3 = fma(z,z, fma(x,x, y*y))
-        float nrm = fmaf(fmaf(az, az, fmaf(ax, ax, ay * ay)), -0.85373472095314f, 1.79284291400159f);
-        ax = ax * nrm; ay = ay * nrm; az = az * nrm;
-        float X = xsx[k], Y = xsy[k], Z = xsz[k];
-        float m = fmaxf(0.6f - fmaf(Z, Z, fmaf(X, X, Y * Y)), 0.0f);
-        m = m * m;
-        m = m * m;
-        float dpx = fmaf(Z, az, fmaf(X, ax, Y * ay));
-        md[k] = m;
-        gxk[k] = dpx;   // reuse: dot(p_k, x_k)
-    }
+    const int jx = (int)sx_mod289(ix), jy = (int)sx_mod289(iy), jz = (int)sx_mod289(iz);
+    // p = permute(permute(permute(i.z + e.z) + i.y + e.y) + i.x + e.x) for the four corners
+    const unsigned short* P = T->perm;
+    const int p0 = P[P[P[jz] + jy] + jx];
+    const int p1 = P[P[P[jz + (a1z ? 1 : 0)] + jy + (a1y ? 1 : 0)] + jx + (a1x ? 1 : 0)];
+    const int p2 = P[P[P[jz + (a2z ? 1 : 0)] + jy + (a2y ? 1 : 0)] + jx + (a2x ? 1 : 0)];
+    const int p3 = P[P[P[jz + 1] + jy + 1] + jx + 1];
+    const float4 G0 = T->grad3[p0], G1 = T->grad3[p1], G2 = T->grad3[p2], G3 = T->grad3[p3];
+    float m0 = fmaxf(0.6f - fmaf(x0z, x0z, fmaf(x0x, x0x, x0y * x0y)), 0.0f);
+    float m1 = fmaxf(0.6f - fmaf(x1z, x1z, fmaf(x1x, x1x, x1y * x1y)), 0.0f);
+    float m2 = fmaxf(0.6f - fmaf(x2z, x2z, fmaf(x2x, x2x, x2y * x2y)), 0.0f);
+    float m3 = fmaxf(0.6f - fmaf(x3z, x3z, fmaf(x3x, x3x, x3y * x3y)), 0.0f);
+    m0 = m0 * m0; m1 = m1 * m1; m2 = m2 * m2; m3 = m3 * m3;
+    m0 = m0 * m0; m1 = m1 * m1; m2 = m2 * m2; m3 = m3 * m3;
+    const float d0 = fmaf(x0z, G0.z, fmaf(x0x, G0.x, x0y * G0.y));
+    const float d1 = fmaf(x1z, G1.z, fmaf(x1x, G1.x, x1y * G1.y));
+    const float d2 = fmaf(x2z, G2.z, fmaf(x2x, G2.x, x2y * G2.y));
+    const float d3 = fmaf(x3z, G3.z, fmaf(x3x, G3.x, x3y * G3.y));
     // 42 * dot(m*m, dots): (t.x + t.y) + (t.z + t.w) with fma on .y and .w
-    float a = fmaf(md[1], gxk[1], md[0] * gxk[0]);
-    float b = fmaf(md[3], gxk[3], md[2] * gxk[2]);
+    float a = fmaf(m1, d1, m0 * d0);
+    float b = fmaf(m3, d3, m2 * d2);
     return b + a;
 }
 template <bool SKEW_Y = false>

@@ -630,8 +630,10 @@ __device__ MMG_NOISE_INLINE bool place_cave_feature(const CaveFeaturePlacement& 
     const int tx = fx, ty = wy - (cp.y + lh), tz = fz;
     const V3 pos = v3((float)fx, (float)fy, (float)fz);
     V3 top = v3((float)tx, (float)ty, (float)tz);
-    Minstd frng = make_rng4(cp.x, cp.y, cp.z, 398132);
-    Minstd brng = make_rng4(wx, wy, wz, 9322743);
+    // the reference seeds both engines on entry (featurePlacement.hpp:1119-1120); nearly every call ends at a
+    // geometric rejection that needs neither, so they are seeded where the first draw happens (same streams)
+#define MMG_FRNG() Minstd frng = make_rng4(cp.x, cp.y, cp.z, 398132)
+#define MMG_BRNG() Minstd brng = make_rng4(wx, wy, wz, 9322743)
     switch (cp.feature)
     {
     case CF_NONE: return false;
@@ -642,9 +644,11 @@ __device__ MMG_NOISE_INLINE bool place_cave_feature(const CaveFeaturePlacement& 
     case CF_CAVE_VINE:
     {
         if (tx != 0 || tz != 0) return false;
+        MMG_FRNG();
         int height = (int)fmaf(frng.u01(), 12.f, 3.f);
         height = height < lh ? height : lh;
         if (!in_range_i(ty, -height, 0)) return false;
+        MMG_BRNG();
         const bool glowing = brng.u01() < 0.2f;
         if (ty == -height) *out = glowing ? B_CAVE_VINES_GLOW_END : B_CAVE_VINES_END;
         else *out = glowing ? B_CAVE_VINES_GLOW_MAIN : B_CAVE_VINES_MAIN;
@@ -653,6 +657,10 @@ __device__ MMG_NOISE_INLINE bool place_cave_feature(const CaveFeaturePlacement& 
     case CF_GLOWSTONE_CLUSTER:
     {
         top.y = top.y * 1.35f;
+        // the scale below is >= 1 and rounding is monotone, so |top * scale| >= |top|: beyond 6 before scaling
+        // is beyond 6 after it
+        if (len3(top) > 6.f) return false;
+        MMG_FRNG();
         top = top * fmaf(frng.u01(), 0.5f, 1.f);
         const float r = len3(top);
         if (r > 6.f) return false;
@@ -664,11 +672,14 @@ __device__ MMG_NOISE_INLINE bool place_cave_feature(const CaveFeaturePlacement& 
     case CF_STORMLIGHT_SPHERE:
     case CF_CEILING_STORMLIGHT_SPHERE:
     {
-        const float radius = fmaf(frng.u01(), 4.f, 3.5f);
         const float dist = cp.feature == CF_STORMLIGHT_SPHERE ? len3(pos) : len3(top);
+        if (dist > 7.5f) return false;      // radius = fma(u01, 4, 3.5) <= 7.5
+        MMG_FRNG();
+        const float radius = fmaf(frng.u01(), 4.f, 3.5f);
         if (dist > radius) return false;
         const float rr = dist / radius;
         const float chance = ss_t((rr + -0.4f) / (0.2f - 0.4f));
+        MMG_BRNG();
         if (brng.u01() < chance) *out = B_GLOWSTONE;
         else *out = random_crystal_block(frng.u01());
         return true;
@@ -685,12 +696,18 @@ __device__ MMG_NOISE_INLINE bool place_cave_feature(const CaveFeaturePlacement& 
         radius = 4.f * fmaf(2.f * radius, radius, 0.5f);
         if (dist > radius) return false;
         if (dist / radius < 0.4f) *out = B_GLOWSTONE;
-        else *out = random_crystal_block(frng.u01());
+        else
+        {
+            MMG_FRNG();
+            *out = random_crystal_block(frng.u01());
+        }
         return true;
     }
     case CF_WARPED_FUNGUS:
     {
         if (abs(fx) + abs(fz) > 6) return false;
+        if (fy < -2 || fy > 8) return false;      // height = (int)fma(u01, 3, 2.5) <= 5, tested again below
+        MMG_FRNG();
         const int height = (int)fmaf(frng.u01(), 3.0f, 2.5f);
         if (fy < -2 || fy > height + 3) return false;
         if (fx == 0 && fz == 0 && in_range_i(fy, 0, height)) { *out = B_WARPED_STEM; return true; }
@@ -698,6 +715,7 @@ __device__ MMG_NOISE_INLINE bool place_cave_feature(const CaveFeaturePlacement& 
         if (in_range_i(sh, 0, 1) && abs(fx) + abs(fz) == 1)
         {
             const float chance = sh == 0 ? 0.2f : 0.5f;
+            MMG_BRNG();
             if (brng.u01() < chance) { *out = B_SHROOMLIGHT; return true; }
         }
         const float capRadius = len2(pos.x, pos.z);
@@ -712,6 +730,8 @@ __device__ MMG_NOISE_INLINE bool place_cave_feature(const CaveFeaturePlacement& 
     {
         const int m2 = abs(fx) + abs(fz);
         if (m2 > 4) return false;
+        if (fy < -2 || fy > 12) return false;     // height = (int)fma(u01, 4.5, 4.5) <= 9, tested again below
+        MMG_FRNG();
         const int height = (int)fmaf(frng.u01(), 4.5f, 4.5f);
         if (fy < -2 || fy > height + 3) return false;
         if (fx == 0 && fz == 0)
@@ -732,7 +752,13 @@ __device__ MMG_NOISE_INLINE bool place_cave_feature(const CaveFeaturePlacement& 
                 const int rx = gx + (int)(hash_fract(fmaf(cz, 402.98f, fmaf(cx, 238.68f, cy * 491.28f))) * 2.f);
                 const int ry = gy + (int)(hash_fract(fmaf(cz, 747.42f, fmaf(cx, 654.37f, cy * 560.45f))) * 2.f);
                 const int rz = gz + (int)(hash_fract(fmaf(cz, 674.81f, fmaf(cx, 640.88f, cy * 151.81f))) * 2.f);
-                if (wx == rx && wy == ry && wz == rz && brng.u01() < 0.65f) *out = B_SHROOMLIGHT;
+                bool light = wx == rx && wy == ry && wz == rz;
+                if (light)
+                {
+                    MMG_BRNG();
+                    light = brng.u01() < 0.65f;
+                }
+                if (light) *out = B_SHROOMLIGHT;
                 else *out = B_AMBER_WART;
                 return true;
             }
@@ -741,6 +767,8 @@ __device__ MMG_NOISE_INLINE bool place_cave_feature(const CaveFeaturePlacement& 
     }
     }
     return false;
+#undef MMG_FRNG
+#undef MMG_BRNG
 }
 
 }  // namespace mmg

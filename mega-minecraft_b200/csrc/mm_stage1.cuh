@@ -14,6 +14,7 @@ namespace mmg {
 __global__ void __launch_bounds__(256) k_heightfield(const int2* __restrict__ origins, float* __restrict__ heightfield,
                                                      float* __restrict__ biomeWeights)
 {
+    noise_tab_stage();
     const int chunk = blockIdx.x;
     const int idx = threadIdx.x;            // x + 16*z
     const int2 o = origins[chunk];

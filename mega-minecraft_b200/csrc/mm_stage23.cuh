@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(256) k_layers(const int* __restrict__ chunkLis
                                                 float* __restrict__ layersOut, int nx)
 {
     __shared__ float sh[18 * 18];
+    noise_tab_stage();
     const int li = blockIdx.x;
     const int chunk = chunkList ? chunkList[li] : li;
     const int idx = threadIdx.x, x = idx & 15, z = idx >> 4;

@@ -186,6 +186,7 @@ struct CaveColumn { float obw, ravTop, ravDepth; int ravActive; };
 __global__ void __launch_bounds__(256) k_cave_columns(const int* __restrict__ chunkList, const int2* __restrict__ origins,
                                                       const float* __restrict__ biomeWeights, CaveColumn* __restrict__ cols)
 {
+    noise_tab_stage();
     const int li = blockIdx.x, chunk = chunkList ? chunkList[li] : li;
     const int idx = threadIdx.x;
     const int2 o = origins[chunk];
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(128, 8) k_caves(const int* __restrict__ chunkL
     __shared__ int shNumFlips;
     __shared__ int shBox[3];
     __shared__ float shJit[3 * kCaveBox * kCaveBox * kCaveBox];
+    noise_tab_stage();
     const int li = blockIdx.x >> 8, idx = blockIdx.x & 255;
     const int chunk = chunkList ? chunkList[li] : li;
     const int2 o = origins[chunk];

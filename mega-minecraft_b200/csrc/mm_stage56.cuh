@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(kFillSeg, 8) k_fill_terrain(const int* __restr
         shCL[t - (NUM_BIOMES + NUM_MATERIALS + 1)] = caveLayers[((size_t)chunk * 256 + idx) * MAX_CAVE_LAYERS + (t - (NUM_BIOMES + NUM_MATERIALS + 1))];
     const int2 o = origins[chunk];
     const int wx = o.x + (idx & 15), wz = o.y + (idx >> 4);
-    __syncthreads();
+    noise_tab_stage();      // includes the barrier that publishes the column data
     bool lush = false;
     uint8_t block = fill_place_block(shW, shLH, shCL, y, height, wx, wz, &lush);
     // warp-aggregated append of the pending voxels
@@ -366,6 +366,8 @@ __global__ void __launch_bounds__(128) k_fill_lush(const int2* __restrict__ orig
                                                    const int* __restrict__ lushCount, uint8_t* __restrict__ blocks)
 {
     const int n = min(*lushCount, kLushQueueCap);
+    if (blockIdx.x * blockDim.x >= n) return;
+    noise_tab_stage();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
         const uint2 e = lushQueue[i];
@@ -443,7 +445,7 @@ __global__ void __launch_bounds__(kFillSeg, 8) k_fill_features(const int* __rest
             nColC += total;
         }
     if (nColF == 0 && nColC == 0) return;
-    __syncthreads();
+    noise_tab_stage();      // includes the barrier that publishes the candidate lists
     uint8_t* out = blocks + (size_t)chunk * 98304 + (size_t)idx * 384 + y;
     const uint8_t block = *out;
     uint8_t fblock = 0;

@@ -118,6 +118,8 @@ int mmgen_init(int device)
         return 1;
     }
     if (!g_stream) MMG_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    MMG_LAUNCH(k_init_noise_tables, 3, 256, 0, g_stream);     // simplex lattice tables (mm_arith.cuh)
+    MMG_CUDA(cudaStreamSynchronize(g_stream));
     g_device = device;
     g_ready = true;
     return 0;
@@ -149,7 +151,7 @@ int mmgen_heightfields(int n, const int32_t* origins, float* out_heightfield, fl
     float* d_h = (float*)g_scratch[1].ptr;
     float* d_w = (float*)g_scratch[2].ptr;
     MMG_CUDA(cudaMemcpyAsync(d_o, origins, (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, g_stream));
-    MMG_LAUNCH(k_heightfield, n, 256, 0, g_stream, d_o, d_h, d_w);
+    MMG_LAUNCH(k_heightfield, n, 256, kNoiseSmemBytes, g_stream, d_o, d_h, d_w);
     if (out_heightfield) MMG_CUDA(cudaMemcpyAsync(out_heightfield, d_h, (size_t)n * 256 * sizeof(float), cudaMemcpyDeviceToHost, g_stream));
     if (out_biomeWeights) MMG_CUDA(cudaMemcpyAsync(out_biomeWeights, d_w, (size_t)n * NUM_BIOMES * 256 * sizeof(float), cudaMemcpyDeviceToHost, g_stream));
     MMG_CUDA(cudaStreamSynchronize(g_stream));
@@ -209,7 +211,7 @@ extern "C" int mmgen_layers(int n, const int32_t* origins, const float* heightfi
     MMG_CUDA(cudaMemcpyAsync(g_scratch[0].ptr, origins, (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, g_stream));
     MMG_CUDA(cudaMemcpyAsync(g_scratch[1].ptr, heightfield18, (size_t)n * 324 * sizeof(float), cudaMemcpyHostToDevice, g_stream));
     MMG_CUDA(cudaMemcpyAsync(g_scratch[2].ptr, biomeWeights, (size_t)n * NUM_BIOMES * 256 * sizeof(float), cudaMemcpyHostToDevice, g_stream));
-    MMG_LAUNCH(k_layers<false>, n, 256, 0, g_stream, (const int*)nullptr, (const int2*)g_scratch[0].ptr,
+    MMG_LAUNCH(k_layers<false>, n, 256, kNoiseSmemBytes, g_stream, (const int*)nullptr, (const int2*)g_scratch[0].ptr,
                (const float*)g_scratch[1].ptr, (const float*)g_scratch[2].ptr, (float*)g_scratch[3].ptr, 0);
     MMG_CUDA(cudaMemcpyAsync(out_layers, g_scratch[3].ptr, (size_t)n * NUM_MATERIALS * 256 * sizeof(float), cudaMemcpyDeviceToHost, g_stream));
     MMG_CUDA(cudaStreamSynchronize(g_stream));
@@ -245,9 +247,9 @@ extern "C" int mmgen_caves(int n, const int32_t* origins, const float* heightfie
     MMG_CUDA(cudaMemcpyAsync(g_scratch[0].ptr, origins, (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, g_stream));
     MMG_CUDA(cudaMemcpyAsync(g_scratch[1].ptr, heightfield, (size_t)n * 256 * sizeof(float), cudaMemcpyHostToDevice, g_stream));
     MMG_CUDA(cudaMemcpyAsync(g_scratch[2].ptr, biomeWeights, (size_t)n * NUM_BIOMES * 256 * sizeof(float), cudaMemcpyHostToDevice, g_stream));
-    MMG_LAUNCH(k_cave_columns, n, 256, 0, g_stream, (const int*)nullptr, (const int2*)g_scratch[0].ptr,
+    MMG_LAUNCH(k_cave_columns, n, 256, kNoiseSmemBytes, g_stream, (const int*)nullptr, (const int2*)g_scratch[0].ptr,
                (const float*)g_scratch[2].ptr, (CaveColumn*)g_scratch[6].ptr);
-    MMG_LAUNCH(k_caves, n * 256, 128, 0, g_stream, (const int*)nullptr, (const int2*)g_scratch[0].ptr,
+    MMG_LAUNCH(k_caves, n * 256, 128, kNoiseSmemBytes, g_stream, (const int*)nullptr, (const int2*)g_scratch[0].ptr,
                (const float*)g_scratch[1].ptr, (const CaveColumn*)g_scratch[6].ptr, (CaveLayer*)g_scratch[3].ptr);
     MMG_CUDA(cudaMemcpyAsync(out_caveLayers, g_scratch[3].ptr, clBytes, cudaMemcpyDeviceToHost, g_stream));
     MMG_CUDA(cudaStreamSynchronize(g_stream));
@@ -262,10 +264,10 @@ static int launchFill(int m, const int* d_list, const int2* d_origins, const flo
                       int strideF, int strideCF, uint8_t* d_blocks, uint2* d_lushQueue, int* d_lushCount, cudaStream_t stream)
 {
     MMG_CUDA(cudaMemsetAsync(d_lushCount, 0, sizeof(int), stream));
-    MMG_LAUNCH(k_fill_terrain, m * 256 * 3, kFillSeg, 0, stream, d_list, d_origins, d_height, d_weights, d_layers, d_caves, d_blocks,
+    MMG_LAUNCH(k_fill_terrain, m * 256 * 3, kFillSeg, kNoiseSmemBytes, stream, d_list, d_origins, d_height, d_weights, d_layers, d_caves, d_blocks,
                d_lushQueue, d_lushCount);
-    MMG_LAUNCH(k_fill_lush, kNumSMs * 8, 128, 0, stream, d_origins, (const uint2*)d_lushQueue, (const int*)d_lushCount, d_blocks);
-    MMG_LAUNCH(k_fill_features, m * 256 * 3, kFillSeg, 0, stream, d_list, d_origins, d_gF, d_gCF, d_info, strideF, strideCF, d_blocks);
+    MMG_LAUNCH(k_fill_lush, kNumSMs * 8, 128, kNoiseSmemBytes, stream, d_origins, (const uint2*)d_lushQueue, (const int*)d_lushCount, d_blocks);
+    MMG_LAUNCH(k_fill_features, m * 256 * 3, kFillSeg, kNoiseSmemBytes, stream, d_list, d_origins, d_gF, d_gCF, d_info, strideF, strideCF, d_blocks);
     MMG_LAUNCH(k_decorators, m, 256, 0, stream, d_list, m, d_origins, d_height, d_weights, d_caves, d_blocks);
     return 0;
 }   // chunks gathered + filled per launch group (bounds the gathered-list buffers)
@@ -413,7 +415,7 @@ static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
         if (!w->d_height) MMG_CUDA(cudaMalloc(&w->d_height, (size_t)w->n * 256 * sizeof(float)));
         if (!w->d_weights) MMG_CUDA(cudaMalloc(&w->d_weights, (size_t)w->n * NUM_BIOMES * 256 * sizeof(float)));
         MMG_CUDA(cudaEventRecord(w->ev[0], w->stream));
-        MMG_LAUNCH(k_heightfield, w->n, 256, 0, w->stream, w->d_origins, w->d_height, w->d_weights);
+        MMG_LAUNCH(k_heightfield, w->n, 256, kNoiseSmemBytes, w->stream, w->d_origins, w->d_height, w->d_weights);
         MMG_CUDA(cudaEventRecord(w->ev[1], w->stream));
         for (auto& s : w->stage) s = std::max<uint8_t>(s, 1);
     }
@@ -431,7 +433,7 @@ static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
             if (!w->d_layers) MMG_CUDA(cudaMalloc(&w->d_layers, (size_t)w->n * NUM_MATERIALS * 256 * sizeof(float)));
             if (!w->d_list) MMG_CUDA(cudaMalloc(&w->d_list, (size_t)w->n * sizeof(int)));
             MMG_CUDA(cudaMemcpyAsync(w->d_list, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, w->stream));
-            MMG_LAUNCH(k_layers<true>, (int)list.size(), 256, 0, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
+            MMG_LAUNCH(k_layers<true>, (int)list.size(), 256, kNoiseSmemBytes, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
                        (const float*)w->d_height, (const float*)w->d_weights, w->d_layers, nx);
             MMG_CUDA(cudaStreamSynchronize(w->stream));   // list buffer is reused below
             for (int i : list) w->stage[i] = std::max<uint8_t>(w->stage[i], 2);
@@ -497,9 +499,9 @@ static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
             if (!w->d_caveCols) MMG_CUDA(cudaMalloc(&w->d_caveCols, (size_t)w->n * 256 * sizeof(CaveColumn)));
             if (!w->d_list) MMG_CUDA(cudaMalloc(&w->d_list, (size_t)w->n * sizeof(int)));
             MMG_CUDA(cudaMemcpyAsync(w->d_list, list.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, w->stream));
-            MMG_LAUNCH(k_cave_columns, m, 256, 0, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
+            MMG_LAUNCH(k_cave_columns, m, 256, kNoiseSmemBytes, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
                        (const float*)w->d_weights, w->d_caveCols);
-            MMG_LAUNCH(k_caves, m * 256, 128, 0, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
+            MMG_LAUNCH(k_caves, m * 256, 128, kNoiseSmemBytes, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
                        (const float*)w->d_height, (const CaveColumn*)w->d_caveCols, w->d_caves);
             MMG_CUDA(cudaStreamSynchronize(w->stream));
             for (int i : list) w->stage[i] = 4;
