@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(256) k_cave_columns(const int* __restrict__ ch
 
 __global__ void __launch_bounds__(128, 8) k_caves(const int* __restrict__ chunkList, const int2* __restrict__ origins,
                                                const float* __restrict__ heightfield, const CaveColumn* __restrict__ cols,
-                                               CaveLayer* __restrict__ caveLayers)
+                                               CaveLayer* __restrict__ caveLayers, uint2* __restrict__ biomeQueue, int* __restrict__ biomeCount,
+                                               int biomeQueueCap)
 {
     __shared__ unsigned int shFilled[13];     // bit y = 1 if solid; word 12 = 0 (y = 384 is "not filled")
     __shared__ int shFlips[2 * MAX_CAVE_LAYERS];
@@ -293,22 +294,62 @@ __global__ void __launch_bounds__(128, 8) k_caves(const int* __restrict__ chunkL
     }
     __syncthreads();
     const int nflips = min(shNumFlips, 2 * MAX_CAVE_LAYERS);
-    if (tid < 2 * MAX_CAVE_LAYERS)
+    if (tid < MAX_CAVE_LAYERS)
     {
-        // thread t handles layer t/2, bottom (even t) or top (odd t) biome
-        const int l = tid >> 1, top = tid & 1;
+        // layer t: (start, end] from consecutive flips; the two cave biomes are looked up by k_cave_biomes
+        const int l = tid;
         const int start = (2 * l < nflips) ? shFlips[2 * l] : 384;
         const int end = (2 * l + 1 < nflips) ? shFlips[2 * l + 1] : 384;
-        int biome = CB_NONE;
-        if (!top) { if (start != 384) biome = cave_biome(wx, start, wz, maxHeight, 329271348); }
-        else { if (end != 384) biome = cave_biome(wx, end + 1, wz, maxHeight, 4982921); }
-        const int other = __shfl_xor_sync(0xffffffffu, biome, 1);
-        if (!top)
+        CaveLayer cl;
+        cl.start = start; cl.end = end; cl.bottomBiome = CB_NONE; cl.topBiome = CB_NONE; cl.pad[0] = cl.pad[1] = 0;
+        const int need = (start != 384 ? 1 : 0) + (end != 384 ? 1 : 0);
+        // warp-aggregated append of this column's lookups (warp 0 holds all 32 layers)
+        int incl = need;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
         {
-            CaveLayer cl;
-            cl.start = start; cl.end = end; cl.bottomBiome = (uint8_t)biome; cl.topBiome = (uint8_t)other; cl.pad[0] = cl.pad[1] = 0;
-            out[l] = cl;
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
         }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int base = 0;
+        if (lane == 0 && total > 0) base = atomicAdd(biomeCount, total);
+        base = __shfl_sync(0xffffffffu, base, 0) + incl - need;
+        const unsigned col = (unsigned)(chunk * 256 + idx);
+        if (start != 384)
+        {
+            if (base < biomeQueueCap) biomeQueue[base] = make_uint2(col, (unsigned)(l << 10 | start));
+            else cl.bottomBiome = (uint8_t)cave_biome(wx, start, wz, maxHeight, 329271348);
+            ++base;
+        }
+        if (end != 384)
+        {
+            if (base < biomeQueueCap) biomeQueue[base] = make_uint2(col, (unsigned)(l << 10 | 1 << 9 | (end + 1)));
+            else cl.topBiome = (uint8_t)cave_biome(wx, end + 1, wz, maxHeight, 4982921);
+        }
+        out[l] = cl;
+    }
+}
+
+// getCaveBiome for the bottom / top of every cave layer (chunk.cu:915-935), one queued lookup per thread.
+// k_caves finds ~5 lookups per column; run there they would occupy 5 lanes of a warp for ~5 kFLOP each.
+__global__ void __launch_bounds__(128) k_cave_biomes(const int2* __restrict__ origins, const float* __restrict__ heightfield,
+                                                     const uint2* __restrict__ biomeQueue, const int* __restrict__ biomeCount, int biomeQueueCap,
+                                                     CaveLayer* __restrict__ caveLayers)
+{
+    const int n = min(*biomeCount, biomeQueueCap);
+    if (blockIdx.x * blockDim.x >= n) return;
+    noise_tab_stage();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const uint2 e = biomeQueue[i];
+        const int chunk = (int)(e.x >> 8), idx = (int)(e.x & 255u);
+        const int l = (int)(e.y >> 10), top = (int)((e.y >> 9) & 1u), y = (int)(e.y & 511u);
+        const int2 o = origins[chunk];
+        const int b = cave_biome(o.x + (idx & 15), y, o.y + (idx >> 4), heightfield[e.x], top ? 4982921 : 329271348);
+        CaveLayer* cl = caveLayers + (size_t)e.x * MAX_CAVE_LAYERS + l;
+        if (top) cl->topBiome = (uint8_t)b;
+        else cl->bottomBiome = (uint8_t)b;
     }
 }
 

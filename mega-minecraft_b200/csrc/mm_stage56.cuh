@@ -449,16 +449,27 @@ __global__ void __launch_bounds__(kFillSeg, 8) k_fill_features(const int* __rest
     uint8_t* out = blocks + (size_t)chunk * 98304 + (size_t)idx * 384 + y;
     const uint8_t block = *out;
     uint8_t fblock = 0;
-    bool placed = false;
+    bool placed = false, ended = false;      // ended: this voxel's scan met the NONE terminator
+    // The scan is warp-cooperative: 32 candidates at a time are tested against the y range of the warp's
+    // 32 voxels (one candidate per lane), and only the ones that overlap it are then offered, in list
+    // order, to the lanes whose own y lies inside the candidate's range.
+    const int lane = t & 31, yw0 = y - lane, yw1 = yw0 + 31;
     if (nColF <= kColCapF)
     {
-        for (int c = 0; c < nColF; ++c)
+        for (int c0 = 0; c0 < nColF; c0 += 32)
         {
-            const Cand k = shCandF[c];
-            if (y < k.lo || y > k.hi || (block != B_AIR && !k.canReplace)) continue;
-            const FeaturePlacement fp = f[k.idx];
-            if (fp.feature == F_NONE) break;
-            if (place_feature(fp, wx, y, wz, &fblock)) { placed = true; break; }
+            const int c = c0 + lane;
+            unsigned m = __ballot_sync(0xffffffffu, c < nColF && shCandF[c].lo <= yw1 && shCandF[c].hi >= yw0);
+            while (m)
+            {
+                const Cand k = shCandF[c0 + __ffs(m) - 1];
+                m &= m - 1;
+                if (placed || ended || y < k.lo || y > k.hi || (block != B_AIR && !k.canReplace)) continue;
+                const FeaturePlacement fp = f[k.idx];
+                if (fp.feature == F_NONE) { ended = true; continue; }
+                placed = place_feature(fp, wx, y, wz, &fblock);
+            }
+            if (__all_sync(0xffffffffu, placed || ended)) break;
         }
     }
     else
@@ -473,29 +484,34 @@ __global__ void __launch_bounds__(kFillSeg, 8) k_fill_features(const int* __rest
             if (place_feature(fp, wx, y, wz, &fblock)) { placed = true; break; }
         }
     }
-    if (!placed)
+    ended = false;
+    if (nColC <= kColCapC)
     {
-        if (nColC <= kColCapC)
+        for (int c0 = 0; c0 < nColC; c0 += 32)
         {
-            for (int c = 0; c < nColC; ++c)
+            const int c = c0 + lane;
+            unsigned m = __ballot_sync(0xffffffffu, c < nColC && shCandC[c].lo <= yw1 && shCandC[c].hi >= yw0);
+            while (m)
             {
-                const Cand k = shCandC[c];
-                if (y < k.lo || y > k.hi || (block != B_AIR && !k.canReplace)) continue;
+                const Cand k = shCandC[c0 + __ffs(m) - 1];
+                m &= m - 1;
+                if (placed || ended || y < k.lo || y > k.hi || (block != B_AIR && !k.canReplace)) continue;
                 const CaveFeaturePlacement cp = cf[k.idx];
-                if (cp.feature == CF_NONE) break;
-                if (place_cave_feature(cp, wx, y, wz, &fblock)) { placed = true; break; }
+                if (cp.feature == CF_NONE) { ended = true; continue; }
+                placed = place_cave_feature(cp, wx, y, wz, &fblock);
             }
+            if (__all_sync(0xffffffffu, placed || ended)) break;
         }
-        else
+    }
+    else if (!placed)
+    {
+        for (int i = 0; i < gi.nCF; ++i)
         {
-            for (int i = 0; i < gi.nCF; ++i)
-            {
-                const CaveFeaturePlacement cp = cf[i];
-                if (cp.feature == CF_NONE) break;
-                if (block != B_AIR && !cp.canReplaceBlocks) continue;
-                if (y < cp.y + c_caveFeatureHeightBounds[cp.feature][0] || y > cp.y + cp.layerHeight + c_caveFeatureHeightBounds[cp.feature][1]) continue;
-                if (place_cave_feature(cp, wx, y, wz, &fblock)) { placed = true; break; }
-            }
+            const CaveFeaturePlacement cp = cf[i];
+            if (cp.feature == CF_NONE) break;
+            if (block != B_AIR && !cp.canReplaceBlocks) continue;
+            if (y < cp.y + c_caveFeatureHeightBounds[cp.feature][0] || y > cp.y + cp.layerHeight + c_caveFeatureHeightBounds[cp.feature][1]) continue;
+            if (place_cave_feature(cp, wx, y, wz, &fblock)) { placed = true; break; }
         }
     }
     if (placed) *out = fblock;

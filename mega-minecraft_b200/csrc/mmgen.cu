@@ -38,7 +38,7 @@ struct Scratch
         return 0;
     }
 };
-static Scratch g_scratch[8];
+static Scratch g_scratch[14];   // [0..7] stage inputs/outputs, [8..11] fill extras, [12..13] cave-biome queue
 static cudaStream_t g_stream = nullptr;
 
 static int requireReady()
@@ -69,7 +69,9 @@ struct MmgenWorld
     int* d_flags = nullptr;           // one "changed" flag per sweep of a batch
     int* d_list = nullptr;            // chunk index lists
     CaveLayer* d_caves = nullptr;     // [chunk][256][32]
-    CaveColumn* d_caveCols = nullptr; // per-column hoisted cave terms
+    CaveColumn* d_caveCols = nullptr; // per-column hoisted cave terms of one cave batch
+    uint2* d_caveQueue = nullptr;     // cave-biome lookups of one cave batch
+    int* d_caveCount = nullptr;
     FeaturePlacement* d_features = nullptr;          // own lists [chunk][kMaxOwnFeatures]
     CaveFeaturePlacement* d_caveFeatures = nullptr;  // own lists [chunk][kMaxOwnCaveFeatures]
     int* d_counts = nullptr;                         // [chunk][2]
@@ -233,6 +235,29 @@ extern "C" int mmgen_erode_zone(const float* gathered, float* out_eroded, int* o
     return 0;
 }
 
+constexpr int kCaveBatch = 4096;                       // chunks per cave launch group
+constexpr int kCaveBiomeQueueCap = kCaveBatch * 256 * 8;  // cave-biome lookups queued per group (avg ~5.4 per column)
+
+// the kernel sequence of Chunk::generateCaves for m chunks (d_list: chunk indices or null; column terms indexed by batch position)
+static int launchCaves(int m, const int* d_list, const int2* d_origins, const float* d_height, const float* d_weights, CaveColumn* d_cols,
+                       CaveLayer* d_caves, uint2* d_queue, int* d_count, cudaStream_t stream)
+{
+    for (int c0 = 0; c0 < m; c0 += kCaveBatch)
+    {
+        const int mb = std::min(kCaveBatch, m - c0);
+        const int* dl = d_list ? d_list + c0 : nullptr;
+        // without a list, chunk index == batch position: offset every per-chunk pointer instead
+        const size_t off = d_list ? 0 : (size_t)c0;
+        MMG_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
+        MMG_LAUNCH(k_cave_columns, mb, 256, kNoiseSmemBytes, stream, dl, d_origins + off, d_weights + off * NUM_BIOMES * 256, d_cols);
+        MMG_LAUNCH(k_caves, mb * 256, 128, kNoiseSmemBytes, stream, dl, d_origins + off, d_height + off * 256, (const CaveColumn*)d_cols,
+                   d_caves + off * 256 * MAX_CAVE_LAYERS, d_queue, d_count, kCaveBiomeQueueCap);
+        MMG_LAUNCH(k_cave_biomes, kNumSMs * 16, 128, kNoiseSmemBytes, stream, d_origins + off, d_height + off * 256, (const uint2*)d_queue,
+                   (const int*)d_count, kCaveBiomeQueueCap, d_caves + off * 256 * MAX_CAVE_LAYERS);
+    }
+    return 0;
+}
+
 extern "C" int mmgen_caves(int n, const int32_t* origins, const float* heightfield, const float* biomeWeights,
                            MmgenCaveLayer* out_caveLayers)
 {
@@ -243,14 +268,15 @@ extern "C" int mmgen_caves(int n, const int32_t* origins, const float* heightfie
     if (g_scratch[1].ensure((size_t)n * 256 * sizeof(float))) return 1;
     if (g_scratch[2].ensure((size_t)n * NUM_BIOMES * 256 * sizeof(float))) return 1;
     if (g_scratch[3].ensure(clBytes)) return 1;
-    if (g_scratch[6].ensure((size_t)n * 256 * sizeof(CaveColumn))) return 1;
+    if (g_scratch[6].ensure((size_t)std::min(n, kCaveBatch) * 256 * sizeof(CaveColumn))) return 1;
     MMG_CUDA(cudaMemcpyAsync(g_scratch[0].ptr, origins, (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, g_stream));
     MMG_CUDA(cudaMemcpyAsync(g_scratch[1].ptr, heightfield, (size_t)n * 256 * sizeof(float), cudaMemcpyHostToDevice, g_stream));
     MMG_CUDA(cudaMemcpyAsync(g_scratch[2].ptr, biomeWeights, (size_t)n * NUM_BIOMES * 256 * sizeof(float), cudaMemcpyHostToDevice, g_stream));
-    MMG_LAUNCH(k_cave_columns, n, 256, kNoiseSmemBytes, g_stream, (const int*)nullptr, (const int2*)g_scratch[0].ptr,
-               (const float*)g_scratch[2].ptr, (CaveColumn*)g_scratch[6].ptr);
-    MMG_LAUNCH(k_caves, n * 256, 128, kNoiseSmemBytes, g_stream, (const int*)nullptr, (const int2*)g_scratch[0].ptr,
-               (const float*)g_scratch[1].ptr, (const CaveColumn*)g_scratch[6].ptr, (CaveLayer*)g_scratch[3].ptr);
+    Scratch* Q = g_scratch + 12;
+    if (Q[0].ensure((size_t)kCaveBiomeQueueCap * sizeof(uint2)) || Q[1].ensure(sizeof(int))) return 1;
+    if (launchCaves(n, nullptr, (const int2*)g_scratch[0].ptr, (const float*)g_scratch[1].ptr, (const float*)g_scratch[2].ptr,
+                    (CaveColumn*)g_scratch[6].ptr, (CaveLayer*)g_scratch[3].ptr, (uint2*)Q[0].ptr, (int*)Q[1].ptr, g_stream))
+        return 1;
     MMG_CUDA(cudaMemcpyAsync(out_caveLayers, g_scratch[3].ptr, clBytes, cudaMemcpyDeviceToHost, g_stream));
     MMG_CUDA(cudaStreamSynchronize(g_stream));
     return 0;
@@ -318,7 +344,7 @@ extern "C" int mmgen_fill(int n, const int32_t* origins, const float* heightfiel
 {
     if (requireReady()) return 1;
     if (n <= 0) return 0;
-    static Scratch X[4];
+    Scratch* X = g_scratch + 8;
     const size_t clBytes = (size_t)n * 256 * MAX_CAVE_LAYERS * sizeof(CaveLayer);
     Scratch* S = g_scratch;
     if (S[0].ensure((size_t)n * sizeof(int2)) || S[1].ensure((size_t)n * 256 * 4) || S[2].ensure((size_t)n * NUM_BIOMES * 256 * 4) ||
@@ -387,6 +413,8 @@ int mmgen_world_destroy(MmgenWorld* w)
     cudaFree(w->d_list);
     cudaFree(w->d_caves);
     cudaFree(w->d_caveCols);
+    cudaFree(w->d_caveQueue);
+    cudaFree(w->d_caveCount);
     cudaFree(w->d_features);
     cudaFree(w->d_caveFeatures);
     cudaFree(w->d_counts);
@@ -496,13 +524,14 @@ static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
         {
             const int m = (int)list.size();
             if (!w->d_caves) MMG_CUDA(cudaMalloc(&w->d_caves, (size_t)w->n * 256 * MAX_CAVE_LAYERS * sizeof(CaveLayer)));
-            if (!w->d_caveCols) MMG_CUDA(cudaMalloc(&w->d_caveCols, (size_t)w->n * 256 * sizeof(CaveColumn)));
+            if (!w->d_caveCols) MMG_CUDA(cudaMalloc(&w->d_caveCols, (size_t)kCaveBatch * 256 * sizeof(CaveColumn)));
             if (!w->d_list) MMG_CUDA(cudaMalloc(&w->d_list, (size_t)w->n * sizeof(int)));
             MMG_CUDA(cudaMemcpyAsync(w->d_list, list.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, w->stream));
-            MMG_LAUNCH(k_cave_columns, m, 256, kNoiseSmemBytes, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
-                       (const float*)w->d_weights, w->d_caveCols);
-            MMG_LAUNCH(k_caves, m * 256, 128, kNoiseSmemBytes, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
-                       (const float*)w->d_height, (const CaveColumn*)w->d_caveCols, w->d_caves);
+            if (!w->d_caveQueue) MMG_CUDA(cudaMalloc(&w->d_caveQueue, (size_t)kCaveBiomeQueueCap * sizeof(uint2)));
+            if (!w->d_caveCount) MMG_CUDA(cudaMalloc(&w->d_caveCount, sizeof(int)));
+            if (launchCaves(m, (const int*)w->d_list, (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights,
+                            w->d_caveCols, w->d_caves, w->d_caveQueue, w->d_caveCount, w->stream))
+                return 1;
             MMG_CUDA(cudaStreamSynchronize(w->stream));
             for (int i : list) w->stage[i] = 4;
         }

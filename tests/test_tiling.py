@@ -1,0 +1,107 @@
+"""Host-side logic of the multi-GPU path (no GPU): tiling, apron rule, and the cross-rank reductions over
+gloo with world_size 2."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+@pytest.fixture(scope="module")
+def pkg(mm):
+    from mega_minecraft_b200 import sharding, tiling
+    return tiling, sharding
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8])
+@pytest.mark.parametrize("region", [(0, 0, 256, 256), (-5, 20, 10, 8), (-100, -37, 64, 96)])
+@pytest.mark.parametrize("align", [1, 12])
+def test_tiles_partition_the_region(pkg, n, region, align):
+    tiling, _ = pkg
+    if region[2] < 16 and align == 12:
+        pytest.skip("region smaller than the alignment grid")
+    ts = tiling.tiles(*region, n, align=align)
+    assert len(ts) == n
+    cover = np.zeros((region[3], region[2]), np.int32)
+    for (x0, z0, nx, nz) in ts:
+        assert nx > 0 and nz > 0
+        cover[z0 - region[1]:z0 - region[1] + nz, x0 - region[0]:x0 - region[0] + nx] += 1
+    assert (cover == 1).all()                      # every chunk in exactly one tile
+    if align > 1 and n > 1:
+        for (x0, z0, nx, nz) in ts:                # interior cuts sit on the zone grid
+            assert x0 == region[0] or x0 % align == 0
+            assert z0 == region[1] or z0 % align == 0
+
+
+def test_apron_rule(pkg):
+    tiling, _ = pkg
+    # C2: filling chunks [3,9)^2 needs exactly the reference's C2 window [-7,19)^2 (one zone + pad + layer ring)
+    assert tiling.apron_window(3, 3, 6, 6) == (-7, -7, 26, 26)
+    c = tiling.stage_chunk_counts(3, 3, 6, 6)
+    assert c == {"S1": 676, "S2": 576, "S3_zones": 1, "S4": 144, "S5": 144, "S6": 36}
+    # C5 on one GPU
+    c = tiling.stage_chunk_counts(0, 0, 256, 256)
+    assert c["S6"] == 65536 and c["S3_zones"] == 23 * 23 and c["S4"] == 262 * 262 and c["S1"] == 290 * 290
+    # negative coordinates: zones are floor-aligned
+    assert tiling.apron_window(-13, -1, 1, 1) == (-24 - 7, -12 - 7, 24 + 14, 24 + 14)
+
+
+def test_combine_checksums_is_order_sensitive(pkg):
+    _, sharding = pkg
+    a = sharding.combine_checksums([1, 2, 3])
+    assert a != sharding.combine_checksums([3, 2, 1]) and a == sharding.combine_checksums([1, 2, 3])
+    assert sharding.reduce_scalar(3.5) == 3.5 and sharding.gather_u64(2 ** 63 + 5) == [2 ** 63 + 5]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world_size, port, region, out):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import mmgen_loader
+    mmgen_loader.load()
+    from mega_minecraft_b200 import sharding
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    tile = sharding.rank_tile(region, rank, world_size)
+    # stand-in for the per-tile block checksum: a function of the tile's chunk coordinates only
+    xs, zs = np.meshgrid(np.arange(tile[0], tile[0] + tile[2]), np.arange(tile[1], tile[1] + tile[3]))
+    check = int((xs.astype(np.int64) * 73856093 ^ zs.astype(np.int64) * 19349663).sum()) & 0xFFFFFFFFFFFFFFFF | (1 << 63)
+    checks = sharding.gather_u64(check)
+    slowest = sharding.reduce_scalar(10.0 + rank, "max")
+    chunks = sharding.reduce_scalar(tile[2] * tile[3], "sum")
+    if rank == 0:
+        out.put((checks, slowest, chunks))
+    dist.destroy_process_group()
+
+
+def test_two_rank_reductions_over_gloo(pkg):
+    tiling, sharding = pkg
+    region = (-8, 4, 24, 36)
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, region, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    checks, slowest, chunks = q.get()
+    assert slowest == 11.0 and chunks == region[2] * region[3]
+    expect = []
+    for t in tiling.tiles(*region, 2):
+        xs, zs = np.meshgrid(np.arange(t[0], t[0] + t[2]), np.arange(t[1], t[1] + t[3]))
+        expect.append(int((xs.astype(np.int64) * 73856093 ^ zs.astype(np.int64) * 19349663).sum()) & 0xFFFFFFFFFFFFFFFF | (1 << 63))
+    assert checks == expect                                           # 64-bit values survive the gather, in rank order
+    assert sharding.combine_checksums(checks) == sharding.combine_checksums(expect)
