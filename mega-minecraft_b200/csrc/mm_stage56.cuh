@@ -433,9 +433,11 @@ __global__ void __launch_bounds__(kFillSeg, 8) k_fill_features(const int* __rest
             {
                 const CaveFeaturePlacement p = cf[i];
                 const int r = c_caveFeatureReach[p.feature];
-                const int lo = p.y + c_caveFeatureHeightBounds[p.feature][0], hi = p.y + p.layerHeight + c_caveFeatureHeightBounds[p.feature][1];
+                const int* band = c_caveFeatureBand[p.feature];
+                const int lo = max(p.y + c_caveFeatureHeightBounds[p.feature][0], p.y + band[0] + (band[1] ? p.layerHeight : 0));
+                const int hi = min(p.y + p.layerHeight + c_caveFeatureHeightBounds[p.feature][1], p.y + band[2] + (band[3] ? p.layerHeight : 0));
                 const bool none = p.feature == CF_NONE;
-                keep = none || (abs(wx - p.x) <= r && abs(wz - p.z) <= r && lo <= y1 && hi >= y0);
+                keep = none || (abs(wx - p.x) <= r && abs(wz - p.z) <= r && lo <= y1 && hi >= y0 && lo <= hi);
                 k.lo = none ? (short)-32768 : (short)max(lo, -32768); k.hi = none ? (short)32767 : (short)min(hi, 32767);
                 k.idx = (unsigned short)i; k.canReplace = (none || p.canReplaceBlocks) ? 1 : 0;
             }

@@ -157,13 +157,25 @@ __constant__ const int c_caveFeatureHeightBounds[NUM_CAVE_FEATURES][2] = {
 //   MEDIUM_PURPLE_MUSHROOM |fx|+|fz| > 8; PURPLE_MUSHROOM hypot(pos * s) > 35 with s >= 0.5;
 //   CRYSTALs max > 25; PALM |fx|+|fz| > 24; CACTUS max > 5;
 //   GLOWSTONE_CLUSTER |top * s| > 6 with s >= 1; STORMLIGHT spheres dist > radius, radius < 7.5;
-//   CRYSTAL_PILLAR hypot > 7; WARPED_FUNGUS |fx|+|fz| > 6; AMBER_FUNGUS |fx|+|fz| > 4.
+//   CRYSTAL_PILLAR dist > radius = 4 (2 (hr - 0.5)^2 + 0.5) <= 4; WARPED_FUNGUS stem, |fx|+|fz| = 1 lights, cap hypot > 3.7;
+//   AMBER_FUNGUS |fx|+|fz| in {0, 1, 2} (stem and cap ring).
 // NONE terminates a list scan (chunk.cu:1448-1451), so it is never culled.
 constexpr int kReachAll = 1 << 20;
 __constant__ const int c_featureReach[NUM_FEATURES] = {
     kReachAll, 5, 8, 0, 43, 15, 20, 12, 8, 6, 6, 15,
     15, 8, 1, 8, 70, 25, 25, 24, 5};
-__constant__ const int c_caveFeatureReach[NUM_CAVE_FEATURES] = {kReachAll, 0, 0, 0, 6, 7, 7, 7, 6, 4};
+__constant__ const int c_caveFeatureReach[NUM_CAVE_FEATURES] = {kReachAll, 0, 0, 0, 6, 7, 7, 4, 3, 2};
+// Vertical extent of the cave features, from the same rasterisers. The reference tests every cave feature
+// against [y + lo, y + layerHeight + hi] (c_caveFeatureHeightBounds) because some hang from the ceiling;
+// each type only ever fills a band anchored at the floor (y) or at the ceiling (y + layerHeight):
+//   {a, aAtCeiling, b, bAtCeiling}: voxels outside [y + a (+ layerHeight), y + b (+ layerHeight)] are never filled.
+//   test pillars fy in [0, lh]; CAVE_VINE ty in [-height, 0], height = (int)fma(u01, 12, 3) <= 14;
+//   GLOWSTONE_CLUSTER |ty * 1.35 * s| <= 6, s >= 1 => |ty| <= 4; STORMLIGHT spheres |fy| resp. |ty| <= radius < 7.5;
+//   CRYSTAL_PILLAR fy >= -8 and ty <= 8; WARPED_FUNGUS fy in [-2, height + 3], height <= 5;
+//   AMBER_FUNGUS fy in [-2, height + 3], height <= 8.
+// A candidate's y range is the intersection of the reference's bound and this band.
+__constant__ const int c_caveFeatureBand[NUM_CAVE_FEATURES][4] = {
+    {-512, 0, 512, 1}, {0, 0, 0, 1}, {0, 0, 0, 1}, {-14, 1, 0, 1}, {-4, 1, 4, 1}, {-7, 0, 7, 0}, {-7, 1, 7, 1}, {-8, 0, 8, 1}, {-2, 0, 8, 0}, {-2, 0, 11, 0}};
 
 // feature / cave-feature / decorator generators (biomeFuncs.hpp:975-1040, 1081-1178, 1189-1252), flattened:
 // c_*Range[biome] = {first, count} into the generator array.
