@@ -213,20 +213,16 @@ def run_own(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from mega_minecraft_b200 import sharding
+
     def max_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        if world_size > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return sharding.reduce_scalar(x, "max")
 
     def sum_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        if world_size > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return sharding.reduce_scalar(x, "sum")
 
     S = args.world
-    tile = tiling.tiles(0, 0, S, S, world_size, align=args.align)[rank]
+    tile = sharding.rank_tile((0, 0, S, S), rank, world_size, align=args.align)
     gen = mm.ChunkGen(local_rank)
     world = gen.region_world(*tile)
     n_target = tile[2] * tile[3]
@@ -239,6 +235,7 @@ def run_own(args):
     world.sync()
     assert int((world.stages() == 6).sum()) == n_target, "not every target chunk was filled"
     checksum = world.block_checksum()
+    hash_sum = world.chunk_hash_sum()
 
     # ---- device-resident leg
     sampler = ClockSampler(local_rank)
@@ -307,11 +304,7 @@ def run_own(args):
                "hbm_frac": hbm6 / (pk["hbm_gbs"] * world_size), "hbm_peak_src": pk["src"]},
     }
     counts = tiling.stage_chunk_counts(*tile)
-    checks = [None] * world_size
-    if world_size > 1:
-        dist.all_gather_object(checks, checksum)
-    else:
-        checks = [checksum]
+    checks = sharding.gather_u64(checksum)
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
@@ -325,7 +318,7 @@ def run_own(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * max(e2e_wall, e2e_dev) / args.steps, "host_checksum": host_sum},
         "gpu_launches": int(sum_over_ranks(launches)),
-        "roofline": roof, "stages": stages, "clocks": clocks, "block_checksums": [("%016x" % c) for c in checks],
+        "roofline": roof, "stages": stages, "clocks": clocks, "block_checksums": [("%016x" % c) for c in checks], "world_hash": "%016x" % (sum(sharding.gather_u64(hash_sum)) & 0xFFFFFFFFFFFFFFFF),
     }
     if rank == 0 and not args.no_cpu and world_size == 1:
         nthreads = os.cpu_count() or 1

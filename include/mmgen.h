@@ -154,6 +154,9 @@ int mmgen_world_device_ptrs(MmgenWorld* w, void** heightfield, void** biomeWeigh
 /* 64-bit FNV-1a of the block volume of every filled chunk, computed on the device (cheap
  * cross-GPU / cross-run equality check for large worlds) */
 int mmgen_world_block_checksum(MmgenWorld* w, uint64_t* out);
+/* sum (mod 2^64) over the filled chunks of a 64-bit hash of (chunk coordinates, block volume): the same
+ * number however a region is tiled over worlds / GPUs, so tiles can be checked against a single world */
+int mmgen_world_chunk_hash_sum(MmgenWorld* w, uint64_t* out);
 
 #ifdef __cplusplus
 }

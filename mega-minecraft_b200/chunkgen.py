@@ -233,6 +233,11 @@ class World:
         self.gen._check(self.L.mmgen_world_block_checksum(self.h, ctypes.byref(v)))
         return v.value
 
+    def chunk_hash_sum(self):
+        v = ctypes.c_uint64(0)
+        self.gen._check(self.L.mmgen_world_chunk_hash_sum(self.h, ctypes.byref(v)))
+        return v.value
+
     def download_features(self, max_per_chunk=4096):
         F = np.zeros((self.n, max_per_chunk), FeaturePlacement)
         CF = np.zeros((self.n, max_per_chunk), CaveFeaturePlacement)

@@ -40,14 +40,20 @@ __device__ __forceinline__ uint32_t hash_u32(uint32_t a)
 struct Minstd
 {
     uint32_t x;
+    // reduction mod the Mersenne prime 2^31 - 1: v = hi * 2^31 + lo == hi + lo (mod m), one conditional subtract
+    static __device__ __forceinline__ uint32_t mod_m(uint64_t v)
+    {
+        uint32_t r = (uint32_t)(v & 0x7fffffffu) + (uint32_t)(v >> 31);     // v < 2^47: r < 2^31 + 2^16
+        return r >= 2147483647u ? r - 2147483647u : r;
+    }
     __device__ __forceinline__ explicit Minstd(uint32_t seed)
     {
-        x = seed % 2147483647u;
+        x = mod_m(seed);
         if (x == 0) x = 1;
     }
     __device__ __forceinline__ uint32_t next()
     {
-        x = (uint32_t)(((uint64_t)x * 48271u) % 2147483647u);
+        x = mod_m((uint64_t)x * 48271u);
         return x;
     }
     __device__ __forceinline__ float u01() { return (float)(next() - 1u) / 2147483648.0f; }
@@ -168,8 +174,21 @@ __device__ MMG_NOISE_INLINE float simplex2_raw(float vx, float vy)
     float i1x = gt ? 1.0f : 0.0f, i1y = gt ? 0.0f : 1.0f;
     float x1x = (x0x + C0) - i1x, x1y = (x0y + C0) - i1y;
     float x2x = x0x + C2, x2y = x0y + C2;
-    // mod(i, 289) = i - 289*floor(i/289) (true division; exact for these integers)
-    const int jx = (int)(ix - 289.0f * floorf(ix / 289.0f)), jy = (int)(iy - 289.0f * floorf(iy / 289.0f));
+    // mod(i, 289) = i - 289*floor(i/289) with a true fp32 division (GLM mod(vec2, float)). For integers
+    // |i| < 2^22 the rounded quotient cannot reach the next integer (its error is < 2^-11, the distance is
+    // >= 1/289), so floor() of it is the exact integer quotient and the result is i mod 289 in [0, 288]:
+    // computed in integers there (an fp32 division is ~15 instructions), in floats elsewhere.
+    int jx, jy;
+    if (fmaxf(fabsf(ix), fabsf(iy)) < 4194304.0f)
+    {
+        jx = (int)ix % 289; jx += jx < 0 ? 289 : 0;
+        jy = (int)iy % 289; jy += jy < 0 ? 289 : 0;
+    }
+    else
+    {
+        jx = (int)(ix - 289.0f * floorf(ix / 289.0f));
+        jy = (int)(iy - 289.0f * floorf(iy / 289.0f));
+    }
     const int e1x = gt ? 1 : 0, e1y = gt ? 0 : 1;
     const float4 G0 = T->grad2[T->perm[T->perm[jy] + jx]];
     const float4 G1 = T->grad2[T->perm[T->perm[jy + e1y] + jx + e1x]];

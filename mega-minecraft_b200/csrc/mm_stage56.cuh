@@ -305,9 +305,10 @@ __global__ void k_gather_info(const FeaturePlacement* __restrict__ gF, const Cav
 //                    Voxels that need the LUSH_CAVES clay / moss decision are queued instead of decided.
 //   k_fill_lush      decides the queued voxels, one per thread (they are rare and scattered: evaluated in
 //                    place they would occupy 3-4 lanes of a warp for a 27-cell Worley + 9 simplex).
-//   k_fill_features  the placement scan: per column segment, the chunk's lists are reduced to the
-//                    placements whose horizontal reach and y range cover the segment (ordered compaction
-//                    into shared memory), so a voxel tests a few candidates instead of up to 2048 + 4096.
+//   k_fill_features  the placement scan: per column, the chunk's lists are reduced to the placements whose
+//                    horizontal reach and y band cover it (ordered compaction into shared memory) and
+//                    those are rasterised placement by placement; the reference tests up to 2048 + 4096
+//                    placements per voxel.
 // The reference decides terrain and features in one pass per voxel; the feature test only looks at
 // whether the terrain block is AIR, which the lush decision does not change, so the order
 // terrain -> lush -> features gives the same blocks.
@@ -377,20 +378,33 @@ __global__ void __launch_bounds__(128) k_fill_lush(const int2* __restrict__ orig
     }
 }
 
-// a placement that can touch this column segment: inclusive y range, index into the chunk's list
+// a placement that can touch this column segment: inclusive y range (clipped to the segment), index into
+// the chunk's list
 struct Cand { short lo, hi; unsigned short idx, canReplace; };
 
-__global__ void __launch_bounds__(kFillSeg, 8) k_fill_features(const int* __restrict__ fillList, const int2* __restrict__ origins,
+constexpr int kFeatSeg = 256;      // voxels per CTA of k_fill_features: y in [0, 256) and [256, 384)
+constexpr unsigned kNoBest = 0xffffffffu;
+
+// Placement scan of one column segment. Work is distributed by PLACEMENT, not by voxel: after the ordered
+// cull each warp takes candidates round-robin and spreads its lanes over the candidate's y band, so the
+// lanes of a warp rasterise the same feature (no divergence in the type switch, RNG seeds are warp-uniform)
+// instead of one voxel each testing dozens of candidates on a few lanes. The reference's rule "the first
+// placement in list order that contains the voxel wins, surface list before cave list" (chunk.cu:1444-1500)
+// becomes an atomicMin over (list position << 8 | block) per voxel.
+__global__ void __launch_bounds__(kFeatSeg, 4) k_fill_features(const int* __restrict__ fillList, const int2* __restrict__ origins,
                                                                const FeaturePlacement* __restrict__ gF, const CaveFeaturePlacement* __restrict__ gCF,
                                                                const GatherInfo* __restrict__ info, int strideF, int strideCF,
                                                                uint8_t* __restrict__ blocks)
 {
     __shared__ Cand shCandF[kColCapF], shCandC[kColCapC];
-    __shared__ int shWarp[kFillSeg / 32];
-    const int seg = blockIdx.x % 3, col = blockIdx.x / 3;
+    __shared__ int shWarp[kFeatSeg / 32];
+    __shared__ unsigned shBest[kFeatSeg];
+    __shared__ uint8_t shBlk[kFeatSeg];
+    __shared__ int shFirstNone[2], shNeedNoise;
+    const int seg = blockIdx.x & 1, col = blockIdx.x >> 1;
     const int li = col >> 8, idx = col & 255;
     const int chunk = fillList ? fillList[li] : li;
-    const int t = threadIdx.x, y0 = seg * kFillSeg, y1 = y0 + kFillSeg - 1, y = y0 + t;
+    const int t = threadIdx.x, y0 = seg * kFeatSeg, y1 = min(y0 + kFeatSeg, 384) - 1, y = y0 + t;
     const GatherInfo gi = info[li];
     const bool segF = gi.nF > 0 && y0 <= gi.fb1 && y1 >= gi.fb0;
     const bool segC = gi.nCF > 0 && y0 <= gi.cfb1 && y1 >= gi.cfb0;
@@ -399,35 +413,40 @@ __global__ void __launch_bounds__(kFillSeg, 8) k_fill_features(const int* __rest
     const int wx = o.x + (idx & 15), wz = o.y + (idx >> 4);
     const FeaturePlacement* f = gF + (size_t)li * strideF;
     const CaveFeaturePlacement* cf = gCF + (size_t)li * strideCF;
+    if (t < 2) shFirstNone[t] = 0x7fffffff;
+    if (t == 2) shNeedNoise = 0;
+    __syncthreads();
     // candidates of this column segment, in list order. NONE ends a list scan in the reference
-    // (chunk.cu:1448-1451, 1477-1480): it is kept with an unbounded range so that the scan below ends there too.
+    // (chunk.cu:1448-1451, 1477-1480): the candidate list is cut at the first NONE.
     int nColF = 0, nColC = 0;
     if (segF)
-        for (int i0 = 0; i0 < gi.nF; i0 += kFillSeg)
+        for (int i0 = 0; i0 < gi.nF; i0 += kFeatSeg)
         {
             const int i = i0 + t;
-            bool keep = false;
+            bool keep = false, none = false;
             Cand k;
             if (i < gi.nF)
             {
                 const FeaturePlacement p = f[i];
                 const int r = c_featureReach[p.feature];
                 const int lo = p.y + c_featureHeightBounds[p.feature][0], hi = p.y + c_featureHeightBounds[p.feature][1];
-                const bool none = p.feature == F_NONE;
+                none = p.feature == F_NONE;
                 keep = none || (abs(wx - p.x) <= r && abs(wz - p.z) <= r && lo <= y1 && hi >= y0);
-                k.lo = none ? (short)-32768 : (short)max(lo, -32768); k.hi = none ? (short)32767 : (short)min(hi, 32767);
-                k.idx = (unsigned short)i; k.canReplace = (none || p.canReplaceBlocks) ? 1 : 0;
+                k.lo = (short)max(lo, y0); k.hi = (short)min(hi, y1);
+                k.idx = (unsigned short)i; k.canReplace = p.canReplaceBlocks ? 1 : 0;
             }
             int total;
             const int off = block_ordered_offset(keep, shWarp, &total);
             if (keep && nColF + off < kColCapF) shCandF[nColF + off] = k;
+            if (none) atomicMin(&shFirstNone[0], nColF + off);
+            if (keep && !none) shNeedNoise = 1;      // surface rasterisers use simplex / Worley noise
             nColF += total;
         }
     if (segC)
-        for (int i0 = 0; i0 < gi.nCF; i0 += kFillSeg)
+        for (int i0 = 0; i0 < gi.nCF; i0 += kFeatSeg)
         {
             const int i = i0 + t;
-            bool keep = false;
+            bool keep = false, none = false;
             Cand k;
             if (i < gi.nCF)
             {
@@ -436,47 +455,32 @@ __global__ void __launch_bounds__(kFillSeg, 8) k_fill_features(const int* __rest
                 const int* band = c_caveFeatureBand[p.feature];
                 const int lo = max(p.y + c_caveFeatureHeightBounds[p.feature][0], p.y + band[0] + (band[1] ? p.layerHeight : 0));
                 const int hi = min(p.y + p.layerHeight + c_caveFeatureHeightBounds[p.feature][1], p.y + band[2] + (band[3] ? p.layerHeight : 0));
-                const bool none = p.feature == CF_NONE;
+                none = p.feature == CF_NONE;
                 keep = none || (abs(wx - p.x) <= r && abs(wz - p.z) <= r && lo <= y1 && hi >= y0 && lo <= hi);
-                k.lo = none ? (short)-32768 : (short)max(lo, -32768); k.hi = none ? (short)32767 : (short)min(hi, 32767);
-                k.idx = (unsigned short)i; k.canReplace = (none || p.canReplaceBlocks) ? 1 : 0;
+                k.lo = (short)max(lo, y0); k.hi = (short)min(hi, y1);
+                k.idx = (unsigned short)i; k.canReplace = p.canReplaceBlocks ? 1 : 0;
+                if (keep && (p.feature == CF_GLOWSTONE_CLUSTER || p.feature == CF_WARPED_FUNGUS || p.feature == CF_AMBER_FUNGUS)) shNeedNoise = 1;
             }
             int total;
             const int off = block_ordered_offset(keep, shWarp, &total);
             if (keep && nColC + off < kColCapC) shCandC[nColC + off] = k;
+            if (none) atomicMin(&shFirstNone[1], nColC + off);
             nColC += total;
         }
+    __syncthreads();
+    const bool overflowF = nColF > kColCapF, overflowC = nColC > kColCapC;
+    nColF = min(nColF, shFirstNone[0]);
+    nColC = min(nColC, shFirstNone[1]);
     if (nColF == 0 && nColC == 0) return;
-    noise_tab_stage();      // includes the barrier that publishes the candidate lists
+    if (shNeedNoise || overflowF || overflowC) noise_tab_stage();
     uint8_t* out = blocks + (size_t)chunk * 98304 + (size_t)idx * 384 + y;
-    const uint8_t block = *out;
-    uint8_t fblock = 0;
-    bool placed = false, ended = false;      // ended: this voxel's scan met the NONE terminator
-    // The scan is warp-cooperative: 32 candidates at a time are tested against the y range of the warp's
-    // 32 voxels (one candidate per lane), and only the ones that overlap it are then offered, in list
-    // order, to the lanes whose own y lies inside the candidate's range.
-    const int lane = t & 31, yw0 = y - lane, yw1 = yw0 + 31;
-    if (nColF <= kColCapF)
+    if (overflowF || overflowC)
     {
-        for (int c0 = 0; c0 < nColF; c0 += 32)
-        {
-            const int c = c0 + lane;
-            unsigned m = __ballot_sync(0xffffffffu, c < nColF && shCandF[c].lo <= yw1 && shCandF[c].hi >= yw0);
-            while (m)
-            {
-                const Cand k = shCandF[c0 + __ffs(m) - 1];
-                m &= m - 1;
-                if (placed || ended || y < k.lo || y > k.hi || (block != B_AIR && !k.canReplace)) continue;
-                const FeaturePlacement fp = f[k.idx];
-                if (fp.feature == F_NONE) { ended = true; continue; }
-                placed = place_feature(fp, wx, y, wz, &fblock);
-            }
-            if (__all_sync(0xffffffffu, placed || ended)) break;
-        }
-    }
-    else
-    {
-        // more candidates than the shared list holds: the reference's own scan (chunk.cu:1444-1470)
+        // more candidates than the shared lists hold: the reference's own per-voxel scan (chunk.cu:1444-1500)
+        if (y > y1) return;
+        const uint8_t block = *out;
+        uint8_t fblock = 0;
+        bool placed = false;
         for (int i = 0; i < gi.nF; ++i)
         {
             const FeaturePlacement fp = f[i];
@@ -485,38 +489,47 @@ __global__ void __launch_bounds__(kFillSeg, 8) k_fill_features(const int* __rest
             if (y < fp.y + c_featureHeightBounds[fp.feature][0] || y > fp.y + c_featureHeightBounds[fp.feature][1]) continue;
             if (place_feature(fp, wx, y, wz, &fblock)) { placed = true; break; }
         }
-    }
-    ended = false;
-    if (nColC <= kColCapC)
-    {
-        for (int c0 = 0; c0 < nColC; c0 += 32)
-        {
-            const int c = c0 + lane;
-            unsigned m = __ballot_sync(0xffffffffu, c < nColC && shCandC[c].lo <= yw1 && shCandC[c].hi >= yw0);
-            while (m)
-            {
-                const Cand k = shCandC[c0 + __ffs(m) - 1];
-                m &= m - 1;
-                if (placed || ended || y < k.lo || y > k.hi || (block != B_AIR && !k.canReplace)) continue;
-                const CaveFeaturePlacement cp = cf[k.idx];
-                if (cp.feature == CF_NONE) { ended = true; continue; }
-                placed = place_cave_feature(cp, wx, y, wz, &fblock);
-            }
-            if (__all_sync(0xffffffffu, placed || ended)) break;
-        }
-    }
-    else if (!placed)
-    {
-        for (int i = 0; i < gi.nCF; ++i)
+        for (int i = 0; i < gi.nCF && !placed; ++i)
         {
             const CaveFeaturePlacement cp = cf[i];
             if (cp.feature == CF_NONE) break;
             if (block != B_AIR && !cp.canReplaceBlocks) continue;
             if (y < cp.y + c_caveFeatureHeightBounds[cp.feature][0] || y > cp.y + cp.layerHeight + c_caveFeatureHeightBounds[cp.feature][1]) continue;
-            if (place_cave_feature(cp, wx, y, wz, &fblock)) { placed = true; break; }
+            if (place_cave_feature(cp, wx, y, wz, &fblock)) placed = true;
+        }
+        if (placed) *out = fblock;
+        return;
+    }
+    shBlk[t] = y <= y1 ? *out : (uint8_t)B_AIR;
+    shBest[t] = kNoBest;
+    __syncthreads();
+    const int lane = t & 31, warp = t >> 5;
+    for (int c = warp; c < nColF + nColC; c += kFeatSeg / 32)
+    {
+        uint8_t fb = 0;
+        if (c < nColF)
+        {
+            const Cand k = shCandF[c];
+            const FeaturePlacement fp = f[k.idx];
+            for (int yy = k.lo + lane; yy <= k.hi; yy += 32)
+            {
+                if (shBlk[yy - y0] != B_AIR && !k.canReplace) continue;
+                if (place_feature(fp, wx, yy, wz, &fb)) atomicMin(&shBest[yy - y0], ((unsigned)c << 8) | fb);
+            }
+        }
+        else
+        {
+            const Cand k = shCandC[c - nColF];
+            const CaveFeaturePlacement cp = cf[k.idx];
+            for (int yy = k.lo + lane; yy <= k.hi; yy += 32)
+            {
+                if (shBlk[yy - y0] != B_AIR && !k.canReplace) continue;
+                if (place_cave_feature(cp, wx, yy, wz, &fb)) atomicMin(&shBest[yy - y0], ((unsigned)c << 8) | fb);
+            }
         }
     }
-    if (placed) *out = fblock;
+    __syncthreads();
+    if (y <= y1 && shBest[t] != kNoBest) *out = (uint8_t)(shBest[t] & 0xffu);
 }
 
 // tryPlaceSingleDecorator (chunk.cu:1634-1677)

@@ -293,7 +293,7 @@ static int launchFill(int m, const int* d_list, const int2* d_origins, const flo
     MMG_LAUNCH(k_fill_terrain, m * 256 * 3, kFillSeg, kNoiseSmemBytes, stream, d_list, d_origins, d_height, d_weights, d_layers, d_caves, d_blocks,
                d_lushQueue, d_lushCount);
     MMG_LAUNCH(k_fill_lush, kNumSMs * 8, 128, kNoiseSmemBytes, stream, d_origins, (const uint2*)d_lushQueue, (const int*)d_lushCount, d_blocks);
-    MMG_LAUNCH(k_fill_features, m * 256 * 3, kFillSeg, kNoiseSmemBytes, stream, d_list, d_origins, d_gF, d_gCF, d_info, strideF, strideCF, d_blocks);
+    MMG_LAUNCH(k_fill_features, m * 256 * 2, kFeatSeg, kNoiseSmemBytes, stream, d_list, d_origins, d_gF, d_gCF, d_info, strideF, strideCF, d_blocks);
     MMG_LAUNCH(k_decorators, m, 256, 0, stream, d_list, m, d_origins, d_height, d_weights, d_caves, d_blocks);
     return 0;
 }   // chunks gathered + filled per launch group (bounds the gathered-list buffers)
@@ -711,31 +711,60 @@ int mmgen_world_device_ptrs(MmgenWorld* w, void** heightfield, void** biomeWeigh
     return 0;
 }
 
+// per-column FNV hashes of every filled chunk (list order), shared by the two checksums below
+static int worldColumnHashes(MmgenWorld* w, std::vector<int>& list, std::vector<unsigned long long>& hs)
+{
+    list.clear();
+    for (int i = 0; i < w->n; ++i)
+        if (w->stage[i] == 6) list.push_back(i);
+    hs.clear();
+    if (list.empty()) return 0;
+    const int m = (int)list.size();
+    int* d_l = nullptr;
+    unsigned long long* d_h = nullptr;
+    MMG_CUDA(cudaMalloc(&d_l, (size_t)m * sizeof(int)));
+    MMG_CUDA(cudaMalloc(&d_h, (size_t)m * 256 * sizeof(unsigned long long)));
+    MMG_CUDA(cudaMemcpyAsync(d_l, list.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, w->stream));
+    MMG_LAUNCH(k_column_hashes, (m * 256 + 255) / 256, 256, 0, w->stream, (const int*)d_l, m, (const uint8_t*)w->d_blocks, d_h);
+    hs.resize((size_t)m * 256);
+    MMG_CUDA(cudaMemcpyAsync(hs.data(), d_h, hs.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->stream));
+    MMG_CUDA(cudaStreamSynchronize(w->stream));
+    cudaFree(d_l);
+    cudaFree(d_h);
+    return 0;
+}
+
 int mmgen_world_block_checksum(MmgenWorld* w, uint64_t* out)
 {
     if (requireReady()) return 1;
     std::vector<int> list;
-    for (int i = 0; i < w->n; ++i)
-        if (w->stage[i] == 6) list.push_back(i);
+    std::vector<unsigned long long> hs;
+    if (worldColumnHashes(w, list, hs)) return 1;
     uint64_t h = 14695981039346656037ull;
-    if (!list.empty())
-    {
-        const int m = (int)list.size();
-        int* d_l = nullptr;
-        unsigned long long* d_h = nullptr;
-        MMG_CUDA(cudaMalloc(&d_l, (size_t)m * sizeof(int)));
-        MMG_CUDA(cudaMalloc(&d_h, (size_t)m * 256 * sizeof(unsigned long long)));
-        MMG_CUDA(cudaMemcpyAsync(d_l, list.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, w->stream));
-        MMG_LAUNCH(k_column_hashes, (m * 256 + 255) / 256, 256, 0, w->stream, (const int*)d_l, m, (const uint8_t*)w->d_blocks, d_h);
-        std::vector<unsigned long long> hs((size_t)m * 256);
-        MMG_CUDA(cudaMemcpyAsync(hs.data(), d_h, hs.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->stream));
-        MMG_CUDA(cudaStreamSynchronize(w->stream));
-        cudaFree(d_l);
-        cudaFree(d_h);
-        for (unsigned long long v : hs)
-            for (int b = 0; b < 8; ++b) { h ^= (v >> (8 * b)) & 0xff; h *= 1099511628211ull; }
-    }
+    for (unsigned long long v : hs)
+        for (int b = 0; b < 8; ++b) { h ^= (v >> (8 * b)) & 0xff; h *= 1099511628211ull; }
     *out = h;
+    return 0;
+}
+
+int mmgen_world_chunk_hash_sum(MmgenWorld* w, uint64_t* out)
+{
+    if (requireReady()) return 1;
+    std::vector<int> list;
+    std::vector<unsigned long long> hs;
+    if (worldColumnHashes(w, list, hs)) return 1;
+    uint64_t total = 0;
+    for (size_t k = 0; k < list.size(); ++k)
+    {
+        const int cx = w->cx0 + list[k] % w->nx, cz = w->cz0 + list[k] / w->nx;
+        uint64_t h = 14695981039346656037ull;
+        auto mix = [&](unsigned long long v) { for (int b = 0; b < 8; ++b) { h ^= (v >> (8 * b)) & 0xff; h *= 1099511628211ull; } };
+        mix((unsigned long long)(long long)cx);
+        mix((unsigned long long)(long long)cz);
+        for (int c = 0; c < 256; ++c) mix(hs[k * 256 + c]);
+        total += h;      // mod 2^64: independent of the order and of how the world is tiled
+    }
+    *out = total;
     return 0;
 }
 

@@ -100,13 +100,17 @@ def test_tiles_are_bit_identical_to_one_world(gen, mm):
     whole = gen.region_world(*region)
     whole.generate(mm.STAGE_ALL)
     ref = whole.download_region_blocks().reshape(region[3], region[2], 16, 16, 384)
+    ref_sum = whole.chunk_hash_sum()
     whole.close()
+    total = 0
     for t in tiling.tiles(*region, 4):
         w = gen.region_world(*t)
         w.generate(mm.STAGE_ALL)
         b = w.download_region_blocks().reshape(t[3], t[2], 16, 16, 384)
+        total = (total + w.chunk_hash_sum()) & 0xFFFFFFFFFFFFFFFF
         w.close()
         assert np.array_equal(b, ref[t[1] - region[1]:t[1] - region[1] + t[3], t[0] - region[0]:t[0] - region[0] + t[2]])
+    assert total == ref_sum                         # the tiling-invariant world hash bench.py reports
 
 
 # ------------------------------------------------------------------ against the oracle, other windows

@@ -11,7 +11,7 @@ txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
 rows = list(csv.reader(txt.splitlines()))
 cur_file, hdr, lines = None, None, {}
 for r in rows:
-    if len(r) == 2 and r[0] == "File Name":
+    if len(r) == 2 and r[0] in ("File Name", "File Path"):
         cur_file = r[1].split("/")[-1]
         continue
     if len(r) > 8 and r[0] == "Line No":
