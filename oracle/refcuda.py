@@ -9,6 +9,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(_HERE, "_ref", "libmmref_cuda.so")
+# the same driver and reference state machine, but with integration/chunk_adapter.cpp linked over the
+# reference's five generation entry points, i.e. the reference application running on libmmgen.so
+ADAPTER_LIB = os.path.join(_HERE, "_ref", "libmmref_adapter.so")
 
 CaveLayer = np.dtype([("start", "<i4"), ("end", "<i4"), ("bottomBiome", "u1"), ("topBiome", "u1"), ("pad", "u1", (2,))])
 FeaturePlacement = np.dtype([("feature", "u1"), ("pad0", "u1", (3,)), ("x", "<i4"), ("y", "<i4"), ("z", "<i4"),
@@ -22,13 +25,17 @@ def available():
     return os.path.exists(LIB)
 
 
+def adapter_available():
+    return os.path.exists(ADAPTER_LIB)
+
+
 def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
 class RefCuda:
-    def __init__(self, device=0):
-        self.L = ctypes.CDLL(LIB)
+    def __init__(self, device=0, adapter=False):
+        self.L = ctypes.CDLL(ADAPTER_LIB if adapter else LIB)
         self.L.mmref_stage_ms.restype = ctypes.c_double
         rc = self.L.mmref_init(device)
         if rc != 0:

@@ -113,6 +113,26 @@ def test_tiles_are_bit_identical_to_one_world(gen, mm):
     assert total == ref_sum                         # the tiling-invariant world hash bench.py reports
 
 
+def test_adapter_runs_reference_state_machine_on_new_kernels(gen, golden):
+    """Drop-in proof: the reference's own Chunk/Zone state machine, CPU feature placement and gather
+    (unmodified objects from oracle/_ref) with integration/chunk_adapter.cpp linked over its five generation
+    entry points reproduces the reference's blocks bit for bit."""
+    from oracle import refcuda
+    if not refcuda.adapter_available():
+        pytest.skip("oracle/_ref/libmmref_adapter.so not built (needs /root/reference at build time)")
+    g = golden["g"]
+    r = refcuda.RefCuda(0, adapter=True).generate(golden["x0"], golden["z0"], golden["nx"], golden["nz"], 6)
+    assert np.array_equal(r["stage"], g["stage"])
+    assert np.array_equal(r["heightfield"].view(np.uint32), g["heightfield"].view(np.uint32))
+    assert np.array_equal(r["layers"][g["zone_idx"]][:, 10:].view(np.uint32), g["zone_layers"][:, 10:].view(np.uint32))
+    for f in ("start", "end", "bottomBiome", "topBiome"):
+        assert np.array_equal(r["cave_layers"][f], g["cave_layers"][f]), f
+    rF = split_lists(g["features"], g["features_off"])
+    assert all(same_placements(a, b) for a, b in zip(r["features"], rF))
+    assert np.array_equal(r["block_idx"], g["block_idx"])
+    assert np.array_equal(r["blocks"], g["blocks"])
+
+
 # ------------------------------------------------------------------ against the oracle, other windows
 @pytest.mark.parametrize("biome", [1, 8, 9, 13, 16, 19, 23])
 def test_stage1_all_biomes_vs_oracle(gen, oracle, biome):
