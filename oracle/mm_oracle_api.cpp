@@ -188,4 +188,34 @@ float mmo_rng3_u01(int x, int y, int z, int ndraw)
     return v;
 }
 
+
+// Observed extent of placed features, by brute force over a box of voxels around each placement (tests of the
+// product's culling tables): placements[n] = {feature, x, y, z, layerHeight}; for placement i every voxel with
+// |dx|,|dz| <= radius and y in [ylo[i], yhi[i]] is tested; out[i] = {hits, max|dx|, max|dz|, min(y - py), max(y - py),
+// min(y - py - lh), max(y - py - lh)} over the voxels the rasteriser fills (y extents are INT_MAX/INT_MIN without hits).
+void mmo_feature_extent(int cave, int n, const int32_t* placements, int radius, const int32_t* ylo, const int32_t* yhi, int32_t* out, int nthreads)
+{
+    parallel_for(n, nthreads, [&](int i) {
+        const int32_t* p = placements + 5 * i;
+        int32_t* o = out + 7 * i;
+        o[0] = o[1] = o[2] = 0; o[3] = o[5] = 2147483647; o[4] = o[6] = -2147483647 - 1;
+        mmo::FeaturePlacement fp; mmo::CaveFeaturePlacement cp;
+        std::memset(&fp, 0, sizeof(fp)); std::memset(&cp, 0, sizeof(cp));
+        fp.feature = (uint8_t)p[0]; fp.x = p[1]; fp.y = p[2]; fp.z = p[3]; fp.canReplaceBlocks = 1;
+        cp.feature = (uint8_t)p[0]; cp.x = p[1]; cp.y = p[2]; cp.z = p[3]; cp.layerHeight = p[4]; cp.canReplaceBlocks = 1;
+        for (int dz = -radius; dz <= radius; ++dz)
+            for (int dx = -radius; dx <= radius; ++dx)
+                for (int y = ylo[i]; y <= yhi[i]; ++y)
+                {
+                    uint8_t b = 0;
+                    const bool hit = cave ? mmo::place_cave_feature(cp, p[1] + dx, y, p[3] + dz, &b) : mmo::place_feature(fp, p[1] + dx, y, p[3] + dz, &b);
+                    if (!hit) continue;
+                    ++o[0];
+                    o[1] = std::max(o[1], std::abs(dx)); o[2] = std::max(o[2], std::abs(dz));
+                    o[3] = std::min(o[3], y - p[2]); o[4] = std::max(o[4], y - p[2]);
+                    o[5] = std::min(o[5], y - p[2] - p[4]); o[6] = std::max(o[6], y - p[2] - p[4]);
+                }
+    });
+}
+
 }  // extern "C"
