@@ -222,9 +222,25 @@ def run_own(args):
         return sharding.reduce_scalar(x, "sum")
 
     S = args.world
-    tile = sharding.rank_tile((0, 0, S, S), rank, world_size, align=args.align)
     gen = mm.ChunkGen(local_rank)
-    world = gen.region_world(*tile)
+    # tiling: equal tiles, then (N > 1) the cuts are moved by feedback from the measured per-rank device time of
+    # untimed balancing passes (sharding.Balancer); the timed steps run on the final, fixed tiling
+    bal = sharding.Balancer((0, 0, S, S), world_size)
+    balance_log = []
+    rounds = args.balance_rounds if world_size > 1 else 0
+    world = None
+    for it in range(rounds + 1):
+        tile = bal.tiles()[rank]
+        world = gen.region_world(*tile)
+        if it == rounds:
+            break
+        world.generate(mm.STAGE_ALL)            # allocations
+        world.reset()
+        world.generate(mm.STAGE_ALL)
+        times = sharding.gather_floats(world.total_ms())
+        balance_log.append({"tiles": [list(t) for t in bal.tiles()], "rank_ms": [round(t, 2) for t in times]})
+        bal.update(times)
+        world.close()
     n_target = tile[2] * tile[3]
     host = torch.empty(n_target * 98304, dtype=torch.uint8, pin_memory=True)
     launches0 = gen.launch_count()
@@ -250,6 +266,7 @@ def run_own(args):
         world.generate(mm.STAGE_ALL)
         dev_ms += world.total_ms()          # CUDA events on the world's stream around the whole generate
         stage_ms += world.stage_ms()
+    rank_ms = [t / args.steps for t in sharding.gather_floats(dev_ms)]
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -312,12 +329,13 @@ def run_own(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic (the world is a pure function of chunk coordinates; no dataset exists)",
         "config": {"workload": "%dx%d-chunk world [0,%d)^2, full 6-stage generation (S1 heightfield/biomes, S2 layers, S3 erosion, S4 caves, "
                                "S5 feature placement+gather, S6 fill+decorators)" % (S, S, S),
-                   "tiling": "%d chunk-coordinate tiles, apron recomputed per tile, no data-path collective" % world_size,
-                   "tile_rank0": list(tile), "chunks_touched_rank0": counts,
+                   "tiling": "%d chunk-coordinate tiles, apron recomputed per tile, no data-path collective%s" % (
+                       world_size, "; cuts balanced by feedback from %d untimed passes (per-rank device time)" % rounds if rounds else ""),
+                   "tiles": [list(t) for t in bal.tiles()], "chunks_touched_rank0": counts,
                    "l2": "working set per step (>= %.1f GB written) far exceeds the 126 MB L2; no flush needed" % (n_target * 98304 / 1e9)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * max(e2e_wall, e2e_dev) / args.steps, "host_checksum": host_sum},
-        "gpu_launches": int(sum_over_ranks(launches)),
+        "gpu_launches": int(sum_over_ranks(launches)), "rank_ms": [round(t, 2) for t in rank_ms], "balance_passes": balance_log,
         "roofline": roof, "stages": stages, "clocks": clocks, "block_checksums": [("%016x" % c) for c in checks], "world_hash": "%016x" % (sum(sharding.gather_u64(hash_sum)) & 0xFFFFFFFFFFFFFFFF),
     }
     if rank == 0 and not args.no_cpu and world_size == 1:
@@ -344,7 +362,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cpu"])
     ap.add_argument("--world", type=int, default=256, help="side of the target region in chunks")
-    ap.add_argument("--align", type=int, default=1, help="round tile cuts to multiples of this many chunks")
+    ap.add_argument("--balance-rounds", type=int, default=2, help="feedback passes that move the tile cuts before the timed steps (N > 1)")
     ap.add_argument("--ref-zones", type=int, default=3, help="the reference CUDA arm generates ZxZ erosion zones (+ apron) per step")
     ap.add_argument("--cpu-cave-chunks", type=int, default=0, help="bound the CPU baseline's S4 sample (0 = the whole zone)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

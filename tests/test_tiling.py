@@ -105,3 +105,30 @@ def test_two_rank_reductions_over_gloo(pkg):
         expect.append(int((xs.astype(np.int64) * 73856093 ^ zs.astype(np.int64) * 19349663).sum()) & 0xFFFFFFFFFFFFFFFF | (1 << 63))
     assert checks == expect                                           # 64-bit values survive the gather, in rank order
     assert sharding.combine_checksums(checks) == sharding.combine_checksums(expect)
+
+
+def test_feedback_balancer_converges_and_partitions(pkg):
+    """Synthetic cost density with a strong gradient: a few feedback rounds bring the tiles to equal cost, and the
+    tiles always partition the region."""
+    _, sharding = pkg
+    region = (0, 0, 256, 256)
+    zz, xx = np.meshgrid(np.arange(256), np.arange(256), indexing="ij")
+    density = 1.0 + 0.5 * (zz < 128) + 0.3 * np.sin(xx / 40.0) + 0.2 * (xx > 200)      # cost per chunk
+
+    def cost(t):
+        return float(density[t[1]:t[1] + t[3], t[0]:t[0] + t[2]].sum())
+
+    for n in (2, 4, 8):
+        b = sharding.Balancer(region, n)
+        first = None
+        for _ in range(4):
+            ts = b.tiles()
+            cover = np.zeros((256, 256), np.int32)
+            for (x0, z0, nx, nz) in ts:
+                assert nx > 0 and nz > 0
+                cover[z0:z0 + nz, x0:x0 + nx] += 1
+            assert (cover == 1).all()
+            imb = b.update([cost(t) for t in ts])
+            first = imb if first is None else first
+        final = [cost(t) for t in b.tiles()]
+        assert max(final) / (sum(final) / len(final)) < 1.03 <= first
