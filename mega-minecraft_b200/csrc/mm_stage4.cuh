@@ -233,12 +233,12 @@ __global__ void __launch_bounds__(128, 8) k_caves(const int* __restrict__ chunkL
         const int y = tid + 128 * k;
         float thr = 0.f, px = 0.f, py = 0.f, pz = 0.f;
         const int st = cave_threshold(wx, y, wz, maxHeight, cc.obw, &thr, &px, &py, &pz);
-        // cells [box, box + kCaveBox)^3 cover the 3x3x3 neighbourhoods of (nearly) all undecided voxels. The table
-        // costs 3 * 216 hashes: with fewer than 8 undecided voxels (e.g. the single voxel y = 128 of the second
-        // slab over low terrain) the 81 hashes per voxel are cheaper computed in place.
+        // cells [box, box + kCaveBox)^3 cover the 3x3x3 neighbourhoods of (nearly) all undecided voxels. (Filling
+        // the table costs 5 hashes per thread; even for a single undecided voxel that is fewer warp instructions
+        // than its 81 hashes computed in place on one lane - measured.)
         if (tid < 3) shBox[tid] = INT_MAX;
-        const bool useTable = __syncthreads_count(st == 2) >= 8;
-        if (st == 2 && useTable)
+        __syncthreads();
+        if (st == 2)
         {
             atomicMin(&shBox[0], (int)floorf(px) - 1);
             atomicMin(&shBox[1], (int)floorf(py) - 1);
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(128, 8) k_caves(const int* __restrict__ chunkL
         }
         __syncthreads();
         bool air = st == 1;
-        if (st == 2) air = (useTable ? special_cave_noise_cached(px, py, pz, bx, by, bz, shJit) : special_cave_noise(px, py, pz)) < thr;
+        if (st == 2) air = special_cave_noise_cached(px, py, pz, bx, by, bz, shJit) < thr;
         if (st != 1 && !air) air = rav.active && (rav.top - rav.depth) < (float)y && y != 0;   // chunk.cu:785-808
         const unsigned int bits = __ballot_sync(0xffffffffu, !air);
         if (lane == 0) shFilled[4 * k + warp] = bits;

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) k_feature_placements(const int* __restric
     }
 }
 
-struct GatherInfo { int nF, nCF; int fb0, fb1, cfb0, cfb1; };
+struct GatherInfo { int nF, nCF; int fb0, fb1, cfb0, cfb1; int needNoise, pad; };
 
 // Position of this thread's kept entry among the kept entries of the whole CTA, in thread order
 // (= list order: the first feature in list order that contains a voxel wins, chunk.cu:1444-1500).
@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(256) k_gather_features(const int* __restrict__
         GatherInfo gi;
         gi.nF = outF; gi.nCF = outC;
         gi.fb0 = shMin[0]; gi.fb1 = shMax[0]; gi.cfb0 = shMin[1]; gi.cfb1 = shMax[1];
+        gi.needNoise = 1; gi.pad = 0;
         info[li] = gi;
     }
 }
@@ -293,6 +294,7 @@ __global__ void k_gather_info(const FeaturePlacement* __restrict__ gF, const Cav
         GatherInfo gi;
         gi.nF = nf; gi.nCF = nc;
         gi.fb0 = shMin[0]; gi.fb1 = shMax[0]; gi.cfb0 = shMin[1]; gi.cfb1 = shMax[1];
+        gi.needNoise = 1; gi.pad = 0;
         info[li] = gi;
     }
 }
@@ -378,158 +380,205 @@ __global__ void __launch_bounds__(128) k_fill_lush(const int2* __restrict__ orig
     }
 }
 
-// a placement that can touch this column segment: inclusive y range (clipped to the segment), index into
-// the chunk's list
-struct Cand { short lo, hi; unsigned short idx, canReplace; };
+// What k_fill_features needs to know about a placement before it touches the rasteriser: the y band it can
+// fill (reference bound intersected with the type's own band, clipped to the world), the columns of THIS
+// chunk its horizontal reach covers, and whether it may overwrite terrain. lo > hi: cannot touch the chunk.
+struct Prep { short lo, hi; unsigned char xr, zr, canReplace, feature; };      // xr = x0 | x1 << 4 (local 0..15), zr likewise
 
-constexpr int kFeatSeg = 256;      // voxels per CTA of k_fill_features: y in [0, 256) and [256, 384)
-constexpr unsigned kNoBest = 0xffffffffu;
-
-// Placement scan of one column segment. Work is distributed by PLACEMENT, not by voxel: after the ordered
-// cull each warp takes candidates round-robin and spreads its lanes over the candidate's y band, so the
-// lanes of a warp rasterise the same feature (no divergence in the type switch, RNG seeds are warp-uniform)
-// instead of one voxel each testing dozens of candidates on a few lanes. The reference's rule "the first
-// placement in list order that contains the voxel wins, surface list before cave list" (chunk.cu:1444-1500)
-// becomes an atomicMin over (list position << 8 | block) per voxel.
-__global__ void __launch_bounds__(kFeatSeg, 4) k_fill_features(const int* __restrict__ fillList, const int2* __restrict__ origins,
-                                                               const FeaturePlacement* __restrict__ gF, const CaveFeaturePlacement* __restrict__ gCF,
-                                                               const GatherInfo* __restrict__ info, int strideF, int strideCF,
-                                                               uint8_t* __restrict__ blocks)
+// One CTA per chunk of the batch: Prep records of the chunk's (already reach-culled, ordered) lists. NONE ends
+// a list scan in the reference (chunk.cu:1448-1451, 1477-1480): the list lengths are cut at the first NONE.
+__global__ void __launch_bounds__(256) k_prepare_placements(const int* __restrict__ fillList, const int2* __restrict__ origins,
+                                                            const FeaturePlacement* __restrict__ gF, const CaveFeaturePlacement* __restrict__ gCF,
+                                                            GatherInfo* __restrict__ info, int strideF, int strideCF,
+                                                            Prep* __restrict__ prepF, Prep* __restrict__ prepC)
 {
-    __shared__ Cand shCandF[kColCapF], shCandC[kColCapC];
-    __shared__ int shWarp[kFeatSeg / 32];
-    __shared__ unsigned shBest[kFeatSeg];
-    __shared__ uint8_t shBlk[kFeatSeg];
-    __shared__ int shFirstNone[2], shNeedNoise;
-    const int seg = blockIdx.x & 1, col = blockIdx.x >> 1;
-    const int li = col >> 8, idx = col & 255;
+    __shared__ int shFirstNone[2], shNoise;
+    const int li = blockIdx.x, chunk = fillList ? fillList[li] : li, tid = threadIdx.x;
+    if (tid < 2) shFirstNone[tid] = 0x7fffffff;
+    if (tid == 2) shNoise = 0;
+    __syncthreads();
+    const int2 o = origins[chunk];
+    const GatherInfo gi = info[li];
+    auto columns = [&](int px, int pz, int r, Prep* k) -> bool {
+        const int x0 = max(px - r, o.x) - o.x, x1 = min(px + r, o.x + 15) - o.x;
+        const int z0 = max(pz - r, o.y) - o.y, z1 = min(pz + r, o.y + 15) - o.y;
+        if (x0 > x1 || z0 > z1) return false;
+        k->xr = (unsigned char)(x0 | x1 << 4); k->zr = (unsigned char)(z0 | z1 << 4);
+        return true;
+    };
+    for (int i = tid; i < gi.nF; i += 256)
+    {
+        const FeaturePlacement p = gF[(size_t)li * strideF + i];
+        Prep k;
+        k.lo = 1; k.hi = 0; k.xr = k.zr = 0; k.canReplace = p.canReplaceBlocks ? 1 : 0; k.feature = p.feature;
+        if (p.feature == F_NONE) atomicMin(&shFirstNone[0], i);
+        else if (columns(p.x, p.z, min(c_featureReach[p.feature], 1 << 16), &k))
+        {
+            k.lo = (short)max(p.y + c_featureHeightBounds[p.feature][0], 0);
+            k.hi = (short)min(p.y + c_featureHeightBounds[p.feature][1], 383);
+            shNoise = 1;      // surface rasterisers use simplex / Worley noise
+        }
+        prepF[(size_t)li * strideF + i] = k;
+    }
+    for (int i = tid; i < gi.nCF; i += 256)
+    {
+        const CaveFeaturePlacement p = gCF[(size_t)li * strideCF + i];
+        Prep k;
+        k.lo = 1; k.hi = 0; k.xr = k.zr = 0; k.canReplace = p.canReplaceBlocks ? 1 : 0; k.feature = p.feature;
+        if (p.feature == CF_NONE) atomicMin(&shFirstNone[1], i);
+        else if (columns(p.x, p.z, min(c_caveFeatureReach[p.feature], 1 << 16), &k))
+        {
+            const int* band = c_caveFeatureBand[p.feature];
+            k.lo = (short)max(max(p.y + c_caveFeatureHeightBounds[p.feature][0], p.y + band[0] + (band[1] ? p.layerHeight : 0)), 0);
+            k.hi = (short)min(min(p.y + p.layerHeight + c_caveFeatureHeightBounds[p.feature][1], p.y + band[2] + (band[3] ? p.layerHeight : 0)), 383);
+            if (p.feature == CF_GLOWSTONE_CLUSTER || p.feature == CF_WARPED_FUNGUS || p.feature == CF_AMBER_FUNGUS) shNoise = 1;
+        }
+        prepC[(size_t)li * strideCF + i] = k;
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+        GatherInfo g2 = gi;
+        g2.nF = min(gi.nF, shFirstNone[0]);
+        g2.nCF = min(gi.nCF, shFirstNone[1]);
+        g2.needNoise = shNoise;
+        info[li] = g2;
+    }
+}
+
+constexpr int kSlab = 32;                  // voxels of a column per CTA of k_fill_features
+constexpr int kSlabPitch = 257;            // shBest[yy][col], padded: lanes that differ in yy hit different banks
+constexpr unsigned kNoBest = 0xffffffffu;
+constexpr int kBigBox = 2048, kMaxBig = 96;   // (column, y) pairs above which a placement is rasterised by the whole CTA
+__constant__ const unsigned c_recip16[17] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096};
+
+// Placement scan of one 32-voxel slab of a chunk (12 slabs per chunk). Work is distributed by PLACEMENT, not
+// by voxel: the warps of the CTA take the chunk's placements round-robin, and a warp spreads its lanes over
+// the (column, y) pairs of the placement's box clipped to this chunk and slab - so the lanes of a warp
+// rasterise the same feature on different voxels instead of one voxel testing hundreds of candidates (a
+// column of a crystal-cave chunk is within reach of ~400 stormlight spheres). The reference's rule "the first
+// placement in list order that contains the voxel wins, surface list before cave list" (chunk.cu:1444-1500)
+// becomes an atomicMin over (list position << 8 | block) per voxel; a voxel already claimed by an earlier
+// placement is not tested again.
+__global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict__ fillList, const int2* __restrict__ origins,
+                                                          const FeaturePlacement* __restrict__ gF, const CaveFeaturePlacement* __restrict__ gCF,
+                                                          const Prep* __restrict__ prepF, const Prep* __restrict__ prepC,
+                                                          const GatherInfo* __restrict__ info, int strideF, int strideCF,
+                                                          uint8_t* __restrict__ blocks)
+{
+    __shared__ unsigned shBest[kSlab * kSlabPitch];
+    __shared__ __align__(16) uint8_t shBlk[256 * kSlab];     // [col][yy]
+    __shared__ int shNext, shNumBig;
+    __shared__ unsigned short shBig[kMaxBig];
+    const int slab = blockIdx.x % 12, li = blockIdx.x / 12;
     const int chunk = fillList ? fillList[li] : li;
-    const int t = threadIdx.x, y0 = seg * kFeatSeg, y1 = min(y0 + kFeatSeg, 384) - 1, y = y0 + t;
+    const int t = threadIdx.x, y0 = slab * kSlab, y1 = y0 + kSlab - 1;
     const GatherInfo gi = info[li];
     const bool segF = gi.nF > 0 && y0 <= gi.fb1 && y1 >= gi.fb0;
     const bool segC = gi.nCF > 0 && y0 <= gi.cfb1 && y1 >= gi.cfb0;
     if (!segF && !segC) return;
     const int2 o = origins[chunk];
-    const int wx = o.x + (idx & 15), wz = o.y + (idx >> 4);
+    // thread t stages column t of the slab (32 consecutive block IDs, 16-byte aligned)
+    uint8_t* colPtr = blocks + (size_t)chunk * 98304 + (size_t)t * 384 + y0;
+    {
+        const uint4 a = reinterpret_cast<const uint4*>(colPtr)[0], b = reinterpret_cast<const uint4*>(colPtr)[1];
+        reinterpret_cast<uint4*>(shBlk + t * kSlab)[0] = a;
+        reinterpret_cast<uint4*>(shBlk + t * kSlab)[1] = b;
+    }
+    for (int i = t; i < kSlab * kSlabPitch; i += 256) shBest[i] = kNoBest;
+    if (t == 0) { shNext = 0; shNumBig = 0; }
+    if (gi.needNoise) noise_tab_stage();
+    __syncthreads();
+    const int lane = t & 31;
+    const int nF = segF ? gi.nF : 0, nC = segC ? gi.nCF : 0;
     const FeaturePlacement* f = gF + (size_t)li * strideF;
     const CaveFeaturePlacement* cf = gCF + (size_t)li * strideCF;
-    if (t < 2) shFirstNone[t] = 0x7fffffff;
-    if (t == 2) shNeedNoise = 0;
-    __syncthreads();
-    // candidates of this column segment, in list order. NONE ends a list scan in the reference
-    // (chunk.cu:1448-1451, 1477-1480): the candidate list is cut at the first NONE.
-    int nColF = 0, nColC = 0;
-    if (segF)
-        for (int i0 = 0; i0 < gi.nF; i0 += kFeatSeg)
+    const Prep* pf = prepF + (size_t)li * strideF;
+    const Prep* pc = prepC + (size_t)li * strideCF;
+    // rasterises (column, y) pairs first, first + step, ... of placement e; returns false if e cannot touch the slab
+    auto raster = [&](int e, int first, int step, bool countOnly, int* totalOut) -> bool {
+        const bool cave = e >= nF;
+        const Prep k = cave ? pc[e - nF] : pf[e];
+        const int lo = max((int)k.lo, y0), hi = min((int)k.hi, y1);
+        if (lo > hi) return false;
+        const int x0 = k.xr & 15, nxc = (k.xr >> 4) - x0 + 1, z0 = k.zr & 15, nzc = (k.zr >> 4) - z0 + 1;
+        const int ny = hi - lo + 1;
+        const int sh = 32 - __clz(ny - 1);                    // ny padded to a power of two: y fastest, no division by ny
+        const int total = (nxc * nzc) << sh;
+        *totalOut = total;
+        if (countOnly) return true;
+        const unsigned key = (unsigned)e << 8;
+        FeaturePlacement fp;
+        CaveFeaturePlacement cp;
+        if (cave) cp = cf[e - nF];
+        else fp = f[e];
+        for (int p = first; p < total; p += step)
         {
-            const int i = i0 + t;
-            bool keep = false, none = false;
-            Cand k;
-            if (i < gi.nF)
-            {
-                const FeaturePlacement p = f[i];
-                const int r = c_featureReach[p.feature];
-                const int lo = p.y + c_featureHeightBounds[p.feature][0], hi = p.y + c_featureHeightBounds[p.feature][1];
-                none = p.feature == F_NONE;
-                keep = none || (abs(wx - p.x) <= r && abs(wz - p.z) <= r && lo <= y1 && hi >= y0);
-                k.lo = (short)max(lo, y0); k.hi = (short)min(hi, y1);
-                k.idx = (unsigned short)i; k.canReplace = p.canReplaceBlocks ? 1 : 0;
-            }
-            int total;
-            const int off = block_ordered_offset(keep, shWarp, &total);
-            if (keep && nColF + off < kColCapF) shCandF[nColF + off] = k;
-            if (none) atomicMin(&shFirstNone[0], nColF + off);
-            if (keep && !none) shNeedNoise = 1;      // surface rasterisers use simplex / Worley noise
-            nColF += total;
+            const int dy = p & ((1 << sh) - 1);
+            if (dy >= ny) continue;
+            const int q = p >> sh;
+            const int dz = (int)((q * c_recip16[nxc]) >> 16), dx = q - dz * nxc;
+            const int x = x0 + dx, z = z0 + dz, y = lo + dy;
+            const int col = x + 16 * z, yy = y - y0;
+            if (shBest[yy * kSlabPitch + col] <= (key | 0xffu)) continue;      // claimed by an earlier placement
+            if (shBlk[col * kSlab + yy] != B_AIR && !k.canReplace) continue;
+            uint8_t fb = 0;
+            const bool hit = cave ? place_cave_feature(cp, o.x + x, y, o.y + z, &fb) : place_feature(fp, o.x + x, y, o.y + z, &fb);
+            if (hit) atomicMin(&shBest[yy * kSlabPitch + col], key | fb);
         }
-    if (segC)
-        for (int i0 = 0; i0 < gi.nCF; i0 += kFeatSeg)
-        {
-            const int i = i0 + t;
-            bool keep = false, none = false;
-            Cand k;
-            if (i < gi.nCF)
-            {
-                const CaveFeaturePlacement p = cf[i];
-                const int r = c_caveFeatureReach[p.feature];
-                const int* band = c_caveFeatureBand[p.feature];
-                const int lo = max(p.y + c_caveFeatureHeightBounds[p.feature][0], p.y + band[0] + (band[1] ? p.layerHeight : 0));
-                const int hi = min(p.y + p.layerHeight + c_caveFeatureHeightBounds[p.feature][1], p.y + band[2] + (band[3] ? p.layerHeight : 0));
-                none = p.feature == CF_NONE;
-                keep = none || (abs(wx - p.x) <= r && abs(wz - p.z) <= r && lo <= y1 && hi >= y0 && lo <= hi);
-                k.lo = (short)max(lo, y0); k.hi = (short)min(hi, y1);
-                k.idx = (unsigned short)i; k.canReplace = p.canReplaceBlocks ? 1 : 0;
-                if (keep && (p.feature == CF_GLOWSTONE_CLUSTER || p.feature == CF_WARPED_FUNGUS || p.feature == CF_AMBER_FUNGUS)) shNeedNoise = 1;
-            }
-            int total;
-            const int off = block_ordered_offset(keep, shWarp, &total);
-            if (keep && nColC + off < kColCapC) shCandC[nColC + off] = k;
-            if (none) atomicMin(&shFirstNone[1], nColC + off);
-            nColC += total;
-        }
-    __syncthreads();
-    const bool overflowF = nColF > kColCapF, overflowC = nColC > kColCapC;
-    nColF = min(nColF, shFirstNone[0]);
-    nColC = min(nColC, shFirstNone[1]);
-    if (nColF == 0 && nColC == 0) return;
-    if (shNeedNoise || overflowF || overflowC) noise_tab_stage();
-    uint8_t* out = blocks + (size_t)chunk * 98304 + (size_t)idx * 384 + y;
-    if (overflowF || overflowC)
+        return true;
+    };
+    // phase 1: warps pull placements from a shared counter (in list order, so that earlier placements tend to
+    // claim their voxels first); placements with a large box (trees, icebergs) are set aside for phase 2
+    for (;;)
     {
-        // more candidates than the shared lists hold: the reference's own per-voxel scan (chunk.cu:1444-1500)
-        if (y > y1) return;
-        const uint8_t block = *out;
-        uint8_t fblock = 0;
-        bool placed = false;
-        for (int i = 0; i < gi.nF; ++i)
+        int e = 0;
+        if (lane == 0) e = atomicAdd(&shNext, 1);
+        e = __shfl_sync(0xffffffffu, e, 0);
+        if (e >= nF + nC) break;
+        int total = 0;
+        if (!raster(e, 0, 0, true, &total)) continue;
+        if (total > kBigBox)
         {
-            const FeaturePlacement fp = f[i];
-            if (fp.feature == F_NONE) break;
-            if (block != B_AIR && !fp.canReplaceBlocks) continue;
-            if (y < fp.y + c_featureHeightBounds[fp.feature][0] || y > fp.y + c_featureHeightBounds[fp.feature][1]) continue;
-            if (place_feature(fp, wx, y, wz, &fblock)) { placed = true; break; }
+            int slot = kMaxBig;
+            if (lane == 0) slot = atomicAdd(&shNumBig, 1);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (slot < kMaxBig)
+            {
+                if (lane == 0) shBig[slot] = (unsigned short)e;
+                continue;
+            }
         }
-        for (int i = 0; i < gi.nCF && !placed; ++i)
-        {
-            const CaveFeaturePlacement cp = cf[i];
-            if (cp.feature == CF_NONE) break;
-            if (block != B_AIR && !cp.canReplaceBlocks) continue;
-            if (y < cp.y + c_caveFeatureHeightBounds[cp.feature][0] || y > cp.y + cp.layerHeight + c_caveFeatureHeightBounds[cp.feature][1]) continue;
-            if (place_cave_feature(cp, wx, y, wz, &fblock)) placed = true;
-        }
-        if (placed) *out = fblock;
-        return;
+        raster(e, lane, 32, false, &total);
     }
-    shBlk[t] = y <= y1 ? *out : (uint8_t)B_AIR;
-    shBest[t] = kNoBest;
     __syncthreads();
-    const int lane = t & 31, warp = t >> 5;
-    for (int c = warp; c < nColF + nColC; c += kFeatSeg / 32)
+    // phase 2: the whole CTA rasterises each large placement together
     {
-        uint8_t fb = 0;
-        if (c < nColF)
+        const int nBig = min(shNumBig, kMaxBig);
+        for (int b = 0; b < nBig; ++b)
         {
-            const Cand k = shCandF[c];
-            const FeaturePlacement fp = f[k.idx];
-            for (int yy = k.lo + lane; yy <= k.hi; yy += 32)
-            {
-                if (shBlk[yy - y0] != B_AIR && !k.canReplace) continue;
-                if (place_feature(fp, wx, yy, wz, &fb)) atomicMin(&shBest[yy - y0], ((unsigned)c << 8) | fb);
-            }
-        }
-        else
-        {
-            const Cand k = shCandC[c - nColF];
-            const CaveFeaturePlacement cp = cf[k.idx];
-            for (int yy = k.lo + lane; yy <= k.hi; yy += 32)
-            {
-                if (shBlk[yy - y0] != B_AIR && !k.canReplace) continue;
-                if (place_cave_feature(cp, wx, yy, wz, &fb)) atomicMin(&shBest[yy - y0], ((unsigned)c << 8) | fb);
-            }
+            int total = 0;
+            raster(shBig[b], t, 256, false, &total);
         }
     }
     __syncthreads();
-    if (y <= y1 && shBest[t] != kNoBest) *out = (uint8_t)(shBest[t] & 0xffu);
+    // thread t writes column t back if any of its 32 voxels was claimed
+    {
+        __align__(16) uint8_t outv[kSlab];
+        bool any = false;
+#pragma unroll
+        for (int yy = 0; yy < kSlab; ++yy)
+        {
+            const unsigned b = shBest[yy * kSlabPitch + t];
+            any = any || b != kNoBest;
+            outv[yy] = b != kNoBest ? (uint8_t)(b & 0xffu) : shBlk[t * kSlab + yy];
+        }
+        if (any)
+        {
+            reinterpret_cast<uint4*>(colPtr)[0] = reinterpret_cast<const uint4*>(outv)[0];
+            reinterpret_cast<uint4*>(colPtr)[1] = reinterpret_cast<const uint4*>(outv)[1];
+        }
+    }
 }
 
 // tryPlaceSingleDecorator (chunk.cu:1634-1677)

@@ -38,7 +38,7 @@ struct Scratch
         return 0;
     }
 };
-static Scratch g_scratch[14];   // [0..7] stage inputs/outputs, [8..11] fill extras, [12..13] cave-biome queue
+static Scratch g_scratch[16];   // [0..7] stage inputs/outputs, [8..11] fill extras, [12..13] cave-biome queue, [14..15] placement Prep records
 static cudaStream_t g_stream = nullptr;
 
 static int requireReady()
@@ -78,6 +78,8 @@ struct MmgenWorld
     FeaturePlacement* d_gF = nullptr;                // gathered lists of one fill batch
     CaveFeaturePlacement* d_gCF = nullptr;
     GatherInfo* d_info = nullptr;
+    Prep* d_prepF = nullptr;                         // per-placement culling records of one fill batch
+    Prep* d_prepC = nullptr;
     uint2* d_lushQueue = nullptr;                    // voxels of one fill batch waiting for the lush-cave decision
     int* d_lushCount = nullptr;
     uint8_t* d_blocks = nullptr;                     // [chunk][16][16][384]
@@ -120,6 +122,8 @@ int mmgen_init(int device)
         return 1;
     }
     if (!g_stream) MMG_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    // k_fill_features: 40 KB static + the 10 KB noise tables exceed the 48 KB default
+    MMG_CUDA(cudaFuncSetAttribute(k_fill_features, cudaFuncAttributeMaxDynamicSharedMemorySize, kNoiseSmemBytes));
     MMG_LAUNCH(k_init_noise_tables, 3, 256, 0, g_stream);     // simplex lattice tables (mm_arith.cuh)
     MMG_CUDA(cudaStreamSynchronize(g_stream));
     g_device = device;
@@ -286,14 +290,17 @@ constexpr int kFillBatch = 512;
 
 // the kernel sequence of Chunk::fill for one batch of m chunks (lists indexed by batch position)
 static int launchFill(int m, const int* d_list, const int2* d_origins, const float* d_height, const float* d_weights, const float* d_layers,
-                      const CaveLayer* d_caves, const FeaturePlacement* d_gF, const CaveFeaturePlacement* d_gCF, const GatherInfo* d_info,
-                      int strideF, int strideCF, uint8_t* d_blocks, uint2* d_lushQueue, int* d_lushCount, cudaStream_t stream)
+                      const CaveLayer* d_caves, const FeaturePlacement* d_gF, const CaveFeaturePlacement* d_gCF, GatherInfo* d_info,
+                      Prep* d_prepF, Prep* d_prepC, int strideF, int strideCF, uint8_t* d_blocks, uint2* d_lushQueue, int* d_lushCount,
+                      cudaStream_t stream)
 {
     MMG_CUDA(cudaMemsetAsync(d_lushCount, 0, sizeof(int), stream));
     MMG_LAUNCH(k_fill_terrain, m * 256 * 3, kFillSeg, kNoiseSmemBytes, stream, d_list, d_origins, d_height, d_weights, d_layers, d_caves, d_blocks,
                d_lushQueue, d_lushCount);
     MMG_LAUNCH(k_fill_lush, kNumSMs * 8, 128, kNoiseSmemBytes, stream, d_origins, (const uint2*)d_lushQueue, (const int*)d_lushCount, d_blocks);
-    MMG_LAUNCH(k_fill_features, m * 256 * 2, kFeatSeg, kNoiseSmemBytes, stream, d_list, d_origins, d_gF, d_gCF, d_info, strideF, strideCF, d_blocks);
+    MMG_LAUNCH(k_prepare_placements, m, 256, 0, stream, d_list, d_origins, d_gF, d_gCF, d_info, strideF, strideCF, d_prepF, d_prepC);
+    MMG_LAUNCH(k_fill_features, m * 12, 256, kNoiseSmemBytes, stream, d_list, d_origins, d_gF, d_gCF, (const Prep*)d_prepF, (const Prep*)d_prepC,
+               (const GatherInfo*)d_info, strideF, strideCF, d_blocks);
     MMG_LAUNCH(k_decorators, m, 256, 0, stream, d_list, m, d_origins, d_height, d_weights, d_caves, d_blocks);
     return 0;
 }   // chunks gathered + filled per launch group (bounds the gathered-list buffers)
@@ -352,7 +359,8 @@ extern "C" int mmgen_fill(int n, const int32_t* origins, const float* heightfiel
         S[5].ensure((size_t)n * featureStride * sizeof(FeaturePlacement) + 16) ||
         S[6].ensure((size_t)n * caveFeatureStride * sizeof(CaveFeaturePlacement) + 16) || S[7].ensure((size_t)n * 2 * sizeof(int)) ||
         X[0].ensure((size_t)n * sizeof(GatherInfo)) || X[1].ensure((size_t)n * 98304) ||
-        X[2].ensure((size_t)kLushQueueCap * sizeof(uint2)) || X[3].ensure(sizeof(int)))
+        X[2].ensure((size_t)kLushQueueCap * sizeof(uint2)) || X[3].ensure(sizeof(int)) ||
+        g_scratch[14].ensure((size_t)n * featureStride * sizeof(Prep) + 16) || g_scratch[15].ensure((size_t)n * caveFeatureStride * sizeof(Prep) + 16))
         return 1;
     MMG_CUDA(cudaMemcpyAsync(S[0].ptr, origins, (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, g_stream));
     MMG_CUDA(cudaMemcpyAsync(S[1].ptr, heightfield, (size_t)n * 256 * 4, cudaMemcpyHostToDevice, g_stream));
@@ -366,7 +374,8 @@ extern "C" int mmgen_fill(int n, const int32_t* origins, const float* heightfiel
                (const int*)S[7].ptr, featureStride, caveFeatureStride, (GatherInfo*)X[0].ptr);
     if (launchFill(n, nullptr, (const int2*)S[0].ptr, (const float*)S[1].ptr, (const float*)S[2].ptr, (const float*)S[4].ptr,
                    (const CaveLayer*)S[3].ptr, (const FeaturePlacement*)S[5].ptr, (const CaveFeaturePlacement*)S[6].ptr,
-                   (const GatherInfo*)X[0].ptr, featureStride, caveFeatureStride, (uint8_t*)X[1].ptr, (uint2*)X[2].ptr, (int*)X[3].ptr, g_stream))
+                   (GatherInfo*)X[0].ptr, (Prep*)g_scratch[14].ptr, (Prep*)g_scratch[15].ptr, featureStride, caveFeatureStride, (uint8_t*)X[1].ptr,
+                   (uint2*)X[2].ptr, (int*)X[3].ptr, g_stream))
         return 1;
     MMG_CUDA(cudaMemcpyAsync(out_blocks, X[1].ptr, (size_t)n * 98304, cudaMemcpyDeviceToHost, g_stream));
     MMG_CUDA(cudaStreamSynchronize(g_stream));
@@ -421,6 +430,8 @@ int mmgen_world_destroy(MmgenWorld* w)
     cudaFree(w->d_gF);
     cudaFree(w->d_gCF);
     cudaFree(w->d_info);
+    cudaFree(w->d_prepF);
+    cudaFree(w->d_prepC);
     cudaFree(w->d_lushQueue);
     cudaFree(w->d_lushCount);
     cudaFree(w->d_blocks);
@@ -582,6 +593,8 @@ static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
             if (!w->d_gF) MMG_CUDA(cudaMalloc(&w->d_gF, (size_t)kFillBatch * MAX_FEATURES * sizeof(FeaturePlacement)));
             if (!w->d_gCF) MMG_CUDA(cudaMalloc(&w->d_gCF, (size_t)kFillBatch * MAX_CAVE_FEATURES * sizeof(CaveFeaturePlacement)));
             if (!w->d_info) MMG_CUDA(cudaMalloc(&w->d_info, (size_t)kFillBatch * sizeof(GatherInfo)));
+            if (!w->d_prepF) MMG_CUDA(cudaMalloc(&w->d_prepF, (size_t)kFillBatch * MAX_FEATURES * sizeof(Prep)));
+            if (!w->d_prepC) MMG_CUDA(cudaMalloc(&w->d_prepC, (size_t)kFillBatch * MAX_CAVE_FEATURES * sizeof(Prep)));
             if (!w->d_lushQueue) MMG_CUDA(cudaMalloc(&w->d_lushQueue, (size_t)kLushQueueCap * sizeof(uint2)));
             if (!w->d_lushCount) MMG_CUDA(cudaMalloc(&w->d_lushCount, sizeof(int)));
             MMG_CUDA(cudaMemcpyAsync(w->d_list, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, w->stream));
@@ -593,7 +606,8 @@ static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
                            (const CaveFeaturePlacement*)w->d_caveFeatures, (const int*)w->d_counts, nx, w->d_gF, w->d_gCF, w->d_info);
                 if (launchFill(m, dl, (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights, (const float*)w->d_eroded,
                                (const CaveLayer*)w->d_caves, (const FeaturePlacement*)w->d_gF, (const CaveFeaturePlacement*)w->d_gCF,
-                               (const GatherInfo*)w->d_info, MAX_FEATURES, MAX_CAVE_FEATURES, w->d_blocks, w->d_lushQueue, w->d_lushCount, w->stream))
+                               w->d_info, w->d_prepF, w->d_prepC, MAX_FEATURES, MAX_CAVE_FEATURES, w->d_blocks, w->d_lushQueue, w->d_lushCount,
+                               w->stream))
                     return 1;
                 if (hostBlocks)
                 {
