@@ -158,6 +158,46 @@ int mmgen_world_block_checksum(MmgenWorld* w, uint64_t* out);
  * number however a region is tiled over worlds / GPUs, so tiles can be checked against a single world */
 int mmgen_world_chunk_hash_sum(MmgenWorld* w, uint64_t* out);
 
+/* ---- streaming scheduler: Terrain::tick (terrain.cpp:587-960) re-hosted on a device-resident world.
+ * The reference's ChunkState machine (chunk.hpp:18-32), spiral order (terrain.cpp:220-252), per-stage FIFO
+ * queues, drain order and action-time budget (terrain.cpp:67-82) are kept, so with the default costs a tick
+ * launches at most the reference's batches (166 heightfields, 100 layers, 62 caves, 62 fills, 1 zone);
+ * stage products stay in HBM (no per-stage host round trip) and a zone is eroded once its whole 24x24-chunk
+ * gather window has layers, which makes every chunk a pure function of its coordinates (see mm_stream.inl).
+ * The session window [cx0, cx0+nx) x [cz0, cz0+nz) bounds what the stream can generate. */
+typedef struct MmgenStream MmgenStream;
+typedef struct {
+    int32_t heightfields, gatherHeightfields, layers, zonesEroded, caves, placements, gatherPlacements, filled, vbos;
+    int32_t actionTimeLeft;   /* budget left after the tick */
+    int32_t idle;             /* 1 when no queue holds work and no state changed: further ticks do nothing until the player moves */
+    float deviceMs;           /* device time of the tick's launches (CUDA events) */
+} MmgenTickStats;
+/* reference ChunkState values reported by mmgen_stream_states (chunk.hpp:18-32) */
+enum {
+    MMGEN_CHUNK_EMPTY = 0, MMGEN_CHUNK_HAS_HEIGHTFIELD, MMGEN_CHUNK_NEEDS_LAYERS, MMGEN_CHUNK_HAS_LAYERS, MMGEN_CHUNK_NEEDS_EROSION,
+    MMGEN_CHUNK_NEEDS_CAVES, MMGEN_CHUNK_NEEDS_FEATURE_PLACEMENTS, MMGEN_CHUNK_NEEDS_GATHER_FEATURE_PLACEMENTS,
+    MMGEN_CHUNK_READY_TO_FILL, MMGEN_CHUNK_FILLED, MMGEN_CHUNK_NEEDS_VBOS, MMGEN_CHUNK_DRAWABLE
+};
+int mmgen_stream_create(int cx0, int cz0, int nx, int nz, MmgenStream** out);
+int mmgen_stream_destroy(MmgenStream* s);
+/* the backing world (downloads, device pointers, checksums); owned by the stream */
+int mmgen_stream_world(MmgenStream* s, MmgenWorld** out);
+/* chunkVbosGenRadius / chunkMaxGenRadius (terrain.cpp:64-65; defaults 16 and 40) */
+int mmgen_stream_set_radii(MmgenStream* s, int vbosGenRadius, int maxGenRadius);
+/* costs9 = {heightfield, gatherHeightfield, layers, erodeZone, caves, featurePlacements, gatherFeaturePlacements, fill,
+ * createVbos} (terrain.cpp:72-80; NULL keeps the current ones), frame cap and refill rate (terrain.cpp:69-70) */
+int mmgen_stream_set_costs(MmgenStream* s, const int32_t* costs9, int maxActionTimePerFrame, int totalActionTimePerSecond);
+/* Terrain::setCurrentChunkPos(chunkPosFromPlayerPos(player)) (terrain.cpp:254-257, 1031-1034); block coordinates */
+int mmgen_stream_set_player(MmgenStream* s, float playerX, float playerZ);
+/* Terrain::tick(deltaTime); returns when the tick's results are complete on the device */
+int mmgen_stream_tick(MmgenStream* s, float deltaTime, MmgenTickStats* out);
+/* ChunkState of every window chunk, raster order */
+int mmgen_stream_states(MmgenStream* s, uint8_t* out);
+/* chunk coordinates (cx, cz) of the chunks filled since the last call, in fill order; *n = pairs written (<= cap) */
+int mmgen_stream_take_filled(MmgenStream* s, int32_t* coords, int cap, int* n);
+/* block volume of one filled chunk into host memory (98 304 bytes) */
+int mmgen_stream_download_chunk(MmgenStream* s, int cx, int cz, uint8_t* out_blocks);
+
 #ifdef __cplusplus
 }
 #endif

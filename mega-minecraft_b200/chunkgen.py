@@ -258,3 +258,92 @@ class World:
             if v is not None:
                 res[k] = v
         return res
+
+
+class TickStats(ctypes.Structure):
+    """MmgenTickStats (include/mmgen.h)."""
+    _fields_ = [(k, ctypes.c_int32) for k in ("heightfields", "gatherHeightfields", "layers", "zonesEroded", "caves", "placements",
+                                               "gatherPlacements", "filled", "vbos", "actionTimeLeft", "idle")] + [("deviceMs", ctypes.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# reference action-time costs (terrain.cpp:72-80): heightfield, gatherHeightfield, layers, erodeZone, caves, featurePlacements,
+# gatherFeaturePlacements, fill, createVbos; frame cap 500, refill 60 * 500 per second (terrain.cpp:69-70)
+REFERENCE_COSTS = (3, 2, 5, 500, 8, 3, 5, 8, 500 // 3)
+CHUNK_FILLED, CHUNK_NEEDS_VBOS, CHUNK_DRAWABLE = 9, 10, 11
+
+
+class Terrain:
+    """The reference's chunk manager re-hosted on a device-resident world (mmgen_stream_*): same method names and
+    meaning as `Terrain` (terrain.hpp:55-131) for the generation path - setCurrentChunkPos, tick - headless."""
+
+    def __init__(self, gen, cx0, cz0, nx, nz):
+        self.gen, self.L = gen, gen.L
+        self.h = ctypes.c_void_p()
+        gen._check(self.L.mmgen_stream_create(cx0, cz0, nx, nz, ctypes.byref(self.h)))
+        self.cx0, self.cz0, self.nx, self.nz = cx0, cz0, nx, nz
+
+    def close(self):
+        if self.h:
+            self.L.mmgen_stream_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_radii(self, vbos_gen_radius=16, max_gen_radius=40):
+        self.gen._check(self.L.mmgen_stream_set_radii(self.h, int(vbos_gen_radius), int(max_gen_radius)))
+
+    def set_costs(self, costs=REFERENCE_COSTS, max_per_frame=500, per_second=60 * 500):
+        c = (ctypes.c_int32 * 9)(*costs) if costs is not None else None
+        self.gen._check(self.L.mmgen_stream_set_costs(self.h, c, int(max_per_frame), int(per_second)))
+
+    def setCurrentChunkPos(self, cx, cz):
+        self.set_player(cx * 16.0 + 8.0, cz * 16.0 + 8.0)
+
+    def set_player(self, x, z):
+        self.gen._check(self.L.mmgen_stream_set_player(self.h, ctypes.c_float(x), ctypes.c_float(z)))
+
+    def tick(self, delta_time=1.0 / 60.0):
+        st = TickStats()
+        self.gen._check(self.L.mmgen_stream_tick(self.h, ctypes.c_float(delta_time), ctypes.byref(st)))
+        return st
+
+    def states(self):
+        out = np.zeros(self.nx * self.nz, np.uint8)
+        self.gen._check(self.L.mmgen_stream_states(self.h, _ptr(out)))
+        return out.reshape(self.nz, self.nx)
+
+    def take_filled(self, cap=4096):
+        coords = np.zeros((cap, 2), np.int32)
+        n = ctypes.c_int(0)
+        self.gen._check(self.L.mmgen_stream_take_filled(self.h, _ptr(coords), cap, ctypes.byref(n)))
+        return coords[:n.value].copy()
+
+    def download_chunk(self, cx, cz):
+        b = np.empty((16, 16, 384), np.uint8)
+        self.gen._check(self.L.mmgen_stream_download_chunk(self.h, int(cx), int(cz), _ptr(b)))
+        return b
+
+    def chunk_hash_sum(self):
+        """Tiling-invariant hash of every filled chunk (mmgen_world_chunk_hash_sum of the backing world)."""
+        w = ctypes.c_void_p()
+        self.gen._check(self.L.mmgen_stream_world(self.h, ctypes.byref(w)))
+        v = ctypes.c_uint64(0)
+        self.gen._check(self.L.mmgen_world_chunk_hash_sum(w, ctypes.byref(v)))
+        return v.value
+
+    def run_until_idle(self, delta_time=1.0 / 60.0, max_ticks=100000):
+        """Ticks until the scheduler has nothing left to do; returns the per-tick stats."""
+        log = []
+        for _ in range(max_ticks):
+            st = self.tick(delta_time)
+            log.append(st.as_dict())
+            if st.idle:
+                break
+        return log

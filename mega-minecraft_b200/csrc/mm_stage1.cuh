@@ -11,11 +11,11 @@
 
 namespace mmg {
 
-__global__ void __launch_bounds__(256) k_heightfield(const int2* __restrict__ origins, float* __restrict__ heightfield,
-                                                     float* __restrict__ biomeWeights)
+__global__ void __launch_bounds__(256) k_heightfield(const int* __restrict__ chunkList, const int2* __restrict__ origins,
+                                                     float* __restrict__ heightfield, float* __restrict__ biomeWeights)
 {
     noise_tab_stage();
-    const int chunk = blockIdx.x;
+    const int chunk = chunkList ? chunkList[blockIdx.x] : blockIdx.x;
     const int idx = threadIdx.x;            // x + 16*z
     const int2 o = origins[chunk];
     const int wx = o.x + (idx & 15), wz = o.y + (idx >> 4);

@@ -5,6 +5,8 @@
 
 #include <algorithm>
 #include <cstring>
+#include <deque>
+#include <queue>
 #include <mutex>
 #include <vector>
 
@@ -157,7 +159,7 @@ int mmgen_heightfields(int n, const int32_t* origins, float* out_heightfield, fl
     float* d_h = (float*)g_scratch[1].ptr;
     float* d_w = (float*)g_scratch[2].ptr;
     MMG_CUDA(cudaMemcpyAsync(d_o, origins, (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, g_stream));
-    MMG_LAUNCH(k_heightfield, n, 256, kNoiseSmemBytes, g_stream, d_o, d_h, d_w);
+    MMG_LAUNCH(k_heightfield, n, 256, kNoiseSmemBytes, g_stream, (const int*)nullptr, (const int2*)d_o, d_h, d_w);
     if (out_heightfield) MMG_CUDA(cudaMemcpyAsync(out_heightfield, d_h, (size_t)n * 256 * sizeof(float), cudaMemcpyDeviceToHost, g_stream));
     if (out_biomeWeights) MMG_CUDA(cudaMemcpyAsync(out_biomeWeights, d_w, (size_t)n * NUM_BIOMES * 256 * sizeof(float), cudaMemcpyDeviceToHost, g_stream));
     MMG_CUDA(cudaStreamSynchronize(g_stream));
@@ -443,22 +445,185 @@ int mmgen_world_destroy(MmgenWorld* w)
     return 0;
 }
 
+}  // extern "C" (everything below is declared with C linkage by mmgen.h; templates cannot sit inside the block)
+
+// ------------------------------------------------------------------ stage runners of the resident world
+// Each runs one stage over an explicit list of window chunks (raster indices) and keeps w->stage up to date.
+// worldGenerate (batch mode) and the streaming scheduler (mm_stream.cuh, Terrain::tick re-hosted) both
+// drive the world through these. Every runner leaves the stream synchronised: the shared list buffer is reused.
+static int worldUploadList(MmgenWorld* w, const std::vector<int>& list)
+{
+    if (!w->d_list) MMG_CUDA(cudaMalloc(&w->d_list, (size_t)w->n * sizeof(int)));
+    MMG_CUDA(cudaMemcpyAsync(w->d_list, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, w->stream));
+    return 0;
+}
+
+// S1 (Chunk::generateHeightfields); list == nullptr: every chunk of the window
+static int worldHeightfields(MmgenWorld* w, const std::vector<int>* list)
+{
+    if (list && list->empty()) return 0;
+    if (!w->d_height) MMG_CUDA(cudaMalloc(&w->d_height, (size_t)w->n * 256 * sizeof(float)));
+    if (!w->d_weights) MMG_CUDA(cudaMalloc(&w->d_weights, (size_t)w->n * NUM_BIOMES * 256 * sizeof(float)));
+    if (list)
+    {
+        if (worldUploadList(w, *list)) return 1;
+        MMG_LAUNCH(k_heightfield, (int)list->size(), 256, kNoiseSmemBytes, w->stream, (const int*)w->d_list, (const int2*)w->d_origins, w->d_height,
+                   w->d_weights);
+        MMG_CUDA(cudaStreamSynchronize(w->stream));
+        for (int i : *list) w->stage[i] = std::max<uint8_t>(w->stage[i], 1);
+    }
+    else
+    {
+        MMG_LAUNCH(k_heightfield, w->n, 256, kNoiseSmemBytes, w->stream, (const int*)nullptr, (const int2*)w->d_origins, w->d_height, w->d_weights);
+        for (auto& s : w->stage) s = std::max<uint8_t>(s, 1);
+    }
+    return 0;
+}
+
+// S2 (gatherHeightfield + Chunk::generateLayers): every listed chunk has its 3x3 neighbourhood at stage >= 1
+static int worldLayers(MmgenWorld* w, const std::vector<int>& list)
+{
+    if (list.empty()) return 0;
+    if (!w->d_layers) MMG_CUDA(cudaMalloc(&w->d_layers, (size_t)w->n * NUM_MATERIALS * 256 * sizeof(float)));
+    if (worldUploadList(w, list)) return 1;
+    MMG_LAUNCH(k_layers<true>, (int)list.size(), 256, kNoiseSmemBytes, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
+               (const float*)w->d_height, (const float*)w->d_weights, w->d_layers, w->nx);
+    MMG_CUDA(cudaStreamSynchronize(w->stream));   // list buffer is reused
+    for (int i : list) w->stage[i] = std::max<uint8_t>(w->stage[i], 2);
+    return 0;
+}
+
+// S3 (Chunk::erodeZone) for zones given by the window-local corner of their 24x24-chunk gather window
+static int worldErode(MmgenWorld* w, const std::vector<int2>& corners)
+{
+    if (corners.empty()) return 0;
+    const int nx = w->nx;
+    if (!w->d_zone) MMG_CUDA(cudaMalloc(&w->d_zone, (size_t)kZoneBatch * kZonePlanes * kErosionCols * sizeof(float)));
+    if (!w->d_zoneCorners) MMG_CUDA(cudaMalloc(&w->d_zoneCorners, (size_t)kZoneBatch * sizeof(int2)));
+    if (!w->d_flags) MMG_CUDA(cudaMalloc(&w->d_flags, kSweepGroup * sizeof(int)));
+    if (!w->d_eroded) MMG_CUDA(cudaMalloc(&w->d_eroded, (size_t)w->n * NUM_MATERIALS * 256 * sizeof(float)));
+    for (size_t z0 = 0; z0 < corners.size(); z0 += kZoneBatch)
+    {
+        const int m = (int)std::min<size_t>(kZoneBatch, corners.size() - z0);
+        MMG_CUDA(cudaMemcpyAsync(w->d_zoneCorners, corners.data() + z0, (size_t)m * sizeof(int2), cudaMemcpyHostToDevice, w->stream));
+        MMG_LAUNCH(k_zone_gather, dim3(12, 12, m), dim3(32, 32), 0, w->stream, (const float*)w->d_layers,
+                   (const float*)w->d_height, w->d_zone, (const int2*)w->d_zoneCorners, nx);
+        int sweeps = 0;
+        if (erodeZonesDevice(w->d_zone, m, w->d_flags, w->stream, &sweeps)) return 1;
+        w->erosionSweeps += sweeps;
+        MMG_LAUNCH(k_zone_scatter, dim3(6, 6, m), dim3(32, 32), 0, w->stream, (const float*)w->d_zone,
+                   (const float*)w->d_layers, w->d_eroded, (const int2*)w->d_zoneCorners, nx);
+        for (int k = 0; k < m; ++k)
+            for (int z = 6; z < 18; ++z)
+                for (int x = 6; x < 18; ++x) w->stage[(corners[z0 + k].y + z) * nx + corners[z0 + k].x + x] = 3;
+    }
+    MMG_CUDA(cudaStreamSynchronize(w->stream));   // the corner buffer is reused
+    return 0;
+}
+
+// S4 (Chunk::generateCaves)
+static int worldCaves(MmgenWorld* w, const std::vector<int>& list)
+{
+    if (list.empty()) return 0;
+    const int m = (int)list.size();
+    if (!w->d_caves) MMG_CUDA(cudaMalloc(&w->d_caves, (size_t)w->n * 256 * MAX_CAVE_LAYERS * sizeof(CaveLayer)));
+    if (!w->d_caveCols) MMG_CUDA(cudaMalloc(&w->d_caveCols, (size_t)kCaveBatch * 256 * sizeof(CaveColumn)));
+    if (!w->d_caveQueue) MMG_CUDA(cudaMalloc(&w->d_caveQueue, (size_t)kCaveBiomeQueueCap * sizeof(uint2)));
+    if (!w->d_caveCount) MMG_CUDA(cudaMalloc(&w->d_caveCount, sizeof(int)));
+    if (worldUploadList(w, list)) return 1;
+    if (launchCaves(m, (const int*)w->d_list, (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights,
+                    w->d_caveCols, w->d_caves, w->d_caveQueue, w->d_caveCount, w->stream))
+        return 1;
+    MMG_CUDA(cudaStreamSynchronize(w->stream));
+    for (int i : list) w->stage[i] = 4;
+    return 0;
+}
+
+// S5a (Chunk::generateFeaturePlacements, a CPU pass in the reference)
+static int worldPlacements(MmgenWorld* w, const std::vector<int>& list)
+{
+    if (list.empty()) return 0;
+    const int m = (int)list.size();
+    if (!w->d_features) MMG_CUDA(cudaMalloc(&w->d_features, (size_t)w->n * kMaxOwnFeatures * sizeof(FeaturePlacement)));
+    if (!w->d_caveFeatures) MMG_CUDA(cudaMalloc(&w->d_caveFeatures, (size_t)w->n * kMaxOwnCaveFeatures * sizeof(CaveFeaturePlacement)));
+    if (!w->d_counts)
+    {
+        MMG_CUDA(cudaMalloc(&w->d_counts, (size_t)w->n * 2 * sizeof(int)));
+        MMG_CUDA(cudaMemsetAsync(w->d_counts, 0, (size_t)w->n * 2 * sizeof(int), w->stream));
+    }
+    if (worldUploadList(w, list)) return 1;
+    MMG_LAUNCH(k_feature_placements, m, 256, 0, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
+               (const float*)w->d_height, (const float*)w->d_weights, (const float*)w->d_eroded, (const CaveLayer*)w->d_caves,
+               w->d_features, w->d_caveFeatures, w->d_counts);
+    MMG_CUDA(cudaStreamSynchronize(w->stream));
+    for (int i : list) w->stage[i] = 5;
+    return 0;
+}
+
+// S5b + S6 (gatherFeaturePlacements + Chunk::fill + placeDecorators): every listed chunk has its 7x7 neighbourhood at
+// stage >= 5. hostBlocks != nullptr: each finished batch is copied to host memory while the next one is being filled,
+// chunk i of the list to slot hostSlot(i).
+template <typename SlotFn>
+static int worldFill(MmgenWorld* w, const std::vector<int>& list, uint8_t* hostBlocks, SlotFn hostSlot)
+{
+    if (list.empty()) return 0;
+    const int nx = w->nx;
+    if (!w->d_blocks) MMG_CUDA(cudaMalloc(&w->d_blocks, (size_t)w->n * 98304));
+    if (!w->d_gF) MMG_CUDA(cudaMalloc(&w->d_gF, (size_t)kFillBatch * MAX_FEATURES * sizeof(FeaturePlacement)));
+    if (!w->d_gCF) MMG_CUDA(cudaMalloc(&w->d_gCF, (size_t)kFillBatch * MAX_CAVE_FEATURES * sizeof(CaveFeaturePlacement)));
+    if (!w->d_info) MMG_CUDA(cudaMalloc(&w->d_info, (size_t)kFillBatch * sizeof(GatherInfo)));
+    if (!w->d_prepF) MMG_CUDA(cudaMalloc(&w->d_prepF, (size_t)kFillBatch * MAX_FEATURES * sizeof(Prep)));
+    if (!w->d_prepC) MMG_CUDA(cudaMalloc(&w->d_prepC, (size_t)kFillBatch * MAX_CAVE_FEATURES * sizeof(Prep)));
+    if (!w->d_lushQueue) MMG_CUDA(cudaMalloc(&w->d_lushQueue, (size_t)kLushQueueCap * sizeof(uint2)));
+    if (!w->d_lushCount) MMG_CUDA(cudaMalloc(&w->d_lushCount, sizeof(int)));
+    if (worldUploadList(w, list)) return 1;
+    for (size_t b0 = 0; b0 < list.size(); b0 += kFillBatch)
+    {
+        const int m = (int)std::min<size_t>(kFillBatch, list.size() - b0);
+        const int* dl = w->d_list + b0;
+        MMG_LAUNCH(k_gather_features, m, 256, 0, w->stream, dl, (const int2*)w->d_origins, (const FeaturePlacement*)w->d_features,
+                   (const CaveFeaturePlacement*)w->d_caveFeatures, (const int*)w->d_counts, nx, w->d_gF, w->d_gCF, w->d_info);
+        if (launchFill(m, dl, (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights, (const float*)w->d_eroded,
+                       (const CaveLayer*)w->d_caves, (const FeaturePlacement*)w->d_gF, (const CaveFeaturePlacement*)w->d_gCF,
+                       w->d_info, w->d_prepF, w->d_prepC, MAX_FEATURES, MAX_CAVE_FEATURES, w->d_blocks, w->d_lushQueue, w->d_lushCount,
+                       w->stream))
+            return 1;
+        if (hostBlocks)
+        {
+            // stream the finished batch to the host while the next batch is being filled:
+            // one copy per run of consecutive chunks whose host slots are consecutive too
+            cudaEvent_t e = w->evBatch[(b0 / kFillBatch) & 1];
+            MMG_CUDA(cudaEventRecord(e, w->stream));
+            MMG_CUDA(cudaStreamWaitEvent(w->copyStream, e, 0));
+            for (int i = 0; i < m;)
+            {
+                int j = i + 1;
+                while (j < m && list[b0 + j] == list[b0 + j - 1] + 1 && hostSlot(list[b0 + j]) == hostSlot(list[b0 + j - 1]) + 1) ++j;
+                const int c0 = list[b0 + i];
+                MMG_CUDA(cudaMemcpyAsync(hostBlocks + hostSlot(c0) * 98304, w->d_blocks + (size_t)c0 * 98304, (size_t)(j - i) * 98304,
+                                         cudaMemcpyDeviceToHost, w->copyStream));
+                i = j;
+            }
+        }
+    }
+    MMG_CUDA(cudaStreamSynchronize(w->stream));
+    for (int i : list) w->stage[i] = 6;
+    return 0;
+}
+
 static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
 {
     if (requireReady()) return 1;
     MMG_CUDA(cudaEventRecord(w->ev[12], w->stream));
     // host-delivery calls take their only input, the chunk origins, from host memory every time
     if (hostBlocks) MMG_CUDA(cudaMemcpyAsync(w->d_origins, w->h_origins.data(), (size_t)w->n * sizeof(int2), cudaMemcpyHostToDevice, w->stream));
+    const int nx = w->nx, nz = w->nz;
     if (stageMask & MMGEN_STAGE_HEIGHTFIELD)
     {
-        if (!w->d_height) MMG_CUDA(cudaMalloc(&w->d_height, (size_t)w->n * 256 * sizeof(float)));
-        if (!w->d_weights) MMG_CUDA(cudaMalloc(&w->d_weights, (size_t)w->n * NUM_BIOMES * 256 * sizeof(float)));
         MMG_CUDA(cudaEventRecord(w->ev[0], w->stream));
-        MMG_LAUNCH(k_heightfield, w->n, 256, kNoiseSmemBytes, w->stream, w->d_origins, w->d_height, w->d_weights);
+        if (worldHeightfields(w, nullptr)) return 1;
         MMG_CUDA(cudaEventRecord(w->ev[1], w->stream));
-        for (auto& s : w->stage) s = std::max<uint8_t>(s, 1);
     }
-    const int nx = w->nx, nz = w->nz;
     if (stageMask & MMGEN_STAGE_LAYERS)
     {
         // chunks whose 3x3 neighbourhood lies inside the window (gatherHeightfield's condition)
@@ -467,16 +632,7 @@ static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
             for (int x = 1; x < nx - 1; ++x)
                 if (w->stage[z * nx + x] >= 1) list.push_back(z * nx + x);
         MMG_CUDA(cudaEventRecord(w->ev[2], w->stream));
-        if (!list.empty())
-        {
-            if (!w->d_layers) MMG_CUDA(cudaMalloc(&w->d_layers, (size_t)w->n * NUM_MATERIALS * 256 * sizeof(float)));
-            if (!w->d_list) MMG_CUDA(cudaMalloc(&w->d_list, (size_t)w->n * sizeof(int)));
-            MMG_CUDA(cudaMemcpyAsync(w->d_list, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, w->stream));
-            MMG_LAUNCH(k_layers<true>, (int)list.size(), 256, kNoiseSmemBytes, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
-                       (const float*)w->d_height, (const float*)w->d_weights, w->d_layers, nx);
-            MMG_CUDA(cudaStreamSynchronize(w->stream));   // list buffer is reused below
-            for (int i : list) w->stage[i] = std::max<uint8_t>(w->stage[i], 2);
-        }
+        if (worldLayers(w, list)) return 1;
         MMG_CUDA(cudaEventRecord(w->ev[3], w->stream));
     }
     if (stageMask & MMGEN_STAGE_EROSION)
@@ -499,30 +655,7 @@ static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
                     for (int x = 0; x < 24 && ok; ++x) ok = w->stage[(lz0 + z) * nx + lx0 + x] >= 2;
                 if (ok) corners.push_back(make_int2(lx0, lz0));
             }
-        if (!corners.empty())
-        {
-            const int batch = std::min<int>(kZoneBatch, (int)corners.size());
-            if (!w->d_zone) MMG_CUDA(cudaMalloc(&w->d_zone, (size_t)kZoneBatch * kZonePlanes * kErosionCols * sizeof(float)));
-            if (!w->d_zoneCorners) MMG_CUDA(cudaMalloc(&w->d_zoneCorners, (size_t)kZoneBatch * sizeof(int2)));
-            if (!w->d_flags) MMG_CUDA(cudaMalloc(&w->d_flags, kSweepGroup * sizeof(int)));
-            if (!w->d_eroded) MMG_CUDA(cudaMalloc(&w->d_eroded, (size_t)w->n * NUM_MATERIALS * 256 * sizeof(float)));
-            (void)batch;
-            for (size_t z0 = 0; z0 < corners.size(); z0 += kZoneBatch)
-            {
-                const int m = (int)std::min<size_t>(kZoneBatch, corners.size() - z0);
-                MMG_CUDA(cudaMemcpyAsync(w->d_zoneCorners, corners.data() + z0, (size_t)m * sizeof(int2), cudaMemcpyHostToDevice, w->stream));
-                MMG_LAUNCH(k_zone_gather, dim3(12, 12, m), dim3(32, 32), 0, w->stream, (const float*)w->d_layers,
-                           (const float*)w->d_height, w->d_zone, (const int2*)w->d_zoneCorners, nx);
-                int sweeps = 0;
-                if (erodeZonesDevice(w->d_zone, m, w->d_flags, w->stream, &sweeps)) return 1;
-                w->erosionSweeps += sweeps;
-                MMG_LAUNCH(k_zone_scatter, dim3(6, 6, m), dim3(32, 32), 0, w->stream, (const float*)w->d_zone,
-                           (const float*)w->d_layers, w->d_eroded, (const int2*)w->d_zoneCorners, nx);
-                for (int k = 0; k < m; ++k)
-                    for (int z = 6; z < 18; ++z)
-                        for (int x = 6; x < 18; ++x) w->stage[(corners[z0 + k].y + z) * nx + corners[z0 + k].x + x] = 3;
-            }
-        }
+        if (worldErode(w, corners)) return 1;
         MMG_CUDA(cudaEventRecord(w->ev[5], w->stream));
     }
     if (stageMask & MMGEN_STAGE_CAVES)
@@ -531,21 +664,7 @@ static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
         for (int i = 0; i < w->n; ++i)
             if (w->stage[i] == 3 && w->inTarget(i % nx, i / nx, 3)) list.push_back(i);
         MMG_CUDA(cudaEventRecord(w->ev[6], w->stream));
-        if (!list.empty())
-        {
-            const int m = (int)list.size();
-            if (!w->d_caves) MMG_CUDA(cudaMalloc(&w->d_caves, (size_t)w->n * 256 * MAX_CAVE_LAYERS * sizeof(CaveLayer)));
-            if (!w->d_caveCols) MMG_CUDA(cudaMalloc(&w->d_caveCols, (size_t)kCaveBatch * 256 * sizeof(CaveColumn)));
-            if (!w->d_list) MMG_CUDA(cudaMalloc(&w->d_list, (size_t)w->n * sizeof(int)));
-            MMG_CUDA(cudaMemcpyAsync(w->d_list, list.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, w->stream));
-            if (!w->d_caveQueue) MMG_CUDA(cudaMalloc(&w->d_caveQueue, (size_t)kCaveBiomeQueueCap * sizeof(uint2)));
-            if (!w->d_caveCount) MMG_CUDA(cudaMalloc(&w->d_caveCount, sizeof(int)));
-            if (launchCaves(m, (const int*)w->d_list, (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights,
-                            w->d_caveCols, w->d_caves, w->d_caveQueue, w->d_caveCount, w->stream))
-                return 1;
-            MMG_CUDA(cudaStreamSynchronize(w->stream));
-            for (int i : list) w->stage[i] = 4;
-        }
+        if (worldCaves(w, list)) return 1;
         MMG_CUDA(cudaEventRecord(w->ev[7], w->stream));
     }
     if (stageMask & MMGEN_STAGE_FEATURES)
@@ -554,23 +673,7 @@ static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
         for (int i = 0; i < w->n; ++i)
             if (w->stage[i] == 4) list.push_back(i);
         MMG_CUDA(cudaEventRecord(w->ev[8], w->stream));
-        if (!list.empty())
-        {
-            const int m = (int)list.size();
-            if (!w->d_features) MMG_CUDA(cudaMalloc(&w->d_features, (size_t)w->n * kMaxOwnFeatures * sizeof(FeaturePlacement)));
-            if (!w->d_caveFeatures) MMG_CUDA(cudaMalloc(&w->d_caveFeatures, (size_t)w->n * kMaxOwnCaveFeatures * sizeof(CaveFeaturePlacement)));
-            if (!w->d_counts)
-            {
-                MMG_CUDA(cudaMalloc(&w->d_counts, (size_t)w->n * 2 * sizeof(int)));
-                MMG_CUDA(cudaMemsetAsync(w->d_counts, 0, (size_t)w->n * 2 * sizeof(int), w->stream));
-            }
-            MMG_CUDA(cudaMemcpyAsync(w->d_list, list.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, w->stream));
-            MMG_LAUNCH(k_feature_placements, m, 256, 0, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
-                       (const float*)w->d_height, (const float*)w->d_weights, (const float*)w->d_eroded, (const CaveLayer*)w->d_caves,
-                       w->d_features, w->d_caveFeatures, w->d_counts);
-            MMG_CUDA(cudaStreamSynchronize(w->stream));
-            for (int i : list) w->stage[i] = 5;
-        }
+        if (worldPlacements(w, list)) return 1;
         MMG_CUDA(cudaEventRecord(w->ev[9], w->stream));
     }
     if (stageMask & MMGEN_STAGE_FILL)
@@ -587,52 +690,11 @@ static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
                 if (ok) list.push_back(z * nx + x);
             }
         MMG_CUDA(cudaEventRecord(w->ev[10], w->stream));
-        if (!list.empty())
-        {
-            if (!w->d_blocks) MMG_CUDA(cudaMalloc(&w->d_blocks, (size_t)w->n * 98304));
-            if (!w->d_gF) MMG_CUDA(cudaMalloc(&w->d_gF, (size_t)kFillBatch * MAX_FEATURES * sizeof(FeaturePlacement)));
-            if (!w->d_gCF) MMG_CUDA(cudaMalloc(&w->d_gCF, (size_t)kFillBatch * MAX_CAVE_FEATURES * sizeof(CaveFeaturePlacement)));
-            if (!w->d_info) MMG_CUDA(cudaMalloc(&w->d_info, (size_t)kFillBatch * sizeof(GatherInfo)));
-            if (!w->d_prepF) MMG_CUDA(cudaMalloc(&w->d_prepF, (size_t)kFillBatch * MAX_FEATURES * sizeof(Prep)));
-            if (!w->d_prepC) MMG_CUDA(cudaMalloc(&w->d_prepC, (size_t)kFillBatch * MAX_CAVE_FEATURES * sizeof(Prep)));
-            if (!w->d_lushQueue) MMG_CUDA(cudaMalloc(&w->d_lushQueue, (size_t)kLushQueueCap * sizeof(uint2)));
-            if (!w->d_lushCount) MMG_CUDA(cudaMalloc(&w->d_lushCount, sizeof(int)));
-            MMG_CUDA(cudaMemcpyAsync(w->d_list, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, w->stream));
-            for (size_t b0 = 0; b0 < list.size(); b0 += kFillBatch)
-            {
-                const int m = (int)std::min<size_t>(kFillBatch, list.size() - b0);
-                const int* dl = w->d_list + b0;
-                MMG_LAUNCH(k_gather_features, m, 256, 0, w->stream, dl, (const int2*)w->d_origins, (const FeaturePlacement*)w->d_features,
-                           (const CaveFeaturePlacement*)w->d_caveFeatures, (const int*)w->d_counts, nx, w->d_gF, w->d_gCF, w->d_info);
-                if (launchFill(m, dl, (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights, (const float*)w->d_eroded,
-                               (const CaveLayer*)w->d_caves, (const FeaturePlacement*)w->d_gF, (const CaveFeaturePlacement*)w->d_gCF,
-                               w->d_info, w->d_prepF, w->d_prepC, MAX_FEATURES, MAX_CAVE_FEATURES, w->d_blocks, w->d_lushQueue, w->d_lushCount,
-                               w->stream))
-                    return 1;
-                if (hostBlocks)
-                {
-                    // stream the finished batch to the host while the next batch is being filled:
-                    // one copy per run of consecutive chunks (a region row is contiguous in the window)
-                    cudaEvent_t e = w->evBatch[(b0 / kFillBatch) & 1];
-                    MMG_CUDA(cudaEventRecord(e, w->stream));
-                    MMG_CUDA(cudaStreamWaitEvent(w->copyStream, e, 0));
-                    for (int i = 0; i < m;)
-                    {
-                        int j = i + 1;
-                        while (j < m && list[b0 + j] == list[b0 + j - 1] + 1) ++j;
-                        const int c0 = list[b0 + i];
-                        const int cx = c0 % nx, cz = c0 / nx;
-                        const size_t slot = w->hasTarget ? (size_t)(cz - w->tz0) * w->tnx + (cx - w->tx0) : (size_t)c0;
-                        // runs never cross a window row, so slots of a run are consecutive too
-                        MMG_CUDA(cudaMemcpyAsync(hostBlocks + slot * 98304, w->d_blocks + (size_t)c0 * 98304, (size_t)(j - i) * 98304,
-                                                 cudaMemcpyDeviceToHost, w->copyStream));
-                        i = j;
-                    }
-                }
-            }
-            MMG_CUDA(cudaStreamSynchronize(w->stream));
-            for (int i : list) w->stage[i] = 6;
-        }
+        // host slots: region raster order (a region row is contiguous in the window)
+        auto slot = [w, nx](int c) -> size_t {
+            return w->hasTarget ? (size_t)(c / nx - w->tz0) * w->tnx + (c % nx - w->tx0) : (size_t)c;
+        };
+        if (worldFill(w, list, hostBlocks, slot)) return 1;
         MMG_CUDA(cudaEventRecord(w->ev[11], w->stream));
     }
     if (hostBlocks)
@@ -657,6 +719,8 @@ int mmgen_world_generate_to_host(MmgenWorld* w, int stageMask, uint8_t* out_bloc
     }
     return worldGenerate(w, stageMask, out_blocks);
 }
+
+#include "mm_stream.inl"
 
 int mmgen_world_reset(MmgenWorld* w)
 {
@@ -848,5 +912,3 @@ int mmgen_world_download(MmgenWorld* w, float* heightfield, float* biomeWeights,
     if (blocks && w->d_blocks) MMG_CUDA(cudaMemcpy(blocks, w->d_blocks, (size_t)w->n * 98304, cudaMemcpyDeviceToHost));
     return 0;
 }
-
-}  // extern "C"
