@@ -256,3 +256,55 @@ def test_erosion_properties(gen, oracle):
     assert (out >= planes[:8] - 1e-3).all()
     again, _ = gen.erode_zone(np.concatenate([out, planes[8:9]]))
     assert np.abs(again - out).max() < 1e-3
+
+
+def test_c4_cave_and_fill_stress_32x32(gen, mm, oracle):
+    """BASELINE.json config 4: 32x32 chunks [0,32)^2 of full 16x384x16 volumes. Size-independent properties over all
+    1024 chunks, the batch operators against the resident world on the same chunks (two host paths, one kernel set),
+    and the oracle's caves + fill on a sample fed with the product's own upstream outputs."""
+    from oracle import oracle as orc
+    world = gen.region_world(0, 0, 32, 32)
+    world.generate(mm.STAGE_ALL)
+    st = world.stages()
+    assert (st == 6).sum() == 1024
+    d = world.download(heightfield=True, biome_weights=True, layers=True, cave_layers=True, blocks=True)
+    nx = world.nx
+    filled = np.nonzero(st.ravel() == 6)[0]
+    blocks = d["blocks"][filled]
+    h = d["heightfield"][filled]
+    # y = 0 is bedrock everywhere (chunk.cu:1207-1210); nothing but air above the highest ground + the tallest feature
+    bedrock = blocks[0, 0, 0, 0]
+    assert (blocks[:, :, :, 0] == bedrock).all()
+    top = max(int(np.floor(d["heightfield"].max())), 128) + 1 + 120      # tallest feature bound, featurePlacement.hpp via c_featureHeightBounds
+    assert (blocks[:, :, :, min(top + 1, 384):] == 0).all()
+    # cave layers: non-empty, sorted, disjoint runs in every column of the region
+    cl = d["cave_layers"][filled]
+    start, end = cl["start"].astype(np.int64), cl["end"].astype(np.int64)
+    used = start != 384
+    assert (end[used] > start[used]).all() and ((start[:, :, 1:] > end[:, :, :-1]) | ~used[:, :, 1:]).all()
+    # idempotence and the two checksums
+    c1, s1 = world.block_checksum(), world.chunk_hash_sum()
+    world.reset()
+    world.generate(mm.STAGE_ALL)
+    assert (world.block_checksum(), world.chunk_hash_sum()) == (c1, s1)
+    # batch operators on a sample: same bytes as the resident world
+    origins = origins_of(world.cx0, world.cz0, world.nx, world.nz)
+    sample = filled[:: 97][:8]
+    hb, wb = gen.heightfields(origins[sample])
+    assert np.array_equal(hb, d["heightfield"][sample]) and np.array_equal(wb, d["biome_weights"][sample])
+    cb = gen.caves(origins[sample], hb, wb)
+    assert cb.tobytes() == d["cave_layers"][sample].tobytes()
+    F, CF = world.download_features()
+    placed = {int(c): F[int(c)] for c in np.nonzero(st.ravel() >= 5)[0]}
+    cplaced = {int(c): CF[int(c)] for c in np.nonzero(st.ravel() >= 5)[0]}
+    gf = [orc.gather_features(placed, int(c) % nx, int(c) // nx, nx) for c in sample]
+    gcf = [orc.gather_features(cplaced, int(c) % nx, int(c) // nx, nx) for c in sample]
+    bb = gen.fill(origins[sample], hb, wb, d["layers"][sample], cb, gf, gcf)
+    assert np.array_equal(bb, d["blocks"][sample])
+    # oracle on the same sample (caves on half of it: the expensive part of the oracle)
+    oc = oracle.caves(origins[sample[:4]], hb[:4], wb[:4])
+    for f in ("start", "end", "bottomBiome", "topBiome"):
+        assert np.array_equal(cb[:4][f], oc[f]), f
+    ob = oracle.fill(origins[sample], hb, wb, d["layers"][sample], cb, gf, gcf)
+    assert np.array_equal(bb, ob)
+    world.close()
