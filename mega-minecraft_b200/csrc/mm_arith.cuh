@@ -51,6 +51,13 @@ struct Minstd
         x = mod_m(seed);
         if (x == 0) x = 1;
     }
+    // resume from a state produced by an earlier Minstd (x is already in [1, m))
+    static __device__ __forceinline__ Minstd from_state(uint32_t state)
+    {
+        Minstd r(1u);
+        r.x = state;
+        return r;
+    }
     __device__ __forceinline__ uint32_t next()
     {
         x = mod_m((uint64_t)x * 48271u);

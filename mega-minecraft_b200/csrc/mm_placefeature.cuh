@@ -109,11 +109,13 @@ __device__ __forceinline__ uint8_t random_crystal_block(float rand)
 }
 
 // featurePlacement.hpp:147-1107. Returns true and sets *out when the voxel belongs to the feature.
-__device__ MMG_NOISE_INLINE bool place_feature(const FeaturePlacement& fp, int wx, int wy, int wz, uint8_t* out)
+// frngState: state of the placement's RNG right after seeding, make_rng4(fp.x, fp.y, fp.z, 1293012).x (featurePlacement.hpp:153),
+// computed once per placement by k_prepare_placements instead of once per voxel.
+__device__ MMG_NOISE_INLINE bool place_feature(const FeaturePlacement& fp, int wx, int wy, int wz, uint32_t frngState, uint8_t* out)
 {
     const int fx = wx - fp.x, fy = wy - fp.y, fz = wz - fp.z;
     V3 pos = v3((float)fx, (float)fy, (float)fz);
-    Minstd frng = make_rng4(fp.x, fp.y, fp.z, 1293012);
+    Minstd frng = Minstd::from_state(frngState);
     Minstd brng = make_rng4(wx, wy, wz, 57847812);
     switch (fp.feature)
     {
@@ -623,7 +625,8 @@ __device__ MMG_NOISE_INLINE bool place_feature(const FeaturePlacement& fp, int w
 }
 
 // featurePlacement.hpp:1110-1380
-__device__ MMG_NOISE_INLINE bool place_cave_feature(const CaveFeaturePlacement& cp, int wx, int wy, int wz, uint8_t* out)
+// frngState: make_rng4(cp.x, cp.y, cp.z, 398132).x, seeded once per placement by k_prepare_placements
+__device__ MMG_NOISE_INLINE bool place_cave_feature(const CaveFeaturePlacement& cp, int wx, int wy, int wz, uint32_t frngState, uint8_t* out)
 {
     const int lh = cp.layerHeight;
     const int fx = wx - cp.x, fy = wy - cp.y, fz = wz - cp.z;
@@ -632,7 +635,7 @@ __device__ MMG_NOISE_INLINE bool place_cave_feature(const CaveFeaturePlacement& 
     V3 top = v3((float)tx, (float)ty, (float)tz);
     // the reference seeds both engines on entry (featurePlacement.hpp:1119-1120); nearly every call ends at a
     // geometric rejection that needs neither, so they are seeded where the first draw happens (same streams)
-#define MMG_FRNG() Minstd frng = make_rng4(cp.x, cp.y, cp.z, 398132)
+#define MMG_FRNG() Minstd frng = Minstd::from_state(frngState)
 #define MMG_BRNG() Minstd brng = make_rng4(wx, wy, wz, 9322743)
     switch (cp.feature)
     {

@@ -383,7 +383,8 @@ __global__ void __launch_bounds__(128) k_fill_lush(const int2* __restrict__ orig
 // What k_fill_features needs to know about a placement before it touches the rasteriser: the y band it can
 // fill (reference bound intersected with the type's own band, clipped to the world), the columns of THIS
 // chunk its horizontal reach covers, and whether it may overwrite terrain. lo > hi: cannot touch the chunk.
-struct Prep { short lo, hi; unsigned char xr, zr, canReplace, feature; };      // xr = x0 | x1 << 4 (local 0..15), zr likewise
+struct Prep { short lo, hi; unsigned char xr, zr, canReplace, feature; uint32_t seed; };      // xr = x0 | x1 << 4 (local 0..15), zr likewise;
+                                                                                              // seed = state of the placement's own RNG
 
 // One CTA per chunk of the batch: Prep records of the chunk's (already reach-culled, ordered) lists. NONE ends
 // a list scan in the reference (chunk.cu:1448-1451, 1477-1480): the list lengths are cut at the first NONE.
@@ -411,6 +412,7 @@ __global__ void __launch_bounds__(256) k_prepare_placements(const int* __restric
         const FeaturePlacement p = gF[(size_t)li * strideF + i];
         Prep k;
         k.lo = 1; k.hi = 0; k.xr = k.zr = 0; k.canReplace = p.canReplaceBlocks ? 1 : 0; k.feature = p.feature;
+        k.seed = make_rng4(p.x, p.y, p.z, 1293012).x;      // featurePlacement.hpp:153: seeded once per placement here, not per voxel
         if (p.feature == F_NONE) atomicMin(&shFirstNone[0], i);
         else if (columns(p.x, p.z, min(c_featureReach[p.feature], 1 << 16), &k))
         {
@@ -425,12 +427,54 @@ __global__ void __launch_bounds__(256) k_prepare_placements(const int* __restric
         const CaveFeaturePlacement p = gCF[(size_t)li * strideCF + i];
         Prep k;
         k.lo = 1; k.hi = 0; k.xr = k.zr = 0; k.canReplace = p.canReplaceBlocks ? 1 : 0; k.feature = p.feature;
+        // featurePlacement.hpp:1119: the placement's own RNG is seeded once here; its first draw fixes the size of
+        // most cave features, so the box is cut to what THIS placement can fill (each bound below is the rasteriser's
+        // own rejection test in place_cave_feature evaluated with the same rounded operations, only tighter than the type's)
+        Minstd frng = make_rng4(p.x, p.y, p.z, 398132);
+        k.seed = frng.x;
+        const float u0 = frng.u01();
+        const int lh = p.layerHeight;
+        int reach = min(c_caveFeatureReach[p.feature], 1 << 16), lo2 = -1024, hi2 = 1024;
+        switch (p.feature)
+        {
+        case CF_CAVE_VINE:
+        {
+            int height = (int)fmaf(u0, 12.f, 3.f);
+            height = height < lh ? height : lh;
+            lo2 = p.y + lh - height; hi2 = p.y + lh;                    // ty in [-height, 0]
+            break;
+        }
+        case CF_GLOWSTONE_CLUSTER:
+        {
+            // |top * scale| <= 6 with top.y scaled by 1.35 first; every component of a vector bounds its length from below
+            const float scale = fmaf(u0, 0.5f, 1.f);
+            int t = 6, v = 4;
+            while (t > 0 && (float)t * scale > 6.f) --t;
+            while (v > 0 && ((float)v * 1.35f) * scale > 6.f) --v;
+            reach = t;
+            lo2 = p.y + lh - v; hi2 = p.y + lh + v;
+            break;
+        }
+        case CF_STORMLIGHT_SPHERE:
+        case CF_CEILING_STORMLIGHT_SPHERE:
+        {
+            // dist <= radius and dist >= |component| (integer offsets: the squares and their sum are exact)
+            const int R = (int)floorf(fmaf(u0, 4.f, 3.5f));
+            reach = R;
+            const int c = p.y + (p.feature == CF_CEILING_STORMLIGHT_SPHERE ? lh : 0);
+            lo2 = c - R; hi2 = c + R;
+            break;
+        }
+        case CF_WARPED_FUNGUS: hi2 = p.y + (int)fmaf(u0, 3.0f, 2.5f) + 3; break;      // fy <= height + 3
+        case CF_AMBER_FUNGUS: hi2 = p.y + (int)fmaf(u0, 4.5f, 4.5f) + 3; break;
+        default: break;
+        }
         if (p.feature == CF_NONE) atomicMin(&shFirstNone[1], i);
-        else if (columns(p.x, p.z, min(c_caveFeatureReach[p.feature], 1 << 16), &k))
+        else if (columns(p.x, p.z, reach, &k))
         {
             const int* band = c_caveFeatureBand[p.feature];
-            k.lo = (short)max(max(p.y + c_caveFeatureHeightBounds[p.feature][0], p.y + band[0] + (band[1] ? p.layerHeight : 0)), 0);
-            k.hi = (short)min(min(p.y + p.layerHeight + c_caveFeatureHeightBounds[p.feature][1], p.y + band[2] + (band[3] ? p.layerHeight : 0)), 383);
+            k.lo = (short)max(max(max(p.y + c_caveFeatureHeightBounds[p.feature][0], p.y + band[0] + (band[1] ? lh : 0)), lo2), 0);
+            k.hi = (short)min(min(min(p.y + lh + c_caveFeatureHeightBounds[p.feature][1], p.y + band[2] + (band[3] ? lh : 0)), hi2), 383);
             if (p.feature == CF_GLOWSTONE_CLUSTER || p.feature == CF_WARPED_FUNGUS || p.feature == CF_AMBER_FUNGUS) shNoise = 1;
         }
         prepC[(size_t)li * strideCF + i] = k;
@@ -523,7 +567,7 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
             if (shBest[yy * kSlabPitch + col] <= (key | 0xffu)) continue;      // claimed by an earlier placement
             if (shBlk[col * kSlab + yy] != B_AIR && !k.canReplace) continue;
             uint8_t fb = 0;
-            const bool hit = cave ? place_cave_feature(cp, o.x + x, y, o.y + z, &fb) : place_feature(fp, o.x + x, y, o.y + z, &fb);
+            const bool hit = cave ? place_cave_feature(cp, o.x + x, y, o.y + z, k.seed, &fb) : place_feature(fp, o.x + x, y, o.y + z, k.seed, &fb);
             if (hit) atomicMin(&shBest[yy * kSlabPitch + col], key | fb);
         }
         return true;
