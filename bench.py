@@ -256,7 +256,9 @@ def run_own(args):
     # ---- device-resident leg
     sampler = ClockSampler(local_rank)
     stage_ms = np.zeros(7)
+    fp32_measured = gen.measure_fp32_peak()          # FFMA microbenchmark on this GPU, right before the timed region
     barrier()
+    gen.kernel_timing(True)                          # CUDA event pairs around every hot-kernel launch, on the world's stream
     sampler.start()
     l0 = gen.launch_count()
     t0 = time.perf_counter()
@@ -270,6 +272,8 @@ def run_own(args):
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
+    ktimes = gen.kernel_times()                      # {kernel: (device ms summed over the timed steps, launches)}
+    gen.kernel_timing(False)
     launches = gen.launch_count() - l0
     dev_s = max_over_ranks(dev_ms / 1e3)
     wall_s = max_over_ranks(wall)
@@ -307,17 +311,37 @@ def run_own(args):
     ach4 = sum_over_ranks(flop_s4) / 1e12 / max(max_over_ranks(stage_ms[4] / 1e3), 1e-9)
     ach6 = sum_over_ranks(flop_s6) / 1e12 / max(max_over_ranks(stage_ms[6] / 1e3), 1e-9)
     hbm6 = sum_over_ranks(n_target * BYTES_FILL_CHUNK) / 1e9 / max(max_over_ranks(stage_ms[6] / 1e3), 1e-9)
-    dom = 6 if stage_ms[6] >= stage_ms[4] else 4
-    roof = {"bound": "fp32", "kernel": "k_fill" if dom == 6 else "k_caves", "achieved": ach6 if dom == 6 else ach4,
-            "peak": pk["fp32_tflops"] * world_size, "unit": "TFLOP/s", "frac": (ach6 if dom == 6 else ach4) / (pk["fp32_tflops"] * world_size),
-            "traffic": None,
-            "peak_src": "nominal CUDA-core FP32 peak (148 SM x 128 lanes x 2 x %.0f MHz) per GPU; MEASURED_PEAKS.json has no FP32 figure" % pk["sm_max_mhz"],
-            "note": "no stage is a dense contraction (tensor cores unused); algorithmic FLOPs = reference noise-primitive calls x canonical cost"}
+    # per-kernel device time per step (this rank), from the event pairs recorded during the timed steps
+    kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in ktimes.items() if v[1]}
+    # dominant kernel = the single kernel with the most device time; its algorithmic FLOPs are defined for k_caves (every
+    # evaluated voxel of shouldGenerateCaveAtBlock) and k_fill_terrain (getCaveBiome per voxel 0 < y <= h, chunk.cu:1243-1370)
+    flops_of = {"k_caves": flop_s4, "k_fill_terrain": flop_s6}
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else "k_caves"
+    roof_kernel = dom if dom in flops_of else max(flops_of, key=lambda k: kernels.get(k, {"ms_per_step": 0})["ms_per_step"])
+    rk = kernels.get(roof_kernel, {"ms_per_step": float("nan"), "launches_per_step": 1})
+    rk_launches = max(rk["launches_per_step"], 1)
+    avg_launch_ms = rk["ms_per_step"] / rk_launches
+    ach = sum_over_ranks(flops_of[roof_kernel]) / world_size / rk_launches / 1e12 / max(avg_launch_ms / 1e3, 1e-12)      # per GPU
+    fp32_all = max_over_ranks(fp32_measured)
+    fp32_peak = min(fp32_all, pk["fp32_tflops"]) if fp32_all > 0 else pk["fp32_tflops"]
+    roof = {"bound": "fp32", "kernel": roof_kernel, "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
+            "traffic": None, "avg_launch_ms": avg_launch_ms, "launches_per_step": rk_launches,
+            "algorithmic_flop_per_launch": flops_of[roof_kernel] / rk_launches,
+            "peak_src": "FFMA microbenchmark run by this process on the same GPU just before the timed region (mmgen_measure_fp32_peak: %.1f TFLOP/s; "
+                        "nominal 148 SM x 128 lanes x 2 x %.0f MHz = %.1f); MEASURED_PEAKS.json carries HBM and bf16 tensor figures only" % (
+                            fp32_measured, pk["sm_max_mhz"], pk["fp32_tflops"]),
+            "dominant_kernel_by_time": dom,
+            "note": "no stage is a dense contraction and none is HBM-bound (S6 moves %.0f GB/s of compulsory bytes), so the bound is the FP32 pipe; "
+                    "algorithmic FLOPs = noise-primitive calls of the reference algorithm x canonical cost (SURVEY.md 8d), evaluations this "
+                    "implementation proves unnecessary still count; k_fill_features (placement rasterisation) has no FLOP model and is reported by time" % hbm6}
     stages = {
-        "S1": {"ms": float(stage_ms[1])}, "S2": {"ms": float(stage_ms[2])}, "S3": {"ms": float(stage_ms[3]), "sweeps": world.erosion_sweeps()},
-        "S4": {"ms": float(stage_ms[4]), "fp32_tflops": ach4, "fp32_frac": ach4 / (pk["fp32_tflops"] * world_size)},
+        "S1": {"ms": float(stage_ms[1])}, "S2": {"ms": float(stage_ms[2])},
+        "S3": {"ms": float(stage_ms[3]), "sweeps": world.erosion_sweeps(),
+               "plane_traffic_gbs": world.erosion_sweeps() * 32 * 3 * 589824 / 1e9 / max(kernels.get("k_erode_sweep", {"ms_per_step": 0})["ms_per_step"] / 1e3, 1e-9),
+               "note": "L2-resident: <= 32 zones x 3 planes x 590 KB per sweep launch"},
+        "S4": {"ms": float(stage_ms[4]), "fp32_tflops": ach4, "fp32_frac": ach4 / (fp32_peak * world_size)},
         "S5": {"ms": float(stage_ms[5])},
-        "S6": {"ms": float(stage_ms[6]), "fp32_tflops": ach6, "fp32_frac": ach6 / (pk["fp32_tflops"] * world_size), "hbm_gbs": hbm6,
+        "S6": {"ms": float(stage_ms[6]), "fp32_tflops": ach6, "fp32_frac": ach6 / (fp32_peak * world_size), "hbm_gbs": hbm6,
                "hbm_frac": hbm6 / (pk["hbm_gbs"] * world_size), "hbm_peak_src": pk["src"]},
     }
     counts = tiling.stage_chunk_counts(*tile)
@@ -336,7 +360,7 @@ def run_own(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * max(e2e_wall, e2e_dev) / args.steps, "host_checksum": host_sum},
         "gpu_launches": int(sum_over_ranks(launches)), "rank_ms": [round(t, 2) for t in rank_ms], "balance_passes": balance_log,
-        "roofline": roof, "stages": stages, "clocks": clocks, "block_checksums": [("%016x" % c) for c in checks], "world_hash": "%016x" % (sum(sharding.gather_u64(hash_sum)) & 0xFFFFFFFFFFFFFFFF),
+        "roofline": roof, "kernels": kernels, "stages": stages, "clocks": clocks, "block_checksums": [("%016x" % c) for c in checks], "world_hash": "%016x" % (sum(sharding.gather_u64(hash_sum)) & 0xFFFFFFFFFFFFFFFF),
     }
     if rank == 0 and not args.no_cpu and world_size == 1:
         nthreads = os.cpu_count() or 1

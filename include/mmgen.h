@@ -198,6 +198,15 @@ int mmgen_stream_take_filled(MmgenStream* s, int32_t* coords, int cap, int* n);
 /* block volume of one filled chunk into host memory (98 304 bytes) */
 int mmgen_stream_download_chunk(MmgenStream* s, int cx, int cz, uint8_t* out_blocks);
 
+/* ---- measurement helpers (bench.py) */
+/* switch per-kernel device timing on / off (CUDA event pairs around the hot kernels' launches, on their stream); clears the record */
+int mmgen_kernel_timing(int enable);
+/* summed device time and launch count per kernel since the last call; kernel i is named mmgen_kernel_name(i); *n = entries written */
+int mmgen_kernel_times(int cap, float* out_ms, int32_t* out_launches, int* n);
+const char* mmgen_kernel_name(int slot);
+/* achieved FP32 FMA rate of this device (TFLOP/s, 8 independent FFMA chains per thread on every SM): roofline denominator */
+int mmgen_measure_fp32_peak(float* out_tflops);
+
 #ifdef __cplusplus
 }
 #endif

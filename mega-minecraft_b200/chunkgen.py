@@ -78,6 +78,25 @@ class ChunkGen:
     def launch_count(self):
         return int(self.L.mmgen_launch_count())
 
+    def kernel_timing(self, enable=True):
+        """Per-kernel device timing (CUDA events around the hot kernels' launches); clears the record."""
+        self._check(self.L.mmgen_kernel_timing(1 if enable else 0))
+
+    def kernel_times(self):
+        """{kernel name: (summed device ms, launches)} since the last call."""
+        ms = np.zeros(32, np.float32)
+        cnt = np.zeros(32, np.int32)
+        n = ctypes.c_int(0)
+        self._check(self.L.mmgen_kernel_times(32, _ptr(ms), _ptr(cnt), ctypes.byref(n)))
+        self.L.mmgen_kernel_name.restype = ctypes.c_char_p
+        return {self.L.mmgen_kernel_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n.value)}
+
+    def measure_fp32_peak(self):
+        """Achieved FP32 FMA rate of the device in TFLOP/s (microbenchmark kernel in libmmgen)."""
+        v = ctypes.c_float(0)
+        self._check(self.L.mmgen_measure_fp32_peak(ctypes.byref(v)))
+        return v.value
+
     @staticmethod
     def origins(chunk_coords):
         """(n,2) chunk coordinates -> (n,2) int32 block origins."""

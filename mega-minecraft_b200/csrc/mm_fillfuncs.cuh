@@ -196,8 +196,11 @@ __device__ __forceinline__ bool needs_cave_biome(uint8_t block) { return block =
 // ------------------------------------------------------------------ chunk.cu:1202-1380
 // weights[24], layersAndHeight[21] (20 layer starts + height), caveLayers[32] of the column
 // *pendingLush: the voxel is lush-cave rock within the moss depth; its block is lush_block(wx, y, wz)
+// *pendingRock: the block is STONE / DEEPSLATE / BLACKSTONE and still has to go through getCaveBiome +
+// caveBiomeBlockPostProcess with the depths *bottomDepth / *topDepth (chunk.cu:1366-1370); the caller either queues
+// it for the dense kernel k_fill_rock or finishes it in place with finish_rock_block.
 __device__ __forceinline__ uint8_t fill_place_block(const float* weights, const float* layersAndHeight, const CaveLayer* caveLayers, int y,
-                                       float height, int wx, int wz, bool* pendingLush)
+                                       float height, int wx, int wz, bool* pendingRock, int* bottomDepth, int* topDepth)
 {
     if (y == 0) return B_BEDROCK;
     const float fy = (float)y;
@@ -248,8 +251,40 @@ __device__ __forceinline__ uint8_t fill_place_block(const float* weights, const 
     if (isTopBlock && block == B_DIRT) block = c_biomeGrassBlock[randBiome];
     biome_post_process(&block, randBiome, wx, y, wz, height, isTopBlock);
     if (needs_cave_biome(block))
-        cave_biome_post_process(&block, cave_biome(wx, y, wz, height, 190249401), wx, y, wz, caveBottomDepth, caveTopDepth, pendingLush);
+    {
+        *pendingRock = true;
+        *bottomDepth = caveBottomDepth;
+        *topDepth = caveTopDepth;
+    }
     return block;
+}
+
+// the deferred tail of chunkFillPlaceBlock for a rock voxel (chunk.cu:1366-1370)
+__device__ __forceinline__ uint8_t finish_rock_block(uint8_t block, int wx, int y, int wz, float height, int bottomDepth, int topDepth, bool* pendingLush)
+{
+    cave_biome_post_process(&block, cave_biome(wx, y, wz, height, 190249401), wx, y, wz, bottomDepth, topDepth, pendingLush);
+    return block;
+}
+
+// Queue record of a rock voxel: x = chunk, y = voxel index (17 bits) | rock kind (2) | bottom depth (6) | top depth (6).
+// The depths only matter as "== 0" (top block) and "in [0, threshold]" with threshold = 1.5 + 4.5 simplex3 (biomeFuncs.hpp:653-657);
+// |simplex3| <= 42 * 4 * max_r((0.6 - r^2)^4 r) * |grad| < 42 * 4 * 0.0209 * 3.2 < 11.3, so threshold < 53: every depth that is
+// negative or above 62 behaves like "far" and is stored as 63.
+__device__ __forceinline__ uint2 pack_rock(int chunk, int voxel, uint8_t block, int bottomDepth, int topDepth)
+{
+    const unsigned kind = block == B_STONE ? 0u : (block == B_DEEPSLATE ? 1u : 2u);
+    const unsigned bd = (bottomDepth < 0 || bottomDepth > 62) ? 63u : (unsigned)bottomDepth;
+    const unsigned td = (topDepth < 0 || topDepth > 62) ? 63u : (unsigned)topDepth;
+    return make_uint2((unsigned)chunk, (unsigned)voxel | kind << 17 | bd << 19 | td << 25);
+}
+__device__ __forceinline__ void unpack_rock(uint2 e, int* chunk, int* voxel, uint8_t* block, int* bottomDepth, int* topDepth)
+{
+    *chunk = (int)e.x;
+    *voxel = (int)(e.y & 0x1ffffu);
+    const unsigned kind = (e.y >> 17) & 3u, bd = (e.y >> 19) & 63u, td = (e.y >> 25) & 63u;
+    *block = kind == 0u ? B_STONE : (kind == 1u ? B_DEEPSLATE : B_BLACKSTONE);
+    *bottomDepth = bd == 63u ? -384 : (int)bd;
+    *topDepth = td == 63u ? -384 : (int)td;
 }
 
 }  // namespace mmg

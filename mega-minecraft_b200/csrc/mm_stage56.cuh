@@ -301,10 +301,12 @@ __global__ void k_gather_info(const FeaturePlacement* __restrict__ gF, const Cav
 
 // kernFill (chunk.cu:1382-1510) as three kernels over one batch of chunks. fillList[li] = chunk index into
 // the resident planes (or li itself); gathered lists are indexed by li with the given strides.
-//   k_fill_terrain   chunkFillPlaceBlock for every voxel: one CTA per 128-voxel segment of a column
-//                    (y fastest => a warp stores 32 consecutive block IDs), three segments per column;
-//                    segments above the terrain and the sea are stored as AIR without further work.
-//                    Voxels that need the LUSH_CAVES clay / moss decision are queued instead of decided.
+//   k_fill_terrain   chunkFillPlaceBlock for every voxel up to the cave-biome step: one CTA per 128-voxel segment
+//                    of a column (y fastest => a warp stores 32 consecutive block IDs), three segments per column;
+//                    segments above the terrain and the sea are stored as AIR without further work. STONE /
+//                    DEEPSLATE / BLACKSTONE voxels - the only ones getCaveBiome can change - are queued.
+//   k_fill_rock      getCaveBiome + caveBiomeBlockPostProcess for the queued voxels, one per thread on dense warps.
+//                    Voxels that need the LUSH_CAVES clay / moss decision are queued once more.
 //   k_fill_lush      decides the queued voxels, one per thread (they are rare and scattered: evaluated in
 //                    place they would occupy 3-4 lanes of a warp for a 27-cell Worley + 9 simplex).
 //   k_fill_features  the placement scan: per column, the chunk's lists are reduced to the placements whose
@@ -317,15 +319,19 @@ __global__ void k_gather_info(const FeaturePlacement* __restrict__ gF, const Cav
 constexpr int kFillSeg = 128;
 constexpr int kColCapF = 512, kColCapC = 1024;   // candidates of one column segment kept in shared memory
 constexpr int kLushQueueCap = 1 << 22;           // queued voxels per fill batch (overflow is decided in place)
+constexpr int kRockQueuePerChunk = 49152;        // rock-queue slots per chunk of a fill batch (typical need ~30 k; overflow is decided in place)
 
+// counters of one fill batch: [0] lush queue length, [1] rock queue length
 __global__ void __launch_bounds__(kFillSeg, 8) k_fill_terrain(const int* __restrict__ fillList, const int2* __restrict__ origins,
                                                               const float* __restrict__ heightfield, const float* __restrict__ biomeWeights,
                                                               const float* __restrict__ layers, const CaveLayer* __restrict__ caveLayers,
-                                                              uint8_t* __restrict__ blocks, uint2* __restrict__ lushQueue, int* __restrict__ lushCount)
+                                                              uint8_t* __restrict__ blocks, uint2* __restrict__ rockQueue, int rockQueueCap,
+                                                              uint2* __restrict__ lushQueue, int* __restrict__ counters)
 {
     __shared__ float shW[NUM_BIOMES];
     __shared__ float shLH[NUM_MATERIALS + 1];
     __shared__ CaveLayer shCL[MAX_CAVE_LAYERS];
+    __shared__ int shCnt[kFillSeg / 32], shBase;
     const int seg = blockIdx.x % 3, col = blockIdx.x / 3;
     const int li = col >> 8, idx = col & 255;
     const int chunk = fillList ? fillList[li] : li;
@@ -345,30 +351,88 @@ __global__ void __launch_bounds__(kFillSeg, 8) k_fill_terrain(const int* __restr
     const int2 o = origins[chunk];
     const int wx = o.x + (idx & 15), wz = o.y + (idx >> 4);
     noise_tab_stage();      // includes the barrier that publishes the column data
-    bool lush = false;
-    uint8_t block = fill_place_block(shW, shLH, shCL, y, height, wx, wz, &lush);
-    // warp-aggregated append of the pending voxels
-    const unsigned m = __ballot_sync(0xffffffffu, lush);
-    if (m)
+    bool rock = false;
+    int bd = -384, td = -384;
+    uint8_t block = fill_place_block(shW, shLH, shCL, y, height, wx, wz, &rock, &bd, &td);
+    // CTA-aggregated append of the rock voxels (one atomic per CTA: the queue takes ~30 k voxels per chunk)
+    const int lane = t & 31, warp = t >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, rock);
+    if (lane == 0) shCnt[warp] = __popc(m);
+    __syncthreads();
+    if (t == 0)
     {
-        const int lane = t & 31, leader = __ffs(m) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(lushCount, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (lush)
+        int total = 0;
+#pragma unroll
+        for (int w = 0; w < kFillSeg / 32; ++w) total += shCnt[w];
+        shBase = total ? atomicAdd(&counters[1], total) : 0;
+    }
+    __syncthreads();
+    if (rock)
+    {
+        int slot = shBase + __popc(m & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; ++w) slot += shCnt[w];
+        if (slot < rockQueueCap) rockQueue[slot] = pack_rock(chunk, idx * 384 + y, block, bd, td);
+        else
         {
-            const int slot = base + __popc(m & ((1u << lane) - 1u));
-            if (slot < kLushQueueCap) lushQueue[slot] = make_uint2((unsigned)chunk, (unsigned)(idx * 384 + y));
-            else block = lush_block(wx, y, wz);
+            // queue full: finish the voxel here (same result, just on a sparse warp)
+            bool lush = false;
+            block = finish_rock_block(block, wx, y, wz, height, bd, td, &lush);
+            if (lush) block = lush_block(wx, y, wz);
         }
     }
     *out = block;
+    (void)lushQueue;
+}
+
+// getCaveBiome + caveBiomeBlockPostProcess for the queued rock voxels, one per thread on dense warps. In k_fill_terrain
+// the same work ran on whatever lanes of a 32-voxel column run happened to be rock below the surface (22 of 32 on average).
+__global__ void __launch_bounds__(128, 8) k_fill_rock(const int2* __restrict__ origins, const float* __restrict__ heightfield,
+                                                      const uint2* __restrict__ rockQueue, int rockQueueCap, uint8_t* __restrict__ blocks,
+                                                      uint2* __restrict__ lushQueue, int* __restrict__ counters)
+{
+    const int n = min(counters[1], rockQueueCap);
+    if (blockIdx.x * blockDim.x >= n) return;
+    noise_tab_stage();
+    const int lane = threadIdx.x & 31;
+    for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x)
+    {
+        const int i = i0 + threadIdx.x;
+        bool lush = false;
+        int chunk = 0, voxel = 0, wx = 0, wz = 0, y = 0;
+        if (i < n)
+        {
+            uint8_t rockBlock;
+            int bd, td;
+            unpack_rock(rockQueue[i], &chunk, &voxel, &rockBlock, &bd, &td);
+            const int idx = voxel / 384;
+            y = voxel - idx * 384;
+            const int2 o = origins[chunk];
+            wx = o.x + (idx & 15); wz = o.y + (idx >> 4);
+            const uint8_t block = finish_rock_block(rockBlock, wx, y, wz, heightfield[(size_t)chunk * 256 + idx], bd, td, &lush);
+            if (block != rockBlock) blocks[(size_t)chunk * 98304 + voxel] = block;
+        }
+        // warp-aggregated append of the voxels that need the lush-cave clay / moss decision
+        const unsigned m = __ballot_sync(0xffffffffu, lush);
+        if (m)
+        {
+            const int leader = __ffs(m) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&counters[0], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (lush)
+            {
+                const int slot = base + __popc(m & ((1u << lane) - 1u));
+                if (slot < kLushQueueCap) lushQueue[slot] = make_uint2((unsigned)chunk, (unsigned)voxel);
+                else blocks[(size_t)chunk * 98304 + voxel] = lush_block(wx, y, wz);
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(128) k_fill_lush(const int2* __restrict__ origins, const uint2* __restrict__ lushQueue,
-                                                   const int* __restrict__ lushCount, uint8_t* __restrict__ blocks)
+                                                   const int* __restrict__ counters, uint8_t* __restrict__ blocks)
 {
-    const int n = min(*lushCount, kLushQueueCap);
+    const int n = min(counters[0], kLushQueueCap);
     if (blockIdx.x * blockDim.x >= n) return;
     noise_tab_stage();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)

@@ -40,7 +40,7 @@ struct Scratch
         return 0;
     }
 };
-static Scratch g_scratch[16];   // [0..7] stage inputs/outputs, [8..11] fill extras, [12..13] cave-biome queue, [14..15] placement Prep records
+static Scratch g_scratch[17];   // [0..7] stage inputs/outputs, [8..11] fill extras, [12..13] cave-biome queue, [14..15] placement Prep records, [16] rock-voxel queue
 static cudaStream_t g_stream = nullptr;
 
 static int requireReady()
@@ -51,6 +51,61 @@ static int requireReady()
         return 1;
     }
     return 0;
+}
+
+
+// ---- per-kernel device timing (mmgen_kernel_timing): CUDA event pairs around the launches of the hot kernels,
+// on the stream they are launched on. Off by default; bench.py switches it on for its timed region.
+enum KernelSlot { K_HEIGHTFIELD, K_LAYERS, K_ERODE_SWEEPS, K_CAVE_COLUMNS, K_CAVES, K_CAVE_BIOMES, K_PLACEMENTS, K_GATHER, K_FILL_TERRAIN,
+                  K_FILL_ROCK, K_FILL_LUSH, K_PREPARE, K_FILL_FEATURES, K_DECORATORS, K_NUM };
+static const char* const kKernelNames[K_NUM] = {"k_heightfield", "k_layers", "k_erode_sweep", "k_cave_columns", "k_caves", "k_cave_biomes",
+                                                "k_feature_placements", "k_gather_features", "k_fill_terrain", "k_fill_rock", "k_fill_lush",
+                                                "k_prepare_placements", "k_fill_features", "k_decorators"};
+struct KernelTimer
+{
+    bool on = false;
+    std::vector<cudaEvent_t> pool;      // pairs: [2i] before, [2i+1] after
+    std::vector<int> slotOf, countOf;
+    size_t used = 0;
+    void begin(int slot, cudaStream_t st, int launches)
+    {
+        if (!on) return;
+        if (2 * used + 2 > pool.size())
+        {
+            cudaEvent_t a, b;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { on = false; return; }
+            pool.push_back(a); pool.push_back(b);
+        }
+        slotOf.resize(used + 1); countOf.resize(used + 1);
+        slotOf[used] = slot; countOf[used] = launches;
+        cudaEventRecord(pool[2 * used], st);
+    }
+    void end(cudaStream_t st)
+    {
+        if (!on) return;
+        cudaEventRecord(pool[2 * used + 1], st);
+        ++used;
+    }
+};
+static KernelTimer g_kt;
+#define MMG_TIMED(slot, stream, launches, stmt) do { g_kt.begin(slot, stream, launches); stmt; g_kt.end(stream); } while (0)
+
+// dependent-FMA microbenchmark for the FP32 roofline denominator: 8 independent chains per thread, all lanes busy
+__global__ void __launch_bounds__(256) k_fp32_peak(float* out, int iters)
+{
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.9999f, c = 1e-4f;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i)
+    {
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+        {
+            a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
 }  // namespace mmg
@@ -83,7 +138,8 @@ struct MmgenWorld
     Prep* d_prepF = nullptr;                         // per-placement culling records of one fill batch
     Prep* d_prepC = nullptr;
     uint2* d_lushQueue = nullptr;                    // voxels of one fill batch waiting for the lush-cave decision
-    int* d_lushCount = nullptr;
+    int* d_lushCount = nullptr;                      // [0] lush queue length, [1] rock queue length
+    uint2* d_rockQueue = nullptr;                    // rock voxels of one fill batch waiting for getCaveBiome (k_fill_rock)
     uint8_t* d_blocks = nullptr;                     // [chunk][16][16][384]
     int erosionSweeps = 0;
     std::vector<uint8_t> stage;
@@ -187,6 +243,7 @@ static int erodeZonesDevice(float* d_zones, int nZones, int* d_flags, cudaStream
         while (!converged)
         {
             MMG_CUDA(cudaMemsetAsync(d_flags, 0, kSweepGroup * sizeof(int), stream));
+            g_kt.begin(K_ERODE_SWEEPS, stream, kSweepGroup);
             for (int b = 0; b < kSweepGroup; ++b)
             {
                 MMG_LAUNCH(k_erode_sweep, dim3(12, 12, nZones), dim3(32, 32), 0, stream, d_zones, pIn, pOut, layer + 1, accIn, accOut,
@@ -196,6 +253,7 @@ static int erodeZonesDevice(float* d_zones, int nZones, int* d_flags, cudaStream
                 first = false;
                 ++sweeps;
             }
+            g_kt.end(stream);
             MMG_CUDA(cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, stream));
             MMG_CUDA(cudaStreamSynchronize(stream));
             converged = (h_flags[kSweepGroup - 1] == 0);
@@ -255,11 +313,12 @@ static int launchCaves(int m, const int* d_list, const int2* d_origins, const fl
         // without a list, chunk index == batch position: offset every per-chunk pointer instead
         const size_t off = d_list ? 0 : (size_t)c0;
         MMG_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
-        MMG_LAUNCH(k_cave_columns, mb, 256, kNoiseSmemBytes, stream, dl, d_origins + off, d_weights + off * NUM_BIOMES * 256, d_cols);
-        MMG_LAUNCH(k_caves, mb * 256, 128, kNoiseSmemBytes, stream, dl, d_origins + off, d_height + off * 256, (const CaveColumn*)d_cols,
-                   d_caves + off * 256 * MAX_CAVE_LAYERS, d_queue, d_count, kCaveBiomeQueueCap);
-        MMG_LAUNCH(k_cave_biomes, kNumSMs * 16, 128, kNoiseSmemBytes, stream, d_origins + off, d_height + off * 256, (const uint2*)d_queue,
-                   (const int*)d_count, kCaveBiomeQueueCap, d_caves + off * 256 * MAX_CAVE_LAYERS);
+        MMG_TIMED(K_CAVE_COLUMNS, stream, 1, MMG_LAUNCH(k_cave_columns, mb, 256, kNoiseSmemBytes, stream, dl, d_origins + off,
+                                                        d_weights + off * NUM_BIOMES * 256, d_cols));
+        MMG_TIMED(K_CAVES, stream, 1, MMG_LAUNCH(k_caves, mb * 256, 128, kNoiseSmemBytes, stream, dl, d_origins + off, d_height + off * 256,
+                                                 (const CaveColumn*)d_cols, d_caves + off * 256 * MAX_CAVE_LAYERS, d_queue, d_count, kCaveBiomeQueueCap));
+        MMG_TIMED(K_CAVE_BIOMES, stream, 1, MMG_LAUNCH(k_cave_biomes, kNumSMs * 16, 128, kNoiseSmemBytes, stream, d_origins + off, d_height + off * 256,
+                                                       (const uint2*)d_queue, (const int*)d_count, kCaveBiomeQueueCap, d_caves + off * 256 * MAX_CAVE_LAYERS));
     }
     return 0;
 }
@@ -293,17 +352,22 @@ constexpr int kFillBatch = 512;
 // the kernel sequence of Chunk::fill for one batch of m chunks (lists indexed by batch position)
 static int launchFill(int m, const int* d_list, const int2* d_origins, const float* d_height, const float* d_weights, const float* d_layers,
                       const CaveLayer* d_caves, const FeaturePlacement* d_gF, const CaveFeaturePlacement* d_gCF, GatherInfo* d_info,
-                      Prep* d_prepF, Prep* d_prepC, int strideF, int strideCF, uint8_t* d_blocks, uint2* d_lushQueue, int* d_lushCount,
-                      cudaStream_t stream)
+                      Prep* d_prepF, Prep* d_prepC, int strideF, int strideCF, uint8_t* d_blocks, uint2* d_rockQueue, uint2* d_lushQueue,
+                      int* d_counters, cudaStream_t stream)
 {
-    MMG_CUDA(cudaMemsetAsync(d_lushCount, 0, sizeof(int), stream));
-    MMG_LAUNCH(k_fill_terrain, m * 256 * 3, kFillSeg, kNoiseSmemBytes, stream, d_list, d_origins, d_height, d_weights, d_layers, d_caves, d_blocks,
-               d_lushQueue, d_lushCount);
-    MMG_LAUNCH(k_fill_lush, kNumSMs * 8, 128, kNoiseSmemBytes, stream, d_origins, (const uint2*)d_lushQueue, (const int*)d_lushCount, d_blocks);
-    MMG_LAUNCH(k_prepare_placements, m, 256, 0, stream, d_list, d_origins, d_gF, d_gCF, d_info, strideF, strideCF, d_prepF, d_prepC);
-    MMG_LAUNCH(k_fill_features, m * 12, 256, kNoiseSmemBytes, stream, d_list, d_origins, d_gF, d_gCF, (const Prep*)d_prepF, (const Prep*)d_prepC,
-               (const GatherInfo*)d_info, strideF, strideCF, d_blocks);
-    MMG_LAUNCH(k_decorators, m, 256, 0, stream, d_list, m, d_origins, d_height, d_weights, d_caves, d_blocks);
+    const int rockCap = (int)std::min<size_t>((size_t)m * kRockQueuePerChunk, (size_t)kFillBatch * kRockQueuePerChunk);
+    MMG_CUDA(cudaMemsetAsync(d_counters, 0, 2 * sizeof(int), stream));
+    MMG_TIMED(K_FILL_TERRAIN, stream, 1, MMG_LAUNCH(k_fill_terrain, m * 256 * 3, kFillSeg, kNoiseSmemBytes, stream, d_list, d_origins, d_height,
+                                                    d_weights, d_layers, d_caves, d_blocks, d_rockQueue, rockCap, d_lushQueue, d_counters));
+    MMG_TIMED(K_FILL_ROCK, stream, 1, MMG_LAUNCH(k_fill_rock, kNumSMs * 8, 128, kNoiseSmemBytes, stream, d_origins, d_height,
+                                                 (const uint2*)d_rockQueue, rockCap, d_blocks, d_lushQueue, d_counters));
+    MMG_TIMED(K_FILL_LUSH, stream, 1, MMG_LAUNCH(k_fill_lush, kNumSMs * 8, 128, kNoiseSmemBytes, stream, d_origins, (const uint2*)d_lushQueue,
+                                                 (const int*)d_counters, d_blocks));
+    MMG_TIMED(K_PREPARE, stream, 1, MMG_LAUNCH(k_prepare_placements, m, 256, 0, stream, d_list, d_origins, d_gF, d_gCF, d_info, strideF, strideCF,
+                                               d_prepF, d_prepC));
+    MMG_TIMED(K_FILL_FEATURES, stream, 1, MMG_LAUNCH(k_fill_features, m * 12, 256, kNoiseSmemBytes, stream, d_list, d_origins, d_gF, d_gCF,
+                                                     (const Prep*)d_prepF, (const Prep*)d_prepC, (const GatherInfo*)d_info, strideF, strideCF, d_blocks));
+    MMG_TIMED(K_DECORATORS, stream, 1, MMG_LAUNCH(k_decorators, m, 256, 0, stream, d_list, m, d_origins, d_height, d_weights, d_caves, d_blocks));
     return 0;
 }   // chunks gathered + filled per launch group (bounds the gathered-list buffers)
 
@@ -361,7 +425,8 @@ extern "C" int mmgen_fill(int n, const int32_t* origins, const float* heightfiel
         S[5].ensure((size_t)n * featureStride * sizeof(FeaturePlacement) + 16) ||
         S[6].ensure((size_t)n * caveFeatureStride * sizeof(CaveFeaturePlacement) + 16) || S[7].ensure((size_t)n * 2 * sizeof(int)) ||
         X[0].ensure((size_t)n * sizeof(GatherInfo)) || X[1].ensure((size_t)n * 98304) ||
-        X[2].ensure((size_t)kLushQueueCap * sizeof(uint2)) || X[3].ensure(sizeof(int)) ||
+        X[2].ensure((size_t)kLushQueueCap * sizeof(uint2)) || X[3].ensure(2 * sizeof(int)) ||
+        g_scratch[16].ensure((size_t)std::min(n, kFillBatch) * kRockQueuePerChunk * sizeof(uint2)) ||
         g_scratch[14].ensure((size_t)n * featureStride * sizeof(Prep) + 16) || g_scratch[15].ensure((size_t)n * caveFeatureStride * sizeof(Prep) + 16))
         return 1;
     MMG_CUDA(cudaMemcpyAsync(S[0].ptr, origins, (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, g_stream));
@@ -377,7 +442,7 @@ extern "C" int mmgen_fill(int n, const int32_t* origins, const float* heightfiel
     if (launchFill(n, nullptr, (const int2*)S[0].ptr, (const float*)S[1].ptr, (const float*)S[2].ptr, (const float*)S[4].ptr,
                    (const CaveLayer*)S[3].ptr, (const FeaturePlacement*)S[5].ptr, (const CaveFeaturePlacement*)S[6].ptr,
                    (GatherInfo*)X[0].ptr, (Prep*)g_scratch[14].ptr, (Prep*)g_scratch[15].ptr, featureStride, caveFeatureStride, (uint8_t*)X[1].ptr,
-                   (uint2*)X[2].ptr, (int*)X[3].ptr, g_stream))
+                   (uint2*)g_scratch[16].ptr, (uint2*)X[2].ptr, (int*)X[3].ptr, g_stream))
         return 1;
     MMG_CUDA(cudaMemcpyAsync(out_blocks, X[1].ptr, (size_t)n * 98304, cudaMemcpyDeviceToHost, g_stream));
     MMG_CUDA(cudaStreamSynchronize(g_stream));
@@ -436,6 +501,7 @@ int mmgen_world_destroy(MmgenWorld* w)
     cudaFree(w->d_prepC);
     cudaFree(w->d_lushQueue);
     cudaFree(w->d_lushCount);
+    cudaFree(w->d_rockQueue);
     cudaFree(w->d_blocks);
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     for (auto& e : w->evBatch) if (e) cudaEventDestroy(e);
@@ -467,14 +533,15 @@ static int worldHeightfields(MmgenWorld* w, const std::vector<int>* list)
     if (list)
     {
         if (worldUploadList(w, *list)) return 1;
-        MMG_LAUNCH(k_heightfield, (int)list->size(), 256, kNoiseSmemBytes, w->stream, (const int*)w->d_list, (const int2*)w->d_origins, w->d_height,
-                   w->d_weights);
+        MMG_TIMED(K_HEIGHTFIELD, w->stream, 1, MMG_LAUNCH(k_heightfield, (int)list->size(), 256, kNoiseSmemBytes, w->stream, (const int*)w->d_list,
+                                                          (const int2*)w->d_origins, w->d_height, w->d_weights));
         MMG_CUDA(cudaStreamSynchronize(w->stream));
         for (int i : *list) w->stage[i] = std::max<uint8_t>(w->stage[i], 1);
     }
     else
     {
-        MMG_LAUNCH(k_heightfield, w->n, 256, kNoiseSmemBytes, w->stream, (const int*)nullptr, (const int2*)w->d_origins, w->d_height, w->d_weights);
+        MMG_TIMED(K_HEIGHTFIELD, w->stream, 1, MMG_LAUNCH(k_heightfield, w->n, 256, kNoiseSmemBytes, w->stream, (const int*)nullptr,
+                                                          (const int2*)w->d_origins, w->d_height, w->d_weights));
         for (auto& s : w->stage) s = std::max<uint8_t>(s, 1);
     }
     return 0;
@@ -486,8 +553,8 @@ static int worldLayers(MmgenWorld* w, const std::vector<int>& list)
     if (list.empty()) return 0;
     if (!w->d_layers) MMG_CUDA(cudaMalloc(&w->d_layers, (size_t)w->n * NUM_MATERIALS * 256 * sizeof(float)));
     if (worldUploadList(w, list)) return 1;
-    MMG_LAUNCH(k_layers<true>, (int)list.size(), 256, kNoiseSmemBytes, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
-               (const float*)w->d_height, (const float*)w->d_weights, w->d_layers, w->nx);
+    MMG_TIMED(K_LAYERS, w->stream, 1, MMG_LAUNCH(k_layers<true>, (int)list.size(), 256, kNoiseSmemBytes, w->stream, (const int*)w->d_list,
+                                                 (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights, w->d_layers, w->nx));
     MMG_CUDA(cudaStreamSynchronize(w->stream));   // list buffer is reused
     for (int i : list) w->stage[i] = std::max<uint8_t>(w->stage[i], 2);
     return 0;
@@ -552,9 +619,9 @@ static int worldPlacements(MmgenWorld* w, const std::vector<int>& list)
         MMG_CUDA(cudaMemsetAsync(w->d_counts, 0, (size_t)w->n * 2 * sizeof(int), w->stream));
     }
     if (worldUploadList(w, list)) return 1;
-    MMG_LAUNCH(k_feature_placements, m, 256, 0, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
-               (const float*)w->d_height, (const float*)w->d_weights, (const float*)w->d_eroded, (const CaveLayer*)w->d_caves,
-               w->d_features, w->d_caveFeatures, w->d_counts);
+    MMG_TIMED(K_PLACEMENTS, w->stream, 1, MMG_LAUNCH(k_feature_placements, m, 256, 0, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
+                                                     (const float*)w->d_height, (const float*)w->d_weights, (const float*)w->d_eroded,
+                                                     (const CaveLayer*)w->d_caves, w->d_features, w->d_caveFeatures, w->d_counts));
     MMG_CUDA(cudaStreamSynchronize(w->stream));
     for (int i : list) w->stage[i] = 5;
     return 0;
@@ -575,18 +642,20 @@ static int worldFill(MmgenWorld* w, const std::vector<int>& list, uint8_t* hostB
     if (!w->d_prepF) MMG_CUDA(cudaMalloc(&w->d_prepF, (size_t)kFillBatch * MAX_FEATURES * sizeof(Prep)));
     if (!w->d_prepC) MMG_CUDA(cudaMalloc(&w->d_prepC, (size_t)kFillBatch * MAX_CAVE_FEATURES * sizeof(Prep)));
     if (!w->d_lushQueue) MMG_CUDA(cudaMalloc(&w->d_lushQueue, (size_t)kLushQueueCap * sizeof(uint2)));
-    if (!w->d_lushCount) MMG_CUDA(cudaMalloc(&w->d_lushCount, sizeof(int)));
+    if (!w->d_lushCount) MMG_CUDA(cudaMalloc(&w->d_lushCount, 2 * sizeof(int)));
+    if (!w->d_rockQueue) MMG_CUDA(cudaMalloc(&w->d_rockQueue, (size_t)kFillBatch * kRockQueuePerChunk * sizeof(uint2)));
     if (worldUploadList(w, list)) return 1;
     for (size_t b0 = 0; b0 < list.size(); b0 += kFillBatch)
     {
         const int m = (int)std::min<size_t>(kFillBatch, list.size() - b0);
         const int* dl = w->d_list + b0;
-        MMG_LAUNCH(k_gather_features, m, 256, 0, w->stream, dl, (const int2*)w->d_origins, (const FeaturePlacement*)w->d_features,
-                   (const CaveFeaturePlacement*)w->d_caveFeatures, (const int*)w->d_counts, nx, w->d_gF, w->d_gCF, w->d_info);
+        MMG_TIMED(K_GATHER, w->stream, 1, MMG_LAUNCH(k_gather_features, m, 256, 0, w->stream, dl, (const int2*)w->d_origins,
+                                                     (const FeaturePlacement*)w->d_features, (const CaveFeaturePlacement*)w->d_caveFeatures,
+                                                     (const int*)w->d_counts, nx, w->d_gF, w->d_gCF, w->d_info));
         if (launchFill(m, dl, (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights, (const float*)w->d_eroded,
                        (const CaveLayer*)w->d_caves, (const FeaturePlacement*)w->d_gF, (const CaveFeaturePlacement*)w->d_gCF,
-                       w->d_info, w->d_prepF, w->d_prepC, MAX_FEATURES, MAX_CAVE_FEATURES, w->d_blocks, w->d_lushQueue, w->d_lushCount,
-                       w->stream))
+                       w->d_info, w->d_prepF, w->d_prepC, MAX_FEATURES, MAX_CAVE_FEATURES, w->d_blocks, w->d_rockQueue, w->d_lushQueue,
+                       w->d_lushCount, w->stream))
             return 1;
         if (hostBlocks)
         {
@@ -910,5 +979,62 @@ int mmgen_world_download(MmgenWorld* w, float* heightfield, float* biomeWeights,
     }
     if (caveLayers && w->d_caves) MMG_CUDA(cudaMemcpy(caveLayers, w->d_caves, (size_t)w->n * 256 * MAX_CAVE_LAYERS * sizeof(CaveLayer), cudaMemcpyDeviceToHost));
     if (blocks && w->d_blocks) MMG_CUDA(cudaMemcpy(blocks, w->d_blocks, (size_t)w->n * 98304, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ------------------------------------------------------------------ measurement helpers
+int mmgen_kernel_timing(int enable)
+{
+    if (requireReady()) return 1;
+    MMG_CUDA(cudaDeviceSynchronize());
+    g_kt.on = enable != 0;
+    g_kt.used = 0;
+    return 0;
+}
+
+int mmgen_kernel_times(int cap, float* out_ms, int32_t* out_launches, int* n)
+{
+    if (requireReady()) return 1;
+    MMG_CUDA(cudaDeviceSynchronize());
+    const int k = std::min<int>(cap, K_NUM);
+    for (int i = 0; i < k; ++i) { out_ms[i] = 0.f; out_launches[i] = 0; }
+    for (size_t e = 0; e < g_kt.used; ++e)
+    {
+        float ms = 0.f;
+        MMG_CUDA(cudaEventElapsedTime(&ms, g_kt.pool[2 * e], g_kt.pool[2 * e + 1]));
+        if (g_kt.slotOf[e] < k) { out_ms[g_kt.slotOf[e]] += ms; out_launches[g_kt.slotOf[e]] += g_kt.countOf[e]; }
+    }
+    g_kt.used = 0;
+    if (n) *n = k;
+    return 0;
+}
+
+const char* mmgen_kernel_name(int slot) { return (slot >= 0 && slot < K_NUM) ? kKernelNames[slot] : ""; }
+
+int mmgen_measure_fp32_peak(float* out_tflops)
+{
+    if (requireReady()) return 1;
+    const int blocks = kNumSMs * 8, iters = 4096;
+    float* d = nullptr;
+    MMG_CUDA(cudaMalloc(&d, (size_t)blocks * 256 * sizeof(float)));
+    cudaEvent_t a, b;
+    MMG_CUDA(cudaEventCreate(&a));
+    MMG_CUDA(cudaEventCreate(&b));
+    float best = 0.f;
+    for (int rep = 0; rep < 5; ++rep)
+    {
+        MMG_CUDA(cudaEventRecord(a, g_stream));
+        MMG_LAUNCH(k_fp32_peak, blocks, 256, 0, g_stream, d, iters);
+        MMG_CUDA(cudaEventRecord(b, g_stream));
+        MMG_CUDA(cudaStreamSynchronize(g_stream));
+        float ms = 0.f;
+        MMG_CUDA(cudaEventElapsedTime(&ms, a, b));
+        const double flop = 2.0 * 8 * 16 * (double)iters * blocks * 256;
+        if (rep > 0) best = std::max(best, (float)(flop / (ms * 1e-3) / 1e12));
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    *out_tflops = best;
     return 0;
 }
