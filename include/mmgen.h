@@ -204,6 +204,9 @@ int mmgen_kernel_timing(int enable);
 /* summed device time and launch count per kernel since the last call; kernel i is named mmgen_kernel_name(i); *n = entries written */
 int mmgen_kernel_times(int cap, float* out_ms, int32_t* out_launches, int* n);
 const char* mmgen_kernel_name(int slot);
+/* tuning knob: queue slots per chunk for the rock voxels that k_fill_terrain hands to k_fill_rock (default and maximum 49 152;
+ * <= 0 restores the default). Voxels that do not fit are finished in place: results never depend on this value. */
+int mmgen_set_rock_queue_per_chunk(int slots);
 /* achieved FP32 FMA rate of this device (TFLOP/s, 8 independent FFMA chains per thread on every SM): roofline denominator */
 int mmgen_measure_fp32_peak(float* out_tflops);
 

@@ -322,6 +322,10 @@ constexpr int kLushQueueCap = 1 << 22;           // queued voxels per fill batch
 constexpr int kRockQueuePerChunk = 49152;        // rock-queue slots per chunk of a fill batch (typical need ~30 k; overflow is decided in place)
 
 // counters of one fill batch: [0] lush queue length, [1] rock queue length
+// One CTA per column, three 128-voxel segments per thread: the column data (24 weights, 21 layer heights, 32 cave
+// layers) is staged once, the simplex tables only if the column can draw a surface biome whose pre/post-process
+// uses noise, and the column's rock voxels take one atomic to reserve their queue slots (segment-major, so that
+// consecutive queue entries are consecutive voxels of a column).
 __global__ void __launch_bounds__(kFillSeg, 8) k_fill_terrain(const int* __restrict__ fillList, const int2* __restrict__ origins,
                                                               const float* __restrict__ heightfield, const float* __restrict__ biomeWeights,
                                                               const float* __restrict__ layers, const CaveLayer* __restrict__ caveLayers,
@@ -331,18 +335,13 @@ __global__ void __launch_bounds__(kFillSeg, 8) k_fill_terrain(const int* __restr
     __shared__ float shW[NUM_BIOMES];
     __shared__ float shLH[NUM_MATERIALS + 1];
     __shared__ CaveLayer shCL[MAX_CAVE_LAYERS];
-    __shared__ int shCnt[kFillSeg / 32], shBase;
-    const int seg = blockIdx.x % 3, col = blockIdx.x / 3;
+    __shared__ int shCnt[3 * (kFillSeg / 32)], shBase;
+    const int col = blockIdx.x;
     const int li = col >> 8, idx = col & 255;
     const int chunk = fillList ? fillList[li] : li;
-    const int t = threadIdx.x, y0 = seg * kFillSeg, y = y0 + t;
+    const int t = threadIdx.x;
     const float height = heightfield[(size_t)chunk * 256 + idx];
-    uint8_t* out = blocks + (size_t)chunk * 98304 + (size_t)idx * 384 + y;
-    if ((float)y0 > height && y0 > SEA_LEVEL)
-    {
-        *out = B_AIR;      // chunkFillPlaceBlock's first exit (chunk.cu:1213-1217) for the whole segment
-        return;
-    }
+    uint8_t* out = blocks + (size_t)chunk * 98304 + (size_t)idx * 384;
     if (t < NUM_BIOMES) shW[t] = biomeWeights[(size_t)chunk * (NUM_BIOMES * 256) + t * 256 + idx];
     else if (t < NUM_BIOMES + NUM_MATERIALS) shLH[t - NUM_BIOMES] = layers[(size_t)chunk * (NUM_MATERIALS * 256) + (t - NUM_BIOMES) * 256 + idx];
     else if (t == NUM_BIOMES + NUM_MATERIALS) shLH[NUM_MATERIALS] = height;
@@ -350,37 +349,70 @@ __global__ void __launch_bounds__(kFillSeg, 8) k_fill_terrain(const int* __restr
         shCL[t - (NUM_BIOMES + NUM_MATERIALS + 1)] = caveLayers[((size_t)chunk * 256 + idx) * MAX_CAVE_LAYERS + (t - (NUM_BIOMES + NUM_MATERIALS + 1))];
     const int2 o = origins[chunk];
     const int wx = o.x + (idx & 15), wz = o.y + (idx >> 4);
-    noise_tab_stage();      // includes the barrier that publishes the column data
-    bool rock = false;
-    int bd = -384, td = -384;
-    uint8_t block = fill_place_block(shW, shLH, shCL, y, height, wx, wz, &rock, &bd, &td);
-    // CTA-aggregated append of the rock voxels (one atomic per CTA: the queue takes ~30 k voxels per chunk)
+    __syncthreads();
+    // biomePre/PostProcess evaluate simplex noise for these biomes only (biomeFuncs.hpp:385-590); random_biome can only
+    // return a biome of weight 0 when it is CORAL_REEF (rand == 0) or the PLAINS fallback, neither of which uses noise
+    const bool needNoise = shW[ARCHIPELAGO] > 0.f || shW[MESA] > 0.f || shW[SHREKS_SWAMP] > 0.f || shW[TIANZI_MOUNTAINS] > 0.f ||
+                           shW[MOUNTAINS] > 0.f || shW[CRYSTALS] > 0.f;
+    if (needNoise) noise_tab_stage();
     const int lane = t & 31, warp = t >> 5;
-    const unsigned m = __ballot_sync(0xffffffffu, rock);
-    if (lane == 0) shCnt[warp] = __popc(m);
+    uint8_t blk[3];
+    uint2 rec[3];
+    unsigned ballots[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+        const int y0 = k * kFillSeg, y = y0 + t;
+        bool rock = false;
+        int bd = -384, td = -384;
+        // chunkFillPlaceBlock's first exit (chunk.cu:1213-1217) for a whole segment above the terrain and the sea
+        blk[k] = ((float)y0 > height && y0 > SEA_LEVEL) ? (uint8_t)B_AIR : fill_place_block(shW, shLH, shCL, y, height, wx, wz, &rock, &bd, &td);
+        rec[k] = rock ? pack_rock(chunk, idx * 384 + y, blk[k], bd, td) : make_uint2(0xffffffffu, 0u);
+        ballots[k] = __ballot_sync(0xffffffffu, rock);
+        if (lane == 0) shCnt[k * (kFillSeg / 32) + warp] = __popc(ballots[k]);
+    }
     __syncthreads();
     if (t == 0)
     {
         int total = 0;
 #pragma unroll
-        for (int w = 0; w < kFillSeg / 32; ++w) total += shCnt[w];
+        for (int w = 0; w < 3 * (kFillSeg / 32); ++w) total += shCnt[w];
         shBase = total ? atomicAdd(&counters[1], total) : 0;
     }
     __syncthreads();
-    if (rock)
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
     {
-        int slot = shBase + __popc(m & ((1u << lane) - 1u));
-        for (int w = 0; w < warp; ++w) slot += shCnt[w];
-        if (slot < rockQueueCap) rockQueue[slot] = pack_rock(chunk, idx * 384 + y, block, bd, td);
-        else
+        if (rec[k].x != 0xffffffffu)
         {
-            // queue full: finish the voxel here (same result, just on a sparse warp)
-            bool lush = false;
-            block = finish_rock_block(block, wx, y, wz, height, bd, td, &lush);
-            if (lush) block = lush_block(wx, y, wz);
+            int slot = shBase + __popc(ballots[k] & ((1u << lane) - 1u));
+            for (int w = 0; w < k * (kFillSeg / 32) + warp; ++w) slot += shCnt[w];
+            if (slot < rockQueueCap) rockQueue[slot] = rec[k];
+            else blk[k] = 0xff;      // queue full (no block id is 0xff): resolved below, once the whole CTA has staged the tables
         }
     }
-    *out = block;
+    // overflow path (rare: needs > 49 152 rock voxels per chunk on average over the batch): same result, on sparse warps
+    bool anyOverflow = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) anyOverflow = anyOverflow || blk[k] == 0xff;
+    if (__syncthreads_or(anyOverflow ? 1 : 0))
+    {
+        if (!needNoise) noise_tab_stage();
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (blk[k] == 0xff)
+            {
+                uint8_t rb; int c2, v2, bd, td;
+                unpack_rock(rec[k], &c2, &v2, &rb, &bd, &td);
+                const int y = k * kFillSeg + t;
+                bool lush = false;
+                // the depths were clamped by pack_rock exactly as the dense kernel sees them
+                blk[k] = finish_rock_block(rb, wx, y, wz, height, bd, td, &lush);
+                if (lush) blk[k] = lush_block(wx, y, wz);
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out[k * kFillSeg + t] = blk[k];
     (void)lushQueue;
 }
 

@@ -348,6 +348,7 @@ extern "C" int mmgen_caves(int n, const int32_t* origins, const float* heightfie
 }
 
 constexpr int kFillBatch = 512;
+static int g_rockQueuePerChunk = kRockQueuePerChunk;   // mmgen_set_rock_queue_per_chunk (tuning / test knob, <= kRockQueuePerChunk)
 
 // the kernel sequence of Chunk::fill for one batch of m chunks (lists indexed by batch position)
 static int launchFill(int m, const int* d_list, const int2* d_origins, const float* d_height, const float* d_weights, const float* d_layers,
@@ -355,9 +356,9 @@ static int launchFill(int m, const int* d_list, const int2* d_origins, const flo
                       Prep* d_prepF, Prep* d_prepC, int strideF, int strideCF, uint8_t* d_blocks, uint2* d_rockQueue, uint2* d_lushQueue,
                       int* d_counters, cudaStream_t stream)
 {
-    const int rockCap = (int)std::min<size_t>((size_t)m * kRockQueuePerChunk, (size_t)kFillBatch * kRockQueuePerChunk);
+    const int rockCap = (int)std::min<size_t>((size_t)m * g_rockQueuePerChunk, (size_t)kFillBatch * kRockQueuePerChunk);
     MMG_CUDA(cudaMemsetAsync(d_counters, 0, 2 * sizeof(int), stream));
-    MMG_TIMED(K_FILL_TERRAIN, stream, 1, MMG_LAUNCH(k_fill_terrain, m * 256 * 3, kFillSeg, kNoiseSmemBytes, stream, d_list, d_origins, d_height,
+    MMG_TIMED(K_FILL_TERRAIN, stream, 1, MMG_LAUNCH(k_fill_terrain, m * 256, kFillSeg, kNoiseSmemBytes, stream, d_list, d_origins, d_height,
                                                     d_weights, d_layers, d_caves, d_blocks, d_rockQueue, rockCap, d_lushQueue, d_counters));
     MMG_TIMED(K_FILL_ROCK, stream, 1, MMG_LAUNCH(k_fill_rock, kNumSMs * 8, 128, kNoiseSmemBytes, stream, d_origins, d_height,
                                                  (const uint2*)d_rockQueue, rockCap, d_blocks, d_lushQueue, d_counters));
@@ -1036,5 +1037,11 @@ int mmgen_measure_fp32_peak(float* out_tflops)
     cudaEventDestroy(b);
     cudaFree(d);
     *out_tflops = best;
+    return 0;
+}
+
+int mmgen_set_rock_queue_per_chunk(int slots)
+{
+    g_rockQueuePerChunk = (slots <= 0 || slots > kRockQueuePerChunk) ? kRockQueuePerChunk : slots;
     return 0;
 }

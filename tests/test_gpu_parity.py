@@ -308,3 +308,16 @@ def test_c4_cave_and_fill_stress_32x32(gen, mm, oracle):
     ob = oracle.fill(origins[sample], hb, wb, d["layers"][sample], cb, gf, gcf)
     assert np.array_equal(bb, ob)
     world.close()
+
+
+def test_rock_queue_overflow_is_result_neutral(gen, mm, golden):
+    """k_fill_terrain queues rock voxels for the dense kernel k_fill_rock; voxels that do not fit in the queue are
+    finished in place. With a queue far too small the blocks must still equal the reference's."""
+    try:
+        gen.L.mmgen_set_rock_queue_per_chunk(1500)
+        world = gen.region_world(3, 3, 6, 6)
+        world.generate(mm.STAGE_ALL)
+        assert np.array_equal(world.download_region_blocks(), golden["g"]["blocks"])
+        world.close()
+    finally:
+        gen.L.mmgen_set_rock_queue_per_chunk(0)
