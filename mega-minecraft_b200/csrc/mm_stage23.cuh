@@ -132,11 +132,22 @@ __global__ void k_zone_gather(const float* __restrict__ layers, const float* __r
 // pIn (+ accumulated heights on the layer's first sweep), writes pOut. Plane roles are indices into the
 // zone's 12 planes; they swap in lockstep for all zones. A zone that has converged is a fixed point of
 // the sweep, so sweeping it again (while other zones of the batch still move) changes nothing.
+//
+// zoneChanged[3][kMaxZoneBatch]: did sweep n change anything in zone z? Sweep n reads row (n-1)%3, sets row n%3 and clears
+// row (n+1)%3. If the previous sweep left a zone untouched, its output planes already equal its input planes (outS = sIn,
+// accumOut = accumIn for every cell), the zone is at a fixed point, and this sweep would write back what pOut already holds:
+// the CTA returns at once. `force` disables the shortcut for the first two sweeps of a layer (the first sweep folds the
+// carried heights into its comparison, so "nothing flagged" does not imply "planes equal" there).
+constexpr int kMaxZoneBatch = 32;
 __global__ void __launch_bounds__(1024) k_erode_sweep(float* __restrict__ zones, int pIn, int pOut, int pUp, int pAccIn, int pAccOut,
-                                                      float rep, int isFirst, int* __restrict__ changedFlag)
+                                                      float rep, int isFirst, int* __restrict__ changedFlag, int* __restrict__ zoneChanged,
+                                                      int sweepNo, int force)
 {
     __shared__ float shS[34 * 34];
     __shared__ float shE[34 * 34];
+    const int rowPrev = ((sweepNo + 2) % 3) * kMaxZoneBatch, rowCur = (sweepNo % 3) * kMaxZoneBatch, rowNext = ((sweepNo + 1) % 3) * kMaxZoneBatch;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) zoneChanged[rowNext + blockIdx.z] = 0;
+    if (!force && zoneChanged[rowPrev + blockIdx.z] == 0) return;
     float* zone = zones + (size_t)blockIdx.z * kZonePlanes * kErosionCols;
     const float* sIn = zone + (size_t)pIn * kErosionCols;
     float* sOut = zone + (size_t)pOut * kErosionCols;
@@ -179,6 +190,7 @@ __global__ void __launch_bounds__(1024) k_erode_sweep(float* __restrict__ zones,
         {
             acc = (ns - s0) + acc;
             *changedFlag = 1;
+            zoneChanged[rowCur + blockIdx.z] = 1;
         }
     }
     sOut[i] = outS;

@@ -228,7 +228,7 @@ int mmgen_heightfields(int n, const int32_t* origins, float* out_heightfield, fl
 static const float kTanRepose[NUM_ERODED] = {1.42814791f, 0.839099586f, 1.0f, 0.839099586f,
                                              0.577350318f, 0.700207531f, 2.14450693f, 1.0f};
 constexpr int kSweepGroup = 8;     // sweeps between two convergence polls
-constexpr int kZoneBatch = 32;     // zones per launch: 32 x 4 live planes x 590 KB = 75 MB, L2-resident
+constexpr int kZoneBatch = kMaxZoneBatch;     // zones per launch: 32 x 4 live planes x 590 KB = 75 MB, L2-resident
 
 static int erodeZonesDevice(float* d_zones, int nZones, int* d_flags, cudaStream_t stream, int* sweepsOut)
 {
@@ -236,9 +236,12 @@ static int erodeZonesDevice(float* d_zones, int nZones, int* d_flags, cudaStream
     int accIn = 10, accOut = 11;     // plane 10 was zeroed by the gather (or by the caller)
     int sweeps = 0;
     int h_flags[kSweepGroup];
+    int* d_zoneChanged = d_flags + kSweepGroup;      // [3][kMaxZoneBatch], see k_erode_sweep
+    MMG_CUDA(cudaMemsetAsync(d_zoneChanged, 0, 3 * kMaxZoneBatch * sizeof(int), stream));
     for (int layer = NUM_ERODED - 1; layer >= 0; --layer)
     {
         int pIn = layer, pOut = 9;
+        int layerSweeps = 0;
         bool first = true, converged = false;
         while (!converged)
         {
@@ -247,7 +250,8 @@ static int erodeZonesDevice(float* d_zones, int nZones, int* d_flags, cudaStream
             for (int b = 0; b < kSweepGroup; ++b)
             {
                 MMG_LAUNCH(k_erode_sweep, dim3(12, 12, nZones), dim3(32, 32), 0, stream, d_zones, pIn, pOut, layer + 1, accIn, accOut,
-                           kTanRepose[layer], first ? 1 : 0, d_flags + b);
+                           kTanRepose[layer], first ? 1 : 0, d_flags + b, d_zoneChanged, sweeps, layerSweeps < 2 ? 1 : 0);
+                ++layerSweeps;
                 std::swap(pIn, pOut);
                 std::swap(accIn, accOut);
                 first = false;
@@ -289,7 +293,7 @@ extern "C" int mmgen_erode_zone(const float* gathered, float* out_eroded, int* o
     if (requireReady()) return 1;
     const size_t P = kErosionCols;
     if (g_scratch[4].ensure(kZonePlanes * P * sizeof(float))) return 1;
-    if (g_scratch[5].ensure(kSweepGroup * sizeof(int))) return 1;
+    if (g_scratch[5].ensure((kSweepGroup + 3 * kMaxZoneBatch) * sizeof(int))) return 1;
     float* d_zone = (float*)g_scratch[4].ptr;
     MMG_CUDA(cudaMemcpyAsync(d_zone, gathered, 9 * P * sizeof(float), cudaMemcpyHostToDevice, g_stream));
     MMG_CUDA(cudaMemsetAsync(d_zone + 10 * P, 0, P * sizeof(float), g_stream));
@@ -568,7 +572,7 @@ static int worldErode(MmgenWorld* w, const std::vector<int2>& corners)
     const int nx = w->nx;
     if (!w->d_zone) MMG_CUDA(cudaMalloc(&w->d_zone, (size_t)kZoneBatch * kZonePlanes * kErosionCols * sizeof(float)));
     if (!w->d_zoneCorners) MMG_CUDA(cudaMalloc(&w->d_zoneCorners, (size_t)kZoneBatch * sizeof(int2)));
-    if (!w->d_flags) MMG_CUDA(cudaMalloc(&w->d_flags, kSweepGroup * sizeof(int)));
+    if (!w->d_flags) MMG_CUDA(cudaMalloc(&w->d_flags, (kSweepGroup + 3 * kMaxZoneBatch) * sizeof(int)));
     if (!w->d_eroded) MMG_CUDA(cudaMalloc(&w->d_eroded, (size_t)w->n * NUM_MATERIALS * 256 * sizeof(float)));
     for (size_t z0 = 0; z0 < corners.size(); z0 += kZoneBatch)
     {
