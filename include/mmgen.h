@@ -198,6 +198,19 @@ int mmgen_stream_take_filled(MmgenStream* s, int32_t* coords, int cap, int* n);
 /* block volume of one filled chunk into host memory (98 304 bytes) */
 int mmgen_stream_download_chunk(MmgenStream* s, int cx, int cz, uint8_t* out_blocks);
 
+/* ---- meshing: Chunk::createVBOs (chunk.cu:1781-2003; a host loop in the reference that re-uploads the blocks' mesh after
+ * Chunk::fill downloaded them) on the device, straight from the resident block volumes. Vertex = rendering/structs.hpp:25-31. */
+typedef struct { float pos[3], nor[3], uv[2]; uint64_t m; } MmgenVertex;   /* 40 B; m = Mats (structs.hpp:7-14) */
+/* meshes n filled chunks given as (cx, cz) pairs, in the reference's vertex / index order, into a device arena owned by
+ * the world (valid until the next call); faces towards a neighbour chunk that is not filled are skipped exactly as the
+ * reference skips a null neighbour (chunk.cu:1908-1911). out_counts[n][2] = {vertices, indices} per chunk (may be NULL). */
+int mmgen_world_mesh(MmgenWorld* w, int n, const int32_t* chunkCoords, int32_t* out_counts);
+/* chunk i of the last mmgen_world_mesh call: copy to host memory, or the device addresses (zero-copy hand-off to a renderer) */
+int mmgen_world_mesh_download(MmgenWorld* w, int i, MmgenVertex* out_verts, uint32_t* out_idx);
+int mmgen_world_mesh_device_ptrs(MmgenWorld* w, int i, void** verts, void** idx, int* nVerts, int* nIdx);
+/* device time of the last mmgen_world_mesh call (both kernels + the count read-back), ms */
+int mmgen_world_mesh_ms(MmgenWorld* w, float* out);
+
 /* ---- measurement helpers (bench.py) */
 /* switch per-kernel device timing on / off (CUDA event pairs around the hot kernels' launches, on their stream); clears the record */
 int mmgen_kernel_timing(int enable);

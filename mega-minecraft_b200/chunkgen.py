@@ -366,3 +366,34 @@ class Terrain:
             if st.idle:
                 break
         return log
+
+
+Vertex = np.dtype([("pos", "<f4", (3,)), ("nor", "<f4", (3,)), ("uv", "<f4", (2,)), ("m", "<u8")])     # MmgenVertex, 40 B
+
+
+def _world_mesh(self, chunk_coords, download=True):
+    """Chunk::createVBOs on the device (mmgen_world_mesh) for filled chunks given as (cx, cz) pairs.
+    Returns [(verts, idx)] per chunk (Vertex records, uint32 indices relative to the chunk), or the counts if not download."""
+    coords = np.ascontiguousarray(chunk_coords, np.int32).reshape(-1, 2)
+    n = coords.shape[0]
+    counts = np.zeros((n, 2), np.int32)
+    self.gen._check(self.L.mmgen_world_mesh(self.h, n, _ptr(coords), _ptr(counts)))
+    if not download:
+        return counts
+    out = []
+    for i in range(n):
+        v = np.zeros(int(counts[i, 0]), Vertex)
+        ix = np.zeros(int(counts[i, 1]), np.uint32)
+        self.gen._check(self.L.mmgen_world_mesh_download(self.h, i, _ptr(v), _ptr(ix)))
+        out.append((v, ix))
+    return out
+
+
+def _world_mesh_ms(self):
+    v = ctypes.c_float(0)
+    self.gen._check(self.L.mmgen_world_mesh_ms(self.h, ctypes.byref(v)))
+    return v.value
+
+
+World.mesh = _world_mesh
+World.mesh_ms = _world_mesh_ms

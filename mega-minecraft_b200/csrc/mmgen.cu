@@ -15,6 +15,7 @@
 #include "mm_stage23.cuh"
 #include "mm_stage4.cuh"
 #include "mm_stage56.cuh"
+#include "mm_mesh.cuh"
 
 namespace mmg {
 
@@ -141,6 +142,17 @@ struct MmgenWorld
     int* d_lushCount = nullptr;                      // [0] lush queue length, [1] rock queue length
     uint2* d_rockQueue = nullptr;                    // rock voxels of one fill batch waiting for getCaveBiome (k_fill_rock)
     uint8_t* d_blocks = nullptr;                     // [chunk][16][16][384]
+    // meshing (mmgen_world_mesh): arena of the last call
+    MeshChunk* d_meshList = nullptr;
+    int* d_meshColOff = nullptr;
+    int* d_meshTotals = nullptr;
+    long long* d_meshBase = nullptr;
+    MeshVertex* d_meshVerts = nullptr;
+    uint32_t* d_meshIdx = nullptr;
+    size_t meshListCap = 0, meshVertCap = 0;
+    std::vector<long long> h_meshBase;
+    std::vector<int> h_meshTotals;
+    float meshMs = 0.f;
     int erosionSweeps = 0;
     std::vector<uint8_t> stage;
     cudaStream_t stream = nullptr;
@@ -508,6 +520,12 @@ int mmgen_world_destroy(MmgenWorld* w)
     cudaFree(w->d_lushCount);
     cudaFree(w->d_rockQueue);
     cudaFree(w->d_blocks);
+    cudaFree(w->d_meshList);
+    cudaFree(w->d_meshColOff);
+    cudaFree(w->d_meshTotals);
+    cudaFree(w->d_meshBase);
+    cudaFree(w->d_meshVerts);
+    cudaFree(w->d_meshIdx);
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     for (auto& e : w->evBatch) if (e) cudaEventDestroy(e);
     if (w->stream) cudaStreamDestroy(w->stream);
@@ -1049,3 +1067,89 @@ int mmgen_set_rock_queue_per_chunk(int slots)
     g_rockQueuePerChunk = (slots <= 0 || slots > kRockQueuePerChunk) ? kRockQueuePerChunk : slots;
     return 0;
 }
+
+// ------------------------------------------------------------------ meshing (Chunk::createVBOs, chunk.cu:1781-2003)
+int mmgen_world_mesh(MmgenWorld* w, int n, const int32_t* chunkCoords, int32_t* out_counts)
+{
+    if (requireReady()) return 1;
+    if (n <= 0) return 0;
+    if (!w->d_blocks) { g_lastError = "mmgen_world_mesh: nothing filled yet"; return 1; }
+    std::vector<MeshChunk> list(n);
+    for (int i = 0; i < n; ++i)
+    {
+        const int x = chunkCoords[2 * i] - w->cx0, z = chunkCoords[2 * i + 1] - w->cz0;
+        if (x < 0 || z < 0 || x >= w->nx || z >= w->nz || w->stage[z * w->nx + x] != 6)
+        {
+            g_lastError = "mmgen_world_mesh: chunk is not filled";
+            return 1;
+        }
+        auto filled = [&](int ax, int az) { return (ax >= 0 && az >= 0 && ax < w->nx && az < w->nz && w->stage[az * w->nx + ax] == 6) ? az * w->nx + ax : -1; };
+        list[i].chunk = z * w->nx + x;
+        list[i].nb[0] = filled(x, z + 1); list[i].nb[1] = filled(x + 1, z); list[i].nb[2] = filled(x, z - 1); list[i].nb[3] = filled(x - 1, z);
+        list[i].origin = w->h_origins[z * w->nx + x];
+    }
+    if ((size_t)n > w->meshListCap)
+    {
+        cudaFree(w->d_meshList); cudaFree(w->d_meshColOff); cudaFree(w->d_meshTotals); cudaFree(w->d_meshBase);
+        w->d_meshList = nullptr; w->d_meshColOff = nullptr; w->d_meshTotals = nullptr; w->d_meshBase = nullptr; w->meshListCap = 0;
+        MMG_CUDA(cudaMalloc(&w->d_meshList, (size_t)n * sizeof(MeshChunk)));
+        MMG_CUDA(cudaMalloc(&w->d_meshColOff, (size_t)n * 256 * sizeof(int)));
+        MMG_CUDA(cudaMalloc(&w->d_meshTotals, (size_t)n * sizeof(int)));
+        MMG_CUDA(cudaMalloc(&w->d_meshBase, (size_t)n * sizeof(long long)));
+        w->meshListCap = (size_t)n;
+    }
+    cudaEvent_t e0 = w->ev[12], e1 = w->ev[13];
+    MMG_CUDA(cudaEventRecord(e0, w->stream));
+    MMG_CUDA(cudaMemcpyAsync(w->d_meshList, list.data(), (size_t)n * sizeof(MeshChunk), cudaMemcpyHostToDevice, w->stream));
+    MMG_LAUNCH(k_mesh_count, n, 256, 0, w->stream, (const MeshChunk*)w->d_meshList, (const uint8_t*)w->d_blocks, w->d_meshColOff, w->d_meshTotals);
+    w->h_meshTotals.resize(n);
+    MMG_CUDA(cudaMemcpyAsync(w->h_meshTotals.data(), w->d_meshTotals, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, w->stream));
+    MMG_CUDA(cudaStreamSynchronize(w->stream));
+    w->h_meshBase.assign(n + 1, 0);
+    for (int i = 0; i < n; ++i) w->h_meshBase[i + 1] = w->h_meshBase[i] + w->h_meshTotals[i];
+    const size_t need = (size_t)w->h_meshBase[n];
+    if (need > w->meshVertCap)
+    {
+        cudaFree(w->d_meshVerts); cudaFree(w->d_meshIdx);
+        w->d_meshVerts = nullptr; w->d_meshIdx = nullptr; w->meshVertCap = 0;
+        const size_t cap = need + need / 4 + 1024;
+        MMG_CUDA(cudaMalloc(&w->d_meshVerts, cap * sizeof(MeshVertex)));
+        MMG_CUDA(cudaMalloc(&w->d_meshIdx, (cap / 4 + 1) * 6 * sizeof(uint32_t)));
+        w->meshVertCap = cap;
+    }
+    MMG_CUDA(cudaMemcpyAsync(w->d_meshBase, w->h_meshBase.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, w->stream));
+    MMG_LAUNCH(k_mesh_emit, n, 256, 0, w->stream, (const MeshChunk*)w->d_meshList, (const uint8_t*)w->d_blocks, (const int*)w->d_meshColOff,
+               (const long long*)w->d_meshBase, w->d_meshVerts, w->d_meshIdx);
+    MMG_CUDA(cudaEventRecord(e1, w->stream));
+    MMG_CUDA(cudaStreamSynchronize(w->stream));
+    MMG_CUDA(cudaEventElapsedTime(&w->meshMs, e0, e1));
+    if (out_counts)
+        for (int i = 0; i < n; ++i)
+        {
+            out_counts[2 * i] = w->h_meshTotals[i];
+            out_counts[2 * i + 1] = w->h_meshTotals[i] / 4 * 6;
+        }
+    return 0;
+}
+
+int mmgen_world_mesh_download(MmgenWorld* w, int i, MmgenVertex* out_verts, uint32_t* out_idx)
+{
+    if (i < 0 || i >= (int)w->h_meshTotals.size()) { g_lastError = "mmgen_world_mesh_download: no such chunk in the last mmgen_world_mesh call"; return 1; }
+    const long long base = w->h_meshBase[i];
+    const int nv = w->h_meshTotals[i];
+    if (nv && out_verts) MMG_CUDA(cudaMemcpy(out_verts, w->d_meshVerts + base, (size_t)nv * sizeof(MeshVertex), cudaMemcpyDeviceToHost));
+    if (nv && out_idx) MMG_CUDA(cudaMemcpy(out_idx, w->d_meshIdx + base / 4 * 6, (size_t)nv / 4 * 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int mmgen_world_mesh_device_ptrs(MmgenWorld* w, int i, void** verts, void** idx, int* nVerts, int* nIdx)
+{
+    if (i < 0 || i >= (int)w->h_meshTotals.size()) { g_lastError = "mmgen_world_mesh_device_ptrs: no such chunk in the last mmgen_world_mesh call"; return 1; }
+    if (verts) *verts = w->d_meshVerts + w->h_meshBase[i];
+    if (idx) *idx = w->d_meshIdx + w->h_meshBase[i] / 4 * 6;
+    if (nVerts) *nVerts = w->h_meshTotals[i];
+    if (nIdx) *nIdx = w->h_meshTotals[i] / 4 * 6;
+    return 0;
+}
+
+int mmgen_world_mesh_ms(MmgenWorld* w, float* out) { *out = w->meshMs; return 0; }

@@ -99,3 +99,32 @@ class RefCuda:
                 gc.append(cf)
             out["block_idx"], out["blocks"], out["gathered_features"], out["gathered_cave_features"] = idx, b, gf, gc
         return out
+
+
+VERTEX = np.dtype([("pos", "<f4", (3,)), ("nor", "<f4", (3,)), ("uv", "<f4", (2,)), ("m", "<u8")])     # rendering/structs.hpp:25-31
+_mesh_lib = None
+
+
+def mesh_chunk(cx, cz, centre, neighbours):
+    """The reference's own Chunk::createVBOs (chunk.cu:1781-2003) on given block volumes; needs no GPU.
+    centre: uint8[16][16][384]; neighbours: 4 volumes or None in Chunk::neighbors order (+z, +x, -z, -x).
+    Returns (verts as VERTEX records, idx uint32)."""
+    global _mesh_lib
+    if _mesh_lib is None:
+        _mesh_lib = ctypes.CDLL(LIB)
+        assert _mesh_lib.mmref_vertex_size() == VERTEX.itemsize
+    blocks5 = np.zeros((5, 98304), np.uint8)
+    blocks5[0] = np.ascontiguousarray(centre, np.uint8).ravel()
+    present = np.zeros(4, np.int32)
+    for i, nb in enumerate(neighbours):
+        if nb is not None:
+            blocks5[i + 1] = np.ascontiguousarray(nb, np.uint8).ravel()
+            present[i] = 1
+    cap = 1 << 20
+    verts = np.zeros(cap, VERTEX)
+    idx = np.zeros(cap * 3 // 2, np.uint32)
+    nidx = ctypes.c_int(0)
+    nv = _mesh_lib.mmref_mesh_chunk(int(cx), int(cz), _ptr(blocks5), _ptr(present), _ptr(verts), cap, _ptr(idx), len(idx), ctypes.byref(nidx))
+    if nv < 0:
+        raise RuntimeError("mesh larger than the oracle's buffers")
+    return verts[:nv].copy(), idx[:nidx.value].copy()

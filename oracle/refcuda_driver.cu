@@ -289,3 +289,33 @@ int mmref_sizeof_feature() { return (int)sizeof(FeaturePlacement); }
 int mmref_sizeof_cave_feature() { return (int)sizeof(CaveFeaturePlacement); }
 
 }  // extern "C"
+
+// ---- meshing oracle: the reference's own Chunk::createVBOs (chunk.cu:1781-2003, a host function) on block volumes
+// supplied by the caller. No CUDA device is needed for this entry point (it runs in the CPU tests as well).
+// blocks5: centre chunk, then the neighbours in the reference's neighbors[] order: +z, +x, -z, -x (chunk.hpp:57,
+// enums.hpp:41-48), 98304 bytes each; present[i] == 0 leaves neighbors[i] null. Returns the vertex count, or -1 if the
+// caps are too small; *nIdxOut = index count. vertsOut receives the reference's Vertex records verbatim (40 bytes each).
+namespace BlockUtils { void init(); }
+extern "C" int mmref_vertex_size() { return (int)sizeof(Vertex); }
+extern "C" int mmref_mesh_chunk(int cx, int cz, const unsigned char* blocks5, const int* present, unsigned char* vertsOut, int vertCap,
+                                unsigned int* idxOut, int idxCap, int* nIdxOut)
+{
+    static bool inited = false;
+    if (!inited) { BlockUtils::init(); inited = true; }
+    std::unique_ptr<Chunk> c[5];
+    const ivec2 off[5] = {ivec2(0, 0), ivec2(0, 1), ivec2(1, 0), ivec2(0, -1), ivec2(-1, 0)};
+    for (int i = 0; i < 5; ++i)
+    {
+        if (i > 0 && !present[i - 1]) continue;
+        c[i] = std::make_unique<Chunk>(ivec2(cx, cz) + off[i]);
+        std::memcpy(c[i]->blocks.data(), blocks5 + (size_t)i * 98304, 98304);
+    }
+    for (int i = 0; i < 4; ++i) c[0]->neighbors[i] = c[i + 1].get();
+    c[0]->createVBOs();
+    const int nv = (int)c[0]->verts.size(), ni = (int)c[0]->idx.size();
+    *nIdxOut = ni;
+    if (nv > vertCap || ni > idxCap) return -1;
+    std::memcpy(vertsOut, c[0]->verts.data(), (size_t)nv * sizeof(Vertex));
+    std::memcpy(idxOut, c[0]->idx.data(), (size_t)ni * sizeof(unsigned int));
+    return nv;
+}
