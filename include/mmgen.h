@@ -171,6 +171,7 @@ typedef struct {
     int32_t actionTimeLeft;   /* budget left after the tick */
     int32_t idle;             /* 1 when no queue holds work and no state changed: further ticks do nothing until the player moves */
     float deviceMs;           /* device time of the tick's launches (CUDA events) */
+    int64_t meshVertices;     /* vertices produced by the tick's createVBOs pass (mmgen_stream_set_meshing) */
 } MmgenTickStats;
 /* reference ChunkState values reported by mmgen_stream_states (chunk.hpp:18-32) */
 enum {
@@ -191,6 +192,10 @@ int mmgen_stream_set_costs(MmgenStream* s, const int32_t* costs9, int maxActionT
 int mmgen_stream_set_player(MmgenStream* s, float playerX, float playerZ);
 /* Terrain::tick(deltaTime); returns when the tick's results are complete on the device */
 int mmgen_stream_tick(MmgenStream* s, float deltaTime, MmgenTickStats* out);
+/* run Chunk::createVBOs on the device (mmgen_world_mesh) for the chunks that leave the VBO queue; off by default */
+int mmgen_stream_set_meshing(MmgenStream* s, int enable);
+/* (cx, cz) pairs of the chunks whose meshes are in the backing world's arena (chunk i for mmgen_world_mesh_device_ptrs / _download) */
+int mmgen_stream_last_meshed(MmgenStream* s, int32_t* coords, int cap, int* n);
 /* ChunkState of every window chunk, raster order */
 int mmgen_stream_states(MmgenStream* s, uint8_t* out);
 /* chunk coordinates (cx, cz) of the chunks filled since the last call, in fill order; *n = pairs written (<= cap) */

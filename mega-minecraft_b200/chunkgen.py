@@ -282,7 +282,8 @@ class World:
 class TickStats(ctypes.Structure):
     """MmgenTickStats (include/mmgen.h)."""
     _fields_ = [(k, ctypes.c_int32) for k in ("heightfields", "gatherHeightfields", "layers", "zonesEroded", "caves", "placements",
-                                               "gatherPlacements", "filled", "vbos", "actionTimeLeft", "idle")] + [("deviceMs", ctypes.c_float)]
+                                               "gatherPlacements", "filled", "vbos", "actionTimeLeft", "idle")] + \
+               [("deviceMs", ctypes.c_float), ("meshVertices", ctypes.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -321,6 +322,10 @@ class Terrain:
     def set_costs(self, costs=REFERENCE_COSTS, max_per_frame=500, per_second=60 * 500):
         c = (ctypes.c_int32 * 9)(*costs) if costs is not None else None
         self.gen._check(self.L.mmgen_stream_set_costs(self.h, c, int(max_per_frame), int(per_second)))
+
+    def set_meshing(self, enable=True):
+        """createVBOs on the device for the chunks that leave the VBO queue."""
+        self.gen._check(self.L.mmgen_stream_set_meshing(self.h, 1 if enable else 0))
 
     def setCurrentChunkPos(self, cx, cz):
         self.set_player(cx * 16.0 + 8.0, cz * 16.0 + 8.0)

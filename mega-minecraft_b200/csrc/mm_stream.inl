@@ -53,6 +53,8 @@ struct MmgenStream
     std::deque<int> newlyFilled;                                 // window indices, for mmgen_stream_take_filled
     cudaEvent_t ev[2] = {};
     uint64_t ticks = 0;
+    bool meshing = false;
+    std::vector<int32_t> lastMeshed;                              // (cx, cz) pairs of the chunks meshed by the last tick that meshed
 
     int idx(int cx, int cz) const { return (cz - w->cz0) * w->nx + (cx - w->cx0); }
     bool inWindow(int cx, int cz) const { return cx >= w->cx0 && cx < w->cx0 + w->nx && cz >= w->cz0 && cz < w->cz0 + w->nz; }
@@ -260,16 +262,31 @@ int mmgen_stream_tick(MmgenStream* s, float deltaTime, MmgenTickStats* out)
     }
     s->actionTimeLeft = (int)std::min<long long>((long long)s->actionTimeLeft + (long long)((double)s->totalActionTimePerSecond * deltaTime),
                                                  s->maxActionTimePerFrame);
-    MMG_CUDA(cudaEventRecord(s->ev[0], w->stream));
     const int nx = w->nx;
-    // createVBOs / buildChunkAccel (terrain.cpp:638-655): meshing is outside this path; the state transition is kept
-    while (!s->qVbos.empty() && s->actionTimeLeft >= s->cost[COST_VBOS])
+    MMG_CUDA(cudaEventRecord(s->ev[0], w->stream));
+    // createVBOs (terrain.cpp:638-655); buildChunkAccel (the OptiX hand-off) is outside this path
     {
-        s->needsUpdateChunks = true;
-        const int i = s->qVbos.front(); s->qVbos.pop();
-        s->state[i] = ST_DRAWABLE; s->ready[i] = 0;
-        s->actionTimeLeft -= s->cost[COST_VBOS];
-        ++st.vbos;
+        std::vector<int32_t> coords;
+        while (!s->qVbos.empty() && s->actionTimeLeft >= s->cost[COST_VBOS])
+        {
+            s->needsUpdateChunks = true;
+            const int i = s->qVbos.front(); s->qVbos.pop();
+            s->state[i] = ST_DRAWABLE; s->ready[i] = 0;
+            s->actionTimeLeft -= s->cost[COST_VBOS];
+            ++st.vbos;
+            coords.push_back(w->cx0 + i % nx);
+            coords.push_back(w->cz0 + i / nx);
+        }
+        // Chunk::createVBOs for the tick's chunks in one pass over the resident blocks (mm_mesh.cuh); the vertex / index
+        // arrays stay in the world's device arena until the next tick (mmgen_world_mesh_device_ptrs / _download, chunk i =
+        // i-th pair of mmgen_stream_last_meshed)
+        if (s->meshing && !coords.empty())
+        {
+            std::vector<int32_t> counts(coords.size());
+            if (mmgen_world_mesh(w, (int)coords.size() / 2, coords.data(), counts.data())) return 1;
+            for (size_t k = 0; k < counts.size(); k += 2) st.meshVertices += counts[k];
+            s->lastMeshed = coords;
+        }
     }
     {
         std::vector<int> list;
@@ -423,5 +440,17 @@ int mmgen_stream_download_chunk(MmgenStream* s, int cx, int cz, uint8_t* out_blo
     }
     MMG_CUDA(cudaMemcpyAsync(out_blocks, s->w->d_blocks + (size_t)s->idx(cx, cz) * 98304, 98304, cudaMemcpyDeviceToHost, s->w->stream));
     MMG_CUDA(cudaStreamSynchronize(s->w->stream));
+    return 0;
+}
+
+// createVBOs on the device for the chunks that leave the VBO queue (off by default: the state transition only)
+int mmgen_stream_set_meshing(MmgenStream* s, int enable) { s->meshing = enable != 0; return 0; }
+
+// (cx, cz) pairs of the chunks in the world's mesh arena, in arena order; *n = pairs written
+int mmgen_stream_last_meshed(MmgenStream* s, int32_t* coords, int cap, int* n)
+{
+    const int k = std::min<int>(cap, (int)s->lastMeshed.size() / 2);
+    std::memcpy(coords, s->lastMeshed.data(), (size_t)k * 2 * sizeof(int32_t));
+    *n = k;
     return 0;
 }

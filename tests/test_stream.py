@@ -141,3 +141,29 @@ def test_stream_errors(gen, mm):
         t.download_chunk(3, 3)          # not filled yet
     assert t.tick(0.0).as_dict()["heightfields"] == 0     # no budget, nothing happens
     t.close()
+
+
+@pytest.mark.gpu
+def test_stream_meshes_drawable_chunks(gen, mm):
+    """With meshing on, the VBO stage runs createVBOs on the device for the chunks it makes DRAWABLE; the vertex totals
+    equal a direct mesh of the same chunks afterwards (all four neighbours are filled by then, as in the reference)."""
+    win, R = (-29, -29, 58, 58), 28
+    t = mm.Terrain(gen, *win)
+    t.set_radii(6, R)
+    t.set_meshing(True)
+    t.set_costs(mm.REFERENCE_COSTS, 4000, 60 * 4000)
+    log = t.run_until_idle(DT)
+    states = t.states()
+    drawable = np.argwhere(states == mm.chunkgen.CHUNK_DRAWABLE)
+    assert len(drawable) == sum(s["vbos"] for s in log) == 13 * 13
+    total = sum(s["meshVertices"] for s in log)
+    assert total > 0
+    # the same chunks meshed in one call on a batch world of the same region
+    lo, hi = expected_filled_range(win[0], win[2], 0, R)
+    world = gen.region_world(lo, lo, hi - lo, hi - lo)
+    world.generate(mm.STAGE_ALL)
+    coords = np.array([[win[0] + x, win[1] + z] for z, x in drawable], np.int32)
+    counts = world.mesh(coords, download=False)
+    assert int(counts[:, 0].sum()) == total
+    world.close()
+    t.close()
