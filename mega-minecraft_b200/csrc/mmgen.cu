@@ -1101,7 +1101,7 @@ int mmgen_world_mesh(MmgenWorld* w, int n, const int32_t* chunkCoords, int32_t* 
     cudaEvent_t e0 = w->ev[12], e1 = w->ev[13];
     MMG_CUDA(cudaEventRecord(e0, w->stream));
     MMG_CUDA(cudaMemcpyAsync(w->d_meshList, list.data(), (size_t)n * sizeof(MeshChunk), cudaMemcpyHostToDevice, w->stream));
-    MMG_LAUNCH(k_mesh_count, n, 256, 0, w->stream, (const MeshChunk*)w->d_meshList, (const uint8_t*)w->d_blocks, w->d_meshColOff, w->d_meshTotals);
+    MMG_LAUNCH(k_mesh_count, n, 32 * kMeshWarps, 0, w->stream, (const MeshChunk*)w->d_meshList, (const uint8_t*)w->d_blocks, w->d_meshColOff, w->d_meshTotals);
     w->h_meshTotals.resize(n);
     MMG_CUDA(cudaMemcpyAsync(w->h_meshTotals.data(), w->d_meshTotals, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, w->stream));
     MMG_CUDA(cudaStreamSynchronize(w->stream));
@@ -1118,7 +1118,7 @@ int mmgen_world_mesh(MmgenWorld* w, int n, const int32_t* chunkCoords, int32_t* 
         w->meshVertCap = cap;
     }
     MMG_CUDA(cudaMemcpyAsync(w->d_meshBase, w->h_meshBase.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, w->stream));
-    MMG_LAUNCH(k_mesh_emit, n, 256, 0, w->stream, (const MeshChunk*)w->d_meshList, (const uint8_t*)w->d_blocks, (const int*)w->d_meshColOff,
+    MMG_LAUNCH(k_mesh_emit, n, 32 * kMeshWarps, 0, w->stream, (const MeshChunk*)w->d_meshList, (const uint8_t*)w->d_blocks, (const int*)w->d_meshColOff,
                (const long long*)w->d_meshBase, w->d_meshVerts, w->d_meshIdx);
     MMG_CUDA(cudaEventRecord(e1, w->stream));
     MMG_CUDA(cudaStreamSynchronize(w->stream));
