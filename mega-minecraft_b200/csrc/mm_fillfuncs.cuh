@@ -266,6 +266,22 @@ __device__ __forceinline__ uint8_t finish_rock_block(uint8_t block, int wx, int 
     return block;
 }
 
+// A rock voxel is "bulk" when neither depth is in [0, 6]: it is not the floor block of a cave (bottom depth 0), and the
+// LUSH_CAVES rule needs a depth <= threshold = fma(simplex3, 4.5, 1.5) < 6.5 (|simplex3| < 1.1: the kernel sum
+// 42 * sum_i (0.6 - r_i^2)^4 r_i |grad| peaks at 1.052 over the simplex cell, |grad| <= 0.999 for all 290 table entries).
+// WARPED_FOREST / AMBER_FOREST only touch floor blocks, NONE nothing: for a bulk voxel only CRYSTAL_CAVES can change the block.
+__device__ __forceinline__ bool rock_is_bulk(int bottomDepth, int topDepth)
+{
+    return (bottomDepth < 0 || bottomDepth > 6) && (topDepth < 0 || topDepth > 6);
+}
+__device__ __forceinline__ uint8_t finish_bulk_rock_block(uint8_t block, int wx, int y, int wz, float height, int bottomDepth, int topDepth)
+{
+    bool lush = false;
+    if (cave_biome_is_crystal(wx, y, wz, height, 190249401))
+        cave_biome_post_process(&block, CB_CRYSTAL_CAVES, wx, y, wz, bottomDepth, topDepth, &lush);
+    return block;
+}
+
 // Queue record of a rock voxel: x = chunk, y = voxel index (17 bits) | rock kind (2) | bottom depth (6) | top depth (6).
 // The depths only matter as "== 0" (top block) and "in [0, threshold]" with threshold = 1.5 + 4.5 simplex3 (biomeFuncs.hpp:653-657);
 // |simplex3| <= 42 * 4 * max_r((0.6 - r^2)^4 r) * |grad| < 42 * 4 * 0.0209 * 3.2 < 11.3, so threshold < 53: every depth that is

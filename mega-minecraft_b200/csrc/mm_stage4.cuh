@@ -57,6 +57,40 @@ __device__ __forceinline__ int cave_biome(int x, int y, int z, float maxHeight, 
     return CB_NONE;
 }
 
+// "Is the cave biome at (x, y, z) CRYSTAL_CAVES?" - the same arithmetic as cave_biome() with the terms that cannot
+// matter left out. CRYSTAL_CAVES is biome 1 with weight ((1 - none) * shallow) * rocky, drawn after NONE (weight none):
+// it is chosen iff rand - none > 0 and (rand - none) - weight <= 0. A factor that is exactly 0 makes the weight 0 and the
+// second test false whatever the other noises are, and the `warped` noise does not enter at all.
+__device__ MMG_NOISE_INLINE bool cave_biome_is_crystal(int x, int y, int z, float maxHeight, int seed)
+{
+    const float px = (float)x, py = (float)y, pz = (float)z;
+    const float qx = px * 0.0470f, qy = py * 0.0470f, qz = pz * 0.0470f;
+    const float cx = fmaf(fbm3<3>(qx, qy, qz), 30.f, px);
+    const float cy = fmaf(fbm3<3>(qx + 5923.45f, qy + 4129.42f, qz + 5790.48f), 24.f, py);
+    const float cz = fmaf(fbm3<3>(qx + 1765.68f, qy + 4704.36f, qz + 5692.12f), 30.f, pz);
+    const float rocky = ss_t(fmaf(simplex3_raw<true>(fmaf(cx, 0.0022f, -9193.23f), fmaf(cy, 0.0022f, -6813.39f), fmaf(cz, 0.0022f, (float)-2171.23)), 42.f, 0.05f) / (0.05f - -0.05f));
+    if (rocky == 0.f) return false;
+    const float nx = cx * 0.2000f, nz = cz * 0.2000f;
+    const float top = fmaf(maxHeight + -128.f, 0.15f, 128.f);
+    const float sdStart = fmaf(fbm2<3>(nx + -4921.34f, nz + 8402.13f), 18.f, top + -72.f);
+    const float sdEnd = fmaf(fbm2<3>(nx + 9411.32f, nz + -3921.34f), 7.f, sdStart + -10.f);
+    const float shallow = ss_t((cy - sdEnd) / (sdStart - sdEnd));
+    if (shallow == 0.f) return false;
+    const float nsStart = fmaf(fbm2<3>(nx, nz), 23.f, top + -19.f);
+    const float nsEnd = fmaf(fbm2<3>(nx + 3821.34f, nz + 4920.32f), 3.f, nsStart + -5.f);
+    const float none = ss_t((cy - nsEnd) / (nsStart - nsEnd));
+    Minstd rng = make_rng4(x, y, z, seed);
+    float rand = rng.u01();
+    rand -= none;                                   // biome 0: NONE
+    if (rand <= 0.f) return false;
+    float w = 1.0f;                                 // biome 1: c_caveBiomeNoiseWeights[1] = {2, 1, 0, 1}
+    w *= 1.0f - none;
+    w *= shallow;
+    w *= rocky;
+    rand -= w;
+    return rand <= 0.f;
+}
+
 // ---------------------------------------------------------------- specialCaveNoise (rng.hpp:282-320)
 // hash (rng.hpp:148-155) at this call site: fma(z, Kz, fma(x, Kx, y*Ky))
 __device__ MMG_NOISE_INLINE float special_cave_noise(float px, float py, float pz)
@@ -164,6 +198,9 @@ __device__ __forceinline__ int cave_threshold(int wx, int y, int wz, float maxHe
     const float npx = (float)wx * 0.0050f, npy = fy * 0.0050f, npz = (float)wz * 0.0050f;
     const float topRatio = ss_t((fmaf(obw, 50.f, fy) + -142.f) / (95.f - 142.f));
     const float bottomRatio = ss_t((fy + -5.f) / (20.f - 5.f));
+    // topRatio is exactly 0 from y = 142 - 50 obw upwards; the threshold below is (finite * topRatio) * finite = 0 there and
+    // the test `thr > 0.04` fails whatever the two fbm3<4> say (8 simplex3 the reference evaluates for every such voxel)
+    if (topRatio == 0.f) return 0;
     float thr = fmaf(fbm3<4>(npx * 4.f, npy * 4.f, npz * 4.f), 0.12f, 0.24f);
     const float huge = ss_t((fbm3<4>(npx * 0.0700f, npy * 0.0700f, npz * 0.0700f) + -0.2f) / (0.4f - 0.2f));
     thr = thr * fmaf(huge, 1.4f, 1.f);

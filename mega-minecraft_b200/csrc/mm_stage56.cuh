@@ -321,21 +321,26 @@ constexpr int kColCapF = 512, kColCapC = 1024;   // candidates of one column seg
 constexpr int kLushQueueCap = 1 << 22;           // queued voxels per fill batch (overflow is decided in place)
 constexpr int kRockQueuePerChunk = 49152;        // rock-queue slots per chunk of a fill batch (typical need ~30 k; overflow is decided in place)
 
-// counters of one fill batch: [0] lush queue length, [1] rock queue length
+// counters of one fill batch: [0] lush queue length, [2] near-rock queue length, [3] bulk-rock queue length ([2..3] are
+// advanced together by one 64-bit atomic). The rock queue has two regions: [0, nearCap) for voxels within 6 blocks of a
+// cave floor / ceiling (full getCaveBiome), [nearCap, nearCap + bulkCap) for bulk voxels (only CRYSTAL_CAVES matters).
 // One CTA per column, three 128-voxel segments per thread: the column data (24 weights, 21 layer heights, 32 cave
 // layers) is staged once, the simplex tables only if the column can draw a surface biome whose pre/post-process
 // uses noise, and the column's rock voxels take one atomic to reserve their queue slots (segment-major, so that
 // consecutive queue entries are consecutive voxels of a column).
+__device__ __forceinline__ int rock_near_cap(int rockQueueCap) { return (rockQueueCap / 3) & ~31; }
+
 __global__ void __launch_bounds__(kFillSeg, 8) k_fill_terrain(const int* __restrict__ fillList, const int2* __restrict__ origins,
                                                               const float* __restrict__ heightfield, const float* __restrict__ biomeWeights,
                                                               const float* __restrict__ layers, const CaveLayer* __restrict__ caveLayers,
                                                               uint8_t* __restrict__ blocks, uint2* __restrict__ rockQueue, int rockQueueCap,
                                                               uint2* __restrict__ lushQueue, int* __restrict__ counters)
 {
+    constexpr int NW = kFillSeg / 32;
     __shared__ float shW[NUM_BIOMES];
     __shared__ float shLH[NUM_MATERIALS + 1];
     __shared__ CaveLayer shCL[MAX_CAVE_LAYERS];
-    __shared__ int shCnt[3 * (kFillSeg / 32)], shBase;
+    __shared__ int shCnt[2][3 * NW], shBase[2];
     const int col = blockIdx.x;
     const int li = col >> 8, idx = col & 255;
     const int chunk = fillList ? fillList[li] : li;
@@ -356,9 +361,11 @@ __global__ void __launch_bounds__(kFillSeg, 8) k_fill_terrain(const int* __restr
                            shW[MOUNTAINS] > 0.f || shW[CRYSTALS] > 0.f;
     if (needNoise) noise_tab_stage();
     const int lane = t & 31, warp = t >> 5;
+    const int nearCap = rock_near_cap(rockQueueCap), bulkCap = rockQueueCap - nearCap;
     uint8_t blk[3];
     uint2 rec[3];
     unsigned ballots[3];
+    int cls[3];                 // -1 not rock, 0 near, 1 bulk
 #pragma unroll
     for (int k = 0; k < 3; ++k)
     {
@@ -368,30 +375,36 @@ __global__ void __launch_bounds__(kFillSeg, 8) k_fill_terrain(const int* __restr
         // chunkFillPlaceBlock's first exit (chunk.cu:1213-1217) for a whole segment above the terrain and the sea
         blk[k] = ((float)y0 > height && y0 > SEA_LEVEL) ? (uint8_t)B_AIR : fill_place_block(shW, shLH, shCL, y, height, wx, wz, &rock, &bd, &td);
         rec[k] = rock ? pack_rock(chunk, idx * 384 + y, blk[k], bd, td) : make_uint2(0xffffffffu, 0u);
-        ballots[k] = __ballot_sync(0xffffffffu, rock);
-        if (lane == 0) shCnt[k * (kFillSeg / 32) + warp] = __popc(ballots[k]);
+        cls[k] = rock ? (rock_is_bulk(bd, td) ? 1 : 0) : -1;
+        const unsigned bNear = __ballot_sync(0xffffffffu, cls[k] == 0), bBulk = __ballot_sync(0xffffffffu, cls[k] == 1);
+        ballots[k] = cls[k] == 1 ? bBulk : bNear;
+        if (lane == 0) { shCnt[0][k * NW + warp] = __popc(bNear); shCnt[1][k * NW + warp] = __popc(bBulk); }
     }
     __syncthreads();
     if (t == 0)
     {
-        int total = 0;
+        unsigned nNear = 0, nBulk = 0;
 #pragma unroll
-        for (int w = 0; w < 3 * (kFillSeg / 32); ++w) total += shCnt[w];
-        shBase = total ? atomicAdd(&counters[1], total) : 0;
+        for (int w = 0; w < 3 * NW; ++w) { nNear += shCnt[0][w]; nBulk += shCnt[1][w]; }
+        unsigned long long old = 0ull;
+        if (nNear | nBulk) old = atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), (unsigned long long)nBulk << 32 | nNear);
+        shBase[0] = (int)(unsigned)(old & 0xffffffffull);
+        shBase[1] = (int)(unsigned)(old >> 32);
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 3; ++k)
     {
-        if (rec[k].x != 0xffffffffu)
+        if (cls[k] >= 0)
         {
-            int slot = shBase + __popc(ballots[k] & ((1u << lane) - 1u));
-            for (int w = 0; w < k * (kFillSeg / 32) + warp; ++w) slot += shCnt[w];
-            if (slot < rockQueueCap) rockQueue[slot] = rec[k];
+            const int q = cls[k];
+            int slot = shBase[q] + __popc(ballots[k] & ((1u << lane) - 1u));
+            for (int w = 0; w < k * NW + warp; ++w) slot += shCnt[q][w];
+            if (slot < (q ? bulkCap : nearCap)) rockQueue[(q ? nearCap : 0) + slot] = rec[k];
             else blk[k] = 0xff;      // queue full (no block id is 0xff): resolved below, once the whole CTA has staged the tables
         }
     }
-    // overflow path (rare: needs > 49 152 rock voxels per chunk on average over the batch): same result, on sparse warps
+    // overflow path (rare: the batch has more rock voxels than queue slots): same result, on sparse warps
     bool anyOverflow = false;
 #pragma unroll
     for (int k = 0; k < 3; ++k) anyOverflow = anyOverflow || blk[k] == 0xff;
@@ -418,29 +431,36 @@ __global__ void __launch_bounds__(kFillSeg, 8) k_fill_terrain(const int* __restr
 
 // getCaveBiome + caveBiomeBlockPostProcess for the queued rock voxels, one per thread on dense warps. In k_fill_terrain
 // the same work ran on whatever lanes of a 32-voxel column run happened to be rock below the surface (22 of 32 on average).
+// Near voxels take the full path; bulk voxels (about 4 of 5) only ask whether the biome is CRYSTAL_CAVES, which skips one
+// simplex3 always and up to twelve simplex2 (cave_biome_is_crystal). The bulk region starts on a warp boundary.
 __global__ void __launch_bounds__(128, 8) k_fill_rock(const int2* __restrict__ origins, const float* __restrict__ heightfield,
                                                       const uint2* __restrict__ rockQueue, int rockQueueCap, uint8_t* __restrict__ blocks,
                                                       uint2* __restrict__ lushQueue, int* __restrict__ counters)
 {
-    const int n = min(counters[1], rockQueueCap);
+    const int nearCap = rock_near_cap(rockQueueCap), bulkCap = rockQueueCap - nearCap;
+    const int nNear = min(counters[2], nearCap), nBulk = min(counters[3], bulkCap);
+    const int nearPad = (nNear + 31) & ~31, n = nearPad + nBulk;
     if (blockIdx.x * blockDim.x >= n) return;
     noise_tab_stage();
     const int lane = threadIdx.x & 31;
     for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x)
     {
         const int i = i0 + threadIdx.x;
+        const bool bulk = i >= nearPad;
         bool lush = false;
         int chunk = 0, voxel = 0, wx = 0, wz = 0, y = 0;
-        if (i < n)
+        if (bulk ? i < n : i < nNear)
         {
             uint8_t rockBlock;
             int bd, td;
-            unpack_rock(rockQueue[i], &chunk, &voxel, &rockBlock, &bd, &td);
+            unpack_rock(rockQueue[bulk ? nearCap + (i - nearPad) : i], &chunk, &voxel, &rockBlock, &bd, &td);
             const int idx = voxel / 384;
             y = voxel - idx * 384;
             const int2 o = origins[chunk];
             wx = o.x + (idx & 15); wz = o.y + (idx >> 4);
-            const uint8_t block = finish_rock_block(rockBlock, wx, y, wz, heightfield[(size_t)chunk * 256 + idx], bd, td, &lush);
+            const float height = heightfield[(size_t)chunk * 256 + idx];
+            const uint8_t block = bulk ? finish_bulk_rock_block(rockBlock, wx, y, wz, height, bd, td)
+                                       : finish_rock_block(rockBlock, wx, y, wz, height, bd, td, &lush);
             if (block != rockBlock) blocks[(size_t)chunk * 98304 + voxel] = block;
         }
         // warp-aggregated append of the voxels that need the lush-cave clay / moss decision

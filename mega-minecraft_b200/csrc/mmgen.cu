@@ -139,7 +139,7 @@ struct MmgenWorld
     Prep* d_prepF = nullptr;                         // per-placement culling records of one fill batch
     Prep* d_prepC = nullptr;
     uint2* d_lushQueue = nullptr;                    // voxels of one fill batch waiting for the lush-cave decision
-    int* d_lushCount = nullptr;                      // [0] lush queue length, [1] rock queue length
+    int* d_lushCount = nullptr;                      // [0] lush queue length, [2] near-rock, [3] bulk-rock queue lengths
     uint2* d_rockQueue = nullptr;                    // rock voxels of one fill batch waiting for getCaveBiome (k_fill_rock)
     uint8_t* d_blocks = nullptr;                     // [chunk][16][16][384]
     // meshing (mmgen_world_mesh): arena of the last call
@@ -373,7 +373,7 @@ static int launchFill(int m, const int* d_list, const int2* d_origins, const flo
                       int* d_counters, cudaStream_t stream)
 {
     const int rockCap = (int)std::min<size_t>((size_t)m * g_rockQueuePerChunk, (size_t)kFillBatch * kRockQueuePerChunk);
-    MMG_CUDA(cudaMemsetAsync(d_counters, 0, 2 * sizeof(int), stream));
+    MMG_CUDA(cudaMemsetAsync(d_counters, 0, 4 * sizeof(int), stream));
     MMG_TIMED(K_FILL_TERRAIN, stream, 1, MMG_LAUNCH(k_fill_terrain, m * 256, kFillSeg, kNoiseSmemBytes, stream, d_list, d_origins, d_height,
                                                     d_weights, d_layers, d_caves, d_blocks, d_rockQueue, rockCap, d_lushQueue, d_counters));
     MMG_TIMED(K_FILL_ROCK, stream, 1, MMG_LAUNCH(k_fill_rock, kNumSMs * 8, 128, kNoiseSmemBytes, stream, d_origins, d_height,
@@ -442,7 +442,7 @@ extern "C" int mmgen_fill(int n, const int32_t* origins, const float* heightfiel
         S[5].ensure((size_t)n * featureStride * sizeof(FeaturePlacement) + 16) ||
         S[6].ensure((size_t)n * caveFeatureStride * sizeof(CaveFeaturePlacement) + 16) || S[7].ensure((size_t)n * 2 * sizeof(int)) ||
         X[0].ensure((size_t)n * sizeof(GatherInfo)) || X[1].ensure((size_t)n * 98304) ||
-        X[2].ensure((size_t)kLushQueueCap * sizeof(uint2)) || X[3].ensure(2 * sizeof(int)) ||
+        X[2].ensure((size_t)kLushQueueCap * sizeof(uint2)) || X[3].ensure(4 * sizeof(int)) ||
         g_scratch[16].ensure((size_t)std::min(n, kFillBatch) * kRockQueuePerChunk * sizeof(uint2)) ||
         g_scratch[14].ensure((size_t)n * featureStride * sizeof(Prep) + 16) || g_scratch[15].ensure((size_t)n * caveFeatureStride * sizeof(Prep) + 16))
         return 1;
@@ -665,7 +665,7 @@ static int worldFill(MmgenWorld* w, const std::vector<int>& list, uint8_t* hostB
     if (!w->d_prepF) MMG_CUDA(cudaMalloc(&w->d_prepF, (size_t)kFillBatch * MAX_FEATURES * sizeof(Prep)));
     if (!w->d_prepC) MMG_CUDA(cudaMalloc(&w->d_prepC, (size_t)kFillBatch * MAX_CAVE_FEATURES * sizeof(Prep)));
     if (!w->d_lushQueue) MMG_CUDA(cudaMalloc(&w->d_lushQueue, (size_t)kLushQueueCap * sizeof(uint2)));
-    if (!w->d_lushCount) MMG_CUDA(cudaMalloc(&w->d_lushCount, 2 * sizeof(int)));
+    if (!w->d_lushCount) MMG_CUDA(cudaMalloc(&w->d_lushCount, 4 * sizeof(int)));
     if (!w->d_rockQueue) MMG_CUDA(cudaMalloc(&w->d_rockQueue, (size_t)kFillBatch * kRockQueuePerChunk * sizeof(uint2)));
     if (worldUploadList(w, list)) return 1;
     for (size_t b0 = 0; b0 < list.size(); b0 += kFillBatch)
