@@ -199,24 +199,45 @@ __device__ __forceinline__ bool needs_cave_biome(uint8_t block) { return block =
 // *pendingRock: the block is STONE / DEEPSLATE / BLACKSTONE and still has to go through getCaveBiome +
 // caveBiomeBlockPostProcess with the depths *bottomDepth / *topDepth (chunk.cu:1366-1370); the caller either queues
 // it for the dense kernel k_fill_rock or finishes it in place with finish_rock_block.
-__device__ __forceinline__ uint8_t fill_place_block(const float* weights, const float* layersAndHeight, const CaveLayer* caveLayers, int y,
+// Per-column constants of chunkFillPlaceBlock, built once per column by the fill kernel: the surface biomes of non-zero
+// weight in index order (randomBiome subtracts the weights in index order and a zero weight changes nothing, so walking
+// only these gives the same pick; the one exception, rand == 0 picking biome 0 whatever its weight, is kept) and isOcean.
+struct ColumnBiomes { int n; bool isOcean; uint8_t biome[NUM_BIOMES]; float weight[NUM_BIOMES]; };
+__device__ __forceinline__ int random_biome_compact(const ColumnBiomes& cb, float rand)
+{
+    if (rand <= 0.f) return 0;                      // biomeFuncs.hpp:39-53 with rand == 0: the first test already passes
+    for (int i = 0; i < cb.n; ++i)
+    {
+        rand -= cb.weight[i];
+        if (rand <= 0.f) return cb.biome[i];
+    }
+    return PLAINS;
+}
+
+__device__ __forceinline__ uint8_t fill_place_block(const ColumnBiomes& cb, const float* layersAndHeight, const CaveLayer* caveLayers, int y,
                                        float height, int wx, int wz, bool* pendingRock, int* bottomDepth, int* topDepth)
 {
     if (y == 0) return B_BEDROCK;
     const float fy = (float)y;
     if (fy > height && y > SEA_LEVEL) return B_AIR;
-    bool isOcean = false;
-    for (int b = 0; b < NUM_OCEAN_BIOMES; ++b)
-        if (weights[b] > 0.f) { isOcean = true; break; }
-    Minstd rng = make_rng3(wx, y, wz);
-    const int randBiome = random_biome(weights, 1, rng.u01());
+    // the surface biome of the voxel (chunk.cu:1232-1236) is a pure function of the position: it is drawn where it is first
+    // needed (the water branch, or a solid voxel below), not for the voxels that turn out to be cave air
+    int randBiome = -1;
+    auto voxel_biome = [&]() {
+        if (randBiome < 0)
+        {
+            Minstd rng = make_rng3(wx, y, wz);
+            randBiome = random_biome_compact(cb, rng.u01());
+        }
+        return randBiome;
+    };
     const bool isTopBlock = fy >= height - 1.f;
     uint8_t block = B_AIR;
     if (fy > height && y <= SEA_LEVEL)
     {
         block = B_WATER;
-        biome_post_process(&block, randBiome, wx, y, wz, height, isTopBlock);
-        if (isOcean) return block;
+        biome_post_process(&block, voxel_biome(), wx, y, wz, height, isTopBlock);
+        if (cb.isOcean) return block;
     }
     int caveBottomDepth = -384, caveTopDepth = -384;
     for (int li = 0; li < MAX_CAVE_LAYERS; ++li)
@@ -234,7 +255,7 @@ __device__ __forceinline__ uint8_t fill_place_block(const float* weights, const 
         caveTopDepth = y - (cl.end + 1);
     }
     if (fy > height) return block;
-    if (biome_pre_process(&block, randBiome, wx, y, wz, height))
+    if (biome_pre_process(&block, voxel_biome(), wx, y, wz, height))
     {
         biome_post_process(&block, randBiome, wx, y, wz, height, isTopBlock);
         return block;

@@ -341,6 +341,7 @@ __global__ void __launch_bounds__(kFillSeg, 8) k_fill_terrain(const int* __restr
     __shared__ float shLH[NUM_MATERIALS + 1];
     __shared__ CaveLayer shCL[MAX_CAVE_LAYERS];
     __shared__ int shCnt[2][3 * NW], shBase[2];
+    __shared__ ColumnBiomes shCB;
     const int col = blockIdx.x;
     const int li = col >> 8, idx = col & 255;
     const int chunk = fillList ? fillList[li] : li;
@@ -359,8 +360,23 @@ __global__ void __launch_bounds__(kFillSeg, 8) k_fill_terrain(const int* __restr
     // return a biome of weight 0 when it is CORAL_REEF (rand == 0) or the PLAINS fallback, neither of which uses noise
     const bool needNoise = shW[ARCHIPELAGO] > 0.f || shW[MESA] > 0.f || shW[SHREKS_SWAMP] > 0.f || shW[TIANZI_MOUNTAINS] > 0.f ||
                            shW[MOUNTAINS] > 0.f || shW[CRYSTALS] > 0.f;
-    if (needNoise) noise_tab_stage();
     const int lane = t & 31, warp = t >> 5;
+    if (warp == 0)
+    {
+        // the column's biomes of non-zero weight, in index order, and isOcean (chunk.cu:1225-1231)
+        const float wgt = lane < NUM_BIOMES ? shW[lane] : 0.f;
+        const unsigned nz = __ballot_sync(0xffffffffu, wgt != 0.f);
+        if (wgt != 0.f)
+        {
+            const int slot = __popc(nz & ((1u << lane) - 1u));
+            shCB.biome[slot] = (uint8_t)lane;
+            shCB.weight[slot] = wgt;
+        }
+        const unsigned ocean = __ballot_sync(0xffffffffu, lane < NUM_OCEAN_BIOMES && wgt > 0.f);
+        if (lane == 0) { shCB.n = __popc(nz); shCB.isOcean = ocean != 0u; }
+    }
+    if (needNoise) noise_tab_stage();
+    else __syncthreads();
     const int nearCap = rock_near_cap(rockQueueCap), bulkCap = rockQueueCap - nearCap;
     uint8_t blk[3];
     uint2 rec[3];
@@ -373,7 +389,7 @@ __global__ void __launch_bounds__(kFillSeg, 8) k_fill_terrain(const int* __restr
         bool rock = false;
         int bd = -384, td = -384;
         // chunkFillPlaceBlock's first exit (chunk.cu:1213-1217) for a whole segment above the terrain and the sea
-        blk[k] = ((float)y0 > height && y0 > SEA_LEVEL) ? (uint8_t)B_AIR : fill_place_block(shW, shLH, shCL, y, height, wx, wz, &rock, &bd, &td);
+        blk[k] = ((float)y0 > height && y0 > SEA_LEVEL) ? (uint8_t)B_AIR : fill_place_block(shCB, shLH, shCL, y, height, wx, wz, &rock, &bd, &td);
         rec[k] = rock ? pack_rock(chunk, idx * 384 + y, blk[k], bd, td) : make_uint2(0xffffffffu, 0u);
         cls[k] = rock ? (rock_is_bulk(bd, td) ? 1 : 0) : -1;
         const unsigned bNear = __ballot_sync(0xffffffffu, cls[k] == 0), bBulk = __ballot_sync(0xffffffffu, cls[k] == 1);
