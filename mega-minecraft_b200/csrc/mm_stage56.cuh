@@ -330,7 +330,7 @@ constexpr int kRockQueuePerChunk = 49152;        // rock-queue slots per chunk o
 // consecutive queue entries are consecutive voxels of a column).
 __device__ __forceinline__ int rock_near_cap(int rockQueueCap) { return (rockQueueCap / 3) & ~31; }
 
-__global__ void __launch_bounds__(kFillSeg, 8) k_fill_terrain(const int* __restrict__ fillList, const int2* __restrict__ origins,
+__global__ void __launch_bounds__(kFillSeg, 12) k_fill_terrain(const int* __restrict__ fillList, const int2* __restrict__ origins,
                                                               const float* __restrict__ heightfield, const float* __restrict__ biomeWeights,
                                                               const float* __restrict__ layers, const CaveLayer* __restrict__ caveLayers,
                                                               uint8_t* __restrict__ blocks, uint2* __restrict__ rockQueue, int rockQueueCap,
