@@ -201,6 +201,10 @@ def run_own(args):
     rank = int(os.environ.get("RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # libraries (NCCL's version banner) write to fd 1: send everything but the final JSON line to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the generation path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -373,7 +377,9 @@ def run_own(args):
     elif rank == 0:
         out["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)          # the JSON line is the only thing this arm writes to stdout
+        print(json.dumps(out), flush=True)
     world.close()
     if world_size > 1:
         dist.destroy_process_group()
