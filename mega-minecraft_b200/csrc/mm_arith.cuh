@@ -103,7 +103,8 @@ struct NoiseTab
 {
     float4 grad3[290];            // normalised 3-D gradient (ax, ay, az) of p   (noise.inl:676-711)
     float4 grad2[290];            // 2-D: (a0, h, norm factor) of p              (noise.inl:622-637)
-    unsigned short perm[584];     // permute(x), x = 0..579
+    unsigned short perm[584];     // 2 * permute(x), x = 0..579: a byte offset into this table (and 1/8 of one into grad*),
+                                  // so that every step of a permute chain is one 3-input add + one load
 };
 constexpr int kNoiseSmemBytes = (int)sizeof(NoiseTab);
 __device__ NoiseTab g_noiseTab;  // filled by k_init_noise_tables
@@ -128,7 +129,7 @@ __device__ __forceinline__ float sx_permute(float x) { return sx_mod289(fmaf(x, 
 __global__ void k_init_noise_tables()
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 584) g_noiseTab.perm[i] = (unsigned short)sx_permute((float)i);
+    if (i < 584) g_noiseTab.perm[i] = (unsigned short)(2 * (int)sx_permute((float)i));      // stored doubled: see NoiseTab
     if (i < 290)
     {
         const float p = (float)i;
@@ -196,10 +197,15 @@ __device__ MMG_NOISE_INLINE float simplex2_raw(float vx, float vy)
         jx = (int)(ix - 289.0f * floorf(ix / 289.0f));
         jy = (int)(iy - 289.0f * floorf(iy / 289.0f));
     }
-    const int e1x = gt ? 1 : 0, e1y = gt ? 0 : 1;
-    const float4 G0 = T->grad2[T->perm[T->perm[jy] + jx]];
-    const float4 G1 = T->grad2[T->perm[T->perm[jy + e1y] + jx + e1x]];
-    const float4 G2 = T->grad2[T->perm[T->perm[jy + 1] + jx + 1]];
+    // permute chains in byte offsets (perm[] holds doubled values): P2(off) = 2 * permute(off / 2)
+    const char* PB = reinterpret_cast<const char*>(T->perm);
+    const char* GB = reinterpret_cast<const char*>(T->grad2);
+    const int jx2 = jx + jx, jy2 = jy + jy;
+    const int e1x = gt ? 2 : 0, e1y = gt ? 0 : 2;
+#define MMG_P2(off) ((int)*reinterpret_cast<const unsigned short*>(PB + (off)))
+    const float4 G0 = *reinterpret_cast<const float4*>(GB + 8 * MMG_P2(MMG_P2(jy2) + jx2));
+    const float4 G1 = *reinterpret_cast<const float4*>(GB + 8 * MMG_P2(MMG_P2(jy2 + e1y) + jx2 + e1x));
+    const float4 G2 = *reinterpret_cast<const float4*>(GB + 8 * MMG_P2(MMG_P2(jy2 + 2) + jx2 + 2));
     float m0 = fmaxf(0.5f - fmaf(x0x, x0x, x0y * x0y), 0.0f);
     float m1 = fmaxf(0.5f - fmaf(x1x, x1x, x1y * x1y), 0.0f);
     float m2 = fmaxf(0.5f - fmaf(x2x, x2x, x2y * x2y), 0.0f);
@@ -240,12 +246,15 @@ __device__ MMG_NOISE_INLINE float simplex3_raw(float vx, float vy, float vz)
     float x3x = x0x - 0.5f, x3y = x0y - 0.5f, x3z = x0z - 0.5f;
     const int jx = (int)sx_mod289(ix), jy = (int)sx_mod289(iy), jz = (int)sx_mod289(iz);
     // p = permute(permute(permute(i.z + e.z) + i.y + e.y) + i.x + e.x) for the four corners
-    const unsigned short* P = T->perm;
-    const int p0 = P[P[P[jz] + jy] + jx];
-    const int p1 = P[P[P[jz + (a1z ? 1 : 0)] + jy + (a1y ? 1 : 0)] + jx + (a1x ? 1 : 0)];
-    const int p2 = P[P[P[jz + (a2z ? 1 : 0)] + jy + (a2y ? 1 : 0)] + jx + (a2x ? 1 : 0)];
-    const int p3 = P[P[P[jz + 1] + jy + 1] + jx + 1];
-    const float4 G0 = T->grad3[p0], G1 = T->grad3[p1], G2 = T->grad3[p2], G3 = T->grad3[p3];
+    const char* PB = reinterpret_cast<const char*>(T->perm);
+    const char* GB = reinterpret_cast<const char*>(T->grad3);
+    const int jx2 = jx + jx, jy2 = jy + jy, jz2 = jz + jz;
+    const int p0 = MMG_P2(MMG_P2(MMG_P2(jz2) + jy2) + jx2);
+    const int p1 = MMG_P2(MMG_P2(MMG_P2(jz2 + (a1z ? 2 : 0)) + jy2 + (a1y ? 2 : 0)) + jx2 + (a1x ? 2 : 0));
+    const int p2 = MMG_P2(MMG_P2(MMG_P2(jz2 + (a2z ? 2 : 0)) + jy2 + (a2y ? 2 : 0)) + jx2 + (a2x ? 2 : 0));
+    const int p3 = MMG_P2(MMG_P2(MMG_P2(jz2 + 2) + jy2 + 2) + jx2 + 2);
+    const float4 G0 = *reinterpret_cast<const float4*>(GB + 8 * p0), G1 = *reinterpret_cast<const float4*>(GB + 8 * p1);
+    const float4 G2 = *reinterpret_cast<const float4*>(GB + 8 * p2), G3 = *reinterpret_cast<const float4*>(GB + 8 * p3);
     float m0 = fmaxf(0.6f - fmaf(x0z, x0z, fmaf(x0x, x0x, x0y * x0y)), 0.0f);
     float m1 = fmaxf(0.6f - fmaf(x1z, x1z, fmaf(x1x, x1x, x1y * x1y)), 0.0f);
     float m2 = fmaxf(0.6f - fmaf(x2z, x2z, fmaf(x2x, x2x, x2y * x2y)), 0.0f);
