@@ -201,11 +201,13 @@ __device__ MMG_NOISE_INLINE float simplex2_raw(float vx, float vy)
     const char* PB = reinterpret_cast<const char*>(T->perm);
     const char* GB = reinterpret_cast<const char*>(T->grad2);
     const int jx2 = jx + jx, jy2 = jy + jy;
-    const int e1x = gt ? 2 : 0, e1y = gt ? 0 : 2;
+    const int e1x = gt ? 2 : 0;
 #define MMG_P2(off) ((int)*reinterpret_cast<const unsigned short*>(PB + (off)))
-    const float4 G0 = *reinterpret_cast<const float4*>(GB + 8 * MMG_P2(MMG_P2(jy2) + jx2));
-    const float4 G1 = *reinterpret_cast<const float4*>(GB + 8 * MMG_P2(MMG_P2(jy2 + e1y) + jx2 + e1x));
-    const float4 G2 = *reinterpret_cast<const float4*>(GB + 8 * MMG_P2(MMG_P2(jy2 + 2) + jx2 + 2));
+    // the middle corner's first permute is one of the two the outer corners load anyway
+    const int py0 = MMG_P2(jy2), py1 = MMG_P2(jy2 + 2);
+    const float4 G0 = *reinterpret_cast<const float4*>(GB + 8 * MMG_P2(py0 + jx2));
+    const float4 G1 = *reinterpret_cast<const float4*>(GB + 8 * MMG_P2((gt ? py0 : py1) + jx2 + e1x));
+    const float4 G2 = *reinterpret_cast<const float4*>(GB + 8 * MMG_P2(py1 + jx2 + 2));
     float m0 = fmaxf(0.5f - fmaf(x0x, x0x, x0y * x0y), 0.0f);
     float m1 = fmaxf(0.5f - fmaf(x1x, x1x, x1y * x1y), 0.0f);
     float m2 = fmaxf(0.5f - fmaf(x2x, x2x, x2y * x2y), 0.0f);
@@ -249,10 +251,12 @@ __device__ MMG_NOISE_INLINE float simplex3_raw(float vx, float vy, float vz)
     const char* PB = reinterpret_cast<const char*>(T->perm);
     const char* GB = reinterpret_cast<const char*>(T->grad3);
     const int jx2 = jx + jx, jy2 = jy + jy, jz2 = jz + jz;
-    const int p0 = MMG_P2(MMG_P2(MMG_P2(jz2) + jy2) + jx2);
-    const int p1 = MMG_P2(MMG_P2(MMG_P2(jz2 + (a1z ? 2 : 0)) + jy2 + (a1y ? 2 : 0)) + jx2 + (a1x ? 2 : 0));
-    const int p2 = MMG_P2(MMG_P2(MMG_P2(jz2 + (a2z ? 2 : 0)) + jy2 + (a2y ? 2 : 0)) + jx2 + (a2x ? 2 : 0));
-    const int p3 = MMG_P2(MMG_P2(MMG_P2(jz2 + 2) + jy2 + 2) + jx2 + 2);
+    // the two middle corners' first permute is one of the two the outer corners load anyway
+    const int pz0 = MMG_P2(jz2), pz1 = MMG_P2(jz2 + 2);
+    const int p0 = MMG_P2(MMG_P2(pz0 + jy2) + jx2);
+    const int p1 = MMG_P2(MMG_P2((a1z ? pz1 : pz0) + jy2 + (a1y ? 2 : 0)) + jx2 + (a1x ? 2 : 0));
+    const int p2 = MMG_P2(MMG_P2((a2z ? pz1 : pz0) + jy2 + (a2y ? 2 : 0)) + jx2 + (a2x ? 2 : 0));
+    const int p3 = MMG_P2(MMG_P2(pz1 + jy2 + 2) + jx2 + 2);
     const float4 G0 = *reinterpret_cast<const float4*>(GB + 8 * p0), G1 = *reinterpret_cast<const float4*>(GB + 8 * p1);
     const float4 G2 = *reinterpret_cast<const float4*>(GB + 8 * p2), G3 = *reinterpret_cast<const float4*>(GB + 8 * p3);
     float m0 = fmaxf(0.6f - fmaf(x0z, x0z, fmaf(x0x, x0x, x0y * x0y)), 0.0f);
