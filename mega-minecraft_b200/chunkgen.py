@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "libmmgen.so")
+_LIB = os.environ.get("MMGEN_LIB") or os.path.join(_HERE, "libmmgen.so")      # MMGEN_LIB: developer override for tuning builds
 
 STAGE_HEIGHTFIELD, STAGE_LAYERS, STAGE_EROSION, STAGE_CAVES, STAGE_FEATURES, STAGE_FILL = 1, 2, 4, 8, 16, 32
 STAGE_ALL = 63

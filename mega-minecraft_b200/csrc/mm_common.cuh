@@ -37,4 +37,12 @@ inline int fail(const char* what, cudaError_t err, const char* file, int line)
 
 constexpr int kNumSMs = 148;   // B200
 
+// resident CTAs per SM the register allocator is asked to allow (tuned on a B200)
+#ifndef MMG_CAVES_MINBLOCKS
+#define MMG_CAVES_MINBLOCKS 10
+#endif
+#ifndef MMG_ROCK_MINBLOCKS
+#define MMG_ROCK_MINBLOCKS 8
+#endif
+
 }  // namespace mmg

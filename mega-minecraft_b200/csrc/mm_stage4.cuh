@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256) k_cave_columns(const int* __restrict__ ch
     cols[(size_t)li * 256 + idx] = c;
 }
 
-__global__ void __launch_bounds__(128, 8) k_caves(const int* __restrict__ chunkList, const int2* __restrict__ origins,
+__global__ void __launch_bounds__(128, MMG_CAVES_MINBLOCKS) k_caves(const int* __restrict__ chunkList, const int2* __restrict__ origins,
                                                const float* __restrict__ heightfield, const CaveColumn* __restrict__ cols,
                                                CaveLayer* __restrict__ caveLayers, uint2* __restrict__ biomeQueue, int* __restrict__ biomeCount,
                                                int biomeQueueCap)

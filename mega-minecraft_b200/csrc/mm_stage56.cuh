@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(kFillSeg, 12) k_fill_terrain(const int* __rest
 // the same work ran on whatever lanes of a 32-voxel column run happened to be rock below the surface (22 of 32 on average).
 // Near voxels take the full path; bulk voxels (about 4 of 5) only ask whether the biome is CRYSTAL_CAVES, which skips one
 // simplex3 always and up to twelve simplex2 (cave_biome_is_crystal). The bulk region starts on a warp boundary.
-__global__ void __launch_bounds__(128, 8) k_fill_rock(const int2* __restrict__ origins, const float* __restrict__ heightfield,
+__global__ void __launch_bounds__(128, MMG_ROCK_MINBLOCKS) k_fill_rock(const int2* __restrict__ origins, const float* __restrict__ heightfield,
                                                       const uint2* __restrict__ rockQueue, int rockQueueCap, uint8_t* __restrict__ blocks,
                                                       uint2* __restrict__ lushQueue, int* __restrict__ counters)
 {
