@@ -174,6 +174,30 @@ __device__ __forceinline__ int block_ordered_offset(bool keep, int* shWarp, int*
     return off + __popc(m & ((1u << lane) - 1u));
 }
 
+// Extent of ONE surface placement where its own first draws fix it (the type's table values are the worst case over all
+// draws). PURPLE_MUSHROOM (featurePlacement.hpp:560-640 / place_feature): pos = offset * scale (* 0.5 with probability 0.2),
+// and a voxel survives the first rejection only if |pos.x|, |pos.z| <= 35 and pos.y <= height + 12 (each length in that test
+// is bounded below by the component: rounding is monotone and sqrt(fl(x^2)) = |x|). The worst case is reach 70 and 120
+// blocks of height; a typical mushroom needs a third of both. Same rounded operations as the rasteriser.
+__device__ __forceinline__ void surface_feature_extent(const FeaturePlacement& p, int* reach, int* yHi)
+{
+    *reach = min(c_featureReach[p.feature], 1 << 16);
+    *yHi = c_featureHeightBounds[p.feature][1];
+    if (p.feature == F_PURPLE_MUSHROOM)
+    {
+        Minstd frng = make_rng4(p.x, p.y, p.z, 1293012);
+        const float scale = fmaf(frng.u01(), 1.2f, 1.f);
+        const bool half = frng.u01() < 0.2f;
+        const float height = fmaf(frng.u01(), 30.f, 25.f);
+        auto scaled = [&](int v) { const float s = (float)v * scale; return half ? s * 0.5f : s; };
+        int t = *reach, h = *yHi;
+        while (t > 0 && scaled(t) > 35.f) --t;
+        while (h > 0 && scaled(h) > height + 12.f) --h;
+        *reach = t;
+        *yHi = h;
+    }
+}
+
 // does a feature at (px, pz) with horizontal reach r touch the 16x16 footprint whose corner is (ox, oz)?
 __device__ __forceinline__ bool reach_hits_chunk(int px, int pz, int r, int ox, int oz)
 {
@@ -212,10 +236,12 @@ __global__ void __launch_bounds__(256) k_gather_features(const int* __restrict__
             const int i = i0 + tid;
             FeaturePlacement p;
             bool keep = false;
+            int reach = 0, yHi = 0;
             if (i < nf)
             {
                 p = sf[i];
-                keep = reach_hits_chunk(p.x, p.z, c_featureReach[p.feature], o.x, o.y);
+                surface_feature_extent(p, &reach, &yHi);
+                keep = reach_hits_chunk(p.x, p.z, reach, o.x, o.y);
             }
             int total;
             const int off = block_ordered_offset(keep, shWarp, &total);
@@ -223,7 +249,7 @@ __global__ void __launch_bounds__(256) k_gather_features(const int* __restrict__
             {
                 dstF[outF + off] = p;
                 mnF = min(mnF, p.y + c_featureHeightBounds[p.feature][0]);
-                mxF = max(mxF, p.y + c_featureHeightBounds[p.feature][1]);
+                mxF = max(mxF, p.y + yHi);
             }
             outF += total;
         }
@@ -515,6 +541,7 @@ __global__ void __launch_bounds__(128) k_fill_lush(const int2* __restrict__ orig
 // What k_fill_features needs to know about a placement before it touches the rasteriser: the y band it can
 // fill (reference bound intersected with the type's own band, clipped to the world), the columns of THIS
 // chunk its horizontal reach covers, and whether it may overwrite terrain. lo > hi: cannot touch the chunk.
+__device__ unsigned g_debugFeatureMask = 0xffffffffu;      // mmgen_debug_feature_mask: profiling experiments only
 struct Prep { short lo, hi; unsigned char xr, zr, canReplace, feature; uint32_t seed; };      // xr = x0 | x1 << 4 (local 0..15), zr likewise;
                                                                                               // seed = state of the placement's own RNG
 
@@ -545,11 +572,13 @@ __global__ void __launch_bounds__(256) k_prepare_placements(const int* __restric
         Prep k;
         k.lo = 1; k.hi = 0; k.xr = k.zr = 0; k.canReplace = p.canReplaceBlocks ? 1 : 0; k.feature = p.feature;
         k.seed = make_rng4(p.x, p.y, p.z, 1293012).x;      // featurePlacement.hpp:153: seeded once per placement here, not per voxel
+        int reach = 0, yHi = 0;
         if (p.feature == F_NONE) atomicMin(&shFirstNone[0], i);
-        else if (columns(p.x, p.z, min(c_featureReach[p.feature], 1 << 16), &k))
+        else if (!((g_debugFeatureMask >> p.feature) & 1u)) { /* experiment knob: type switched off */ }
+        else if (surface_feature_extent(p, &reach, &yHi), columns(p.x, p.z, reach, &k))
         {
             k.lo = (short)max(p.y + c_featureHeightBounds[p.feature][0], 0);
-            k.hi = (short)min(p.y + c_featureHeightBounds[p.feature][1], 383);
+            k.hi = (short)min(p.y + yHi, 383);
             shNoise = 1;      // surface rasterisers use simplex / Worley noise
         }
         prepF[(size_t)li * strideF + i] = k;

@@ -1153,3 +1153,10 @@ int mmgen_world_mesh_device_ptrs(MmgenWorld* w, int i, void** verts, void** idx,
 }
 
 int mmgen_world_mesh_ms(MmgenWorld* w, float* out) { *out = w->meshMs; return 0; }
+
+// profiling experiments only: surface feature types whose bit is 0 are not rasterised (results then differ from the reference)
+extern "C" int mmgen_debug_feature_mask(unsigned mask)
+{
+    MMG_CUDA(cudaMemcpyToSymbol(g_debugFeatureMask, &mask, sizeof(mask)));
+    return 0;
+}
