@@ -183,6 +183,14 @@ __device__ __forceinline__ void surface_feature_extent(const FeaturePlacement& p
 {
     *reach = min(c_featureReach[p.feature], 1 << 16);
     *yHi = c_featureHeightBounds[p.feature][1];
+    // rasterisers whose first statement rejects the whole placement by its own height (place_feature: F_ICEBERG, F_CORAL,
+    // F_MEDIUM_CRYSTAL / F_CRYSTAL): such a placement fills nothing anywhere
+    if ((p.feature == F_ICEBERG && p.y > SEA_LEVEL - 32) || (p.feature == F_CORAL && p.y > SEA_LEVEL - 6) ||
+        ((p.feature == F_MEDIUM_CRYSTAL || p.feature == F_CRYSTAL) && p.y > 180))
+    {
+        *reach = -(1 << 20);
+        return;
+    }
     if (p.feature == F_PURPLE_MUSHROOM)
     {
         Minstd frng = make_rng4(p.x, p.y, p.z, 1293012);
@@ -631,6 +639,7 @@ __global__ void __launch_bounds__(256) k_prepare_placements(const int* __restric
         default: break;
         }
         if (p.feature == CF_NONE) atomicMin(&shFirstNone[1], i);
+        else if (!((g_debugFeatureMask >> (21 + p.feature)) & 1u)) { /* experiment knob: type switched off */ }
         else if (columns(p.x, p.z, reach, &k))
         {
             const int* band = c_caveFeatureBand[p.feature];

@@ -19,6 +19,11 @@ def run(mask):
 full = run(0xffffffff)
 none = run(0)
 print("all types %.2f ms, no surface features %.2f ms" % (full, none))
-for t in (16, 2, 4, 6, 7, 17, 18, 9, 8, 10):
+for t in (16, 2, 4, 17):
     print("without %-24s %.2f ms  (saves %.2f)" % (names[t], run(0xffffffff & ~(1 << t)), full - run(0xffffffff & ~(1 << t))))
+cnames = "NONE TEST_GLOWSTONE_PILLAR TEST_SHROOMLIGHT_PILLAR CAVE_VINE GLOWSTONE_CLUSTER STORMLIGHT_SPHERE CEILING_STORMLIGHT_SPHERE CRYSTAL_PILLAR WARPED_FUNGUS AMBER_FUNGUS".split()
+nocave = run(0xffffffff & ~(0x3ff << 21))
+print("no cave features %.2f ms" % nocave)
+for t in range(3, 10):
+    print("without cave %-26s %.2f ms  (saves %.2f)" % (cnames[t], run(0xffffffff & ~(1 << (21 + t))), full - run(0xffffffff & ~(1 << (21 + t)))))
 gen.L.mmgen_debug_feature_mask(0xffffffff)
