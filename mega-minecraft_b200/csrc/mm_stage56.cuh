@@ -550,6 +550,11 @@ __global__ void __launch_bounds__(128) k_fill_lush(const int2* __restrict__ orig
 // fill (reference bound intersected with the type's own band, clipped to the world), the columns of THIS
 // chunk its horizontal reach covers, and whether it may overwrite terrain. lo > hi: cannot touch the chunk.
 __device__ unsigned g_debugFeatureMask = 0xffffffffu;      // mmgen_debug_feature_mask: profiling experiments only
+#ifdef MMG_FEATURE_STATS
+// developer build (tools/feature_census.py): per feature type [0..20] surface, [32..41] cave: warp clock cycles spent in the
+// rasteriser loop, (column, y) pairs put on the rasteriser, pairs that reached the rasteriser call, hits
+__device__ unsigned long long g_featStats[64][4];
+#endif
 struct Prep { short lo, hi; unsigned char xr, zr, canReplace, feature; uint32_t seed; };      // xr = x0 | x1 << 4 (local 0..15), zr likewise;
                                                                                               // seed = state of the placement's own RNG
 
@@ -664,6 +669,11 @@ constexpr int kSlab = 32;                  // voxels of a column per CTA of k_fi
 constexpr int kSlabPitch = 257;            // shBest[yy][col], padded: lanes that differ in yy hit different banks
 constexpr unsigned kNoBest = 0xffffffffu;
 constexpr int kBigBox = 2048, kMaxBig = 96;   // (column, y) pairs above which a placement is rasterised by the whole CTA
+// ceil(2^32 / n), n = 2..32 ([0], [1] unused)
+__constant__ const unsigned c_recip32[33] = {0, 0, 0x80000000u, 0x55555556u, 0x40000000u, 0x33333334u, 0x2aaaaaabu, 0x24924925u, 0x20000000u,
+    0x1c71c71du, 0x1999999au, 0x1745d175u, 0x15555556u, 0x13b13b14u, 0x12492493u, 0x11111112u, 0x10000000u, 0x0f0f0f10u, 0x0e38e38fu,
+    0x0d79435fu, 0x0ccccccdu, 0x0c30c30du, 0x0ba2e8bbu, 0x0b21642du, 0x0aaaaaabu, 0x0a3d70a4u, 0x09d89d8au, 0x097b425fu, 0x0924924au,
+    0x08d3dcb1u, 0x08888889u, 0x08421085u, 0x08000000u};
 __constant__ const unsigned c_recip16[17] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096};
 
 // Placement scan of one 32-voxel slab of a chunk (12 slabs per chunk). Work is distributed by PLACEMENT, not
@@ -684,6 +694,7 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
     __shared__ __align__(16) uint8_t shBlk[256 * kSlab];     // [col][yy]
     __shared__ int shNext, shNumBig;
     __shared__ unsigned short shBig[kMaxBig];
+    __shared__ unsigned short shQueue[8 * 64];               // per warp: pairs that passed the filter, waiting for a full warp
     const int slab = blockIdx.x % 12, li = blockIdx.x / 12;
     const int chunk = fillList ? fillList[li] : li;
     const int t = threadIdx.x, y0 = slab * kSlab, y1 = y0 + kSlab - 1;
@@ -709,7 +720,12 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
     const CaveFeaturePlacement* cf = gCF + (size_t)li * strideCF;
     const Prep* pf = prepF + (size_t)li * strideF;
     const Prep* pc = prepC + (size_t)li * strideCF;
-    // rasterises (column, y) pairs first, first + step, ... of placement e; returns false if e cannot touch the slab
+    // rasterises the (column, y) pairs of placement e that the calling WARP owns: pairs [first, first + 32), [first + step,
+    // first + step + 32), ... one per lane; returns false if e cannot touch the slab. Two steps per round: a cheap filter
+    // (voxel already claimed by an earlier placement / solid and the placement may not replace blocks) pushes the
+    // surviving pairs onto the warp's queue, and the rasteriser runs on full warps popped from that queue - a cave
+    // feature's box is mostly rock, so without the queue 3 or 4 lanes of 32 reach the rasteriser.
+    unsigned short* wq = shQueue + (t >> 5) * 64;
     auto raster = [&](int e, int first, int step, bool countOnly, int* totalOut) -> bool {
         const bool cave = e >= nF;
         const Prep k = cave ? pc[e - nF] : pf[e];
@@ -717,29 +733,69 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
         if (lo > hi) return false;
         const int x0 = k.xr & 15, nxc = (k.xr >> 4) - x0 + 1, z0 = k.zr & 15, nzc = (k.zr >> 4) - z0 + 1;
         const int ny = hi - lo + 1;
-        const int sh = 32 - __clz(ny - 1);                    // ny padded to a power of two: y fastest, no division by ny
-        const int total = (nxc * nzc) << sh;
+        const int total = nxc * nzc * ny;                     // y fastest
         *totalOut = total;
         if (countOnly) return true;
+        const unsigned rny = c_recip32[ny];                   // ceil(2^32 / ny): __umulhi(p, rny) = p / ny for p < 2^27
         const unsigned key = (unsigned)e << 8;
         FeaturePlacement fp;
         CaveFeaturePlacement cp;
         if (cave) cp = cf[e - nF];
         else fp = f[e];
-        for (int p = first; p < total; p += step)
+#ifdef MMG_FEATURE_STATS
+        const long long statT0 = clock64();
+        const int statSlot = (cave ? 32 : 0) + k.feature;
+#endif
+        int qn = 0;
+        for (int base = first;; base += step)
         {
-            const int dy = p & ((1 << sh) - 1);
-            if (dy >= ny) continue;
-            const int q = p >> sh;
-            const int dz = (int)((q * c_recip16[nxc]) >> 16), dx = q - dz * nxc;
-            const int x = x0 + dx, z = z0 + dz, y = lo + dy;
-            const int col = x + 16 * z, yy = y - y0;
-            if (shBest[yy * kSlabPitch + col] <= (key | 0xffu)) continue;      // claimed by an earlier placement
-            if (shBlk[col * kSlab + yy] != B_AIR && !k.canReplace) continue;
-            uint8_t fb = 0;
-            const bool hit = cave ? place_cave_feature(cp, o.x + x, y, o.y + z, k.seed, &fb) : place_feature(fp, o.x + x, y, o.y + z, k.seed, &fb);
-            if (hit) atomicMin(&shBest[yy * kSlabPitch + col], key | fb);
+            const bool more = base < total;                   // warp-uniform
+            if (more)
+            {
+                const int p = base + lane;
+                bool cand = false;
+                int code = 0;
+                if (p < total)
+                {
+                    const int q = ny > 1 ? (int)__umulhi((unsigned)p, rny) : p, dy = p - q * ny;
+                    const int dz = (int)((q * c_recip16[nxc]) >> 16), dx = q - dz * nxc;
+                    const int col = (x0 + dx) + 16 * (z0 + dz), yy = lo + dy - y0;
+                    code = col << 5 | yy;
+                    cand = shBest[yy * kSlabPitch + col] > (key | 0xffu) &&      // not claimed by an earlier placement
+                           (k.canReplace || shBlk[col * kSlab + yy] == B_AIR);
+#ifdef MMG_FEATURE_STATS
+                    atomicAdd(&g_featStats[statSlot][1], 1ull);
+#endif
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, cand);
+                if (cand) wq[qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short)code;
+                qn += __popc(m);
+                __syncwarp();
+            }
+            if (qn >= 32 || (!more && qn > 0))
+            {
+                const int n = min(qn, 32);
+                qn -= n;
+                const int code = wq[qn + (lane < n ? lane : 0)];
+                __syncwarp();
+                if (lane < n)
+                {
+                    const int col = code >> 5, yy = code & 31, x = col & 15, z = col >> 4, y = y0 + yy;
+                    uint8_t fb = 0;
+                    const bool hit = cave ? place_cave_feature(cp, o.x + x, y, o.y + z, k.seed, &fb) : place_feature(fp, o.x + x, y, o.y + z, k.seed, &fb);
+                    if (hit) atomicMin(&shBest[yy * kSlabPitch + col], key | fb);
+#ifdef MMG_FEATURE_STATS
+                    atomicAdd(&g_featStats[statSlot][2], 1ull);
+                    if (hit) atomicAdd(&g_featStats[statSlot][3], 1ull);
+#endif
+                }
+            }
+            if (!more) break;
         }
+#ifdef MMG_FEATURE_STATS
+        __syncwarp();
+        if (lane == 0) atomicAdd(&g_featStats[statSlot][0], (unsigned long long)(clock64() - statT0));
+#endif
         return true;
     };
     // phase 1: warps pull placements from a shared counter (in list order, so that earlier placements tend to
@@ -763,7 +819,7 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
                 continue;
             }
         }
-        raster(e, lane, 32, false, &total);
+        raster(e, 0, 32, false, &total);
     }
     __syncthreads();
     // phase 2: the whole CTA rasterises each large placement together
@@ -772,7 +828,7 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
         for (int b = 0; b < nBig; ++b)
         {
             int total = 0;
-            raster(shBig[b], t, 256, false, &total);
+            raster(shBig[b], t & ~31, 256, false, &total);
         }
     }
     __syncthreads();

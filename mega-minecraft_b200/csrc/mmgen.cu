@@ -1160,3 +1160,14 @@ extern "C" int mmgen_debug_feature_mask(unsigned mask)
     MMG_CUDA(cudaMemcpyToSymbol(g_debugFeatureMask, &mask, sizeof(mask)));
     return 0;
 }
+#ifdef MMG_FEATURE_STATS
+// developer build only (nvcc -DMMG_FEATURE_STATS, tools/feature_census.py): read and clear the rasteriser census
+extern "C" int mmgen_debug_feature_stats(unsigned long long* out)
+{
+    MMG_CUDA(cudaDeviceSynchronize());
+    MMG_CUDA(cudaMemcpyFromSymbol(out, g_featStats, sizeof(unsigned long long) * 64 * 4));
+    static unsigned long long zero[64 * 4];
+    MMG_CUDA(cudaMemcpyToSymbol(g_featStats, zero, sizeof(zero)));
+    return 0;
+}
+#endif

@@ -1,0 +1,34 @@
+#!/usr/bin/env python3
+"""Developer tool (GPU box): census of k_fill_features per feature type - warp cycles in the rasteriser loop, (column, y)
+pairs offered, pairs that reached the rasteriser, hits. Needs the stats build:
+  nvcc <NVCC_FLAGS> -DMMG_FEATURE_STATS -o mega-minecraft_b200/libmmgen_stats.so mega-minecraft_b200/csrc/mmgen.cu
+  MMGEN_LIB=mega-minecraft_b200/libmmgen_stats.so python tools/feature_census.py 128"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import mmgen_loader  # noqa: E402
+
+mm = mmgen_loader.load()
+gen = mm.ChunkGen(0)
+S = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+w = gen.region_world(0, 0, S, S)
+names = "NONE SPHERE CORAL KELP ICEBERG ACACIA REDWOOD CYPRESS BIRCH PINE PINE_SHRUB RAFFLESIA LARGE_JUNGLE SMALL_JUNGLE TINY_JUNGLE MEDIUM_PURPLE_MUSHROOM PURPLE_MUSHROOM MEDIUM_CRYSTAL CRYSTAL PALM CACTUS".split()
+cnames = "NONE TEST_GLOWSTONE_PILLAR TEST_SHROOMLIGHT_PILLAR CAVE_VINE GLOWSTONE_CLUSTER STORMLIGHT_SPHERE CEILING_STORMLIGHT_SPHERE CRYSTAL_PILLAR WARPED_FUNGUS AMBER_FUNGUS".split()
+st = np.zeros((64, 4), np.uint64)
+w.generate(mm.STAGE_ALL); w.sync()
+gen.L.mmgen_debug_feature_stats(st.ctypes.data_as(ctypes.c_void_p))
+tot = float(st[:, 0].sum())
+rows = []
+for i in range(64):
+    if st[i, 1] == 0:
+        continue
+    n = names[i] if i < 32 else "cave " + cnames[i - 32]
+    rows.append((int(st[i, 0]), n, int(st[i, 1]), int(st[i, 2]), int(st[i, 3])))
+print("%-30s %8s %12s %12s %12s %8s" % ("type", "cycles%", "pairs", "rasterised", "hits", "cyc/pair"))
+for c, n, a, b, h in sorted(rows, reverse=True):
+    print("%-30s %7.1f%% %12d %12d %12d %8.1f" % (n, 100 * c / tot, a, b, h, c / max(a, 1) * 32))
