@@ -28,6 +28,11 @@ __device__ __forceinline__ float ratio_of(float v, float lo, float hi) { return 
 constexpr float kPi = 3.14159265358979323846264338327f, kTwoPi = 6.28318530717958647692528676655f,
                 kPiOverTwo = 1.57079632679489661923132169163f;
 
+// One copy each of the libdevice routines the rasterisers call (sincosf alone is inlined with its large-argument
+// reduction at eight call sites otherwise): place_feature was 123 KB of SASS and the kernel stalled on instruction fetch.
+__device__ __noinline__ void pf_sincosf(float a, float* s, float* c) { sincosf(a, s, c); }
+__device__ __noinline__ float pf_powf(float a, float b) { return powf(a, b); }
+
 // rng.hpp:52-63. distFromLine = |vecLine*ratio - pointPos| (the product is fused into the subtraction)
 __device__ __forceinline__ bool line_params(V3 pos, V3 l1, V3 l2, float* ratio, float* dist)
 {
@@ -39,7 +44,7 @@ __device__ __forceinline__ bool line_params(V3 pos, V3 l1, V3 l2, float* ratio, 
 }
 
 // featurePlacement.hpp:68-74
-__device__ __forceinline__ bool in_rasterized_line(int fx, int fy, int fz, V3 l1, V3 l2)
+__device__ __noinline__ bool in_rasterized_line(int fx, int fy, int fz, V3 l1, V3 l2)
 {
     float ratio, dist;
     const bool inLine = line_params(v3((float)fx + 0.5f, (float)fy + 0.5f, (float)fz + 0.5f), l1, l2, &ratio, &dist);
@@ -85,7 +90,7 @@ __device__ __forceinline__ V3 cross3(V3 a, V3 b)
 {
     return v3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
 }
-__device__ __forceinline__ bool in_crystal(V3 pos, V3 p1, V3 p2, float radiusMul)
+__device__ __noinline__ bool in_crystal(V3 pos, V3 p1, V3 p2, float radiusMul)
 {
     float ratio, dist;
     if (!line_params(pos, p1, p2, &ratio, &dist)) return false;
@@ -108,10 +113,46 @@ __device__ __forceinline__ uint8_t random_crystal_block(float rand)
     return r < 1.f ? B_MAGENTA_CRYSTAL : (r < 2.f ? B_CYAN_CRYSTAL : B_GREEN_CRYSTAL);
 }
 
+// PURPLE_MUSHROOM (featurePlacement.hpp:560-640): scale, the halving flag, height, the seven spline points of the stem, the
+// end point of the cap segment and the cap radius are drawn from the PLACEMENT's RNG stream in a fixed order - the reference
+// redoes the 17 draws and the de Casteljau evaluation (70 mix() of vec3) for every voxel of the box. Computed once per
+// (warp, placement) into shared memory by k_fill_features; same operations in the same order, so the same bits.
+// geom[0] scale, [1] halved (0/1), [2] height, [3..23] spline[7], [24..26] cap end, [27] cap radius
+constexpr int kMushroomSplinePoints = 7, kMushroomGeomFloats = 28;
+__device__ __noinline__ void purple_mushroom_geom(uint32_t frngState, float* geom)
+{
+    Minstd frng = Minstd::from_state(frngState);
+    const float scale = fmaf(frng.u01(), 1.2f, 1.f);
+    const bool half = frng.u01() < 0.2f;
+    const float height = fmaf(frng.u01(), 30.f, 25.f);
+    constexpr int NC = 5, NS = kMushroomSplinePoints;
+    V3 ctrl[NC];
+    ctrl[0] = v3(0, 0, 0);
+    for (int i = 1; i < NC; ++i)
+    {
+        const float a = frng.u11(), b = frng.u11(), c = frng.u11();
+        V3 off = v3(a * 6.f, b * 2.f, c * 6.f);
+        if (i == NC - 1) off = off * 0.6f;
+        const float f = (float)i / 4.f;
+        ctrl[i] = v3(fmaf(0.f, f, off.x), fmaf(height, f, off.y), fmaf(0.f, f, off.z));
+    }
+    V3 spline[NS];
+    de_casteljau<NC, NS>(ctrl, spline);
+    const V3 n = normalize3(spline[NS - 1] - spline[NS - 2]);
+    const float l = fmaf(frng.u01(), 1.5f, 3.f);
+    const V3 end = v3(fmaf(n.x, l, spline[NS - 1].x), fmaf(n.y, l, spline[NS - 1].y), fmaf(n.z, l, spline[NS - 1].z));
+    const float radius = fmaf(frng.u01(), 7.f, 12.f) * mixf(0.8f, 1.2f, (height - 33.f) / 40.f);
+    geom[0] = scale; geom[1] = half ? 1.f : 0.f; geom[2] = height;
+    for (int i = 0; i < NS; ++i) { geom[3 + 3 * i] = spline[i].x; geom[4 + 3 * i] = spline[i].y; geom[5 + 3 * i] = spline[i].z; }
+    geom[24] = end.x; geom[25] = end.y; geom[26] = end.z;
+    geom[27] = radius;
+}
+
 // featurePlacement.hpp:147-1107. Returns true and sets *out when the voxel belongs to the feature.
 // frngState: state of the placement's RNG right after seeding, make_rng4(fp.x, fp.y, fp.z, 1293012).x (featurePlacement.hpp:153),
-// computed once per placement by k_prepare_placements instead of once per voxel.
-__device__ MMG_NOISE_INLINE bool place_feature(const FeaturePlacement& fp, int wx, int wy, int wz, uint32_t frngState, uint8_t* out)
+// computed once per placement by k_prepare_placements instead of once per voxel. geom: purple_mushroom_geom() of the placement
+// (read for F_PURPLE_MUSHROOM only).
+__device__ MMG_NOISE_INLINE bool place_feature(const FeaturePlacement& fp, int wx, int wy, int wz, uint32_t frngState, const float* geom, uint8_t* out)
 {
     const int fx = wx - fp.x, fy = wy - fp.y, fz = wz - fp.z;
     V3 pos = v3((float)fx, (float)fy, (float)fz);
@@ -206,7 +247,7 @@ __device__ MMG_NOISE_INLINE bool place_feature(const FeaturePlacement& fp, int w
         if (fx == 0 && fz == 0 && in_range_i(fy, 0, trunk)) { *out = B_ACACIA_WOOD; return true; }
         float angle = frng.u01() * kTwoPi;
         V3 bs = v3(0.f, (float)trunk, 0.f), be = v3(0, 0, 0);
-        sincosf(angle, &be.z, &be.x);
+        pf_sincosf(angle, &be.z, &be.x);
         {
             const float s = fmaf(frng.u01(), 1.5f, 2.f);
             be = v3(fmaf(be.x, s, bs.x), fmaf(be.y, s, bs.y), fmaf(be.z, s, bs.z));
@@ -220,7 +261,7 @@ __device__ MMG_NOISE_INLINE bool place_feature(const FeaturePlacement& fp, int w
         angle = angle + fmaf(frng.u01(), kPi, kPiOverTwo);
         bs = v3(0.f, fmaf(frng.u01(), -0.8f, (float)trunk - 0.8f), 0.f);
         be = v3(0, 0, 0);
-        sincosf(angle, &be.z, &be.x);
+        pf_sincosf(angle, &be.z, &be.x);
         {
             const float s = fmaf(frng.u01(), 1.f, 1.5f);
             be = v3(fmaf(be.x, s, bs.x), fmaf(be.y, s, bs.y), fmaf(be.z, s, bs.z));
@@ -242,7 +283,7 @@ __device__ MMG_NOISE_INLINE bool place_feature(const FeaturePlacement& fp, int w
         const float tr = ratio_of(pos.y, -4.f, height);
         if (saturated(tr))
         {
-            float radius = 2.f / (tr + 2.f) + 0.08f / powf(tr + 0.4f, 3.f);
+            float radius = 2.f / (tr + 2.f) + 0.08f / pf_powf(tr + 0.4f, 3.f);
             radius = fmaf(simplex3<true>((float)wx * 0.1300f, (float)wy * 0.1300f, (float)wz * 0.1300f) * 0.3f,
                           ss_t((tr + -0.6f) / (0.2f - 0.6f)), radius);
             if (hd < radius) { *out = B_REDWOOD_WOOD; return true; }
@@ -289,7 +330,7 @@ __device__ MMG_NOISE_INLINE bool place_feature(const FeaturePlacement& fp, int w
         const float tr = ratio_of(pos.y, -2.f, trunkHeight);
         if (saturated(tr))
         {
-            float radius = fmaf((1.3f + tr) / powf(0.73f + tr, 4.f), 0.5f, 0.5f);
+            float radius = fmaf((1.3f + tr) / pf_powf(0.73f + tr, 4.f), 0.5f, 0.5f);
             radius = radius * fmaf(simplex3<true>((float)wx * 0.1500f, (float)wy * 0.1500f, (float)wz * 0.1500f) * 0.3f,
                                    ss_t((tr + -0.55f) / (0.15f - 0.55f)), 1.f);
             if (td < radius) { *out = B_CYPRESS_WOOD; return true; }
@@ -304,7 +345,7 @@ __device__ MMG_NOISE_INLINE bool place_feature(const FeaturePlacement& fp, int w
             angle = angle + fmaf(frng.u01(), kPi, kPiOverTwo);
             const V3 bs = v3(0.f, branchHeight, 0.f);
             V3 be = v3(0, 0, 0);
-            sincosf(angle, &be.z, &be.x);
+            pf_sincosf(angle, &be.z, &be.x);
             be = be * fmaf(frng.u01(), 1.5f, 4.f);
             be.y = fmaf(frng.u01(), 1.2f, 2.2f);
             be = be * fmaf(ratio_of(branchHeight, 0.f, trunkHeight), -0.3f, 1.f);
@@ -331,7 +372,7 @@ __device__ MMG_NOISE_INLINE bool place_feature(const FeaturePlacement& fp, int w
         const float leavesEnd = fmaf(fmaf(frng.u01(), 1.2f, 4.2f), tm, fh);
         const float ratio = (pos.y - leavesStart) / (leavesEnd - leavesStart);
         if (!in_range_f(ratio, 0.f, 1.f)) return false;
-        const float x = powf(ratio, 0.8f);
+        const float x = pf_powf(ratio, 0.8f);
         const float poly = (((0.5f * x) * x) * x - ((1.5f * x) * x)) + x;
         const float leavesRadius = (5.f * poly) * fmaf(frng.u01(), 0.8f, 2.8f);
         if (len2(pos.x, pos.z) > leavesRadius) return false;
@@ -373,10 +414,10 @@ __device__ MMG_NOISE_INLINE bool place_feature(const FeaturePlacement& fp, int w
     }
     case F_PURPLE_MUSHROOM:
     {
-        const float scale = fmaf(frng.u01(), 1.2f, 1.f);
+        // geom: what the reference derives from the placement's RNG stream for every voxel again (purple_mushroom_geom)
+        const float scale = geom[0], height = geom[2];
         pos = pos * scale;
-        if (frng.u01() < 0.2f) pos = pos * 0.5f;
-        const float height = fmaf(frng.u01(), 30.f, 25.f);
+        if (geom[1] != 0.f) pos = pos * 0.5f;
         {
             const float x2 = pos.x * pos.x, z2 = pos.z * pos.z;     // shared squares: not fused
             const float dy = pos.y - height;
@@ -384,34 +425,13 @@ __device__ MMG_NOISE_INLINE bool place_feature(const FeaturePlacement& fp, int w
                 (sqrtf(x2 + z2) > 8.f && (pos.y < height + -12.f || sqrtf(z2 + fmaf(dy, dy, x2)) > 35.f)))
                 return false;
         }
-        constexpr int NC = 5, NS = 7;
-        V3 ctrl[NC];
-        ctrl[0] = v3(0, 0, 0);
-        for (int i = 1; i < NC; ++i)
-        {
-            const float a = frng.u11(), b = frng.u11(), c = frng.u11();
-            V3 off = v3(a * 6.f, b * 2.f, c * 6.f);
-            if (i == NC - 1) off = off * 0.6f;
-            const float f = (float)i / 4.f;
-            ctrl[i] = v3(fmaf(0.f, f, off.x), fmaf(height, f, off.y), fmaf(0.f, f, off.z));
-        }
-        V3 spline[NS];
-        de_casteljau<NC, NS>(ctrl, spline);
+        constexpr int NS = kMushroomSplinePoints;
+#pragma unroll 1
         for (int i = 0; i < NS; ++i)
         {
-            const V3 p1 = spline[i];
-            V3 p2;
-            if (i < NS - 1)
-            {
-                p2 = spline[i + 1];
-                if (pos.y < p1.y - 3.f || pos.y > p2.y + 3.f) continue;
-            }
-            else
-            {
-                const V3 n = normalize3(p1 - spline[i - 1]);
-                const float l = fmaf(frng.u01(), 1.5f, 3.f);
-                p2 = v3(fmaf(n.x, l, p1.x), fmaf(n.y, l, p1.y), fmaf(n.z, l, p1.z));
-            }
+            const V3 p1 = v3(geom[3 + 3 * i], geom[4 + 3 * i], geom[5 + 3 * i]);
+            const V3 p2 = v3(geom[6 + 3 * i], geom[7 + 3 * i], geom[8 + 3 * i]);     // i = NS - 1: the cap's end point
+            if (i < NS - 1 && (pos.y < p1.y - 3.f || pos.y > p2.y + 3.f)) continue;
             float ratio, dist;
             const bool inRatio = line_params(pos, p1, p2, &ratio, &dist);
             float radius;
@@ -425,7 +445,7 @@ __device__ MMG_NOISE_INLINE bool place_feature(const FeaturePlacement& fp, int w
             }
             else
             {
-                radius = fmaf(frng.u01(), 7.f, 12.f) * mixf(0.8f, 1.2f, (height - 33.f) / 40.f);
+                radius = geom[27];
                 block = (dist < radius - 1.8f && ratio < 0.5f && scale < 1.4f) ? B_MUSHROOM_UNDERSIDE : B_PURPLE_MUSHROOM_CAP;
             }
             if ((inRatio && dist <= radius) || (i < NS - 1 && ratio < 0.f && len3(p1 - pos) < radius) ||
@@ -457,7 +477,7 @@ __device__ MMG_NOISE_INLINE bool place_feature(const FeaturePlacement& fp, int w
         {
             const float angle = startAngle + ((float)i * kTwoPi) * 0.2f;
             float s, co;
-            sincosf(-angle, &s, &co);
+            pf_sincosf(-angle, &s, &co);
             V3 pp = v3(fmaf(pos.x, co, pos.z * s), pos.y - 3.2f, fmaf(pos.z, co, -(pos.x * s)));
             pp.y = pp.y - (float)(i % 2) * 0.53f;
             pp.y = fmaf(fminf(fmaxf((fabsf(pp.x - 3.f) - 1.5f) / 1.5f, 0.f), 1.f), 1.3f, pp.y);
@@ -489,7 +509,7 @@ __device__ MMG_NOISE_INLINE bool place_feature(const FeaturePlacement& fp, int w
             const float angle = kTwoPi * frng.u01();
             const V3 bs = v3(0.f, branchHeight, 0.f);
             V3 be = v3(0, 0, 0);
-            sincosf(-angle, &be.z, &be.x);
+            pf_sincosf(-angle, &be.z, &be.x);
             {
                 const float s = fmaf(frng.u01(), 1.5f, 3.f);
                 be = v3(fmaf(be.x, s, bs.x), fmaf(be.y, s, bs.y), fmaf(be.z, s, bs.z));
@@ -610,7 +630,7 @@ __device__ MMG_NOISE_INLINE bool place_feature(const FeaturePlacement& fp, int w
         {
             angle = angle + fmaf(frng.u01(), kPi, kPiOverTwo);
             V3 s = v3(0, 0, 0);
-            sincosf(angle, &s.z, &s.x);
+            pf_sincosf(angle, &s.z, &s.x);
             V3 e = s;
             s = s * 3.f;
             e = e * fmaf(frng.u01(), 3.f, 6.f);

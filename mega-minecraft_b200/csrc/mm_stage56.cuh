@@ -668,7 +668,10 @@ __global__ void __launch_bounds__(256) k_prepare_placements(const int* __restric
 constexpr int kSlab = 32;                  // voxels of a column per CTA of k_fill_features
 constexpr int kSlabPitch = 257;            // shBest[yy][col], padded: lanes that differ in yy hit different banks
 constexpr unsigned kNoBest = 0xffffffffu;
-constexpr int kBigBox = 2048, kMaxBig = 96;   // (column, y) pairs above which a placement is rasterised by the whole CTA
+#ifndef MMG_BIGBOX
+#define MMG_BIGBOX 2048
+#endif
+constexpr int kBigBox = MMG_BIGBOX, kMaxBig = 96;   // (column, y) pairs above which a placement is rasterised by the whole CTA
 // ceil(2^32 / n), n = 2..32 ([0], [1] unused)
 __constant__ const unsigned c_recip32[33] = {0, 0, 0x80000000u, 0x55555556u, 0x40000000u, 0x33333334u, 0x2aaaaaabu, 0x24924925u, 0x20000000u,
     0x1c71c71du, 0x1999999au, 0x1745d175u, 0x15555556u, 0x13b13b14u, 0x12492493u, 0x11111112u, 0x10000000u, 0x0f0f0f10u, 0x0e38e38fu,
@@ -694,6 +697,7 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
     __shared__ __align__(16) uint8_t shBlk[256 * kSlab];     // [col][yy]
     __shared__ int shNext, shNumBig;
     __shared__ unsigned short shBig[kMaxBig];
+    __shared__ float shGeom[8 * kMushroomGeomFloats];        // per warp: purple_mushroom_geom of the placement being rasterised
     __shared__ unsigned short shQueue[8 * 64];               // per warp: pairs that passed the filter, waiting for a full warp
     const int slab = blockIdx.x % 12, li = blockIdx.x / 12;
     const int chunk = fillList ? fillList[li] : li;
@@ -726,6 +730,7 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
     // surviving pairs onto the warp's queue, and the rasteriser runs on full warps popped from that queue - a cave
     // feature's box is mostly rock, so without the queue 3 or 4 lanes of 32 reach the rasteriser.
     unsigned short* wq = shQueue + (t >> 5) * 64;
+    float* wgeom = shGeom + (t >> 5) * kMushroomGeomFloats;
     auto raster = [&](int e, int first, int step, bool countOnly, int* totalOut) -> bool {
         const bool cave = e >= nF;
         const Prep k = cave ? pc[e - nF] : pf[e];
@@ -742,6 +747,11 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
         CaveFeaturePlacement cp;
         if (cave) cp = cf[e - nF];
         else fp = f[e];
+        if (!cave && k.feature == F_PURPLE_MUSHROOM)
+        {
+            purple_mushroom_geom(k.seed, wgeom);      // every lane writes the same values
+            __syncwarp();
+        }
 #ifdef MMG_FEATURE_STATS
         const long long statT0 = clock64();
         const int statSlot = (cave ? 32 : 0) + k.feature;
@@ -782,7 +792,7 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
                 {
                     const int col = code >> 5, yy = code & 31, x = col & 15, z = col >> 4, y = y0 + yy;
                     uint8_t fb = 0;
-                    const bool hit = cave ? place_cave_feature(cp, o.x + x, y, o.y + z, k.seed, &fb) : place_feature(fp, o.x + x, y, o.y + z, k.seed, &fb);
+                    const bool hit = cave ? place_cave_feature(cp, o.x + x, y, o.y + z, k.seed, &fb) : place_feature(fp, o.x + x, y, o.y + z, k.seed, wgeom, &fb);
                     if (hit) atomicMin(&shBest[yy * kSlabPitch + col], key | fb);
 #ifdef MMG_FEATURE_STATS
                     atomicAdd(&g_featStats[statSlot][2], 1ull);
