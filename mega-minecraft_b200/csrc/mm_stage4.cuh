@@ -13,6 +13,11 @@
 
 namespace mmg {
 
+#ifdef MMG_FEATURE_STATS
+// developer build: voxels whose "huge caves" term was proved 0 but is not (must stay 0); voxels evaluated without / with proof
+__device__ unsigned long long g_hugeMismatch, g_hugeVoxels[2];
+#endif
+
 // ---------------------------------------------------------------- cave biome (biomeFuncs.hpp:135-220)
 struct CaveBiomeNoise { float v[4]; };   // none, shallow, warped, rocky
 
@@ -189,7 +194,10 @@ __device__ __forceinline__ float special_cave_noise_cached(float px, float py, f
 
 // chunk.cu:755-810, first half: everything up to the cave-noise threshold. Returns 0 = solid, 1 = air,
 // 2 = undecided: the warped specialCaveNoise at (*px, *py, *pz) has to be compared with *thr.
-__device__ __forceinline__ int cave_threshold(int wx, int y, int wz, float maxHeight, float obw, float* thrOut, float* px, float* py, float* pz)
+//
+// hugeZero: the caller has proved that the "huge caves" term is exactly 0 at this voxel (huge_zero_mask below); its four
+// simplex3 are then skipped: fma(0, 1.4, 1) = 1 and thr * 1 = thr, the same bits.
+__device__ __forceinline__ int cave_threshold(int wx, int y, int wz, float maxHeight, float obw, bool hugeZero, float* thrOut, float* px, float* py, float* pz)
 {
     if (y == 0) return 0;
     const int hi = (int)maxHeight;
@@ -201,9 +209,20 @@ __device__ __forceinline__ int cave_threshold(int wx, int y, int wz, float maxHe
     // topRatio is exactly 0 from y = 142 - 50 obw upwards; the threshold below is (finite * topRatio) * finite = 0 there and
     // the test `thr > 0.04` fails whatever the two fbm3<4> say (8 simplex3 the reference evaluates for every such voxel)
     if (topRatio == 0.f) return 0;
+#ifdef MMG_FEATURE_STATS
+    const bool hugeCheck = hugeZero;      // developer build: evaluate the term anyway and count voxels where the proof was wrong
+    hugeZero = false;
+    atomicAdd(&g_hugeVoxels[hugeCheck ? 1 : 0], 1ull);
+#endif
     float thr = fmaf(fbm3<4>(npx * 4.f, npy * 4.f, npz * 4.f), 0.12f, 0.24f);
-    const float huge = ss_t((fbm3<4>(npx * 0.0700f, npy * 0.0700f, npz * 0.0700f) + -0.2f) / (0.4f - 0.2f));
-    thr = thr * fmaf(huge, 1.4f, 1.f);
+    if (!hugeZero)
+    {
+        const float huge = ss_t((fbm3<4>(npx * 0.0700f, npy * 0.0700f, npz * 0.0700f) + -0.2f) / (0.4f - 0.2f));
+#ifdef MMG_FEATURE_STATS
+        if (hugeCheck && huge != 0.f) atomicAdd(&g_hugeMismatch, 1ull);
+#endif
+        thr = thr * fmaf(huge, 1.4f, 1.f);
+    }
     thr = (fmaf(bottomRatio, 0.7f, 0.3f) * topRatio) * thr;
     // the reference always evaluates the warped specialCaveNoise (15 simplex + 27 hashed cells) and then
     // tests `thr > 0.04 && caveNoise < thr` (chunk.cu:776-783); where the threshold test alone fails
@@ -218,7 +237,32 @@ __device__ __forceinline__ int cave_threshold(int wx, int y, int wz, float maxHe
     return 2;
 }
 
-struct CaveColumn { float obw, ravTop, ravDepth; int ravActive; };
+// The "huge caves" term of the threshold, smoothstep(0.2, 0.4, fbm3<4>(pos * 0.00035)), is exactly 0 wherever the fbm is
+// <= 0.2 - most of the world - yet the reference pays its four simplex3 at every voxel. The fbm is Lipschitz: one octave is
+// 42 * simplex3_raw, whose gradient norm stays below 7.6 (20 M finite-difference samples of the oracle's restatement;
+// kSimplex3Lipschitz = 10 is used), so along y the fbm moves by at most sum_i 2^-(i+1) * 2^i * 0.00035 * 10 = 0.007 per
+// voxel. One sample at the middle of each 16-voxel run (y = 16 s + 8, s = 0..8: every voxel the threshold is evaluated
+// for has y < 142) that is <= 0.2 - 8 * 0.007 - 0.004 (rounding, sample position) proves huge == 0 for the whole run.
+// Bit s of the mask = proved for y in [16 s, 16 s + 16). Validated over the 256x256-chunk world by the census build
+// (-DMMG_FEATURE_STATS evaluates the term anyway and counts disagreements: none) and by the unchanged world hash.
+constexpr float kSimplex3Lipschitz = 10.f;
+constexpr int kHugeRun = 16, kHugeSamples = 9;
+__device__ __forceinline__ unsigned huge_zero_mask(int wx, int wz)
+{
+    constexpr float perVoxel = 4.f * 0.5f * (0.0050f * 0.0700f) * kSimplex3Lipschitz;
+    constexpr float limit = 0.2f - (kHugeRun / 2) * perVoxel - 0.004f;
+    const float npx = (float)wx * 0.0050f, npz = (float)wz * 0.0050f;
+    unsigned mask = 0u;
+#pragma unroll 1
+    for (int s = 0; s < kHugeSamples; ++s)
+    {
+        const float npy = (float)(kHugeRun * s + kHugeRun / 2) * 0.0050f;
+        if (fbm3<4>(npx * 0.0700f, npy * 0.0700f, npz * 0.0700f) <= limit) mask |= 1u << s;
+    }
+    return mask;
+}
+
+struct CaveColumn { float obw, ravTop, ravDepth; int ravActive; unsigned hugeZeroMask; };
 
 __global__ void __launch_bounds__(256) k_cave_columns(const int* __restrict__ chunkList, const int2* __restrict__ origins,
                                                       const float* __restrict__ biomeWeights, CaveColumn* __restrict__ cols)
@@ -234,6 +278,7 @@ __global__ void __launch_bounds__(256) k_cave_columns(const int* __restrict__ ch
     const Ravine r = ravine_column(o.x + (idx & 15), o.y + (idx >> 4), obw);
     CaveColumn c;
     c.obw = obw; c.ravTop = r.top; c.ravDepth = r.depth; c.ravActive = r.active ? 1 : 0;
+    c.hugeZeroMask = huge_zero_mask(o.x + (idx & 15), o.y + (idx >> 4));
     cols[(size_t)li * 256 + idx] = c;
 }
 
@@ -269,7 +314,8 @@ __global__ void __launch_bounds__(128, MMG_CAVES_MINBLOCKS) k_caves(const int* _
         }
         const int y = tid + 128 * k;
         float thr = 0.f, px = 0.f, py = 0.f, pz = 0.f;
-        const int st = cave_threshold(wx, y, wz, maxHeight, cc.obw, &thr, &px, &py, &pz);
+        const bool hugeZero = y < kHugeRun * kHugeSamples && ((cc.hugeZeroMask >> (y / kHugeRun)) & 1u);
+        const int st = cave_threshold(wx, y, wz, maxHeight, cc.obw, hugeZero, &thr, &px, &py, &pz);
         // cells [box, box + kCaveBox)^3 cover the 3x3x3 neighbourhoods of (nearly) all undecided voxels. (Filling
         // the table costs 5 hashes per thread; even for a single undecided voxel that is fewer warp instructions
         // than its 81 hashes computed in place on one lane - measured.)

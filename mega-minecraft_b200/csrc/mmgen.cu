@@ -1170,4 +1170,12 @@ extern "C" int mmgen_debug_feature_stats(unsigned long long* out)
     MMG_CUDA(cudaMemcpyToSymbol(g_featStats, zero, sizeof(zero)));
     return 0;
 }
+// out[0] = voxels where huge_zero_mask's proof was wrong (must be 0), out[1] / out[2] = threshold voxels without / with proof
+extern "C" int mmgen_debug_huge_stats(unsigned long long* out)
+{
+    MMG_CUDA(cudaDeviceSynchronize());
+    MMG_CUDA(cudaMemcpyFromSymbol(out, g_hugeMismatch, sizeof(unsigned long long)));
+    MMG_CUDA(cudaMemcpyFromSymbol(out + 1, g_hugeVoxels, 2 * sizeof(unsigned long long)));
+    return 0;
+}
 #endif

@@ -32,3 +32,7 @@ for i in range(64):
 print("%-30s %8s %12s %12s %12s %8s" % ("type", "cycles%", "pairs", "rasterised", "hits", "cyc/pair"))
 for c, n, a, b, h in sorted(rows, reverse=True):
     print("%-30s %7.1f%% %12d %12d %12d %8.1f" % (n, 100 * c / tot, a, b, h, c / max(a, 1) * 32))
+hs = np.zeros(3, np.uint64)
+gen.L.mmgen_debug_huge_stats(hs.ctypes.data_as(ctypes.c_void_p))
+print("huge-caves term: proved zero for %d of %d threshold voxels (%.1f %%), proof wrong for %d (must be 0)"
+      % (hs[2], hs[1] + hs[2], 100.0 * float(hs[2]) / max(float(hs[1] + hs[2]), 1.0), hs[0]))
