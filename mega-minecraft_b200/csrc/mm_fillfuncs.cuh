@@ -295,14 +295,6 @@ __device__ __forceinline__ bool rock_is_bulk(int bottomDepth, int topDepth)
 {
     return (bottomDepth < 0 || bottomDepth > 6) && (topDepth < 0 || topDepth > 6);
 }
-__device__ __forceinline__ uint8_t finish_bulk_rock_block(uint8_t block, int wx, int y, int wz, float height, int bottomDepth, int topDepth)
-{
-    bool lush = false;
-    if (cave_biome_is_crystal(wx, y, wz, height, 190249401))
-        cave_biome_post_process(&block, CB_CRYSTAL_CAVES, wx, y, wz, bottomDepth, topDepth, &lush);
-    return block;
-}
-
 // Queue record of a rock voxel: x = chunk, y = voxel index (17 bits) | rock kind (2) | bottom depth (6) | top depth (6).
 // The depths only matter as "== 0" (top block) and "in [0, threshold]" with threshold = 1.5 + 4.5 simplex3 (biomeFuncs.hpp:653-657);
 // |simplex3| <= 42 * 4 * max_r((0.6 - r^2)^4 r) * |grad| < 42 * 4 * 0.0209 * 3.2 < 11.3, so threshold < 53: every depth that is

@@ -481,36 +481,84 @@ __global__ void __launch_bounds__(kFillSeg, 12) k_fill_terrain(const int* __rest
 
 // getCaveBiome + caveBiomeBlockPostProcess for the queued rock voxels, one per thread on dense warps. In k_fill_terrain
 // the same work ran on whatever lanes of a 32-voxel column run happened to be rock below the surface (22 of 32 on average).
-// Near voxels take the full path; bulk voxels (about 4 of 5) only ask whether the biome is CRYSTAL_CAVES, which skips one
-// simplex3 always and up to twelve simplex2 (cave_biome_is_crystal). The bulk region starts on a warp boundary.
+// Near voxels take the full path. Bulk voxels (about 4 of 5) only ask whether the biome is CRYSTAL_CAVES, which skips one
+// simplex3 always and up to twelve simplex2 (cave_biome_is_crystal) - and only where CRYSTAL_CAVES would change the block
+// at all: its rule (cave_biome_post_process) turns the voxel into QUARTZ where one simplex3 is < -0.25 and otherwise STONE /
+// DEEPSLATE into their cobbled form with probability 0.5 / 0.4 by a position hash; neither depends on the biome noise, so
+// both are decided first (1 simplex3 + 1 sin) and the 10+ simplex3 of the biome question are spent on the voxels that would
+// change (about half), compacted through a per-warp queue so that they run on full warps. The bulk region starts on a
+// warp boundary.
 __global__ void __launch_bounds__(128, MMG_ROCK_MINBLOCKS) k_fill_rock(const int2* __restrict__ origins, const float* __restrict__ heightfield,
                                                       const uint2* __restrict__ rockQueue, int rockQueueCap, uint8_t* __restrict__ blocks,
                                                       uint2* __restrict__ lushQueue, int* __restrict__ counters)
 {
+    __shared__ uint2 shPending[4 * 64];      // per warp: bulk voxels CRYSTAL_CAVES would change, waiting for a full warp
     const int nearCap = rock_near_cap(rockQueueCap), bulkCap = rockQueueCap - nearCap;
     const int nNear = min(counters[2], nearCap), nBulk = min(counters[3], bulkCap);
     const int nearPad = (nNear + 31) & ~31, n = nearPad + nBulk;
     if (blockIdx.x * blockDim.x >= n) return;
     noise_tab_stage();
     const int lane = threadIdx.x & 31;
+    uint2* wq = shPending + (threadIdx.x >> 5) * 64;
+    int qn = 0;
+    // pops up to 32 pending bulk voxels: x = chunk, y = voxel | kind << 17 | (quartz ? 1 << 19 : 0)
+    auto drain = [&]() {
+        const int cnt = min(qn, 32);
+        qn -= cnt;
+        const uint2 e = wq[qn + (lane < cnt ? lane : 0)];
+        __syncwarp();
+        if (lane < cnt)
+        {
+            const int chunk = (int)e.x, voxel = (int)(e.y & 0x1ffffu), idx = voxel / 384, y = voxel - idx * 384;
+            const int2 o = origins[chunk];
+            if (cave_biome_is_crystal(o.x + (idx & 15), y, o.y + (idx >> 4), heightfield[(size_t)chunk * 256 + idx], 190249401))
+                blocks[(size_t)chunk * 98304 + voxel] = ((e.y >> 19) & 1u) ? B_QUARTZ : ((((e.y >> 17) & 3u) == 0u) ? B_COBBLESTONE : B_COBBLED_DEEPSLATE);
+        }
+    };
     for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x)
     {
         const int i = i0 + threadIdx.x;
-        const bool bulk = i >= nearPad;
+        const bool bulk = i >= nearPad;      // warp-uniform
+        if (bulk)
+        {
+            bool change = false;
+            uint2 e = make_uint2(0u, 0u);
+            if (i < n)
+            {
+                e = rockQueue[nearCap + (i - nearPad)];
+                const int chunk = (int)e.x, voxel = (int)(e.y & 0x1ffffu), idx = voxel / 384, y = voxel - idx * 384;
+                const unsigned kind = (e.y >> 17) & 3u;      // 0 STONE, 1 DEEPSLATE, 2 BLACKSTONE (pack_rock)
+                const int2 o = origins[chunk];
+                const int wx = o.x + (idx & 15), wz = o.y + (idx >> 4);
+                // cave_biome_post_process, CB_CRYSTAL_CAVES
+                const float s = (float)(wx + wz);
+                const float quartz = simplex3<true>((float)(wx + y) * 0.05f, (float)(wz + 5819323) * 0.05f, (s + s) * 0.05f);
+                const bool isQuartz = quartz < -0.25f;
+                change = isQuartz;
+                if (!isQuartz && kind != 2u)
+                    change = hash_fract(fmaf((float)wz, 640.88f, fmaf((float)wx, 238.68f, (float)y * 491.28f))) < (kind == 0u ? 0.5f : 0.4f);
+                e.y = (e.y & 0x7ffffu) | (isQuartz ? 1u << 19 : 0u);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, change);
+            if (change) wq[qn + __popc(m & ((1u << lane) - 1u))] = e;
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 32) drain();
+            continue;
+        }
         bool lush = false;
         int chunk = 0, voxel = 0, wx = 0, wz = 0, y = 0;
-        if (bulk ? i < n : i < nNear)
+        if (i < nNear)
         {
             uint8_t rockBlock;
             int bd, td;
-            unpack_rock(rockQueue[bulk ? nearCap + (i - nearPad) : i], &chunk, &voxel, &rockBlock, &bd, &td);
+            unpack_rock(rockQueue[i], &chunk, &voxel, &rockBlock, &bd, &td);
             const int idx = voxel / 384;
             y = voxel - idx * 384;
             const int2 o = origins[chunk];
             wx = o.x + (idx & 15); wz = o.y + (idx >> 4);
             const float height = heightfield[(size_t)chunk * 256 + idx];
-            const uint8_t block = bulk ? finish_bulk_rock_block(rockBlock, wx, y, wz, height, bd, td)
-                                       : finish_rock_block(rockBlock, wx, y, wz, height, bd, td, &lush);
+            const uint8_t block = finish_rock_block(rockBlock, wx, y, wz, height, bd, td, &lush);
             if (block != rockBlock) blocks[(size_t)chunk * 98304 + voxel] = block;
         }
         // warp-aggregated append of the voxels that need the lush-cave clay / moss decision
@@ -529,6 +577,7 @@ __global__ void __launch_bounds__(128, MMG_ROCK_MINBLOCKS) k_fill_rock(const int
             }
         }
     }
+    if (qn > 0) drain();
 }
 
 __global__ void __launch_bounds__(128) k_fill_lush(const int2* __restrict__ origins, const uint2* __restrict__ lushQueue,
