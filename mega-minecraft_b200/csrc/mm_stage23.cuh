@@ -133,28 +133,46 @@ __global__ void k_zone_gather(const float* __restrict__ layers, const float* __r
 // zone's 12 planes; they swap in lockstep for all zones. A zone that has converged is a fixed point of
 // the sweep, so sweeping it again (while other zones of the batch still move) changes nothing.
 //
-// zoneChanged[3][kMaxZoneBatch]: did sweep n change anything in zone z? Sweep n reads row (n-1)%3, sets row n%3 and clears
-// row (n+1)%3. If the previous sweep left a zone untouched, its output planes already equal its input planes (outS = sIn,
-// accumOut = accumIn for every cell), the zone is at a fixed point, and this sweep would write back what pOut already holds:
-// the CTA returns at once. `force` disables the shortcut for the first two sweeps of a layer (the first sweep folds the
-// carried heights into its comparison, so "nothing flagged" does not imply "planes equal" there).
+// tileChanged[3][kMaxZoneBatch][144]: did sweep n change a cell of 32x32 tile t of zone z? Sweep n reads row (n-1)%3, sets
+// row n%3 and clears row (n+1)%3. A tile's result depends on the 34x34 cells around it, i.e. on its 3x3 tile neighbourhood.
+// If the previous sweep changed none of those nine tiles (because it found nothing to change there, or because it was
+// itself skipped), their input and output planes are equal (outS = sIn, accumOut = accumIn for every cell), this sweep
+// would recompute what the previous one found and write back what pOut already holds: the CTA returns at once. Erosion
+// activity is local (steep slopes), so most tiles of a zone go quiet long before its last one does. `force` disables the
+// shortcut for the first two sweeps of a layer (the first sweep folds the carried heights into its comparison, so
+// "nothing flagged" does not imply "planes equal" there).
 constexpr int kMaxZoneBatch = 32;
+constexpr int kZoneTiles = 144;      // 12 x 12 tiles of 32 x 32 cells
+// (A persistent variant - two CTAs per SM walking the tiles - was measured and is slower: 54.7 vs 39.4 ms per 256x256 world;
+// with one tile per CTA the block scheduler overlaps the staging of one tile with the arithmetic of others.)
 __global__ void __launch_bounds__(1024) k_erode_sweep(float* __restrict__ zones, int pIn, int pOut, int pUp, int pAccIn, int pAccOut,
-                                                      float rep, int isFirst, int* __restrict__ changedFlag, int* __restrict__ zoneChanged,
+                                                      float rep, int isFirst, int* __restrict__ changedFlag, int* __restrict__ tileChanged,
                                                       int sweepNo, int force)
 {
     __shared__ float shS[34 * 34];
     __shared__ float shE[34 * 34];
-    const int rowPrev = ((sweepNo + 2) % 3) * kMaxZoneBatch, rowCur = (sweepNo % 3) * kMaxZoneBatch, rowNext = ((sweepNo + 1) % 3) * kMaxZoneBatch;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) zoneChanged[rowNext + blockIdx.z] = 0;
-    if (!force && zoneChanged[rowPrev + blockIdx.z] == 0) return;
+    const int rowSize = kMaxZoneBatch * kZoneTiles;
+    const int* rowPrev = tileChanged + ((sweepNo + 2) % 3) * rowSize + blockIdx.z * kZoneTiles;
+    int* rowCur = tileChanged + (sweepNo % 3) * rowSize + blockIdx.z * kZoneTiles;
+    int* rowNext = tileChanged + ((sweepNo + 1) % 3) * rowSize + blockIdx.z * kZoneTiles;
+    const int tile = blockIdx.x + 12 * blockIdx.y;
+    const int lx = threadIdx.x, lz = threadIdx.y, lid = lx + 32 * lz;
+    {
+        if (lid == 9) rowNext[tile] = 0;
+        int moved = force;
+        if (!force && lid < 9)
+        {
+            const int tx = (int)blockIdx.x + lid % 3 - 1, tz = (int)blockIdx.y + lid / 3 - 1;
+            if (tx >= 0 && tx < 12 && tz >= 0 && tz < 12) moved = rowPrev[tx + 12 * tz];
+        }
+        if (!__syncthreads_or(moved)) return;
+    }
     float* zone = zones + (size_t)blockIdx.z * kZonePlanes * kErosionCols;
     const float* sIn = zone + (size_t)pIn * kErosionCols;
     float* sOut = zone + (size_t)pOut * kErosionCols;
     const float* eUp = zone + (size_t)pUp * kErosionCols;
     const float* accumIn = zone + (size_t)pAccIn * kErosionCols;
     float* accumOut = zone + (size_t)pAccOut * kErosionCols;
-    const int lx = threadIdx.x, lz = threadIdx.y, lid = lx + 32 * lz;
     const int bx0 = blockIdx.x * 32, bz0 = blockIdx.y * 32;
     for (int t = lid; t < 34 * 34; t += 1024)
     {
@@ -190,7 +208,7 @@ __global__ void __launch_bounds__(1024) k_erode_sweep(float* __restrict__ zones,
         {
             acc = (ns - s0) + acc;
             *changedFlag = 1;
-            zoneChanged[rowCur + blockIdx.z] = 1;
+            rowCur[tile] = 1;
         }
     }
     sOut[i] = outS;

@@ -15,7 +15,7 @@ namespace mmg {
 
 #ifdef MMG_FEATURE_STATS
 // developer build: voxels whose "huge caves" term was proved 0 but is not (must stay 0); voxels evaluated without / with proof
-__device__ unsigned long long g_hugeMismatch, g_hugeVoxels[2];
+__device__ unsigned long long g_hugeMismatch, g_hugeVoxels[2], g_caveWarped;      // g_caveWarped: voxels that evaluated the warped specialCaveNoise
 #endif
 
 // ---------------------------------------------------------------- cave biome (biomeFuncs.hpp:135-220)
@@ -342,6 +342,9 @@ __global__ void __launch_bounds__(128, MMG_CAVES_MINBLOCKS) k_caves(const int* _
         }
         __syncthreads();
         bool air = st == 1;
+#ifdef MMG_FEATURE_STATS
+        if (st == 2) atomicAdd(&g_caveWarped, 1ull);
+#endif
         if (st == 2) air = special_cave_noise_cached(px, py, pz, bx, by, bz, shJit) < thr;
         if (st != 1 && !air) air = rav.active && (rav.top - rav.depth) < (float)y && y != 0;   // chunk.cu:785-808
         const unsigned int bits = __ballot_sync(0xffffffffu, !air);

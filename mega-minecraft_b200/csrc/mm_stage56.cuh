@@ -717,10 +717,11 @@ __global__ void __launch_bounds__(256) k_prepare_placements(const int* __restric
 constexpr int kSlab = 32;                  // voxels of a column per CTA of k_fill_features
 constexpr int kSlabPitch = 257;            // shBest[yy][col], padded: lanes that differ in yy hit different banks
 constexpr unsigned kNoBest = 0xffffffffu;
-#ifndef MMG_BIGBOX
-#define MMG_BIGBOX 2048
+constexpr int kRound = 1024;               // placements scanned per round (the round's active list lives in shared memory)
+#ifndef MMG_TILE
+#define MMG_TILE 512
 #endif
-constexpr int kBigBox = MMG_BIGBOX, kMaxBig = 96;   // (column, y) pairs above which a placement is rasterised by the whole CTA
+constexpr int kTile = MMG_TILE;            // (column, y) pairs of one unit of work
 // ceil(2^32 / n), n = 2..32 ([0], [1] unused)
 __constant__ const unsigned c_recip32[33] = {0, 0, 0x80000000u, 0x55555556u, 0x40000000u, 0x33333334u, 0x2aaaaaabu, 0x24924925u, 0x20000000u,
     0x1c71c71du, 0x1999999au, 0x1745d175u, 0x15555556u, 0x13b13b14u, 0x12492493u, 0x11111112u, 0x10000000u, 0x0f0f0f10u, 0x0e38e38fu,
@@ -728,14 +729,21 @@ __constant__ const unsigned c_recip32[33] = {0, 0, 0x80000000u, 0x55555556u, 0x4
     0x08d3dcb1u, 0x08888889u, 0x08421085u, 0x08000000u};
 __constant__ const unsigned c_recip16[17] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096};
 
-// Placement scan of one 32-voxel slab of a chunk (12 slabs per chunk). Work is distributed by PLACEMENT, not
-// by voxel: the warps of the CTA take the chunk's placements round-robin, and a warp spreads its lanes over
-// the (column, y) pairs of the placement's box clipped to this chunk and slab - so the lanes of a warp
-// rasterise the same feature on different voxels instead of one voxel testing hundreds of candidates (a
-// column of a crystal-cave chunk is within reach of ~400 stormlight spheres). The reference's rule "the first
-// placement in list order that contains the voxel wins, surface list before cave list" (chunk.cu:1444-1500)
-// becomes an atomicMin over (list position << 8 | block) per voxel; a voxel already claimed by an earlier
-// placement is not tested again.
+// Placement scan of one 32-voxel slab of a chunk (12 slabs per chunk). Work is distributed by PLACEMENT, not by voxel: a
+// placement's box clipped to this chunk and slab is a list of (column, y) pairs, cut into tiles of kTile pairs, and the
+// warps of the CTA pull tiles from a shared counter - so the lanes of a warp rasterise the same feature on different voxels
+// instead of one voxel testing hundreds of candidates (a column of a crystal-cave chunk is within reach of ~400 stormlight
+// spheres), and a mushroom's 8000 pairs are shared by all warps while a vine's 15 occupy one warp for one step.
+//   round (kRound placements): every thread tests the Prep records of its placements against the slab; the ones that touch
+//     it enter the round's active list with their first tile number (one packed shared-memory atomic hands out both, so
+//     tile numbers grow with the slot and a tile finds its placement by binary search);
+//   tile: a cheap filter (voxel already claimed by an earlier placement / solid and the placement may not replace blocks)
+//     pushes the surviving pairs onto the warp's queue and the rasteriser runs on full warps popped from it - a cave
+//     feature's box is mostly rock, so without the queue 3 or 4 lanes of 32 reach the rasteriser. The queue is kept while
+//     the warp's next tile belongs to the same placement.
+// The reference's rule "the first placement in list order that contains the voxel wins, surface list before cave list"
+// (chunk.cu:1444-1500) becomes an atomicMin over (list position << 8 | block) per voxel, so the order in which tiles are
+// processed does not matter.
 __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict__ fillList, const int2* __restrict__ origins,
                                                           const FeaturePlacement* __restrict__ gF, const CaveFeaturePlacement* __restrict__ gCF,
                                                           const Prep* __restrict__ prepF, const Prep* __restrict__ prepC,
@@ -743,9 +751,11 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
                                                           uint8_t* __restrict__ blocks)
 {
     __shared__ unsigned shBest[kSlab * kSlabPitch];
-    __shared__ __align__(16) uint8_t shBlk[256 * kSlab];     // [col][yy]
-    __shared__ int shNext, shNumBig;
-    __shared__ unsigned short shBig[kMaxBig];
+    __shared__ unsigned shAir[256];                          // per column: bit yy = the terrain block is AIR
+    __shared__ unsigned shActBase[kRound];                   // active list of the round: first tile number ...
+    __shared__ unsigned short shActE[kRound];                // ... and list position of the placement
+    __shared__ unsigned shPacked;                            // tiles handed out << 11 | active placements
+    __shared__ int shNextTile;
     __shared__ float shGeom[8 * kMushroomGeomFloats];        // per warp: purple_mushroom_geom of the placement being rasterised
     __shared__ unsigned short shQueue[8 * 64];               // per warp: pairs that passed the filter, waiting for a full warp
     const int slab = blockIdx.x % 12, li = blockIdx.x / 12;
@@ -756,156 +766,156 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
     const bool segC = gi.nCF > 0 && y0 <= gi.cfb1 && y1 >= gi.cfb0;
     if (!segF && !segC) return;
     const int2 o = origins[chunk];
-    // thread t stages column t of the slab (32 consecutive block IDs, 16-byte aligned)
+    // thread t owns column t of the slab (32 consecutive block IDs, 16-byte aligned)
     uint8_t* colPtr = blocks + (size_t)chunk * 98304 + (size_t)t * 384 + y0;
     {
         const uint4 a = reinterpret_cast<const uint4*>(colPtr)[0], b = reinterpret_cast<const uint4*>(colPtr)[1];
-        reinterpret_cast<uint4*>(shBlk + t * kSlab)[0] = a;
-        reinterpret_cast<uint4*>(shBlk + t * kSlab)[1] = b;
+        const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        unsigned air = 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (((w[k] >> (8 * j)) & 0xffu) == (unsigned)B_AIR) air |= 1u << (4 * k + j);
+        shAir[t] = air;
     }
     for (int i = t; i < kSlab * kSlabPitch; i += 256) shBest[i] = kNoBest;
-    if (t == 0) { shNext = 0; shNumBig = 0; }
     if (gi.needNoise) noise_tab_stage();
-    __syncthreads();
     const int lane = t & 31;
-    const int nF = segF ? gi.nF : 0, nC = segC ? gi.nCF : 0;
+    const int nF = segF ? gi.nF : 0, nC = segC ? gi.nCF : 0, nTot = nF + nC;
     const FeaturePlacement* f = gF + (size_t)li * strideF;
     const CaveFeaturePlacement* cf = gCF + (size_t)li * strideCF;
     const Prep* pf = prepF + (size_t)li * strideF;
     const Prep* pc = prepC + (size_t)li * strideCF;
-    // rasterises the (column, y) pairs of placement e that the calling WARP owns: pairs [first, first + 32), [first + step,
-    // first + step + 32), ... one per lane; returns false if e cannot touch the slab. Two steps per round: a cheap filter
-    // (voxel already claimed by an earlier placement / solid and the placement may not replace blocks) pushes the
-    // surviving pairs onto the warp's queue, and the rasteriser runs on full warps popped from that queue - a cave
-    // feature's box is mostly rock, so without the queue 3 or 4 lanes of 32 reach the rasteriser.
     unsigned short* wq = shQueue + (t >> 5) * 64;
     float* wgeom = shGeom + (t >> 5) * kMushroomGeomFloats;
-    auto raster = [&](int e, int first, int step, bool countOnly, int* totalOut) -> bool {
-        const bool cave = e >= nF;
-        const Prep k = cave ? pc[e - nF] : pf[e];
-        const int lo = max((int)k.lo, y0), hi = min((int)k.hi, y1);
-        if (lo > hi) return false;
-        const int x0 = k.xr & 15, nxc = (k.xr >> 4) - x0 + 1, z0 = k.zr & 15, nzc = (k.zr >> 4) - z0 + 1;
-        const int ny = hi - lo + 1;
-        const int total = nxc * nzc * ny;                     // y fastest
-        *totalOut = total;
-        if (countOnly) return true;
-        const unsigned rny = c_recip32[ny];                   // ceil(2^32 / ny): __umulhi(p, rny) = p / ny for p < 2^27
-        const unsigned key = (unsigned)e << 8;
-        FeaturePlacement fp;
-        CaveFeaturePlacement cp;
-        if (cave) cp = cf[e - nF];
-        else fp = f[e];
-        if (!cave && k.feature == F_PURPLE_MUSHROOM)
+
+    // the warp's current placement
+    int curE = -1, qn = 0;
+    bool cave = false;
+    Prep k = {};
+    FeaturePlacement fp = {};
+    CaveFeaturePlacement cp = {};
+    unsigned key = 0u;
+    // rasterises up to 32 queued pairs of the current placement
+    auto drain = [&]() {
+        const int n = min(qn, 32);
+        qn -= n;
+        const int code = wq[qn + (lane < n ? lane : 0)];
+        __syncwarp();
+        if (lane < n)
         {
-            purple_mushroom_geom(k.seed, wgeom);      // every lane writes the same values
-            __syncwarp();
-        }
+            const int col = code >> 5, yy = code & 31, x = col & 15, z = col >> 4, y = y0 + yy;
+            uint8_t fb = 0;
+            const bool hit = cave ? place_cave_feature(cp, o.x + x, y, o.y + z, k.seed, &fb) : place_feature(fp, o.x + x, y, o.y + z, k.seed, wgeom, &fb);
+            if (hit) atomicMin(&shBest[yy * kSlabPitch + col], key | fb);
 #ifdef MMG_FEATURE_STATS
-        const long long statT0 = clock64();
-        const int statSlot = (cave ? 32 : 0) + k.feature;
+            atomicAdd(&g_featStats[(cave ? 32 : 0) + k.feature][2], 1ull);
+            if (hit) atomicAdd(&g_featStats[(cave ? 32 : 0) + k.feature][3], 1ull);
 #endif
-        int qn = 0;
-        for (int base = first;; base += step)
+        }
+    };
+
+    for (int r0 = 0; r0 < nTot; r0 += kRound)
+    {
+        __syncthreads();                                      // first round: staging above; later rounds: the previous round's lists are free
+        if (t == 0) { shPacked = 0u; shNextTile = 0; }
+        __syncthreads();
+        const int r1 = min(r0 + kRound, nTot);
+        for (int e = r0 + t; e < r1; e += 256)
         {
-            const bool more = base < total;                   // warp-uniform
-            if (more)
+            const Prep q = e >= nF ? pc[e - nF] : pf[e];
+            const int lo = max((int)q.lo, y0), hi = min((int)q.hi, y1);
+            if (lo > hi) continue;
+            const int total = ((q.xr >> 4) - (q.xr & 15) + 1) * ((q.zr >> 4) - (q.zr & 15) + 1) * (hi - lo + 1);
+            const unsigned old = atomicAdd(&shPacked, (unsigned)((total + kTile - 1) / kTile) << 11 | 1u);
+            shActE[old & 0x7ffu] = (unsigned short)e;
+            shActBase[old & 0x7ffu] = old >> 11;
+        }
+        __syncthreads();
+        const int nAct = (int)(shPacked & 0x7ffu), nTiles = (int)(shPacked >> 11);
+        for (;;)
+        {
+            int tile = 0;
+            if (lane == 0) tile = atomicAdd(&shNextTile, 1);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tile >= nTiles) break;
+            int s0 = 0, s1 = nAct - 1;                        // last slot whose first tile is <= tile
+            while (s0 < s1)
+            {
+                const int mid = (s0 + s1 + 1) >> 1;
+                if ((int)shActBase[mid] <= tile) s0 = mid; else s1 = mid - 1;
+            }
+            const int e = shActE[s0], firstPair = (tile - (int)shActBase[s0]) * kTile;
+            if (e != curE)
+            {
+                if (qn > 0) drain();                          // the queue holds fewer than 32 pairs between tiles
+                curE = e;
+                cave = e >= nF;
+                k = cave ? pc[e - nF] : pf[e];
+                key = (unsigned)e << 8;
+                if (cave) cp = cf[e - nF];
+                else
+                {
+                    fp = f[e];
+                    if (k.feature == F_PURPLE_MUSHROOM)
+                    {
+                        __syncwarp();
+                        purple_mushroom_geom(k.seed, wgeom);      // every lane writes the same values
+                        __syncwarp();
+                    }
+                }
+            }
+            const int lo = max((int)k.lo, y0), hi = min((int)k.hi, y1);
+            const int x0 = k.xr & 15, nxc = (k.xr >> 4) - x0 + 1, z0 = k.zr & 15, nzc = (k.zr >> 4) - z0 + 1;
+            const int ny = hi - lo + 1;
+            const int lastPair = min(firstPair + kTile, nxc * nzc * ny);      // y fastest
+            const unsigned rny = c_recip32[ny];                               // ceil(2^32 / ny): __umulhi(p, rny) = p / ny for p < 2^27
+            for (int base = firstPair; base < lastPair; base += 32)
             {
                 const int p = base + lane;
                 bool cand = false;
                 int code = 0;
-                if (p < total)
+                if (p < lastPair)
                 {
                     const int q = ny > 1 ? (int)__umulhi((unsigned)p, rny) : p, dy = p - q * ny;
                     const int dz = (int)((q * c_recip16[nxc]) >> 16), dx = q - dz * nxc;
                     const int col = (x0 + dx) + 16 * (z0 + dz), yy = lo + dy - y0;
                     code = col << 5 | yy;
                     cand = shBest[yy * kSlabPitch + col] > (key | 0xffu) &&      // not claimed by an earlier placement
-                           (k.canReplace || shBlk[col * kSlab + yy] == B_AIR);
+                           (k.canReplace || ((shAir[col] >> yy) & 1u));
 #ifdef MMG_FEATURE_STATS
-                    atomicAdd(&g_featStats[statSlot][1], 1ull);
+                    atomicAdd(&g_featStats[(cave ? 32 : 0) + k.feature][1], 1ull);
 #endif
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, cand);
                 if (cand) wq[qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short)code;
                 qn += __popc(m);
                 __syncwarp();
-            }
-            if (qn >= 32 || (!more && qn > 0))
-            {
-                const int n = min(qn, 32);
-                qn -= n;
-                const int code = wq[qn + (lane < n ? lane : 0)];
-                __syncwarp();
-                if (lane < n)
-                {
-                    const int col = code >> 5, yy = code & 31, x = col & 15, z = col >> 4, y = y0 + yy;
-                    uint8_t fb = 0;
-                    const bool hit = cave ? place_cave_feature(cp, o.x + x, y, o.y + z, k.seed, &fb) : place_feature(fp, o.x + x, y, o.y + z, k.seed, wgeom, &fb);
-                    if (hit) atomicMin(&shBest[yy * kSlabPitch + col], key | fb);
-#ifdef MMG_FEATURE_STATS
-                    atomicAdd(&g_featStats[statSlot][2], 1ull);
-                    if (hit) atomicAdd(&g_featStats[statSlot][3], 1ull);
-#endif
-                }
-            }
-            if (!more) break;
-        }
-#ifdef MMG_FEATURE_STATS
-        __syncwarp();
-        if (lane == 0) atomicAdd(&g_featStats[statSlot][0], (unsigned long long)(clock64() - statT0));
-#endif
-        return true;
-    };
-    // phase 1: warps pull placements from a shared counter (in list order, so that earlier placements tend to
-    // claim their voxels first); placements with a large box (trees, icebergs) are set aside for phase 2
-    for (;;)
-    {
-        int e = 0;
-        if (lane == 0) e = atomicAdd(&shNext, 1);
-        e = __shfl_sync(0xffffffffu, e, 0);
-        if (e >= nF + nC) break;
-        int total = 0;
-        if (!raster(e, 0, 0, true, &total)) continue;
-        if (total > kBigBox)
-        {
-            int slot = kMaxBig;
-            if (lane == 0) slot = atomicAdd(&shNumBig, 1);
-            slot = __shfl_sync(0xffffffffu, slot, 0);
-            if (slot < kMaxBig)
-            {
-                if (lane == 0) shBig[slot] = (unsigned short)e;
-                continue;
+                if (qn >= 32) drain();
             }
         }
-        raster(e, 0, 32, false, &total);
-    }
-    __syncthreads();
-    // phase 2: the whole CTA rasterises each large placement together
-    {
-        const int nBig = min(shNumBig, kMaxBig);
-        for (int b = 0; b < nBig; ++b)
-        {
-            int total = 0;
-            raster(shBig[b], t & ~31, 256, false, &total);
-        }
+        if (qn > 0) drain();
+        curE = -1;
     }
     __syncthreads();
     // thread t writes column t back if any of its 32 voxels was claimed
     {
-        __align__(16) uint8_t outv[kSlab];
         bool any = false;
 #pragma unroll
-        for (int yy = 0; yy < kSlab; ++yy)
-        {
-            const unsigned b = shBest[yy * kSlabPitch + t];
-            any = any || b != kNoBest;
-            outv[yy] = b != kNoBest ? (uint8_t)(b & 0xffu) : shBlk[t * kSlab + yy];
-        }
+        for (int yy = 0; yy < kSlab; ++yy) any = any || shBest[yy * kSlabPitch + t] != kNoBest;
         if (any)
         {
-            reinterpret_cast<uint4*>(colPtr)[0] = reinterpret_cast<const uint4*>(outv)[0];
-            reinterpret_cast<uint4*>(colPtr)[1] = reinterpret_cast<const uint4*>(outv)[1];
+            uint4 ab[2] = {reinterpret_cast<const uint4*>(colPtr)[0], reinterpret_cast<const uint4*>(colPtr)[1]};
+            uint8_t* outv = reinterpret_cast<uint8_t*>(ab);
+#pragma unroll
+            for (int yy = 0; yy < kSlab; ++yy)
+            {
+                const unsigned b = shBest[yy * kSlabPitch + t];
+                if (b != kNoBest) outv[yy] = (uint8_t)(b & 0xffu);
+            }
+            reinterpret_cast<uint4*>(colPtr)[0] = ab[0];
+            reinterpret_cast<uint4*>(colPtr)[1] = ab[1];
         }
     }
 }

@@ -248,8 +248,8 @@ static int erodeZonesDevice(float* d_zones, int nZones, int* d_flags, cudaStream
     int accIn = 10, accOut = 11;     // plane 10 was zeroed by the gather (or by the caller)
     int sweeps = 0;
     int h_flags[kSweepGroup];
-    int* d_zoneChanged = d_flags + kSweepGroup;      // [3][kMaxZoneBatch], see k_erode_sweep
-    MMG_CUDA(cudaMemsetAsync(d_zoneChanged, 0, 3 * kMaxZoneBatch * sizeof(int), stream));
+    int* d_zoneChanged = d_flags + kSweepGroup;      // [3][kMaxZoneBatch][kZoneTiles], see k_erode_sweep
+    MMG_CUDA(cudaMemsetAsync(d_zoneChanged, 0, 3 * kMaxZoneBatch * kZoneTiles * sizeof(int), stream));
     for (int layer = NUM_ERODED - 1; layer >= 0; --layer)
     {
         int pIn = layer, pOut = 9;
@@ -305,7 +305,7 @@ extern "C" int mmgen_erode_zone(const float* gathered, float* out_eroded, int* o
     if (requireReady()) return 1;
     const size_t P = kErosionCols;
     if (g_scratch[4].ensure(kZonePlanes * P * sizeof(float))) return 1;
-    if (g_scratch[5].ensure((kSweepGroup + 3 * kMaxZoneBatch) * sizeof(int))) return 1;
+    if (g_scratch[5].ensure((kSweepGroup + 3 * kMaxZoneBatch * kZoneTiles) * sizeof(int))) return 1;
     float* d_zone = (float*)g_scratch[4].ptr;
     MMG_CUDA(cudaMemcpyAsync(d_zone, gathered, 9 * P * sizeof(float), cudaMemcpyHostToDevice, g_stream));
     MMG_CUDA(cudaMemsetAsync(d_zone + 10 * P, 0, P * sizeof(float), g_stream));
@@ -590,7 +590,7 @@ static int worldErode(MmgenWorld* w, const std::vector<int2>& corners)
     const int nx = w->nx;
     if (!w->d_zone) MMG_CUDA(cudaMalloc(&w->d_zone, (size_t)kZoneBatch * kZonePlanes * kErosionCols * sizeof(float)));
     if (!w->d_zoneCorners) MMG_CUDA(cudaMalloc(&w->d_zoneCorners, (size_t)kZoneBatch * sizeof(int2)));
-    if (!w->d_flags) MMG_CUDA(cudaMalloc(&w->d_flags, (kSweepGroup + 3 * kMaxZoneBatch) * sizeof(int)));
+    if (!w->d_flags) MMG_CUDA(cudaMalloc(&w->d_flags, (kSweepGroup + 3 * kMaxZoneBatch * kZoneTiles) * sizeof(int)));
     if (!w->d_eroded) MMG_CUDA(cudaMalloc(&w->d_eroded, (size_t)w->n * NUM_MATERIALS * 256 * sizeof(float)));
     for (size_t z0 = 0; z0 < corners.size(); z0 += kZoneBatch)
     {
@@ -1170,12 +1170,14 @@ extern "C" int mmgen_debug_feature_stats(unsigned long long* out)
     MMG_CUDA(cudaMemcpyToSymbol(g_featStats, zero, sizeof(zero)));
     return 0;
 }
-// out[0] = voxels where huge_zero_mask's proof was wrong (must be 0), out[1] / out[2] = threshold voxels without / with proof
+// out[0] = voxels where huge_zero_mask's proof was wrong (must be 0), out[1] / out[2] = threshold voxels without / with proof,
+// out[3] = voxels that went on to the warped specialCaveNoise
 extern "C" int mmgen_debug_huge_stats(unsigned long long* out)
 {
     MMG_CUDA(cudaDeviceSynchronize());
     MMG_CUDA(cudaMemcpyFromSymbol(out, g_hugeMismatch, sizeof(unsigned long long)));
     MMG_CUDA(cudaMemcpyFromSymbol(out + 1, g_hugeVoxels, 2 * sizeof(unsigned long long)));
+    MMG_CUDA(cudaMemcpyFromSymbol(out + 3, g_caveWarped, sizeof(unsigned long long)));
     return 0;
 }
 #endif
