@@ -143,9 +143,11 @@ __global__ void k_zone_gather(const float* __restrict__ layers, const float* __r
 // "nothing flagged" does not imply "planes equal" there).
 constexpr int kMaxZoneBatch = 32;
 constexpr int kZoneTiles = 144;      // 12 x 12 tiles of 32 x 32 cells
-// (A persistent variant - two CTAs per SM walking the tiles - was measured and is slower: 54.7 vs 39.4 ms per 256x256 world;
-// with one tile per CTA the block scheduler overlaps the staging of one tile with the arithmetic of others.)
-__global__ void __launch_bounds__(1024) k_erode_sweep(float* __restrict__ zones, int pIn, int pOut, int pUp, int pAccIn, int pAccOut,
+// (A persistent variant - two 1024-thread CTAs per SM walking the tiles - was measured and is slower: 54.7 vs 39.4 ms per
+// 256x256 world; with one tile per CTA the block scheduler overlaps the staging of one tile with the arithmetic of others.)
+// One CTA of 32 x 8 threads per tile, four rows per thread: a quiet tile costs the launch of 8 warps, not 32.
+constexpr int kErodeRows = 8;
+__global__ void __launch_bounds__(32 * kErodeRows) k_erode_sweep(float* __restrict__ zones, int pIn, int pOut, int pUp, int pAccIn, int pAccOut,
                                                       float rep, int isFirst, int* __restrict__ changedFlag, int* __restrict__ tileChanged,
                                                       int sweepNo, int force)
 {
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(1024) k_erode_sweep(float* __restrict__ zones,
     int* rowCur = tileChanged + (sweepNo % 3) * rowSize + blockIdx.z * kZoneTiles;
     int* rowNext = tileChanged + ((sweepNo + 1) % 3) * rowSize + blockIdx.z * kZoneTiles;
     const int tile = blockIdx.x + 12 * blockIdx.y;
-    const int lx = threadIdx.x, lz = threadIdx.y, lid = lx + 32 * lz;
+    const int lx = threadIdx.x, lid = lx + 32 * threadIdx.y;
     {
         if (lid == 9) rowNext[tile] = 0;
         int moved = force;
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(1024) k_erode_sweep(float* __restrict__ zones,
     const float* accumIn = zone + (size_t)pAccIn * kErosionCols;
     float* accumOut = zone + (size_t)pAccOut * kErosionCols;
     const int bx0 = blockIdx.x * 32, bz0 = blockIdx.y * 32;
-    for (int t = lid; t < 34 * 34; t += 1024)
+    for (int t = lid; t < 34 * 34; t += 32 * kErodeRows)
     {
         int gx = bx0 - 1 + (t % 34), gz = bz0 - 1 + (t / 34);
         gx = min(max(gx, 0), kErosionSide - 1);       // clamp-to-edge halo, chunk.cu:545
@@ -185,34 +187,44 @@ __global__ void __launch_bounds__(1024) k_erode_sweep(float* __restrict__ zones,
         shE[t] = eUp[j] + a;
     }
     __syncthreads();
-    const int gx = bx0 + lx, gz = bz0 + lz, i = gx + kErosionSide * gz;
-    const int c = (lx + 1) + 34 * (lz + 1);
-    const float s0 = shS[c], e0 = shE[c];
     const float repDiag = rep * kSqrt2;
-    float ns = s0, maxT = e0 - s0;
+    bool changed = false;
 #pragma unroll
-    for (int d = 0; d < 8; ++d)
+    for (int r = 0; r < 32 / kErodeRows; ++r)
     {
-        const int j = c + c_dirVecs2d[d][0] + 34 * c_dirVecs2d[d][1];
-        const float sj = shS[j];
-        ns = fmaxf(ns, sj - ((d & 1) ? repDiag : rep));
-        maxT = fmaxf(maxT, shE[j] - sj);
-    }
-    ns = fminf(ns, e0);
-    float outS = sIn[i];
-    float acc = accumIn[i];
-    if (maxT > 0.0f)
-    {
-        outS = ns;
-        if (ns != s0)
+        const int lz = threadIdx.y + kErodeRows * r;
+        const int gx = bx0 + lx, gz = bz0 + lz, i = gx + kErosionSide * gz;
+        const int c = (lx + 1) + 34 * (lz + 1);
+        const float s0 = shS[c], e0 = shE[c];
+        float ns = s0, maxT = e0 - s0;
+#pragma unroll
+        for (int d = 0; d < 8; ++d)
         {
-            acc = (ns - s0) + acc;
-            *changedFlag = 1;
-            rowCur[tile] = 1;
+            const int j = c + c_dirVecs2d[d][0] + 34 * c_dirVecs2d[d][1];
+            const float sj = shS[j];
+            ns = fmaxf(ns, sj - ((d & 1) ? repDiag : rep));
+            maxT = fmaxf(maxT, shE[j] - sj);
         }
+        ns = fminf(ns, e0);
+        float outS = sIn[i];
+        float acc = accumIn[i];
+        if (maxT > 0.0f)
+        {
+            outS = ns;
+            if (ns != s0)
+            {
+                acc = (ns - s0) + acc;
+                changed = true;
+            }
+        }
+        sOut[i] = outS;
+        accumOut[i] = acc;
     }
-    sOut[i] = outS;
-    accumOut[i] = acc;
+    if (changed)
+    {
+        *changedFlag = 1;
+        rowCur[tile] = 1;
+    }
 }
 
 // scatter the centre 12x12 chunks back (copyLayers(..., false)) into the eroded layer set and apply

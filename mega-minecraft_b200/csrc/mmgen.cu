@@ -261,7 +261,7 @@ static int erodeZonesDevice(float* d_zones, int nZones, int* d_flags, cudaStream
             g_kt.begin(K_ERODE_SWEEPS, stream, kSweepGroup);
             for (int b = 0; b < kSweepGroup; ++b)
             {
-                MMG_LAUNCH(k_erode_sweep, dim3(12, 12, nZones), dim3(32, 32), 0, stream, d_zones, pIn, pOut, layer + 1, accIn, accOut,
+                MMG_LAUNCH(k_erode_sweep, dim3(12, 12, nZones), dim3(32, kErodeRows), 0, stream, d_zones, pIn, pOut, layer + 1, accIn, accOut,
                            kTanRepose[layer], first ? 1 : 0, d_flags + b, d_zoneChanged, sweeps, layerSweeps < 2 ? 1 : 0);
                 ++layerSweeps;
                 std::swap(pIn, pOut);
