@@ -146,7 +146,10 @@ constexpr int kZoneTiles = 144;      // 12 x 12 tiles of 32 x 32 cells
 // (A persistent variant - two 1024-thread CTAs per SM walking the tiles - was measured and is slower: 54.7 vs 39.4 ms per
 // 256x256 world; with one tile per CTA the block scheduler overlaps the staging of one tile with the arithmetic of others.)
 // One CTA of 32 x 8 threads per tile, four rows per thread: a quiet tile costs the launch of 8 warps, not 32.
-constexpr int kErodeRows = 8;
+#ifndef MMG_ERODE_ROWS
+#define MMG_ERODE_ROWS 8
+#endif
+constexpr int kErodeRows = MMG_ERODE_ROWS;
 __global__ void __launch_bounds__(32 * kErodeRows) k_erode_sweep(float* __restrict__ zones, int pIn, int pOut, int pUp, int pAccIn, int pAccOut,
                                                       float rep, int isFirst, int* __restrict__ changedFlag, int* __restrict__ tileChanged,
                                                       int sweepNo, int force)
