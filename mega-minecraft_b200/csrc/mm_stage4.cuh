@@ -15,7 +15,7 @@ namespace mmg {
 
 #ifdef MMG_FEATURE_STATS
 // developer build: voxels whose "huge caves" term was proved 0 but is not (must stay 0); voxels evaluated without / with proof
-__device__ unsigned long long g_hugeMismatch, g_hugeVoxels[2], g_caveWarped;      // g_caveWarped: voxels that evaluated the warped specialCaveNoise
+__device__ unsigned long long g_hugeMismatch, g_hugeVoxels[2], g_caveWarped, g_cavePending[3];      // g_cavePending: decided by bounds / pending / decided wrongly (must stay 0);      // g_caveWarped: voxels that evaluated the warped specialCaveNoise
 #endif
 
 // ---------------------------------------------------------------- cave biome (biomeFuncs.hpp:135-220)
@@ -192,12 +192,29 @@ __device__ __forceinline__ float special_cave_noise_cached(float px, float py, f
     return d3 / d1 + -1.0f;
 }
 
-// chunk.cu:755-810, first half: everything up to the cave-noise threshold. Returns 0 = solid, 1 = air,
-// 2 = undecided: the warped specialCaveNoise at (*px, *py, *pz) has to be compared with *thr.
-//
-// hugeZero: the caller has proved that the "huge caves" term is exactly 0 at this voxel (huge_zero_mask below); its four
-// simplex3 are then skipped: fma(0, 1.4, 1) = 1 and thr * 1 = thr, the same bits.
-__device__ __forceinline__ int cave_threshold(int wx, int y, int wz, float maxHeight, float obw, bool hugeZero, float* thrOut, float* px, float* py, float* pz)
+// chunk.cu:755-810, first half: everything up to the cave-noise threshold
+//     thr = (fma(bottomRatio, 0.7, 0.3) * topRatio) * (fma(fbmA, 0.12, 0.24) * fma(huge, 1.4, 1)),   air <=> thr > 0.04 && noise < thr,
+// split so that fbmA = fbm3<4>(pos * 0.02) - four simplex3 of the 23 per voxel - is only evaluated where it can matter.
+// Every operation of thr is monotone in fbmA (rounding is monotone, the other factors are >= 0), and |fbmA| < 1
+// (|42 * simplex3_raw| <= 1.052, see mm_fillfuncs.cuh; amplitudes sum to 0.9375), so cave_thr(-1) <= thr <= cave_thr(+1)
+// exactly as computed. A voxel whose upper bound fails `> 0.04` is solid without any noise; one whose warped cave noise is
+// >= the upper bound is solid, one whose noise is < the lower bound (and that bound > 0.04) is air; only the rest
+// (k_caves queues them and evaluates fbmA on dense warps) need the exact threshold.
+struct CaveThr { float ratio, hugeFactor; };      // ratio = fma(bottomRatio, 0.7, 0.3) * topRatio
+__device__ __forceinline__ float cave_thr(const CaveThr& c, float fbmA)
+{
+    float thr = fmaf(fbmA, 0.12f, 0.24f);
+    thr = thr * c.hugeFactor;                     // huge == 0: fma(0, 1.4, 1) = 1 and thr * 1 = thr, the same bits
+    return c.ratio * thr;
+}
+__device__ __forceinline__ float cave_fbm_a(int wx, int y, int wz)
+{
+    const float npx = (float)wx * 0.0050f, npy = (float)y * 0.0050f, npz = (float)wz * 0.0050f;
+    return fbm3<4>(npx * 4.f, npy * 4.f, npz * 4.f);
+}
+// Returns 0 = solid, 1 = air, 2 = the warped specialCaveNoise at (*px, *py, *pz) has to be compared with the threshold *c.
+// hugeZero: the caller has proved that the "huge caves" term is exactly 0 at this voxel (huge_zero_mask below).
+__device__ __forceinline__ int cave_threshold(int wx, int y, int wz, float maxHeight, float obw, bool hugeZero, CaveThr* c, float* px, float* py, float* pz)
 {
     if (y == 0) return 0;
     const int hi = (int)maxHeight;
@@ -206,34 +223,33 @@ __device__ __forceinline__ int cave_threshold(int wx, int y, int wz, float maxHe
     const float npx = (float)wx * 0.0050f, npy = fy * 0.0050f, npz = (float)wz * 0.0050f;
     const float topRatio = ss_t((fmaf(obw, 50.f, fy) + -142.f) / (95.f - 142.f));
     const float bottomRatio = ss_t((fy + -5.f) / (20.f - 5.f));
-    // topRatio is exactly 0 from y = 142 - 50 obw upwards; the threshold below is (finite * topRatio) * finite = 0 there and
-    // the test `thr > 0.04` fails whatever the two fbm3<4> say (8 simplex3 the reference evaluates for every such voxel)
+    // topRatio is exactly 0 from y = 142 - 50 obw upwards; the threshold is (finite * 0) * finite = 0 there and
+    // the test `thr > 0.04` fails whatever the noises say
     if (topRatio == 0.f) return 0;
+    c->ratio = fmaf(bottomRatio, 0.7f, 0.3f) * topRatio;
+    c->hugeFactor = 1.f;
 #ifdef MMG_FEATURE_STATS
     const bool hugeCheck = hugeZero;      // developer build: evaluate the term anyway and count voxels where the proof was wrong
     hugeZero = false;
     atomicAdd(&g_hugeVoxels[hugeCheck ? 1 : 0], 1ull);
 #endif
-    float thr = fmaf(fbm3<4>(npx * 4.f, npy * 4.f, npz * 4.f), 0.12f, 0.24f);
     if (!hugeZero)
     {
         const float huge = ss_t((fbm3<4>(npx * 0.0700f, npy * 0.0700f, npz * 0.0700f) + -0.2f) / (0.4f - 0.2f));
 #ifdef MMG_FEATURE_STATS
         if (hugeCheck && huge != 0.f) atomicAdd(&g_hugeMismatch, 1ull);
 #endif
-        thr = thr * fmaf(huge, 1.4f, 1.f);
+        c->hugeFactor = fmaf(huge, 1.4f, 1.f);
     }
-    thr = (fmaf(bottomRatio, 0.7f, 0.3f) * topRatio) * thr;
     // the reference always evaluates the warped specialCaveNoise (15 simplex + 27 hashed cells) and then
-    // tests `thr > 0.04 && caveNoise < thr` (chunk.cu:776-783); where the threshold test alone fails
-    // (topRatio -> 0 towards y = 142 - 50 obw) the noise cannot matter and is not evaluated
-    if (!(thr > 0.04f)) return 0;
+    // tests `thr > 0.04 && caveNoise < thr` (chunk.cu:776-783); where even the largest possible threshold fails the first
+    // test (topRatio -> 0 towards y = 142 - 50 obw) no noise can matter
+    if (!(cave_thr(*c, 1.f) > 0.04f)) return 0;
     const float ax = npx * 0.8000f, ay = npy * 0.8000f, az = npz * 0.8000f;
     const float o1 = fbm3<5>(ax, ay, az);
     const float o2 = fbm3<5>(ax + 5923.45f, ay + 4129.42f, az + 5790.48f);
     const float o3 = fbm3<5>(ax + 1765.68f, ay + 4704.36f, az + 5692.12f);
     *px = fmaf(o1, 1.8f, npx); *py = fmaf(npy, 1.6f, o2 * 1.8f); *pz = fmaf(o3, 1.8f, npz);
-    *thrOut = thr;
     return 2;
 }
 
@@ -292,6 +308,10 @@ __global__ void __launch_bounds__(128, MMG_CAVES_MINBLOCKS) k_caves(const int* _
     __shared__ int shNumFlips;
     __shared__ int shBox[3];
     __shared__ float shJit[3 * kCaveBox * kCaveBox * kCaveBox];
+    __shared__ int shNumPending;              // voxels of the slab whose exact threshold is still needed (cave_threshold)
+    __shared__ unsigned char shPendY[128];
+    __shared__ float shPendNoise[128];
+    __shared__ CaveThr shPendThr[128];
     noise_tab_stage();
     const int li = blockIdx.x >> 8, idx = blockIdx.x & 255;
     const int chunk = chunkList ? chunkList[li] : li;
@@ -313,13 +333,15 @@ __global__ void __launch_bounds__(128, MMG_CAVES_MINBLOCKS) k_caves(const int* _
             continue;
         }
         const int y = tid + 128 * k;
-        float thr = 0.f, px = 0.f, py = 0.f, pz = 0.f;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        CaveThr ct = {0.f, 1.f};
         const bool hugeZero = y < kHugeRun * kHugeSamples && ((cc.hugeZeroMask >> (y / kHugeRun)) & 1u);
-        const int st = cave_threshold(wx, y, wz, maxHeight, cc.obw, hugeZero, &thr, &px, &py, &pz);
+        const int st = cave_threshold(wx, y, wz, maxHeight, cc.obw, hugeZero, &ct, &px, &py, &pz);
         // cells [box, box + kCaveBox)^3 cover the 3x3x3 neighbourhoods of (nearly) all undecided voxels. (Filling
         // the table costs 5 hashes per thread; even for a single undecided voxel that is fewer warp instructions
         // than its 81 hashes computed in place on one lane - measured.)
         if (tid < 3) shBox[tid] = INT_MAX;
+        if (tid == 3) shNumPending = 0;
         __syncthreads();
         if (st == 2)
         {
@@ -341,15 +363,53 @@ __global__ void __launch_bounds__(128, MMG_CAVES_MINBLOCKS) k_caves(const int* _
             }
         }
         __syncthreads();
-        bool air = st == 1;
+        bool air = st == 1, pending = false;
+        float noise = 0.f;
+        if (st == 2)
+        {
+            noise = special_cave_noise_cached(px, py, pz, bx, by, bz, shJit);
+            const float thrLo = cave_thr(ct, -1.f), thrHi = cave_thr(ct, 1.f);      // thrLo <= thr <= thrHi, thrHi > 0.04 here
+            if (noise < thrHi)      // else solid: noise < thr is impossible
+            {
+                if (thrLo > 0.04f && noise < thrLo) air = true;      // thr > 0.04 && noise < thr whatever fbmA is
+                else pending = true;
+            }
 #ifdef MMG_FEATURE_STATS
-        if (st == 2) atomicAdd(&g_caveWarped, 1ull);
+            atomicAdd(&g_caveWarped, 1ull);
+            atomicAdd(&g_cavePending[pending ? 1 : 0], 1ull);
+            if (!pending)
+            {
+                const float thr = cave_thr(ct, cave_fbm_a(wx, y, wz));
+                if ((thr > 0.04f && noise < thr) != air) atomicAdd(&g_cavePending[2], 1ull);
+            }
 #endif
-        if (st == 2) air = special_cave_noise_cached(px, py, pz, bx, by, bz, shJit) < thr;
-        if (st != 1 && !air) air = rav.active && (rav.top - rav.depth) < (float)y && y != 0;   // chunk.cu:785-808
+        }
+        if (st != 1 && !air && !pending) air = rav.active && (rav.top - rav.depth) < (float)y && y != 0;   // chunk.cu:785-808
+        // pending voxels (a few per warp) are listed and get their exact threshold on adjacent lanes below; until then solid
+        const unsigned pm = __ballot_sync(0xffffffffu, pending);
+        if (pm)
+        {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&shNumPending, __popc(pm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pending)
+            {
+                const int slot = base + __popc(pm & ((1u << lane) - 1u));
+                shPendY[slot] = (unsigned char)tid; shPendNoise[slot] = noise; shPendThr[slot] = ct;
+            }
+        }
         const unsigned int bits = __ballot_sync(0xffffffffu, !air);
         if (lane == 0) shFilled[4 * k + warp] = bits;
-        __syncthreads();      // shBox / shJit are reused by the next slab
+        __syncthreads();
+        if (tid < shNumPending)
+        {
+            const int t2 = shPendY[tid], y2 = t2 + 128 * k;
+            const float thr = cave_thr(shPendThr[tid], cave_fbm_a(wx, y2, wz));
+            bool air2 = thr > 0.04f && shPendNoise[tid] < thr;
+            if (!air2) air2 = rav.active && (rav.top - rav.depth) < (float)y2;      // y2 != 0: y == 0 never gets here
+            if (air2) atomicAnd(&shFilled[4 * k + (t2 >> 5)], ~(1u << (t2 & 31)));
+        }
+        __syncthreads();      // shBox / shJit / the pending list are reused by the next slab
     }
     __syncthreads();
     CaveLayer* out = caveLayers + ((size_t)chunk * 256 + idx) * MAX_CAVE_LAYERS;

@@ -1171,13 +1171,15 @@ extern "C" int mmgen_debug_feature_stats(unsigned long long* out)
     return 0;
 }
 // out[0] = voxels where huge_zero_mask's proof was wrong (must be 0), out[1] / out[2] = threshold voxels without / with proof,
-// out[3] = voxels that went on to the warped specialCaveNoise
+// out[3] = voxels that went on to the warped specialCaveNoise, out[4] / out[5] = of those: decided by the threshold bounds /
+// needing the exact threshold, out[6] = decided wrongly by the bounds (must be 0)
 extern "C" int mmgen_debug_huge_stats(unsigned long long* out)
 {
     MMG_CUDA(cudaDeviceSynchronize());
     MMG_CUDA(cudaMemcpyFromSymbol(out, g_hugeMismatch, sizeof(unsigned long long)));
     MMG_CUDA(cudaMemcpyFromSymbol(out + 1, g_hugeVoxels, 2 * sizeof(unsigned long long)));
     MMG_CUDA(cudaMemcpyFromSymbol(out + 3, g_caveWarped, sizeof(unsigned long long)));
+    MMG_CUDA(cudaMemcpyFromSymbol(out + 4, g_cavePending, 3 * sizeof(unsigned long long)));
     return 0;
 }
 #endif

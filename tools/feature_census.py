@@ -32,7 +32,7 @@ for i in range(64):
 print("%-30s %8s %12s %12s %12s" % ("type", "rast.%", "pairs", "rasterised", "hits"))
 for c, n, a, b, h in sorted(rows, key=lambda r: -r[3]):
     print("%-30s %7.1f%% %12d %12d %12d" % (n, 100 * b / tot, a, b, h))
-hs = np.zeros(4, np.uint64)
+hs = np.zeros(7, np.uint64)
 gen.L.mmgen_debug_huge_stats(hs.ctypes.data_as(ctypes.c_void_p))
 print("huge-caves term: proved zero for %d of %d threshold voxels (%.1f %%), proof wrong for %d (must be 0)"
       % (hs[2], hs[1] + hs[2], 100.0 * float(hs[2]) / max(float(hs[1] + hs[2]), 1.0), hs[0]))
@@ -41,3 +41,5 @@ st = w.stages().ravel()
 alg = int(np.maximum(np.floor(hgt).astype(np.int64)[st >= 4], 128).sum())
 print("k_caves: algorithmic voxels (0 < y <= max(h, 128)) %d, threshold evaluated %d (%.3f), warped noise + Worley evaluated %d (%.3f)"
       % (alg, hs[1] + hs[2], float(hs[1] + hs[2]) / alg, hs[3], float(hs[3]) / alg))
+print("k_caves threshold bounds: %d voxels decided without fbmA, %d needed it (%.1f %%), decided wrongly %d (must be 0)"
+      % (hs[4], hs[5], 100.0 * float(hs[5]) / max(float(hs[4] + hs[5]), 1.0), hs[6]))
