@@ -309,9 +309,9 @@ __global__ void __launch_bounds__(128, MMG_CAVES_MINBLOCKS) k_caves(const int* _
     __shared__ int shBox[3];
     __shared__ float shJit[3 * kCaveBox * kCaveBox * kCaveBox];
     __shared__ int shNumPending;              // voxels of the slab whose exact threshold is still needed (cave_threshold)
-    __shared__ unsigned char shPendY[128];
-    __shared__ float shPendNoise[128];
-    __shared__ CaveThr shPendThr[128];
+    __shared__ unsigned short shPendY[384];
+    __shared__ float shPendNoise[384];
+    __shared__ CaveThr shPendThr[384];
     noise_tab_stage();
     const int li = blockIdx.x >> 8, idx = blockIdx.x & 255;
     const int chunk = chunkList ? chunkList[li] : li;
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(128, MMG_CAVES_MINBLOCKS) k_caves(const int* _
     Ravine rav;
     rav.active = cc.ravActive != 0; rav.top = cc.ravTop; rav.depth = cc.ravDepth;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) shFilled[12] = 0u;
+    if (tid == 0) { shFilled[12] = 0u; shNumPending = 0; }
     const int hi = (int)maxHeight, yTop = hi > SEA_LEVEL ? hi : SEA_LEVEL;   // above this every voxel is air
 #pragma unroll 1
     for (int k = 0; k < 3; ++k)
@@ -341,7 +341,6 @@ __global__ void __launch_bounds__(128, MMG_CAVES_MINBLOCKS) k_caves(const int* _
         // the table costs 5 hashes per thread; even for a single undecided voxel that is fewer warp instructions
         // than its 81 hashes computed in place on one lane - measured.)
         if (tid < 3) shBox[tid] = INT_MAX;
-        if (tid == 3) shNumPending = 0;
         __syncthreads();
         if (st == 2)
         {
@@ -395,21 +394,21 @@ __global__ void __launch_bounds__(128, MMG_CAVES_MINBLOCKS) k_caves(const int* _
             if (pending)
             {
                 const int slot = base + __popc(pm & ((1u << lane) - 1u));
-                shPendY[slot] = (unsigned char)tid; shPendNoise[slot] = noise; shPendThr[slot] = ct;
+                shPendY[slot] = (unsigned short)y; shPendNoise[slot] = noise; shPendThr[slot] = ct;
             }
         }
         const unsigned int bits = __ballot_sync(0xffffffffu, !air);
         if (lane == 0) shFilled[4 * k + warp] = bits;
-        __syncthreads();
-        if (tid < shNumPending)
-        {
-            const int t2 = shPendY[tid], y2 = t2 + 128 * k;
-            const float thr = cave_thr(shPendThr[tid], cave_fbm_a(wx, y2, wz));
-            bool air2 = thr > 0.04f && shPendNoise[tid] < thr;
-            if (!air2) air2 = rav.active && (rav.top - rav.depth) < (float)y2;      // y2 != 0: y == 0 never gets here
-            if (air2) atomicAnd(&shFilled[4 * k + (t2 >> 5)], ~(1u << (t2 & 31)));
-        }
-        __syncthreads();      // shBox / shJit / the pending list are reused by the next slab
+        __syncthreads();      // shBox / shJit are reused by the next slab
+    }
+    // the column's pending voxels (all slabs together: ~26 per column) get their exact threshold on adjacent lanes
+    for (int i = tid; i < shNumPending; i += 128)
+    {
+        const int y2 = shPendY[i];
+        const float thr = cave_thr(shPendThr[i], cave_fbm_a(wx, y2, wz));
+        bool air2 = thr > 0.04f && shPendNoise[i] < thr;
+        if (!air2) air2 = rav.active && (rav.top - rav.depth) < (float)y2;      // y2 != 0: y == 0 never gets here
+        if (air2) atomicAnd(&shFilled[y2 >> 5], ~(1u << (y2 & 31)));
     }
     __syncthreads();
     CaveLayer* out = caveLayers + ((size_t)chunk * 256 + idx) * MAX_CAVE_LAYERS;
