@@ -36,6 +36,9 @@ UNIT = "chunks/s"
 F_S2, F_S3, F_W3CELL, F_SIN = 140, 330, 60, 20
 FLOP_CAVE_VOXEL = 23 * F_S3 + 27 * F_W3CELL + 81 * F_SIN          # one evaluated voxel of shouldGenerateCaveAtBlock
 FLOP_CAVE_BIOME = 11 * F_S3 + 12 * F_S2                           # one getCaveBiome
+# what k_caves executes of FLOP_CAVE_VOXEL after its exact early-outs (threshold bounds, huge-caves proof, tabulated cell hashes),
+# counted by the census build over the 256x256 world: profiles/r01_census_v8.txt
+EXECUTED_OVER_ALGORITHMIC_CAVES = 0.48
 BYTES_FILL_CHUNK = 242688                                         # S6 compulsory I/O per chunk (without feature lists)
 BYTES_CAVES_CHUNK = 107528
 
@@ -331,6 +334,10 @@ def run_own(args):
     roof = {"bound": "fp32", "kernel": roof_kernel, "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
             "traffic": None, "avg_launch_ms": avg_launch_ms, "launches_per_step": rk_launches,
             "algorithmic_flop_per_launch": flops_of[roof_kernel] / rk_launches,
+            "executed": ({"flop_ratio_to_algorithmic": EXECUTED_OVER_ALGORITHMIC_CAVES, "achieved": ach * EXECUTED_OVER_ALGORITHMIC_CAVES,
+                          "frac": ach * EXECUTED_OVER_ALGORITHMIC_CAVES / fp32_peak,
+                          "src": "census build over the same world (profiles/r01_census_v8.txt): evaluations proved unnecessary are not executed; "
+                                 "ncu issue-slot utilisation of the kernel is in profiles/"} if roof_kernel == "k_caves" else None),
             "peak_src": "FFMA microbenchmark run by this process on the same GPU just before the timed region (mmgen_measure_fp32_peak: %.1f TFLOP/s; "
                         "nominal 148 SM x 128 lanes x 2 x %.0f MHz = %.1f); MEASURED_PEAKS.json carries HBM and bf16 tensor figures only" % (
                             fp32_measured, pk["sm_max_mhz"], pk["fp32_tflops"]),

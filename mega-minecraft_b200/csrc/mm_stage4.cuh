@@ -298,6 +298,10 @@ __global__ void __launch_bounds__(256) k_cave_columns(const int* __restrict__ ch
     cols[(size_t)li * 256 + idx] = c;
 }
 
+#ifndef MMG_CAVE_COLS
+#define MMG_CAVE_COLS 1
+#endif
+constexpr int kCaveColsPerCta = MMG_CAVE_COLS;
 __global__ void __launch_bounds__(128, MMG_CAVES_MINBLOCKS) k_caves(const int* __restrict__ chunkList, const int2* __restrict__ origins,
                                                const float* __restrict__ heightfield, const CaveColumn* __restrict__ cols,
                                                CaveLayer* __restrict__ caveLayers, uint2* __restrict__ biomeQueue, int* __restrict__ biomeCount,
@@ -313,9 +317,17 @@ __global__ void __launch_bounds__(128, MMG_CAVES_MINBLOCKS) k_caves(const int* _
     __shared__ float shPendNoise[384];
     __shared__ CaveThr shPendThr[384];
     noise_tab_stage();
-    const int li = blockIdx.x >> 8, idx = blockIdx.x & 255;
+    const int li = blockIdx.x / (256 / kCaveColsPerCta);
     const int chunk = chunkList ? chunkList[li] : li;
     const int2 o = origins[chunk];
+    // kCaveColsPerCta consecutive columns per CTA would stage the 10 KB of noise tables once for all of them (4 % of the
+    // instructions, profiles/r01_k_caves_v8.txt) - measured slower (2, 4, 8 columns: 325 vs 317 ms per 256x256 world: the
+    // staging of one CTA overlaps the arithmetic of the nine others on the SM, the columns of one CTA run one after the other)
+#pragma unroll 1
+    for (int colIt = 0; colIt < kCaveColsPerCta; ++colIt)
+    {
+    const int idx = (blockIdx.x % (256 / kCaveColsPerCta)) * kCaveColsPerCta + colIt;
+    if (colIt) __syncthreads();      // the previous column's shared arrays are free
     const int wx = o.x + (idx & 15), wz = o.y + (idx >> 4);
     const float maxHeight = heightfield[(size_t)chunk * 256 + idx];
     const CaveColumn cc = cols[(size_t)li * 256 + idx];
@@ -476,6 +488,7 @@ __global__ void __launch_bounds__(128, MMG_CAVES_MINBLOCKS) k_caves(const int* _
         }
         out[l] = cl;
     }
+    }      // columns of this CTA
 }
 
 // getCaveBiome for the bottom / top of every cave layer (chunk.cu:915-935), one queued lookup per thread.

@@ -331,7 +331,7 @@ static int launchCaves(int m, const int* d_list, const int2* d_origins, const fl
         MMG_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
         MMG_TIMED(K_CAVE_COLUMNS, stream, 1, MMG_LAUNCH(k_cave_columns, mb, 256, kNoiseSmemBytes, stream, dl, d_origins + off,
                                                         d_weights + off * NUM_BIOMES * 256, d_cols));
-        MMG_TIMED(K_CAVES, stream, 1, MMG_LAUNCH(k_caves, mb * 256, 128, kNoiseSmemBytes, stream, dl, d_origins + off, d_height + off * 256,
+        MMG_TIMED(K_CAVES, stream, 1, MMG_LAUNCH(k_caves, mb * (256 / kCaveColsPerCta), 128, kNoiseSmemBytes, stream, dl, d_origins + off, d_height + off * 256,
                                                  (const CaveColumn*)d_cols, d_caves + off * 256 * MAX_CAVE_LAYERS, d_queue, d_count, kCaveBiomeQueueCap));
         MMG_TIMED(K_CAVE_BIOMES, stream, 1, MMG_LAUNCH(k_cave_biomes, kNumSMs * 16, 128, kNoiseSmemBytes, stream, d_origins + off, d_height + off * 256,
                                                        (const uint2*)d_queue, (const int*)d_count, kCaveBiomeQueueCap, d_caves + off * 256 * MAX_CAVE_LAYERS));
