@@ -153,27 +153,6 @@ __global__ void __launch_bounds__(256) k_feature_placements(const int* __restric
 
 struct GatherInfo { int nF, nCF; int fb0, fb1, cfb0, cfb1; int needNoise, pad; };
 
-// Position of this thread's kept entry among the kept entries of the whole CTA, in thread order
-// (= list order: the first feature in list order that contains a voxel wins, chunk.cu:1444-1500).
-// All threads of the CTA call it; *total = kept entries of the round. shWarp: one int per warp.
-__device__ __forceinline__ int block_ordered_offset(bool keep, int* shWarp, int* total)
-{
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    if (lane == 0) shWarp[warp] = __popc(m);
-    __syncthreads();
-    int off = 0, tot = 0;
-    for (int w = 0; w < nw; ++w)
-    {
-        const int c = shWarp[w];
-        off += (w < warp) ? c : 0;
-        tot += c;
-    }
-    __syncthreads();
-    *total = tot;
-    return off + __popc(m & ((1u << lane) - 1u));
-}
-
 // Extent of ONE surface placement where its own first draws fix it (the type's table values are the worst case over all
 // draws). PURPLE_MUSHROOM (featurePlacement.hpp:560-640 / place_feature): pos = offset * scale (* 0.5 with probability 0.2),
 // and a voxel survives the first rejection only if |pos.x|, |pos.z| <= 35 and pos.y <= height + 12 (each length in that test
@@ -217,81 +196,119 @@ __device__ __forceinline__ bool reach_hits_chunk(int px, int pz, int r, int ox, 
 // (2048 / 4096) exactly as the reference does; of that list only the placements whose horizontal
 // reach (c_featureReach) touches this chunk are kept, in order. The reference scans all of them per
 // voxel; the dropped ones cannot contain a voxel of this chunk, so the blocks are identical.
+// The 49 neighbour lists are independent except for where their kept entries go, so the warps of the CTA take them
+// round-robin twice: once to count what each list keeps, and - after a prefix sum over the 49 counts - once to write the
+// kept entries at their final positions (a list at a time with block-wide ordered compaction was one long dependent chain:
+// 95 us per launch against 20 us).
 __global__ void __launch_bounds__(256) k_gather_features(const int* __restrict__ fillList, const int2* __restrict__ origins,
                                                          const FeaturePlacement* __restrict__ features,
                                                          const CaveFeaturePlacement* __restrict__ caveFeatures, const int* __restrict__ counts,
                                                          int nx, FeaturePlacement* __restrict__ gF, CaveFeaturePlacement* __restrict__ gCF,
                                                          GatherInfo* __restrict__ info)
 {
-    __shared__ int shMin[2], shMax[2], shWarp[8];
+    __shared__ int shMin[2], shMax[2];
+    __shared__ int shN[2][49];         // entries of list k after the reference's truncation at MAX_FEATURES / MAX_CAVE_FEATURES
+    __shared__ int shKept[2][50];      // kept entries of list k, then (exclusive prefix) where they start in the output
     const int li = blockIdx.x, chunk = fillList[li];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 2) { shMin[tid] = 384; shMax[tid] = -1; }
     const int2 o = origins[chunk];
-    int baseF = 0, baseC = 0, outF = 0, outC = 0;
-    int mnF = 384, mxF = -1, mnC = 384, mxC = -1;
-    FeaturePlacement* dstF = gF + (size_t)li * MAX_FEATURES;
-    CaveFeaturePlacement* dstC = gCF + (size_t)li * MAX_CAVE_FEATURES;
-    for (int k = 0; k < 49; ++k)
+    if (warp < 2)
     {
-        if (baseF >= MAX_FEATURES && baseC >= MAX_CAVE_FEATURES) break;
-        const int nchunk = chunk + c_gatherOffsets[k][0] + c_gatherOffsets[k][1] * nx;
-        const int nf = min(counts[2 * nchunk], MAX_FEATURES - baseF), nc = min(counts[2 * nchunk + 1], MAX_CAVE_FEATURES - baseC);
-        const FeaturePlacement* sf = features + (size_t)nchunk * kMaxOwnFeatures;
-        const CaveFeaturePlacement* sc = caveFeatures + (size_t)nchunk * kMaxOwnCaveFeatures;
-        for (int i0 = 0; i0 < nf; i0 += 256)
+        // list lengths in the reference's concatenation order, cut where the concatenation reaches the cap (chunk.cu:1158-1187)
+        const int cap = warp == 0 ? MAX_FEATURES : MAX_CAVE_FEATURES;
+        int base = 0;
+        for (int k0 = 0; k0 < 49; k0 += 32)
         {
-            const int i = i0 + tid;
-            FeaturePlacement p;
-            bool keep = false;
-            int reach = 0, yHi = 0;
-            if (i < nf)
+            const int k = k0 + lane;
+            const int c = k < 49 ? counts[2 * (chunk + c_gatherOffsets[k][0] + c_gatherOffsets[k][1] * nx) + warp] : 0;
+            int incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
             {
-                p = sf[i];
-                surface_feature_extent(p, &reach, &yHi);
-                keep = reach_hits_chunk(p.x, p.z, reach, o.x, o.y);
+                const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
             }
-            int total;
-            const int off = block_ordered_offset(keep, shWarp, &total);
-            if (keep)
-            {
-                dstF[outF + off] = p;
-                mnF = min(mnF, p.y + c_featureHeightBounds[p.feature][0]);
-                mxF = max(mxF, p.y + yHi);
-            }
-            outF += total;
+            const int before = base + incl - c;
+            if (k < 49) shN[warp][k] = max(min(c, cap - before), 0);
+            base += __shfl_sync(0xffffffffu, incl, 31);
         }
-        for (int i0 = 0; i0 < nc; i0 += 256)
-        {
-            const int i = i0 + tid;
-            CaveFeaturePlacement p;
-            bool keep = false;
-            if (i < nc)
-            {
-                p = sc[i];
-                keep = reach_hits_chunk(p.x, p.z, c_caveFeatureReach[p.feature], o.x, o.y);
-            }
-            int total;
-            const int off = block_ordered_offset(keep, shWarp, &total);
-            if (keep)
-            {
-                dstC[outC + off] = p;
-                mnC = min(mnC, p.y + c_caveFeatureHeightBounds[p.feature][0]);
-                mxC = max(mxC, p.y + p.layerHeight + c_caveFeatureHeightBounds[p.feature][1]);
-            }
-            outC += total;
-        }
-        baseF += counts[2 * nchunk];
-        baseC += counts[2 * nchunk + 1];
     }
     __syncthreads();
+    FeaturePlacement* dstF = gF + (size_t)li * MAX_FEATURES;
+    CaveFeaturePlacement* dstC = gCF + (size_t)li * MAX_CAVE_FEATURES;
+    int mnF = 384, mxF = -1, mnC = 384, mxC = -1;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass)
+    {
+        for (int k = warp; k < 49; k += 8)
+        {
+            const int nchunk = chunk + c_gatherOffsets[k][0] + c_gatherOffsets[k][1] * nx;
+            const FeaturePlacement* sf = features + (size_t)nchunk * kMaxOwnFeatures;
+            const CaveFeaturePlacement* sc = caveFeatures + (size_t)nchunk * kMaxOwnCaveFeatures;
+            const int nf = shN[0][k], nc = shN[1][k];
+            int outF = pass ? shKept[0][k] : 0, outC = pass ? shKept[1][k] : 0;
+            for (int i0 = 0; i0 < nf; i0 += 32)
+            {
+                const int i = i0 + lane;
+                FeaturePlacement p;
+                bool keep = false;
+                int reach = 0, yHi = 0;
+                if (i < nf)
+                {
+                    p = sf[i];
+                    surface_feature_extent(p, &reach, &yHi);
+                    keep = reach_hits_chunk(p.x, p.z, reach, o.x, o.y);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (pass && keep)
+                {
+                    dstF[outF + __popc(m & ((1u << lane) - 1u))] = p;
+                    mnF = min(mnF, p.y + c_featureHeightBounds[p.feature][0]);
+                    mxF = max(mxF, p.y + yHi);
+                }
+                outF += __popc(m);
+            }
+            for (int i0 = 0; i0 < nc; i0 += 32)
+            {
+                const int i = i0 + lane;
+                CaveFeaturePlacement p;
+                bool keep = false;
+                if (i < nc)
+                {
+                    p = sc[i];
+                    keep = reach_hits_chunk(p.x, p.z, c_caveFeatureReach[p.feature], o.x, o.y);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (pass && keep)
+                {
+                    dstC[outC + __popc(m & ((1u << lane) - 1u))] = p;
+                    mnC = min(mnC, p.y + c_caveFeatureHeightBounds[p.feature][0]);
+                    mxC = max(mxC, p.y + p.layerHeight + c_caveFeatureHeightBounds[p.feature][1]);
+                }
+                outC += __popc(m);
+            }
+            if (!pass && lane == 0) { shKept[0][k] = outF; shKept[1][k] = outC; }
+        }
+        __syncthreads();
+        if (!pass)
+        {
+            if (tid < 2)
+            {
+                int run = 0;
+                for (int k = 0; k < 49; ++k) { const int c = shKept[tid][k]; shKept[tid][k] = run; run += c; }
+                shKept[tid][49] = run;
+            }
+            __syncthreads();
+        }
+    }
     atomicMin(&shMin[0], mnF); atomicMax(&shMax[0], mxF);
     atomicMin(&shMin[1], mnC); atomicMax(&shMax[1], mxC);
     __syncthreads();
     if (tid == 0)
     {
         GatherInfo gi;
-        gi.nF = outF; gi.nCF = outC;
+        gi.nF = shKept[0][49]; gi.nCF = shKept[1][49];
         gi.fb0 = shMin[0]; gi.fb1 = shMax[0]; gi.cfb0 = shMin[1]; gi.cfb1 = shMax[1];
         gi.needNoise = 1; gi.pad = 0;
         info[li] = gi;
