@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
     __shared__ unsigned shPacked;                            // tiles handed out << 11 | active placements
     __shared__ int shNextTile;
     __shared__ float shGeom[8 * kMushroomGeomFloats];        // per warp: purple_mushroom_geom of the placement being rasterised
-    __shared__ unsigned short shQueue[8 * 64];               // per warp: pairs that passed the filter, waiting for a full warp
+    __shared__ unsigned short shQueue[8 * 96];               // per warp: pairs that passed the filter, waiting for a full warp (< 32 + 2 x 32)
     const int slab = blockIdx.x % 12, li = blockIdx.x / 12;
     const int chunk = fillList ? fillList[li] : li;
     const int t = threadIdx.x, y0 = slab * kSlab, y1 = y0 + kSlab - 1;
@@ -804,7 +804,7 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
     const CaveFeaturePlacement* cf = gCF + (size_t)li * strideCF;
     const Prep* pf = prepF + (size_t)li * strideF;
     const Prep* pc = prepC + (size_t)li * strideCF;
-    unsigned short* wq = shQueue + (t >> 5) * 64;
+    unsigned short* wq = shQueue + (t >> 5) * 96;
     float* wgeom = shGeom + (t >> 5) * kMushroomGeomFloats;
 
     // the warp's current placement
@@ -888,28 +888,35 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
             const int ny = hi - lo + 1;
             const int lastPair = min(firstPair + kTile, nxc * nzc * ny);      // y fastest
             const unsigned rny = c_recip32[ny];                               // ceil(2^32 / ny): __umulhi(p, rny) = p / ny for p < 2^27
-            for (int base = firstPair; base < lastPair; base += 32)
+            // two rounds of 32 pairs per iteration: two independent index / load chains in flight
+            for (int base = firstPair; base < lastPair; base += 64)
             {
-                const int p = base + lane;
-                bool cand = false;
-                int code = 0;
-                if (p < lastPair)
+                bool cand[2] = {false, false};
+                int code[2] = {0, 0};
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
                 {
-                    const int q = ny > 1 ? (int)__umulhi((unsigned)p, rny) : p, dy = p - q * ny;
-                    const int dz = (int)((q * c_recip16[nxc]) >> 16), dx = q - dz * nxc;
-                    const int col = (x0 + dx) + 16 * (z0 + dz), yy = lo + dy - y0;
-                    code = col << 5 | yy;
-                    cand = shBest[yy * kSlabPitch + col] > (key | 0xffu) &&      // not claimed by an earlier placement
-                           (k.canReplace || ((shAir[col] >> yy) & 1u));
+                    const int p = base + 32 * u + lane;
+                    if (p < lastPair)
+                    {
+                        const int q = ny > 1 ? (int)__umulhi((unsigned)p, rny) : p, dy = p - q * ny;
+                        const int dz = (int)((q * c_recip16[nxc]) >> 16), dx = q - dz * nxc;
+                        const int col = (x0 + dx) + 16 * (z0 + dz), yy = lo + dy - y0;
+                        code[u] = col << 5 | yy;
+                        cand[u] = shBest[yy * kSlabPitch + col] > (key | 0xffu) &&      // not claimed by an earlier placement
+                                  (k.canReplace || ((shAir[col] >> yy) & 1u));
 #ifdef MMG_FEATURE_STATS
-                    atomicAdd(&g_featStats[(cave ? 32 : 0) + k.feature][1], 1ull);
+                        atomicAdd(&g_featStats[(cave ? 32 : 0) + k.feature][1], 1ull);
 #endif
+                    }
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, cand);
-                if (cand) wq[qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short)code;
-                qn += __popc(m);
+                const unsigned m0 = __ballot_sync(0xffffffffu, cand[0]), m1 = __ballot_sync(0xffffffffu, cand[1]);
+                const unsigned below = (1u << lane) - 1u;
+                if (cand[0]) wq[qn + __popc(m0 & below)] = (unsigned short)code[0];
+                if (cand[1]) wq[qn + __popc(m0) + __popc(m1 & below)] = (unsigned short)code[1];
+                qn += __popc(m0) + __popc(m1);
                 __syncwarp();
-                if (qn >= 32) drain();
+                while (qn >= 32) drain();
             }
         }
         if (qn > 0) drain();
