@@ -14,7 +14,9 @@ __device__ MMG_NOISE_INLINE float worley3_lush(float px, float py, float pz)
     const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
     const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
     const float nfx = fx - px, nfy = fy - py, nfz = fz - pz;
-    float d1 = FLT_MAX, d2 = FLT_MAX;
+    // only the smallest distance is used: the minimum is taken over the squares and rooted once (sqrtf is monotone, so
+    // the smallest rounded root is the root of the smallest square)
+    float q1 = FLT_MAX;
 #pragma unroll 1
     for (int x = -1; x <= 1; ++x)
 #pragma unroll 1
@@ -27,11 +29,9 @@ __device__ MMG_NOISE_INLINE float worley3_lush(float px, float py, float pz)
                 const float jy = hash_fract(fmaf(cz, 747.42f, fmaf(cy, 560.45f, cx * 654.37f)));
                 const float jz = hash_fract(fmaf(cz, 674.81f, fmaf(cy, 151.81f, cx * 640.88f)));
                 const float dx = nfx + (jx + (float)x), dy = nfy + (jy + (float)y), dz = nfz + (jz + (float)z);
-                const float dist = sqrtf(fmaf(dz, dz, fmaf(dx, dx, dy * dy)));
-                if (dist < d1) { d2 = d1; d1 = dist; }
-                else if (dist < d2) { d2 = dist; }
+                q1 = fminf(q1, fmaf(dz, dz, fmaf(dx, dx, dy * dy)));
             }
-    return d1;
+    return sqrtf(q1);
 }
 
 // ------------------------------------------------------------------ biomeFuncs.hpp:385-406

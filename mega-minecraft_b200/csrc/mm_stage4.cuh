@@ -161,12 +161,16 @@ __device__ __forceinline__ void cave_cell_jitter(int icx, int icy, int icz, floa
 // dozen cells; the reference recomputes 27 x 3 sin() hashes per voxel). Cells outside the table are
 // computed in place. Same cells, same order, same comparisons as special_cave_noise.
 constexpr int kCaveBox = 6;
+// The three smallest distances are selected on the SQUARED distances and only d1 and d3 are square-rooted: sqrtf is
+// monotone (correctly rounded), so the k-th smallest of the rounded roots is the root of the k-th smallest square - the
+// same two numbers the reference's insertion on sqrt'ed distances ends with (equal roots are interchangeable), for 2
+// instead of 27 IEEE square roots per voxel.
 __device__ __forceinline__ float special_cave_noise_cached(float px, float py, float pz, int bx, int by, int bz, const float* shJit)
 {
     const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
     const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
     const float nfx = fx - px, nfy = fy - py, nfz = fz - pz;
-    float d1 = FLT_MAX, d2 = FLT_MAX, d3 = FLT_MAX;
+    float q1 = FLT_MAX, q2 = FLT_MAX, q3 = FLT_MAX;
 #pragma unroll 1
     for (int x = -1; x <= 1; ++x)
 #pragma unroll 1
@@ -184,12 +188,12 @@ __device__ __forceinline__ float special_cave_noise_cached(float px, float py, f
                 else
                     cave_cell_jitter(ix + x, iy + y, iz + z, &jx, &jy, &jz);
                 const float dx = nfx + (jx + (float)x), dy = nfy + (jy + (float)y), dz = nfz + (jz + (float)z);
-                const float dist = sqrtf(fmaf(dz, dz, fmaf(dx, dx, dy * dy)));
-                if (dist < d1) { d3 = d2; d2 = d1; d1 = dist; }
-                else if (dist < d2) { d3 = d2; d2 = dist; }
-                else if (dist < d3) { d3 = dist; }
+                const float q = fmaf(dz, dz, fmaf(dx, dx, dy * dy));      // dist = sqrtf(q) in the reference
+                if (q < q1) { q3 = q2; q2 = q1; q1 = q; }
+                else if (q < q2) { q3 = q2; q2 = q; }
+                else if (q < q3) { q3 = q; }
             }
-    return d3 / d1 + -1.0f;
+    return sqrtf(q3) / sqrtf(q1) + -1.0f;
 }
 
 // chunk.cu:755-810, first half: everything up to the cave-noise threshold
