@@ -167,32 +167,62 @@ constexpr int kCaveBox = 6;
 // instead of 27 IEEE square roots per voxel.
 __device__ __forceinline__ float special_cave_noise_cached(float px, float py, float pz, int bx, int by, int bz, const float* shJit)
 {
+    constexpr int N3 = kCaveBox * kCaveBox * kCaveBox;
     const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
     const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
     const float nfx = fx - px, nfy = fy - py, nfz = fz - pz;
     float q1 = FLT_MAX, q2 = FLT_MAX, q3 = FLT_MAX;
+    // keeps the three smallest squares (a 5-instruction min / max network; the values, not their order of arrival, matter)
+    auto insert = [&](float q) {
+        const float a = fminf(q1, q); q = fmaxf(q1, q); q1 = a;
+        const float b = fminf(q2, q); q = fmaxf(q2, q); q2 = b;
+        q3 = fminf(q3, q);
+    };
+    const int ux0 = ix - 1 - bx, uy0 = iy - 1 - by, uz0 = iz - 1 - bz;
+    if ((unsigned)ux0 <= (unsigned)(kCaveBox - 3) && (unsigned)uy0 <= (unsigned)(kCaveBox - 3) && (unsigned)uz0 <= (unsigned)(kCaveBox - 3))
+    {
+        // the whole 3x3x3 neighbourhood is in the table (nearly always): no per-cell bounds tests
+        const float* J = shJit + (ux0 * kCaveBox + uy0) * kCaveBox + uz0;
+        float ox = -1.f;
 #pragma unroll 1
-    for (int x = -1; x <= 1; ++x)
+        for (int x = 0; x < 3; ++x, ox += 1.f)
+        {
+            float oy = -1.f;
 #pragma unroll 1
-        for (int y = -1; y <= 1; ++y)
-#pragma unroll
-            for (int z = -1; z <= 1; ++z)
+            for (int y = 0; y < 3; ++y, oy += 1.f)
             {
-                const int ux = ix + x - bx, uy = iy + y - by, uz = iz + z - bz;
-                float jx, jy, jz;
-                if ((unsigned)ux < (unsigned)kCaveBox && (unsigned)uy < (unsigned)kCaveBox && (unsigned)uz < (unsigned)kCaveBox)
+                const float* Jc = J + (x * kCaveBox + y) * kCaveBox;
+#pragma unroll
+                for (int z = 0; z < 3; ++z)
                 {
-                    const int c = (ux * kCaveBox + uy) * kCaveBox + uz;
-                    jx = shJit[c]; jy = shJit[c + kCaveBox * kCaveBox * kCaveBox]; jz = shJit[c + 2 * kCaveBox * kCaveBox * kCaveBox];
+                    const float dx = nfx + (Jc[z] + ox), dy = nfy + (Jc[z + N3] + oy), dz = nfz + (Jc[z + 2 * N3] + (float)(z - 1));
+                    insert(fmaf(dz, dz, fmaf(dx, dx, dy * dy)));      // dist = sqrtf(this) in the reference
                 }
-                else
-                    cave_cell_jitter(ix + x, iy + y, iz + z, &jx, &jy, &jz);
-                const float dx = nfx + (jx + (float)x), dy = nfy + (jy + (float)y), dz = nfz + (jz + (float)z);
-                const float q = fmaf(dz, dz, fmaf(dx, dx, dy * dy));      // dist = sqrtf(q) in the reference
-                if (q < q1) { q3 = q2; q2 = q1; q1 = q; }
-                else if (q < q2) { q3 = q2; q2 = q; }
-                else if (q < q3) { q3 = q; }
             }
+        }
+    }
+    else
+    {
+#pragma unroll 1
+        for (int x = -1; x <= 1; ++x)
+#pragma unroll 1
+            for (int y = -1; y <= 1; ++y)
+#pragma unroll 1
+                for (int z = -1; z <= 1; ++z)
+                {
+                    const int ux = ix + x - bx, uy = iy + y - by, uz = iz + z - bz;
+                    float jx, jy, jz;
+                    if ((unsigned)ux < (unsigned)kCaveBox && (unsigned)uy < (unsigned)kCaveBox && (unsigned)uz < (unsigned)kCaveBox)
+                    {
+                        const int c = (ux * kCaveBox + uy) * kCaveBox + uz;
+                        jx = shJit[c]; jy = shJit[c + N3]; jz = shJit[c + 2 * N3];
+                    }
+                    else
+                        cave_cell_jitter(ix + x, iy + y, iz + z, &jx, &jy, &jz);
+                    const float dx = nfx + (jx + (float)x), dy = nfy + (jy + (float)y), dz = nfz + (jz + (float)z);
+                    insert(fmaf(dz, dz, fmaf(dx, dx, dy * dy)));
+                }
+    }
     return sqrtf(q3) / sqrtf(q1) + -1.0f;
 }
 
