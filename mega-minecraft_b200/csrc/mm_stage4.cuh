@@ -165,7 +165,7 @@ constexpr int kCaveBox = 6;
 // monotone (correctly rounded), so the k-th smallest of the rounded roots is the root of the k-th smallest square - the
 // same two numbers the reference's insertion on sqrt'ed distances ends with (equal roots are interchangeable), for 2
 // instead of 27 IEEE square roots per voxel.
-__device__ __forceinline__ float special_cave_noise_cached(float px, float py, float pz, int bx, int by, int bz, const float* shJit)
+__device__ __forceinline__ float special_cave_noise_cached(float px, float py, float pz, int bx, int by, int bz, int ex, int ey, int ez, const float* shJit)
 {
     constexpr int N3 = kCaveBox * kCaveBox * kCaveBox;
     const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
@@ -179,7 +179,8 @@ __device__ __forceinline__ float special_cave_noise_cached(float px, float py, f
         q3 = fminf(q3, q);
     };
     const int ux0 = ix - 1 - bx, uy0 = iy - 1 - by, uz0 = iz - 1 - bz;
-    if ((unsigned)ux0 <= (unsigned)(kCaveBox - 3) && (unsigned)uy0 <= (unsigned)(kCaveBox - 3) && (unsigned)uz0 <= (unsigned)(kCaveBox - 3))
+    // the table holds cells [box, box + (ex, ey, ez)) (ex, ey, ez in 3..kCaveBox: what the slab's voxels touch)
+    if ((unsigned)ux0 <= (unsigned)(ex - 3) && (unsigned)uy0 <= (unsigned)(ey - 3) && (unsigned)uz0 <= (unsigned)(ez - 3))
     {
         // the whole 3x3x3 neighbourhood is in the table (nearly always): no per-cell bounds tests
         const float* J = shJit + (ux0 * kCaveBox + uy0) * kCaveBox + uz0;
@@ -212,7 +213,7 @@ __device__ __forceinline__ float special_cave_noise_cached(float px, float py, f
                 {
                     const int ux = ix + x - bx, uy = iy + y - by, uz = iz + z - bz;
                     float jx, jy, jz;
-                    if ((unsigned)ux < (unsigned)kCaveBox && (unsigned)uy < (unsigned)kCaveBox && (unsigned)uz < (unsigned)kCaveBox)
+                    if ((unsigned)ux < (unsigned)ex && (unsigned)uy < (unsigned)ey && (unsigned)uz < (unsigned)ez)
                     {
                         const int c = (ux * kCaveBox + uy) * kCaveBox + uz;
                         jx = shJit[c]; jy = shJit[c + N3]; jz = shJit[c + 2 * N3];
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(128, MMG_CAVES_MINBLOCKS) k_caves(const int* _
     __shared__ unsigned int shFilled[13];     // bit y = 1 if solid; word 12 = 0 (y = 384 is "not filled")
     __shared__ int shFlips[2 * MAX_CAVE_LAYERS];
     __shared__ int shNumFlips;
-    __shared__ int shBox[3];
+    __shared__ int shBox[6];                  // min corner, max corner of the Worley cells the slab touches
     __shared__ float shJit[3 * kCaveBox * kCaveBox * kCaveBox];
     __shared__ int shNumPending;              // voxels of the slab whose exact threshold is still needed (cave_threshold)
     __shared__ unsigned short shPendY[384];
@@ -387,21 +388,27 @@ __global__ void __launch_bounds__(128, MMG_CAVES_MINBLOCKS) k_caves(const int* _
         // the table costs 5 hashes per thread; even for a single undecided voxel that is fewer warp instructions
         // than its 81 hashes computed in place on one lane - measured.)
         if (tid < 3) shBox[tid] = INT_MAX;
+        else if (tid < 6) shBox[tid] = INT_MIN;
         __syncthreads();
         if (st == 2)
         {
-            atomicMin(&shBox[0], (int)floorf(px) - 1);
-            atomicMin(&shBox[1], (int)floorf(py) - 1);
-            atomicMin(&shBox[2], (int)floorf(pz) - 1);
+            const int cx = (int)floorf(px), cy = (int)floorf(py), cz = (int)floorf(pz);
+            atomicMin(&shBox[0], cx - 1); atomicMin(&shBox[1], cy - 1); atomicMin(&shBox[2], cz - 1);
+            atomicMax(&shBox[3], cx + 1); atomicMax(&shBox[4], cy + 1); atomicMax(&shBox[5], cz + 1);
         }
         __syncthreads();
+        // only the cells the slab's voxels touch are tabulated (typically 4 x 5 x 4, and 3 x 3 x 3 for the dozen voxels of
+        // the second slab; a full 6 x 6 x 6 table per slab was 13 % of the kernel's instructions), at most kCaveBox per axis
         const int bx = shBox[0], by = shBox[1], bz = shBox[2];
+        int ex = 0, ey = 0, ez = 0;
         if (bx != INT_MAX)
         {
             constexpr int N3 = kCaveBox * kCaveBox * kCaveBox;
-            for (int c = tid; c < N3; c += 128)
+            ex = min(shBox[3] - bx + 1, kCaveBox); ey = min(shBox[4] - by + 1, kCaveBox); ez = min(shBox[5] - bz + 1, kCaveBox);
+            for (int i = tid; i < ex * ey * ez; i += 128)
             {
-                const int uz = c % kCaveBox, uy = (c / kCaveBox) % kCaveBox, ux = c / (kCaveBox * kCaveBox);
+                const int uz = i % ez, r = i / ez, uy = r % ey, ux = r / ey;
+                const int c = (ux * kCaveBox + uy) * kCaveBox + uz;
                 float jx, jy, jz;
                 cave_cell_jitter(bx + ux, by + uy, bz + uz, &jx, &jy, &jz);
                 shJit[c] = jx; shJit[c + N3] = jy; shJit[c + 2 * N3] = jz;
@@ -412,7 +419,7 @@ __global__ void __launch_bounds__(128, MMG_CAVES_MINBLOCKS) k_caves(const int* _
         float noise = 0.f;
         if (st == 2)
         {
-            noise = special_cave_noise_cached(px, py, pz, bx, by, bz, shJit);
+            noise = special_cave_noise_cached(px, py, pz, bx, by, bz, ex, ey, ez, shJit);
             const float thrLo = cave_thr(ct, -1.f), thrHi = cave_thr(ct, 1.f);      // thrLo <= thr <= thrHi, thrHi > 0.04 here
             if (noise < thrHi)      // else solid: noise < thr is impossible
             {
