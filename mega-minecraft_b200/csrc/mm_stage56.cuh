@@ -350,25 +350,26 @@ __global__ void k_gather_info(const FeaturePlacement* __restrict__ gF, const Cav
     }
 }
 
-// kernFill (chunk.cu:1382-1510) as three kernels over one batch of chunks. fillList[li] = chunk index into
+// kernFill (chunk.cu:1382-1510) as a sequence of kernels over one batch of chunks. fillList[li] = chunk index into
 // the resident planes (or li itself); gathered lists are indexed by li with the given strides.
-//   k_fill_terrain   chunkFillPlaceBlock for every voxel up to the cave-biome step: one CTA per 128-voxel segment
-//                    of a column (y fastest => a warp stores 32 consecutive block IDs), three segments per column;
-//                    segments above the terrain and the sea are stored as AIR without further work. STONE /
-//                    DEEPSLATE / BLACKSTONE voxels - the only ones getCaveBiome can change - are queued.
-//   k_fill_rock      getCaveBiome + caveBiomeBlockPostProcess for the queued voxels, one per thread on dense warps.
-//                    Voxels that need the LUSH_CAVES clay / moss decision are queued once more.
+//   k_fill_terrain   chunkFillPlaceBlock for every voxel up to the cave-biome step: one CTA per column, three 128-voxel
+//                    segments per thread (y fastest => a warp stores 32 consecutive block IDs); segments above the
+//                    terrain and the sea are stored as AIR without further work. STONE / DEEPSLATE / BLACKSTONE
+//                    voxels - the only ones getCaveBiome can change - are queued (near / bulk regions).
+//   k_fill_rock      getCaveBiome + caveBiomeBlockPostProcess for the queued voxels, one per thread on dense warps;
+//                    bulk voxels first decide what CRYSTAL_CAVES would do to them. Voxels that need the LUSH_CAVES
+//                    clay / moss decision are queued once more.
 //   k_fill_lush      decides the queued voxels, one per thread (they are rare and scattered: evaluated in
 //                    place they would occupy 3-4 lanes of a warp for a 27-cell Worley + 9 simplex).
-//   k_fill_features  the placement scan: per column, the chunk's lists are reduced to the placements whose
-//                    horizontal reach and y band cover it (ordered compaction into shared memory) and
-//                    those are rasterised placement by placement; the reference tests up to 2048 + 4096
+//   k_prepare_placements  per placement of the chunk's gathered lists: the RNG state after seeding and the box its own
+//                    first draws allow (Prep).
+//   k_fill_features  the placement scan, one CTA per 32-voxel slab of a chunk: the placements' boxes are cut into tiles of
+//                    (column, y) pairs that the warps pull from a shared counter; the reference tests up to 2048 + 4096
 //                    placements per voxel.
 // The reference decides terrain and features in one pass per voxel; the feature test only looks at
 // whether the terrain block is AIR, which the lush decision does not change, so the order
 // terrain -> lush -> features gives the same blocks.
 constexpr int kFillSeg = 128;
-constexpr int kColCapF = 512, kColCapC = 1024;   // candidates of one column segment kept in shared memory
 constexpr int kLushQueueCap = 1 << 22;           // queued voxels per fill batch (overflow is decided in place)
 constexpr int kRockQueuePerChunk = 49152;        // rock-queue slots per chunk of a fill batch (typical need ~30 k; overflow is decided in place)
 
