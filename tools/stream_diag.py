@@ -1,3 +1,6 @@
+#!/usr/bin/env python3
+"""Developer tool (GPU box): per-kernel device times of the streaming scheduler (8x and unbounded frame budget), to see which
+kernel a change of the streaming numbers comes from. usage: python tools/stream_diag.py"""
 import os, sys, time
 sys.path.insert(0, os.getcwd())
 import mmgen_loader
