@@ -39,6 +39,9 @@ FLOP_CAVE_BIOME = 11 * F_S3 + 12 * F_S2                           # one getCaveB
 # what k_caves executes of FLOP_CAVE_VOXEL after its exact early-outs (threshold bounds, huge-caves proof, tabulated cell hashes),
 # counted by the census build over the 256x256 world: profiles/r01_census_v8.txt
 EXECUTED_OVER_ALGORITHMIC_CAVES = 0.48
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_caves launch of 4096 chunks (ncu --set full, profiles/r01_k_caves_v9.txt):
+# 26.3 MB read + 376.6 MB written, against 107 528 algorithmic bytes per chunk (98 304 of them the CaveLayer output)
+CAVES_DRAM_BYTES_PER_CHUNK = (26.340352e6 + 376.603904e6) / 4096
 BYTES_FILL_CHUNK = 242688                                         # S6 compulsory I/O per chunk (without feature lists)
 BYTES_CAVES_CHUNK = 107528
 
@@ -332,7 +335,10 @@ def run_own(args):
     fp32_all = max_over_ranks(fp32_measured)
     fp32_peak = min(fp32_all, pk["fp32_tflops"]) if fp32_all > 0 else pk["fp32_tflops"]
     roof = {"bound": "fp32", "kernel": roof_kernel, "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
-            "traffic": None, "avg_launch_ms": avg_launch_ms, "launches_per_step": rk_launches,
+            "traffic": (CAVES_DRAM_BYTES_PER_CHUNK * int((st >= 4).sum()) / rk_launches if roof_kernel == "k_caves" else None),
+            "traffic_src": "ncu capture of one 4096-chunk k_caves launch (profiles/r01_k_caves_v9.txt), scaled to this run's chunks per launch; "
+                           "algorithmic bytes per chunk: 107528",
+            "avg_launch_ms": avg_launch_ms, "launches_per_step": rk_launches,
             "algorithmic_flop_per_launch": flops_of[roof_kernel] / rk_launches,
             "executed": ({"flop_ratio_to_algorithmic": EXECUTED_OVER_ALGORITHMIC_CAVES, "achieved": ach * EXECUTED_OVER_ALGORITHMIC_CAVES,
                           "frac": ach * EXECUTED_OVER_ALGORITHMIC_CAVES / fp32_peak,
