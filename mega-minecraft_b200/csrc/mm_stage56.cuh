@@ -762,14 +762,31 @@ __constant__ const unsigned c_recip16[17] = {0, 65536, 32768, 21846, 16384, 1310
 // The reference's rule "the first placement in list order that contains the voxel wins, surface list before cave list"
 // (chunk.cu:1444-1500) becomes an atomicMin over (list position << 8 | block) per voxel, so the order in which tiles are
 // processed does not matter.
+//
+// Experiment for the next round (-DMMG_SPLIT_FEATURES, NOT validated on a GPU yet; the default build does not contain it): the
+// kernel stalls on instruction fetch (130 KB of rasterisers against a 32 KB L1.5 cache), so the scan is split into a surface
+// pass (PASS 1) and a cave pass (PASS 2) whose rasteriser code (13 KB) fits. "Surface list before cave list" is kept by a
+// per-slab bit mask of the voxels the surface pass claimed (stormlight spheres may replace blocks, so "not AIR" is not enough).
+#ifdef MMG_SPLIT_FEATURES
+template <int PASS>
+#else
+constexpr int PASS = 0;      // 0: both lists in one pass
+#endif
 __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict__ fillList, const int2* __restrict__ origins,
                                                           const FeaturePlacement* __restrict__ gF, const CaveFeaturePlacement* __restrict__ gCF,
                                                           const Prep* __restrict__ prepF, const Prep* __restrict__ prepC,
                                                           const GatherInfo* __restrict__ info, int strideF, int strideCF,
-                                                          uint8_t* __restrict__ blocks)
+                                                          uint8_t* __restrict__ blocks
+#ifdef MMG_SPLIT_FEATURES
+                                                          , unsigned* __restrict__ claimedMasks      // [batch chunk][12 slabs][256 columns]
+#endif
+                                                          )
 {
     __shared__ unsigned shBest[kSlab * kSlabPitch];
     __shared__ unsigned shAir[256];                          // per column: bit yy = the terrain block is AIR
+#ifdef MMG_SPLIT_FEATURES
+    __shared__ unsigned shClaimed[256];                      // PASS 2: per column, bit yy = claimed by a surface placement
+#endif
     __shared__ unsigned shActBase[kRound];                   // active list of the round: first tile number ...
     __shared__ unsigned short shActE[kRound];                // ... and list position of the placement
     __shared__ unsigned shPacked;                            // tiles handed out << 11 | active placements
@@ -780,8 +797,9 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
     const int chunk = fillList ? fillList[li] : li;
     const int t = threadIdx.x, y0 = slab * kSlab, y1 = y0 + kSlab - 1;
     const GatherInfo gi = info[li];
-    const bool segF = gi.nF > 0 && y0 <= gi.fb1 && y1 >= gi.fb0;
-    const bool segC = gi.nCF > 0 && y0 <= gi.cfb1 && y1 >= gi.cfb0;
+    const bool segFAll = gi.nF > 0 && y0 <= gi.fb1 && y1 >= gi.fb0;       // what the surface pass sees
+    const bool segF = PASS != 2 && segFAll;
+    const bool segC = PASS != 1 && gi.nCF > 0 && y0 <= gi.cfb1 && y1 >= gi.cfb0;
     if (!segF && !segC) return;
     const int2 o = origins[chunk];
     // thread t owns column t of the slab (32 consecutive block IDs, 16-byte aligned)
@@ -797,6 +815,11 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
                 if (((w[k] >> (8 * j)) & 0xffu) == (unsigned)B_AIR) air |= 1u << (4 * k + j);
         shAir[t] = air;
     }
+#ifdef MMG_SPLIT_FEATURES
+    // voxels the surface pass claimed (it ran on this slab iff segFAll): out of bounds for every cave placement
+    unsigned* maskPtr = claimedMasks + ((size_t)li * 12 + slab) * 256 + t;
+    if (PASS == 2) shClaimed[t] = segFAll ? *maskPtr : 0u;
+#endif
     for (int i = t; i < kSlab * kSlabPitch; i += 256) shBest[i] = kNoBest;
     if (gi.needNoise) noise_tab_stage();
     const int lane = t & 31;
@@ -825,7 +848,8 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
         {
             const int col = code >> 5, yy = code & 31, x = col & 15, z = col >> 4, y = y0 + yy;
             uint8_t fb = 0;
-            const bool hit = cave ? place_cave_feature(cp, o.x + x, y, o.y + z, k.seed, &fb) : place_feature(fp, o.x + x, y, o.y + z, k.seed, wgeom, &fb);
+            const bool isCave = PASS == 1 ? false : (PASS == 2 ? true : cave);      // a compile-time constant in the split passes
+            const bool hit = isCave ? place_cave_feature(cp, o.x + x, y, o.y + z, k.seed, &fb) : place_feature(fp, o.x + x, y, o.y + z, k.seed, wgeom, &fb);
             if (hit) atomicMin(&shBest[yy * kSlabPitch + col], key | fb);
 #ifdef MMG_FEATURE_STATS
             atomicAdd(&g_featStats[(cave ? 32 : 0) + k.feature][2], 1ull);
@@ -869,10 +893,10 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
             {
                 if (qn > 0) drain();                          // the queue holds fewer than 32 pairs between tiles
                 curE = e;
-                cave = e >= nF;
+                cave = PASS == 1 ? false : (PASS == 2 ? true : e >= nF);
                 k = cave ? pc[e - nF] : pf[e];
                 key = (unsigned)e << 8;
-                if (cave) cp = cf[e - nF];
+                if (PASS == 2 || (PASS == 0 && cave)) cp = cf[e - nF];
                 else
                 {
                     fp = f[e];
@@ -906,6 +930,9 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
                         code[u] = col << 5 | yy;
                         cand[u] = shBest[yy * kSlabPitch + col] > (key | 0xffu) &&      // not claimed by an earlier placement
                                   (k.canReplace || ((shAir[col] >> yy) & 1u));
+#ifdef MMG_SPLIT_FEATURES
+                        if (PASS == 2) cand[u] = cand[u] && !((shClaimed[col] >> yy) & 1u);
+#endif
 #ifdef MMG_FEATURE_STATS
                         atomicAdd(&g_featStats[(cave ? 32 : 0) + k.feature][1], 1ull);
 #endif
@@ -929,6 +956,15 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
         bool any = false;
 #pragma unroll
         for (int yy = 0; yy < kSlab; ++yy) any = any || shBest[yy * kSlabPitch + t] != kNoBest;
+#ifdef MMG_SPLIT_FEATURES
+        if (PASS == 1)
+        {
+            unsigned claimed = 0u;
+#pragma unroll
+            for (int yy = 0; yy < kSlab; ++yy) claimed |= (shBest[yy * kSlabPitch + t] != kNoBest ? 1u : 0u) << yy;
+            *maskPtr = claimed;
+        }
+#endif
         if (any)
         {
             uint4 ab[2] = {reinterpret_cast<const uint4*>(colPtr)[0], reinterpret_cast<const uint4*>(colPtr)[1]};

@@ -193,7 +193,12 @@ int mmgen_init(int device)
     }
     if (!g_stream) MMG_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     // k_fill_features: 40 KB static + the 10 KB noise tables exceed the 48 KB default
+#ifdef MMG_SPLIT_FEATURES
+    MMG_CUDA(cudaFuncSetAttribute(k_fill_features<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNoiseSmemBytes));
+    MMG_CUDA(cudaFuncSetAttribute(k_fill_features<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNoiseSmemBytes));
+#else
     MMG_CUDA(cudaFuncSetAttribute(k_fill_features, cudaFuncAttributeMaxDynamicSharedMemorySize, kNoiseSmemBytes));
+#endif
     MMG_LAUNCH(k_init_noise_tables, 3, 256, 0, g_stream);     // simplex lattice tables (mm_arith.cuh)
     MMG_CUDA(cudaStreamSynchronize(g_stream));
     g_device = device;
@@ -382,8 +387,28 @@ static int launchFill(int m, const int* d_list, const int2* d_origins, const flo
                                                  (const int*)d_counters, d_blocks));
     MMG_TIMED(K_PREPARE, stream, 1, MMG_LAUNCH(k_prepare_placements, m, 256, 0, stream, d_list, d_origins, d_gF, d_gCF, d_info, strideF, strideCF,
                                                d_prepF, d_prepC));
+#ifdef MMG_SPLIT_FEATURES
+    {
+        // experiment (see k_fill_features): surface pass, then cave pass with the surface pass's claimed-voxel masks
+        static unsigned* d_claimed = nullptr;
+        static size_t claimedCap = 0;
+        if ((size_t)m > claimedCap)
+        {
+            cudaFree(d_claimed);
+            MMG_CUDA(cudaMalloc(&d_claimed, (size_t)m * 12 * 256 * sizeof(unsigned)));
+            claimedCap = (size_t)m;
+        }
+        g_kt.begin(K_FILL_FEATURES, stream, 2);
+        MMG_LAUNCH(k_fill_features<1>, m * 12, 256, kNoiseSmemBytes, stream, d_list, d_origins, d_gF, d_gCF, (const Prep*)d_prepF,
+                   (const Prep*)d_prepC, (const GatherInfo*)d_info, strideF, strideCF, d_blocks, d_claimed);
+        MMG_LAUNCH(k_fill_features<2>, m * 12, 256, kNoiseSmemBytes, stream, d_list, d_origins, d_gF, d_gCF, (const Prep*)d_prepF,
+                   (const Prep*)d_prepC, (const GatherInfo*)d_info, strideF, strideCF, d_blocks, d_claimed);
+        g_kt.end(stream);
+    }
+#else
     MMG_TIMED(K_FILL_FEATURES, stream, 1, MMG_LAUNCH(k_fill_features, m * 12, 256, kNoiseSmemBytes, stream, d_list, d_origins, d_gF, d_gCF,
                                                      (const Prep*)d_prepF, (const Prep*)d_prepC, (const GatherInfo*)d_info, strideF, strideCF, d_blocks));
+#endif
     MMG_TIMED(K_DECORATORS, stream, 1, MMG_LAUNCH(k_decorators, m, 256, 0, stream, d_list, m, d_origins, d_height, d_weights, d_caves, d_blocks));
     return 0;
 }   // chunks gathered + filled per launch group (bounds the gathered-list buffers)
