@@ -66,7 +66,9 @@ const char* mmgen_last_error(void);
 /* number of kernel launches issued by this library since mmgen_init (bench.py's gpu_launches) */
 uint64_t mmgen_launch_count(void);
 
-/* ---- batch operators (host pointers) ---- */
+/* ---- batch operators (host pointers) ----
+ * Like the reference's entry points (file-static staging buffers, terrain.cpp:131-152) they share one stream and one set of
+ * device scratch buffers; concurrent calls from several host threads are serialised inside the library. */
 
 /* Chunk::generateHeightfields, chunk.hpp:100-108 / chunk.cu:187-229 */
 int mmgen_heightfields(int n, const int32_t* origins, float* out_heightfield, float* out_biomeWeights);
@@ -96,9 +98,28 @@ int mmgen_feature_placements(int n, const int32_t* origins, const float* heightf
                              MmgenFeaturePlacement* out_features, MmgenCaveFeaturePlacement* out_caveFeatures,
                              int32_t* out_counts);
 
+/* Chunk::gatherFeaturePlacements, chunk.hpp:152 / chunk.cu:1158-1196 (CPU in the reference): the own lists of a chunk's 7x7
+ * neighbourhood concatenated in the reference's fixed order (mmgen_gather_offsets writes that table: 49 (dx, dz) chunk
+ * offsets, chunk.cu:1158-1167). The own lists live in a pool of m chunks laid out as mmgen_feature_placements writes them
+ * (features[m][featureStride], caveFeatures[m][caveFeatureStride], counts[m][2]); neighbours[n][49] holds, for each of the n
+ * chunks to gather for, the pool index of the chunk at offset k (< 0: no such chunk, skipped). Outputs are the lists
+ * Chunk::fill uploads: out_features[n][2048], out_caveFeatures[n][4096] cut at the reference's caps (chunk.cu:1573-1578),
+ * out_counts[n][2] = the untruncated lengths. These are mmgen_fill's inputs (clamp the counts to the caps). */
+int mmgen_gather_offsets(int32_t* out49x2);
+int mmgen_gather_features(int n, const int32_t* neighbours, int m, const MmgenFeaturePlacement* features, int featureStride,
+                          const MmgenCaveFeaturePlacement* caveFeatures, int caveFeatureStride, const int32_t* counts,
+                          MmgenFeaturePlacement* out_features, MmgenCaveFeaturePlacement* out_caveFeatures, int32_t* out_counts);
+
+/* Which reading of Chunk::tryGenerateCaveFeaturePlacement (chunk.cu:1010-1038: no return statement where its jittered-grid
+ * test fails - undefined behaviour) stage 5 follows. 0 (default) = the reference as built by nvcc/g++ on Linux, which drops
+ * the test - the executable oracle of the parity contract; 1 = the source text (test honoured, a failed test is `false`).
+ * Applies to mmgen_feature_placements, the world and the stream from the next call on. */
+int mmgen_set_cave_grid_test(int honoured);
+
 /* Chunk::fill incl. Chunk::placeDecorators, chunk.hpp:154-172 / chunk.cu:1202-1747.
  * features / caveFeatures: the GATHERED lists per chunk (what gatherFeaturePlacements builds,
- * chunk.cu:1158-1196), numFeatures[n][2] = {surface, cave} list lengths (no terminator needed). */
+ * chunk.cu:1158-1196), numFeatures[n][2] = {surface, cave} list lengths (no terminator needed); a length above its
+ * stride is an error. */
 int mmgen_fill(int n, const int32_t* origins, const float* heightfield, const float* biomeWeights,
                const float* layers, const MmgenCaveLayer* caveLayers,
                const MmgenFeaturePlacement* features, const MmgenCaveFeaturePlacement* caveFeatures,
@@ -157,6 +178,8 @@ int mmgen_world_block_checksum(MmgenWorld* w, uint64_t* out);
 /* sum (mod 2^64) over the filled chunks of a 64-bit hash of (chunk coordinates, block volume): the same
  * number however a region is tiled over worlds / GPUs, so tiles can be checked against a single world */
 int mmgen_world_chunk_hash_sum(MmgenWorld* w, uint64_t* out);
+/* the terms of that sum: chunk coordinates (cx, cz) and hash of every filled chunk, raster order; *n = filled chunks (may exceed cap) */
+int mmgen_world_chunk_hashes(MmgenWorld* w, int cap, int32_t* coords, uint64_t* hashes, int* n);
 
 /* ---- streaming scheduler: Terrain::tick (terrain.cpp:587-960) re-hosted on a device-resident world.
  * The reference's ChunkState machine (chunk.hpp:18-32), spiral order (terrain.cpp:220-252), per-stage FIFO

@@ -2,8 +2,9 @@
 // of `Chunk` (/root/reference/src/terrain/chunk.hpp:100-172) that forward to the C ABI in include/mmgen.h.
 //
 // A maintainer of the reference adds this file to the build, links libmmgen.so, and removes (or
-// #ifdef's out) the definitions of the same five functions in src/terrain/chunk.cu (lines 187-229,
-// 417-469, 658-723, 939-993, 1518-1632). Terrain::tick (terrain.cpp:587-960) and everything else in the
+// #ifdef's out) the definitions of the same functions in src/terrain/chunk.cu: the five batch entry points (lines 187-229,
+// 417-469, 658-723, 939-993, 1518-1632) and the two CPU passes of stage 5 (generateFeaturePlacements :1147-1156,
+// otherChunkGatherFeaturePlacements :1169-1187, the data movement of gatherFeaturePlacements). Terrain::tick (terrain.cpp:587-960) and everything else in the
 // application stay as they are: same signatures, same ownership (the staging buffers Terrain passes in
 // are used as the host-side batch buffers; the dev_* pointers and the stream are unused because the
 // library owns its device memory), same result contract (per-chunk host arrays complete on return).
@@ -13,6 +14,7 @@
 // run the reference state machine on the new kernels (tests/test_gpu_parity.py::test_adapter_*).
 #include "terrain/chunk.hpp"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -29,6 +31,8 @@ void check(int rc, const char* what)
     std::exit(EXIT_FAILURE);
 }
 
+int g_calls[7];      // how often each entry point below ran (mmadapter_calls: lets a test see that the overrides are the ones in use)
+
 void ensureInit()
 {
     static bool ready = false;
@@ -41,10 +45,13 @@ void ensureInit()
 
 }  // namespace
 
+extern "C" int mmadapter_calls(int entryPoint) { return (entryPoint >= 0 && entryPoint < 7) ? g_calls[entryPoint] : -1; }
+
 void Chunk::generateHeightfields(std::vector<Chunk*>& chunks, ivec2* host_chunkWorldBlockPositions, ivec2*, float* host_heightfields, float*,
                                  float* host_biomeWeights, float*, cudaStream_t)
 {
     ensureInit();
+    ++g_calls[0];
     const int n = (int)chunks.size();
     for (int i = 0; i < n; ++i) host_chunkWorldBlockPositions[i] = ivec2(chunks[i]->worldBlockPos.x, chunks[i]->worldBlockPos.z);
     check(mmgen_heightfields(n, (const int32_t*)host_chunkWorldBlockPositions, host_heightfields, host_biomeWeights), "Chunk::generateHeightfield()");
@@ -59,6 +66,7 @@ void Chunk::generateLayers(std::vector<Chunk*>& chunks, float* host_heightfields
                            ivec2* host_chunkWorldBlockPositions, ivec2*, float* host_layers, float*, cudaStream_t)
 {
     ensureInit();
+    ++g_calls[1];
     const int n = (int)chunks.size();
     for (int i = 0; i < n; ++i)
     {
@@ -75,6 +83,7 @@ void Chunk::generateLayers(std::vector<Chunk*>& chunks, float* host_heightfields
 void Chunk::erodeZone(Zone* zonePtr, float* host_gatheredLayers, float*, float*, cudaStream_t)
 {
     ensureInit();
+    ++g_calls[2];
     // copyLayers(zone, gathered, true) (chunk.cu:603-656): 8 loose layer planes + the heightfield plane of the 24x24-chunk window
     constexpr int side = EROSION_GRID_SIDE_LENGTH_BLOCKS, cols = EROSION_GRID_NUM_COLS;
     for (int cz = 0; cz < ZONE_SIZE * 2; ++cz)
@@ -110,6 +119,7 @@ void Chunk::generateCaves(std::vector<Chunk*>& chunks, float* host_heightfields,
                           ivec2* host_chunkWorldBlockPositions, ivec2*, CaveLayer* host_caveLayers, CaveLayer*, cudaStream_t)
 {
     ensureInit();
+    ++g_calls[3];
     const int n = (int)chunks.size();
     for (int i = 0; i < n; ++i)
     {
@@ -129,6 +139,7 @@ void Chunk::fill(std::vector<Chunk*>& chunks, float* host_heightfields, float*, 
                  CaveLayer* host_caveLayers, CaveLayer*, FeaturePlacement*, CaveFeaturePlacement*, Block* host_blocks, Block*, cudaStream_t)
 {
     ensureInit();
+    ++g_calls[4];
     static_assert(sizeof(FeaturePlacement) == sizeof(MmgenFeaturePlacement) && sizeof(CaveFeaturePlacement) == sizeof(MmgenCaveFeaturePlacement),
                   "placement wire layouts");
     const int n = (int)chunks.size();
@@ -168,4 +179,61 @@ void Chunk::fill(std::vector<Chunk*>& chunks, float* host_heightfields, float*, 
                      (uint8_t*)host_blocks),
           "Chunk::fill()");
     for (int i = 0; i < n; ++i) std::memcpy(chunks[i]->blocks.data(), host_blocks + i * devBlocksSize, devBlocksSize * sizeof(Block));
+}
+
+// ---- stage 5 (CPU passes in the reference): per-chunk member functions, so one chunk per call
+void Chunk::generateFeaturePlacements()
+{
+    ensureInit();
+    ++g_calls[5];
+    static std::vector<MmgenFeaturePlacement> f(256);
+    static std::vector<MmgenCaveFeaturePlacement> cf(MMGEN_MAX_CAVE_FEATURES);
+    const int32_t origin[2] = {worldBlockPos.x, worldBlockPos.z};
+    int32_t counts[2] = {0, 0};
+    // a chunk's own cave list is only ever consumed up to the gather cap (it is first or later in every concatenation)
+    check(mmgen_feature_placements(1, origin, heightfield.data(), biomeWeights.data(), layers.data(), (const MmgenCaveLayer*)caveLayers.data(),
+                                   MMGEN_MAX_CAVE_FEATURES, f.data(), cf.data(), counts),
+          "Chunk::generateFeaturePlacements()");
+    const FeaturePlacement* pf = (const FeaturePlacement*)f.data();
+    const CaveFeaturePlacement* pc = (const CaveFeaturePlacement*)cf.data();
+    featurePlacements.assign(pf, pf + std::min<int>(counts[0], 256));
+    caveFeaturePlacements.assign(pc, pc + std::min<int>(counts[1], MMGEN_MAX_CAVE_FEATURES));
+}
+
+void Chunk::otherChunkGatherFeaturePlacements(Chunk* chunkPtr, Chunk* const (&neighborChunks)[13][13], int centerX, int centerZ)
+{
+    ensureInit();
+    ++g_calls[6];
+    static int32_t offsets[49][2];
+    static bool haveOffsets = false;
+    if (!haveOffsets) { check(mmgen_gather_offsets(&offsets[0][0]), "mmgen_gather_offsets"); haveOffsets = true; }
+    // pool = the 49 neighbours in the reference's order (chunk.cu:1158-1167), so neighbours[k] = k
+    const Chunk* nb[49];
+    size_t strideF = 1, strideC = 1;
+    for (int k = 0; k < 49; ++k)
+    {
+        nb[k] = neighborChunks[centerZ + offsets[k][1]][centerX + offsets[k][0]];
+        strideF = std::max(strideF, nb[k]->featurePlacements.size());
+        strideC = std::max(strideC, nb[k]->caveFeaturePlacements.size());
+    }
+    static std::vector<FeaturePlacement> poolF, outF(MMGEN_MAX_FEATURES);
+    static std::vector<CaveFeaturePlacement> poolC, outC(MMGEN_MAX_CAVE_FEATURES);
+    poolF.assign(49 * strideF, FeaturePlacement{Feature::NONE});
+    poolC.assign(49 * strideC, CaveFeaturePlacement{CaveFeature::NONE});
+    int32_t idx[49], counts[49][2], outCounts[2] = {0, 0};
+    for (int k = 0; k < 49; ++k)
+    {
+        idx[k] = k;
+        std::copy(nb[k]->featurePlacements.begin(), nb[k]->featurePlacements.end(), poolF.begin() + k * strideF);
+        std::copy(nb[k]->caveFeaturePlacements.begin(), nb[k]->caveFeaturePlacements.end(), poolC.begin() + k * strideC);
+        counts[k][0] = (int32_t)nb[k]->featurePlacements.size();
+        counts[k][1] = (int32_t)nb[k]->caveFeaturePlacements.size();
+    }
+    check(mmgen_gather_features(1, idx, 49, (const MmgenFeaturePlacement*)poolF.data(), (int)strideF, (const MmgenCaveFeaturePlacement*)poolC.data(),
+                                (int)strideC, &counts[0][0], (MmgenFeaturePlacement*)outF.data(), (MmgenCaveFeaturePlacement*)outC.data(), outCounts),
+          "Chunk::gatherFeaturePlacements()");
+    // the reference clears the surface list only (chunk.cu:1171); both are cleared after the fill (chunk.cu:1586, 1601)
+    chunkPtr->gatheredFeaturePlacements.assign(outF.begin(), outF.begin() + std::min<int>(outCounts[0], MMGEN_MAX_FEATURES));
+    chunkPtr->gatheredCaveFeaturePlacements.insert(chunkPtr->gatheredCaveFeaturePlacements.end(), outC.begin(),
+                                                   outC.begin() + std::min<int>(outCounts[1], MMGEN_MAX_CAVE_FEATURES));
 }

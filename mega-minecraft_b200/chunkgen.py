@@ -145,6 +145,33 @@ class ChunkGen:
         return [F[i, :min(counts[i, 0], max_per_chunk)].copy() for i in range(n)], \
                [CF[i, :min(counts[i, 1], max_per_chunk)].copy() for i in range(n)]
 
+    def gather_offsets(self):
+        """The reference's 49 (dx, dz) chunk offsets in gather order (chunk.cu:1158-1167)."""
+        out = np.zeros((49, 2), np.int32)
+        self._check(self.L.mmgen_gather_offsets(_ptr(out)))
+        return out
+
+    def gather_features(self, neighbours, features, cave_features):
+        """Chunk::gatherFeaturePlacements (chunk.cu:1158-1196). features / cave_features: own lists of a pool of chunks (as
+        feature_placements returns them); neighbours: (n, 49) pool indices in the reference's order (-1 = absent).
+        Returns (gathered, gathered_cave, counts): per-chunk lists cut at 2048 / 4096 and the untruncated (n, 2) counts."""
+        nb = np.ascontiguousarray(neighbours, np.int32).reshape(-1, 49)
+        n, m = nb.shape[0], len(features)
+        sf = max(1, max(len(f) for f in features))
+        sc = max(1, max(len(f) for f in cave_features))
+        F = np.zeros((m, sf), FeaturePlacement)
+        CF = np.zeros((m, sc), CaveFeaturePlacement)
+        counts = np.zeros((m, 2), np.int32)
+        for i in range(m):
+            F[i, :len(features[i])] = features[i]
+            CF[i, :len(cave_features[i])] = cave_features[i]
+            counts[i] = (len(features[i]), len(cave_features[i]))
+        oF = np.zeros((n, 2048), FeaturePlacement)
+        oC = np.zeros((n, 4096), CaveFeaturePlacement)
+        oc = np.zeros((n, 2), np.int32)
+        self._check(self.L.mmgen_gather_features(n, _ptr(nb), m, _ptr(F), sf, _ptr(CF), sc, _ptr(counts), _ptr(oF), _ptr(oC), _ptr(oc)))
+        return [oF[i, :min(oc[i, 0], 2048)].copy() for i in range(n)], [oC[i, :min(oc[i, 1], 4096)].copy() for i in range(n)], oc
+
     def fill(self, origins, heightfield, weights, layers, cave_layers, gathered, gathered_cave):
         """Chunk::fill incl. placeDecorators (chunk.cu:1518-1747); gathered lists per chunk, untruncated."""
         origins = np.ascontiguousarray(origins, dtype=np.int32).reshape(-1, 2)
@@ -256,6 +283,15 @@ class World:
         v = ctypes.c_uint64(0)
         self.gen._check(self.L.mmgen_world_chunk_hash_sum(self.h, ctypes.byref(v)))
         return v.value
+
+    def chunk_hashes(self):
+        """{(cx, cz): 64-bit hash of (coordinates, block volume)} for every filled chunk; chunk_hash_sum() is their sum mod 2^64."""
+        cap = self.n
+        coords = np.zeros((cap, 2), np.int32)
+        hs = np.zeros(cap, np.uint64)
+        n = ctypes.c_int(0)
+        self.gen._check(self.L.mmgen_world_chunk_hashes(self.h, cap, _ptr(coords), _ptr(hs), ctypes.byref(n)))
+        return {(int(coords[k, 0]), int(coords[k, 1])): int(hs[k]) for k in range(n.value)}
 
     def download_features(self, max_per_chunk=4096):
         F = np.zeros((self.n, max_per_chunk), FeaturePlacement)

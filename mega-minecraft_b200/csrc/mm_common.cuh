@@ -35,7 +35,8 @@ inline int fail(const char* what, cudaError_t err, const char* file, int line)
         MMG_CUDA(cudaGetLastError());                                         \
     } while (0)
 
-constexpr int kNumSMs = 148;   // B200
+extern int g_numSMs;            // multiprocessor count of the bound device (148 on a B200), set by mmgen_init
+#define kNumSMs (::mmg::g_numSMs)
 
 // resident CTAs per SM the register allocator is asked to allow (tuned on a B200)
 #ifndef MMG_CAVES_MINBLOCKS

@@ -7,7 +7,14 @@
 
 namespace mmg {
 
-constexpr bool kCaveGridTestIgnored = true;
+// Chunk::tryGenerateCaveFeaturePlacement (chunk.cu:1010-1038) has no return statement on the path where its jittered-grid
+// test fails: undefined behaviour. The reference as built on this image (nvcc 12.9 host pass = g++ 13 -O3) resolves it by
+// dropping the test - a cave feature is emitted in every column that passes the chance / ceiling / lava / min-height tests
+// (seen in the disassembly of the reference object and in its outputs) - and that build is the executable oracle the
+// parity contract names, so it is the default here (0). mmgen_set_cave_grid_test(1) selects the reading of the source
+// text instead: the grid test is honoured and a failed test counts as `false` (the walk goes on to the next generator) -
+// what a compiler that keeps the test produces (the reference targets MSVC). DESIGN.md section 2 lists this switch.
+__device__ int g_caveGridTestHonoured = 0;
 
 // chunk.cu:999-1008 (host arithmetic)
 __device__ __forceinline__ bool is_feature_pos(int wx, int wz, int cell, int pad, int seed)

@@ -49,7 +49,7 @@ __device__ __forceinline__ void column_features(int wx, int wz, float height, co
                 if (rand >= gen.chance || top != (gen.fromCeiling != 0) || (!gen.inLava && (top ? cl.end : cl.start + 1) <= LAVA_LEVEL) ||
                     layerHeight < gen.minLayerHeight)
                     continue;
-                if (kCaveGridTestIgnored || is_feature_pos(wx, wz, gen.cell, gen.pad, seed))
+                if (!g_caveGridTestHonoured || is_feature_pos(wx, wz, gen.cell, gen.pad, seed))
                 {
                     if (outCF && nc < maxCave)
                     {
@@ -312,6 +312,46 @@ __global__ void __launch_bounds__(256) k_gather_features(const int* __restrict__
         gi.fb0 = shMin[0]; gi.fb1 = shMax[0]; gi.cfb0 = shMin[1]; gi.cfb1 = shMax[1];
         gi.needNoise = 1; gi.pad = 0;
         info[li] = gi;
+    }
+}
+
+// Batch-operator form of Chunk::gatherFeaturePlacements (chunk.cu:1158-1196): one CTA per chunk to gather for. The own lists
+// of its 49 neighbours (indices into a pool of chunks, in the order of the reference's offset table; < 0 = absent) are
+// concatenated in that order, nothing culled, and cut at the caps the reference's fill uploads (2048 / 4096,
+// chunk.cu:1573-1578); outCounts holds the untruncated lengths, which is what the reference's host vectors would hold.
+__global__ void __launch_bounds__(256) k_gather_concat(const int* __restrict__ neighbours, const FeaturePlacement* __restrict__ features, int strideF,
+                                                       const CaveFeaturePlacement* __restrict__ caveFeatures, int strideC,
+                                                       const int* __restrict__ counts, FeaturePlacement* __restrict__ outF,
+                                                       CaveFeaturePlacement* __restrict__ outC, int* __restrict__ outCounts)
+{
+    __shared__ int shSrc[49], shN[2][49], shOff[2][50];
+    const int li = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 49)
+    {
+        const int src = neighbours[li * 49 + tid];
+        shSrc[tid] = src;
+        shN[0][tid] = src >= 0 ? min(counts[2 * src], strideF) : 0;
+        shN[1][tid] = src >= 0 ? min(counts[2 * src + 1], strideC) : 0;
+    }
+    __syncthreads();
+    if (tid < 2)
+    {
+        int run = 0;
+        for (int k = 0; k < 49; ++k) { shOff[tid][k] = run; run += shN[tid][k]; }
+        shOff[tid][49] = run;
+        outCounts[2 * li + tid] = run;
+    }
+    __syncthreads();
+    for (int k = warp; k < 49; k += 8)
+    {
+        const int src = shSrc[k];
+        if (src < 0) continue;
+        const FeaturePlacement* sf = features + (size_t)src * strideF;
+        const CaveFeaturePlacement* sc = caveFeatures + (size_t)src * strideC;
+        for (int i = lane; i < shN[0][k]; i += 32)
+            if (shOff[0][k] + i < MAX_FEATURES) outF[(size_t)li * MAX_FEATURES + shOff[0][k] + i] = sf[i];
+        for (int i = lane; i < shN[1][k]; i += 32)
+            if (shOff[1][k] + i < MAX_CAVE_FEATURES) outC[(size_t)li * MAX_CAVE_FEATURES + shOff[1][k] + i] = sc[i];
     }
 }
 
@@ -616,11 +656,14 @@ __global__ void __launch_bounds__(128) k_fill_lush(const int2* __restrict__ orig
 // What k_fill_features needs to know about a placement before it touches the rasteriser: the y band it can
 // fill (reference bound intersected with the type's own band, clipped to the world), the columns of THIS
 // chunk its horizontal reach covers, and whether it may overwrite terrain. lo > hi: cannot touch the chunk.
-__device__ unsigned g_debugFeatureMask = 0xffffffffu;      // mmgen_debug_feature_mask: profiling experiments only
 #ifdef MMG_FEATURE_STATS
+__device__ unsigned g_debugFeatureMask = 0xffffffffu;      // mmgen_debug_feature_mask: developer build only
+#define MMG_FEATURE_ENABLED(bit) ((g_debugFeatureMask >> (bit)) & 1u)
 // developer build (tools/feature_census.py): per feature type [0..20] surface, [32..41] cave: warp clock cycles spent in the
 // rasteriser loop, (column, y) pairs put on the rasteriser, pairs that reached the rasteriser call, hits
 __device__ unsigned long long g_featStats[64][4];
+#else
+#define MMG_FEATURE_ENABLED(bit) true
 #endif
 struct Prep { short lo, hi; unsigned char xr, zr, canReplace, feature; uint32_t seed; };      // xr = x0 | x1 << 4 (local 0..15), zr likewise;
                                                                                               // seed = state of the placement's own RNG
@@ -654,7 +697,7 @@ __global__ void __launch_bounds__(256) k_prepare_placements(const int* __restric
         k.seed = make_rng4(p.x, p.y, p.z, 1293012).x;      // featurePlacement.hpp:153: seeded once per placement here, not per voxel
         int reach = 0, yHi = 0;
         if (p.feature == F_NONE) atomicMin(&shFirstNone[0], i);
-        else if (!((g_debugFeatureMask >> p.feature) & 1u)) { /* experiment knob: type switched off */ }
+        else if (!MMG_FEATURE_ENABLED(p.feature)) { /* developer build: type switched off */ }
         else if (surface_feature_extent(p, &reach, &yHi), columns(p.x, p.z, reach, &k))
         {
             k.lo = (short)max(p.y + c_featureHeightBounds[p.feature][0], 0);
@@ -711,7 +754,7 @@ __global__ void __launch_bounds__(256) k_prepare_placements(const int* __restric
         default: break;
         }
         if (p.feature == CF_NONE) atomicMin(&shFirstNone[1], i);
-        else if (!((g_debugFeatureMask >> (21 + p.feature)) & 1u)) { /* experiment knob: type switched off */ }
+        else if (!MMG_FEATURE_ENABLED(21 + p.feature)) { /* developer build: type switched off */ }
         else if (columns(p.x, p.z, reach, &k))
         {
             const int* band = c_caveFeatureBand[p.feature];
@@ -736,70 +779,55 @@ constexpr int kSlab = 32;                  // voxels of a column per CTA of k_fi
 constexpr int kSlabPitch = 257;            // shBest[yy][col], padded: lanes that differ in yy hit different banks
 constexpr unsigned kNoBest = 0xffffffffu;
 constexpr int kRound = 1024;               // placements scanned per round (the round's active list lives in shared memory)
+// ceil(65536 / n), n = 1..16 ([0] unused): (c * c_recip16[n]) >> 16 = c / n for c < 256
+__constant__ const unsigned c_recip16[17] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096};
+
+// columns of a placement's box that make one unit of work (tile): about 512 (column, y) pairs, at least one warp of columns
 #ifndef MMG_TILE
 #define MMG_TILE 512
 #endif
-constexpr int kTile = MMG_TILE;            // (column, y) pairs of one unit of work
-// ceil(2^32 / n), n = 2..32 ([0], [1] unused)
-__constant__ const unsigned c_recip32[33] = {0, 0, 0x80000000u, 0x55555556u, 0x40000000u, 0x33333334u, 0x2aaaaaabu, 0x24924925u, 0x20000000u,
-    0x1c71c71du, 0x1999999au, 0x1745d175u, 0x15555556u, 0x13b13b14u, 0x12492493u, 0x11111112u, 0x10000000u, 0x0f0f0f10u, 0x0e38e38fu,
-    0x0d79435fu, 0x0ccccccdu, 0x0c30c30du, 0x0ba2e8bbu, 0x0b21642du, 0x0aaaaaabu, 0x0a3d70a4u, 0x09d89d8au, 0x097b425fu, 0x0924924au,
-    0x08d3dcb1u, 0x08888889u, 0x08421085u, 0x08000000u};
-__constant__ const unsigned c_recip16[17] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096};
+__device__ __forceinline__ int cols_per_tile(int ny) { return ny >= MMG_TILE / 32 ? 32 : (ny >= MMG_TILE / 64 ? 64 : (ny >= MMG_TILE / 128 ? 128 : 256)); }
 
 // Placement scan of one 32-voxel slab of a chunk (12 slabs per chunk). Work is distributed by PLACEMENT, not by voxel: a
-// placement's box clipped to this chunk and slab is a list of (column, y) pairs, cut into tiles of kTile pairs, and the
+// placement's box clipped to this chunk and slab is a set of columns with a y band, cut into tiles of columns, and the
 // warps of the CTA pull tiles from a shared counter - so the lanes of a warp rasterise the same feature on different voxels
 // instead of one voxel testing hundreds of candidates (a column of a crystal-cave chunk is within reach of ~400 stormlight
 // spheres), and a mushroom's 8000 pairs are shared by all warps while a vine's 15 occupy one warp for one step.
 //   round (kRound placements): every thread tests the Prep records of its placements against the slab; the ones that touch
 //     it enter the round's active list with their first tile number (one packed shared-memory atomic hands out both, so
 //     tile numbers grow with the slot and a tile finds its placement by binary search);
-//   tile: a cheap filter (voxel already claimed by an earlier placement / solid and the placement may not replace blocks)
-//     pushes the surviving pairs onto the warp's queue and the rasteriser runs on full warps popped from it - a cave
-//     feature's box is mostly rock, so without the queue 3 or 4 lanes of 32 reach the rasteriser. The queue is kept while
-//     the warp's next tile belongs to the same placement.
+//   tile: each lane takes a COLUMN of the box and builds the 32-bit mask of its candidate voxels in one step - the band,
+//     ANDed with the column's air mask unless the placement may replace blocks (a cave feature's box is mostly rock: 11-15 %
+//     of the pairs are candidates, and the voxel-at-a-time filter that used to find them was 57 % of the kernel's
+//     instructions, ncu profiles/r01_k_fill_features_v8.txt). The set bits are handed to the warp's queue two per lane and
+//     round; a voxel some placement already claimed (per-column claim mask) is dropped there if the claim is an earlier
+//     placement's. The rasteriser runs on full warps popped from the queue, which is kept while the warp's next tile
+//     belongs to the same placement.
 // The reference's rule "the first placement in list order that contains the voxel wins, surface list before cave list"
 // (chunk.cu:1444-1500) becomes an atomicMin over (list position << 8 | block) per voxel, so the order in which tiles are
-// processed does not matter.
-//
-// Experiment for the next round (-DMMG_SPLIT_FEATURES, NOT validated on a GPU yet; the default build does not contain it): the
-// kernel stalls on instruction fetch (130 KB of rasterisers against a 32 KB L1.5 cache), so the scan is split into a surface
-// pass (PASS 1) and a cave pass (PASS 2) whose rasteriser code (13 KB) fits. "Surface list before cave list" is kept by a
-// per-slab bit mask of the voxels the surface pass claimed (stormlight spheres may replace blocks, so "not AIR" is not enough).
-#ifdef MMG_SPLIT_FEATURES
-template <int PASS>
-#else
-constexpr int PASS = 0;      // 0: both lists in one pass
-#endif
+// processed does not matter. (A split into a surface pass and a cave pass, to shrink the code each pass keeps in the
+// instruction cache, was measured in round 2: 214 ms against 162 ms per 256x256 world - dropped.)
 __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict__ fillList, const int2* __restrict__ origins,
                                                           const FeaturePlacement* __restrict__ gF, const CaveFeaturePlacement* __restrict__ gCF,
                                                           const Prep* __restrict__ prepF, const Prep* __restrict__ prepC,
                                                           const GatherInfo* __restrict__ info, int strideF, int strideCF,
-                                                          uint8_t* __restrict__ blocks
-#ifdef MMG_SPLIT_FEATURES
-                                                          , unsigned* __restrict__ claimedMasks      // [batch chunk][12 slabs][256 columns]
-#endif
-                                                          )
+                                                          uint8_t* __restrict__ blocks)
 {
     __shared__ unsigned shBest[kSlab * kSlabPitch];
     __shared__ unsigned shAir[256];                          // per column: bit yy = the terrain block is AIR
-#ifdef MMG_SPLIT_FEATURES
-    __shared__ unsigned shClaimed[256];                      // PASS 2: per column, bit yy = claimed by a surface placement
-#endif
+    __shared__ unsigned shClaim[256];                        // per column: bit yy = some placement has claimed the voxel (shBest != kNoBest)
     __shared__ unsigned shActBase[kRound];                   // active list of the round: first tile number ...
     __shared__ unsigned short shActE[kRound];                // ... and list position of the placement
     __shared__ unsigned shPacked;                            // tiles handed out << 11 | active placements
     __shared__ int shNextTile;
     __shared__ float shGeom[8 * kMushroomGeomFloats];        // per warp: purple_mushroom_geom of the placement being rasterised
-    __shared__ unsigned short shQueue[8 * 96];               // per warp: pairs that passed the filter, waiting for a full warp (< 32 + 2 x 32)
+    __shared__ unsigned short shQueue[8 * 96];               // per warp: candidates waiting for a full warp (< 32 + 2 x 32)
     const int slab = blockIdx.x % 12, li = blockIdx.x / 12;
     const int chunk = fillList ? fillList[li] : li;
     const int t = threadIdx.x, y0 = slab * kSlab, y1 = y0 + kSlab - 1;
     const GatherInfo gi = info[li];
-    const bool segFAll = gi.nF > 0 && y0 <= gi.fb1 && y1 >= gi.fb0;       // what the surface pass sees
-    const bool segF = PASS != 2 && segFAll;
-    const bool segC = PASS != 1 && gi.nCF > 0 && y0 <= gi.cfb1 && y1 >= gi.cfb0;
+    const bool segF = gi.nF > 0 && y0 <= gi.fb1 && y1 >= gi.fb0;
+    const bool segC = gi.nCF > 0 && y0 <= gi.cfb1 && y1 >= gi.cfb0;
     if (!segF && !segC) return;
     const int2 o = origins[chunk];
     // thread t owns column t of the slab (32 consecutive block IDs, 16-byte aligned)
@@ -814,12 +842,8 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
             for (int j = 0; j < 4; ++j)
                 if (((w[k] >> (8 * j)) & 0xffu) == (unsigned)B_AIR) air |= 1u << (4 * k + j);
         shAir[t] = air;
+        shClaim[t] = 0u;
     }
-#ifdef MMG_SPLIT_FEATURES
-    // voxels the surface pass claimed (it ran on this slab iff segFAll): out of bounds for every cave placement
-    unsigned* maskPtr = claimedMasks + ((size_t)li * 12 + slab) * 256 + t;
-    if (PASS == 2) shClaimed[t] = segFAll ? *maskPtr : 0u;
-#endif
     for (int i = t; i < kSlab * kSlabPitch; i += 256) shBest[i] = kNoBest;
     if (gi.needNoise) noise_tab_stage();
     const int lane = t & 31;
@@ -838,7 +862,7 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
     FeaturePlacement fp = {};
     CaveFeaturePlacement cp = {};
     unsigned key = 0u;
-    // rasterises up to 32 queued pairs of the current placement
+    // rasterises up to 32 queued voxels of the current placement
     auto drain = [&]() {
         const int n = min(qn, 32);
         qn -= n;
@@ -848,9 +872,12 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
         {
             const int col = code >> 5, yy = code & 31, x = col & 15, z = col >> 4, y = y0 + yy;
             uint8_t fb = 0;
-            const bool isCave = PASS == 1 ? false : (PASS == 2 ? true : cave);      // a compile-time constant in the split passes
-            const bool hit = isCave ? place_cave_feature(cp, o.x + x, y, o.y + z, k.seed, &fb) : place_feature(fp, o.x + x, y, o.y + z, k.seed, wgeom, &fb);
-            if (hit) atomicMin(&shBest[yy * kSlabPitch + col], key | fb);
+            const bool hit = cave ? place_cave_feature(cp, o.x + x, y, o.y + z, k.seed, &fb) : place_feature(fp, o.x + x, y, o.y + z, k.seed, wgeom, &fb);
+            if (hit)
+            {
+                atomicMin(&shBest[yy * kSlabPitch + col], key | fb);
+                atomicOr(&shClaim[col], 1u << yy);
+            }
 #ifdef MMG_FEATURE_STATS
             atomicAdd(&g_featStats[(cave ? 32 : 0) + k.feature][2], 1ull);
             if (hit) atomicAdd(&g_featStats[(cave ? 32 : 0) + k.feature][3], 1ull);
@@ -869,8 +896,8 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
             const Prep q = e >= nF ? pc[e - nF] : pf[e];
             const int lo = max((int)q.lo, y0), hi = min((int)q.hi, y1);
             if (lo > hi) continue;
-            const int total = ((q.xr >> 4) - (q.xr & 15) + 1) * ((q.zr >> 4) - (q.zr & 15) + 1) * (hi - lo + 1);
-            const unsigned old = atomicAdd(&shPacked, (unsigned)((total + kTile - 1) / kTile) << 11 | 1u);
+            const int ncols = ((q.xr >> 4) - (q.xr & 15) + 1) * ((q.zr >> 4) - (q.zr & 15) + 1), cpt = cols_per_tile(hi - lo + 1);
+            const unsigned old = atomicAdd(&shPacked, (unsigned)((ncols + cpt - 1) / cpt) << 11 | 1u);
             shActE[old & 0x7ffu] = (unsigned short)e;
             shActBase[old & 0x7ffu] = old >> 11;
         }
@@ -888,15 +915,15 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
                 const int mid = (s0 + s1 + 1) >> 1;
                 if ((int)shActBase[mid] <= tile) s0 = mid; else s1 = mid - 1;
             }
-            const int e = shActE[s0], firstPair = (tile - (int)shActBase[s0]) * kTile;
+            const int e = shActE[s0];
             if (e != curE)
             {
-                if (qn > 0) drain();                          // the queue holds fewer than 32 pairs between tiles
+                if (qn > 0) drain();                          // the queue holds fewer than 32 voxels between tiles
                 curE = e;
-                cave = PASS == 1 ? false : (PASS == 2 ? true : e >= nF);
+                cave = e >= nF;
                 k = cave ? pc[e - nF] : pf[e];
                 key = (unsigned)e << 8;
-                if (PASS == 2 || (PASS == 0 && cave)) cp = cf[e - nF];
+                if (cave) cp = cf[e - nF];
                 else
                 {
                     fp = f[e];
@@ -910,41 +937,49 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
             }
             const int lo = max((int)k.lo, y0), hi = min((int)k.hi, y1);
             const int x0 = k.xr & 15, nxc = (k.xr >> 4) - x0 + 1, z0 = k.zr & 15, nzc = (k.zr >> 4) - z0 + 1;
-            const int ny = hi - lo + 1;
-            const int lastPair = min(firstPair + kTile, nxc * nzc * ny);      // y fastest
-            const unsigned rny = c_recip32[ny];                               // ceil(2^32 / ny): __umulhi(p, rny) = p / ny for p < 2^27
-            // two rounds of 32 pairs per iteration: two independent index / load chains in flight
-            for (int base = firstPair; base < lastPair; base += 64)
-            {
-                bool cand[2] = {false, false};
-                int code[2] = {0, 0};
-#pragma unroll
-                for (int u = 0; u < 2; ++u)
-                {
-                    const int p = base + 32 * u + lane;
-                    if (p < lastPair)
-                    {
-                        const int q = ny > 1 ? (int)__umulhi((unsigned)p, rny) : p, dy = p - q * ny;
-                        const int dz = (int)((q * c_recip16[nxc]) >> 16), dx = q - dz * nxc;
-                        const int col = (x0 + dx) + 16 * (z0 + dz), yy = lo + dy - y0;
-                        code[u] = col << 5 | yy;
-                        cand[u] = shBest[yy * kSlabPitch + col] > (key | 0xffu) &&      // not claimed by an earlier placement
-                                  (k.canReplace || ((shAir[col] >> yy) & 1u));
-#ifdef MMG_SPLIT_FEATURES
-                        if (PASS == 2) cand[u] = cand[u] && !((shClaimed[col] >> yy) & 1u);
-#endif
+            const int ny = hi - lo + 1, cpt = cols_per_tile(ny);
+            const int c0 = (tile - (int)shActBase[s0]) * cpt, c1 = min(c0 + cpt, nxc * nzc);
+            const unsigned band = (0xffffffffu >> (32 - ny)) << (lo - y0);      // 1 <= ny <= 32
+            const unsigned rnx = c_recip16[nxc];
 #ifdef MMG_FEATURE_STATS
-                        atomicAdd(&g_featStats[(cave ? 32 : 0) + k.feature][1], 1ull);
+            if (lane == 0) atomicAdd(&g_featStats[(cave ? 32 : 0) + k.feature][1], (unsigned long long)((c1 - c0) * ny));
 #endif
-                    }
+            for (int cb = c0; cb < c1; cb += 32)
+            {
+                // one column per lane: its candidate voxels as a bit mask
+                const int c = cb + lane;
+                int col = 0;
+                unsigned cand = 0u, claimed = 0u;
+                if (c < c1)
+                {
+                    const int dz = (int)(((unsigned)c * rnx) >> 16), dx = c - dz * nxc;
+                    col = (x0 + dx) + 16 * (z0 + dz);
+                    cand = band & (k.canReplace ? 0xffffffffu : shAir[col]);
+                    claimed = shClaim[col];      // may miss claims made meanwhile: only costs a rasteriser call, atomicMin decides
                 }
-                const unsigned m0 = __ballot_sync(0xffffffffu, cand[0]), m1 = __ballot_sync(0xffffffffu, cand[1]);
-                const unsigned below = (1u << lane) - 1u;
-                if (cand[0]) wq[qn + __popc(m0 & below)] = (unsigned short)code[0];
-                if (cand[1]) wq[qn + __popc(m0) + __popc(m1 & below)] = (unsigned short)code[1];
-                qn += __popc(m0) + __popc(m1);
-                __syncwarp();
-                while (qn >= 32) drain();
+                // the set bits go to the queue, at most two per lane and round (two independent chains in flight)
+                while (__any_sync(0xffffffffu, cand != 0u))
+                {
+                    bool ok[2];
+                    int code[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+                    {
+                        ok[u] = cand != 0u;
+                        const int b = __ffs((int)cand) - 1;
+                        cand &= cand - 1u;
+                        code[u] = col << 5 | (b & 31);
+                        // claimed by an earlier placement of the list: nothing this one does there can matter
+                        if (ok[u] && ((claimed >> b) & 1u)) ok[u] = shBest[b * kSlabPitch + col] > (key | 0xffu);
+                    }
+                    const unsigned m0 = __ballot_sync(0xffffffffu, ok[0]), m1 = __ballot_sync(0xffffffffu, ok[1]);
+                    const unsigned below = (1u << lane) - 1u;
+                    if (ok[0]) wq[qn + __popc(m0 & below)] = (unsigned short)code[0];
+                    if (ok[1]) wq[qn + __popc(m0) + __popc(m1 & below)] = (unsigned short)code[1];
+                    qn += __popc(m0) + __popc(m1);
+                    __syncwarp();
+                    while (qn >= 32) drain();
+                }
             }
         }
         if (qn > 0) drain();
@@ -952,32 +987,18 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
     }
     __syncthreads();
     // thread t writes column t back if any of its 32 voxels was claimed
+    if (shClaim[t] != 0u)
     {
-        bool any = false;
+        uint4 ab[2] = {reinterpret_cast<const uint4*>(colPtr)[0], reinterpret_cast<const uint4*>(colPtr)[1]};
+        uint8_t* outv = reinterpret_cast<uint8_t*>(ab);
 #pragma unroll
-        for (int yy = 0; yy < kSlab; ++yy) any = any || shBest[yy * kSlabPitch + t] != kNoBest;
-#ifdef MMG_SPLIT_FEATURES
-        if (PASS == 1)
+        for (int yy = 0; yy < kSlab; ++yy)
         {
-            unsigned claimed = 0u;
-#pragma unroll
-            for (int yy = 0; yy < kSlab; ++yy) claimed |= (shBest[yy * kSlabPitch + t] != kNoBest ? 1u : 0u) << yy;
-            *maskPtr = claimed;
+            const unsigned b = shBest[yy * kSlabPitch + t];
+            if (b != kNoBest) outv[yy] = (uint8_t)(b & 0xffu);
         }
-#endif
-        if (any)
-        {
-            uint4 ab[2] = {reinterpret_cast<const uint4*>(colPtr)[0], reinterpret_cast<const uint4*>(colPtr)[1]};
-            uint8_t* outv = reinterpret_cast<uint8_t*>(ab);
-#pragma unroll
-            for (int yy = 0; yy < kSlab; ++yy)
-            {
-                const unsigned b = shBest[yy * kSlabPitch + t];
-                if (b != kNoBest) outv[yy] = (uint8_t)(b & 0xffu);
-            }
-            reinterpret_cast<uint4*>(colPtr)[0] = ab[0];
-            reinterpret_cast<uint4*>(colPtr)[1] = ab[1];
-        }
+        reinterpret_cast<uint4*>(colPtr)[0] = ab[0];
+        reinterpret_cast<uint4*>(colPtr)[1] = ab[1];
     }
 }
 

@@ -21,7 +21,13 @@ namespace mmg {
 
 thread_local std::string g_lastError;
 uint64_t g_launchCount = 0;
+int g_numSMs = 148;
 static bool g_ready = false;
+// The batch operators share one stream, one set of scratch buffers and the kernel timer (like the reference, whose staging
+// buffers are file-static, terrain.cpp:131-152): calls into them are serialised by this mutex. World / stream objects own
+// their buffers; one world must not be driven from two threads at once.
+static std::mutex g_batchMutex;
+#define MMG_BATCH_LOCK() std::lock_guard<std::mutex> mmg_batch_lock_(g_batchMutex)
 static int g_device = -1;
 
 // grow-only device scratch for the batch operators (the reference's Terrain owns fixed staging
@@ -158,6 +164,7 @@ struct MmgenWorld
     cudaStream_t stream = nullptr;
     cudaStream_t copyStream = nullptr;   // device->host block copies overlapped with the fill (generate_to_host)
     cudaEvent_t ev[14] = {};             // [2s-2, 2s-1] bracket stage s; [12, 13] bracket the whole generate
+    cudaEvent_t evMesh[2] = {};          // bracket mmgen_world_mesh (its own pair: total_ms keeps the last generate's time)
     cudaEvent_t evBatch[2] = {};
     // target region (mmgen_world_create_for_region): only what filling it needs is computed
     bool hasTarget = false;
@@ -185,20 +192,20 @@ int mmgen_init(int device)
     }
     MMG_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
+    cudaFuncAttributes fattr;
     MMG_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10)
+    // the library carries sm_100a SASS only (arch-specific: no PTX fallback for other Blackwell parts)
+    if (prop.major != 10 || prop.minor != 0 || cudaFuncGetAttributes(&fattr, k_init_noise_tables) != cudaSuccess)
     {
-        g_lastError = "mmgen_init: kernels are built for sm_100a only";
+        cudaGetLastError();
+        g_lastError = "mmgen_init: device " + std::to_string(device) + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                      "; the kernels of this library are built for sm_100a (B200) only and there is no fallback";
         return 1;
     }
+    g_numSMs = prop.multiProcessorCount;
     if (!g_stream) MMG_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     // k_fill_features: 40 KB static + the 10 KB noise tables exceed the 48 KB default
-#ifdef MMG_SPLIT_FEATURES
-    MMG_CUDA(cudaFuncSetAttribute(k_fill_features<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNoiseSmemBytes));
-    MMG_CUDA(cudaFuncSetAttribute(k_fill_features<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNoiseSmemBytes));
-#else
     MMG_CUDA(cudaFuncSetAttribute(k_fill_features, cudaFuncAttributeMaxDynamicSharedMemorySize, kNoiseSmemBytes));
-#endif
     MMG_LAUNCH(k_init_noise_tables, 3, 256, 0, g_stream);     // simplex lattice tables (mm_arith.cuh)
     MMG_CUDA(cudaStreamSynchronize(g_stream));
     g_device = device;
@@ -224,6 +231,7 @@ int mmgen_shutdown(void)
 int mmgen_heightfields(int n, const int32_t* origins, float* out_heightfield, float* out_biomeWeights)
 {
     if (requireReady()) return 1;
+    MMG_BATCH_LOCK();
     if (n <= 0) return 0;
     if (g_scratch[0].ensure((size_t)n * sizeof(int2))) return 1;
     if (g_scratch[1].ensure((size_t)n * 256 * sizeof(float))) return 1;
@@ -249,7 +257,6 @@ constexpr int kZoneBatch = kMaxZoneBatch;     // zones per launch: 32 x 4 live p
 
 static int erodeZonesDevice(float* d_zones, int nZones, int* d_flags, cudaStream_t stream, int* sweepsOut)
 {
-    const size_t P = kErosionCols;
     int accIn = 10, accOut = 11;     // plane 10 was zeroed by the gather (or by the caller)
     int sweeps = 0;
     int h_flags[kSweepGroup];
@@ -282,7 +289,6 @@ static int erodeZonesDevice(float* d_zones, int nZones, int* d_flags, cudaStream
         // an even number of sweeps per group: the result is back in the layer's own plane
         static_assert(kSweepGroup % 2 == 0, "ping-pong must end in the layer plane");
     }
-    (void)P;
     if (sweepsOut) *sweepsOut = sweeps;
     return 0;
 }
@@ -290,6 +296,7 @@ static int erodeZonesDevice(float* d_zones, int nZones, int* d_flags, cudaStream
 extern "C" int mmgen_layers(int n, const int32_t* origins, const float* heightfield18, const float* biomeWeights, float* out_layers)
 {
     if (requireReady()) return 1;
+    MMG_BATCH_LOCK();
     if (n <= 0) return 0;
     if (g_scratch[0].ensure((size_t)n * sizeof(int2))) return 1;
     if (g_scratch[1].ensure((size_t)n * 324 * sizeof(float))) return 1;
@@ -308,6 +315,7 @@ extern "C" int mmgen_layers(int n, const int32_t* origins, const float* heightfi
 extern "C" int mmgen_erode_zone(const float* gathered, float* out_eroded, int* out_sweeps)
 {
     if (requireReady()) return 1;
+    MMG_BATCH_LOCK();
     const size_t P = kErosionCols;
     if (g_scratch[4].ensure(kZonePlanes * P * sizeof(float))) return 1;
     if (g_scratch[5].ensure((kSweepGroup + 3 * kMaxZoneBatch * kZoneTiles) * sizeof(int))) return 1;
@@ -348,6 +356,7 @@ extern "C" int mmgen_caves(int n, const int32_t* origins, const float* heightfie
                            MmgenCaveLayer* out_caveLayers)
 {
     if (requireReady()) return 1;
+    MMG_BATCH_LOCK();
     if (n <= 0) return 0;
     const size_t clBytes = (size_t)n * 256 * MAX_CAVE_LAYERS * sizeof(CaveLayer);
     if (g_scratch[0].ensure((size_t)n * sizeof(int2))) return 1;
@@ -387,28 +396,8 @@ static int launchFill(int m, const int* d_list, const int2* d_origins, const flo
                                                  (const int*)d_counters, d_blocks));
     MMG_TIMED(K_PREPARE, stream, 1, MMG_LAUNCH(k_prepare_placements, m, 256, 0, stream, d_list, d_origins, d_gF, d_gCF, d_info, strideF, strideCF,
                                                d_prepF, d_prepC));
-#ifdef MMG_SPLIT_FEATURES
-    {
-        // experiment (see k_fill_features): surface pass, then cave pass with the surface pass's claimed-voxel masks
-        static unsigned* d_claimed = nullptr;
-        static size_t claimedCap = 0;
-        if ((size_t)m > claimedCap)
-        {
-            cudaFree(d_claimed);
-            MMG_CUDA(cudaMalloc(&d_claimed, (size_t)m * 12 * 256 * sizeof(unsigned)));
-            claimedCap = (size_t)m;
-        }
-        g_kt.begin(K_FILL_FEATURES, stream, 2);
-        MMG_LAUNCH(k_fill_features<1>, m * 12, 256, kNoiseSmemBytes, stream, d_list, d_origins, d_gF, d_gCF, (const Prep*)d_prepF,
-                   (const Prep*)d_prepC, (const GatherInfo*)d_info, strideF, strideCF, d_blocks, d_claimed);
-        MMG_LAUNCH(k_fill_features<2>, m * 12, 256, kNoiseSmemBytes, stream, d_list, d_origins, d_gF, d_gCF, (const Prep*)d_prepF,
-                   (const Prep*)d_prepC, (const GatherInfo*)d_info, strideF, strideCF, d_blocks, d_claimed);
-        g_kt.end(stream);
-    }
-#else
     MMG_TIMED(K_FILL_FEATURES, stream, 1, MMG_LAUNCH(k_fill_features, m * 12, 256, kNoiseSmemBytes, stream, d_list, d_origins, d_gF, d_gCF,
                                                      (const Prep*)d_prepF, (const Prep*)d_prepC, (const GatherInfo*)d_info, strideF, strideCF, d_blocks));
-#endif
     MMG_TIMED(K_DECORATORS, stream, 1, MMG_LAUNCH(k_decorators, m, 256, 0, stream, d_list, m, d_origins, d_height, d_weights, d_caves, d_blocks));
     return 0;
 }   // chunks gathered + filled per launch group (bounds the gathered-list buffers)
@@ -419,6 +408,7 @@ extern "C" int mmgen_feature_placements(int n, const int32_t* origins, const flo
                                         int32_t* out_counts)
 {
     if (requireReady()) return 1;
+    MMG_BATCH_LOCK();
     if (n <= 0) return 0;
     const size_t clBytes = (size_t)n * 256 * MAX_CAVE_LAYERS * sizeof(CaveLayer);
     Scratch* S = g_scratch;
@@ -452,13 +442,87 @@ extern "C" int mmgen_feature_placements(int n, const int32_t* origins, const flo
     return 0;
 }
 
+extern "C" int mmgen_gather_offsets(int32_t* out49x2)
+{
+    static const int off[49][2] = {
+        {0, 0}, {0, 1}, {1, 1}, {1, 0}, {1, -1}, {0, -1}, {-1, -1}, {-1, 0}, {-1, 1}, {2, 0}, {2, 1}, {2, 2}, {1, 2}, {0, 2},
+        {-1, 2}, {-2, 2}, {-2, 1}, {-2, 0}, {-2, -1}, {-2, -2}, {-1, -2}, {0, -2}, {1, -2}, {2, -2}, {2, -1},
+        {-3, -3}, {-2, -3}, {-1, -3}, {0, -3}, {1, -3}, {2, -3}, {3, -3}, {3, -2}, {3, -1}, {3, 0}, {3, 1}, {3, 2}, {3, 3},
+        {2, 3}, {1, 3}, {0, 3}, {-1, 3}, {-2, 3}, {-3, 3}, {-3, 2}, {-3, 1}, {-3, 0}, {-3, -1}, {-3, -2}};      // == c_gatherOffsets
+    std::memcpy(out49x2, off, sizeof(off));
+    return 0;
+}
+
+extern "C" int mmgen_gather_features(int n, const int32_t* neighbours, int m, const MmgenFeaturePlacement* features, int featureStride,
+                                     const MmgenCaveFeaturePlacement* caveFeatures, int caveFeatureStride, const int32_t* counts,
+                                     MmgenFeaturePlacement* out_features, MmgenCaveFeaturePlacement* out_caveFeatures, int32_t* out_counts)
+{
+    if (requireReady()) return 1;
+    MMG_BATCH_LOCK();
+    if (n <= 0) return 0;
+    if (m <= 0 || featureStride <= 0 || caveFeatureStride <= 0 || !neighbours || !features || !caveFeatures || !counts || !out_counts)
+    {
+        g_lastError = "mmgen_gather_features: bad arguments";
+        return 1;
+    }
+    for (int i = 0; i < n * 49; ++i)
+        if (neighbours[i] >= m)
+        {
+            g_lastError = "mmgen_gather_features: neighbour index " + std::to_string(neighbours[i]) + " outside the pool of " + std::to_string(m) + " chunks";
+            return 1;
+        }
+    Scratch* S = g_scratch;
+    if (S[0].ensure((size_t)n * 49 * sizeof(int)) || S[5].ensure((size_t)m * featureStride * sizeof(FeaturePlacement)) ||
+        S[6].ensure((size_t)m * caveFeatureStride * sizeof(CaveFeaturePlacement)) || S[7].ensure((size_t)(m + n) * 2 * sizeof(int)) ||
+        g_scratch[8].ensure((size_t)n * MAX_FEATURES * sizeof(FeaturePlacement)) || g_scratch[9].ensure((size_t)n * MAX_CAVE_FEATURES * sizeof(CaveFeaturePlacement)))
+        return 1;
+    int* d_counts = (int*)S[7].ptr;
+    int* d_outCounts = d_counts + (size_t)m * 2;
+    MMG_CUDA(cudaMemcpyAsync(S[0].ptr, neighbours, (size_t)n * 49 * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    MMG_CUDA(cudaMemcpyAsync(S[5].ptr, features, (size_t)m * featureStride * sizeof(FeaturePlacement), cudaMemcpyHostToDevice, g_stream));
+    MMG_CUDA(cudaMemcpyAsync(S[6].ptr, caveFeatures, (size_t)m * caveFeatureStride * sizeof(CaveFeaturePlacement), cudaMemcpyHostToDevice, g_stream));
+    MMG_CUDA(cudaMemcpyAsync(d_counts, counts, (size_t)m * 2 * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    MMG_LAUNCH(k_gather_concat, n, 256, 0, g_stream, (const int*)S[0].ptr, (const FeaturePlacement*)S[5].ptr, featureStride,
+               (const CaveFeaturePlacement*)S[6].ptr, caveFeatureStride, (const int*)d_counts, (FeaturePlacement*)g_scratch[8].ptr,
+               (CaveFeaturePlacement*)g_scratch[9].ptr, d_outCounts);
+    MMG_CUDA(cudaMemcpyAsync(out_counts, d_outCounts, (size_t)n * 2 * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    MMG_CUDA(cudaStreamSynchronize(g_stream));
+    for (int i = 0; i < n; ++i)
+    {
+        const int nf = std::min(out_counts[2 * i], MAX_FEATURES), nc = std::min(out_counts[2 * i + 1], MAX_CAVE_FEATURES);
+        if (nf && out_features) MMG_CUDA(cudaMemcpyAsync(out_features + (size_t)i * MAX_FEATURES, (FeaturePlacement*)g_scratch[8].ptr + (size_t)i * MAX_FEATURES,
+                                                         (size_t)nf * sizeof(FeaturePlacement), cudaMemcpyDeviceToHost, g_stream));
+        if (nc && out_caveFeatures) MMG_CUDA(cudaMemcpyAsync(out_caveFeatures + (size_t)i * MAX_CAVE_FEATURES, (CaveFeaturePlacement*)g_scratch[9].ptr + (size_t)i * MAX_CAVE_FEATURES,
+                                                             (size_t)nc * sizeof(CaveFeaturePlacement), cudaMemcpyDeviceToHost, g_stream));
+    }
+    MMG_CUDA(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
 extern "C" int mmgen_fill(int n, const int32_t* origins, const float* heightfield, const float* biomeWeights, const float* layers,
                           const MmgenCaveLayer* caveLayers, const MmgenFeaturePlacement* features,
                           const MmgenCaveFeaturePlacement* caveFeatures, const int32_t* numFeatures, int featureStride,
                           int caveFeatureStride, uint8_t* out_blocks)
 {
     if (requireReady()) return 1;
+    MMG_BATCH_LOCK();
     if (n <= 0) return 0;
+    // the lists are read with the caller's strides: a count beyond its stride (or beyond the reference's caps, which the
+    // gather never exceeds, chunk.cu:1573-1578) would read past the caller's arrays
+    if (featureStride < 0 || caveFeatureStride < 0 || !numFeatures)
+    {
+        g_lastError = "mmgen_fill: bad strides / numFeatures";
+        return 1;
+    }
+    for (int i = 0; i < n; ++i)
+        if (numFeatures[2 * i] < 0 || numFeatures[2 * i + 1] < 0 || numFeatures[2 * i] > featureStride || numFeatures[2 * i + 1] > caveFeatureStride ||
+            (numFeatures[2 * i] > 0 && !features) || (numFeatures[2 * i + 1] > 0 && !caveFeatures))
+        {
+            g_lastError = "mmgen_fill: chunk " + std::to_string(i) + " has {" + std::to_string(numFeatures[2 * i]) + ", " +
+                          std::to_string(numFeatures[2 * i + 1]) + "} placements but the strides are {" + std::to_string(featureStride) + ", " +
+                          std::to_string(caveFeatureStride) + "}";
+            return 1;
+        }
     Scratch* X = g_scratch + 8;
     const size_t clBytes = (size_t)n * 256 * MAX_CAVE_LAYERS * sizeof(CaveLayer);
     Scratch* S = g_scratch;
@@ -506,6 +570,7 @@ int mmgen_world_create(int cx0, int cz0, int nx, int nz, MmgenWorld** out)
     MMG_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     MMG_CUDA(cudaStreamCreateWithFlags(&w->copyStream, cudaStreamNonBlocking));
     for (auto& e : w->ev) MMG_CUDA(cudaEventCreate(&e));
+    for (auto& e : w->evMesh) MMG_CUDA(cudaEventCreate(&e));
     for (auto& e : w->evBatch) MMG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     std::vector<int2> origins(w->n);
     for (int z = 0; z < nz; ++z)
@@ -552,6 +617,7 @@ int mmgen_world_destroy(MmgenWorld* w)
     cudaFree(w->d_meshVerts);
     cudaFree(w->d_meshIdx);
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : w->evMesh) if (e) cudaEventDestroy(e);
     for (auto& e : w->evBatch) if (e) cudaEventDestroy(e);
     if (w->stream) cudaStreamDestroy(w->stream);
     if (w->copyStream) cudaStreamDestroy(w->copyStream);
@@ -767,6 +833,8 @@ static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
                 // with a target region only zones that meet target (+) 3 chunks are eroded
                 if (w->hasTarget && (lx0 + 18 <= w->tx0 - 3 || lx0 + 6 >= w->tx0 + w->tnx + 3 ||
                                      lz0 + 18 <= w->tz0 - 3 || lz0 + 6 >= w->tz0 + w->tnz + 3)) continue;
+                // a zone is eroded once: its 144 centre chunks move from stage 2 to 3 together (later stages are never demoted)
+                if (w->stage[(lz0 + 6) * nx + lx0 + 6] >= 3) continue;
                 bool ok = true;
                 for (int z = 0; z < 24 && ok; ++z)
                     for (int x = 0; x < 24 && ok; ++x) ok = w->stage[(lz0 + z) * nx + lx0 + x] >= 2;
@@ -942,13 +1010,12 @@ int mmgen_world_block_checksum(MmgenWorld* w, uint64_t* out)
     return 0;
 }
 
-int mmgen_world_chunk_hash_sum(MmgenWorld* w, uint64_t* out)
+// hash of (chunk coordinates, block volume) of every filled chunk, list order = raster order of the filled chunks
+static int worldChunkHashes(MmgenWorld* w, std::vector<int>& list, std::vector<uint64_t>& out)
 {
-    if (requireReady()) return 1;
-    std::vector<int> list;
     std::vector<unsigned long long> hs;
     if (worldColumnHashes(w, list, hs)) return 1;
-    uint64_t total = 0;
+    out.resize(list.size());
     for (size_t k = 0; k < list.size(); ++k)
     {
         const int cx = w->cx0 + list[k] % w->nx, cz = w->cz0 + list[k] / w->nx;
@@ -957,9 +1024,37 @@ int mmgen_world_chunk_hash_sum(MmgenWorld* w, uint64_t* out)
         mix((unsigned long long)(long long)cx);
         mix((unsigned long long)(long long)cz);
         for (int c = 0; c < 256; ++c) mix(hs[k * 256 + c]);
-        total += h;      // mod 2^64: independent of the order and of how the world is tiled
+        out[k] = h;
     }
+    return 0;
+}
+
+int mmgen_world_chunk_hash_sum(MmgenWorld* w, uint64_t* out)
+{
+    if (requireReady()) return 1;
+    std::vector<int> list;
+    std::vector<uint64_t> hs;
+    if (worldChunkHashes(w, list, hs)) return 1;
+    uint64_t total = 0;
+    for (uint64_t h : hs) total += h;      // mod 2^64: independent of the order and of how the world is tiled
     *out = total;
+    return 0;
+}
+
+int mmgen_world_chunk_hashes(MmgenWorld* w, int cap, int32_t* coords, uint64_t* hashes, int* n)
+{
+    if (requireReady()) return 1;
+    std::vector<int> list;
+    std::vector<uint64_t> hs;
+    if (worldChunkHashes(w, list, hs)) return 1;
+    const int m = std::min<int>(cap, (int)list.size());
+    for (int k = 0; k < m; ++k)
+    {
+        coords[2 * k] = w->cx0 + list[k] % w->nx;
+        coords[2 * k + 1] = w->cz0 + list[k] / w->nx;
+        hashes[k] = hs[k];
+    }
+    if (n) *n = (int)list.size();
     return 0;
 }
 
@@ -1027,6 +1122,15 @@ int mmgen_world_download(MmgenWorld* w, float* heightfield, float* biomeWeights,
     }
     if (caveLayers && w->d_caves) MMG_CUDA(cudaMemcpy(caveLayers, w->d_caves, (size_t)w->n * 256 * MAX_CAVE_LAYERS * sizeof(CaveLayer), cudaMemcpyDeviceToHost));
     if (blocks && w->d_blocks) MMG_CUDA(cudaMemcpy(blocks, w->d_blocks, (size_t)w->n * 98304, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// see mm_featurefuncs.cuh: 0 = the reference as built on Linux (default, the parity target), 1 = the source-text reading
+int mmgen_set_cave_grid_test(int honoured)
+{
+    if (requireReady()) return 1;
+    const int v = honoured ? 1 : 0;
+    MMG_CUDA(cudaMemcpyToSymbol(g_caveGridTestHonoured, &v, sizeof(v)));
     return 0;
 }
 
@@ -1123,7 +1227,7 @@ int mmgen_world_mesh(MmgenWorld* w, int n, const int32_t* chunkCoords, int32_t* 
         MMG_CUDA(cudaMalloc(&w->d_meshBase, (size_t)n * sizeof(long long)));
         w->meshListCap = (size_t)n;
     }
-    cudaEvent_t e0 = w->ev[12], e1 = w->ev[13];
+    cudaEvent_t e0 = w->evMesh[0], e1 = w->evMesh[1];
     MMG_CUDA(cudaEventRecord(e0, w->stream));
     MMG_CUDA(cudaMemcpyAsync(w->d_meshList, list.data(), (size_t)n * sizeof(MeshChunk), cudaMemcpyHostToDevice, w->stream));
     MMG_LAUNCH(k_mesh_count, n, 32 * kMeshWarps, 0, w->stream, (const MeshChunk*)w->d_meshList, (const uint8_t*)w->d_blocks, w->d_meshColOff, w->d_meshTotals);
@@ -1179,13 +1283,13 @@ int mmgen_world_mesh_device_ptrs(MmgenWorld* w, int i, void** verts, void** idx,
 
 int mmgen_world_mesh_ms(MmgenWorld* w, float* out) { *out = w->meshMs; return 0; }
 
-// profiling experiments only: surface feature types whose bit is 0 are not rasterised (results then differ from the reference)
+#ifdef MMG_FEATURE_STATS
+// developer build only: surface feature types whose bit is 0 are not rasterised (results then differ from the reference)
 extern "C" int mmgen_debug_feature_mask(unsigned mask)
 {
     MMG_CUDA(cudaMemcpyToSymbol(g_debugFeatureMask, &mask, sizeof(mask)));
     return 0;
 }
-#ifdef MMG_FEATURE_STATS
 // developer build only (nvcc -DMMG_FEATURE_STATS, tools/feature_census.py): read and clear the rasteriser census
 extern "C" int mmgen_debug_feature_stats(unsigned long long* out)
 {

@@ -9,7 +9,8 @@ is the equality checksum and the timing reduction.
 
 
 def grid_for(n_ranks):
-    """(columns, rows) of the tile grid: as square as possible, rows >= columns (1, 2, 4, 8 -> 1x1, 1x2, 2x2, 2x4)."""
+    """(columns, rows) = (cuts along x, cuts along z) of the tile grid: as square as possible, columns >= rows
+    (1, 2, 4, 8 ranks -> 1x1, 2x1, 2x2, 4x2). Rank order is row-major (z-major): rank = row * columns + column."""
     if n_ranks < 1:
         raise ValueError("n_ranks must be >= 1")
     gx = 1

@@ -10,7 +10,9 @@
 //  * Chunk::tryGenerateCaveFeaturePlacement() falls off its end without a return when the grid test
 //    fails (chunk.cu:1028-1038). g++ compiles that undefined behaviour by dropping the test: the
 //    placement is emitted whenever the chance / ceiling / lava / min-height tests pass (seen in the
-//    disassembly of the reference object and in its outputs). kCaveGridTestIgnored records that.
+//    disassembly of the reference object and in its outputs). That is the default (cave_grid_test_honoured() == 0);
+//    mmo_set_cave_grid_test(1) selects the source-text reading instead (test honoured, failure = `false`), which the
+//    product offers as mmgen_set_cave_grid_test(1).
 #pragma once
 #include <vector>
 #include "mm_hostmath.h"
@@ -19,7 +21,7 @@
 
 namespace mmo {
 
-constexpr bool kCaveGridTestIgnored = true;
+inline int& cave_grid_test_honoured() { static int v = 0; return v; }      // set between calls only (mmo_set_cave_grid_test)
 
 // chunk.cu:999-1008 (host arithmetic)
 static inline bool is_feature_pos(int wx, int wz, int cell, int pad, int seed)
@@ -54,6 +56,7 @@ static inline void column_feature_placements(int wx, int wz, float height, const
                                              std::vector<FeaturePlacement>& feats, std::vector<CaveFeaturePlacement>& caveFeats)
 {
     const int groundHeight = (int)height;
+    const bool honoured = cave_grid_test_honoured() != 0;
     Minstd rng = make_rng3(wx, wz, 329828101);
     bool surfaceIsCave = false;
     for (int li = 0; li < MAX_CAVE_LAYERS; ++li)
@@ -75,7 +78,7 @@ static inline void column_feature_placements(int wx, int wz, float height, const
                 if (rand >= gen.chance || top != gen.fromCeiling || (!gen.inLava && (top ? cl.end : cl.start + 1) <= LAVA_LEVEL) ||
                     layerHeight < gen.minLayerHeight)
                     continue;
-                if (kCaveGridTestIgnored || is_feature_pos(wx, wz, gen.gridCellSize, gen.gridCellPadding, seed))
+                if (!honoured || is_feature_pos(wx, wz, gen.gridCellSize, gen.gridCellPadding, seed))
                 {
                     CaveFeaturePlacement p = {};
                     p.feature = gen.feature; p.x = wx; p.y = cl.start + 1; p.z = wz; p.layerHeight = layerHeight;

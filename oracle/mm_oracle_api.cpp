@@ -101,6 +101,10 @@ void mmo_caves(int n, const int32_t* origins, const float* heightfield, const fl
 }
 int mmo_cave_biome(int x, int y, int z, float maxHeight, int seed) { return mmo::cave_biome(x, y, z, maxHeight, seed); }
 
+// 0 (default): the reference as built here (g++ drops the grid test of tryGenerateCaveFeaturePlacement, chunk.cu:1028-1038);
+// 1: the source-text reading (test honoured, failure = false). Call between stage calls only.
+void mmo_set_cave_grid_test(int honoured) { mmo::cave_grid_test_honoured() = honoured ? 1 : 0; }
+
 // Chunk::generateFeaturePlacements (chunk.cu:1147-1156). Lists are written with stride maxPerChunk;
 // counts[n][2] = {surface, cave} (the true counts, even if larger than maxPerChunk).
 void mmo_feature_placements(int n, const int32_t* origins, const float* heightfield, const float* weights, const float* layers,

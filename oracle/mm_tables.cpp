@@ -12,9 +12,13 @@ static const uint32_t kTanRepose[NUM_ERODED] = {0x3FB6CD8Du, 0x3F56CF3Bu, 0x3F80
                                                 0x3F13CD3Bu, 0x3F3340CDu, 0x40093F9Au, 0x3F800000u};
 float material_tan_repose(int erodedIdx) { return dm_u2f(kTanRepose[erodedIdx]); }
 
+// Both tables are built inside the initialiser of a function-local static (thread-safe since C++11): the first
+// callers are the worker threads of mmo_layers' parallel_for, which must never see a half-filled table.
+struct MaterialTable { MaterialInfo infos[NUM_MATERIALS]; };
 const MaterialInfo* material_infos()
 {
-    static MaterialInfo infos[NUM_MATERIALS] = {
+    static const MaterialTable table = [] {
+    MaterialTable t = {{
         // stratified: thickness, noise amplitude, noise scale (biomeFuncs.hpp:814-827)
         {B_BLACKSTONE, 32.f, 32.f, 0.0030f}, {B_DEEPSLATE, 66.f, 20.f, 0.0045f}, {B_SLATE, 6.f, 24.f, 0.0062f},
         {B_STONE, 40.f, 30.f, 0.0050f}, {B_TUFF, 24.f, 42.f, 0.0060f}, {B_CALCITE, 20.f, 30.f, 0.0040f},
@@ -23,21 +27,19 @@ const MaterialInfo* material_infos()
         {B_RED_SANDSTONE, 3.0f, 2.0f, 0.0035f}, {B_SANDSTONE, 3.5f, 1.5f, 0.0025f},
         // eroded: thickness, tan(angle of repose), max slope (biomeFuncs.hpp:830-837)
         {B_GRAVEL, 2.5f, 0.f, 1.8f}, {B_CLAY, 2.7f, 0.f, 1.8f}, {B_MUD, 2.3f, 0.f, 1.6f}, {B_DIRT, 4.2f, 0.f, 1.2f},
-        {B_RED_SAND, 3.5f, 0.f, 1.5f}, {B_SAND, 3.8f, 0.f, 1.4f}, {B_SMOOTH_SAND, 4.5f, 0.f, 4.0f}, {B_SNOW, 2.5f, 0.f, 1.5f}};
-    static bool init = false;
-    if (!init)
-    {
-        for (int i = 0; i < NUM_ERODED; ++i) infos[NUM_STRATIFIED + i].v1 = material_tan_repose(i);
-        init = true;
-    }
-    return infos;
+        {B_RED_SAND, 3.5f, 0.f, 1.5f}, {B_SAND, 3.8f, 0.f, 1.4f}, {B_SMOOTH_SAND, 4.5f, 0.f, 4.0f}, {B_SNOW, 2.5f, 0.f, 1.5f}}};
+    for (int i = 0; i < NUM_ERODED; ++i) t.infos[NUM_STRATIFIED + i].v1 = material_tan_repose(i);
+    return t;
+    }();
+    return table.infos;
 }
 
+struct WeightTable { float w[NUM_BIOMES * NUM_MATERIALS]; };
 const float* biome_material_weights()
 {
-    static float w[NUM_BIOMES * NUM_MATERIALS];
-    static bool init = false;
-    if (init) return w;
+    static const WeightTable table = [] {
+    WeightTable t;
+    float* w = t.w;
     auto set = [&](int biome, int material, float v) { w[material + NUM_MATERIALS * biome] = v; };
     for (int i = 0; i < NUM_BIOMES * NUM_MATERIALS; ++i) w[i] = 1.f;
     for (int b = 0; b < NUM_BIOMES; ++b)
@@ -66,8 +68,9 @@ const float* biome_material_weights()
     set(OASIS, M_SANDSTONE, 1.0f); set(OASIS, M_CLAY, 0.4f); set(OASIS, M_DIRT, 0.6f); set(OASIS, M_SAND, 0.4f);
     set(DESERT, M_SANDSTONE, 1.0f); set(DESERT, M_DIRT, 0.0f); set(DESERT, M_SAND, 1.0f);
     set(MOUNTAINS, M_GRAVEL, 1.0f);
-    init = true;
-    return w;
+    return t;
+    }();
+    return table.w;
 }
 
 // ---- feature generators (biomeFuncs.hpp:975-1040) ----

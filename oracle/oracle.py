@@ -10,7 +10,7 @@ _LIB = os.path.join(_HERE, "libmmoracle.so")
 
 
 def build():
-    subprocess.run(["make", "-C", _HERE, "oracle"], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run(["make", "-C", _HERE, "oracle", "variants"], check=True, stdout=subprocess.DEVNULL)
     return _LIB
 
 
@@ -19,10 +19,13 @@ def _ptr(a):
 
 
 class Oracle:
-    def __init__(self, nthreads=None):
-        if not os.path.exists(_LIB):
+    def __init__(self, nthreads=None, variant=None):
+        """variant: None = the oracle; "unfused" / "contract" = diagnostic builds with other FMA contraction (see Makefile),
+        only for classifying block flips - never a parity reference."""
+        lib = _LIB if variant is None else os.path.join(_HERE, "libmmoracle_%s.so" % variant)
+        if not os.path.exists(lib):
             build()
-        self.L = ctypes.CDLL(_LIB)
+        self.L = ctypes.CDLL(lib)
         self.nthreads = nthreads or os.cpu_count() or 1
         for f in ("mmo_sinf", "mmo_cosf", "mmo_simplex2", "mmo_simplex3", "mmo_powf", "mmo_rng3_u01"):
             getattr(self.L, f).restype = ctypes.c_float
@@ -71,6 +74,10 @@ class Oracle:
         out = np.zeros((n, 256, 32), CaveLayer)
         self.L.mmo_caves(n, _ptr(origins), _ptr(h), _ptr(w), _ptr(out), self.nthreads)
         return out
+
+    def set_cave_grid_test(self, honoured):
+        """False (default): the reference as built here; True: the source-text reading (see mm_features.h)."""
+        self.L.mmo_set_cave_grid_test(1 if honoured else 0)
 
     def feature_placements(self, origins, heightfield, weights, layers, cave_layers, max_per_chunk=4096):
         from .refcuda import FeaturePlacement, CaveFeaturePlacement

@@ -1,6 +1,7 @@
 """Parity of the CUDA path (called through the C ABI, include/mmgen.h) against
  (a) the golden vectors produced by the UNMODIFIED reference CUDA pipeline, and
- (b) the CPU oracle on other seeded windows (all 24 surface biomes, every feature type),
+ (b) the CPU oracle on other seeded windows (S1 on all 24 surface biomes, the whole pipeline on four of them;
+     tests/test_reference_tour.py holds the whole pipeline to the reference's CUDA generator on all 24),
 plus size-independent properties at larger sizes. Integer / byte outputs: bit-exact. Heights and
 layers: bit-exact against the oracle; <= 1e-5 relative against the reference (north_star)."""
 import numpy as np
@@ -51,6 +52,71 @@ def test_batch_ops_vs_reference_golden(gen, golden):
     gcf = [orc.gather_features(clists, int(c) % nx, int(c) // nx, nx) for c in bidx]
     blocks = gen.fill(origins[bidx], g["heightfield"][bidx], g["biome_weights"][bidx], g["zone_layers"][sel], g["cave_layers"][sel], gf, gcf)
     assert np.array_equal(blocks, g["blocks"])
+
+
+def test_gather_features_op_vs_reference_golden(gen, golden):
+    """mmgen_gather_features (Chunk::gatherFeaturePlacements, chunk.cu:1158-1196): the reference's own placement lists of the
+    golden zone gathered in the reference's order; feeding the result to mmgen_fill must give the reference's blocks."""
+    from oracle import oracle as orc
+    g, nx, origins = golden["g"], golden["nx"], golden["origins"]
+    zone, bidx = g["zone_idx"], g["block_idx"]
+    rF, rCF = split_lists(g["features"], g["features_off"]), split_lists(g["cave_features"], g["cave_features_off"])
+    off = gen.gather_offsets()
+    assert [tuple(o) for o in off] == [tuple(o) for o in orc.GATHER_OFFSETS]
+    pos = {int(c): k for k, c in enumerate(zone)}
+    nb = np.array([[pos.get(int(c) + int(dx) + int(dz) * nx, -1) for dx, dz in off] for c in bidx], np.int32)
+    assert (nb >= 0).all()                                     # the filled chunks' 7x7 neighbourhoods lie inside the zone
+    gf, gcf, counts = gen.gather_features(nb, rF, [c[:4096] for c in rCF])
+    lists = {int(c): rF[k] for k, c in enumerate(zone)}
+    clists = {int(c): rCF[k][:4096] for k, c in enumerate(zone)}
+    for k, c in enumerate(bidx):
+        ef = orc.gather_features(lists, int(c) % nx, int(c) // nx, nx)
+        ec = orc.gather_features(clists, int(c) % nx, int(c) // nx, nx)
+        assert counts[k, 0] == len(ef) and counts[k, 1] == len(ec)
+        assert same_placements(gf[k], ef[:2048]) and same_placements(gcf[k], ec[:4096])
+    # an absent neighbour contributes nothing
+    nb2 = nb[:1].copy()
+    nb2[0, 5] = -1
+    _, _, c2 = gen.gather_features(nb2, rF, [c[:4096] for c in rCF])
+    assert c2[0, 0] == counts[0, 0] - len(rF[nb[0, 5]]) and c2[0, 1] == counts[0, 1] - min(len(rCF[nb[0, 5]]), 4096)
+    sel = np.array([pos[int(c)] for c in bidx])
+    blocks = gen.fill(origins[bidx], g["heightfield"][bidx], g["biome_weights"][bidx], g["zone_layers"][sel], g["cave_layers"][sel], gf, gcf)
+    assert np.array_equal(blocks, g["blocks"])
+
+
+def test_fill_rejects_counts_beyond_the_stride(gen, mm, golden):
+    origins = golden["origins"][:1]
+    z = np.zeros
+    F = z((1, 4), mm.FeaturePlacement)
+    CF = z((1, 4), mm.CaveFeaturePlacement)
+    counts = np.array([[5, 0]], np.int32)
+    import ctypes
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = gen.L.mmgen_fill(1, p(origins), p(z((1, 256), np.float32)), p(z((1, 24, 256), np.float32)), p(z((1, 20, 256), np.float32)),
+                          p(z((1, 256, 32), mm.CaveLayer)), p(F), p(CF), p(counts), 4, 4, p(z((1, 98304), np.uint8)))
+    assert rc != 0 and b"placements but the strides" in gen.L.mmgen_last_error()
+
+
+def test_cave_grid_test_switch_vs_oracle(gen, oracle, golden):
+    """mmgen_set_cave_grid_test(1): the source-text reading of tryGenerateCaveFeaturePlacement (grid test honoured). The
+    default (0) is the reference as built and is what every other test pins; both readings are checked against the oracle."""
+    g, origins = golden["g"], golden["origins"]
+    zone = g["zone_idx"][:24]
+    args = (origins[zone], g["heightfield"][zone], g["biome_weights"][zone], g["zone_layers"][:24], g["cave_layers"][:24])
+    try:
+        gen._check(gen.L.mmgen_set_cave_grid_test(1))
+        oracle.set_cave_grid_test(True)
+        F1, CF1 = gen.feature_placements(*args)
+        oF1, oCF1 = oracle.feature_placements(*args)
+    finally:
+        gen._check(gen.L.mmgen_set_cave_grid_test(0))
+        oracle.set_cave_grid_test(False)
+    F0, CF0 = gen.feature_placements(*args)
+    assert all(same_placements(a, b) for a, b in zip(F1, oF1)) and all(same_placements(a, b) for a, b in zip(CF1, oCF1))
+    n0, n1 = sum(len(c) for c in CF0), sum(len(c) for c in CF1)
+    assert 0 < n1 < n0                                         # the honoured grid test thins the cave placements out
+    rCF = split_lists(g["cave_features"], g["cave_features_off"])[:24]
+    assert all(same_placements(a, b[:4096]) for a, b in zip(CF0, rCF))      # the default is the reference build's behaviour
 
 
 def test_world_mode_vs_reference_golden(gen, mm, golden):
@@ -115,13 +181,17 @@ def test_tiles_are_bit_identical_to_one_world(gen, mm):
 
 def test_adapter_runs_reference_state_machine_on_new_kernels(gen, golden):
     """Drop-in proof: the reference's own Chunk/Zone state machine, CPU feature placement and gather
-    (unmodified objects from oracle/_ref) with integration/chunk_adapter.cpp linked over its five generation
-    entry points reproduces the reference's blocks bit for bit."""
+    (unmodified objects from oracle/_ref) with integration/chunk_adapter.cpp linked over its five batch entry points and
+    the two CPU passes of stage 5 reproduces the reference's blocks bit for bit."""
     from oracle import refcuda
     if not refcuda.adapter_available():
         pytest.skip("oracle/_ref/libmmref_adapter.so not built (needs /root/reference at build time)")
     g = golden["g"]
-    r = refcuda.RefCuda(0, adapter=True).generate(golden["x0"], golden["z0"], golden["nx"], golden["nz"], 6)
+    ra = refcuda.RefCuda(0, adapter=True)
+    r = ra.generate(golden["x0"], golden["z0"], golden["nx"], golden["nz"], 6)
+    # all seven overridden entry points ran: S1, S2, S3, S4, S6 and the two CPU passes of S5 (placements per chunk, gather per chunk)
+    calls = [ra.L.mmadapter_calls(i) for i in range(7)]
+    assert all(c > 0 for c in calls) and calls[5] >= 144 and calls[6] >= 36, calls
     assert np.array_equal(r["stage"], g["stage"])
     assert np.array_equal(r["heightfield"].view(np.uint32), g["heightfield"].view(np.uint32))
     assert np.array_equal(r["layers"][g["zone_idx"]][:, 10:].view(np.uint32), g["zone_layers"][:, 10:].view(np.uint32))
@@ -134,7 +204,7 @@ def test_adapter_runs_reference_state_machine_on_new_kernels(gen, golden):
 
 
 # ------------------------------------------------------------------ against the oracle, other windows
-@pytest.mark.parametrize("biome", [1, 8, 9, 13, 16, 19, 23])
+@pytest.mark.parametrize("biome", sorted(BIOME_CHUNKS))
 def test_stage1_all_biomes_vs_oracle(gen, oracle, biome):
     cx, cz = BIOME_CHUNKS[biome]
     origins = origins_of(cx - 2, cz - 2, 5, 5)
@@ -142,7 +212,8 @@ def test_stage1_all_biomes_vs_oracle(gen, oracle, biome):
     oh, ow = oracle.heightfields(origins)
     assert w[12, biome].min() == 1.0                            # the window really is that biome
     assert np.array_equal(w.view(np.uint32), ow.view(np.uint32))
-    # powf goes through MUFU.RCP on the GPU (oracle/mm_devmath.h:dm_rcp_approx): last-bit differences allowed there
+    # the three biomes whose height function calls powf (ARCHIPELAGO, SPARSE_DESERT, MOUNTAINS; biomeFuncs.hpp:235,311,375):
+    # powf goes through MUFU.RCP on the GPU (oracle/mm_devmath.h:dm_rcp_approx), last-bit differences allowed there
     tol_bits = 2 if biome in (1, 13, 23) else 0
     diff = np.abs(h.view(np.int32).astype(np.int64) - oh.view(np.int32))
     assert diff.max() <= tol_bits, int(diff.max())

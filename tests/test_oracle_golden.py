@@ -74,6 +74,27 @@ def test_s5_feature_placements_exact_and_ordered(oracle, golden):
         assert same_placements(a, b)
 
 
+def test_s5_cave_grid_test_readings(oracle, golden):
+    """tryGenerateCaveFeaturePlacement has no return statement where its grid test fails (chunk.cu:1028-1038). The default
+    reading (what g++ made of it: test dropped) reproduces the reference build's lists - the test above. The source-text
+    reading (set_cave_grid_test(True): test honoured, a failed test is `false`) must thin the cave placements out by more
+    than an order of magnitude (grid cells are 3..16 blocks wide) and leave the setting restorable."""
+    g = golden["g"]
+    zone = g["zone_idx"][:36]
+    args = (golden["origins"][zone], g["heightfield"][zone], g["biome_weights"][zone], g["zone_layers"][:36], g["cave_layers"][:36])
+    F0, CF0 = oracle.feature_placements(*args)
+    try:
+        oracle.set_cave_grid_test(True)
+        F1, CF1 = oracle.feature_placements(*args)
+    finally:
+        oracle.set_cave_grid_test(False)
+    n0, n1 = sum(len(c) for c in CF0), sum(len(c) for c in CF1)
+    assert 0 < n1 < n0 / 8, (n0, n1)
+    assert sum(len(f) for f in F1) > 0
+    F2, CF2 = oracle.feature_placements(*args)
+    assert all(same_placements(a, b) for a, b in zip(CF0, CF2)) and all(same_placements(a, b) for a, b in zip(F0, F2))
+
+
 def test_s6_blocks_bit_exact(oracle, golden):
     from oracle import oracle as orc
     g, nx = golden["g"], golden["nx"]

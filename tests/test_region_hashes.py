@@ -1,26 +1,40 @@
-"""Known-answer regression (GPU): block hashes of three regions, all six stages through the device-resident world.
+"""Known answers away from the golden window (GPU): three regions, all six stages through the device-resident world, held
+to the REFERENCE's block volumes.
 
-The values were produced by this implementation (tools/region_hashes.py on a B200) at the end of round 1, when the same
-build was bit-exact against the reference's own outputs on the golden window and the biome tour (tests/test_gpu_parity.py)
-and its 256x256-world hash had stayed bd54b5fa89ddee8d through every exact shortcut of DESIGN.md section 5. They pin what
-the golden window cannot: far-away coordinates (hash arguments of 1e7 and more, the Payne-Hanek path of sinf), other biomes,
-and batch sizes of a few thousand chunks. A change here means a block changed somewhere in these regions."""
+tests/golden/region_hashes.{json,npz} were made by tools/region_hashes.py on a B200: the unmodified reference CUDA pipeline
+(oracle/_ref) generated each region, and its block volumes were hashed per chunk with the function the product computes on
+the device (mmgen_world_chunk_hashes: FNV-1a per column, then over (cx, cz, 256 column hashes)). The regions pin what the
+golden window cannot: far-away coordinates (hash arguments of 1e7 and more, the Payne-Hanek path of sinf), other biomes,
+batches of a few thousand chunks. The product must reproduce every chunk hash except the chunks that held a block flip
+when the pins were made - those flips are listed in the json with coordinates and both block IDs (3 of 2.3e8 voxels and
+4 of 1.0e8: fp32 threshold boundaries) and the product must not differ anywhere else."""
+import json
+import os
+
+import numpy as np
 import pytest
 
-REGIONS = {
-    (0, 0, 48, 48): 0xff6ad635b943370b,
-    (-300, 500, 32, 32): 0x8751db62bfabe470,
-    (4000, -4000, 24, 36): 0xc52eb5a863df57b9,
-}
+from conftest import ROOT
+
+PINS = os.path.join(ROOT, "tests", "golden", "region_hashes.json")
+REGIONS = [(0, 0, 48, 48), (-300, 500, 32, 32), (4000, -4000, 24, 36)]
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("region", sorted(REGIONS))
-def test_region_hash(gen, mm, region):
+@pytest.mark.parametrize("region", REGIONS)
+def test_region_chunk_hashes_match_the_reference(gen, mm, region):
+    pins = json.load(open(PINS))["regions"]["%d,%d,%d,%d" % region]
+    ref_hashes = np.load(os.path.join(ROOT, "tests", "golden", "region_hashes.npz"))["%d,%d,%d,%d" % region]
+    rx0, rz0, rnx, rnz = region
     w = gen.region_world(*region)
     try:
         w.generate(mm.STAGE_ALL)
         w.sync()
-        assert w.chunk_hash_sum() == REGIONS[region]
+        own = w.chunk_hashes()
     finally:
         w.close()
+    assert len(own) == rnx * rnz == len(ref_hashes)
+    differing = {(rx0 + k % rnx, rz0 + k // rnx) for k in range(rnx * rnz) if own[(rx0 + k % rnx, rz0 + k // rnx)] != int(ref_hashes[k])}
+    known = {tuple(f["chunk"]) for f in pins["product_flips_when_pinned"]}
+    assert differing <= known, "chunks that differ from the reference and held no known flip: %s" % sorted(differing - known)
+    assert len(pins["product_flips_when_pinned"]) / pins["voxels"] < 1e-6

@@ -36,6 +36,14 @@ def test_tiles_partition_the_region(pkg, n, region, align):
             assert z0 == region[1] or z0 % align == 0
 
 
+def test_grid_for_is_pinned(pkg):
+    tiling, _ = pkg
+    assert [tiling.grid_for(n) for n in (1, 2, 3, 4, 6, 8)] == [(1, 1), (2, 1), (1, 3), (2, 2), (2, 3), (4, 2)]
+    # rank order is row-major: the first `columns` tiles share z0
+    ts = tiling.tiles(0, 0, 256, 256, 8)
+    assert len({t[1] for t in ts[:4]}) == 1 and ts[4][1] > ts[0][1]
+
+
 def test_apron_rule(pkg):
     tiling, _ = pkg
     # C2: filling chunks [3,9)^2 needs exactly the reference's C2 window [-7,19)^2 (one zone + pad + layer ring)

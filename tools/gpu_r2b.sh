@@ -1,0 +1,11 @@
+# round 2, call B (GPU box): reference pins, full GPU suite incl. the reference tour (new k_fill_features filter), bench
+OUT=gpurun_out/r2b; mkdir -p $OUT
+timeout 600 python tools/region_hashes.py --write > $OUT/region_hashes.log 2>&1; echo "hashes rc=$?"; tail -12 $OUT/region_hashes.log
+timeout 1500 python -m pytest tests -m gpu -q --durations=8 > $OUT/pytest.log 2>&1; echo "pytest rc=$?"; tail -30 $OUT/pytest.log
+cp gpurun_out/parity_tour.json $OUT/ 2>/dev/null
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; tail -3 $OUT/bench.err
+python - <<P
+import json
+j = json.loads(open("$OUT/bench.json").read().strip().splitlines()[-1])
+print(round(j["value"]), j["world_hash"], round(j["e2e"]["value"]), {k: round(v["ms_per_step"], 1) for k, v in j["kernels"].items()})
+P
