@@ -44,6 +44,21 @@ EXECUTED_OVER_ALGORITHMIC_CAVES = 0.48
 CAVES_DRAM_BYTES_PER_CHUNK = (26.340352e6 + 376.603904e6) / 4096
 BYTES_FILL_CHUNK = 242688                                         # S6 compulsory I/O per chunk (without feature lists)
 BYTES_CAVES_CHUNK = 107528
+BYTES_S1_CHUNK, BYTES_S2_CHUNK = 25608, 46360
+BYTES_S3_CELL_SWEEP = 12                                          # 2 planes read + 1 written per cell and sweep (1 769 472 B per 384^2 sweep)
+# SURVEY.md 8(d) static call counts of getHeight per active biome, in canonical FLOPs: simplex2 140, Worley2 = 9 cells x 45 + 18 sinf x 20
+F_W2 = 9 * 45 + 18 * F_SIN
+FLOP_BIOME_HEIGHT = [5 * F_S2] * 24
+for _b, _c in {1: 9 * F_S2, 14: 6 * F_S2, 16: 6 * F_S2, 23: 15 * F_S2, 8: 16 * F_S2 + 2 * F_W2, 9: 15 * F_S2 + F_W2, 13: 6 * F_S2 + F_W2,
+               15: 9 * F_S2 + 2 * F_W2, 19: 6 * F_S2 + F_W2 + 3 * F_SIN}.items():
+    FLOP_BIOME_HEIGHT[_b] = _c
+FLOP_BIOME_NOISE = 11 * F_S2                                      # getBiomeNoise per column
+FLOP_FBM5 = 5 * F_S2                                              # one stratified layer's thickness noise (S2)
+# issue-slot utilisation of the S6 kernels from the committed ncu captures (the placement scan has no noise-primitive FLOP model:
+# SURVEY.md 8(d) counts weights, smoothsteps and layer / list logic as 0 FLOP)
+NCU_ISSUE = {"k_caves": (87.5, "profiles/r01_k_caves_v9.txt"), "k_fill_rock": (74.0, "profiles/r01_k_fill_rock_v8.txt"),
+             "k_fill_terrain": (68.0, "profiles/r01_k_fill_terrain_v8.txt"), "k_fill_features": (52.7, "profiles/r02_k_fill_features_v1.txt"),
+             "k_erode_sweep": (37.0, "profiles/r01_k_erode_sweep_v8.txt")}
 
 
 def peaks():
@@ -171,7 +186,9 @@ def run_reference_cuda(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (the world is a pure function of chunk coordinates; no dataset exists)",
-        "config": {"workload": "full 6-stage generation, reference CUDA pipeline (unmodified chunk.cu for sm_100) incl. its CPU stages", "sample": sample},
+        "config": {"workload": "full 6-stage generation, reference CUDA pipeline (unmodified chunk.cu for sm_100) incl. its CPU stages", "sample": sample,
+                   "same_config_note": "a bounded sample, not the 256x256 world: %d chunks filled per step; chunks/s is per filled chunk and includes the "
+                                       "apron (S1-S3 on the whole window are < 2 %% of the reference's step)" % filled},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample,
                          "note": "the reference has no CPU generator: its own implementation of the path is CUDA kernels driven by one host thread"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -195,6 +212,157 @@ def run_reference_cpu(args):
                       "config": {"workload": "%dx%d-chunk world, full 6-stage generation" % (args.world, args.world)},
                       "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
                       "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "stage_detail": detail}))
+
+
+def cheap_stage_rooflines(wc, steps, kernels, fp32_peak, hbm_peak):
+    """Rooflines of S1 / S2 / S3 from the library's work counters (mmgen_work_counters), per step of this rank."""
+    wc = [float(v) / steps for v in wc]
+    ms = lambda k: kernels.get(k, {"ms_per_step": 0.0})["ms_per_step"]
+    f1 = sum(wc[b] * FLOP_BIOME_HEIGHT[b] for b in range(24)) + wc[24] * FLOP_BIOME_NOISE
+    f2 = wc[25] * FLOP_FBM5
+    b3 = wc[27] * 1024 * BYTES_S3_CELL_SWEEP
+    s1 = {"algorithmic_flop": f1, "fp32_tflops": f1 / 1e12 / max(ms("k_heightfield") / 1e3, 1e-9), "columns": wc[24],
+          "active_biomes_per_column": sum(wc[:24]) / max(wc[24], 1.0), "hbm_gbs": wc[24] / 256 * BYTES_S1_CHUNK / 1e9 / max(ms("k_heightfield") / 1e3, 1e-9)}
+    s2 = {"algorithmic_flop": f2, "fp32_tflops": f2 / 1e12 / max(ms("k_layers") / 1e3, 1e-9), "fbm5_per_column": wc[25] / max(wc[26], 1.0),
+          "hbm_gbs": wc[26] / 256 * BYTES_S2_CHUNK / 1e9 / max(ms("k_layers") / 1e3, 1e-9)}
+    s3 = {"tiles_swept": wc[27], "tiles_launched": wc[27] + wc[28], "algorithmic_bytes": b3,
+          "plane_traffic_gbs": b3 / 1e9 / max(ms("k_erode_sweep") / 1e3, 1e-9)}
+    for d in (s1, s2):
+        d["fp32_frac"] = d["fp32_tflops"] / fp32_peak
+        d["hbm_frac"] = d["hbm_gbs"] / hbm_peak
+        d["bound"] = "fp32"
+    s3["frac_of_hbm_peak"] = s3["plane_traffic_gbs"] / hbm_peak
+    s3["bound"] = "L2 bandwidth + launch latency (the planes of a 32-zone batch, 75 MB, stay in the 126 MB L2; HBM peak is the only measured " \
+                  "bandwidth figure, so the fraction is against it)"
+    return s1, s2, s3
+
+
+def run_c4(args):
+    """BASELINE.json config 4: cave / cave-biome + chunk-fill stress on [0,32)^2 - S4 and S6 timed in isolation with S1-S3 (and S5
+    for the fill) precomputed and resident."""
+    import torch
+    import mmgen_loader
+    mm = mmgen_loader.load()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the generation path has no CPU fallback")
+    gen = mm.ChunkGen(0)
+    pk = peaks()
+    world = gen.region_world(0, 0, 32, 32)
+    world.generate(mm.STAGE_ALL)
+    world.sync()
+    n_target = 1024
+    st = world.stages().ravel()
+    n_caved = int((st >= 4).sum())
+    hgt = np.floor(world.download(heightfield=True)["heightfield"]).astype(np.int64)
+    cave_voxels = int(np.maximum(hgt[st >= 4], 128).sum())
+    fill_voxels = int(np.clip(hgt[st == 6], 1, 383).sum())
+    fp32 = min(gen.measure_fp32_peak(), pk["fp32_tflops"])
+    sampler = ClockSampler(0)
+    t4 = t6 = 0.0
+    for i in range(args.warmup + args.steps):
+        if i == args.warmup:
+            torch.cuda.synchronize()
+            gen.kernel_timing(True)
+            sampler.start()
+            l0 = gen.launch_count()
+        world.rewind(3)
+        world.generate(mm.STAGE_CAVES)
+        a = float(world.stage_ms()[4])
+        world.generate(mm.STAGE_FEATURES)
+        world.generate(mm.STAGE_FILL)
+        b = float(world.stage_ms()[6])
+        if i >= args.warmup:
+            t4 += a
+            t6 += b
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    kt = gen.kernel_times()
+    gen.kernel_timing(False)
+    launches = gen.launch_count() - l0
+    t4 /= args.steps
+    t6 /= args.steps
+    assert int((world.stages() == 6).sum()) == n_target
+    kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in kt.items() if v[1]}
+    s4 = {"ms": t4, "chunks": n_caved, "chunks_per_s": n_caved / (t4 / 1e3), "fp32_tflops": cave_voxels * FLOP_CAVE_VOXEL / 1e12 / (t4 / 1e3),
+          "hbm_gbs": n_caved * BYTES_CAVES_CHUNK / 1e9 / (t4 / 1e3), "executed_over_algorithmic": EXECUTED_OVER_ALGORITHMIC_CAVES}
+    s6 = {"ms": t6, "chunks": n_target, "chunks_per_s": n_target / (t6 / 1e3), "fp32_tflops": fill_voxels * FLOP_CAVE_BIOME / 1e12 / (t6 / 1e3),
+          "hbm_gbs": n_target * BYTES_FILL_CHUNK / 1e9 / (t6 / 1e3)}
+    for d in (s4, s6):
+        d["fp32_frac"] = d["fp32_tflops"] / fp32
+        d["hbm_frac"] = d["hbm_gbs"] / pk["hbm_gbs"]
+    s4["executed_fp32_frac"] = s4["fp32_frac"] * EXECUTED_OVER_ALGORITHMIC_CAVES
+    dom = "k_caves"
+    out = {"metric": "c4_cave_and_fill_stress_chunks_per_sec", "value": n_target / ((t4 + t6) / 1e3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": t4 + t6, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic (the world is a pure function of chunk coordinates; no dataset exists)",
+           "config": {"workload": "BASELINE config 4: 32x32 chunks [0,32)^2 of full 16x384x16 volumes; S4 (caves + cave biomes, on the region (+) 3 chunks "
+                                  "= %d chunks) and S6 (fill + decorators, 1024 chunks) each timed in isolation by CUDA events, S1-S3 and S5 resident" % n_caved,
+                      "l2": "S4 writes %.0f MB and S6 %.0f MB per step: beyond the 126 MB L2 only for S6; no flush (inputs of a step were written by the "
+                            "previous stage of the same step)" % (n_caved * 98304 / 1e6, n_target * 98304 / 1e6)},
+           "stages": {"S4": s4, "S6": s6}, "kernels": kernels, "gpu_launches": int(launches), "clocks": clocks,
+           "roofline": {"bound": "fp32", "kernel": dom, "achieved": s4["fp32_tflops"], "peak": fp32, "unit": "TFLOP/s", "frac": s4["fp32_frac"],
+                        "traffic": CAVES_DRAM_BYTES_PER_CHUNK * n_caved, "executed": {"frac": s4["executed_fp32_frac"]},
+                        "note": "S6 as HBM: %.1f GB/s of compulsory bytes = %.4f of the measured %.0f GB/s; it is bound by per-voxel noise and the placement "
+                                "scan, not by HBM" % (s6["hbm_gbs"], s6["hbm_frac"], pk["hbm_gbs"])},
+           "e2e": None, "cpu_baseline": None}
+    print(json.dumps(out), flush=True)
+    world.close()
+
+
+def run_c3(args):
+    """BASELINE.json config 3: a 64x64-chunk region streamed around a standing player at the reference's load pattern (spiral order,
+    per-stage FIFO queues, action-time budget: Terrain::tick, terrain.cpp:587-960) through mmgen_stream_*."""
+    import torch
+    import mmgen_loader
+    mm = mmgen_loader.load()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the generation path has no CPU fallback")
+    gen = mm.ChunkGen(0)
+    R = 51                                     # generation radius: fills the 66x66 chunks around the player
+    profiles = {"reference": (500, 60 * 500), "budget_x8": (4000, 60 * 4000), "unbounded": (1 << 24, 1 << 30)}
+    res = {}
+    sampler = ClockSampler(0)
+    launches = 0
+    for name, (cap, rate) in profiles.items():
+        runs = []
+        for rep in range(args.warmup + args.steps):
+            if name == "reference" and rep == args.warmup:
+                sampler.start()
+            l0 = gen.launch_count()
+            t = mm.Terrain(gen, -R - 1, -R - 1, 2 * R + 2, 2 * R + 2)
+            t.set_radii(16, R)
+            t.set_costs(mm.REFERENCE_COSTS, cap, rate)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            log = t.run_until_idle(1.0 / 32.0)
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            filled = sum(s["filled"] for s in log)
+            dev = sum(s["deviceMs"] for s in log)
+            h = t.chunk_hash_sum()
+            t.close()
+            if rep >= args.warmup:
+                runs.append((wall, dev, filled, len(log)))
+                if name == "reference":
+                    launches += gen.launch_count() - l0
+        if name == "reference":
+            clocks = sampler.stop()
+        wall = sum(r[0] for r in runs) / len(runs)
+        dev = sum(r[1] for r in runs) / len(runs)
+        res[name] = {"ticks": runs[0][3], "chunks_filled": runs[0][2], "wall_ms": 1e3 * wall, "device_ms": dev, "chunks_per_s": runs[0][2] / wall,
+                     "frame_budget": cap, "hash": "%016x" % h,
+                     "max_batch": {k: max(s[k] for s in log) for k in ("heightfields", "layers", "caves", "filled", "zonesEroded")}}
+    r = res["reference"]
+    out = {"metric": "c3_streaming_chunks_per_sec", "value": r["chunks_per_s"], "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": r["wall_ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic (the world is a pure function of chunk coordinates; no dataset exists)",
+           "config": {"workload": "BASELINE config 3: 66x66 chunks streamed around a standing player (generation radius 51) by the re-hosted Terrain::tick "
+                                  "at the reference's action-time costs (<= 166 heightfields / 100 layers / 62 caves / 62 fills / 1 zone per tick); "
+                                  "a step = one whole session from an empty world to idle, wall clock incl. every per-tick synchronisation",
+                      "timing": "wall clock around the session (the scheduler is host code; device time of the ticks' launches is in device_ms)"},
+           "profiles": res, "gpu_launches": int(launches), "clocks": clocks, "e2e": None, "cpu_baseline": None,
+           "roofline": None}
+    print(json.dumps(out), flush=True)
 
 
 def run_own(args):
@@ -269,6 +437,7 @@ def run_own(args):
     fp32_measured = gen.measure_fp32_peak()          # FFMA microbenchmark on this GPU, right before the timed region
     barrier()
     gen.kernel_timing(True)                          # CUDA event pairs around every hot-kernel launch, on the world's stream
+    gen.work_counters(reset=True)                    # S1 / S2 / S3 work counters of the timed steps
     sampler.start()
     l0 = gen.launch_count()
     t0 = time.perf_counter()
@@ -283,6 +452,7 @@ def run_own(args):
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
     ktimes = gen.kernel_times()                      # {kernel: (device ms summed over the timed steps, launches)}
+    wcount = gen.work_counters(reset=True)
     gen.kernel_timing(False)
     launches = gen.launch_count() - l0
     dev_s = max_over_ranks(dev_ms / 1e3)
@@ -351,15 +521,24 @@ def run_own(args):
             "note": "no stage is a dense contraction and none is HBM-bound (S6 moves %.0f GB/s of compulsory bytes), so the bound is the FP32 pipe; "
                     "algorithmic FLOPs = noise-primitive calls of the reference algorithm x canonical cost (SURVEY.md 8d), evaluations this "
                     "implementation proves unnecessary still count; k_fill_features (placement rasterisation) has no FLOP model and is reported by time" % hbm6}
+    r1, r2, r3 = cheap_stage_rooflines(wcount, args.steps, kernels, fp32_peak, pk["hbm_gbs"])      # this rank's counters and kernel times
+    s6k = {k: {"ms": kernels[k]["ms_per_step"], "share_of_S6": kernels[k]["ms_per_step"] / max(float(stage_ms[6]), 1e-9),
+               "issue_slot_utilisation_pct": NCU_ISSUE[k][0], "src": NCU_ISSUE[k][1]}
+           for k in ("k_fill_terrain", "k_fill_rock", "k_fill_features") if k in kernels}
     stages = {
-        "S1": {"ms": float(stage_ms[1])}, "S2": {"ms": float(stage_ms[2])},
-        "S3": {"ms": float(stage_ms[3]), "sweeps": world.erosion_sweeps(),
-               "plane_traffic_gbs": world.erosion_sweeps() * 32 * 3 * 589824 / 1e9 / max(kernels.get("k_erode_sweep", {"ms_per_step": 0})["ms_per_step"] / 1e3, 1e-9),
-               "note": "L2-resident: <= 32 zones x 3 planes x 590 KB per sweep launch"},
-        "S4": {"ms": float(stage_ms[4]), "fp32_tflops": ach4, "fp32_frac": ach4 / (fp32_peak * world_size)},
-        "S5": {"ms": float(stage_ms[5])},
-        "S6": {"ms": float(stage_ms[6]), "fp32_tflops": ach6, "fp32_frac": ach6 / (fp32_peak * world_size), "hbm_gbs": hbm6,
-               "hbm_frac": hbm6 / (pk["hbm_gbs"] * world_size), "hbm_peak_src": pk["src"]},
+        "S1": dict(r1, ms=float(stage_ms[1])), "S2": dict(r2, ms=float(stage_ms[2])),
+        "S3": dict(r3, ms=float(stage_ms[3]), sweeps=world.erosion_sweeps(), issue_slot_utilisation_pct=NCU_ISSUE["k_erode_sweep"][0]),
+        "S4": {"ms": float(stage_ms[4]), "bound": "fp32", "fp32_tflops": ach4, "fp32_frac": ach4 / (fp32_peak * world_size),
+               "executed_fp32_frac": ach4 / (fp32_peak * world_size) * EXECUTED_OVER_ALGORITHMIC_CAVES,
+               "hbm_gbs": sum_over_ranks(int((st >= 4).sum()) * BYTES_CAVES_CHUNK) / 1e9 / max(max_over_ranks(stage_ms[4] / 1e3), 1e-9),
+               "issue_slot_utilisation_pct": NCU_ISSUE["k_caves"][0]},
+        "S5": {"ms": float(stage_ms[5]), "bound": "latency (integer / RNG walk per column; time only, SURVEY.md 8(d))"},
+        "S6": {"ms": float(stage_ms[6]), "bound": "fp32 / issue (per-voxel noise + placement scan), not HBM", "fp32_tflops": ach6,
+               "fp32_frac": ach6 / (fp32_peak * world_size), "hbm_gbs": hbm6, "hbm_frac": hbm6 / (pk["hbm_gbs"] * world_size),
+               "hbm_peak_src": pk["src"], "kernels": s6k,
+               "note": "algorithmic FLOPs = getCaveBiome (11 simplex3 + 12 simplex2) per voxel 0 < y <= h as the reference evaluates it; the placement "
+                       "scan (k_fill_features) is integer / shared-memory work that SURVEY.md 8(d) counts as 0 FLOP: it is reported by time and by "
+                       "the issue-slot utilisation of its ncu capture"},
     }
     counts = tiling.stage_chunk_counts(*tile)
     checks = sharding.gather_u64(checksum)
@@ -409,6 +588,9 @@ def main():
     ap.add_argument("--ref-zones", type=int, default=3, help="the reference CUDA arm generates ZxZ erosion zones (+ apron) per step")
     ap.add_argument("--cpu-cave-chunks", type=int, default=0, help="bound the CPU baseline's S4 sample (0 = the whole zone)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", default="c5", choices=["c5", "c3", "c4"],
+                    help="c5 (default): the 256x256-chunk world the metric is quoted on; c3: 64x64 streaming region at the reference's tick pattern; "
+                         "c4: cave + fill stress on 32x32 chunks, S4 and S6 timed in isolation (BASELINE.json configs 3 and 4; one GPU)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl != "b200":
@@ -418,6 +600,11 @@ def main():
             run_reference_cuda(args)
         else:
             run_reference_cpu(args)
+        return
+    if args.config != "c5":
+        if rank != 0:
+            return
+        (run_c3 if args.config == "c3" else run_c4)(args)
         return
     run_own(args)
 

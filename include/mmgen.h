@@ -145,6 +145,9 @@ int mmgen_world_destroy(MmgenWorld* w);
 int mmgen_world_window(MmgenWorld* w, int* out8);
 /* forget all progress (stages back to 0); buffers stay allocated */
 int mmgen_world_reset(MmgenWorld* w);
+/* forget the progress beyond `stage` (0..6): chunks further along fall back to it and the later stages can be generated again
+ * from the resident products of the earlier ones (used to time one stage in isolation, BASELINE config 4) */
+int mmgen_world_rewind(MmgenWorld* w, int stage);
 int mmgen_world_generate(MmgenWorld* w, int stageMask);
 /* mmgen_world_generate + delivery of the block volumes into HOST memory, the reference's contract for
  * Chunk::fill (results complete in host memory on return, chunk.cu:1621): out_blocks is
@@ -245,6 +248,10 @@ int mmgen_kernel_timing(int enable);
 /* summed device time and launch count per kernel since the last call; kernel i is named mmgen_kernel_name(i); *n = entries written */
 int mmgen_kernel_times(int cap, float* out_ms, int32_t* out_launches, int* n);
 const char* mmgen_kernel_name(int slot);
+/* work counters of the cheap stages since the last reset, for their roofline figures (32 values): [0..23] S1 columns in which
+ * surface biome b had weight > 0 (its height function ran), [24] S1 columns, [25] S2 fbm<5> evaluations, [26] S2 columns,
+ * [27] S3 32x32 tiles swept, [28] S3 tile launches that returned at the quiet-tile test. reset != 0 clears them afterwards. */
+int mmgen_work_counters(uint64_t* out32, int reset);
 /* tuning knob: queue slots per chunk for the rock voxels that k_fill_terrain hands to k_fill_rock (default and maximum 49 152;
  * <= 0 restores the default). Voxels that do not fit are finished in place: results never depend on this value. */
 int mmgen_set_rock_queue_per_chunk(int slots);

@@ -91,6 +91,12 @@ class ChunkGen:
         self.L.mmgen_kernel_name.restype = ctypes.c_char_p
         return {self.L.mmgen_kernel_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n.value)}
 
+    def work_counters(self, reset=True):
+        """mmgen_work_counters: 32 uint64 counters of the cheap stages (see include/mmgen.h)."""
+        out = np.zeros(32, np.uint64)
+        self._check(self.L.mmgen_work_counters(_ptr(out), 1 if reset else 0))
+        return out
+
     def measure_fp32_peak(self):
         """Achieved FP32 FMA rate of the device in TFLOP/s (microbenchmark kernel in libmmgen)."""
         v = ctypes.c_float(0)
@@ -240,6 +246,10 @@ class World:
 
     def reset(self):
         self.gen._check(self.L.mmgen_world_reset(self.h))
+
+    def rewind(self, stage):
+        """Chunks beyond `stage` fall back to it; later stages can be generated again from the resident earlier products."""
+        self.gen._check(self.L.mmgen_world_rewind(self.h, int(stage)))
 
     def generate_to_host(self, out_blocks_ptr, stage_mask=STAGE_ALL):
         """Generate and deliver the region's block volumes to host memory at address out_blocks_ptr

@@ -38,6 +38,15 @@ inline int fail(const char* what, cudaError_t err, const char* file, int line)
 extern int g_numSMs;            // multiprocessor count of the bound device (148 on a B200), set by mmgen_init
 #define kNumSMs (::mmg::g_numSMs)
 
+// Work counters for the roofline figures of the cheap stages (mmgen_work_counters; bench.py turns them into algorithmic
+// FLOPs / bytes with SURVEY.md 8(d)'s canonical costs). Always on: a few warp-aggregated atomics per CTA of S1 / S2 / S3.
+//   [0..23] S1: columns in which surface biome b has weight > 0 (getHeight is evaluated for exactly those, chunk.cu:171-179)
+//   [24]    S1: columns;  [25] S2: fbm<5> evaluations (one per stratified layer with weight > 0 that is reached, chunk.cu:308-320)
+//   [26]    S2: columns;  [27] S3: 32x32 tiles actually swept (k_erode_sweep CTAs that did not return at the quiet-tile test)
+//   [28]    S3: tile CTAs that returned at the quiet-tile test (swept + quiet = launched)
+enum { W_S1_BIOME0 = 0, W_S1_COLUMNS = 24, W_S2_FBM5 = 25, W_S2_COLUMNS = 26, W_S3_TILES_SWEPT = 27, W_S3_TILES_QUIET = 28, W_NUM = 32 };
+__device__ unsigned long long g_work[W_NUM];
+
 // resident CTAs per SM the register allocator is asked to allow (tuned on a B200)
 #ifndef MMG_CAVES_MINBLOCKS
 #define MMG_CAVES_MINBLOCKS 10

@@ -20,8 +20,23 @@ __global__ void __launch_bounds__(256) k_heightfield(const int* __restrict__ chu
     const int2 o = origins[chunk];
     const int wx = o.x + (idx & 15), wz = o.y + (idx >> 4);
     float* w = biomeWeights + (size_t)chunk * (NUM_BIOMES * 256) + idx;
-    const float h = surface_column(wx, wz, w, 256);
+    unsigned active = 0u;
+    const float h = surface_column(wx, wz, w, 256, &active);
     heightfield[(size_t)chunk * 256 + idx] = h;
+    // work counters (mm_common.cuh): per biome, the columns of this CTA that evaluated its height function
+    __shared__ unsigned shCount[NUM_BIOMES];
+    if (idx < NUM_BIOMES) shCount[idx] = 0u;
+    __syncthreads();
+    const int lane = idx & 31;
+#pragma unroll
+    for (int b = 0; b < NUM_BIOMES; ++b)
+    {
+        const unsigned m = __ballot_sync(0xffffffffu, (active >> b) & 1u);
+        if (lane == 0 && m) atomicAdd(&shCount[b], (unsigned)__popc(m));
+    }
+    __syncthreads();
+    if (idx < NUM_BIOMES && shCount[idx]) atomicAdd(&g_work[W_S1_BIOME0 + idx], (unsigned long long)shCount[idx]);
+    if (idx == NUM_BIOMES) atomicAdd(&g_work[W_S1_COLUMNS], 256ull);
 }
 
 }  // namespace mmg

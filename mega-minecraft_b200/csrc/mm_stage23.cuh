@@ -71,8 +71,10 @@ __global__ void __launch_bounds__(256) k_layers(const int* __restrict__ chunkLis
         for (int b = 0; b < NUM_BIOMES; ++b) acc = fmaf(w[b], c_biomeMaterialWeights[b][m], acc);
         return acc;
     };
+    int nFbm = 0;      // work counter: fbm<5> evaluations of this column
     auto thickness = [&](int l, float tw) -> float {
         if (!(tw > 0.0f)) return 0.0f;
+        ++nFbm;
         const float off = (float)l * 5283.64f;
         const MaterialInfo mi = c_materialInfos[l];
         const float f = fbm2<5>(fmaf(mi.v2, fx, off), fmaf(mi.v2, fz, off));
@@ -102,6 +104,13 @@ __global__ void __launch_bounds__(256) k_layers(const int* __restrict__ chunkLis
         const float lh = fmaxf(mi.thickness * ((mi.v2 - slope) / mi.v2), 0.0f);
         height = fmaf(-matWeight(l), lh, height);
         out[l * 256] = height;
+    }
+    {
+        int v = nFbm;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if ((idx & 31) == 0) atomicAdd(&g_work[W_S2_FBM5], (unsigned long long)v);
+        if (idx == 32) atomicAdd(&g_work[W_S2_COLUMNS], 256ull);
     }
 }
 
@@ -170,7 +179,9 @@ __global__ void __launch_bounds__(32 * kErodeRows) k_erode_sweep(float* __restri
             const int tx = (int)blockIdx.x + lid % 3 - 1, tz = (int)blockIdx.y + lid / 3 - 1;
             if (tx >= 0 && tx < 12 && tz >= 0 && tz < 12) moved = rowPrev[tx + 12 * tz];
         }
-        if (!__syncthreads_or(moved)) return;
+        const int live = __syncthreads_or(moved);
+        if (lid == 10) atomicAdd(&g_work[live ? W_S3_TILES_SWEPT : W_S3_TILES_QUIET], 1ull);
+        if (!live) return;
     }
     float* zone = zones + (size_t)blockIdx.z * kZonePlanes * kErosionCols;
     const float* sIn = zone + (size_t)pIn * kErosionCols;

@@ -779,6 +779,10 @@ constexpr int kSlab = 32;                  // voxels of a column per CTA of k_fi
 constexpr int kSlabPitch = 257;            // shBest[yy][col], padded: lanes that differ in yy hit different banks
 constexpr unsigned kNoBest = 0xffffffffu;
 constexpr int kRound = 1024;               // placements scanned per round (the round's active list lives in shared memory)
+#ifndef MMG_QCAP
+#define MMG_QCAP 96
+#endif
+constexpr int kFeatQueue = MMG_QCAP;       // candidates a warp collects before it calls the rasteriser (>= 96: one round adds up to 64)
 // ceil(65536 / n), n = 1..16 ([0] unused): (c * c_recip16[n]) >> 16 = c / n for c < 256
 __constant__ const unsigned c_recip16[17] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096};
 
@@ -805,8 +809,12 @@ __device__ __forceinline__ int cols_per_tile(int ny) { return ny >= MMG_TILE / 3
 //     belongs to the same placement.
 // The reference's rule "the first placement in list order that contains the voxel wins, surface list before cave list"
 // (chunk.cu:1444-1500) becomes an atomicMin over (list position << 8 | block) per voxel, so the order in which tiles are
-// processed does not matter. (A split into a surface pass and a cave pass, to shrink the code each pass keeps in the
-// instruction cache, was measured in round 2: 214 ms against 162 ms per 256x256 world - dropped.)
+// processed does not matter.
+// Measured and dropped in round 2 (per 256x256 world; the kernel is bound by instruction fetch - stalled_no_instruction 4.4
+// warps per issue, profiles/r02_k_fill_features_v1.txt - and by the latency of its short per-tile chains, not by the number
+// of rasteriser calls): a surface pass + a cave pass so that each pass's rasterisers fit the instruction cache (214 ms
+// against 162); column-level ball / disc / diamond tests that cut the rasteriser calls by 29 % (spheres: only hits reach
+// the rasteriser) but lengthen the per-column chain (174 ms against 147, profiles/r02_fill_features_variants.txt).
 __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict__ fillList, const int2* __restrict__ origins,
                                                           const FeaturePlacement* __restrict__ gF, const CaveFeaturePlacement* __restrict__ gCF,
                                                           const Prep* __restrict__ prepF, const Prep* __restrict__ prepC,
@@ -821,7 +829,7 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
     __shared__ unsigned shPacked;                            // tiles handed out << 11 | active placements
     __shared__ int shNextTile;
     __shared__ float shGeom[8 * kMushroomGeomFloats];        // per warp: purple_mushroom_geom of the placement being rasterised
-    __shared__ unsigned short shQueue[8 * 96];               // per warp: candidates waiting for a full warp (< 32 + 2 x 32)
+    __shared__ unsigned short shQueue[8 * kFeatQueue];       // per warp: candidates waiting for the rasteriser
     const int slab = blockIdx.x % 12, li = blockIdx.x / 12;
     const int chunk = fillList ? fillList[li] : li;
     const int t = threadIdx.x, y0 = slab * kSlab, y1 = y0 + kSlab - 1;
@@ -852,7 +860,7 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
     const CaveFeaturePlacement* cf = gCF + (size_t)li * strideCF;
     const Prep* pf = prepF + (size_t)li * strideF;
     const Prep* pc = prepC + (size_t)li * strideCF;
-    unsigned short* wq = shQueue + (t >> 5) * 96;
+    unsigned short* wq = shQueue + (t >> 5) * kFeatQueue;
     float* wgeom = shGeom + (t >> 5) * kMushroomGeomFloats;
 
     // the warp's current placement
@@ -918,7 +926,7 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
             const int e = shActE[s0];
             if (e != curE)
             {
-                if (qn > 0) drain();                          // the queue holds fewer than 32 voxels between tiles
+                while (qn > 0) drain();                       // another placement: the queue is rasterised to the end
                 curE = e;
                 cave = e >= nF;
                 k = cave ? pc[e - nF] : pf[e];
@@ -978,11 +986,13 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
                     if (ok[1]) wq[qn + __popc(m0) + __popc(m1 & below)] = (unsigned short)code[1];
                     qn += __popc(m0) + __popc(m1);
                     __syncwarp();
-                    while (qn >= 32) drain();
+                    // (deeper queues - 160, 256 entries, so that several rasteriser calls run back to back - measured no faster)
+                    if (qn > kFeatQueue - 64)
+                        while (qn >= 32) drain();
                 }
             }
         }
-        if (qn > 0) drain();
+        while (qn > 0) drain();
         curE = -1;
     }
     __syncthreads();

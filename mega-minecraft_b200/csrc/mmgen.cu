@@ -915,6 +915,14 @@ int mmgen_world_reset(MmgenWorld* w)
     return 0;
 }
 
+int mmgen_world_rewind(MmgenWorld* w, int stage)
+{
+    if (stage < 0 || stage > 6) { g_lastError = "mmgen_world_rewind: stage must be 0..6"; return 1; }
+    MMG_CUDA(cudaStreamSynchronize(w->stream));
+    for (auto& s : w->stage) s = std::min<uint8_t>(s, (uint8_t)stage);
+    return 0;
+}
+
 int mmgen_world_create_for_region(int rx0, int rz0, int rnx, int rnz, MmgenWorld** out)
 {
     if (rnx <= 0 || rnz <= 0 || !out)
@@ -1158,6 +1166,20 @@ int mmgen_kernel_times(int cap, float* out_ms, int32_t* out_launches, int* n)
     }
     g_kt.used = 0;
     if (n) *n = k;
+    return 0;
+}
+
+int mmgen_work_counters(uint64_t* out32, int reset)
+{
+    if (requireReady()) return 1;
+    MMG_CUDA(cudaDeviceSynchronize());
+    static_assert(W_NUM == 32, "mmgen.h documents 32 counters");
+    if (out32) MMG_CUDA(cudaMemcpyFromSymbol(out32, g_work, sizeof(unsigned long long) * W_NUM));
+    if (reset)
+    {
+        static const unsigned long long zero[W_NUM] = {};
+        MMG_CUDA(cudaMemcpyToSymbol(g_work, zero, sizeof(zero)));
+    }
     return 0;
 }
 

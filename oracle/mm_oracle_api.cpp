@@ -166,6 +166,39 @@ void mmo_fill(int n, const int32_t* origins, const float* heightfield, const flo
         if (decorate) mmo::place_decorators(origins[2 * c], origins[2 * c + 1], h, w, ccl, blocks);
     });
 }
+// Diagnostic for block flips on RAFFLESIA petals (tests/test_reference_tour.py): the signed distances of the five petal
+// cylinders at a voxel, computed exactly as place_feature's F_RAFFLESIA case does (mm_placefeature.h), plus the same
+// distances with the petal rotation evaluated in double precision. out[0..4] = sd (fp32 path), out[5..9] = sd (double
+// rotation), out[10] = startAngle. A voxel whose smallest |sd| is a few ulps sits on the petal's surface.
+void mmo_debug_rafflesia(int px, int py, int pz, int wx, int wy, int wz, float* out)
+{
+    using namespace mmo;
+    V3 pos = v3((float)(wx - px), (float)(wy - py), (float)(wz - pz));
+    Minstd frng = make_rng4(px, py, pz, 1293012);
+    const float posY = pos.y;
+    pos = pos * 0.8f;
+    const float u = frng.u01();
+    out[10] = u * kTwoPi;
+    for (int i = 0; i < 5; ++i)
+    {
+        const float angle = i == 0 ? u * kTwoPi : pf_fma(u, kTwoPi, ((float)i * kTwoPi) * 0.2f);
+        for (int dbl = 0; dbl < 2; ++dbl)
+        {
+            float s, co;
+            if (dbl) { s = (float)sin(-(double)angle); co = (float)cos(-(double)angle); }
+            else dm_sincosf(-angle, &s, &co);
+            V3 pp = v3(pf_fma(pos.x, co, pos.z * s), pf_fma(posY, 0.8f, -3.2f), pf_fma(pos.z, co, -(pos.x * s)));
+            pp.y = pp.y - (float)(i % 2) * 0.53f;
+            pp.y = pf_fma(fminf(fmaxf((fabsf(pp.x - 3.f) - 1.5f) / 1.5f, 0.f), 1.f), 1.3f, pp.y);
+            pp.x = pp.x - 3.8f;
+            pp.z = pp.z * 1.2f;
+            const float dx = fabsf(len2(pp.x, pp.z)) - 2.5f, dy = fabsf(pp.y) - 0.5f;
+            const float mx = fmaxf(dx, 0.f), my = fmaxf(dy, 0.f);
+            out[5 * dbl + i] = fminf(fmaxf(dx, dy), 0.0f) + sqrtf(pf_fma(mx, mx, my * my));
+        }
+    }
+}
+
 float mmo_host_sinf(float x) { return mmo::hm_sinf(x); }
 
 // noise-primitive call counters accumulated since the last reset: simplex2, simplex3, sin, worley cells 2-D / 3-D

@@ -456,9 +456,12 @@ static inline bool place_feature(const FeaturePlacement& fp, int wx, int wy, int
     case F_RAFFLESIA:
     {
         if (pos.y > 10.f || len3(pos) > 15.f) return false;
+        // the reference build fuses the scaling of y into what follows (its SASS: FFMA y, 0.8, -1 and FFMA y, 0.8, -3.2);
+        // x and z are scaled by a plain multiply
+        const float posY = pos.y;
         pos = pos * 0.8f;
         V3 c = pos;
-        c.y = c.y - 1.f;
+        c.y = pf_fma(posY, 0.8f, -1.f);
         c.y = c.y * 1.4f;
         // the three sphere SDFs share x*x and z*z (computed once, rounded); only the y term is fused
         const float cx2 = c.x * c.x, cz2 = c.z * c.z;
@@ -468,13 +471,15 @@ static inline bool place_feature(const FeaturePlacement& fp, int wx, int wy, int
         const float hole = sqrtf(cz2 + pf_fma(y2, y2, cx2)) - 1.8f;
         sdf = fmaxf(sdf, -hole);
         if (sdf < 0.f) { *out = c.y > 1.f ? B_RAFFLESIA_CENTER : B_RAFFLESIA_STEM; return true; }
-        const float startAngle = frng.u01() * kTwoPi;
+        // startAngle + i * (2 pi / 5): the reference build folds the constant and fuses the product u * 2 pi into the sum for
+        // i >= 1 (FFMA u, 2pi, 1.2566371 ...), petal 0 uses the rounded product
+        const float u = frng.u01();
         for (int i = 0; i < 5; ++i)
         {
-            const float angle = startAngle + ((float)i * kTwoPi) * 0.2f;
+            const float angle = i == 0 ? u * kTwoPi : pf_fma(u, kTwoPi, ((float)i * kTwoPi) * 0.2f);
             float s, co;
             dm_sincosf(-angle, &s, &co);
-            V3 pp = v3(pf_fma(pos.x, co, pos.z * s), pos.y - 3.2f, pf_fma(pos.z, co, -(pos.x * s)));
+            V3 pp = v3(pf_fma(pos.x, co, pos.z * s), pf_fma(posY, 0.8f, -3.2f), pf_fma(pos.z, co, -(pos.x * s)));
             pp.y = pp.y - (float)(i % 2) * 0.53f;
             pp.y = pf_fma(fminf(fmaxf((fabsf(pp.x - 3.f) - 1.5f) / 1.5f, 0.f), 1.f), 1.3f, pp.y);
             pp.x = pp.x - 3.8f;

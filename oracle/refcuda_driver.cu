@@ -18,6 +18,7 @@
 
 #include <chrono>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -128,6 +129,13 @@ int mmref_init(int device)
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
+// Order in which the window's zones are eroded: 0 = ascending (zone x, zone z), 1 = descending. The reference erodes a zone
+// from whatever its 24x24-chunk gather window holds at that moment (copyLayers reads chunk->layers, chunk.cu:603-656, and
+// erodeZone writes the centre chunks' layers back in place, :711-721), so a zone eroded AFTER a neighbour sees that
+// neighbour's already-eroded pad: its rim depends on the order, which in the game is the player's path (terrain.cpp:471-566).
+static int g_zoneOrder = 0;
+void mmref_set_zone_order(int descending) { g_zoneOrder = descending ? 1 : 0; }
+
 // Runs the reference pipeline over chunk window [x0,x0+nx) x [z0,z0+nz) up to `lastStage`
 // (1..6), each chunk as far as the reference state machine allows inside that window.
 // unwrittenLayerFill: bit pattern written over dev_layers before every generateLayers call so
@@ -193,10 +201,11 @@ int mmref_generate(int x0, int z0, int nx, int nz, int lastStage, unsigned int u
 
     // S3: zones whose 24x24 window lies in the window and has layers (terrain.cpp:471-522)
     t = nowMs();
-    std::vector<Zone*> eroded;
-    for (auto& kv : W.zones)
+    std::vector<Zone*> eroded, zoneOrder;
+    for (auto& kv : W.zones) zoneOrder.push_back(kv.second.get());
+    if (g_zoneOrder) std::reverse(zoneOrder.begin(), zoneOrder.end());
+    for (Zone* zone : zoneOrder)
     {
-        Zone* zone = kv.second.get();
         bool ok = true;
         zone->gatheredChunks.assign(ZONE_SIZE * ZONE_SIZE * 4, nullptr);
         for (int gz = 0; gz < 2 * ZONE_SIZE && ok; ++gz)

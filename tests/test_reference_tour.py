@@ -158,6 +158,13 @@ def test_window_vs_reference_cuda(gen, mm, oracle, ref, name, chunk):
                 rec["traced_to"] = ("fp32 threshold boundary in a rasteriser: the reference's block is reproduced when the fused multiply-adds "
                                     "are " + " / ".join("rounded twice" if v.endswith("unfused") else "contracted everywhere" for v in repro)) \
                     if repro else "not reproduced by either FMA variant of the oracle (see layer starts: terrain threshold?)"
+                if 82 in (rec["product"], rec["reference"]):      # RAFFLESIA_PETAL: how far from the petal surface is the voxel?
+                    import ctypes
+                    for q in near:
+                        if not q["cave"] and q["feature"] == 11:
+                            sd = np.zeros(11, np.float32)
+                            oracle.L.mmo_debug_rafflesia(wx - q["dx"], int(y) - q["dy"], wz - q["dz"], wx, int(y), wz, sd.ctypes.data_as(ctypes.c_void_p))
+                            rec["rafflesia_petal_signed_distances"] = [float(v) for v in sd[:5]]
                 _report["flips"].append(rec)
     _report["windows"][name] = s
     # a single window may hold a flip or two (fp32 threshold boundaries); the rate over the tour is asserted below
@@ -178,3 +185,78 @@ def test_tour_flip_rate_and_report():
         pass
     assert n / max(v, 1) < FLIP_RATE_BOUND, "block flip rate %.3g over %d voxels" % (n / max(v, 1), v)
     assert not _report["tolerance_violations"], json.dumps(_report["tolerance_violations"])[:2000]
+
+
+def _erosion_deviations(prod, refl, chunks, nx, x0, z0):
+    """Columns whose eroded / backward layers (materials 10..19) differ by more than REL_TOL, with their position in the
+    384x384 erosion grid of their zone: [(cx, cz, x, z, grid_col, grid_row, on_tile_border, max_abs)]."""
+    out = []
+    a, b = prod[chunks][:, 10:].astype(np.float64), refl[chunks][:, 10:].astype(np.float64)
+    bad = (np.abs(a - b) > REL_TOL * np.abs(b)).any(axis=1)                  # (chunk, column)
+    for k, col in np.argwhere(bad):
+        c = int(chunks[k])
+        cx, cz, x, z = x0 + c % nx, z0 + c // nx, int(col) % 16, int(col) // 16
+        gc, gr = (cx - ((cx // 12) * 12 - 6)) * 16 + x, (cz - ((cz // 12) * 12 - 6)) * 16 + z
+        out.append((cx, cz, x, z, gc, gr, gc % 32 in (0, 31) or gr % 32 in (0, 31), float(np.abs(a[k, :, col] - b[k, :, col]).max())))
+    return out
+
+
+def test_reference_erosion_depends_on_zone_order_along_seams(gen, mm, ref):
+    """Multi-zone windows: the one place where the product deliberately is not the reference-as-driven.
+
+    The reference erodes a zone from whatever its 24x24-chunk gather window holds at that moment and writes the eroded centre
+    back in place (copyLayers / erodeZone, chunk.cu:603-656, 711-721). A zone eroded AFTER a neighbour therefore relaxes
+    against that neighbour's already-eroded pad, whose carried heights (accumulatedHeights, chunk.cu:507-512, 585) are gone:
+    the first one or two cells of its centre next to that pad come out differently (up to ~0.2 blocks). Which neighbour came
+    first is the player's path in the game (terrain.cpp:471-566) and the map order in oracle/refcuda_driver.cu, so the
+    reference has no unique value on those cells. The product keeps the un-eroded S2 layers for every pad, i.e. erodes every
+    zone as if it were the first: a pure function of coordinates, which tiles on different GPUs need to agree at their seams.
+
+    Shown on the 16 zones of the (-300, 500) region with the unmodified reference: it is deterministic (two runs in the same
+    order are bit-identical - this is not the in-place halo race of SURVEY.md B-4), it disagrees with ITSELF between
+    ascending and descending zone order, every cell where the product differs from it lies within three cells of the
+    centre-region edge that faces an earlier-eroded neighbour, and the zone eroded first in either order equals the product."""
+    from mega_minecraft_b200 import tiling
+    region = (-300, 500, 32, 32)
+    x0, z0, nx, nz = tiling.apron_window(*region)
+    world = gen.world(x0, z0, nx, nz)
+    try:
+        world.generate(mm.STAGE_HEIGHTFIELD | mm.STAGE_LAYERS | mm.STAGE_EROSION)
+        d = world.download(layers=True)
+        wst = world.stages().ravel()
+    finally:
+        world.close()
+    runs = []
+    try:
+        for order in (0, 0, 1):
+            ref.L.mmref_set_zone_order(order)
+            runs.append(ref.generate(x0, z0, nx, nz, 3))
+    finally:
+        ref.L.mmref_set_zone_order(0)
+    eroded = np.nonzero(wst >= 3)[0]
+    assert len(eroded) == 16 * 144 and all(np.array_equal(np.nonzero(r["stage"].ravel() >= 3)[0], eroded) for r in runs)
+    out = {"window": [x0, z0, nx, nz], "zones": len(eroded) // 144, "columns": int(len(eroded) * 256)}
+    # deterministic: same order, same bits
+    assert _bits(runs[0]["layers"][eroded][:, 10:], runs[1]["layers"][eroded][:, 10:]) == 0
+    seam = {0: (96, 97, 98), 1: (285, 286, 287)}      # centre cells facing the lower (ascending) / higher (descending) neighbour
+    for name, order, r in (("ascending", 0, runs[0]), ("descending", 1, runs[2])):
+        dev = _erosion_deviations(d["layers"], r["layers"], eroded, nx, x0, z0)
+        on_seam = [v[4] in seam[order] or v[5] in seam[order] for v in dev]
+        out[name] = {"columns_beyond_1e-5": len(dev), "all_on_seams_facing_earlier_zones": all(on_seam), "max_abs": max([v[7] for v in dev] + [0.0]),
+                     "worst": [list(v) for v in sorted(dev, key=lambda v: -v[7])[:6]]}
+        assert all(on_seam), [v for v, ok in zip(dev, on_seam) if not ok][:4]
+        assert len(dev) < 0.001 * len(eroded) * 256
+        # the zone eroded first (lowest / highest zone coordinates) saw no eroded pad: bit-exact
+        zx = (min if order == 0 else max)((x0 + int(c) % nx) // 12 for c in eroded) * 12
+        zz = (min if order == 0 else max)((z0 + int(c) // nx) // 12 for c in eroded) * 12
+        first = np.array([c for c in eroded if (x0 + int(c) % nx) // 12 * 12 == zx and (z0 + int(c) // nx) // 12 * 12 == zz])
+        assert len(first) == 144 and _rel(d["layers"][first][:, 10:], r["layers"][first][:, 10:]) <= REL_TOL
+    both = _erosion_deviations(runs[0]["layers"], runs[2]["layers"], eroded, nx, x0, z0)
+    out["reference_ascending_vs_descending"] = {"columns_beyond_1e-5": len(both), "max_abs": max([v[7] for v in both] + [0.0])}
+    assert len(both) > 0, "the reference no longer depends on the zone order: revisit DESIGN.md section 2"
+    _report["erosion_zone_order"] = out
+    try:
+        with open(os.path.join(ROOT, "gpurun_out", "parity_tour.json"), "w") as f:
+            json.dump(_report, f, indent=1)
+    except OSError:
+        pass

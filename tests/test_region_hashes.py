@@ -6,8 +6,11 @@ tests/golden/region_hashes.{json,npz} were made by tools/region_hashes.py on a B
 the device (mmgen_world_chunk_hashes: FNV-1a per column, then over (cx, cz, 256 column hashes)). The regions pin what the
 golden window cannot: far-away coordinates (hash arguments of 1e7 and more, the Payne-Hanek path of sinf), other biomes,
 batches of a few thousand chunks. The product must reproduce every chunk hash except the chunks that held a block flip
-when the pins were made - those flips are listed in the json with coordinates and both block IDs (3 of 2.3e8 voxels and
-4 of 1.0e8: fp32 threshold boundaries) and the product must not differ anywhere else."""
+when the pins were made - those flips are listed in the json with coordinates, both block IDs and both sides' layer starts
+(3 of 2.3e8 voxels and 4 of 1.0e8). All seven sit on the first row / column of a zone whose neighbour the reference driver
+eroded earlier: there the reference's eroded heights depend on the zone order (tests/test_reference_tour.py::
+test_reference_erosion_depends_on_zone_order_along_seams) and the product, which erodes every zone as
+if it were the first, is a few hundredths of a block away. The product must not differ anywhere else."""
 import json
 import os
 
