@@ -401,10 +401,18 @@ def run_own(args):
 
     S = args.world
     gen = mm.ChunkGen(local_rank)
-    # tiling: equal tiles, then (N > 1) the cuts are moved by feedback from the measured per-rank device time of
-    # untimed balancing passes (sharding.Balancer); the timed steps run on the final, fixed tiling
-    bal = sharding.Balancer((0, 0, S, S), world_size)
+    region = (0, 0, S, S)
+    # Tiling (N > 1): the cuts are placed by a cost PREDICTOR that needs stage 1 only - every rank evaluates the stage-1 cost
+    # features of a strip of the region (mmgen_chunk_costs, < 1 ms), the strips are all-gathered and every rank derives the same
+    # cuts (sharding.chunk_cost_map / Balancer.cut_by_cost). The prediction is repeated inside every timed step and its wall time
+    # is part of the step. --balance-rounds > 0 adds the round-1 feedback passes (untimed full generations) on top.
+    bal = sharding.Balancer(region, world_size)
     balance_log = []
+    predictor_ms = 0.0
+    if world_size > 1 and not args.equal_tiles:
+        t0 = time.perf_counter()
+        bal.cut_by_cost(sharding.chunk_cost_map(gen, region, rank, world_size))
+        predictor_ms = 1e3 * (time.perf_counter() - t0)
     rounds = args.balance_rounds if world_size > 1 else 0
     world = None
     for it in range(rounds + 1):
@@ -419,13 +427,76 @@ def run_own(args):
         balance_log.append({"tiles": [list(t) for t in bal.tiles()], "rank_ms": [round(t, 2) for t in times]})
         bal.update(times)
         world.close()
+    tiles_final = bal.tiles()
     n_target = tile[2] * tile[3]
     host = torch.empty(n_target * 98304, dtype=torch.uint8, pin_memory=True)
+    exchange = sharding.HaloExchange(tiles_final, rank) if world_size > 1 else None
+
+    def predict():
+        """The in-step part of the balancing: stage-1 cost features of this rank's strip, all-gather, cuts. Returns wall ms."""
+        if world_size == 1 or args.equal_tiles or rounds:
+            return 0.0
+        t0 = time.perf_counter()
+        b2 = sharding.Balancer(region, world_size)
+        b2.cut_by_cost(sharding.chunk_cost_map(gen, region, rank, world_size))
+        assert b2.tiles() == tiles_final, "the predictor is deterministic: the tiles of the resident worlds stay valid"
+        return 1e3 * (time.perf_counter() - t0)
+
+    def step(variant, to_host=False):
+        """One generation of this rank's tile. Returns (ms, exchange ms): device time of the generate call(s) (CUDA events on the
+        world's stream) + wall time of the predictor and, for the exchange variant, of pack / NCCL send-recv / unpack."""
+        ms = predict()
+        step.predict_ms += ms
+        world.reset()
+        if variant == "exchange":
+            world.generate(mm.STAGE_ALL & ~mm.STAGE_FILL)
+            ms += world.total_ms()
+            t0 = time.perf_counter()
+            exchange.run(world)
+            x = 1e3 * (time.perf_counter() - t0)
+            if to_host:
+                world.generate_to_host(host.data_ptr(), mm.STAGE_FILL)
+            else:
+                world.generate(mm.STAGE_FILL)
+            return ms + x + world.total_ms(), x
+        if to_host:
+            world.generate_to_host(host.data_ptr(), mm.STAGE_ALL)
+        else:
+            world.generate(mm.STAGE_ALL)
+        return ms + world.total_ms(), 0.0
+
+    step.predict_ms = 0.0
+
+    def set_variant(variant):
+        if variant == "exchange":
+            world.set_exchange_region(*region)
+        else:
+            world.set_exchange_region(0, 0, 0, 0)
+
+    # ---- which halo variant is faster on this box? (north_star: "recomputed redundantly or exchanged ... whichever measures faster")
+    variants = {}
+    if world_size > 1 and args.halo == "auto":
+        for v in ("recompute", "exchange"):
+            set_variant(v)
+            step(v)                               # allocations / NCCL channels
+            barrier()
+            tms = 0.0
+            for _ in range(2):
+                tms += step(v)[0]
+            variants[v] = max_over_ranks(tms / 2)
+            barrier()
+        variant = min(variants, key=variants.get)
+    else:
+        variant = args.halo if (world_size > 1 and args.halo != "auto") else "recompute"
+    set_variant(variant)
     launches0 = gen.launch_count()
 
-    for _ in range(args.warmup):
-        world.reset()
-        world.generate(mm.STAGE_ALL)
+    for i in range(args.warmup):
+        if i == args.warmup - 1:
+            gen.kernel_timing(True)              # the last warm-up step creates the CUDA events the per-kernel timing of the timed steps reuses
+        step(variant)
+    gen.kernel_times()
+    gen.kernel_timing(False)
     world.sync()
     assert int((world.stages() == 6).sum()) == n_target, "not every target chunk was filled"
     checksum = world.block_checksum()
@@ -442,16 +513,21 @@ def run_own(args):
     l0 = gen.launch_count()
     t0 = time.perf_counter()
     dev_ms = 0.0
+    xch_ms = 0.0
+    step.predict_ms = 0.0
+    ktimes = {}
     for _ in range(args.steps):
-        world.reset()
-        world.generate(mm.STAGE_ALL)
-        dev_ms += world.total_ms()          # CUDA events on the world's stream around the whole generate
+        a, x = step(variant)
+        dev_ms += a
+        xch_ms += x
         stage_ms += world.stage_ms()
+        for k, v in gen.kernel_times().items():      # {kernel: (device ms, launches)} of this step; frees the event pairs for the next one
+            ktimes[k] = (ktimes.get(k, (0.0, 0))[0] + v[0], ktimes.get(k, (0.0, 0))[1] + v[1])
     rank_ms = [t / args.steps for t in sharding.gather_floats(dev_ms)]
+    predict_ms_per_step = step.predict_ms / args.steps
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
-    ktimes = gen.kernel_times()                      # {kernel: (device ms summed over the timed steps, launches)}
     wcount = gen.work_counters(reset=True)
     gen.kernel_timing(False)
     launches = gen.launch_count() - l0
@@ -461,15 +537,12 @@ def run_own(args):
     value = total_chunks * args.steps / dev_s
 
     # ---- end-to-end leg: origins from host memory, block volumes into pinned host memory
-    world.reset()
-    world.generate_to_host(host.data_ptr(), mm.STAGE_ALL)
+    step(variant, to_host=True)
     barrier()
     t0 = time.perf_counter()
     e2e_ms = 0.0
     for _ in range(args.steps):
-        world.reset()
-        world.generate_to_host(host.data_ptr(), mm.STAGE_ALL)
-        e2e_ms += world.total_ms()
+        e2e_ms += step(variant, to_host=True)[0]
     barrier()
     e2e_wall = max_over_ranks(time.perf_counter() - t0)
     e2e_dev = max_over_ranks(e2e_ms / 1e3)
@@ -549,9 +622,16 @@ def run_own(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic (the world is a pure function of chunk coordinates; no dataset exists)",
         "config": {"workload": "%dx%d-chunk world [0,%d)^2, full 6-stage generation (S1 heightfield/biomes, S2 layers, S3 erosion, S4 caves, "
                                "S5 feature placement+gather, S6 fill+decorators)" % (S, S, S),
-                   "tiling": "%d chunk-coordinate tiles, apron recomputed per tile, no data-path collective%s" % (
-                       world_size, "; cuts balanced by feedback from %d untimed passes (per-rank device time)" % rounds if rounds else ""),
-                   "tiles": [list(t) for t in bal.tiles()], "chunks_touched_rank0": counts,
+                   "tiling": ("one tile (the whole region)" if world_size == 1 else "%d chunk-coordinate tiles; halo variant '%s'%s; cuts %s%s" % (
+                       world_size, variant,
+                       " (placement lists of the 3-chunk ring exchanged with NCCL send/recv: %d bytes sent by rank 0 per step, %.2f ms per step incl. "
+                       "pack / unpack; stages 4 + 5a run on the own tile only)" % (exchange.bytes_sent, xch_ms / args.steps) if variant == "exchange"
+                       else " (apron recomputed per tile, no data-path collective)",
+                       "equal" if args.equal_tiles else "from the stage-1 cost predictor, recomputed inside every timed step (%.2f ms of wall time per step, part of "
+                       "the step time; %.1f ms at set-up incl. allocations)" % (predict_ms_per_step, predictor_ms),
+                       "; then moved by feedback from %d untimed passes (per-rank device time)" % rounds if rounds else "")),
+                   "halo_variants_ms_per_step": {k: round(v, 2) for k, v in variants.items()},
+                   "tiles": [list(t) for t in tiles_final], "chunks_touched_rank0": counts,
                    "l2": "working set per step (>= %.1f GB written) far exceeds the 126 MB L2; no flush needed" % (n_target * 98304 / 1e9)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * max(e2e_wall, e2e_dev) / args.steps, "host_checksum": host_sum},
@@ -584,7 +664,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cpu"])
     ap.add_argument("--world", type=int, default=256, help="side of the target region in chunks")
-    ap.add_argument("--balance-rounds", type=int, default=2, help="feedback passes that move the tile cuts before the timed steps (N > 1)")
+    ap.add_argument("--balance-rounds", type=int, default=0, help="extra feedback passes (untimed full generations) that move the tile cuts (N > 1)")
+    ap.add_argument("--equal-tiles", action="store_true", help="equal tiles instead of the stage-1 cost predictor (N > 1)")
+    ap.add_argument("--halo", default="auto", choices=["auto", "recompute", "exchange"],
+                    help="N > 1: recompute the 3-chunk placement ring per tile, exchange it over NCCL, or measure both and keep the faster (auto)")
     ap.add_argument("--ref-zones", type=int, default=3, help="the reference CUDA arm generates ZxZ erosion zones (+ apron) per step")
     ap.add_argument("--cpu-cave-chunks", type=int, default=0, help="bound the CPU baseline's S4 sample (0 = the whole zone)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

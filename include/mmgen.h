@@ -28,6 +28,7 @@
 #ifndef MMGEN_H
 #define MMGEN_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -141,6 +142,21 @@ int mmgen_world_create(int cx0, int cz0, int nx, int nz, MmgenWorld** out);
  * identical to a larger window's. This is the unit a multi-GPU tiling gives to each GPU. */
 int mmgen_world_create_for_region(int rx0, int rz0, int rnx, int rnz, MmgenWorld** out);
 int mmgen_world_destroy(MmgenWorld* w);
+/* ---- halo exchange between tiles of one world (multi-GPU; SURVEY.md 8(e) option B). By default a region world recomputes
+ * the placements (stages 4 + 5a) of the 3-chunk ring around its tile. After mmgen_world_set_exchange_region(global region in
+ * chunk coordinates) it computes them only for its own tile and for ring chunks outside the global region; the rest of the
+ * ring belongs to neighbouring tiles, whose worlds pack their lists (mmgen_world_pack_placements) into a DEVICE buffer that the
+ * caller moves (NCCL send / recv, or a peer copy) and this world unpacks (mmgen_world_unpack_placements) before it runs the
+ * fill. Message = int32 counts[n][2], then per chunk of the rectangle (raster order) its surface and cave lists packed; *bytes
+ * is its length (return code 2 and *bytes set when capBytes is too small). Rectangles are in world chunk coordinates.
+ * gnx <= 0 switches the exchange off again. */
+int mmgen_world_set_exchange_region(MmgenWorld* w, int gx0, int gz0, int gnx, int gnz);
+int mmgen_world_pack_placements(MmgenWorld* w, int cx0, int cz0, int nx, int nz, void* d_buf, size_t capBytes, size_t* bytes);
+int mmgen_world_unpack_placements(MmgenWorld* w, int cx0, int cz0, int nx, int nz, const void* d_buf, size_t bytes);
+/* Cost features of n chunks from stage 1 alone (runs Chunk::generateHeightfields on them and reduces on the device), for
+ * cutting balanced tiles before anything expensive has run: out_costs[n][3] = {cave-stage voxels sum max(floor(h), 128),
+ * fill-stage voxels sum clamp(floor(h), 1, 383), land columns sum (1 - ocean/beach weight)}. */
+int mmgen_chunk_costs(int n, const int32_t* origins, float* out_costs);
 /* out8 = {window cx0, cz0, nx, nz, region rx0, rz0, rnx, rnz} (region == window without a target) */
 int mmgen_world_window(MmgenWorld* w, int* out8);
 /* forget all progress (stages back to 0); buffers stay allocated */

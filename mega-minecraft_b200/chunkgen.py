@@ -91,6 +91,14 @@ class ChunkGen:
         self.L.mmgen_kernel_name.restype = ctypes.c_char_p
         return {self.L.mmgen_kernel_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n.value)}
 
+    def chunk_costs(self, origins):
+        """mmgen_chunk_costs: (n, 3) float32 cost features of chunks from stage 1 alone: cave-stage voxels, fill-stage voxels,
+        land columns."""
+        origins = np.ascontiguousarray(origins, dtype=np.int32).reshape(-1, 2)
+        out = np.zeros((origins.shape[0], 3), np.float32)
+        self._check(self.L.mmgen_chunk_costs(origins.shape[0], _ptr(origins), _ptr(out)))
+        return out
+
     def work_counters(self, reset=True):
         """mmgen_work_counters: 32 uint64 counters of the cheap stages (see include/mmgen.h)."""
         out = np.zeros(32, np.uint64)
@@ -246,6 +254,26 @@ class World:
 
     def reset(self):
         self.gen._check(self.L.mmgen_world_reset(self.h))
+
+    def set_exchange_region(self, gx0, gz0, gnx, gnz):
+        """Halo exchange: placements of ring chunks inside this global region come from the neighbouring tiles' worlds
+        (pack_placements / unpack_placements) instead of being recomputed. gnx <= 0 switches it off."""
+        self.gen._check(self.L.mmgen_world_set_exchange_region(self.h, int(gx0), int(gz0), int(gnx), int(gnz)))
+
+    def pack_placements(self, rect, dev_ptr, cap_bytes):
+        """Packs the placement lists of the chunk rectangle rect = (cx0, cz0, nx, nz) into the DEVICE buffer at dev_ptr.
+        Returns (bytes, ok): ok is False when the buffer is too small (bytes is then the size needed)."""
+        n = ctypes.c_size_t(0)
+        rc = self.L.mmgen_world_pack_placements(self.h, int(rect[0]), int(rect[1]), int(rect[2]), int(rect[3]), ctypes.c_void_p(int(dev_ptr)),
+                                                ctypes.c_size_t(int(cap_bytes)), ctypes.byref(n))
+        if rc == 2:
+            return n.value, False
+        self.gen._check(rc)
+        return n.value, True
+
+    def unpack_placements(self, rect, dev_ptr, nbytes):
+        self.gen._check(self.L.mmgen_world_unpack_placements(self.h, int(rect[0]), int(rect[1]), int(rect[2]), int(rect[3]),
+                                                             ctypes.c_void_p(int(dev_ptr)), ctypes.c_size_t(int(nbytes))))
 
     def rewind(self, stage):
         """Chunks beyond `stage` fall back to it; later stages can be generated again from the resident earlier products."""

@@ -1118,6 +1118,68 @@ __global__ void __launch_bounds__(256) k_decorators(const int* __restrict__ fill
 }
 
 
+// ---- halo exchange of placement lists between tiles (multi-GPU, SURVEY.md 8(e) option B)
+// Wire format of one message (a rectangle of n chunks, raster order): int32 counts[n][2] = {surface, cave} list lengths, then
+// per chunk its surface list (20 B records) followed by its cave list (24 B records), packed. byteOff[i] = where chunk i's
+// records start (a multiple of 4). One CTA per chunk, copied as 32-bit words.
+__global__ void __launch_bounds__(256) k_pack_placements(const int* __restrict__ chunkIdx, const long long* __restrict__ byteOff,
+                                                         const FeaturePlacement* __restrict__ features,
+                                                         const CaveFeaturePlacement* __restrict__ caveFeatures, const int* __restrict__ counts,
+                                                         uint8_t* __restrict__ buf)
+{
+    const int i = blockIdx.x, chunk = chunkIdx[i];
+    const int nF = counts[2 * chunk], nC = counts[2 * chunk + 1];
+    if (threadIdx.x < 2) reinterpret_cast<int*>(buf)[2 * i + threadIdx.x] = threadIdx.x ? nC : nF;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(buf + byteOff[i]);
+    const uint32_t* sf = reinterpret_cast<const uint32_t*>(features + (size_t)chunk * kMaxOwnFeatures);
+    const uint32_t* sc = reinterpret_cast<const uint32_t*>(caveFeatures + (size_t)chunk * kMaxOwnCaveFeatures);
+    const int wF = nF * (int)(sizeof(FeaturePlacement) / 4), wC = nC * (int)(sizeof(CaveFeaturePlacement) / 4);
+    for (int t = threadIdx.x; t < wF; t += 256) dst[t] = sf[t];
+    for (int t = threadIdx.x; t < wC; t += 256) dst[wF + t] = sc[t];
+}
+
+__global__ void __launch_bounds__(256) k_unpack_placements(const int* __restrict__ chunkIdx, const long long* __restrict__ byteOff,
+                                                           const uint8_t* __restrict__ buf, FeaturePlacement* __restrict__ features,
+                                                           CaveFeaturePlacement* __restrict__ caveFeatures, int* __restrict__ counts)
+{
+    const int i = blockIdx.x, chunk = chunkIdx[i];
+    const int nF = min(reinterpret_cast<const int*>(buf)[2 * i], kMaxOwnFeatures), nC = min(reinterpret_cast<const int*>(buf)[2 * i + 1], kMaxOwnCaveFeatures);
+    if (threadIdx.x < 2) counts[2 * chunk + threadIdx.x] = threadIdx.x ? nC : nF;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(buf + byteOff[i]);
+    uint32_t* df = reinterpret_cast<uint32_t*>(features + (size_t)chunk * kMaxOwnFeatures);
+    uint32_t* dc = reinterpret_cast<uint32_t*>(caveFeatures + (size_t)chunk * kMaxOwnCaveFeatures);
+    const int wF = nF * (int)(sizeof(FeaturePlacement) / 4), wC = nC * (int)(sizeof(CaveFeaturePlacement) / 4);
+    for (int t = threadIdx.x; t < wF; t += 256) df[t] = src[t];
+    for (int t = threadIdx.x; t < wC; t += 256) dc[t] = src[wF + t];
+}
+
+// Cost features of a chunk from its stage-1 output, for cutting balanced tiles before anything expensive has run:
+// out[chunk] = {sum over columns of max(floor(h), 128)  (voxels the cave stage evaluates, chunk.cu:761-764),
+//               sum of clamp(floor(h), 1, 383)          (voxels the fill stage looks up a cave biome for),
+//               sum of (1 - ocean/beach weight)         (land columns: where surface features grow)}
+__global__ void __launch_bounds__(256) k_chunk_cost(const float* __restrict__ heightfield, const float* __restrict__ biomeWeights, float* __restrict__ out)
+{
+    __shared__ float sh[3][8];
+    const int chunk = blockIdx.x, idx = threadIdx.x;
+    const int hi = (int)floorf(heightfield[(size_t)chunk * 256 + idx]);
+    float v[3] = {(float)max(hi, SEA_LEVEL), (float)min(max(hi, 1), 383), 1.f};
+    for (int b = 0; b < NUM_OCEAN_BEACH_BIOMES; ++b) v[2] -= biomeWeights[(size_t)chunk * (NUM_BIOMES * 256) + b * 256 + idx];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], d);
+        if ((idx & 31) == 0) sh[k][idx >> 5] = v[k];
+    }
+    __syncthreads();
+    if (idx < 3)
+    {
+        float s = 0.f;
+        for (int wq = 0; wq < 8; ++wq) s += sh[idx][wq];
+        out[3 * chunk + idx] = s;
+    }
+}
+
 // 64-bit FNV-1a of each filled column (384 bytes), for cheap equality checks of large worlds
 __global__ void k_column_hashes(const int* __restrict__ fillList, int n, const uint8_t* __restrict__ blocks, unsigned long long* __restrict__ out)
 {

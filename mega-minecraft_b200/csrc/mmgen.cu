@@ -173,6 +173,21 @@ struct MmgenWorld
     {
         return !hasTarget || (x >= tx0 - grow && x < tx0 + tnx + grow && z >= tz0 - grow && z < tz0 + tnz + grow);
     }
+    // halo exchange (mmgen_world_set_exchange_region): chunks of the global region [gx0, gx0+gnx) x [gz0, gz0+gnz) (window-local)
+    // outside the own target tile belong to another world, which computes their placements and sends them
+    bool hasGlobal = false;
+    int gx0 = 0, gz0 = 0, gnx = 0, gnz = 0;
+    // does THIS world have to compute the placements (S4 + S5a) of window chunk (x, z)?
+    bool ownsPlacements(int x, int z) const
+    {
+        if (!inTarget(x, z, 3)) return false;
+        if (!hasGlobal || inTarget(x, z, 0)) return true;
+        return !(x >= gx0 && x < gx0 + gnx && z >= gz0 && z < gz0 + gnz);
+    }
+    // scratch of the exchange: chunk indices and byte offsets of one message
+    int* d_xIdx = nullptr;
+    long long* d_xOff = nullptr;
+    size_t xCap = 0;
 };
 
 extern "C" {
@@ -610,6 +625,8 @@ int mmgen_world_destroy(MmgenWorld* w)
     cudaFree(w->d_lushCount);
     cudaFree(w->d_rockQueue);
     cudaFree(w->d_blocks);
+    cudaFree(w->d_xIdx);
+    cudaFree(w->d_xOff);
     cudaFree(w->d_meshList);
     cudaFree(w->d_meshColOff);
     cudaFree(w->d_meshTotals);
@@ -833,6 +850,14 @@ static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
                 // with a target region only zones that meet target (+) 3 chunks are eroded
                 if (w->hasTarget && (lx0 + 18 <= w->tx0 - 3 || lx0 + 6 >= w->tx0 + w->tnx + 3 ||
                                      lz0 + 18 <= w->tz0 - 3 || lz0 + 6 >= w->tz0 + w->tnz + 3)) continue;
+                if (w->hasGlobal)
+                {
+                    // halo exchange: only zones holding a chunk whose placements this world computes itself
+                    bool any = false;
+                    for (int z = 6; z < 18 && !any; ++z)
+                        for (int x = 6; x < 18 && !any; ++x) any = w->ownsPlacements(lx0 + x, lz0 + z);
+                    if (!any) continue;
+                }
                 // a zone is eroded once: its 144 centre chunks move from stage 2 to 3 together (later stages are never demoted)
                 if (w->stage[(lz0 + 6) * nx + lx0 + 6] >= 3) continue;
                 bool ok = true;
@@ -847,7 +872,7 @@ static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
     {
         std::vector<int> list;
         for (int i = 0; i < w->n; ++i)
-            if (w->stage[i] == 3 && w->inTarget(i % nx, i / nx, 3)) list.push_back(i);
+            if (w->stage[i] == 3 && w->ownsPlacements(i % nx, i / nx)) list.push_back(i);
         MMG_CUDA(cudaEventRecord(w->ev[6], w->stream));
         if (worldCaves(w, list)) return 1;
         MMG_CUDA(cudaEventRecord(w->ev[7], w->stream));
@@ -939,6 +964,128 @@ int mmgen_world_create_for_region(int rx0, int rz0, int rnx, int rnz, MmgenWorld
     MmgenWorld* w = *out;
     w->hasTarget = true;
     w->tx0 = rx0 - w->cx0; w->tz0 = rz0 - w->cz0; w->tnx = rnx; w->tnz = rnz;
+    return 0;
+}
+
+int mmgen_world_set_exchange_region(MmgenWorld* w, int gx0, int gz0, int gnx, int gnz)
+{
+    if (gnx <= 0 || gnz <= 0) { w->hasGlobal = false; return 0; }
+    if (!w->hasTarget) { g_lastError = "mmgen_world_set_exchange_region: the world has no target region (mmgen_world_create_for_region)"; return 1; }
+    w->hasGlobal = true;
+    w->gx0 = gx0 - w->cx0; w->gz0 = gz0 - w->cz0; w->gnx = gnx; w->gnz = gnz;
+    return 0;
+}
+
+// chunk indices (window raster) of a world-coordinate rectangle, validated; grows the exchange scratch
+static int exchangeRect(MmgenWorld* w, int cx0, int cz0, int nx, int nz, std::vector<int>& idx, const char* who)
+{
+    const int lx0 = cx0 - w->cx0, lz0 = cz0 - w->cz0;
+    if (nx <= 0 || nz <= 0 || lx0 < 0 || lz0 < 0 || lx0 + nx > w->nx || lz0 + nz > w->nz)
+    {
+        g_lastError = std::string(who) + ": rectangle outside the world's window";
+        return 1;
+    }
+    idx.resize((size_t)nx * nz);
+    for (int z = 0; z < nz; ++z)
+        for (int x = 0; x < nx; ++x) idx[(size_t)z * nx + x] = (lz0 + z) * w->nx + lx0 + x;
+    if (idx.size() > w->xCap)
+    {
+        cudaFree(w->d_xIdx); cudaFree(w->d_xOff);
+        w->d_xIdx = nullptr; w->d_xOff = nullptr; w->xCap = 0;
+        MMG_CUDA(cudaMalloc(&w->d_xIdx, idx.size() * sizeof(int)));
+        MMG_CUDA(cudaMalloc(&w->d_xOff, idx.size() * sizeof(long long)));
+        w->xCap = idx.size();
+    }
+    return 0;
+}
+
+int mmgen_world_pack_placements(MmgenWorld* w, int cx0, int cz0, int nx, int nz, void* d_buf, size_t capBytes, size_t* bytes)
+{
+    if (requireReady()) return 1;
+    std::vector<int> idx;
+    if (exchangeRect(w, cx0, cz0, nx, nz, idx, "mmgen_world_pack_placements")) return 1;
+    const int n = (int)idx.size();
+    for (int i : idx)
+        if (w->stage[i] < 5) { g_lastError = "mmgen_world_pack_placements: a chunk of the rectangle has no placements yet"; return 1; }
+    // the counts of the rectangle's rows are contiguous in the world's count plane
+    std::vector<int> cnt((size_t)n * 2);
+    MMG_CUDA(cudaMemcpy2DAsync(cnt.data(), (size_t)nx * 2 * sizeof(int), w->d_counts + (size_t)idx[0] * 2, (size_t)w->nx * 2 * sizeof(int),
+                               (size_t)nx * 2 * sizeof(int), nz, cudaMemcpyDeviceToHost, w->stream));
+    MMG_CUDA(cudaStreamSynchronize(w->stream));
+    std::vector<long long> off(n);
+    long long at = (long long)n * 2 * sizeof(int);
+    for (int i = 0; i < n; ++i)
+    {
+        off[i] = at;
+        at += (long long)cnt[2 * i] * sizeof(FeaturePlacement) + (long long)cnt[2 * i + 1] * sizeof(CaveFeaturePlacement);
+    }
+    if (bytes) *bytes = (size_t)at;
+    if ((size_t)at > capBytes || !d_buf)
+    {
+        g_lastError = "mmgen_world_pack_placements: the message needs " + std::to_string(at) + " bytes, the buffer holds " + std::to_string(capBytes);
+        return 2;
+    }
+    MMG_CUDA(cudaMemcpyAsync(w->d_xIdx, idx.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, w->stream));
+    MMG_CUDA(cudaMemcpyAsync(w->d_xOff, off.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, w->stream));
+    MMG_LAUNCH(k_pack_placements, n, 256, 0, w->stream, (const int*)w->d_xIdx, (const long long*)w->d_xOff, (const FeaturePlacement*)w->d_features,
+               (const CaveFeaturePlacement*)w->d_caveFeatures, (const int*)w->d_counts, (uint8_t*)d_buf);
+    MMG_CUDA(cudaStreamSynchronize(w->stream));      // the caller hands d_buf to another stream (NCCL)
+    return 0;
+}
+
+int mmgen_world_unpack_placements(MmgenWorld* w, int cx0, int cz0, int nx, int nz, const void* d_buf, size_t bytes)
+{
+    if (requireReady()) return 1;
+    std::vector<int> idx;
+    if (exchangeRect(w, cx0, cz0, nx, nz, idx, "mmgen_world_unpack_placements")) return 1;
+    const int n = (int)idx.size();
+    if (bytes < (size_t)n * 2 * sizeof(int)) { g_lastError = "mmgen_world_unpack_placements: message shorter than its header"; return 1; }
+    if (!w->d_features) MMG_CUDA(cudaMalloc(&w->d_features, (size_t)w->n * kMaxOwnFeatures * sizeof(FeaturePlacement)));
+    if (!w->d_caveFeatures) MMG_CUDA(cudaMalloc(&w->d_caveFeatures, (size_t)w->n * kMaxOwnCaveFeatures * sizeof(CaveFeaturePlacement)));
+    if (!w->d_counts)
+    {
+        MMG_CUDA(cudaMalloc(&w->d_counts, (size_t)w->n * 2 * sizeof(int)));
+        MMG_CUDA(cudaMemsetAsync(w->d_counts, 0, (size_t)w->n * 2 * sizeof(int), w->stream));
+    }
+    std::vector<int> cnt((size_t)n * 2);
+    MMG_CUDA(cudaMemcpyAsync(cnt.data(), d_buf, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, w->stream));
+    MMG_CUDA(cudaStreamSynchronize(w->stream));
+    std::vector<long long> off(n);
+    long long at = (long long)n * 2 * sizeof(int);
+    for (int i = 0; i < n; ++i)
+    {
+        if (cnt[2 * i] < 0 || cnt[2 * i] > kMaxOwnFeatures || cnt[2 * i + 1] < 0 || cnt[2 * i + 1] > kMaxOwnCaveFeatures)
+        {
+            g_lastError = "mmgen_world_unpack_placements: corrupt header";
+            return 1;
+        }
+        off[i] = at;
+        at += (long long)cnt[2 * i] * sizeof(FeaturePlacement) + (long long)cnt[2 * i + 1] * sizeof(CaveFeaturePlacement);
+    }
+    if ((size_t)at != bytes) { g_lastError = "mmgen_world_unpack_placements: message length does not match its header"; return 1; }
+    MMG_CUDA(cudaMemcpyAsync(w->d_xIdx, idx.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, w->stream));
+    MMG_CUDA(cudaMemcpyAsync(w->d_xOff, off.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, w->stream));
+    MMG_LAUNCH(k_unpack_placements, n, 256, 0, w->stream, (const int*)w->d_xIdx, (const long long*)w->d_xOff, (const uint8_t*)d_buf, w->d_features,
+               w->d_caveFeatures, w->d_counts);
+    MMG_CUDA(cudaStreamSynchronize(w->stream));      // the scratch lists are reused by the next message
+    for (int i : idx) w->stage[i] = std::max<uint8_t>(w->stage[i], 5);
+    return 0;
+}
+
+int mmgen_chunk_costs(int n, const int32_t* origins, float* out_costs)
+{
+    if (requireReady()) return 1;
+    MMG_BATCH_LOCK();
+    if (n <= 0) return 0;
+    Scratch* S = g_scratch;
+    if (S[0].ensure((size_t)n * sizeof(int2)) || S[1].ensure((size_t)n * 256 * sizeof(float)) || S[2].ensure((size_t)n * NUM_BIOMES * 256 * sizeof(float)) ||
+        S[3].ensure((size_t)n * 3 * sizeof(float)))
+        return 1;
+    MMG_CUDA(cudaMemcpyAsync(S[0].ptr, origins, (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, g_stream));
+    MMG_LAUNCH(k_heightfield, n, 256, kNoiseSmemBytes, g_stream, (const int*)nullptr, (const int2*)S[0].ptr, (float*)S[1].ptr, (float*)S[2].ptr);
+    MMG_LAUNCH(k_chunk_cost, n, 256, 0, g_stream, (const float*)S[1].ptr, (const float*)S[2].ptr, (float*)S[3].ptr);
+    MMG_CUDA(cudaMemcpyAsync(out_costs, S[3].ptr, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, g_stream));
+    MMG_CUDA(cudaStreamSynchronize(g_stream));
     return 0;
 }
 

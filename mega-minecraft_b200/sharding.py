@@ -61,6 +61,109 @@ def gather_floats(value):
     return [float(o.item()) for o in out]
 
 
+def _grow(t, g):
+    return (t[0] - g, t[1] - g, t[2] + 2 * g, t[3] + 2 * g)
+
+
+def _intersect(a, b):
+    x0, z0 = max(a[0], b[0]), max(a[1], b[1])
+    x1, z1 = min(a[0] + a[2], b[0] + b[2]), min(a[1] + a[3], b[1] + b[3])
+    return (x0, z0, x1 - x0, z1 - z0) if x1 > x0 and z1 > z0 else None
+
+
+def exchange_plan(tiles, rank, halo=3):
+    """Halo exchange of placement lists (SURVEY.md 8(e) option B): [(peer, send_rect, recv_rect)] for `rank`. A rank fills
+    its tile from the placements of tile (+) 3 chunks (gather order chunk.cu:1158-1187); the part of that ring that lies in
+    a peer's tile is computed there and sent: send_rect = my tile n (peer tile (+) halo), recv_rect = peer tile n (my tile
+    (+) halo). Both are non-empty for the same peers, so every pair exchanges exactly one message each way."""
+    me = tiles[rank]
+    plan = []
+    for peer, t in enumerate(tiles):
+        if peer == rank:
+            continue
+        send, recv = _intersect(me, _grow(t, halo)), _intersect(t, _grow(me, halo))
+        assert (send is None) == (recv is None)
+        if send is not None:
+            plan.append((peer, send, recv))
+    return plan
+
+
+class HaloExchange:
+    """Moves the packed placement lists between the ranks' device-resident worlds with NCCL send / recv over NVLink (two
+    rounds: message lengths, then payloads), one device buffer pair per peer."""
+
+    def __init__(self, tiles, rank, bytes_per_chunk=48 * 1024):
+        self.plan = exchange_plan(tiles, rank)
+        dev = _dev()
+        self.send = {p: torch.empty(s[2] * s[3] * bytes_per_chunk, dtype=torch.uint8, device=dev) for p, s, _ in self.plan}
+        self.recv = {p: torch.empty(r[2] * r[3] * bytes_per_chunk, dtype=torch.uint8, device=dev) for p, _, r in self.plan}
+        self.slen = {p: torch.zeros(1, dtype=torch.int64, device=dev) for p, _, _ in self.plan}
+        self.rlen = {p: torch.zeros(1, dtype=torch.int64, device=dev) for p, _, _ in self.plan}
+        self.bytes_sent = 0
+
+    def run(self, world):
+        """world: the rank's World after stages 1-5 on its own tile. Returns the bytes this rank sent."""
+        if not self.plan:
+            return 0
+        sizes = {}
+        for peer, srect, _ in self.plan:
+            n, ok = world.pack_placements(srect, self.send[peer].data_ptr(), self.send[peer].numel())
+            if not ok:                                   # rare: a denser strip than the buffer was sized for
+                self.send[peer] = torch.empty(n + n // 4, dtype=torch.uint8, device=self.send[peer].device)
+                n, ok = world.pack_placements(srect, self.send[peer].data_ptr(), self.send[peer].numel())
+                assert ok
+            sizes[peer] = n
+            self.slen[peer].fill_(n)
+        ops = []
+        for peer, _, _ in self.plan:
+            ops.append(dist.P2POp(dist.isend, self.slen[peer], peer))
+            ops.append(dist.P2POp(dist.irecv, self.rlen[peer], peer))
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        rsizes = {peer: int(self.rlen[peer].item()) for peer, _, _ in self.plan}
+        for peer, n in rsizes.items():
+            if n > self.recv[peer].numel():
+                self.recv[peer] = torch.empty(n + n // 4, dtype=torch.uint8, device=self.recv[peer].device)
+        ops = []
+        for peer, _, _ in self.plan:
+            ops.append(dist.P2POp(dist.isend, self.send[peer][:sizes[peer]], peer))
+            ops.append(dist.P2POp(dist.irecv, self.recv[peer][:rsizes[peer]], peer))
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        torch.cuda.synchronize()
+        for peer, _, rrect in self.plan:
+            world.unpack_placements(rrect, self.recv[peer].data_ptr(), rsizes[peer])
+        self.bytes_sent = sum(sizes.values())
+        return self.bytes_sent
+
+
+# Relative cost of a chunk from its stage-1 features (ChunkGen.chunk_costs: cave voxels, fill voxels, land columns), fitted to
+# measured per-tile device times of the 256x256 bench world on a B200 (tools/fit_cost_model.py; only ratios matter)
+# (25 tiles of three tilings, 62-109 ms each: 1.2 % rms, 2.9 % worst-case error; by area alone 13.5 % / 22.6 %; profiles/r02_cost_model.txt)
+COST_WEIGHTS = (7.0e-5, 1.126e-3, 2.89e-3, 4.91e-3)      # ms: x cave voxels / 1e4, x fill voxels / 1e4, x land columns / 256, per chunk
+
+
+def chunk_cost_map(gen, region, rank=0, world_size=1, weights=COST_WEIGHTS):
+    """(rnz, rnx) predicted cost per chunk of `region`, from stage 1 alone: every rank evaluates the features of a strip of
+    rows (mmgen_chunk_costs), the strips are all-gathered, every rank ends up with the same map."""
+    rx0, rz0, rnx, rnz = region
+    rows = tiling.split_points(rz0, rnz, world_size) if rnz >= world_size else [rz0] + [rz0 + rnz] * world_size
+    z0, z1 = rows[rank], rows[rank + 1]
+    zz, xx = np.meshgrid(np.arange(z0, z1, dtype=np.int32), np.arange(rx0, rx0 + rnx, dtype=np.int32), indexing="ij")
+    origins = np.ascontiguousarray(np.stack([xx.ravel() * 16, zz.ravel() * 16], axis=1), np.int32)
+    f = gen.chunk_costs(origins).reshape(z1 - z0, rnx, 3) if len(origins) else np.zeros((0, rnx, 3), np.float32)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        most = max(b - a for a, b in zip(rows, rows[1:]))
+        t = torch.zeros((most, rnx, 3), dtype=torch.float32)
+        t[:z1 - z0] = torch.from_numpy(f)
+        t = t.to(_dev(), non_blocking=True)
+        out = torch.empty((world_size * most, rnx, 3), dtype=torch.float32, device=t.device)
+        dist.all_gather_into_tensor(out, t)          # one collective, one read-back
+        out = out.cpu().numpy().reshape(world_size, most, rnx, 3)
+        f = np.concatenate([out[r, :b - a] for r, (a, b) in enumerate(zip(rows, rows[1:]))], axis=0)
+    return weights[0] * f[:, :, 0] / 1e4 + weights[1] * f[:, :, 1] / 1e4 + weights[2] * f[:, :, 2] / 256.0 + weights[3]
+
+
 class Balancer:
     """Feedback load balancing of the tiling.
 
@@ -100,6 +203,16 @@ class Balancer:
             cuts.append(c)
         cuts.append(len(cost))
         return [start + c for c in cuts]
+
+    def cut_by_cost(self, cost):
+        """cost: (rnz, rnx) predicted cost per chunk (chunk_cost_map). Moves the cuts so that every tile carries the same
+        predicted cost - rows first, then the cuts inside every row - without any rehearsal pass."""
+        rx0, rz0, rnx, rnz = self.region
+        cost = np.asarray(cost, np.float64)
+        assert cost.shape == (rnz, rnx)
+        self.zs = self._cuts(cost.sum(axis=1), self.gz, rz0)
+        self.xs = [self._cuts(cost[self.zs[j] - rz0:self.zs[j + 1] - rz0].sum(axis=0), self.gx, rx0) for j in range(self.gz)]
+        return self.tiles()
 
     def update(self, times):
         """times: per-rank cost of the current tiles (rank order). Moves the cuts; returns the predicted imbalance before the move."""

@@ -88,8 +88,18 @@ def _worker(rank, world_size, port, region, out):
     checks = sharding.gather_u64(check)
     slowest = sharding.reduce_scalar(10.0 + rank, "max")
     chunks = sharding.reduce_scalar(tile[2] * tile[3], "sum")
+
+    class FakeGen:      # stage-1 cost features as a function of the chunk origin: the strips must reassemble to the one-rank map
+        def chunk_costs(self, origins):
+            o = origins.astype(np.float32)
+            return np.stack([o[:, 0] + 1000.0, o[:, 1] * 2.0, o[:, 0] - o[:, 1]], axis=1).astype(np.float32)
+
+    cost = sharding.chunk_cost_map(FakeGen(), region, rank, world_size, weights=(1.0, 2.0, 3.0, 0.5))
+    tiles = sharding.Balancer(region, world_size).cut_by_cost(np.abs(cost) + 1.0)
     if rank == 0:
-        out.put((checks, slowest, chunks))
+        out.put((checks, slowest, chunks, cost, tiles))
+    else:
+        out.put(tiles)
     dist.destroy_process_group()
 
 
@@ -105,8 +115,18 @@ def test_two_rank_reductions_over_gloo(pkg):
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
-    checks, slowest, chunks = q.get()
+    got = [q.get(), q.get()]
+    (checks, slowest, chunks, cost, tiles0), tiles1 = (got[0], got[1]) if len(got[0]) == 5 else (got[1], got[0])
     assert slowest == 11.0 and chunks == region[2] * region[3]
+
+    class FakeGen:
+        def chunk_costs(self, origins):
+            o = origins.astype(np.float32)
+            return np.stack([o[:, 0] + 1000.0, o[:, 1] * 2.0, o[:, 0] - o[:, 1]], axis=1).astype(np.float32)
+
+    single = sharding.chunk_cost_map(FakeGen(), region, 0, 1, weights=(1.0, 2.0, 3.0, 0.5))
+    assert cost.shape == (region[3], region[2]) and np.array_equal(cost, single)      # the all-gathered strips = the one-rank map
+    assert tiles0 == tiles1                                                            # every rank derives the same cuts
     expect = []
     for t in tiling.tiles(*region, 2):
         xs, zs = np.meshgrid(np.arange(t[0], t[0] + t[2]), np.arange(t[1], t[1] + t[3]))
