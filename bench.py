@@ -454,16 +454,21 @@ def run_own(args):
             t0 = time.perf_counter()
             exchange.run(world)
             x = 1e3 * (time.perf_counter() - t0)
-            if to_host:
-                world.generate_to_host(host.data_ptr(), mm.STAGE_FILL)
-            else:
-                world.generate(mm.STAGE_FILL)
+            deliver(mm.STAGE_FILL, to_host)
             return ms + x + world.total_ms(), x
-        if to_host:
-            world.generate_to_host(host.data_ptr(), mm.STAGE_ALL)
-        else:
-            world.generate(mm.STAGE_ALL)
+        deliver(mm.STAGE_ALL, to_host)
         return ms + world.total_ms(), 0.0
+
+    enc_index = torch.empty(n_target * 2, dtype=torch.int64, pin_memory=True)
+    enc_bytes = [0]
+
+    def deliver(mask, to_host):
+        if to_host == "encoded":      # run-length coded on the device (format MMCH1), payload + index into pinned host memory
+            enc_bytes[0] = world.generate_to_host_encoded(host.data_ptr(), host.numel(), enc_index.numpy().view(np.uint64).reshape(-1, 2), mask)
+        elif to_host:
+            world.generate_to_host(host.data_ptr(), mask)
+        else:
+            world.generate(mask)
 
     step.predict_ms = 0.0
 
@@ -547,9 +552,27 @@ def run_own(args):
     e2e_wall = max_over_ranks(time.perf_counter() - t0)
     e2e_dev = max_over_ranks(e2e_ms / 1e3)
     e2e_value = total_chunks * args.steps / max(e2e_wall, e2e_dev)
+    host_sum = int(host.view(torch.int64).sum().item()) if rank == 0 else 0
+
+    # ---- the same with the block volumes delivered in the library's wire format (MMCH1 run-length code, decoded on the host by
+    # mmgen_decode_chunk): an extra figure, not the headline e2e - the reference's contract is the raw volume
+    step(variant, to_host="encoded")
+    barrier()
+    t0 = time.perf_counter()
+    enc_ms = 0.0
+    for _ in range(args.steps):
+        enc_ms += step(variant, to_host="encoded")[0]
+    barrier()
+    enc_wall = max_over_ranks(time.perf_counter() - t0)
+    enc_dev = max_over_ranks(enc_ms / 1e3)
+    enc_value = total_chunks * args.steps / max(enc_wall, enc_dev)
+    enc_total = sum_over_ranks(enc_bytes[0])
+    if rank == 0:      # spot check: a delivered chunk decodes to a plausible volume (bedrock at y = 0)
+        idx = enc_index.numpy().view(np.uint64).reshape(-1, 2)
+        blk = mm.decode_chunk(host.numpy()[int(idx[0, 0]):int(idx[0, 0] + idx[0, 1])])
+        assert blk.shape == (16, 16, 384) and len(np.unique(blk[:, :, 0])) == 1
     h2d = sum_over_ranks(world.n * 8)
     d2h = sum_over_ranks(n_target * 98304)
-    host_sum = int(host.view(torch.int64).sum().item()) if rank == 0 else 0
 
     # ---- roofline of the dominant kernel (algorithmic FLOPs from the heightfield)
     stage_ms /= args.steps
@@ -635,6 +658,10 @@ def run_own(args):
                    "l2": "working set per step (>= %.1f GB written) far exceeds the 126 MB L2; no flush needed" % (n_target * 98304 / 1e9)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * max(e2e_wall, e2e_dev) / args.steps, "host_checksum": host_sum},
+        "e2e_encoded": {"value": enc_value, "unit": UNIT, "d2h_bytes_per_step": int(enc_total), "compression": d2h / max(enc_total, 1),
+                        "ms_per_step": 1e3 * max(enc_wall, enc_dev) / args.steps,
+                        "note": "block volumes run-length coded on the device (wire format MMCH1, include/mmgen.h) and delivered as payload + index; "
+                                "decoded on the host by mmgen_decode_chunk"},
         "gpu_launches": int(sum_over_ranks(launches)), "rank_ms": [round(t, 2) for t in rank_ms], "balance_passes": balance_log,
         "roofline": roof, "kernels": kernels, "stages": stages, "clocks": clocks, "block_checksums": [("%016x" % c) for c in checks], "world_hash": "%016x" % (sum(sharding.gather_u64(hash_sum)) & 0xFFFFFFFFFFFFFFFF),
     }

@@ -170,6 +170,24 @@ int mmgen_world_generate(MmgenWorld* w, int stageMask);
  * uint8[rnz][rnx][98304] in region raster order (window raster order without a target region), ideally
  * page-locked; filled batches are copied while later batches are still being filled. */
 int mmgen_world_generate_to_host(MmgenWorld* w, int stageMask, uint8_t* out_blocks);
+/* ---- chunk wire / on-disk format MMCH1 (the reference ships raw volumes and has no file format):
+ *   encoded chunk := uint16 nRuns[256] (column order x + 16 z, little endian), then for each column nRuns x {uint8 block,
+ *   uint8 length} with length 1..255 and a column's lengths adding up to 384, zero-padded to a multiple of 16 bytes; a chunk
+ *   whose code would reach 98 304 bytes is stored raw and recognised by that length.
+ * mmgen_world_generate_to_host_encoded: like mmgen_world_generate_to_host, but the block volumes are run-length coded on the
+ * device and delivered as one payload in out_buf (ideally page-locked) plus out_index[rnz * rnx][2] = {offset, bytes} of every
+ * chunk of the region in raster order; *out_bytes = payload length. Return code 2 (and *out_bytes = the size needed) when
+ * capBytes is too small. mmgen_decode_chunk (host) restores uint8[16][16][384] from one encoded chunk. */
+int mmgen_world_generate_to_host_encoded(MmgenWorld* w, int stageMask, uint8_t* out_buf, size_t capBytes, uint64_t* out_index,
+                                         size_t* out_bytes);
+int mmgen_decode_chunk(const uint8_t* enc, size_t nbytes, uint8_t* out_blocks);
+/* region files: header "MMRG", version, region rectangle, the index, then the payload - exactly what
+ * mmgen_world_generate_to_host_encoded delivered. read_chunk decodes one chunk (cx, cz in chunk coordinates). */
+typedef struct MmgenRegionFile MmgenRegionFile;
+int mmgen_region_save(const char* path, int rx0, int rz0, int rnx, int rnz, const uint64_t* index, const uint8_t* payload, size_t payloadBytes);
+int mmgen_region_open(const char* path, MmgenRegionFile** out, int32_t* out_rect4);
+int mmgen_region_read_chunk(MmgenRegionFile* r, int cx, int cz, uint8_t* out_blocks);
+int mmgen_region_close(MmgenRegionFile* r);
 /* blocks until all queued work of the world is done */
 int mmgen_world_sync(MmgenWorld* w);
 /* furthest completed stage per chunk (0..6), raster order i = (cz-cz0)*nx + (cx-cx0) */

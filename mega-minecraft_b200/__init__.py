@@ -4,6 +4,6 @@ The directory name is not a Python identifier; load it with `mmgen_loader.load()
 (tests, bench.py and __graft_entry__.py do) - it registers this package as `mega_minecraft_b200`.
 """
 from .chunkgen import (  # noqa: F401
-    ChunkGen, World, Terrain, TickStats, Vertex, REFERENCE_COSTS, MmgenError, lib_path, build, CaveLayer, FeaturePlacement, CaveFeaturePlacement,
+    ChunkGen, World, Terrain, TickStats, Vertex, RegionFile, decode_chunk, save_region, REFERENCE_COSTS, MmgenError, lib_path, build, CaveLayer, FeaturePlacement, CaveFeaturePlacement,
     STAGE_HEIGHTFIELD, STAGE_LAYERS, STAGE_EROSION, STAGE_CAVES, STAGE_FEATURES, STAGE_FILL, STAGE_ALL,
 )

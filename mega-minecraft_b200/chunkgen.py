@@ -284,6 +284,16 @@ class World:
         (uint8[rnz][rnx][98304]; pinned memory makes the copy overlap the fill)."""
         self.gen._check(self.L.mmgen_world_generate_to_host(self.h, int(stage_mask), ctypes.c_void_p(int(out_blocks_ptr))))
 
+    def generate_to_host_encoded(self, out_ptr, cap_bytes, index, stage_mask=STAGE_ALL):
+        """Generate and deliver the region's block volumes run-length coded (format MMCH1, include/mmgen.h) into host memory
+        at out_ptr; index: uint64 array (rnz * rnx, 2) that receives {offset, bytes} per chunk. Returns the payload length;
+        raises MmgenError when cap_bytes is too small (the message names the size needed)."""
+        n = ctypes.c_size_t(0)
+        assert index.dtype == np.uint64 and index.size >= 2 * self.rnx * self.rnz
+        self.gen._check(self.L.mmgen_world_generate_to_host_encoded(self.h, int(stage_mask), ctypes.c_void_p(int(out_ptr)), ctypes.c_size_t(int(cap_bytes)),
+                                                                    _ptr(index), ctypes.byref(n)))
+        return n.value
+
     def total_ms(self):
         v = ctypes.c_float(0)
         self.gen._check(self.L.mmgen_world_total_ms(self.h, ctypes.byref(v)))
@@ -351,6 +361,55 @@ class World:
             if v is not None:
                 res[k] = v
         return res
+
+
+def _codec_lib():
+    L = ChunkGen.lib()
+    L.mmgen_last_error.restype = ctypes.c_char_p
+    return L
+
+
+def decode_chunk(enc):
+    """One MMCH1-encoded chunk (bytes / uint8 array) -> uint8[16][16][384] (mmgen_decode_chunk, host code, needs no GPU)."""
+    enc = np.ascontiguousarray(np.frombuffer(enc, np.uint8) if isinstance(enc, (bytes, bytearray, memoryview)) else enc, np.uint8)
+    out = np.empty((16, 16, 384), np.uint8)
+    L = _codec_lib()
+    if L.mmgen_decode_chunk(_ptr(enc), ctypes.c_size_t(enc.size), _ptr(out)) != 0:
+        raise MmgenError(L.mmgen_last_error().decode())
+    return out
+
+
+def save_region(path, region, index, payload):
+    """Writes a region file (header, index, MMCH1 payload) from what World.generate_to_host_encoded delivered."""
+    L = _codec_lib()
+    index = np.ascontiguousarray(index, np.uint64)
+    payload = np.ascontiguousarray(payload, np.uint8)
+    if L.mmgen_region_save(str(path).encode(), int(region[0]), int(region[1]), int(region[2]), int(region[3]), _ptr(index), _ptr(payload),
+                           ctypes.c_size_t(payload.size)) != 0:
+        raise MmgenError(L.mmgen_last_error().decode())
+
+
+class RegionFile:
+    """Random access to the chunks of a region file (mmgen_region_open / read_chunk / close)."""
+
+    def __init__(self, path):
+        self.L = _codec_lib()
+        self.h = ctypes.c_void_p()
+        rect = (ctypes.c_int32 * 4)()
+        if self.L.mmgen_region_open(str(path).encode(), ctypes.byref(self.h), rect) != 0:
+            raise MmgenError(self.L.mmgen_last_error().decode())
+        self.region = tuple(rect)
+
+    def read_chunk(self, cx, cz):
+        out = np.empty((16, 16, 384), np.uint8)
+        if self.L.mmgen_region_read_chunk(self.h, int(cx), int(cz), _ptr(out)) != 0:
+            raise MmgenError(self.L.mmgen_last_error().decode())
+        return out
+
+    def close(self):
+        if self.h:
+            self.L.mmgen_region_close(self.h)
+            self.h = ctypes.c_void_p()
 
 
 class TickStats(ctypes.Structure):

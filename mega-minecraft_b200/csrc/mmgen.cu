@@ -16,6 +16,7 @@
 #include "mm_stage4.cuh"
 #include "mm_stage56.cuh"
 #include "mm_mesh.cuh"
+#include "mm_codec.cuh"
 
 namespace mmg {
 
@@ -119,8 +120,13 @@ __global__ void __launch_bounds__(256) k_fp32_peak(float* out, int iters)
 
 using namespace mmg;
 
+struct CodecState;
+static void codecFree(CodecState* c);
+struct EncodedOut { uint8_t* buf; size_t cap; uint64_t* index; size_t bytes; };      // mmgen_world_generate_to_host_encoded
+
 struct MmgenWorld
 {
+    CodecState* codec = nullptr;         // encoder scratch + arena (mm_codec.inl), created on first use
     int cx0 = 0, cz0 = 0, nx = 0, nz = 0, n = 0;
     int2* d_origins = nullptr;
     std::vector<int2> h_origins;
@@ -625,6 +631,7 @@ int mmgen_world_destroy(MmgenWorld* w)
     cudaFree(w->d_lushCount);
     cudaFree(w->d_rockQueue);
     cudaFree(w->d_blocks);
+    codecFree(w->codec);
     cudaFree(w->d_xIdx);
     cudaFree(w->d_xOff);
     cudaFree(w->d_meshList);
@@ -761,10 +768,23 @@ static int worldPlacements(MmgenWorld* w, const std::vector<int>& list)
 // S5b + S6 (gatherFeaturePlacements + Chunk::fill + placeDecorators): every listed chunk has its 7x7 neighbourhood at
 // stage >= 5. hostBlocks != nullptr: each finished batch is copied to host memory while the next one is being filled,
 // chunk i of the list to slot hostSlot(i).
+static int codecEnsure(MmgenWorld* w, size_t targets, size_t batches);
+static int codecEncodeBatch(MmgenWorld* w, int b, int m, const int* dl, const int* h_slots);
+static int codecDeliver(MmgenWorld* w, int batches, size_t targets, EncodedOut* enc);
+
 template <typename SlotFn>
-static int worldFill(MmgenWorld* w, const std::vector<int>& list, uint8_t* hostBlocks, SlotFn hostSlot)
+static int worldFill(MmgenWorld* w, const std::vector<int>& list, uint8_t* hostBlocks, SlotFn hostSlot, EncodedOut* enc = nullptr)
 {
     if (list.empty()) return 0;
+    const int nBatches = (int)((list.size() + kFillBatch - 1) / kFillBatch);
+    std::vector<int> slots;
+    if (enc)
+    {
+        size_t targets = 0;
+        for (int c : list) targets = std::max(targets, hostSlot(c) + 1);
+        if (codecEnsure(w, targets, (size_t)nBatches)) return 1;
+        enc->bytes = targets;      // number of index entries, replaced by the byte count in codecDeliver
+    }
     const int nx = w->nx;
     if (!w->d_blocks) MMG_CUDA(cudaMalloc(&w->d_blocks, (size_t)w->n * 98304));
     if (!w->d_gF) MMG_CUDA(cudaMalloc(&w->d_gF, (size_t)kFillBatch * MAX_FEATURES * sizeof(FeaturePlacement)));
@@ -788,7 +808,13 @@ static int worldFill(MmgenWorld* w, const std::vector<int>& list, uint8_t* hostB
                        w->d_info, w->d_prepF, w->d_prepC, MAX_FEATURES, MAX_CAVE_FEATURES, w->d_blocks, w->d_rockQueue, w->d_lushQueue,
                        w->d_lushCount, w->stream))
             return 1;
-        if (hostBlocks)
+        if (enc)
+        {
+            slots.resize(m);
+            for (int i = 0; i < m; ++i) slots[i] = (int)hostSlot(list[b0 + i]);
+            if (codecEncodeBatch(w, (int)(b0 / kFillBatch), m, dl, slots.data())) return 1;
+        }
+        else if (hostBlocks)
         {
             // stream the finished batch to the host while the next batch is being filled:
             // one copy per run of consecutive chunks whose host slots are consecutive too
@@ -806,17 +832,18 @@ static int worldFill(MmgenWorld* w, const std::vector<int>& list, uint8_t* hostB
             }
         }
     }
+    if (enc && codecDeliver(w, nBatches, enc->bytes, enc)) return 1;
     MMG_CUDA(cudaStreamSynchronize(w->stream));
     for (int i : list) w->stage[i] = 6;
     return 0;
 }
 
-static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
+static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks, EncodedOut* enc = nullptr)
 {
     if (requireReady()) return 1;
     MMG_CUDA(cudaEventRecord(w->ev[12], w->stream));
     // host-delivery calls take their only input, the chunk origins, from host memory every time
-    if (hostBlocks) MMG_CUDA(cudaMemcpyAsync(w->d_origins, w->h_origins.data(), (size_t)w->n * sizeof(int2), cudaMemcpyHostToDevice, w->stream));
+    if (hostBlocks || enc) MMG_CUDA(cudaMemcpyAsync(w->d_origins, w->h_origins.data(), (size_t)w->n * sizeof(int2), cudaMemcpyHostToDevice, w->stream));
     const int nx = w->nx, nz = w->nz;
     if (stageMask & MMGEN_STAGE_HEIGHTFIELD)
     {
@@ -904,17 +931,17 @@ static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks)
         auto slot = [w, nx](int c) -> size_t {
             return w->hasTarget ? (size_t)(c / nx - w->tz0) * w->tnx + (c % nx - w->tx0) : (size_t)c;
         };
-        if (worldFill(w, list, hostBlocks, slot)) return 1;
+        if (worldFill(w, list, hostBlocks, slot, enc)) return 1;
         MMG_CUDA(cudaEventRecord(w->ev[11], w->stream));
     }
-    if (hostBlocks)
+    if (hostBlocks || enc)
     {
         // the whole-generate bracket includes the tail of the download
         MMG_CUDA(cudaEventRecord(w->evBatch[0], w->copyStream));
         MMG_CUDA(cudaStreamWaitEvent(w->stream, w->evBatch[0], 0));
     }
     MMG_CUDA(cudaEventRecord(w->ev[13], w->stream));
-    if (hostBlocks) MMG_CUDA(cudaStreamSynchronize(w->stream));
+    if (hostBlocks || enc) MMG_CUDA(cudaStreamSynchronize(w->stream));
     return 0;
 }
 
@@ -930,7 +957,22 @@ int mmgen_world_generate_to_host(MmgenWorld* w, int stageMask, uint8_t* out_bloc
     return worldGenerate(w, stageMask, out_blocks);
 }
 
+int mmgen_world_generate_to_host_encoded(MmgenWorld* w, int stageMask, uint8_t* out_buf, size_t capBytes, uint64_t* out_index, size_t* out_bytes)
+{
+    if (!out_buf || !out_index || !out_bytes)
+    {
+        g_lastError = "mmgen_world_generate_to_host_encoded: null output pointer";
+        return 1;
+    }
+    EncodedOut enc = {out_buf, capBytes, out_index, 0};
+    *out_bytes = 0;
+    const int rc = worldGenerate(w, stageMask, nullptr, &enc);
+    *out_bytes = enc.bytes;
+    return rc;
+}
+
 #include "mm_stream.inl"
+#include "mm_codec.inl"
 
 int mmgen_world_reset(MmgenWorld* w)
 {
