@@ -273,6 +273,20 @@ int mmgen_world_mesh(MmgenWorld* w, int n, const int32_t* chunkCoords, int32_t* 
 /* chunk i of the last mmgen_world_mesh call: copy to host memory, or the device addresses (zero-copy hand-off to a renderer) */
 int mmgen_world_mesh_download(MmgenWorld* w, int i, MmgenVertex* out_verts, uint32_t* out_idx);
 int mmgen_world_mesh_device_ptrs(MmgenWorld* w, int i, void** verts, void** idx, int* nVerts, int* nIdx);
+/* ---- hand-off to the path tracer: OptixRenderer::buildChunkAccel (optixRenderer.cpp:223-368) copies a chunk's host vertex /
+ * index vectors to the device (initFromVector, :229-230) and describes them as one OptixBuildInput triangle array. For the
+ * meshes of the last mmgen_world_mesh call the description can be filled from the device arena directly: one MmgenGasInput
+ * per chunk holds exactly the triangleArray fields buildChunkAccel sets (vertex format float3 at stride sizeof(Vertex) = 40,
+ * index format unsigned int3 at stride 12; integration/optix_handoff.cpp shows the binding and checks the layouts against
+ * rendering/structs.hpp:25-31). *n = chunks of the last mesh call (may exceed cap). */
+typedef struct {
+    uint64_t vertexBuffer;            /* CUdeviceptr: MmgenVertex[numVertices] */
+    uint32_t numVertices, vertexStrideInBytes;
+    uint64_t indexBuffer;             /* CUdeviceptr: uint32[numIndexTriplets][3], indices relative to this chunk's vertices */
+    uint32_t numIndexTriplets, indexStrideInBytes;
+    int32_t cx, cz;                   /* chunk coordinates */
+} MmgenGasInput;
+int mmgen_world_mesh_gas_inputs(MmgenWorld* w, int cap, MmgenGasInput* out, int* n);
 /* device time of the last mmgen_world_mesh call (both kernels + the count read-back), ms */
 int mmgen_world_mesh_ms(MmgenWorld* w, float* out);
 

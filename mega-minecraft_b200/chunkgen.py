@@ -533,5 +533,20 @@ def _world_mesh_ms(self):
     return v.value
 
 
+GasInput = np.dtype([("vertexBuffer", "<u8"), ("numVertices", "<u4"), ("vertexStrideInBytes", "<u4"), ("indexBuffer", "<u8"),
+                     ("numIndexTriplets", "<u4"), ("indexStrideInBytes", "<u4"), ("cx", "<i4"), ("cz", "<i4")])      # MmgenGasInput, 40 B
+
+
+def _world_mesh_gas_inputs(self):
+    """mmgen_world_mesh_gas_inputs: the OptiX triangle-array description (device pointers into the mesh arena) of every chunk
+    of the last mesh() call - what OptixRenderer::buildChunkAccel needs instead of host vectors."""
+    n = ctypes.c_int(0)
+    self.gen._check(self.L.mmgen_world_mesh_gas_inputs(self.h, 0, None, ctypes.byref(n)))
+    out = np.zeros(n.value, GasInput)
+    self.gen._check(self.L.mmgen_world_mesh_gas_inputs(self.h, n.value, _ptr(out), ctypes.byref(n)))
+    return out
+
+
+World.mesh_gas_inputs = _world_mesh_gas_inputs
 World.mesh = _world_mesh
 World.mesh_ms = _world_mesh_ms

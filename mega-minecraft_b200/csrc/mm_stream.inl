@@ -105,20 +105,46 @@ static void streamUpdateChunk(MmgenStream* s, int dx, int dz)
 // `i` that is in state `cur` and whose (2R+1)^2 neighbourhood is at `cur` or beyond moves to `next`
 static void streamGather(MmgenStream* s, int i, int R, uint8_t cur, uint8_t next)
 {
+    // floodFill (chunk.cu:53-91): breadth-first from chunk i over the four edge neighbours, inside the (4R+1)^2 window around it,
+    // through chunks at state `cur` or beyond only - a chunk behind a less advanced one is not found
     const int nx = s->w->nx, nz = s->w->nz;
-    const int x0 = i % nx, z0 = i / nx;
+    const int x0 = i % nx, z0 = i / nx, radius = 2 * R, D = 4 * R + 1;
+    // (the reference marks a chunk visited when it is popped, so its queue holds duplicates; marking at push time reaches the
+    // same set with every chunk queued once)
+    uint8_t found[13 * 13] = {}, queued[13 * 13] = {};      // R <= 3
+    int queue[13 * 13], head = 0, tail = 0;
+    auto slot = [&](int x, int z) { return (z - z0 + radius) * D + (x - x0 + radius); };
+    queue[tail++] = i;
+    queued[slot(x0, z0)] = 1;
+    while (head < tail)
+    {
+        const int p = queue[head++];
+        const int px = p % nx, pz = p / nx;
+        if (s->state[p] < cur) continue;
+        found[slot(px, pz)] = 1;
+        const int nb[4][2] = {{px, pz + 1}, {px + 1, pz}, {px, pz - 1}, {px - 1, pz}};
+        for (const auto& n : nb)
+        {
+            if (n[0] < 0 || n[1] < 0 || n[0] >= nx || n[1] >= nz) continue;
+            const int k = n[1] * nx + n[0];
+            if (!s->exists[k] || abs(n[0] - x0) > radius || abs(n[1] - z0) > radius || queued[slot(n[0], n[1])]) continue;
+            queued[slot(n[0], n[1])] = 1;
+            queue[tail++] = k;
+        }
+    }
+    // iterateNeighborChunks (chunk.cu:93-136): centres within R that are at `cur` and whose (2R+1)^2 neighbourhood was found
     for (int cz = z0 - R; cz <= z0 + R; ++cz)
         for (int cx = x0 - R; cx <= x0 + R; ++cx)
         {
-            if (cx < R || cz < R || cx >= nx - R || cz >= nz - R) continue;
+            if (cx < 0 || cz < 0 || cx >= nx || cz >= nz || !found[slot(cx, cz)]) continue;
             const int c = cz * nx + cx;
-            if (!s->exists[c] || s->state[c] != cur) continue;
+            if (s->state[c] != cur) continue;
             bool ok = true;
             for (int oz = -R; oz <= R && ok; ++oz)
                 for (int ox = -R; ox <= R && ok; ++ox)
                 {
-                    const int k = (cz + oz) * nx + cx + ox;
-                    ok = s->exists[k] && s->state[k] >= cur;
+                    const int ax = cx + ox, az = cz + oz;
+                    ok = ax >= 0 && az >= 0 && ax < nx && az < nz && found[slot(ax, az)];
                 }
             if (ok) s->setState(c, next);
         }
@@ -131,8 +157,14 @@ static void streamAddZonesToTry(MmgenStream* s, int i)
     const int nx = s->w->nx;
     const int cx = s->w->cx0 + i % nx, cz = s->w->cz0 + i / nx;
     const int zx = floorDiv12(cx), zz = floorDiv12(cz);
-    const int sx = (cx - zx * 12) < 6 ? -1 : 1, sz = (cz - zz * 12) < 6 ? -1 : 1;
-    const int cand[4][2] = {{zx, zz}, {zx + sx, zz}, {zx, zz + sz}, {zx + sx, zz + sz}};
+    // own zone, then directions startDirIdx .. startDirIdx + 2 (clockwise from north) with the reference's start table: 4 / 6 for
+    // the west half of the zone (south / north), 0 / 2 for the east half (terrain.cpp:436-444). For the east half these are not
+    // the zones whose windows contain the chunk; the table is kept as it is (pinned to the real Terrain::tick through the model).
+    static const int kDir[8][2] = {{0, 1}, {1, 1}, {1, 0}, {1, -1}, {0, -1}, {-1, -1}, {-1, 0}, {-1, 1}};
+    const bool east = (cx - zx * 12) >= 6, north = (cz - zz * 12) >= 6;
+    const int start = east ? (north ? 2 : 0) : (north ? 6 : 4);
+    int cand[4][2] = {{zx, zz}, {0, 0}, {0, 0}, {0, 0}};
+    for (int k = 0; k < 3; ++k) { cand[k + 1][0] = zx + kDir[(start + k) % 8][0]; cand[k + 1][1] = zz + kDir[(start + k) % 8][1]; }
     for (const auto& c : cand)
     {
         const int lx = c[0] - s->zx0, lz = c[1] - s->zz0;
@@ -267,26 +299,38 @@ int mmgen_stream_tick(MmgenStream* s, float deltaTime, MmgenTickStats* out)
     // createVBOs (terrain.cpp:638-655); buildChunkAccel (the OptiX hand-off) is outside this path
     {
         std::vector<int32_t> coords;
-        while (!s->qVbos.empty() && s->actionTimeLeft >= s->cost[COST_VBOS])
+        std::vector<int> picked;
+        int budget = s->actionTimeLeft;
+        while (!s->qVbos.empty() && budget >= s->cost[COST_VBOS])
         {
-            s->needsUpdateChunks = true;
             const int i = s->qVbos.front(); s->qVbos.pop();
-            s->state[i] = ST_DRAWABLE; s->ready[i] = 0;
-            s->actionTimeLeft -= s->cost[COST_VBOS];
-            ++st.vbos;
+            picked.push_back(i);
+            budget -= s->cost[COST_VBOS];
             coords.push_back(w->cx0 + i % nx);
             coords.push_back(w->cz0 + i / nx);
         }
         // Chunk::createVBOs for the tick's chunks in one pass over the resident blocks (mm_mesh.cuh); the vertex / index
         // arrays stay in the world's device arena until the next tick (mmgen_world_mesh_device_ptrs / _download, chunk i =
-        // i-th pair of mmgen_stream_last_meshed)
+        // i-th pair of mmgen_stream_last_meshed). The chunks become DRAWABLE only once their meshes exist: if the mesher
+        // fails they go back to the head of the queue and the tick reports the error with the scheduler state unchanged.
         if (s->meshing && !coords.empty())
         {
             std::vector<int32_t> counts(coords.size());
-            if (mmgen_world_mesh(w, (int)coords.size() / 2, coords.data(), counts.data())) return 1;
+            if (mmgen_world_mesh(w, (int)coords.size() / 2, coords.data(), counts.data()))
+            {
+                std::queue<int> q;
+                for (int i : picked) q.push(i);
+                while (!s->qVbos.empty()) { q.push(s->qVbos.front()); s->qVbos.pop(); }
+                s->qVbos.swap(q);
+                return 1;
+            }
             for (size_t k = 0; k < counts.size(); k += 2) st.meshVertices += counts[k];
             s->lastMeshed = coords;
         }
+        for (int i : picked) { s->state[i] = ST_DRAWABLE; s->ready[i] = 0; }
+        if (!picked.empty()) s->needsUpdateChunks = true;
+        s->actionTimeLeft = budget;
+        st.vbos = (int)picked.size();
     }
     {
         std::vector<int> list;
@@ -403,6 +447,31 @@ int mmgen_stream_tick(MmgenStream* s, float deltaTime, MmgenTickStats* out)
     st.idle = !s->needsUpdateChunks && s->zonesToTry.empty() && s->zonesToErode.empty() && s->qHeightfield.empty() &&
               s->qGatherHeightfield.empty() && s->qLayers.empty() && s->qCaves.empty() && s->qPlacements.empty() &&
               s->qGatherPlacements.empty() && s->qFill.empty() && s->qVbos.empty();
+    if (st.idle)
+    {
+        // Safety net, after everything the reference's rules can do is done: its quadrant table (streamAddZonesToTry) re-tests, for
+        // chunks in the east half of a zone, zones whose windows do not contain the chunk, so the chunk that completes a zone's
+        // window may never put that zone up for its test and the zone stays un-eroded (a hole in the world) until the player
+        // moves. When the stream would fall idle, every zone that is not queued yet is put up once more.
+        for (int z = 0; z < s->nzx * s->nzz; ++z)
+        {
+            if (s->zoneQueued[z]) continue;
+            const int lx0 = (s->zx0 + z % s->nzx) * 12 - 6 - w->cx0, lz0 = (s->zz0 + z / s->nzx) * 12 - 6 - w->cz0;
+            if (lx0 < 0 || lz0 < 0 || lx0 + 24 > w->nx || lz0 + 24 > w->nz) continue;
+            bool ok = true;
+            for (int dz = 0; dz < 24 && ok; ++dz)
+                for (int dx = 0; dx < 24 && ok; ++dx)
+                {
+                    const int k = (lz0 + dz) * w->nx + lx0 + dx;
+                    ok = s->exists[k] && s->state[k] >= ST_HAS_LAYERS;
+                }
+            if (!ok) continue;
+            s->zoneInTry[z] = 1;
+            s->zonesToTry.push_back(z);
+            s->needsUpdateChunks = true;
+            st.idle = 0;
+        }
+    }
     ++s->ticks;
     if (out) *out = st;
     return 0;

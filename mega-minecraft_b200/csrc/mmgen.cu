@@ -137,7 +137,9 @@ struct MmgenWorld
     float* d_zone = nullptr;          // kZoneBatch zones x (9 planes + 1 scratch plane + 2 accum planes)
     int2* d_zoneCorners = nullptr;
     int* d_flags = nullptr;           // one "changed" flag per sweep of a batch
-    int* d_list = nullptr;            // chunk index lists
+    int* d_list = nullptr;            // chunk index list of the stage call being queued: a slice of d_listRing
+    int* d_listRing = nullptr;        // kListSlots slices of n ints; a stage call takes the next one, so that the calls of one generate /
+    int listSlot = 0;                 // one tick can be queued back to back without waiting for the previous stage's kernels
     CaveLayer* d_caves = nullptr;     // [chunk][256][32]
     CaveColumn* d_caveCols = nullptr; // per-column hoisted cave terms of one cave batch
     uint2* d_caveQueue = nullptr;     // cave-biome lookups of one cave batch
@@ -164,6 +166,7 @@ struct MmgenWorld
     size_t meshListCap = 0, meshVertCap = 0;
     std::vector<long long> h_meshBase;
     std::vector<int> h_meshTotals;
+    std::vector<int32_t> h_meshCoords;   // (cx, cz) of the chunks of the last mmgen_world_mesh call
     float meshMs = 0.f;
     int erosionSweeps = 0;
     std::vector<uint8_t> stage;
@@ -614,7 +617,7 @@ int mmgen_world_destroy(MmgenWorld* w)
     cudaFree(w->d_zone);
     cudaFree(w->d_zoneCorners);
     cudaFree(w->d_flags);
-    cudaFree(w->d_list);
+    cudaFree(w->d_listRing);
     cudaFree(w->d_caves);
     cudaFree(w->d_caveCols);
     cudaFree(w->d_caveQueue);
@@ -654,10 +657,16 @@ int mmgen_world_destroy(MmgenWorld* w)
 // ------------------------------------------------------------------ stage runners of the resident world
 // Each runs one stage over an explicit list of window chunks (raster indices) and keeps w->stage up to date.
 // worldGenerate (batch mode) and the streaming scheduler (mm_stream.cuh, Terrain::tick re-hosted) both
-// drive the world through these. Every runner leaves the stream synchronised: the shared list buffer is reused.
+// drive the world through these. The runners only queue work (erosion excepted: its convergence is polled); callers that
+// read results synchronise (downloads, checksums, mmgen_world_sync, the end of a stream tick).
+constexpr int kListSlots = 8;
 static int worldUploadList(MmgenWorld* w, const std::vector<int>& list)
 {
-    if (!w->d_list) MMG_CUDA(cudaMalloc(&w->d_list, (size_t)w->n * sizeof(int)));
+    if (!w->d_listRing) MMG_CUDA(cudaMalloc(&w->d_listRing, (size_t)kListSlots * w->n * sizeof(int)));
+    w->d_list = w->d_listRing + (size_t)w->listSlot * w->n;
+    w->listSlot = (w->listSlot + 1) % kListSlots;
+    // pageable source: staged before the call returns, the device copy runs in stream order (after the kernels that read this
+    // slice kListSlots stage calls ago)
     MMG_CUDA(cudaMemcpyAsync(w->d_list, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, w->stream));
     return 0;
 }
@@ -673,7 +682,6 @@ static int worldHeightfields(MmgenWorld* w, const std::vector<int>* list)
         if (worldUploadList(w, *list)) return 1;
         MMG_TIMED(K_HEIGHTFIELD, w->stream, 1, MMG_LAUNCH(k_heightfield, (int)list->size(), 256, kNoiseSmemBytes, w->stream, (const int*)w->d_list,
                                                           (const int2*)w->d_origins, w->d_height, w->d_weights));
-        MMG_CUDA(cudaStreamSynchronize(w->stream));
         for (int i : *list) w->stage[i] = std::max<uint8_t>(w->stage[i], 1);
     }
     else
@@ -693,7 +701,6 @@ static int worldLayers(MmgenWorld* w, const std::vector<int>& list)
     if (worldUploadList(w, list)) return 1;
     MMG_TIMED(K_LAYERS, w->stream, 1, MMG_LAUNCH(k_layers<true>, (int)list.size(), 256, kNoiseSmemBytes, w->stream, (const int*)w->d_list,
                                                  (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights, w->d_layers, w->nx));
-    MMG_CUDA(cudaStreamSynchronize(w->stream));   // list buffer is reused
     for (int i : list) w->stage[i] = std::max<uint8_t>(w->stage[i], 2);
     return 0;
 }
@@ -739,7 +746,6 @@ static int worldCaves(MmgenWorld* w, const std::vector<int>& list)
     if (launchCaves(m, (const int*)w->d_list, (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights,
                     w->d_caveCols, w->d_caves, w->d_caveQueue, w->d_caveCount, w->stream))
         return 1;
-    MMG_CUDA(cudaStreamSynchronize(w->stream));
     for (int i : list) w->stage[i] = 4;
     return 0;
 }
@@ -760,7 +766,6 @@ static int worldPlacements(MmgenWorld* w, const std::vector<int>& list)
     MMG_TIMED(K_PLACEMENTS, w->stream, 1, MMG_LAUNCH(k_feature_placements, m, 256, 0, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
                                                      (const float*)w->d_height, (const float*)w->d_weights, (const float*)w->d_eroded,
                                                      (const CaveLayer*)w->d_caves, w->d_features, w->d_caveFeatures, w->d_counts));
-    MMG_CUDA(cudaStreamSynchronize(w->stream));
     for (int i : list) w->stage[i] = 5;
     return 0;
 }
@@ -833,7 +838,6 @@ static int worldFill(MmgenWorld* w, const std::vector<int>& list, uint8_t* hostB
         }
     }
     if (enc && codecDeliver(w, nBatches, enc->bytes, enc)) return 1;
-    MMG_CUDA(cudaStreamSynchronize(w->stream));
     for (int i : list) w->stage[i] = 6;
     return 0;
 }
@@ -1463,12 +1467,36 @@ int mmgen_world_mesh(MmgenWorld* w, int n, const int32_t* chunkCoords, int32_t* 
     MMG_CUDA(cudaEventRecord(e1, w->stream));
     MMG_CUDA(cudaStreamSynchronize(w->stream));
     MMG_CUDA(cudaEventElapsedTime(&w->meshMs, e0, e1));
+    w->h_meshCoords.assign(chunkCoords, chunkCoords + 2 * (size_t)n);
     if (out_counts)
         for (int i = 0; i < n; ++i)
         {
             out_counts[2 * i] = w->h_meshTotals[i];
             out_counts[2 * i + 1] = w->h_meshTotals[i] / 4 * 6;
         }
+    return 0;
+}
+
+// OptixRenderer::buildChunkAccel (optixRenderer.cpp:223-368) uploads chunkPtr->verts / idx from host vectors (initFromVector,
+// :229-230) and describes them to OptiX as one triangle array. The same description for the meshes that already sit in the
+// device arena: nothing crosses PCIe, and one optixAccelBuild can take the whole batch.
+int mmgen_world_mesh_gas_inputs(MmgenWorld* w, int cap, MmgenGasInput* out, int* n)
+{
+    const int m = (int)w->h_meshTotals.size();
+    if (n) *n = m;
+    for (int i = 0; i < m && i < cap; ++i)
+    {
+        MmgenGasInput g;
+        g.vertexBuffer = (uint64_t)(uintptr_t)(w->d_meshVerts + w->h_meshBase[i]);
+        g.numVertices = (uint32_t)w->h_meshTotals[i];
+        g.vertexStrideInBytes = (uint32_t)sizeof(MeshVertex);
+        g.indexBuffer = (uint64_t)(uintptr_t)(w->d_meshIdx + w->h_meshBase[i] / 4 * 6);
+        g.numIndexTriplets = (uint32_t)(w->h_meshTotals[i] / 4 * 2);
+        g.indexStrideInBytes = 12u;
+        g.cx = w->h_meshCoords[2 * i];
+        g.cz = w->h_meshCoords[2 * i + 1];
+        out[i] = g;
+    }
     return 0;
 }
 

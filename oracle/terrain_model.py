@@ -11,10 +11,11 @@ One rule differs from the reference on purpose and is the same rule the product 
 queued for erosion when its WHOLE 24x24-chunk gather window has layers (the reference only waits for the
 neighbour zones that already exist, terrain.cpp:488-523), and chunks outside the session window never exist.
 
-Parity of this model is UNPINNED against an executable reference: terrain.cpp is MSVC-only (std::exception(const
-char*), terrain.cpp:468) and drags in the GL/OptiX renderer, so it cannot be compiled here. What is
-pinned is the data: whatever order the scheduler fills chunks in, their blocks equal the batch world's, which is
-held bit-exact to the reference's output (tests/golden/c2_window.npz).
+PINNED against the executable reference: oracle/_ref/libmmref_terrain.so is the UNMODIFIED terrain.cpp (g++ with one
+force-included compatibility header, oracle/Makefile target `terrain`) driven headless by oracle/refterrain_driver.cpp;
+tests/test_stream.py::test_model_equals_the_real_terrain_tick holds this model to it tick by tick (batch sizes of all nine
+stages, fill order) for a standing and a walking player. The data is pinned separately: whatever order the scheduler fills
+chunks in, their blocks equal the batch world's, which is held bit-exact to the reference's output.
 """
 from collections import deque
 
@@ -48,7 +49,11 @@ def spiral(max_gen_radius):
 
 class TerrainModel:
     def __init__(self, cx0, cz0, nx, nz, vbos_gen_radius=16, max_gen_radius=40, costs=None,
-                 max_per_frame=MAX_ACTION_TIME_PER_FRAME, per_second=TOTAL_ACTION_TIME_PER_SECOND):
+                 max_per_frame=MAX_ACTION_TIME_PER_FRAME, per_second=TOTAL_ACTION_TIME_PER_SECOND, zone_order=None):
+        # zone_order: [(zone x, zone z) in zone units] - when several zones become ready in the same update, queue them in this
+        # order. The reference iterates an unordered_set<Zone*> there (terrain.cpp:543-563), i.e. in heap-address order; replaying
+        # the order a real run took makes the model comparable with that run tick by tick. Default: insertion order.
+        self.zone_rank = {z: i for i, z in enumerate(zone_order)} if zone_order is not None else None
         self.cx0, self.cz0, self.nx, self.nz = cx0, cz0, nx, nz
         self.vbos_r, self.max_r = vbos_gen_radius, max_gen_radius
         self.cost = dict(COSTS if costs is None else costs)
@@ -100,25 +105,47 @@ class TerrainModel:
             self.q["vbos"].append(c)
 
     def gather(self, c, R, cur, nxt):
-        """floodFillAndIterateNeighbors<4R+1> (chunk.cu:53-147): centres within R of c in state `cur` whose
-        (2R+1)^2 neighbourhood exists at `cur` or beyond move to `nxt`."""
+        """floodFillAndIterateNeighbors<4R+1> (chunk.cu:53-147). floodFill: breadth-first from c over the four edge
+        neighbours, inside the (4R+1)^2 window around c, through chunks at state `cur` or beyond only - a chunk behind a
+        less advanced one is not found. iterateNeighborChunks: centres within R of c that are at `cur` and whose whole
+        (2R+1)^2 neighbourhood was found move to `nxt`."""
+        radius = 2 * R
+        found, visited, queue = set(), set(), deque([c])
+        while queue:
+            p = queue.popleft()
+            visited.add(p)
+            if self.state.get(p, -1) < cur:
+                continue
+            found.add(p)
+            for n in ((p[0], p[1] + 1), (p[0] + 1, p[1]), (p[0], p[1] - 1), (p[0] - 1, p[1])):
+                if n not in self.state or n in visited or max(abs(n[0] - c[0]), abs(n[1] - c[1])) > radius:
+                    continue
+                queue.append(n)
         for cz in range(c[1] - R, c[1] + R + 1):
             for cx in range(c[0] - R, c[0] + R + 1):
-                if self.state.get((cx, cz)) != cur:
+                if (cx, cz) not in found or self.state[(cx, cz)] != cur:
                     continue
-                if all(self.state.get((cx + ox, cz + oz), -1) >= cur for oz in range(-R, R + 1) for ox in range(-R, R + 1)):
+                if all((cx + ox, cz + oz) in found for oz in range(-R, R + 1) for ox in range(-R, R + 1)):
                     self.set_state((cx, cz), nxt)
+
+    # Terrain::addZonesToTryErosionSet (terrain.cpp:431-453): the chunk's own zone plus three neighbour zones chosen by the
+    # quadrant of the zone the chunk lies in - start direction 4 / 6 for the west half (south / north), 0 / 2 for the east half
+    # (south / north), then three consecutive directions clockwise from north. (For the east half that is NOT the three zones
+    # whose gather windows contain the chunk - the table is what the reference does, and the scheduler is pinned to it.)
+    QUADRANT_ZONES = {(False, False): ((0, -1), (-1, -1), (-1, 0)), (False, True): ((-1, 0), (-1, 1), (0, 1)),
+                      (True, False): ((0, 1), (1, 1), (1, 0)), (True, True): ((1, 0), (1, -1), (0, -1))}
 
     def add_zones_to_try(self, c):
         zx, zz = c[0] // 12, c[1] // 12
-        sx = -1 if c[0] - 12 * zx < 6 else 1
-        sz = -1 if c[1] - 12 * zz < 6 else 1
-        for z in ((zx, zz), (zx + sx, zz), (zx, zz + sz), (zx + sx, zz + sz)):
+        east, north = c[0] - 12 * zx >= 6, c[1] - 12 * zz >= 6
+        for z in ((zx, zz),) + tuple((zx + dx, zz + dz) for dx, dz in self.QUADRANT_ZONES[(east, north)]):
             if z in self.zones_queued or z in self.zones_to_try:
                 continue
             self.zones_to_try.append(z)
 
     def update_zones(self):
+        if self.zone_rank is not None:
+            self.zones_to_try.sort(key=lambda z: self.zone_rank.get(z, 1 << 30))
         for z in self.zones_to_try:
             x0, z0 = 12 * z[0] - 6, 12 * z[1] - 6
             if all(self.state.get((x0 + dx, z0 + dz), -1) >= HAS_LAYERS for dz in range(24) for dx in range(24)):
@@ -199,6 +226,21 @@ class TerrainModel:
             st["heightfields"] += 1
         st["actionTimeLeft"] = self.left
         st["idle"] = int(not self.needs_update and not self.zones_to_try and not self.zones_to_erode and not any(self.q.values()))
+        if st["idle"]:
+            # the product's safety net (mm_stream.inl): zones whose window is complete but which the reference's quadrant table
+            # never put up for their test are tried when the stream would otherwise fall idle (never happens in the runs that
+            # are compared with the real terrain.cpp: there the reference itself finishes every zone)
+            zx0, zz0 = self.cx0 // 12, self.cz0 // 12
+            for zz in range(zz0, (self.cz0 + self.nz - 1) // 12 + 1):
+                for zx in range(zx0, (self.cx0 + self.nx - 1) // 12 + 1):
+                    z = (zx, zz)
+                    if z in self.zones_queued:
+                        continue
+                    x0, z0 = 12 * zx - 6, 12 * zz - 6
+                    if all(self.state.get((x0 + dx, z0 + dz), -1) >= HAS_LAYERS for dz in range(24) for dx in range(24)):
+                        self.zones_to_try.append(z)
+                        self.needs_update = True
+                        st["idle"] = 0
         return st
 
     def run_until_idle(self, dt=1.0 / 60.0, max_ticks=100000):

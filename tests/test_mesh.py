@@ -57,6 +57,24 @@ def test_mesh_matches_reference_createvbos(gen, mm, golden, mesh_golden):
     # any subset / order of chunks gives the same per-chunk arrays (arena offsets do not leak into the indices)
     sub = world.mesh(coords[[20, 3]])
     assert sub[0][0].tobytes() == meshes[20][0].tobytes() and sub[1][1].tobytes() == meshes[3][1].tobytes()
+    # hand-off to the path tracer (OptixRenderer::buildChunkAccel, optixRenderer.cpp:223-368): the triangle-array description
+    # of every meshed chunk points into the device arena - no host vectors, no upload
+    meshes = world.mesh(coords)
+    gas = world.mesh_gas_inputs()
+    assert gas.dtype.itemsize == 40 and len(gas) == len(coords)
+    assert np.array_equal(np.stack([gas["cx"], gas["cz"]], axis=1), coords)
+    assert (gas["vertexStrideInBytes"] == 40).all() and (gas["indexStrideInBytes"] == 12).all()
+    assert np.array_equal(gas["numVertices"], mesh_golden["counts"][:, 0]) and np.array_equal(gas["numIndexTriplets"] * 3, mesh_golden["counts"][:, 1])
+    # chunks are packed back to back in the arena, vertices 40 bytes apart, 6 indices per 4 vertices
+    assert np.array_equal(np.diff(gas["vertexBuffer"].astype(np.int64)), gas["numVertices"][:-1].astype(np.int64) * 40)
+    assert np.array_equal(np.diff(gas["indexBuffer"].astype(np.int64)), gas["numIndexTriplets"][:-1].astype(np.int64) * 12)
+    assert (gas["vertexBuffer"] % 8 == 0).all() and (gas["indexBuffer"] % 4 == 0).all()
+    import ctypes
+    for k in (0, 7, 35):                                    # the same addresses mmgen_world_mesh_device_ptrs / _download use
+        pv, pi, nv, ni = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int(0), ctypes.c_int(0)
+        gen._check(gen.L.mmgen_world_mesh_device_ptrs(world.h, k, ctypes.byref(pv), ctypes.byref(pi), ctypes.byref(nv), ctypes.byref(ni)))
+        assert (pv.value, pi.value, nv.value, ni.value) == (int(gas["vertexBuffer"][k]), int(gas["indexBuffer"][k]), int(gas["numVertices"][k]),
+                                                            3 * int(gas["numIndexTriplets"][k]))
     with pytest.raises(mm.MmgenError):
         world.mesh(np.array([[100, 100]], np.int32))
     world.close()

@@ -49,6 +49,38 @@ def test_model_keeps_reference_batch_caps_and_reaches_the_region():
     assert max(abs(m.filled_order[0][0]), abs(m.filled_order[0][1])) <= 12
 
 
+KEYS = ("heightfields", "gatherHeightfields", "layers", "zonesEroded", "caves", "placements", "gatherPlacements", "filled", "vbos")
+
+
+@pytest.mark.parametrize("moves,window", [([(0, 0)], (-41, -41, 82, 82)), ([(0, 0), (24, 0)], (-41, -41, 106, 82)), ([(-7, 5)], (-48, -36, 82, 82))])
+def test_model_equals_the_real_terrain_tick(moves, window):
+    """Pins the scheduler model to the reference's OWN scheduler: the unmodified terrain.cpp (oracle/_ref/libmmref_terrain.so,
+    built by oracle/Makefile with g++ and one force-included compatibility header) is run headless with the generation kernels
+    switched off - its batch sizes, orders and budgets do not depend on the data - and must agree with oracle/terrain_model.py
+    tick by tick in all nine per-stage counts and in the order chunks are filled, for a standing player, a walking player
+    and a player away from the origin. The one thing taken FROM the run is the order in which the reference erodes zones that
+    become ready in the same update: it iterates an unordered_set<Zone*> there (heap-address order)."""
+    from oracle import refterrain
+    if not refterrain.available():
+        pytest.skip("oracle/_ref/libmmref_terrain.so not built (needs /root/reference at build time)")
+    ref = refterrain.run_session(moves, DT)
+    m = tm.TerrainModel(*window, zone_order=[tuple(z) for z in ref["eroded"]])
+    log = []
+    for i, mv in enumerate(moves):
+        m.set_player_chunk(*mv)
+        seg = m.run_until_idle(DT)
+        # the reference run keeps ticking a few idle ticks after each move (that is how the driver detects idleness)
+        end = ref["segments"][i + 1] if i + 1 < len(moves) else len(ref["ticks"])
+        log += [[t[k] for k in KEYS] for t in seg]
+        log += [[0] * 9] * (end - len(log))
+    assert len(log) == len(ref["ticks"])
+    bad = [i for i, (a, b) in enumerate(zip(log, ref["ticks"])) if a != b]
+    assert not bad, "first tick that differs: %d model %s reference %s" % (bad[0], log[bad[0]], ref["ticks"][bad[0]])
+    assert [list(c) for c in m.filled_order] == ref["filled"]                      # the order chunks are filled in
+    assert sum(t[7] for t in ref["ticks"]) == len(m.filled()) > 1500
+    assert max(t[0] for t in ref["ticks"]) == 166 and max(t[2] for t in ref["ticks"]) == 100 and max(t[7] for t in ref["ticks"]) == 62
+
+
 def test_model_player_walk_extends_the_filled_region():
     m = tm.TerrainModel(-41, -41, 106, 82)
     m.run_until_idle()
