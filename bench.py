@@ -3,12 +3,19 @@
 region (BASELINE.json metric), its roofline reading and two measured baselines.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--world S]
-      own arm. One process per GPU (torchrun for N > 1). The S x S-chunk target region is split into
-      N chunk-coordinate tiles; each rank fills its tile in its own device-resident world (apron
-      recomputed, no data-path collective) => total work fixed => "scaling": "strong".
-      `value`  = target chunks / device time of mmgen_world_generate (everything stays in HBM).
-      `e2e`    = the same through mmgen_world_generate_to_host: chunk origins come from host memory
-                 and the block volumes are delivered into pinned HOST memory inside the timed region.
+      own arm, BASELINE config 5: the S x S-chunk world [0, S)^2 (default 256). One process per GPU (torchrun for N > 1); the
+      region is split into N chunk-coordinate tiles whose cuts come from a stage-1 cost predictor (every rank evaluates the
+      features of a strip, all-gather, same cuts everywhere - repeated inside every timed step); each rank fills its tile in
+      its own device-resident world => total work fixed => "scaling": "strong". The 3-chunk placement ring around a tile is
+      either recomputed or exchanged over NCCL send / recv; both are measured before the timed steps and the faster is kept
+      (--halo).
+      `value`  = target chunks / device time of mmgen_world_generate (everything stays in HBM; CUDA events, MAX over ranks).
+      `e2e`    = the same through mmgen_world_generate_to_host: chunk origins come from host memory and the raw block
+                 volumes are delivered into pinned HOST memory inside the timed region.
+      `e2e_encoded` = the same with the volumes run-length coded on the device (wire format MMCH1) - an extra, not the headline.
+      `roofline`, `stages` = per-stage algorithmic FLOPs / bytes over device time; S1-S3 from device work counters.
+  python bench.py --config c4      BASELINE config 4: cave + fill stress on 32x32 chunks, S4 and S6 timed in isolation.
+  python bench.py --config c3      BASELINE config 3: 64x64-chunk streaming region at the reference's tick pattern (mmgen_stream_*).
   python bench.py --impl reference [...]
       the UNMODIFIED reference pipeline (chunk.cu built by oracle/Makefile into oracle/_ref) on the
       same GPU with its own batch caps, pinned staging buffers and CPU stages, on a bounded sample.
@@ -670,7 +677,9 @@ def run_own(args):
         rates, detail = cpu_stage_rates(nthreads, cave_chunks=args.cpu_cave_chunks)
         out["cpu_baseline"] = {"value": cpu_whole_job_rate(rates, tiling.stage_chunk_counts(0, 0, S, S)), "unit": UNIT, "cores": nthreads, "kind": "port",
                                "sample": "oracle port (C++ -O2, no fast-math) on %d host threads: S1 on 676, S2 on 576 chunks, S3 on 1 zone, S4+S5 on %d, "
-                                         "S6 on %d chunks of the C2 window; whole-job rate extrapolated with this workload's per-stage chunk counts"
+                                         "S6 on %d chunks of the C2 window; whole-job rate extrapolated with this workload's per-stage chunk counts. "
+                                         "A thin extrapolation, and it FLATTERS the CPU: S6 is timed with each chunk's own placements only, not the "
+                                         "gathered 49-list scan (up to 6144 placements per voxel) that dominates the reference's fill"
                                          % (nthreads, detail["S4"]["units"], detail["S6"]["units"]),
                                "stage_rates": {k: round(v, 2) for k, v in rates.items()}}
     elif rank == 0:

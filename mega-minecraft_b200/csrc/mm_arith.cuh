@@ -120,6 +120,8 @@ __device__ __forceinline__ void noise_tab_stage()
     for (int i = threadIdx.x + blockDim.x * threadIdx.y; i < kNoiseSmemBytes / 16; i += blockDim.x * blockDim.y) mmg_dyn_smem[i] = src[i];
     __syncthreads();
 }
+// (Reading the tables where they lie - global memory through L1 - instead of staging them per CTA was measured in round 2:
+// k_caves 79.2 ms against 70.9, k_fill_rock 34.2 against 28.6 per 128x128 region; profiles/r02_variants.txt.)
 
 // permute(x) = mod289((34x+1)x) on small non-negative integers: every step is exact in fp32,
 // so contraction cannot change it (34*580+1 and its product with 580 are < 2^24).

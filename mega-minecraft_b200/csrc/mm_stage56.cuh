@@ -532,8 +532,15 @@ __global__ void __launch_bounds__(kFillSeg, 12) k_fill_terrain(const int* __rest
                 if (lush) blk[k] = lush_block(wx, y, wz);
             }
     }
+    // the column's 384 block IDs leave as 24 16-byte vector stores (the column is 384 contiguous, 16-byte aligned bytes).
+    // Measured (round 2, profiles/r02_variants.txt): the same time as three one-byte stores per thread - the kernel is bound by
+    // the per-voxel logic, not by its 96 KB of stores per chunk; 2 or 4 columns per CTA with one queue reservation are slower
+    // (17.7 / 21.3 ms against 15.3 per 128x128 region: fewer resident CTAs to hide the staging latency).
+    __shared__ __align__(16) uint8_t shOut[384];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) out[k * kFillSeg + t] = blk[k];
+    for (int k = 0; k < 3; ++k) shOut[k * kFillSeg + t] = blk[k];
+    __syncthreads();
+    if (t < 24) reinterpret_cast<uint4*>(out)[t] = reinterpret_cast<const uint4*>(shOut)[t];
     (void)lushQueue;
 }
 
