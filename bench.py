@@ -124,6 +124,28 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def prefer_gpu_numa_node(index):
+    """Best effort: make this process allocate host memory on the NUMA node the GPU hangs off, before the pinned delivery buffer
+    is created - at 8 GPUs the raw block volumes (6.4 GB per step) otherwise all land on the node the container's CPUs belong to
+    and half the GPUs write across the socket link. Uses set_mempolicy(MPOL_PREFERRED) through libc; returns what happened."""
+    try:
+        import ctypes
+        out = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True, timeout=20)
+        bus = out.stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]                              # sysfs uses a 4-digit PCI domain
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+        if node < 0 or node not in nodes:
+            return {"gpu_numa_node": node, "nodes": nodes, "policy": "unchanged (no NUMA information)"}
+        libc = ctypes.CDLL("libc.so.6", use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        rc = libc.syscall(238, 1, ctypes.byref(mask), 64)      # SYS_set_mempolicy (x86-64), MPOL_PREFERRED
+        return {"gpu_numa_node": node, "nodes": nodes, "policy": "MPOL_PREFERRED" if rc == 0 else "unchanged (set_mempolicy errno %d)" % ctypes.get_errno()}
+    except Exception as e:      # noqa: BLE001
+        return {"policy": "unchanged (%s)" % type(e).__name__}
+
+
 # ------------------------------------------------------------------------------------------ CPU port
 def cpu_stage_rates(nthreads, cave_chunks=None, fill_chunks=None):
     """Times the oracle port stage by stage on one 26x26-chunk window (zone (0,0) + pad + ring, the C2
@@ -436,6 +458,7 @@ def run_own(args):
         world.close()
     tiles_final = bal.tiles()
     n_target = tile[2] * tile[3]
+    numa = prefer_gpu_numa_node(local_rank) if world_size > 1 else {"policy": "unchanged (one GPU)"}
     host = torch.empty(n_target * 98304, dtype=torch.uint8, pin_memory=True)
     exchange = sharding.HaloExchange(tiles_final, rank) if world_size > 1 else None
 
@@ -518,25 +541,33 @@ def run_own(args):
     sampler = ClockSampler(local_rank)
     stage_ms = np.zeros(7)
     fp32_measured = gen.measure_fp32_peak()          # FFMA microbenchmark on this GPU, right before the timed region
-    barrier()
     gen.kernel_timing(True)                          # CUDA event pairs around every hot-kernel launch, on the world's stream
     gen.work_counters(reset=True)                    # S1 / S2 / S3 work counters of the timed steps
-    sampler.start()
+    sampler.start()                                  # forks nvidia-smi: tens of ms, different on every rank - before the barrier
+    barrier()
     l0 = gen.launch_count()
     t0 = time.perf_counter()
     dev_ms = 0.0
     xch_ms = 0.0
     step.predict_ms = 0.0
     ktimes = {}
+    t_step = t_book = 0.0
     for _ in range(args.steps):
+        ta = time.perf_counter()
         a, x = step(variant)
+        tb = time.perf_counter()
         dev_ms += a
         xch_ms += x
         stage_ms += world.stage_ms()
         for k, v in gen.kernel_times().items():      # {kernel: (device ms, launches)} of this step; frees the event pairs for the next one
             ktimes[k] = (ktimes.get(k, (0.0, 0))[0] + v[0], ktimes.get(k, (0.0, 0))[1] + v[1])
+        t_step += tb - ta
+        t_book += time.perf_counter() - tb
     rank_ms = [t / args.steps for t in sharding.gather_floats(dev_ms)]
     predict_ms_per_step = step.predict_ms / args.steps
+    # where a rank's wall time goes per step: inside step() (predictor + generate + exchange, host view) and the bookkeeping between steps
+    rank_wall = [[round(1e3 * v / args.steps, 2) for v in sharding.gather_floats(q)] for q in (t_step, t_book)]
+    rank_predict = [round(v / args.steps, 2) for v in sharding.gather_floats(step.predict_ms)]
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -664,12 +695,14 @@ def run_own(args):
                    "tiles": [list(t) for t in tiles_final], "chunks_touched_rank0": counts,
                    "l2": "working set per step (>= %.1f GB written) far exceeds the 126 MB L2; no flush needed" % (n_target * 98304 / 1e9)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * max(e2e_wall, e2e_dev) / args.steps, "host_checksum": host_sum},
+                "ms_per_step": 1e3 * max(e2e_wall, e2e_dev) / args.steps, "host_checksum": host_sum,
+                "d2h_gbs": d2h / 1e9 / (max(e2e_wall, e2e_dev) / args.steps), "host_memory_rank0": numa},
         "e2e_encoded": {"value": enc_value, "unit": UNIT, "d2h_bytes_per_step": int(enc_total), "compression": d2h / max(enc_total, 1),
                         "ms_per_step": 1e3 * max(enc_wall, enc_dev) / args.steps,
                         "note": "block volumes run-length coded on the device (wire format MMCH1, include/mmgen.h) and delivered as payload + index; "
                                 "decoded on the host by mmgen_decode_chunk"},
         "gpu_launches": int(sum_over_ranks(launches)), "rank_ms": [round(t, 2) for t in rank_ms], "balance_passes": balance_log,
+        "rank_wall_ms": {"step": rank_wall[0], "bookkeeping_between_steps": rank_wall[1], "predictor_incl_wait_for_slowest_rank": rank_predict},
         "roofline": roof, "kernels": kernels, "stages": stages, "clocks": clocks, "block_checksums": [("%016x" % c) for c in checks], "world_hash": "%016x" % (sum(sharding.gather_u64(hash_sum)) & 0xFFFFFFFFFFFFFFFF),
     }
     if rank == 0 and not args.no_cpu and world_size == 1:
