@@ -591,6 +591,8 @@ def run_own(args):
     e2e_dev = max_over_ranks(e2e_ms / 1e3)
     e2e_value = total_chunks * args.steps / max(e2e_wall, e2e_dev)
     host_sum = int(host.view(torch.int64).sum().item()) if rank == 0 else 0
+    sample_slots = np.unique(np.linspace(0, n_target - 1, 64).astype(np.int64))       # raw volumes kept to check the encoded delivery against
+    raw_sample = host.numpy().reshape(-1)[: n_target * 98304].reshape(n_target, 98304)[sample_slots].copy()
 
     # ---- the same with the block volumes delivered in the library's wire format (MMCH1 run-length code, decoded on the host by
     # mmgen_decode_chunk): an extra figure, not the headline e2e - the reference's contract is the raw volume
@@ -605,10 +607,10 @@ def run_own(args):
     enc_dev = max_over_ranks(enc_ms / 1e3)
     enc_value = total_chunks * args.steps / max(enc_wall, enc_dev)
     enc_total = sum_over_ranks(enc_bytes[0])
-    if rank == 0:      # spot check: a delivered chunk decodes to a plausible volume (bedrock at y = 0)
-        idx = enc_index.numpy().view(np.uint64).reshape(-1, 2)
-        blk = mm.decode_chunk(host.numpy()[int(idx[0, 0]):int(idx[0, 0] + idx[0, 1])])
-        assert blk.shape == (16, 16, 384) and len(np.unique(blk[:, :, 0])) == 1
+    idx = enc_index.numpy().view(np.uint64).reshape(-1, 2)      # every rank: 64 chunks of its tile decode to the raw delivery's bytes
+    for k, slot in enumerate(sample_slots):
+        blk = mm.decode_chunk(host.numpy()[int(idx[slot, 0]):int(idx[slot, 0] + idx[slot, 1])])
+        assert np.array_equal(blk.reshape(-1), raw_sample[k]), "encoded delivery differs from the raw delivery at slot %d" % slot
     h2d = sum_over_ranks(world.n * 8)
     d2h = sum_over_ranks(n_target * 98304)
 
