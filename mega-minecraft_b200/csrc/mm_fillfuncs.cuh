@@ -133,9 +133,9 @@ __device__ __forceinline__ uint8_t lush_block(int wx, int y, int wz)
     float ny = (float)y * 0.025f;
     ny = ny + 192031.9821f;
     const float ax = nx * 0.4f, ay = ny * 0.4f, az = nz * 0.4f;
-    const float o1 = fbm3<3, false>(ax, ay, az);
-    const float o2 = fbm3<3, true>(ax + 5923.45f, ay + 4129.42f, az + 5790.48f);
-    const float o3 = fbm3<3, true>(ax + 1765.68f, ay + 4704.36f, az + 5692.12f);
+    const float o1 = fbm3_paired<3, false>(ax, ay, az);
+    const f32x2 o23 = fbm3x2<3, true>(f2_make(ax + 5923.45f, ax + 1765.68f), f2_make(ay + 4129.42f, ay + 4704.36f), f2_make(az + 5790.48f, az + 5692.12f));
+    const float o2 = f2_lo(o23), o3 = f2_hi(o23);
     const float clay = worley3_lush(fmaf(o1, 2.f, nx), fmaf(o2, 2.f, ny), fmaf(o3, 2.f, nz));
     return clay < 0.25f ? B_CLAY : B_MOSS;
 }

@@ -25,20 +25,27 @@ __device__ MMG_NOISE_INLINE CaveBiomeNoise cave_biome_noise(int x, int y, int z,
 {
     const float px = (float)x, py = (float)y, pz = (float)z;
     const float qx = px * 0.0470f, qy = py * 0.0470f, qz = pz * 0.0470f;
-    const float cx = fmaf(fbm3<3>(qx, qy, qz), 30.f, px);
-    const float cy = fmaf(fbm3<3>(qx + 5923.45f, qy + 4129.42f, qz + 5790.48f), 24.f, py);
-    const float cz = fmaf(fbm3<3>(qx + 1765.68f, qy + 4704.36f, qz + 5692.12f), 30.f, pz);
+    float o1, o2, o3;
+    fbm3_from3<3>(qx, qy, qz, &o1, &o2, &o3);      // noise evaluations in pairs (packed fp32, mm_arith.cuh): same values
+    const float cx = fmaf(o1, 30.f, px);
+    const float cy = fmaf(o2, 24.f, py);
+    const float cz = fmaf(o3, 30.f, pz);
     const float nx = cx * 0.2000f, nz = cz * 0.2000f;
     const float top = fmaf(maxHeight + -128.f, 0.15f, 128.f);
-    const float nsStart = fmaf(fbm2<3>(nx, nz), 23.f, top + -19.f);
-    const float nsEnd = fmaf(fbm2<3>(nx + 3821.34f, nz + 4920.32f), 3.f, nsStart + -5.f);
-    const float sdStart = fmaf(fbm2<3>(nx + -4921.34f, nz + 8402.13f), 18.f, top + -72.f);
-    const float sdEnd = fmaf(fbm2<3>(nx + 9411.32f, nz + -3921.34f), 7.f, sdStart + -10.f);
+    const f32x2 ns = fbm2x2<3>(f2_make(nx, nx + 3821.34f), f2_make(nz, nz + 4920.32f));
+    const f32x2 sd = fbm2x2<3>(f2_make(nx + -4921.34f, nx + 9411.32f), f2_make(nz + 8402.13f, nz + -3921.34f));
+    const float nsStart = fmaf(f2_lo(ns), 23.f, top + -19.f);
+    const float nsEnd = fmaf(f2_hi(ns), 3.f, nsStart + -5.f);
+    const float sdStart = fmaf(f2_lo(sd), 18.f, top + -72.f);
+    const float sdEnd = fmaf(f2_hi(sd), 7.f, sdStart + -10.f);
     CaveBiomeNoise n;
     n.v[0] = ss_t((cy - nsEnd) / (nsStart - nsEnd));
     n.v[1] = ss_t((cy - sdEnd) / (sdStart - sdEnd));
-    n.v[2] = ss_t(fmaf(simplex3_raw<true>(fmaf(cx, 0.0030f, 5821.32f), fmaf(cy, 0.0030f, 4920.12f), fmaf(cz, 0.0030f, 7931.59f)), 42.f, 0.05f) / (0.05f - -0.05f));
-    n.v[3] = ss_t(fmaf(simplex3_raw<true>(fmaf(cx, 0.0022f, -9193.23f), fmaf(cy, 0.0022f, -6813.39f), fmaf(cz, 0.0022f, (float)-2171.23)), 42.f, 0.05f) / (0.05f - -0.05f));
+    const f32x2 wr = simplex3x2_raw<true>(f2_make(fmaf(cx, 0.0030f, 5821.32f), fmaf(cx, 0.0022f, -9193.23f)),
+                                          f2_make(fmaf(cy, 0.0030f, 4920.12f), fmaf(cy, 0.0022f, -6813.39f)),
+                                          f2_make(fmaf(cz, 0.0030f, 7931.59f), fmaf(cz, 0.0022f, (float)-2171.23)));
+    n.v[2] = ss_t(fmaf(f2_lo(wr), 42.f, 0.05f) / (0.05f - -0.05f));
+    n.v[3] = ss_t(fmaf(f2_hi(wr), 42.f, 0.05f) / (0.05f - -0.05f));
     return n;
 }
 
@@ -70,19 +77,23 @@ __device__ MMG_NOISE_INLINE bool cave_biome_is_crystal(int x, int y, int z, floa
 {
     const float px = (float)x, py = (float)y, pz = (float)z;
     const float qx = px * 0.0470f, qy = py * 0.0470f, qz = pz * 0.0470f;
-    const float cx = fmaf(fbm3<3>(qx, qy, qz), 30.f, px);
-    const float cy = fmaf(fbm3<3>(qx + 5923.45f, qy + 4129.42f, qz + 5790.48f), 24.f, py);
-    const float cz = fmaf(fbm3<3>(qx + 1765.68f, qy + 4704.36f, qz + 5692.12f), 30.f, pz);
+    float o1, o2, o3;
+    fbm3_from3<3>(qx, qy, qz, &o1, &o2, &o3);
+    const float cx = fmaf(o1, 30.f, px);
+    const float cy = fmaf(o2, 24.f, py);
+    const float cz = fmaf(o3, 30.f, pz);
     const float rocky = ss_t(fmaf(simplex3_raw<true>(fmaf(cx, 0.0022f, -9193.23f), fmaf(cy, 0.0022f, -6813.39f), fmaf(cz, 0.0022f, (float)-2171.23)), 42.f, 0.05f) / (0.05f - -0.05f));
     if (rocky == 0.f) return false;
     const float nx = cx * 0.2000f, nz = cz * 0.2000f;
     const float top = fmaf(maxHeight + -128.f, 0.15f, 128.f);
-    const float sdStart = fmaf(fbm2<3>(nx + -4921.34f, nz + 8402.13f), 18.f, top + -72.f);
-    const float sdEnd = fmaf(fbm2<3>(nx + 9411.32f, nz + -3921.34f), 7.f, sdStart + -10.f);
+    const f32x2 sd = fbm2x2<3>(f2_make(nx + -4921.34f, nx + 9411.32f), f2_make(nz + 8402.13f, nz + -3921.34f));
+    const float sdStart = fmaf(f2_lo(sd), 18.f, top + -72.f);
+    const float sdEnd = fmaf(f2_hi(sd), 7.f, sdStart + -10.f);
     const float shallow = ss_t((cy - sdEnd) / (sdStart - sdEnd));
     if (shallow == 0.f) return false;
-    const float nsStart = fmaf(fbm2<3>(nx, nz), 23.f, top + -19.f);
-    const float nsEnd = fmaf(fbm2<3>(nx + 3821.34f, nz + 4920.32f), 3.f, nsStart + -5.f);
+    const f32x2 ns = fbm2x2<3>(f2_make(nx, nx + 3821.34f), f2_make(nz, nz + 4920.32f));
+    const float nsStart = fmaf(f2_lo(ns), 23.f, top + -19.f);
+    const float nsEnd = fmaf(f2_hi(ns), 3.f, nsStart + -5.f);
     const float none = ss_t((cy - nsEnd) / (nsStart - nsEnd));
     Minstd rng = make_rng4(x, y, z, seed);
     float rand = rng.u01();
@@ -184,21 +195,37 @@ __device__ __forceinline__ float special_cave_noise_cached(float px, float py, f
     {
         // the whole 3x3x3 neighbourhood is in the table (nearly always): no per-cell bounds tests
         const float* J = shJit + (ux0 * kCaveBox + uy0) * kCaveBox + uz0;
+        // cells two at a time with packed fp32 (mm_arith.cuh): per x the rows y = 0 / y = 1 pair up for each z, the row y = 2 pairs
+        // z = 0 / z = 1 and leaves z = 2 - same sums, same squares; the order of arrival does not matter to insert()
+        const f32x2 nfx2 = f2_dup(nfx), nfy2 = f2_dup(nfy), nfz2 = f2_dup(nfz);
         float ox = -1.f;
 #pragma unroll 1
         for (int x = 0; x < 3; ++x, ox += 1.f)
         {
-            float oy = -1.f;
-#pragma unroll 1
-            for (int y = 0; y < 3; ++y, oy += 1.f)
-            {
-                const float* Jc = J + (x * kCaveBox + y) * kCaveBox;
+            const float* Jc = J + x * kCaveBox * kCaveBox;
+            const f32x2 ox2 = f2_dup(ox), oy01 = f2_make(-1.f, 0.f);
 #pragma unroll
-                for (int z = 0; z < 3; ++z)
-                {
-                    const float dx = nfx + (Jc[z] + ox), dy = nfy + (Jc[z + N3] + oy), dz = nfz + (Jc[z + 2 * N3] + (float)(z - 1));
-                    insert(fmaf(dz, dz, fmaf(dx, dx, dy * dy)));      // dist = sqrtf(this) in the reference
-                }
+            for (int z = 0; z < 3; ++z)
+            {
+                const f32x2 dx = f2_add(nfx2, f2_add(f2_make(Jc[z], Jc[kCaveBox + z]), ox2));
+                const f32x2 dy = f2_add(nfy2, f2_add(f2_make(Jc[z + N3], Jc[kCaveBox + z + N3]), oy01));
+                const f32x2 dz = f2_add(nfz2, f2_add(f2_make(Jc[z + 2 * N3], Jc[kCaveBox + z + 2 * N3]), f2_dup((float)(z - 1))));
+                const f32x2 q = f2_fma(dz, dz, f2_fma(dx, dx, f2_mul(dy, dy)));
+                insert(f2_lo(q));
+                insert(f2_hi(q));
+            }
+            const float* Jr = Jc + 2 * kCaveBox;
+            {
+                const f32x2 dx = f2_add(nfx2, f2_add(f2_make(Jr[0], Jr[1]), ox2));
+                const f32x2 dy = f2_add(nfy2, f2_add(f2_make(Jr[N3], Jr[1 + N3]), f2_dup(1.f)));
+                const f32x2 dz = f2_add(nfz2, f2_add(f2_make(Jr[2 * N3], Jr[1 + 2 * N3]), f2_make(-1.f, 0.f)));
+                const f32x2 q = f2_fma(dz, dz, f2_fma(dx, dx, f2_mul(dy, dy)));
+                insert(f2_lo(q));
+                insert(f2_hi(q));
+            }
+            {
+                const float dx = nfx + (Jr[2] + ox), dy = nfy + (Jr[2 + N3] + 1.f), dz = nfz + (Jr[2 + 2 * N3] + 1.f);
+                insert(fmaf(dz, dz, fmaf(dx, dx, dy * dy)));      // dist = sqrtf(this) in the reference
             }
         }
     }
@@ -245,7 +272,7 @@ __device__ __forceinline__ float cave_thr(const CaveThr& c, float fbmA)
 __device__ __forceinline__ float cave_fbm_a(int wx, int y, int wz)
 {
     const float npx = (float)wx * 0.0050f, npy = (float)y * 0.0050f, npz = (float)wz * 0.0050f;
-    return fbm3<4>(npx * 4.f, npy * 4.f, npz * 4.f);
+    return fbm3_paired<4>(npx * 4.f, npy * 4.f, npz * 4.f);
 }
 // Returns 0 = solid, 1 = air, 2 = the warped specialCaveNoise at (*px, *py, *pz) has to be compared with the threshold *c.
 // hugeZero: the caller has proved that the "huge caves" term is exactly 0 at this voxel (huge_zero_mask below).
@@ -281,9 +308,8 @@ __device__ __forceinline__ int cave_threshold(int wx, int y, int wz, float maxHe
     // test (topRatio -> 0 towards y = 142 - 50 obw) no noise can matter
     if (!(cave_thr(*c, 1.f) > 0.04f)) return 0;
     const float ax = npx * 0.8000f, ay = npy * 0.8000f, az = npz * 0.8000f;
-    const float o1 = fbm3<5>(ax, ay, az);
-    const float o2 = fbm3<5>(ax + 5923.45f, ay + 4129.42f, az + 5790.48f);
-    const float o3 = fbm3<5>(ax + 1765.68f, ay + 4704.36f, az + 5692.12f);
+    float o1, o2, o3;
+    fbm3_from3<5>(ax, ay, az, &o1, &o2, &o3);
     *px = fmaf(o1, 1.8f, npx); *py = fmaf(npy, 1.6f, o2 * 1.8f); *pz = fmaf(o3, 1.8f, npz);
     return 2;
 }

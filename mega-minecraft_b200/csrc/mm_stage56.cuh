@@ -422,6 +422,16 @@ constexpr int kRockQueuePerChunk = 49152;        // rock-queue slots per chunk o
 // consecutive queue entries are consecutive voxels of a column).
 __device__ __forceinline__ int rock_near_cap(int rockQueueCap) { return (rockQueueCap / 3) & ~31; }
 
+// what k_fill_rock / k_fill_lush would do to a rock voxel, in place - a real function so that its registers and spills stay
+// out of k_fill_terrain's main path (it only runs when the rock queue of a batch overflows)
+__device__ __noinline__ uint8_t finish_rock_overflow(uint8_t rb, int wx, int y, int wz, float height, int bd, int td)
+{
+    bool lush = false;
+    uint8_t b = finish_rock_block(rb, wx, y, wz, height, bd, td, &lush);
+    if (lush) b = lush_block(wx, y, wz);
+    return b;
+}
+
 __global__ void __launch_bounds__(kFillSeg, 12) k_fill_terrain(const int* __restrict__ fillList, const int2* __restrict__ origins,
                                                               const float* __restrict__ heightfield, const float* __restrict__ biomeWeights,
                                                               const float* __restrict__ layers, const CaveLayer* __restrict__ caveLayers,
@@ -526,10 +536,8 @@ __global__ void __launch_bounds__(kFillSeg, 12) k_fill_terrain(const int* __rest
                 uint8_t rb; int c2, v2, bd, td;
                 unpack_rock(rec[k], &c2, &v2, &rb, &bd, &td);
                 const int y = k * kFillSeg + t;
-                bool lush = false;
                 // the depths were clamped by pack_rock exactly as the dense kernel sees them
-                blk[k] = finish_rock_block(rb, wx, y, wz, height, bd, td, &lush);
-                if (lush) blk[k] = lush_block(wx, y, wz);
+                blk[k] = finish_rock_overflow(rb, wx, y, wz, height, bd, td);
             }
     }
     // the column's 384 block IDs leave as 24 16-byte vector stores (the column is 384 contiguous, 16-byte aligned bytes).
