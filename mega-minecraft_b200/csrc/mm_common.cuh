@@ -49,7 +49,7 @@ __device__ unsigned long long g_work[W_NUM];
 
 // resident CTAs per SM the register allocator is asked to allow (tuned on a B200)
 #ifndef MMG_CAVES_MINBLOCKS
-#define MMG_CAVES_MINBLOCKS 10
+#define MMG_CAVES_MINBLOCKS 5
 #endif
 #ifndef MMG_ROCK_MINBLOCKS
 #define MMG_ROCK_MINBLOCKS 8

@@ -4,9 +4,9 @@
 //
 // Mapping: k_cave_columns computes the y-independent terms once per column (ocean+beach weight and
 // the whole ravine test: 24 simplex + a 9-cell Worley that the reference re-evaluates for every one
-// of 384 voxels); k_caves then runs one 128-thread CTA per column, three voxels per thread, skips
-// the 2/3 of voxels that are decided by y alone, packs the solid/air column into 12 ballot words,
-// extracts flips with bit scans and evaluates the <= 64 cave-biome lookups in parallel.
+// of 384 voxels); k_caves then runs one 288-thread CTA per pair of columns: the voxels that are not decided by y alone
+// (at most 141 per column) are listed and evaluated one per thread on dense warps, the solid/air columns are kept as
+// 12 words of bits each, flips come from bit scans and the <= 64 cave-biome lookups per column go to a queue.
 // FP32-pipe bound: ~23 simplex3 + 27 hashed cells per evaluated voxel; algorithmic bytes 107 528 B/chunk.
 #pragma once
 #include "mm_surface.cuh"
@@ -15,7 +15,7 @@ namespace mmg {
 
 #ifdef MMG_FEATURE_STATS
 // developer build: voxels whose "huge caves" term was proved 0 but is not (must stay 0); voxels evaluated without / with proof
-__device__ unsigned long long g_hugeMismatch, g_hugeVoxels[2], g_caveWarped, g_cavePending[3];      // g_cavePending: decided by bounds / pending / decided wrongly (must stay 0);      // g_caveWarped: voxels that evaluated the warped specialCaveNoise
+__device__ unsigned long long g_hugeMismatch, g_hugeVoxels[2], g_caveWarped, g_cavePending[3], g_caveTable[2];      // g_caveTable: survivors whose 27 Worley cells were not / were all in the jitter table;      // g_cavePending: decided by bounds / pending / decided wrongly (must stay 0);      // g_caveWarped: voxels that evaluated the warped specialCaveNoise
 #endif
 
 // ---------------------------------------------------------------- cave biome (biomeFuncs.hpp:135-220)
@@ -269,20 +269,26 @@ __device__ __forceinline__ float cave_thr(const CaveThr& c, float fbmA)
     thr = thr * c.hugeFactor;                     // huge == 0: fma(0, 1.4, 1) = 1 and thr * 1 = thr, the same bits
     return c.ratio * thr;
 }
+__device__ __forceinline__ float cave_huge_factor(int wx, int y, int wz)
+{
+    const float npx = (float)wx * 0.0050f, npy = (float)y * 0.0050f, npz = (float)wz * 0.0050f;
+    const float huge = ss_t((fbm3<4>(npx * 0.0700f, npy * 0.0700f, npz * 0.0700f) + -0.2f) / (0.4f - 0.2f));
+    return fmaf(huge, 1.4f, 1.f);
+}
 __device__ __forceinline__ float cave_fbm_a(int wx, int y, int wz)
 {
     const float npx = (float)wx * 0.0050f, npy = (float)y * 0.0050f, npz = (float)wz * 0.0050f;
     return fbm3_paired<4>(npx * 4.f, npy * 4.f, npz * 4.f);
 }
-// Returns 0 = solid, 1 = air, 2 = the warped specialCaveNoise at (*px, *py, *pz) has to be compared with the threshold *c.
-// hugeZero: the caller has proved that the "huge caves" term is exactly 0 at this voxel (huge_zero_mask below).
-__device__ __forceinline__ int cave_threshold(int wx, int y, int wz, float maxHeight, float obw, bool hugeZero, CaveThr* c, float* px, float* py, float* pz)
+// The predicate in two steps. cave_threshold_cheap (no noise): 0 = solid, 1 = air, 2 = "survivor": the noise has to be asked.
+// hugeZero: the caller has proved that the "huge caves" term is exactly 0 at this voxel (huge_zero_mask below); the upper-bound
+// test then needs no noise either.
+__device__ __forceinline__ int cave_threshold_cheap(int y, float maxHeight, float obw, bool hugeZero, CaveThr* c)
 {
     if (y == 0) return 0;
     const int hi = (int)maxHeight;
     if (y > (hi > SEA_LEVEL ? hi : SEA_LEVEL)) return 1;
     const float fy = (float)y;
-    const float npx = (float)wx * 0.0050f, npy = fy * 0.0050f, npz = (float)wz * 0.0050f;
     const float topRatio = ss_t((fmaf(obw, 50.f, fy) + -142.f) / (95.f - 142.f));
     const float bottomRatio = ss_t((fy + -5.f) / (20.f - 5.f));
     // topRatio is exactly 0 from y = 142 - 50 obw upwards; the threshold is (finite * 0) * finite = 0 there and
@@ -290,6 +296,17 @@ __device__ __forceinline__ int cave_threshold(int wx, int y, int wz, float maxHe
     if (topRatio == 0.f) return 0;
     c->ratio = fmaf(bottomRatio, 0.7f, 0.3f) * topRatio;
     c->hugeFactor = 1.f;
+    // the reference always evaluates the warped specialCaveNoise (15 simplex + 27 hashed cells) and then
+    // tests `thr > 0.04 && caveNoise < thr` (chunk.cu:776-783); where even the largest possible threshold fails the first
+    // test (topRatio -> 0 towards y = 142 - 50 obw) no noise can matter
+    if (hugeZero && !(cave_thr(*c, 1.f) > 0.04f)) return 0;
+    return 2;
+}
+// cave_threshold_noise, for survivors: 0 = solid after all, 2 = the warped specialCaveNoise at (*px, *py, *pz) has to be
+// compared with the threshold *c.
+__device__ __forceinline__ int cave_threshold_noise(int wx, int y, int wz, bool hugeZero, CaveThr* c, float* px, float* py, float* pz)
+{
+    const float npx = (float)wx * 0.0050f, npy = (float)y * 0.0050f, npz = (float)wz * 0.0050f;
 #ifdef MMG_FEATURE_STATS
     const bool hugeCheck = hugeZero;      // developer build: evaluate the term anyway and count voxels where the proof was wrong
     hugeZero = false;
@@ -302,11 +319,8 @@ __device__ __forceinline__ int cave_threshold(int wx, int y, int wz, float maxHe
         if (hugeCheck && huge != 0.f) atomicAdd(&g_hugeMismatch, 1ull);
 #endif
         c->hugeFactor = fmaf(huge, 1.4f, 1.f);
+        if (!(cave_thr(*c, 1.f) > 0.04f)) return 0;
     }
-    // the reference always evaluates the warped specialCaveNoise (15 simplex + 27 hashed cells) and then
-    // tests `thr > 0.04 && caveNoise < thr` (chunk.cu:776-783); where even the largest possible threshold fails the first
-    // test (topRatio -> 0 towards y = 142 - 50 obw) no noise can matter
-    if (!(cave_thr(*c, 1.f) > 0.04f)) return 0;
     const float ax = npx * 0.8000f, ay = npy * 0.8000f, az = npz * 0.8000f;
     float o1, o2, o3;
     fbm3_from3<5>(ax, ay, az, &o1, &o2, &o3);
@@ -359,93 +373,107 @@ __global__ void __launch_bounds__(256) k_cave_columns(const int* __restrict__ ch
     cols[(size_t)li * 256 + idx] = c;
 }
 
+// kCaveCols consecutive columns (one chunk row, x = 0 .. 15) per CTA. Only voxels 1 <= y <= 141 can need the noise (topRatio is 0
+// from y = 142 - 50 obw upwards), so the survivors of all the columns - at most 141 each - are listed and the threads walk the
+// list: the noise runs on full warps (one partly filled warp per CTA) and the CTA synchronises four times in all, where one
+// column per 128-thread CTA in 128-voxel slabs spent a whole warp on the few voxels from 128 up and synchronised four times per
+// slab (ncu, profiles/r02_k_caves_v2_src.txt: 26 of 32 lanes active in the noise code, 14 % of the stall samples at one slab
+// barrier). The columns are 0.005 Worley cells apart and share one jitter table.
+// Measured per 128x128-chunk region (profiles/r02_k_caves_columns.txt): 1 column / 128 threads 60.8 ms, 2 / 288 58.9, 4 / 128 52.5,
+// 8 / 256 49.9, 16 / 256 48.6 (5 CTAs per SM; 4: 49.1; 384 threads x 3: 49.4; 512 x 2: 51.7).
 #ifndef MMG_CAVE_COLS
-#define MMG_CAVE_COLS 1
+#define MMG_CAVE_COLS 16
 #endif
-constexpr int kCaveColsPerCta = MMG_CAVE_COLS;
-__global__ void __launch_bounds__(128, MMG_CAVES_MINBLOCKS) k_caves(const int* __restrict__ chunkList, const int2* __restrict__ origins,
+#ifndef MMG_CAVE_THREADS
+#define MMG_CAVE_THREADS 256
+#endif
+constexpr int kCaveCols = MMG_CAVE_COLS, kCaveThreads = MMG_CAVE_THREADS, kCaveSurvivorTop = 141, kCaveListCap = kCaveCols * kCaveSurvivorTop + 32;
+static_assert(256 % kCaveCols == 0 && kCaveCols <= 64, "whole groups of columns per chunk; 6 bits of column in a list entry");
+__global__ void __launch_bounds__(kCaveThreads, MMG_CAVES_MINBLOCKS) k_caves(const int* __restrict__ chunkList, const int2* __restrict__ origins,
                                                const float* __restrict__ heightfield, const CaveColumn* __restrict__ cols,
                                                CaveLayer* __restrict__ caveLayers, uint2* __restrict__ biomeQueue, int* __restrict__ biomeCount,
                                                int biomeQueueCap)
 {
-    __shared__ unsigned int shFilled[13];     // bit y = 1 if solid; word 12 = 0 (y = 384 is "not filled")
-    __shared__ int shFlips[2 * MAX_CAVE_LAYERS];
-    __shared__ int shNumFlips;
-    __shared__ int shBox[6];                  // min corner, max corner of the Worley cells the slab touches
+    __shared__ unsigned int shFilled[kCaveCols][13];  // bit y = 1 if solid; word 12 = 0 (y = 384 is "not filled")
+    __shared__ int shFlips[kCaveThreads / 32][2 * MAX_CAVE_LAYERS];      // per warp
     __shared__ float shJit[3 * kCaveBox * kCaveBox * kCaveBox];
-    __shared__ int shNumPending;              // voxels of the slab whose exact threshold is still needed (cave_threshold)
-    __shared__ unsigned short shPendY[384];
-    __shared__ float shPendNoise[384];
-    __shared__ CaveThr shPendThr[384];
-    noise_tab_stage();
-    const int li = blockIdx.x / (256 / kCaveColsPerCta);
-    const int chunk = chunkList ? chunkList[li] : li;
-    const int2 o = origins[chunk];
-    // kCaveColsPerCta consecutive columns per CTA would stage the 10 KB of noise tables once for all of them (4 % of the
-    // instructions, profiles/r01_k_caves_v8.txt) - measured slower (2, 4, 8 columns: 325 vs 317 ms per 256x256 world: the
-    // staging of one CTA overlaps the arithmetic of the nine others on the SM, the columns of one CTA run one after the other)
-#pragma unroll 1
-    for (int colIt = 0; colIt < kCaveColsPerCta; ++colIt)
-    {
-    const int idx = (blockIdx.x % (256 / kCaveColsPerCta)) * kCaveColsPerCta + colIt;
-    if (colIt) __syncthreads();      // the previous column's shared arrays are free
-    const int wx = o.x + (idx & 15), wz = o.y + (idx >> 4);
-    const float maxHeight = heightfield[(size_t)chunk * 256 + idx];
-    const CaveColumn cc = cols[(size_t)li * 256 + idx];
-    Ravine rav;
-    rav.active = cc.ravActive != 0; rav.top = cc.ravTop; rav.depth = cc.ravDepth;
+    __shared__ int shNumList, shNumPending;
+    __shared__ unsigned short shList[kCaveListCap];      // survivors: column << 9 | y
+    __shared__ unsigned short shPendCY[kCaveListCap];    // voxels whose exact threshold is still needed (cave_fbm_a)
+    __shared__ float shPendNoise[kCaveListCap];          // (their threshold terms are recomputed: a dozen instructions, and 6 bytes per entry let 16 columns fit)
+    __shared__ float shHeight[kCaveCols];
+    __shared__ CaveColumn shCol[kCaveCols];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { shFilled[12] = 0u; shNumPending = 0; }
-    const int hi = (int)maxHeight, yTop = hi > SEA_LEVEL ? hi : SEA_LEVEL;   // above this every voxel is air
-#pragma unroll 1
-    for (int k = 0; k < 3; ++k)
+    const int li = blockIdx.x / (256 / kCaveCols);
+    const int chunk = chunkList ? chunkList[li] : li;
+    const int idx0 = (blockIdx.x % (256 / kCaveCols)) * kCaveCols;      // columns idx0 .. idx0 + kCaveCols - 1: same z, consecutive x
+    if (tid < kCaveCols)
     {
-        if (128 * k > yTop)
+        shHeight[tid] = heightfield[(size_t)chunk * 256 + idx0 + tid];
+        shCol[tid] = cols[(size_t)li * 256 + idx0 + tid];
+    }
+    if (tid == 0) { shNumList = 0; shNumPending = 0; }
+    noise_tab_stage();      // its barrier also publishes the column data above
+    const int2 o = origins[chunk];
+    const int wx0 = o.x + (idx0 & 15), wz0 = o.y + (idx0 >> 4);      // column c of the CTA: x = (idx0 + c) & 15, z = (idx0 + c) >> 4
+    // ---- the Worley jitter table: kCaveBox^3 cells around where the survivors' warped sample positions are expected -
+    // p = pos * 0.005 * (1, 1.6, 1) + 1.8 * fbm3From3, y = 1 .. ~132, |fbm| mostly < 0.5 - chosen BEFORE the noise is known,
+    // so that no barrier separates the noise from the Worley evaluation; a voxel whose 3x3x3 cells are not all in the table
+    // computes the missing jitters in place (special_cave_noise_cached), the result is the same either way.
+    const int bx = (int)floorf((float)wx0 * 0.0050f - 2.5f), by = (int)floorf(0.53f - 2.5f), bz = (int)floorf((float)wz0 * 0.0050f - 2.5f);
+    {
+        constexpr int N3 = kCaveBox * kCaveBox * kCaveBox;
+        for (int i = tid; i < N3; i += kCaveThreads)
         {
-            if (lane == 0) shFilled[4 * k + warp] = 0u;      // the whole slab is air (chunk.cu:761-764)
-            continue;
+            const int uz = i % kCaveBox, r = i / kCaveBox, uy = r % kCaveBox, ux = r / kCaveBox;
+            float jx, jy, jz;
+            cave_cell_jitter(bx + ux, by + uy, bz + uz, &jx, &jy, &jz);
+            shJit[i] = jx; shJit[i + N3] = jy; shJit[i + 2 * N3] = jz;
         }
-        const int y = tid + 128 * k;
-        float px = 0.f, py = 0.f, pz = 0.f;
-        CaveThr ct = {0.f, 1.f};
+    }
+    // ---- every voxel's state without noise: one warp per 32-voxel word of a column
+    for (int wd = warp; wd < 12 * kCaveCols; wd += kCaveThreads / 32)
+    {
+        const int c = wd / 12, y = (wd % 12) * 32 + lane;
+        const CaveColumn& cc = shCol[c];
         const bool hugeZero = y < kHugeRun * kHugeSamples && ((cc.hugeZeroMask >> (y / kHugeRun)) & 1u);
-        const int st = cave_threshold(wx, y, wz, maxHeight, cc.obw, hugeZero, &ct, &px, &py, &pz);
-        // cells [box, box + kCaveBox)^3 cover the 3x3x3 neighbourhoods of (nearly) all undecided voxels. (Filling
-        // the table costs 5 hashes per thread; even for a single undecided voxel that is fewer warp instructions
-        // than its 81 hashes computed in place on one lane - measured.)
-        if (tid < 3) shBox[tid] = INT_MAX;
-        else if (tid < 6) shBox[tid] = INT_MIN;
-        __syncthreads();
-        if (st == 2)
+        CaveThr ct;
+        const int st = cave_threshold_cheap(y, shHeight[c], cc.obw, hugeZero, &ct);
+        // solid voxels fall to the ravine rule (chunk.cu:785-808); survivors count as solid until their noise says otherwise
+        bool solid = st != 1;
+        if (st == 0) solid = !(cc.ravActive != 0 && (cc.ravTop - cc.ravDepth) < (float)y && y != 0);
+        const unsigned int bits = __ballot_sync(0xffffffffu, solid);
+        const unsigned int sv = __ballot_sync(0xffffffffu, st == 2);
+        if (lane == 0) shFilled[c][wd % 12] = bits;
+        if (sv)
         {
-            const int cx = (int)floorf(px), cy = (int)floorf(py), cz = (int)floorf(pz);
-            atomicMin(&shBox[0], cx - 1); atomicMin(&shBox[1], cy - 1); atomicMin(&shBox[2], cz - 1);
-            atomicMax(&shBox[3], cx + 1); atomicMax(&shBox[4], cy + 1); atomicMax(&shBox[5], cz + 1);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&shNumList, __popc(sv));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int slot = base + __popc(sv & ((1u << lane) - 1u));
+            if (st == 2 && slot < kCaveListCap) shList[slot] = (unsigned short)(c << 9 | y);
         }
-        __syncthreads();
-        // only the cells the slab's voxels touch are tabulated (typically 4 x 5 x 4, and 3 x 3 x 3 for the dozen voxels of
-        // the second slab; a full 6 x 6 x 6 table per slab was 13 % of the kernel's instructions), at most kCaveBox per axis
-        const int bx = shBox[0], by = shBox[1], bz = shBox[2];
-        int ex = 0, ey = 0, ez = 0;
-        if (bx != INT_MAX)
-        {
-            constexpr int N3 = kCaveBox * kCaveBox * kCaveBox;
-            ex = min(shBox[3] - bx + 1, kCaveBox); ey = min(shBox[4] - by + 1, kCaveBox); ez = min(shBox[5] - bz + 1, kCaveBox);
-            for (int i = tid; i < ex * ey * ez; i += 128)
-            {
-                const int uz = i % ez, r = i / ez, uy = r % ey, ux = r / ey;
-                const int c = (ux * kCaveBox + uy) * kCaveBox + uz;
-                float jx, jy, jz;
-                cave_cell_jitter(bx + ux, by + uy, bz + uz, &jx, &jy, &jz);
-                shJit[c] = jx; shJit[c + N3] = jy; shJit[c + 2 * N3] = jz;
-            }
-        }
-        __syncthreads();
-        bool air = st == 1, pending = false;
+    }
+    if (tid < kCaveCols) shFilled[tid][12] = 0u;
+    __syncthreads();
+    // ---- the survivors: threshold bounds, the warped sample position, the Worley noise there
+    const int nList = min(shNumList, kCaveListCap);      // only 1 <= y <= 141 survive
+    for (int i = tid; i < nList; i += kCaveThreads)
+    {
+        const int e = shList[i];
+        const int c = e >> 9, y = e & 511;
+        const CaveColumn& cc = shCol[c];
+        const bool hugeZero = y < kHugeRun * kHugeSamples && ((cc.hugeZeroMask >> (y / kHugeRun)) & 1u);
+        CaveThr ct = {0.f, 1.f};
+        float px = 0.f, py = 0.f, pz = 0.f;
+        cave_threshold_cheap(y, shHeight[c], cc.obw, hugeZero, &ct);      // recomputes ratio (a dozen instructions) instead of storing it
+        const int wx = o.x + ((idx0 + c) & 15), wz = o.y + ((idx0 + c) >> 4);
+        const int st = cave_threshold_noise(wx, y, wz, hugeZero, &ct, &px, &py, &pz);
+        bool air = false, pending = false;
         float noise = 0.f;
         if (st == 2)
         {
-            noise = special_cave_noise_cached(px, py, pz, bx, by, bz, ex, ey, ez, shJit);
+            noise = special_cave_noise_cached(px, py, pz, bx, by, bz, kCaveBox, kCaveBox, kCaveBox, shJit);
             const float thrLo = cave_thr(ct, -1.f), thrHi = cave_thr(ct, 1.f);      // thrLo <= thr <= thrHi, thrHi > 0.04 here
             if (noise < thrHi)      // else solid: noise < thr is impossible
             {
@@ -460,44 +488,52 @@ __global__ void __launch_bounds__(128, MMG_CAVES_MINBLOCKS) k_caves(const int* _
                 const float thr = cave_thr(ct, cave_fbm_a(wx, y, wz));
                 if ((thr > 0.04f && noise < thr) != air) atomicAdd(&g_cavePending[2], 1ull);
             }
+            {
+                const int ux0 = (int)floorf(px) - 1 - bx, uy0 = (int)floorf(py) - 1 - by, uz0 = (int)floorf(pz) - 1 - bz;
+                const bool inTable = (unsigned)ux0 <= (unsigned)(kCaveBox - 3) && (unsigned)uy0 <= (unsigned)(kCaveBox - 3) && (unsigned)uz0 <= (unsigned)(kCaveBox - 3);
+                atomicAdd(&g_caveTable[inTable ? 1 : 0], 1ull);
+            }
 #endif
         }
-        if (st != 1 && !air && !pending) air = rav.active && (rav.top - rav.depth) < (float)y && y != 0;   // chunk.cu:785-808
+        if (!air && !pending) air = cc.ravActive != 0 && (cc.ravTop - cc.ravDepth) < (float)y;      // chunk.cu:785-808 (y != 0 here)
+        if (air) atomicAnd(&shFilled[c][y >> 5], ~(1u << (y & 31)));
         // pending voxels (a few per warp) are listed and get their exact threshold on adjacent lanes below; until then solid
-        const unsigned pm = __ballot_sync(0xffffffffu, pending);
-        if (pm)
+        if (pending)
         {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&shNumPending, __popc(pm));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (pending)
-            {
-                const int slot = base + __popc(pm & ((1u << lane) - 1u));
-                shPendY[slot] = (unsigned short)y; shPendNoise[slot] = noise; shPendThr[slot] = ct;
-            }
+            const int slot = atomicAdd(&shNumPending, 1);
+            shPendCY[slot] = (unsigned short)(c << 9 | y); shPendNoise[slot] = noise;
         }
-        const unsigned int bits = __ballot_sync(0xffffffffu, !air);
-        if (lane == 0) shFilled[4 * k + warp] = bits;
-        __syncthreads();      // shBox / shJit are reused by the next slab
-    }
-    // the column's pending voxels (all slabs together: ~26 per column) get their exact threshold on adjacent lanes
-    for (int i = tid; i < shNumPending; i += 128)
-    {
-        const int y2 = shPendY[i];
-        const float thr = cave_thr(shPendThr[i], cave_fbm_a(wx, y2, wz));
-        bool air2 = thr > 0.04f && shPendNoise[i] < thr;
-        if (!air2) air2 = rav.active && (rav.top - rav.depth) < (float)y2;      // y2 != 0: y == 0 never gets here
-        if (air2) atomicAnd(&shFilled[y2 >> 5], ~(1u << (y2 & 31)));
     }
     __syncthreads();
+    // the pending voxels of all columns (~25 each) get their exact threshold on adjacent lanes
+    for (int i = tid; i < shNumPending; i += kCaveThreads)
+    {
+        const int e = shPendCY[i], c2 = e >> 9, y2 = e & 511;
+        const CaveColumn& cc = shCol[c2];
+        const int wx = o.x + ((idx0 + c2) & 15), wz = o.y + ((idx0 + c2) >> 4);
+        const bool hugeZero = y2 < kHugeRun * kHugeSamples && ((cc.hugeZeroMask >> (y2 / kHugeRun)) & 1u);
+        CaveThr ct;
+        cave_threshold_cheap(y2, shHeight[c2], cc.obw, hugeZero, &ct);
+        if (!hugeZero) ct.hugeFactor = cave_huge_factor(wx, y2, wz);      // 0.5 % of the voxels
+        const float thr = cave_thr(ct, cave_fbm_a(wx, y2, wz));
+        bool air2 = thr > 0.04f && shPendNoise[i] < thr;
+        if (!air2) air2 = cc.ravActive != 0 && (cc.ravTop - cc.ravDepth) < (float)y2;      // y2 != 0: y == 0 never gets here
+        if (air2) atomicAnd(&shFilled[c2][y2 >> 5], ~(1u << (y2 & 31)));
+    }
+    __syncthreads();
+    // ---- a warp per column turns the bit column into cave layers
+    for (int c = warp; c < kCaveCols; c += kCaveThreads / 32)
+    {
+    const int idx = idx0 + c, wx = o.x + (idx & 15), wz = o.y + (idx >> 4);
+    const float maxHeight = shHeight[c];
     CaveLayer* out = caveLayers + ((size_t)chunk * 256 + idx) * MAX_CAVE_LAYERS;
-    if (warp == 0)
+    int nflips;
     {
         // flips: filled[y] != filled[y+1]
         unsigned int f = 0u;
         if (lane < 12)
         {
-            const unsigned int w0 = shFilled[lane], w1 = shFilled[lane + 1];
+            const unsigned int w0 = shFilled[c][lane], w1 = shFilled[c][lane + 1];
             f = w0 ^ ((w0 >> 1) | (w1 << 31));
         }
         const int cnt = __popc(f);
@@ -508,28 +544,26 @@ __global__ void __launch_bounds__(128, MMG_CAVES_MINBLOCKS) k_caves(const int* _
             const int v = __shfl_up_sync(0xffffffffu, base, d);
             if (lane >= d) base += v;
         }
-        if (lane == 11) shNumFlips = base;
+        nflips = min(__shfl_sync(0xffffffffu, base, 11), 2 * MAX_CAVE_LAYERS);
         base -= cnt;
         while (f)
         {
             const int b = __ffs(f) - 1;
             f &= f - 1;
-            if (base < 2 * MAX_CAVE_LAYERS) shFlips[base] = 32 * lane + b;
+            if (base < 2 * MAX_CAVE_LAYERS) shFlips[warp][base] = 32 * lane + b;
             ++base;
         }
     }
-    __syncthreads();
-    const int nflips = min(shNumFlips, 2 * MAX_CAVE_LAYERS);
-    if (tid < MAX_CAVE_LAYERS)
+    __syncwarp();
     {
-        // layer t: (start, end] from consecutive flips; the two cave biomes are looked up by k_cave_biomes
-        const int l = tid;
-        const int start = (2 * l < nflips) ? shFlips[2 * l] : 384;
-        const int end = (2 * l + 1 < nflips) ? shFlips[2 * l + 1] : 384;
+        // layer l: (start, end] from consecutive flips; the two cave biomes are looked up by k_cave_biomes
+        const int l = lane;
+        const int start = (2 * l < nflips) ? shFlips[warp][2 * l] : 384;
+        const int end = (2 * l + 1 < nflips) ? shFlips[warp][2 * l + 1] : 384;
         CaveLayer cl;
         cl.start = start; cl.end = end; cl.bottomBiome = CB_NONE; cl.topBiome = CB_NONE; cl.pad[0] = cl.pad[1] = 0;
         const int need = (start != 384 ? 1 : 0) + (end != 384 ? 1 : 0);
-        // warp-aggregated append of this column's lookups (warp 0 holds all 32 layers)
+        // warp-aggregated append of this column's lookups (the warp holds all 32 layers)
         int incl = need;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1)
@@ -555,7 +589,8 @@ __global__ void __launch_bounds__(128, MMG_CAVES_MINBLOCKS) k_caves(const int* _
         }
         out[l] = cl;
     }
-    }      // columns of this CTA
+    __syncwarp();
+    }      // columns of this warp
 }
 
 // getCaveBiome for the bottom / top of every cave layer (chunk.cu:915-935), one queued lookup per thread.

@@ -368,7 +368,7 @@ static int launchCaves(int m, const int* d_list, const int2* d_origins, const fl
         MMG_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
         MMG_TIMED(K_CAVE_COLUMNS, stream, 1, MMG_LAUNCH(k_cave_columns, mb, 256, kNoiseSmemBytes, stream, dl, d_origins + off,
                                                         d_weights + off * NUM_BIOMES * 256, d_cols));
-        MMG_TIMED(K_CAVES, stream, 1, MMG_LAUNCH(k_caves, mb * (256 / kCaveColsPerCta), 128, kNoiseSmemBytes, stream, dl, d_origins + off, d_height + off * 256,
+        MMG_TIMED(K_CAVES, stream, 1, MMG_LAUNCH(k_caves, mb * (256 / kCaveCols), kCaveThreads, kNoiseSmemBytes, stream, dl, d_origins + off, d_height + off * 256,
                                                  (const CaveColumn*)d_cols, d_caves + off * 256 * MAX_CAVE_LAYERS, d_queue, d_count, kCaveBiomeQueueCap));
         MMG_TIMED(K_CAVE_BIOMES, stream, 1, MMG_LAUNCH(k_cave_biomes, kNumSMs * 16, 128, kNoiseSmemBytes, stream, d_origins + off, d_height + off * 256,
                                                        (const uint2*)d_queue, (const int*)d_count, kCaveBiomeQueueCap, d_caves + off * 256 * MAX_CAVE_LAYERS));
@@ -1540,7 +1540,8 @@ extern "C" int mmgen_debug_feature_stats(unsigned long long* out)
 }
 // out[0] = voxels where huge_zero_mask's proof was wrong (must be 0), out[1] / out[2] = threshold voxels without / with proof,
 // out[3] = voxels that went on to the warped specialCaveNoise, out[4] / out[5] = of those: decided by the threshold bounds /
-// needing the exact threshold, out[6] = decided wrongly by the bounds (must be 0)
+// needing the exact threshold, out[6] = decided wrongly by the bounds (must be 0), out[7] / out[8] = Worley evaluations with
+// cells outside / all cells inside the CTA's jitter table
 extern "C" int mmgen_debug_huge_stats(unsigned long long* out)
 {
     MMG_CUDA(cudaDeviceSynchronize());
@@ -1548,6 +1549,7 @@ extern "C" int mmgen_debug_huge_stats(unsigned long long* out)
     MMG_CUDA(cudaMemcpyFromSymbol(out + 1, g_hugeVoxels, 2 * sizeof(unsigned long long)));
     MMG_CUDA(cudaMemcpyFromSymbol(out + 3, g_caveWarped, sizeof(unsigned long long)));
     MMG_CUDA(cudaMemcpyFromSymbol(out + 4, g_cavePending, 3 * sizeof(unsigned long long)));
+    MMG_CUDA(cudaMemcpyFromSymbol(out + 7, g_caveTable, 2 * sizeof(unsigned long long)));
     return 0;
 }
 #endif

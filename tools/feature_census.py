@@ -32,7 +32,7 @@ for i in range(64):
 print("%-30s %8s %12s %12s %12s" % ("type", "rast.%", "pairs", "rasterised", "hits"))
 for c, n, a, b, h in sorted(rows, key=lambda r: -r[3]):
     print("%-30s %7.1f%% %12d %12d %12d" % (n, 100 * b / tot, a, b, h))
-hs = np.zeros(7, np.uint64)
+hs = np.zeros(9, np.uint64)
 gen.L.mmgen_debug_huge_stats(hs.ctypes.data_as(ctypes.c_void_p))
 print("huge-caves term: proved zero for %d of %d threshold voxels (%.1f %%), proof wrong for %d (must be 0)"
       % (hs[2], hs[1] + hs[2], 100.0 * float(hs[2]) / max(float(hs[1] + hs[2]), 1.0), hs[0]))
@@ -43,3 +43,5 @@ print("k_caves: algorithmic voxels (0 < y <= max(h, 128)) %d, threshold evaluate
       % (alg, hs[1] + hs[2], float(hs[1] + hs[2]) / alg, hs[3], float(hs[3]) / alg))
 print("k_caves threshold bounds: %d voxels decided without fbmA, %d needed it (%.1f %%), decided wrongly %d (must be 0)"
       % (hs[4], hs[5], 100.0 * float(hs[5]) / max(float(hs[4] + hs[5]), 1.0), hs[6]))
+print("k_caves jitter table: %d Worley evaluations had all 27 cells in the CTA's table, %d did not (%.2f %%)"
+      % (hs[8], hs[7], 100.0 * float(hs[7]) / max(float(hs[7] + hs[8]), 1.0)))
