@@ -142,15 +142,17 @@ __device__ __forceinline__ Ravine ravine_column(int wx, int wz, float obw)
 {
     Ravine r = {false, 0.f, 0.f};
     const float rx = (float)wx * 0.0015f, rz = (float)wz * 0.0015f;
-    const float ox = fbm2<4>(rx * 10.f, rz * 10.f), oz = fbm2<4>(rx * 10.f + 5923.45f, rz * 10.f + 4129.42f);
+    const f32x2 oxz = fbm2x2<4>(f2_make(rx * 10.f, rx * 10.f + 5923.45f), f2_make(rz * 10.f, rz * 10.f + 4129.42f));      // noise in pairs (mm_arith.cuh)
+    const float ox = f2_lo(oxz), oz = f2_hi(oxz);
     const Worley2 w = worley2(fmaf(ox, 0.03f, rx), fmaf(oz, 0.03f, rz));
     const float thr = (1.f - obw) * 0.12f;
     if (!(w.d1 < thr)) return r;
     const float colorX = hash_fract(fmaf(w.cpx, 238.68f, w.cpy * 491.28f));
     r.top = fmaf(colorX, 24.f, 120.f);
     const float ratio = 1.f - (w.d1 / thr);
-    float depth = ss_t(ratio / 0.3f) * fmaf(fbm2<4>(fmaf(rx, 8.f, 8391.32f), fmaf(rz, 8.f, 4821.39f)), 26.f, 60.f);
-    const float waveOff = fbm2<4>(fmaf(rx, 3.f, 5129.32f), fmaf(rz, 3.f, 1392.49f)) * 4.f;
+    const f32x2 dw = fbm2x2<4>(f2_make(fmaf(rx, 8.f, 8391.32f), fmaf(rx, 3.f, 5129.32f)), f2_make(fmaf(rz, 8.f, 4821.39f), fmaf(rz, 3.f, 1392.49f)));
+    float depth = ss_t(ratio / 0.3f) * fmaf(f2_lo(dw), 26.f, 60.f);
+    const float waveOff = f2_hi(dw) * 4.f;
     const float wave = sinf(fmaf(rx + rz, 15.f, waveOff));
     depth = depth * ss_t((wave + -0.4f) / (0.6f - 0.4f));
     r.depth = depth;
@@ -272,7 +274,7 @@ __device__ __forceinline__ float cave_thr(const CaveThr& c, float fbmA)
 __device__ __forceinline__ float cave_huge_factor(int wx, int y, int wz)
 {
     const float npx = (float)wx * 0.0050f, npy = (float)y * 0.0050f, npz = (float)wz * 0.0050f;
-    const float huge = ss_t((fbm3<4>(npx * 0.0700f, npy * 0.0700f, npz * 0.0700f) + -0.2f) / (0.4f - 0.2f));
+    const float huge = ss_t((fbm3_paired<4>(npx * 0.0700f, npy * 0.0700f, npz * 0.0700f) + -0.2f) / (0.4f - 0.2f));
     return fmaf(huge, 1.4f, 1.f);
 }
 __device__ __forceinline__ float cave_fbm_a(int wx, int y, int wz)
@@ -314,7 +316,7 @@ __device__ __forceinline__ int cave_threshold_noise(int wx, int y, int wz, bool 
 #endif
     if (!hugeZero)
     {
-        const float huge = ss_t((fbm3<4>(npx * 0.0700f, npy * 0.0700f, npz * 0.0700f) + -0.2f) / (0.4f - 0.2f));
+        const float huge = ss_t((fbm3_paired<4>(npx * 0.0700f, npy * 0.0700f, npz * 0.0700f) + -0.2f) / (0.4f - 0.2f));
 #ifdef MMG_FEATURE_STATS
         if (hugeCheck && huge != 0.f) atomicAdd(&g_hugeMismatch, 1ull);
 #endif
@@ -348,7 +350,7 @@ __device__ __forceinline__ unsigned huge_zero_mask(int wx, int wz)
     for (int s = 0; s < kHugeSamples; ++s)
     {
         const float npy = (float)(kHugeRun * s + kHugeRun / 2) * 0.0050f;
-        if (fbm3<4>(npx * 0.0700f, npy * 0.0700f, npz * 0.0700f) <= limit) mask |= 1u << s;
+        if (fbm3_paired<4>(npx * 0.0700f, npy * 0.0700f, npz * 0.0700f) <= limit) mask |= 1u << s;
     }
     return mask;
 }
@@ -438,7 +440,14 @@ __global__ void __launch_bounds__(kCaveThreads, MMG_CAVES_MINBLOCKS) k_caves(con
         const CaveColumn& cc = shCol[c];
         const bool hugeZero = y < kHugeRun * kHugeSamples && ((cc.hugeZeroMask >> (y / kHugeRun)) & 1u);
         CaveThr ct;
-        const int st = cave_threshold_cheap(y, shHeight[c], cc.obw, hugeZero, &ct);
+        int st;
+        if (y >= 160)      // warp-uniform: topRatio is 0 from y = 142 up, only "above the terrain and the sea" is left to ask
+        {
+            const int hi = (int)shHeight[c];
+            st = y > (hi > SEA_LEVEL ? hi : SEA_LEVEL) ? 1 : 0;
+        }
+        else
+            st = cave_threshold_cheap(y, shHeight[c], cc.obw, hugeZero, &ct);
         // solid voxels fall to the ravine rule (chunk.cu:785-808); survivors count as solid until their noise says otherwise
         bool solid = st != 1;
         if (st == 0) solid = !(cc.ravActive != 0 && (cc.ravTop - cc.ravDepth) < (float)y && y != 0);
