@@ -392,10 +392,9 @@ __global__ void k_gather_info(const FeaturePlacement* __restrict__ gF, const Cav
 
 // kernFill (chunk.cu:1382-1510) as a sequence of kernels over one batch of chunks. fillList[li] = chunk index into
 // the resident planes (or li itself); gathered lists are indexed by li with the given strides.
-//   k_fill_terrain   chunkFillPlaceBlock for every voxel up to the cave-biome step: one CTA per column, three 128-voxel
-//                    segments per thread (y fastest => a warp stores 32 consecutive block IDs); segments above the
-//                    terrain and the sea are stored as AIR without further work. STONE / DEEPSLATE / BLACKSTONE
-//                    voxels - the only ones getCaveBiome can change - are queued (near / bulk regions).
+//   k_fill_terrain   chunkFillPlaceBlock for every voxel up to the cave-biome step: one CTA per chunk row (16 columns), the
+//                    voxels that are not above the terrain and the sea walked as one dense list; STONE / DEEPSLATE /
+//                    BLACKSTONE voxels - the only ones getCaveBiome can change - are queued (near / bulk regions).
 //   k_fill_rock      getCaveBiome + caveBiomeBlockPostProcess for the queued voxels, one per thread on dense warps;
 //                    bulk voxels first decide what CRYSTAL_CAVES would do to them. Voxels that need the LUSH_CAVES
 //                    clay / moss decision are queued once more.
@@ -409,17 +408,12 @@ __global__ void k_gather_info(const FeaturePlacement* __restrict__ gF, const Cav
 // The reference decides terrain and features in one pass per voxel; the feature test only looks at
 // whether the terrain block is AIR, which the lush decision does not change, so the order
 // terrain -> lush -> features gives the same blocks.
-constexpr int kFillSeg = 128;
 constexpr int kLushQueueCap = 1 << 22;           // queued voxels per fill batch (overflow is decided in place)
 constexpr int kRockQueuePerChunk = 49152;        // rock-queue slots per chunk of a fill batch (typical need ~30 k; overflow is decided in place)
 
 // counters of one fill batch: [0] lush queue length, [2] near-rock queue length, [3] bulk-rock queue length ([2..3] are
 // advanced together by one 64-bit atomic). The rock queue has two regions: [0, nearCap) for voxels within 6 blocks of a
 // cave floor / ceiling (full getCaveBiome), [nearCap, nearCap + bulkCap) for bulk voxels (only CRYSTAL_CAVES matters).
-// One CTA per column, three 128-voxel segments per thread: the column data (24 weights, 21 layer heights, 32 cave
-// layers) is staged once, the simplex tables only if the column can draw a surface biome whose pre/post-process
-// uses noise, and the column's rock voxels take one atomic to reserve their queue slots (segment-major, so that
-// consecutive queue entries are consecutive voxels of a column).
 __device__ __forceinline__ int rock_near_cap(int rockQueueCap) { return (rockQueueCap / 3) & ~31; }
 
 // what k_fill_rock / k_fill_lush would do to a rock voxel, in place - a real function so that its registers and spills stay
@@ -432,124 +426,197 @@ __device__ __noinline__ uint8_t finish_rock_overflow(uint8_t rb, int wx, int y, 
     return b;
 }
 
-__global__ void __launch_bounds__(kFillSeg, 12) k_fill_terrain(const int* __restrict__ fillList, const int2* __restrict__ origins,
+// ---- k_fill_terrain, one CTA per chunk ROW (16 columns x = 0 .. 15 of one z): the voxels that are not "above the terrain
+// and the sea" are walked as one dense list by 384 threads. Against one 128-thread CTA per column: the row's column data
+// (24 weights, 21 layer heights, 32 cave layers per column) arrives by coalesced loads once, the rock voxels of 16 columns
+// take ONE queue reservation whose round trip is overlapped with the row's 6 KB of output stores, and the lanes of a warp
+// are consecutive voxels that all need work (ncu of the per-column kernel, profiles/r02_k_fill_terrain_v1_src.txt: 45 % of the
+// stall samples at the two barriers around the column loads and the queue atomic, 24.5 of 32 lanes active).
+// Measured per 128x128-chunk region (profiles/r02_k_fill_terrain_rows.txt): per column 15.9 ms; rows with 256 threads x 3 / 4 / 5
+// CTAs per SM 15.4 / 12.9 / 12.1; 320 x 5 11.7; 384 x 4 / 5 11.3 / 11.0; 512 x 4 11.0 - the kernel is latency-bound and wants
+// resident warps more than registers (32 per thread at 384 x 5).
+#ifndef MMG_TERRAIN_THREADS
+#define MMG_TERRAIN_THREADS 384
+#endif
+constexpr int kRowCols = 16, kRowThreads = MMG_TERRAIN_THREADS;
+__global__ void __launch_bounds__(kRowThreads, MMG_TERRAIN_MINBLOCKS) k_fill_terrain(const int* __restrict__ fillList, const int2* __restrict__ origins,
                                                               const float* __restrict__ heightfield, const float* __restrict__ biomeWeights,
                                                               const float* __restrict__ layers, const CaveLayer* __restrict__ caveLayers,
                                                               uint8_t* __restrict__ blocks, uint2* __restrict__ rockQueue, int rockQueueCap,
-                                                              uint2* __restrict__ lushQueue, int* __restrict__ counters)
+                                                              int* __restrict__ counters)
 {
-    constexpr int NW = kFillSeg / 32;
-    __shared__ float shW[NUM_BIOMES];
-    __shared__ float shLH[NUM_MATERIALS + 1];
-    __shared__ CaveLayer shCL[MAX_CAVE_LAYERS];
-    __shared__ int shCnt[2][3 * NW], shBase[2];
-    __shared__ ColumnBiomes shCB;
-    const int col = blockIdx.x;
-    const int li = col >> 8, idx = col & 255;
+    __shared__ float shW[kRowCols][NUM_BIOMES];
+    __shared__ float shLH[kRowCols][NUM_MATERIALS + 1];
+    __shared__ __align__(16) CaveLayer shCL[kRowCols][MAX_CAVE_LAYERS];
+    __shared__ ColumnBiomes shCB[kRowCols];
+    __shared__ int shStart[kRowCols + 1];                 // dense voxel list: column c owns [shStart[c], shStart[c + 1])
+    __shared__ __align__(16) uint8_t shOut[kRowCols * 384];
+    __shared__ unsigned short shRock[kRowCols * 384];     // per visited voxel: 0 = not rock, else 0x8000 | bottom depth << 6 | top depth (clamped as pack_rock does)
+    __shared__ int shCount[2], shLocal[2], shBase[2], shFlags;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int li = blockIdx.x >> 4, row = blockIdx.x & 15;
     const int chunk = fillList ? fillList[li] : li;
-    const int t = threadIdx.x;
-    const float height = heightfield[(size_t)chunk * 256 + idx];
-    uint8_t* out = blocks + (size_t)chunk * 98304 + (size_t)idx * 384;
-    if (t < NUM_BIOMES) shW[t] = biomeWeights[(size_t)chunk * (NUM_BIOMES * 256) + t * 256 + idx];
-    else if (t < NUM_BIOMES + NUM_MATERIALS) shLH[t - NUM_BIOMES] = layers[(size_t)chunk * (NUM_MATERIALS * 256) + (t - NUM_BIOMES) * 256 + idx];
-    else if (t == NUM_BIOMES + NUM_MATERIALS) shLH[NUM_MATERIALS] = height;
-    else if (t < NUM_BIOMES + NUM_MATERIALS + 1 + MAX_CAVE_LAYERS)
-        shCL[t - (NUM_BIOMES + NUM_MATERIALS + 1)] = caveLayers[((size_t)chunk * 256 + idx) * MAX_CAVE_LAYERS + (t - (NUM_BIOMES + NUM_MATERIALS + 1))];
-    const int2 o = origins[chunk];
-    const int wx = o.x + (idx & 15), wz = o.y + (idx >> 4);
-    __syncthreads();
-    // biomePre/PostProcess evaluate simplex noise for these biomes only (biomeFuncs.hpp:385-590); random_biome can only
-    // return a biome of weight 0 when it is CORAL_REEF (rand == 0) or the PLAINS fallback, neither of which uses noise
-    const bool needNoise = shW[ARCHIPELAGO] > 0.f || shW[MESA] > 0.f || shW[SHREKS_SWAMP] > 0.f || shW[TIANZI_MOUNTAINS] > 0.f ||
-                           shW[MOUNTAINS] > 0.f || shW[CRYSTALS] > 0.f;
-    const int lane = t & 31, warp = t >> 5;
-    if (warp == 0)
+    const int idx0 = row * kRowCols;
+    // ---- the row's column data, coalesced: 16 consecutive floats per biome / material plane, 6 KB of contiguous cave layers
+    for (int i = t; i < NUM_BIOMES * kRowCols; i += kRowThreads)
+        shW[i & 15][i >> 4] = biomeWeights[(size_t)chunk * (NUM_BIOMES * 256) + (i >> 4) * 256 + idx0 + (i & 15)];
+    for (int i = t; i < NUM_MATERIALS * kRowCols; i += kRowThreads)
+        shLH[i & 15][i >> 4] = layers[(size_t)chunk * (NUM_MATERIALS * 256) + (i >> 4) * 256 + idx0 + (i & 15)];
     {
-        // the column's biomes of non-zero weight, in index order, and isOcean (chunk.cu:1225-1231)
-        const float wgt = lane < NUM_BIOMES ? shW[lane] : 0.f;
+        static_assert(sizeof(CaveLayer) == 12 && (kRowCols * MAX_CAVE_LAYERS * 12) % 16 == 0, "cave layers of a row are copied as uint4");
+        const uint4* src = reinterpret_cast<const uint4*>(caveLayers + ((size_t)chunk * 256 + idx0) * MAX_CAVE_LAYERS);
+        uint4* dst = reinterpret_cast<uint4*>(&shCL[0][0]);
+        for (int i = t; i < kRowCols * MAX_CAVE_LAYERS * 12 / 16; i += kRowThreads) dst[i] = src[i];
+    }
+    for (int i = t; i < kRowCols * 384 / 16; i += kRowThreads) reinterpret_cast<uint4*>(shOut)[i] = make_uint4(0u, 0u, 0u, 0u);      // B_AIR == 0
+    static_assert(B_AIR == 0, "the row buffer starts as air");
+    if (t < kRowCols) shLH[t][NUM_MATERIALS] = heightfield[(size_t)chunk * 256 + idx0 + t];
+    if (t == 0) { shCount[0] = shCount[1] = 0; shLocal[0] = shLocal[1] = 0; shFlags = 0; }
+    const int2 o = origins[chunk];
+    const int wz = o.y + row;
+    __syncthreads();
+    // ---- per column (two per warp): the biomes of non-zero weight in index order, isOcean (chunk.cu:1225-1231); does any column
+    // need the simplex tables? biomePre/PostProcess evaluate noise for these biomes only (biomeFuncs.hpp:385-590); random_biome
+    // can only return a biome of weight 0 when it is CORAL_REEF (rand == 0) or the PLAINS fallback, neither of which uses noise
+    for (int c = warp; c < kRowCols; c += kRowThreads / 32)
+    {
+        const float wgt = lane < NUM_BIOMES ? shW[c][lane] : 0.f;
         const unsigned nz = __ballot_sync(0xffffffffu, wgt != 0.f);
         if (wgt != 0.f)
         {
             const int slot = __popc(nz & ((1u << lane) - 1u));
-            shCB.biome[slot] = (uint8_t)lane;
-            shCB.weight[slot] = wgt;
+            shCB[c].biome[slot] = (uint8_t)lane;
+            shCB[c].weight[slot] = wgt;
         }
         const unsigned ocean = __ballot_sync(0xffffffffu, lane < NUM_OCEAN_BIOMES && wgt > 0.f);
-        if (lane == 0) { shCB.n = __popc(nz); shCB.isOcean = ocean != 0u; }
-    }
-    if (needNoise) noise_tab_stage();
-    else __syncthreads();
-    const int nearCap = rock_near_cap(rockQueueCap), bulkCap = rockQueueCap - nearCap;
-    uint8_t blk[3];
-    uint2 rec[3];
-    unsigned ballots[3];
-    int cls[3];                 // -1 not rock, 0 near, 1 bulk
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-    {
-        const int y0 = k * kFillSeg, y = y0 + t;
-        bool rock = false;
-        int bd = -384, td = -384;
-        // chunkFillPlaceBlock's first exit (chunk.cu:1213-1217) for a whole segment above the terrain and the sea
-        blk[k] = ((float)y0 > height && y0 > SEA_LEVEL) ? (uint8_t)B_AIR : fill_place_block(shCB, shLH, shCL, y, height, wx, wz, &rock, &bd, &td);
-        rec[k] = rock ? pack_rock(chunk, idx * 384 + y, blk[k], bd, td) : make_uint2(0xffffffffu, 0u);
-        cls[k] = rock ? (rock_is_bulk(bd, td) ? 1 : 0) : -1;
-        const unsigned bNear = __ballot_sync(0xffffffffu, cls[k] == 0), bBulk = __ballot_sync(0xffffffffu, cls[k] == 1);
-        ballots[k] = cls[k] == 1 ? bBulk : bNear;
-        if (lane == 0) { shCnt[0][k * NW + warp] = __popc(bNear); shCnt[1][k * NW + warp] = __popc(bBulk); }
-    }
-    __syncthreads();
-    if (t == 0)
-    {
-        unsigned nNear = 0, nBulk = 0;
-#pragma unroll
-        for (int w = 0; w < 3 * NW; ++w) { nNear += shCnt[0][w]; nBulk += shCnt[1][w]; }
-        unsigned long long old = 0ull;
-        if (nNear | nBulk) old = atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), (unsigned long long)nBulk << 32 | nNear);
-        shBase[0] = (int)(unsigned)(old & 0xffffffffull);
-        shBase[1] = (int)(unsigned)(old >> 32);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-    {
-        if (cls[k] >= 0)
+        const unsigned noisy = __ballot_sync(0xffffffffu, wgt > 0.f && (lane == ARCHIPELAGO || lane == MESA || lane == SHREKS_SWAMP || lane == TIANZI_MOUNTAINS ||
+                                                                         lane == MOUNTAINS || lane == CRYSTALS));
+        if (lane == 0)
         {
-            const int q = cls[k];
-            int slot = shBase[q] + __popc(ballots[k] & ((1u << lane) - 1u));
-            for (int w = 0; w < k * NW + warp; ++w) slot += shCnt[q][w];
-            if (slot < (q ? bulkCap : nearCap)) rockQueue[(q ? nearCap : 0) + slot] = rec[k];
-            else blk[k] = 0xff;      // queue full (no block id is 0xff): resolved below, once the whole CTA has staged the tables
+            shCB[c].n = __popc(nz); shCB[c].isOcean = ocean != 0u;
+            if (noisy) atomicOr(&shFlags, 1);
         }
     }
-    // overflow path (rare: the batch has more rock voxels than queue slots): same result, on sparse warps
-    bool anyOverflow = false;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) anyOverflow = anyOverflow || blk[k] == 0xff;
-    if (__syncthreads_or(anyOverflow ? 1 : 0))
+    if (warp == 0)
     {
-        if (!needNoise) noise_tab_stage();
+        // voxels of column c that are not "above the terrain and the sea" (chunkFillPlaceBlock's first exit, chunk.cu:1213-1217):
+        // y <= 128 or y <= height
+        int n = 0;
+        if (lane < kRowCols)
+        {
+            const float h = shLH[lane][NUM_MATERIALS];
+            int top = SEA_LEVEL;
+            if (h > (float)SEA_LEVEL) top = min(383, (int)floorf(h));      // the largest y with (float)y <= h
+            n = top + 1;
+        }
+        int incl = n;
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-            if (blk[k] == 0xff)
-            {
-                uint8_t rb; int c2, v2, bd, td;
-                unpack_rock(rec[k], &c2, &v2, &rb, &bd, &td);
-                const int y = k * kFillSeg + t;
-                // the depths were clamped by pack_rock exactly as the dense kernel sees them
-                blk[k] = finish_rock_overflow(rb, wx, y, wz, height, bd, td);
-            }
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane < kRowCols) shStart[lane + 1] = incl;
+        if (lane == 0) shStart[0] = 0;
     }
-    // the column's 384 block IDs leave as 24 16-byte vector stores (the column is 384 contiguous, 16-byte aligned bytes).
-    // Measured (round 2, profiles/r02_variants.txt): the same time as three one-byte stores per thread - the kernel is bound by
-    // the per-voxel logic, not by its 96 KB of stores per chunk; 2 or 4 columns per CTA with one queue reservation are slower
-    // (17.7 / 21.3 ms against 15.3 per 128x128 region: fewer resident CTAs to hide the staging latency).
-    __shared__ __align__(16) uint8_t shOut[384];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) shOut[k * kFillSeg + t] = blk[k];
     __syncthreads();
-    if (t < 24) reinterpret_cast<uint4*>(out)[t] = reinterpret_cast<const uint4*>(shOut)[t];
-    (void)lushQueue;
+    const bool needNoise = (shFlags & 1) != 0;
+    if (needNoise) noise_tab_stage();
+    const int total = shStart[kRowCols];
+    // ---- pass 1: the block of every listed voxel; rock voxels (the only ones getCaveBiome can change) are marked
+    for (int i0 = warp * 32; i0 < total; i0 += kRowThreads)
+    {
+        const int i = i0 + lane;
+        int cls = -1;
+        if (i < total)
+        {
+            int c = 0;
+#pragma unroll
+            for (int d = 8; d > 0; d >>= 1) if (shStart[c + d] <= i) c += d;
+            const int y = i - shStart[c];
+            const float height = shLH[c][NUM_MATERIALS];
+            bool rock = false;
+            int bd = -384, td = -384;
+            const uint8_t blk = fill_place_block(shCB[c], shLH[c], shCL[c], y, height, o.x + c, wz, &rock, &bd, &td);
+            shOut[c * 384 + y] = blk;
+            unsigned short info = 0;
+            if (rock)
+            {
+                const unsigned b6 = (bd < 0 || bd > 62) ? 63u : (unsigned)bd, t6 = (td < 0 || td > 62) ? 63u : (unsigned)td;
+                info = (unsigned short)(0x8000u | b6 << 6 | t6);
+                cls = rock_is_bulk(bd, td) ? 1 : 0;
+            }
+            shRock[c * 384 + y] = info;
+        }
+        const unsigned bNear = __ballot_sync(0xffffffffu, cls == 0), bBulk = __ballot_sync(0xffffffffu, cls == 1);
+        if (lane == 0)
+        {
+            if (bNear) atomicAdd(&shCount[0], __popc(bNear));
+            if (bBulk) atomicAdd(&shCount[1], __popc(bBulk));
+        }
+    }
+    __syncthreads();
+    // ---- one reservation for the row's rock voxels; its round trip overlaps the row's output stores
+    const int nearCap = rock_near_cap(rockQueueCap), bulkCap = rockQueueCap - nearCap;
+    unsigned long long old = 0ull;
+    const unsigned nNear = (unsigned)shCount[0], nBulk = (unsigned)shCount[1];
+    if (t == 0 && (nNear | nBulk)) old = atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), (unsigned long long)nBulk << 32 | nNear);
+    {
+        uint4* out = reinterpret_cast<uint4*>(blocks + (size_t)chunk * 98304 + (size_t)idx0 * 384);      // 16 columns = 6144 contiguous bytes
+        for (int i = t; i < kRowCols * 384 / 16; i += kRowThreads) out[i] = reinterpret_cast<const uint4*>(shOut)[i];
+    }
+    if (t == 0)
+    {
+        shBase[0] = (int)(unsigned)(old & 0xffffffffull);
+        shBase[1] = (int)(unsigned)(old >> 32);
+        if (shBase[0] + (int)nNear > nearCap || shBase[1] + (int)nBulk > bulkCap) shFlags |= 2;      // some voxel will not fit the queue
+    }
+    __syncthreads();
+    const bool overflow = (shFlags & 2) != 0;
+    if (overflow && !needNoise) noise_tab_stage();      // the in-place path below evaluates noise
+    // ---- pass 2: the marked voxels go to the queue (near / bulk regions)
+    for (int i0 = warp * 32; i0 < total; i0 += kRowThreads)
+    {
+        const int i = i0 + lane;
+        int cls = -1, c = 0, y = 0;
+        unsigned info = 0;
+        if (i < total)
+        {
+#pragma unroll
+            for (int d = 8; d > 0; d >>= 1) if (shStart[c + d] <= i) c += d;
+            y = i - shStart[c];
+            info = shRock[c * 384 + y];
+            if (info)
+            {
+                const unsigned b6 = (info >> 6) & 63u, t6 = info & 63u;
+                cls = (b6 > 6u && t6 > 6u) ? 1 : 0;      // rock_is_bulk on the clamped depths: 63 stands for "negative or beyond 62"
+            }
+        }
+        const unsigned bNear = __ballot_sync(0xffffffffu, cls == 0), bBulk = __ballot_sync(0xffffffffu, cls == 1);
+        int baseN = 0, baseB = 0;
+        if (lane == 0)
+        {
+            if (bNear) baseN = atomicAdd(&shLocal[0], __popc(bNear));
+            if (bBulk) baseB = atomicAdd(&shLocal[1], __popc(bBulk));
+        }
+        baseN = __shfl_sync(0xffffffffu, baseN, 0); baseB = __shfl_sync(0xffffffffu, baseB, 0);
+        if (cls >= 0)
+        {
+            const uint8_t blk = shOut[c * 384 + y];
+            const int idx = idx0 + c;
+            const unsigned kind = blk == B_STONE ? 0u : (blk == B_DEEPSLATE ? 1u : 2u);
+            const uint2 rec = make_uint2((unsigned)chunk, (unsigned)(idx * 384 + y) | kind << 17 | ((info >> 6) & 63u) << 19 | (info & 63u) << 25);      // == pack_rock
+            const int slot = cls ? shBase[1] + baseB + __popc(bBulk & ((1u << lane) - 1u)) : shBase[0] + baseN + __popc(bNear & ((1u << lane) - 1u));
+            if (slot < (cls ? bulkCap : nearCap)) rockQueue[(cls ? nearCap : 0) + slot] = rec;
+            else
+            {
+                // queue full (rare: the batch has more rock voxels than queue slots): same result, in place
+                uint8_t rb; int c2, v2, bd, td;
+                unpack_rock(rec, &c2, &v2, &rb, &bd, &td);
+                blocks[(size_t)chunk * 98304 + (size_t)idx * 384 + y] = finish_rock_overflow(rb, o.x + c, y, wz, shLH[c][NUM_MATERIALS], bd, td);
+            }
+        }
+    }
 }
 
 // getCaveBiome + caveBiomeBlockPostProcess for the queued rock voxels, one per thread on dense warps. In k_fill_terrain

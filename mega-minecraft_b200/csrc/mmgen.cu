@@ -412,9 +412,9 @@ static int launchFill(int m, const int* d_list, const int2* d_origins, const flo
 {
     const int rockCap = (int)std::min<size_t>((size_t)m * g_rockQueuePerChunk, (size_t)kFillBatch * kRockQueuePerChunk);
     MMG_CUDA(cudaMemsetAsync(d_counters, 0, 4 * sizeof(int), stream));
-    MMG_TIMED(K_FILL_TERRAIN, stream, 1, MMG_LAUNCH(k_fill_terrain, m * 256, kFillSeg, kNoiseSmemBytes, stream, d_list, d_origins, d_height,
-                                                    d_weights, d_layers, d_caves, d_blocks, d_rockQueue, rockCap, d_lushQueue, d_counters));
-    MMG_TIMED(K_FILL_ROCK, stream, 1, MMG_LAUNCH(k_fill_rock, kNumSMs * 8, 128, kNoiseSmemBytes, stream, d_origins, d_height,
+    MMG_TIMED(K_FILL_TERRAIN, stream, 1, MMG_LAUNCH(k_fill_terrain, m * 16, kRowThreads, kNoiseSmemBytes, stream, d_list, d_origins, d_height,
+                                                    d_weights, d_layers, d_caves, d_blocks, d_rockQueue, rockCap, d_counters));
+    MMG_TIMED(K_FILL_ROCK, stream, 1, MMG_LAUNCH(k_fill_rock, kNumSMs * MMG_ROCK_MINBLOCKS, 128, kNoiseSmemBytes, stream, d_origins, d_height,
                                                  (const uint2*)d_rockQueue, rockCap, d_blocks, d_lushQueue, d_counters));
     MMG_TIMED(K_FILL_LUSH, stream, 1, MMG_LAUNCH(k_fill_lush, kNumSMs * 8, 128, kNoiseSmemBytes, stream, d_origins, (const uint2*)d_lushQueue,
                                                  (const int*)d_counters, d_blocks));
