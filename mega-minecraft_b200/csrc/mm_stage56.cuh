@@ -897,7 +897,19 @@ __device__ __forceinline__ int cols_per_tile(int ny) { return ny >= MMG_TILE / 3
 // of rasteriser calls): a surface pass + a cave pass so that each pass's rasterisers fit the instruction cache (214 ms
 // against 162); column-level ball / disc / diamond tests that cut the rasteriser calls by 29 % (spheres: only hits reach
 // the rasteriser) but lengthen the per-column chain (174 ms against 147, profiles/r02_fill_features_variants.txt).
-__global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict__ fillList, const int2* __restrict__ origins,
+// CTA shape, measured per 128x128-chunk region (profiles/r02_k_fill_features_shapes.txt): 256 threads x 4 CTAs per SM 37.2 ms,
+// 384 x 3 34.1, 512 x 2 31.3 (the same 32 warps and 64 registers as 256 x 4, but half the shared memory - 94 KB instead of
+// 220 KB per SM - which leaves the L1 its capacity for the Prep records and placement lists), 768 x 1 33.9; every shape that
+// drops below 56 registers per thread is slower (384 x 4: 44.3, 512 x 3: 39.4).
+#ifndef MMG_FEAT_THREADS
+#define MMG_FEAT_THREADS 512
+#endif
+#ifndef MMG_FEAT_MINBLOCKS
+#define MMG_FEAT_MINBLOCKS 2
+#endif
+constexpr int kFeatThreads = MMG_FEAT_THREADS;
+static_assert(kFeatThreads >= 256 && kFeatThreads % 32 == 0, "thread t < 256 owns column t of the slab");
+__global__ void __launch_bounds__(kFeatThreads, MMG_FEAT_MINBLOCKS) k_fill_features(const int* __restrict__ fillList, const int2* __restrict__ origins,
                                                           const FeaturePlacement* __restrict__ gF, const CaveFeaturePlacement* __restrict__ gCF,
                                                           const Prep* __restrict__ prepF, const Prep* __restrict__ prepC,
                                                           const GatherInfo* __restrict__ info, int strideF, int strideCF,
@@ -910,8 +922,8 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
     __shared__ unsigned short shActE[kRound];                // ... and list position of the placement
     __shared__ unsigned shPacked;                            // tiles handed out << 11 | active placements
     __shared__ int shNextTile;
-    __shared__ float shGeom[8 * kMushroomGeomFloats];        // per warp: purple_mushroom_geom of the placement being rasterised
-    __shared__ unsigned short shQueue[8 * kFeatQueue];       // per warp: candidates waiting for the rasteriser
+    __shared__ float shGeom[(kFeatThreads / 32) * kMushroomGeomFloats];        // per warp: purple_mushroom_geom of the placement being rasterised
+    __shared__ unsigned short shQueue[(kFeatThreads / 32) * kFeatQueue];       // per warp: candidates waiting for the rasteriser
     const int slab = blockIdx.x % 12, li = blockIdx.x / 12;
     const int chunk = fillList ? fillList[li] : li;
     const int t = threadIdx.x, y0 = slab * kSlab, y1 = y0 + kSlab - 1;
@@ -921,7 +933,8 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
     if (!segF && !segC) return;
     const int2 o = origins[chunk];
     // thread t owns column t of the slab (32 consecutive block IDs, 16-byte aligned)
-    uint8_t* colPtr = blocks + (size_t)chunk * 98304 + (size_t)t * 384 + y0;
+    uint8_t* colPtr = blocks + (size_t)chunk * 98304 + (size_t)(t & 255) * 384 + y0;
+    if (t < 256)
     {
         const uint4 a = reinterpret_cast<const uint4*>(colPtr)[0], b = reinterpret_cast<const uint4*>(colPtr)[1];
         const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -934,7 +947,7 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
         shAir[t] = air;
         shClaim[t] = 0u;
     }
-    for (int i = t; i < kSlab * kSlabPitch; i += 256) shBest[i] = kNoBest;
+    for (int i = t; i < kSlab * kSlabPitch; i += kFeatThreads) shBest[i] = kNoBest;
     if (gi.needNoise) noise_tab_stage();
     const int lane = t & 31;
     const int nF = segF ? gi.nF : 0, nC = segC ? gi.nCF : 0, nTot = nF + nC;
@@ -981,7 +994,7 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
         if (t == 0) { shPacked = 0u; shNextTile = 0; }
         __syncthreads();
         const int r1 = min(r0 + kRound, nTot);
-        for (int e = r0 + t; e < r1; e += 256)
+        for (int e = r0 + t; e < r1; e += kFeatThreads)
         {
             const Prep q = e >= nF ? pc[e - nF] : pf[e];
             const int lo = max((int)q.lo, y0), hi = min((int)q.hi, y1);
@@ -1079,7 +1092,7 @@ __global__ void __launch_bounds__(256, 4) k_fill_features(const int* __restrict_
     }
     __syncthreads();
     // thread t writes column t back if any of its 32 voxels was claimed
-    if (shClaim[t] != 0u)
+    if (t < 256 && shClaim[t] != 0u)
     {
         uint4 ab[2] = {reinterpret_cast<const uint4*>(colPtr)[0], reinterpret_cast<const uint4*>(colPtr)[1]};
         uint8_t* outv = reinterpret_cast<uint8_t*>(ab);

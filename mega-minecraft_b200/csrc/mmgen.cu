@@ -420,7 +420,7 @@ static int launchFill(int m, const int* d_list, const int2* d_origins, const flo
                                                  (const int*)d_counters, d_blocks));
     MMG_TIMED(K_PREPARE, stream, 1, MMG_LAUNCH(k_prepare_placements, m, 256, 0, stream, d_list, d_origins, d_gF, d_gCF, d_info, strideF, strideCF,
                                                d_prepF, d_prepC));
-    MMG_TIMED(K_FILL_FEATURES, stream, 1, MMG_LAUNCH(k_fill_features, m * 12, 256, kNoiseSmemBytes, stream, d_list, d_origins, d_gF, d_gCF,
+    MMG_TIMED(K_FILL_FEATURES, stream, 1, MMG_LAUNCH(k_fill_features, m * 12, kFeatThreads, kNoiseSmemBytes, stream, d_list, d_origins, d_gF, d_gCF,
                                                      (const Prep*)d_prepF, (const Prep*)d_prepC, (const GatherInfo*)d_info, strideF, strideCF, d_blocks));
     MMG_TIMED(K_DECORATORS, stream, 1, MMG_LAUNCH(k_decorators, m, 256, 0, stream, d_list, m, d_origins, d_height, d_weights, d_caves, d_blocks));
     return 0;
