@@ -271,16 +271,16 @@ __device__ __forceinline__ float cave_thr(const CaveThr& c, float fbmA)
     thr = thr * c.hugeFactor;                     // huge == 0: fma(0, 1.4, 1) = 1 and thr * 1 = thr, the same bits
     return c.ratio * thr;
 }
+__device__ __forceinline__ float cave_fbm_a(int wx, int y, int wz)
+{
+    const float npx = (float)wx * 0.0050f, npy = (float)y * 0.0050f, npz = (float)wz * 0.0050f;
+    return fbm3_paired<4>(npx * 4.f, npy * 4.f, npz * 4.f);
+}
 __device__ __forceinline__ float cave_huge_factor(int wx, int y, int wz)
 {
     const float npx = (float)wx * 0.0050f, npy = (float)y * 0.0050f, npz = (float)wz * 0.0050f;
     const float huge = ss_t((fbm3_paired<4>(npx * 0.0700f, npy * 0.0700f, npz * 0.0700f) + -0.2f) / (0.4f - 0.2f));
     return fmaf(huge, 1.4f, 1.f);
-}
-__device__ __forceinline__ float cave_fbm_a(int wx, int y, int wz)
-{
-    const float npx = (float)wx * 0.0050f, npy = (float)y * 0.0050f, npz = (float)wz * 0.0050f;
-    return fbm3_paired<4>(npx * 4.f, npy * 4.f, npz * 4.f);
 }
 // The predicate in two steps. cave_threshold_cheap (no noise): 0 = solid, 1 = air, 2 = "survivor": the noise has to be asked.
 // hugeZero: the caller has proved that the "huge caves" term is exactly 0 at this voxel (huge_zero_mask below); the upper-bound
