@@ -139,8 +139,10 @@ class HaloExchange:
 
 # Relative cost of a chunk from its stage-1 features (ChunkGen.chunk_costs: cave voxels, fill voxels, land columns), fitted to
 # measured per-tile device times of the 256x256 bench world on a B200 (tools/fit_cost_model.py; only ratios matter)
-# (25 tiles of three tilings, 62-109 ms each: 1.2 % rms, 2.9 % worst-case error; by area alone 13.5 % / 22.6 %; profiles/r02_cost_model.txt)
-COST_WEIGHTS = (7.0e-5, 1.126e-3, 2.89e-3, 4.91e-3)      # ms: x cave voxels / 1e4, x fill voxels / 1e4, x land columns / 256, per chunk
+# (25 tiles of three tilings, 49-85 ms each: 1.4 % rms, 4.6 % worst-case error; by area alone 12.6 % / 22.4 %; profiles/r02_cost_model_v2.txt.
+# Refitted after the kernels of DESIGN.md 5 items 21-25: the cave stage got cheaper relative to the fill, its voxel count is almost
+# collinear with the fill's and the non-negative fit gives it no weight of its own.)
+COST_WEIGHTS = (0.0, 8.842e-4, 2.056e-3, 4.005e-3)      # ms: x cave voxels / 1e4, x fill voxels / 1e4, x land columns / 256, per chunk
 
 
 def chunk_cost_map(gen, region, rank=0, world_size=1, weights=COST_WEIGHTS):

@@ -19,7 +19,8 @@ if len(sys.argv) > 2 and sys.argv[1] == "--fit":
     own = np.array([s["own"] for s in samples])
     # ms ~ a * cave voxels / 1e4 + b * fill voxels / 1e4 + c * land columns / 256 + d * chunks + e (per tile)
     A = np.stack([own[:, 0] / 1e4, own[:, 1] / 1e4, own[:, 2] / 256.0, n, np.ones_like(n)], axis=1)
-    w, *_ = np.linalg.lstsq(A, ms, rcond=None)
+    from scipy.optimize import nnls      # non-negative: cave and fill voxels are strongly correlated, plain least squares lets one go negative
+    w, _ = nnls(A, ms)
     pred = A @ w
     area = np.linalg.lstsq(np.stack([n, np.ones_like(n)], axis=1), ms, rcond=None)[0]
     pa = np.stack([n, np.ones_like(n)], axis=1) @ area
