@@ -75,36 +75,43 @@ __global__ void __launch_bounds__(256) k_encode_count(const int* __restrict__ li
 
 // pass 2 (one CTA): where every chunk of the batch goes in the arena, appended after what earlier batches wrote.
 // index[slot] = {offset, bytes}; batchInfo = {arena offset of the batch, bytes of the batch}
-__global__ void __launch_bounds__(512) k_encode_place(int m, const int* __restrict__ slots, const unsigned* __restrict__ sizes,
+constexpr int kEncodePlaceThreads = 1024;
+__global__ void __launch_bounds__(kEncodePlaceThreads) k_encode_place(int m, const int* __restrict__ slots, const unsigned* __restrict__ sizes,
                                                       unsigned long long* __restrict__ arenaUsed, unsigned long long* __restrict__ offsets,
                                                       unsigned long long* __restrict__ index, unsigned long long* __restrict__ batchInfo)
 {
-    __shared__ unsigned long long sh[512];
+    __shared__ unsigned long long sh[kEncodePlaceThreads];
     const int t = threadIdx.x;
-    const unsigned long long mine = t < m ? sizes[t] : 0ull;
-    sh[t] = mine;
-    __syncthreads();
-    for (int d = 1; d < 512; d <<= 1)
-    {
-        const unsigned long long a = t >= d ? sh[t - d] : 0ull;
-        __syncthreads();
-        sh[t] += a;
-        __syncthreads();
-    }
     const unsigned long long base = *arenaUsed;
-    if (t < m)
+    unsigned long long carry = 0ull;      // bytes of the batch's chunks before this group of kEncodePlaceThreads
+    for (int c0 = 0; c0 < m; c0 += kEncodePlaceThreads)
     {
-        const unsigned long long off = base + sh[t] - mine;
-        offsets[t] = off;
-        index[2 * (size_t)slots[t]] = off;
-        index[2 * (size_t)slots[t] + 1] = mine;
+        const int i = c0 + t;
+        const unsigned long long mine = i < m ? sizes[i] : 0ull;
+        __syncthreads();      // the previous group's totals have been read
+        sh[t] = mine;
+        __syncthreads();
+        for (int d = 1; d < kEncodePlaceThreads; d <<= 1)
+        {
+            const unsigned long long a = t >= d ? sh[t - d] : 0ull;
+            __syncthreads();
+            sh[t] += a;
+            __syncthreads();
+        }
+        if (i < m)
+        {
+            const unsigned long long off = base + carry + sh[t] - mine;
+            offsets[i] = off;
+            index[2 * (size_t)slots[i]] = off;
+            index[2 * (size_t)slots[i] + 1] = mine;
+        }
+        carry += sh[kEncodePlaceThreads - 1];
     }
-    __syncthreads();
     if (t == 0)
     {
         batchInfo[0] = base;
-        batchInfo[1] = sh[511];
-        *arenaUsed = base + sh[511];
+        batchInfo[1] = carry;
+        *arenaUsed = base + carry;
     }
 }
 

@@ -72,7 +72,7 @@ static int codecEncodeBatch(MmgenWorld* w, int b, int m, const int* dl, const in
     if (b == 0) MMG_CUDA(cudaMemsetAsync(c->d_used, 0, sizeof(unsigned long long), w->stream));
     MMG_CUDA(cudaMemcpyAsync(c->d_slots, h_slots, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, w->stream));
     MMG_LAUNCH(k_encode_count, m, 256, 0, w->stream, dl, (const uint8_t*)w->d_blocks, c->d_nRuns, c->d_sizes);
-    MMG_LAUNCH(k_encode_place, 1, 512, 0, w->stream, m, (const int*)c->d_slots, (const unsigned*)c->d_sizes, c->d_used, c->d_offsets, c->d_index,
+    MMG_LAUNCH(k_encode_place, 1, kEncodePlaceThreads, 0, w->stream, m, (const int*)c->d_slots, (const unsigned*)c->d_sizes, c->d_used, c->d_offsets, c->d_index,
                c->d_batchInfo + 2 * (size_t)b);
     MMG_LAUNCH(k_encode_emit, m, 256, 0, w->stream, dl, (const uint8_t*)w->d_blocks, (const unsigned short*)c->d_nRuns, (const unsigned*)c->d_sizes,
                (const unsigned long long*)c->d_offsets, c->d_arena);

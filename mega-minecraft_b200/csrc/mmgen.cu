@@ -401,7 +401,13 @@ extern "C" int mmgen_caves(int n, const int32_t* origins, const float* heightfie
     return 0;
 }
 
-constexpr int kFillBatch = 512;
+// chunks per fill batch: every fill kernel ends in a tail of half-empty SMs, and k_fill_features (12 CTAs per chunk, two per SM,
+// uneven durations) has the longest one. Per 128x128 region (profiles/r02_fill_batch.txt): 256 chunks 146.9 ms, 512 133.3, 1024
+// 126.8, 2048 123.5, 4096 121.9; 2048 keeps the last batch's host copy (the only one not overlapped) at 200 MB.
+#ifndef MMG_FILL_BATCH
+#define MMG_FILL_BATCH 2048
+#endif
+constexpr int kFillBatch = MMG_FILL_BATCH;
 static int g_rockQueuePerChunk = kRockQueuePerChunk;   // mmgen_set_rock_queue_per_chunk (tuning / test knob, <= kRockQueuePerChunk)
 
 // the kernel sequence of Chunk::fill for one batch of m chunks (lists indexed by batch position)
@@ -792,14 +798,15 @@ static int worldFill(MmgenWorld* w, const std::vector<int>& list, uint8_t* hostB
     }
     const int nx = w->nx;
     if (!w->d_blocks) MMG_CUDA(cudaMalloc(&w->d_blocks, (size_t)w->n * 98304));
-    if (!w->d_gF) MMG_CUDA(cudaMalloc(&w->d_gF, (size_t)kFillBatch * MAX_FEATURES * sizeof(FeaturePlacement)));
-    if (!w->d_gCF) MMG_CUDA(cudaMalloc(&w->d_gCF, (size_t)kFillBatch * MAX_CAVE_FEATURES * sizeof(CaveFeaturePlacement)));
-    if (!w->d_info) MMG_CUDA(cudaMalloc(&w->d_info, (size_t)kFillBatch * sizeof(GatherInfo)));
-    if (!w->d_prepF) MMG_CUDA(cudaMalloc(&w->d_prepF, (size_t)kFillBatch * MAX_FEATURES * sizeof(Prep)));
-    if (!w->d_prepC) MMG_CUDA(cudaMalloc(&w->d_prepC, (size_t)kFillBatch * MAX_CAVE_FEATURES * sizeof(Prep)));
+    const size_t cap = std::min<size_t>((size_t)kFillBatch, (size_t)w->n);      // the longest batch this world can ever fill
+    if (!w->d_gF) MMG_CUDA(cudaMalloc(&w->d_gF, cap * MAX_FEATURES * sizeof(FeaturePlacement)));
+    if (!w->d_gCF) MMG_CUDA(cudaMalloc(&w->d_gCF, cap * MAX_CAVE_FEATURES * sizeof(CaveFeaturePlacement)));
+    if (!w->d_info) MMG_CUDA(cudaMalloc(&w->d_info, cap * sizeof(GatherInfo)));
+    if (!w->d_prepF) MMG_CUDA(cudaMalloc(&w->d_prepF, cap * MAX_FEATURES * sizeof(Prep)));
+    if (!w->d_prepC) MMG_CUDA(cudaMalloc(&w->d_prepC, cap * MAX_CAVE_FEATURES * sizeof(Prep)));
     if (!w->d_lushQueue) MMG_CUDA(cudaMalloc(&w->d_lushQueue, (size_t)kLushQueueCap * sizeof(uint2)));
     if (!w->d_lushCount) MMG_CUDA(cudaMalloc(&w->d_lushCount, 4 * sizeof(int)));
-    if (!w->d_rockQueue) MMG_CUDA(cudaMalloc(&w->d_rockQueue, (size_t)kFillBatch * kRockQueuePerChunk * sizeof(uint2)));
+    if (!w->d_rockQueue) MMG_CUDA(cudaMalloc(&w->d_rockQueue, cap * kRockQueuePerChunk * sizeof(uint2)));
     if (worldUploadList(w, list)) return 1;
     for (size_t b0 = 0; b0 < list.size(); b0 += kFillBatch)
     {
