@@ -661,6 +661,17 @@ def run_own(args):
     s6k = {k: {"ms": kernels[k]["ms_per_step"], "share_of_S6": kernels[k]["ms_per_step"] / max(float(stage_ms[6]), 1e-9),
                "issue_slot_utilisation_pct": NCU_ISSUE[k][0], "src": NCU_ISSUE[k][1]}
            for k in ("k_fill_terrain", "k_fill_rock", "k_fill_features") if k in kernels}
+    if "k_fill_features" in s6k:
+        # work model of the placement scan from the kernel's own counters (mmgen_work_counters [29..31], this rank, per step)
+        placements, pairs, rast = (float(wcount[i]) / args.steps for i in (29, 30, 31))
+        kms = max(s6k["k_fill_features"]["ms"], 1e-9)
+        s6k["k_fill_features"].update({
+            "algorithmic_placement_tests": placements * 98304.0,      # the reference tests every gathered placement at every voxel of the chunk
+            "pairs_examined": pairs, "pairs_rasterised": rast, "examined_over_algorithmic": pairs / max(placements * 98304.0, 1.0),
+            "algorithmic_tests_per_s": placements * 98304.0 / (kms * 1e-3), "rasterised_pairs_per_s": rast / (kms * 1e-3),
+            "note": "no FLOP model (SURVEY.md 8(d): integer / shared-memory work): algorithmic work = gathered placements x 98 304 voxels as the "
+                    "reference scans them; pairs_examined = (column, y) pairs inside the placements' clipped boxes, pairs_rasterised = the ones "
+                    "that were neither claimed by an earlier placement nor excluded by the air test"})
     stages = {
         "S1": dict(r1, ms=float(stage_ms[1])), "S2": dict(r2, ms=float(stage_ms[2])),
         "S3": dict(r3, ms=float(stage_ms[3]), sweeps=world.erosion_sweeps(), issue_slot_utilisation_pct=NCU_ISSUE["k_erode_sweep"][0]),

@@ -298,7 +298,9 @@ int mmgen_kernel_times(int cap, float* out_ms, int32_t* out_launches, int* n);
 const char* mmgen_kernel_name(int slot);
 /* work counters of the cheap stages since the last reset, for their roofline figures (32 values): [0..23] S1 columns in which
  * surface biome b had weight > 0 (its height function ran), [24] S1 columns, [25] S2 fbm<5> evaluations, [26] S2 columns,
- * [27] S3 32x32 tiles swept, [28] S3 tile launches that returned at the quiet-tile test. reset != 0 clears them afterwards. */
+ * [27] S3 32x32 tiles swept, [28] S3 tile launches that returned at the quiet-tile test, [29] S6 gathered placements of the filled
+ * chunks, [30] S6 (column, y) pairs inside the placements' clipped boxes that the placement scan looked at, [31] pairs that reached
+ * a rasteriser. reset != 0 clears them afterwards. */
 int mmgen_work_counters(uint64_t* out32, int reset);
 /* tuning knob: queue slots per chunk for the rock voxels that k_fill_terrain hands to k_fill_rock (default and maximum 49 152;
  * <= 0 restores the default). Voxels that do not fit are finished in place: results never depend on this value. */

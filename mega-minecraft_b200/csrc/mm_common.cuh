@@ -44,7 +44,10 @@ extern int g_numSMs;            // multiprocessor count of the bound device (148
 //   [24]    S1: columns;  [25] S2: fbm<5> evaluations (one per stratified layer with weight > 0 that is reached, chunk.cu:308-320)
 //   [26]    S2: columns;  [27] S3: 32x32 tiles actually swept (k_erode_sweep CTAs that did not return at the quiet-tile test)
 //   [28]    S3: tile CTAs that returned at the quiet-tile test (swept + quiet = launched)
-enum { W_S1_BIOME0 = 0, W_S1_COLUMNS = 24, W_S2_FBM5 = 25, W_S2_COLUMNS = 26, W_S3_TILES_SWEPT = 27, W_S3_TILES_QUIET = 28, W_NUM = 32 };
+//   [29]    S6: gathered placements of the filled chunks (the reference tests each of them at each of the chunk's 98 304 voxels, chunk.cu:1444-1500)
+//   [30]    S6: (column, y) pairs inside the placements' clipped boxes that k_fill_features looked at;  [31] pairs that reached a rasteriser
+enum { W_S1_BIOME0 = 0, W_S1_COLUMNS = 24, W_S2_FBM5 = 25, W_S2_COLUMNS = 26, W_S3_TILES_SWEPT = 27, W_S3_TILES_QUIET = 28,
+       W_S6_PLACEMENTS = 29, W_S6_PAIRS = 30, W_S6_RASTERISED = 31, W_NUM = 32 };
 __device__ unsigned long long g_work[W_NUM];
 
 // resident CTAs per SM the register allocator is asked to allow (tuned on a B200)
