@@ -44,11 +44,12 @@ F_S2, F_S3, F_W3CELL, F_SIN = 140, 330, 60, 20
 FLOP_CAVE_VOXEL = 23 * F_S3 + 27 * F_W3CELL + 81 * F_SIN          # one evaluated voxel of shouldGenerateCaveAtBlock
 FLOP_CAVE_BIOME = 11 * F_S3 + 12 * F_S2                           # one getCaveBiome
 # what k_caves executes of FLOP_CAVE_VOXEL after its exact early-outs (threshold bounds, huge-caves proof, tabulated cell hashes),
-# counted by the census build over the 256x256 world: profiles/r01_census_v8.txt
+# counted by the census build (profiles/r02_census_v2.txt: warped noise + Worley at 77.2 % of the algorithmic voxels, fbmA at 19.3 % of
+# those, the huge-caves term at 0.4 %, cell hashes tabulated)
 EXECUTED_OVER_ALGORITHMIC_CAVES = 0.48
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_caves launch of 4096 chunks (ncu --set full, profiles/r01_k_caves_v9.txt):
-# 26.3 MB read + 376.6 MB written, against 107 528 algorithmic bytes per chunk (98 304 of them the CaveLayer output)
-CAVES_DRAM_BYTES_PER_CHUNK = (26.340352e6 + 376.603904e6) / 4096
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_caves launch of 4096 chunks (ncu --set full, profiles/r02_k_caves_final.txt):
+# 26.8 MB read + 407.9 MB written, against 107 528 algorithmic bytes per chunk (98 304 of them the CaveLayer output)
+CAVES_DRAM_BYTES_PER_CHUNK = (26.836736e6 + 407.892992e6) / 4096
 BYTES_FILL_CHUNK = 242688                                         # S6 compulsory I/O per chunk (without feature lists)
 BYTES_CAVES_CHUNK = 107528
 BYTES_S1_CHUNK, BYTES_S2_CHUNK = 25608, 46360
@@ -63,9 +64,12 @@ FLOP_BIOME_NOISE = 11 * F_S2                                      # getBiomeNois
 FLOP_FBM5 = 5 * F_S2                                              # one stratified layer's thickness noise (S2)
 # issue-slot utilisation of the S6 kernels from the committed ncu captures (the placement scan has no noise-primitive FLOP model:
 # SURVEY.md 8(d) counts weights, smoothsteps and layer / list logic as 0 FLOP)
-NCU_ISSUE = {"k_caves": (87.5, "profiles/r01_k_caves_v9.txt"), "k_fill_rock": (74.0, "profiles/r01_k_fill_rock_v8.txt"),
-             "k_fill_terrain": (68.0, "profiles/r01_k_fill_terrain_v8.txt"), "k_fill_features": (52.7, "profiles/r02_k_fill_features_v1.txt"),
-             "k_erode_sweep": (37.0, "profiles/r01_k_erode_sweep_v8.txt")}
+NCU_ISSUE = {"k_caves": (83.7, "profiles/r02_k_caves_final.txt"), "k_fill_rock": (70.6, "profiles/r02_k_fill_rock_final.txt"),
+             "k_fill_terrain": (80.8, "profiles/r02_k_fill_terrain_final.txt"), "k_fill_features": (75.6, "profiles/r02_k_fill_features_final.txt"),
+             "k_erode_sweep": (38.3, "profiles/r02_k_erode_sweep_final.txt")}
+# the same captures: FMA-pipe and ALU-pipe cycles active (% of peak), active lanes per executed warp instruction
+NCU_PIPES = {"k_caves": (47.6, 58.5, 30.3), "k_fill_rock": (43.0, 49.6, 27.7), "k_fill_terrain": (15.3, 65.8, 23.1),
+             "k_fill_features": (19.2, 59.0, 25.5), "k_erode_sweep": (10.6, 21.3, 29.9)}
 
 
 def peaks():
@@ -642,14 +646,20 @@ def run_own(args):
     fp32_peak = min(fp32_all, pk["fp32_tflops"]) if fp32_all > 0 else pk["fp32_tflops"]
     roof = {"bound": "fp32", "kernel": roof_kernel, "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
             "traffic": (CAVES_DRAM_BYTES_PER_CHUNK * int((st >= 4).sum()) / rk_launches if roof_kernel == "k_caves" else None),
-            "traffic_src": "ncu capture of one 4096-chunk k_caves launch (profiles/r01_k_caves_v9.txt), scaled to this run's chunks per launch; "
+            "traffic_src": "ncu capture of one 4096-chunk k_caves launch (profiles/r02_k_caves_final.txt), scaled to this run's chunks per launch; "
                            "algorithmic bytes per chunk: 107528",
             "avg_launch_ms": avg_launch_ms, "launches_per_step": rk_launches,
             "algorithmic_flop_per_launch": flops_of[roof_kernel] / rk_launches,
             "executed": ({"flop_ratio_to_algorithmic": EXECUTED_OVER_ALGORITHMIC_CAVES, "achieved": ach * EXECUTED_OVER_ALGORITHMIC_CAVES,
                           "frac": ach * EXECUTED_OVER_ALGORITHMIC_CAVES / fp32_peak,
-                          "src": "census build over the same world (profiles/r01_census_v8.txt): evaluations proved unnecessary are not executed; "
-                                 "ncu issue-slot utilisation of the kernel is in profiles/"} if roof_kernel == "k_caves" else None),
+                          "src": "census build (profiles/r02_census_v2.txt): evaluations proved unnecessary are not executed. Both figures are work "
+                                 "rates in SURVEY.md 8(d)'s canonical FLOPs (simplex3 = 330 FLOP, a hashed Worley cell 60 + 3 x 20), not pipe "
+                                 "occupancy: this implementation reads the lattice hash and the gradients from tables and retires two fp32 "
+                                 "operations per packed instruction, so a canonical FLOP costs it less than a FLOP. What the hardware saw is in `ncu`."}
+                         if roof_kernel == "k_caves" else None),
+            "ncu": {"issue_slot_utilisation_pct": NCU_ISSUE[roof_kernel][0], "fma_pipe_pct": NCU_PIPES[roof_kernel][0],
+                    "alu_pipe_pct": NCU_PIPES[roof_kernel][1], "active_lanes_of_32": NCU_PIPES[roof_kernel][2], "src": NCU_ISSUE[roof_kernel][1]}
+                   if roof_kernel in NCU_ISSUE else None,
             "peak_src": "FFMA microbenchmark run by this process on the same GPU just before the timed region (mmgen_measure_fp32_peak: %.1f TFLOP/s; "
                         "nominal 148 SM x 128 lanes x 2 x %.0f MHz = %.1f); MEASURED_PEAKS.json carries HBM and bf16 tensor figures only" % (
                             fp32_measured, pk["sm_max_mhz"], pk["fp32_tflops"]),
@@ -659,7 +669,8 @@ def run_own(args):
                     "implementation proves unnecessary still count; k_fill_features (placement rasterisation) has no FLOP model and is reported by time" % hbm6}
     r1, r2, r3 = cheap_stage_rooflines(wcount, args.steps, kernels, fp32_peak, pk["hbm_gbs"])      # this rank's counters and kernel times
     s6k = {k: {"ms": kernels[k]["ms_per_step"], "share_of_S6": kernels[k]["ms_per_step"] / max(float(stage_ms[6]), 1e-9),
-               "issue_slot_utilisation_pct": NCU_ISSUE[k][0], "src": NCU_ISSUE[k][1]}
+               "issue_slot_utilisation_pct": NCU_ISSUE[k][0], "fma_pipe_pct": NCU_PIPES[k][0], "alu_pipe_pct": NCU_PIPES[k][1],
+               "active_lanes_of_32": NCU_PIPES[k][2], "src": NCU_ISSUE[k][1]}
            for k in ("k_fill_terrain", "k_fill_rock", "k_fill_features") if k in kernels}
     if "k_fill_features" in s6k:
         # work model of the placement scan from the kernel's own counters (mmgen_work_counters [29..31], this rank, per step)
