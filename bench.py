@@ -380,10 +380,20 @@ def run_c3(args):
                     launches += gen.launch_count() - l0
         if name == "reference":
             clocks = sampler.stop()
+        # one more session, untimed, with CUDA event pairs around every hot-kernel launch: where the device time of the ticks goes
+        gen.kernel_timing(True)
+        t = mm.Terrain(gen, -R - 1, -R - 1, 2 * R + 2, 2 * R + 2)
+        t.set_radii(16, R)
+        t.set_costs(mm.REFERENCE_COSTS, cap, rate)
+        t.run_until_idle(1.0 / 32.0)
+        torch.cuda.synchronize()
+        t.close()
+        ktimes = {k: {"ms": round(v[0], 3), "launches": int(v[1])} for k, v in gen.kernel_times().items() if v[1]}
+        gen.kernel_timing(False)
         wall = sum(r[0] for r in runs) / len(runs)
         dev = sum(r[1] for r in runs) / len(runs)
         res[name] = {"ticks": runs[0][3], "chunks_filled": runs[0][2], "wall_ms": 1e3 * wall, "device_ms": dev, "chunks_per_s": runs[0][2] / wall,
-                     "frame_budget": cap, "hash": "%016x" % h,
+                     "frame_budget": cap, "hash": "%016x" % h, "kernels": ktimes,
                      "max_batch": {k: max(s[k] for s in log) for k in ("heightfields", "layers", "caves", "filled", "zonesEroded")}}
     r = res["reference"]
     out = {"metric": "c3_streaming_chunks_per_sec", "value": r["chunks_per_s"], "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,

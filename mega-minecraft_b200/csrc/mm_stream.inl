@@ -216,6 +216,16 @@ static void streamCheckNeedsVbos(MmgenStream* s, int i)
     if (s->state[i] == ST_FILLED) s->setState(i, ST_NEEDS_VBOS);
 }
 
+#ifndef MMG_STREAM_MIN_FILL
+#define MMG_STREAM_MIN_FILL 64
+#endif
+// the most chunks one tick can fill under the action-time budget: what the world sizes its fill scratch for
+static void streamFillHint(MmgenStream* s)
+{
+    const long long perTick = s->cost[COST_FILL] > 0 ? (long long)s->maxActionTimePerFrame / s->cost[COST_FILL] : (long long)kFillBatch;
+    s->w->fillHint = (size_t)std::min<long long>(std::max<long long>(perTick, MMG_STREAM_MIN_FILL), (long long)kFillBatch);
+}
+
 int mmgen_stream_create(int cx0, int cz0, int nx, int nz, MmgenStream** out)
 {
     if (requireReady()) return 1;
@@ -231,6 +241,8 @@ int mmgen_stream_create(int cx0, int cz0, int nx, int nz, MmgenStream** out)
     s->zoneInTry.assign((size_t)s->nzx * s->nzz, 0);
     for (auto& e : s->ev) MMG_CUDA(cudaEventCreate(&e));
     streamBuildSpiral(s);
+    streamFillHint(s);
+    if (worldReserve(s->w)) { mmgen_stream_destroy(s); return 1; }
     *out = s;
     return 0;
 }
@@ -265,7 +277,8 @@ int mmgen_stream_set_costs(MmgenStream* s, const int32_t* costs9, int maxActionT
             s->cost[k] = costs9[k];
         }
     s->maxActionTimePerFrame = maxActionTimePerFrame; s->totalActionTimePerSecond = totalActionTimePerSecond;
-    return 0;
+    streamFillHint(s);
+    return worldReserve(s->w);      // a larger budget needs larger fill scratch: now, not in a tick
 }
 
 // Terrain::setCurrentChunkPos with chunkPosFromPlayerPos (terrain.cpp:254-257, 1031-1034); block coordinates

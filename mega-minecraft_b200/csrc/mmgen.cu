@@ -155,6 +155,9 @@ struct MmgenWorld
     uint2* d_lushQueue = nullptr;                    // voxels of one fill batch waiting for the lush-cave decision
     int* d_lushCount = nullptr;                      // [0] lush queue length, [2] near-rock, [3] bulk-rock queue lengths
     uint2* d_rockQueue = nullptr;                    // rock voxels of one fill batch waiting for getCaveBiome (k_fill_rock)
+    size_t fillCap = 0;                              // chunks per fill batch the scratch above (d_gF .. d_rockQueue) is sized for
+    size_t fillHint = 0;                             // streaming sessions: the most chunks a tick can fill (0 = a batch world)
+    bool reserving = false;                          // worldReserve: the stage runners allocate their buffers and return
     uint8_t* d_blocks = nullptr;                     // [chunk][16][16][384]
     // meshing (mmgen_world_mesh): arena of the last call
     MeshChunk* d_meshList = nullptr;
@@ -680,9 +683,10 @@ static int worldUploadList(MmgenWorld* w, const std::vector<int>& list)
 // S1 (Chunk::generateHeightfields); list == nullptr: every chunk of the window
 static int worldHeightfields(MmgenWorld* w, const std::vector<int>* list)
 {
-    if (list && list->empty()) return 0;
+    if (list && list->empty() && !w->reserving) return 0;
     if (!w->d_height) MMG_CUDA(cudaMalloc(&w->d_height, (size_t)w->n * 256 * sizeof(float)));
     if (!w->d_weights) MMG_CUDA(cudaMalloc(&w->d_weights, (size_t)w->n * NUM_BIOMES * 256 * sizeof(float)));
+    if (w->reserving) return worldUploadList(w, std::vector<int>());
     if (list)
     {
         if (worldUploadList(w, *list)) return 1;
@@ -702,8 +706,9 @@ static int worldHeightfields(MmgenWorld* w, const std::vector<int>* list)
 // S2 (gatherHeightfield + Chunk::generateLayers): every listed chunk has its 3x3 neighbourhood at stage >= 1
 static int worldLayers(MmgenWorld* w, const std::vector<int>& list)
 {
-    if (list.empty()) return 0;
+    if (list.empty() && !w->reserving) return 0;
     if (!w->d_layers) MMG_CUDA(cudaMalloc(&w->d_layers, (size_t)w->n * NUM_MATERIALS * 256 * sizeof(float)));
+    if (w->reserving) return 0;
     if (worldUploadList(w, list)) return 1;
     MMG_TIMED(K_LAYERS, w->stream, 1, MMG_LAUNCH(k_layers<true>, (int)list.size(), 256, kNoiseSmemBytes, w->stream, (const int*)w->d_list,
                                                  (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights, w->d_layers, w->nx));
@@ -714,12 +719,13 @@ static int worldLayers(MmgenWorld* w, const std::vector<int>& list)
 // S3 (Chunk::erodeZone) for zones given by the window-local corner of their 24x24-chunk gather window
 static int worldErode(MmgenWorld* w, const std::vector<int2>& corners)
 {
-    if (corners.empty()) return 0;
+    if (corners.empty() && !w->reserving) return 0;
     const int nx = w->nx;
     if (!w->d_zone) MMG_CUDA(cudaMalloc(&w->d_zone, (size_t)kZoneBatch * kZonePlanes * kErosionCols * sizeof(float)));
     if (!w->d_zoneCorners) MMG_CUDA(cudaMalloc(&w->d_zoneCorners, (size_t)kZoneBatch * sizeof(int2)));
     if (!w->d_flags) MMG_CUDA(cudaMalloc(&w->d_flags, (kSweepGroup + 3 * kMaxZoneBatch * kZoneTiles) * sizeof(int)));
     if (!w->d_eroded) MMG_CUDA(cudaMalloc(&w->d_eroded, (size_t)w->n * NUM_MATERIALS * 256 * sizeof(float)));
+    if (w->reserving) return 0;
     for (size_t z0 = 0; z0 < corners.size(); z0 += kZoneBatch)
     {
         const int m = (int)std::min<size_t>(kZoneBatch, corners.size() - z0);
@@ -742,12 +748,13 @@ static int worldErode(MmgenWorld* w, const std::vector<int2>& corners)
 // S4 (Chunk::generateCaves)
 static int worldCaves(MmgenWorld* w, const std::vector<int>& list)
 {
-    if (list.empty()) return 0;
+    if (list.empty() && !w->reserving) return 0;
     const int m = (int)list.size();
     if (!w->d_caves) MMG_CUDA(cudaMalloc(&w->d_caves, (size_t)w->n * 256 * MAX_CAVE_LAYERS * sizeof(CaveLayer)));
     if (!w->d_caveCols) MMG_CUDA(cudaMalloc(&w->d_caveCols, (size_t)kCaveBatch * 256 * sizeof(CaveColumn)));
     if (!w->d_caveQueue) MMG_CUDA(cudaMalloc(&w->d_caveQueue, (size_t)kCaveBiomeQueueCap * sizeof(uint2)));
     if (!w->d_caveCount) MMG_CUDA(cudaMalloc(&w->d_caveCount, sizeof(int)));
+    if (w->reserving) return 0;
     if (worldUploadList(w, list)) return 1;
     if (launchCaves(m, (const int*)w->d_list, (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights,
                     w->d_caveCols, w->d_caves, w->d_caveQueue, w->d_caveCount, w->stream))
@@ -759,7 +766,7 @@ static int worldCaves(MmgenWorld* w, const std::vector<int>& list)
 // S5a (Chunk::generateFeaturePlacements, a CPU pass in the reference)
 static int worldPlacements(MmgenWorld* w, const std::vector<int>& list)
 {
-    if (list.empty()) return 0;
+    if (list.empty() && !w->reserving) return 0;
     const int m = (int)list.size();
     if (!w->d_features) MMG_CUDA(cudaMalloc(&w->d_features, (size_t)w->n * kMaxOwnFeatures * sizeof(FeaturePlacement)));
     if (!w->d_caveFeatures) MMG_CUDA(cudaMalloc(&w->d_caveFeatures, (size_t)w->n * kMaxOwnCaveFeatures * sizeof(CaveFeaturePlacement)));
@@ -768,6 +775,7 @@ static int worldPlacements(MmgenWorld* w, const std::vector<int>& list)
         MMG_CUDA(cudaMalloc(&w->d_counts, (size_t)w->n * 2 * sizeof(int)));
         MMG_CUDA(cudaMemsetAsync(w->d_counts, 0, (size_t)w->n * 2 * sizeof(int), w->stream));
     }
+    if (w->reserving) return 0;
     if (worldUploadList(w, list)) return 1;
     MMG_TIMED(K_PLACEMENTS, w->stream, 1, MMG_LAUNCH(k_feature_placements, m, 256, 0, w->stream, (const int*)w->d_list, (const int2*)w->d_origins,
                                                      (const float*)w->d_height, (const float*)w->d_weights, (const float*)w->d_eroded,
@@ -786,7 +794,7 @@ static int codecDeliver(MmgenWorld* w, int batches, size_t targets, EncodedOut* 
 template <typename SlotFn>
 static int worldFill(MmgenWorld* w, const std::vector<int>& list, uint8_t* hostBlocks, SlotFn hostSlot, EncodedOut* enc = nullptr)
 {
-    if (list.empty()) return 0;
+    if (list.empty() && !w->reserving) return 0;
     const int nBatches = (int)((list.size() + kFillBatch - 1) / kFillBatch);
     std::vector<int> slots;
     if (enc)
@@ -798,15 +806,29 @@ static int worldFill(MmgenWorld* w, const std::vector<int>& list, uint8_t* hostB
     }
     const int nx = w->nx;
     if (!w->d_blocks) MMG_CUDA(cudaMalloc(&w->d_blocks, (size_t)w->n * 98304));
-    const size_t cap = std::min<size_t>((size_t)kFillBatch, (size_t)w->n);      // the longest batch this world can ever fill
-    if (!w->d_gF) MMG_CUDA(cudaMalloc(&w->d_gF, cap * MAX_FEATURES * sizeof(FeaturePlacement)));
-    if (!w->d_gCF) MMG_CUDA(cudaMalloc(&w->d_gCF, cap * MAX_CAVE_FEATURES * sizeof(CaveFeaturePlacement)));
-    if (!w->d_info) MMG_CUDA(cudaMalloc(&w->d_info, cap * sizeof(GatherInfo)));
-    if (!w->d_prepF) MMG_CUDA(cudaMalloc(&w->d_prepF, cap * MAX_FEATURES * sizeof(Prep)));
-    if (!w->d_prepC) MMG_CUDA(cudaMalloc(&w->d_prepC, cap * MAX_CAVE_FEATURES * sizeof(Prep)));
+    // scratch of one fill batch (0.66 MB per chunk: 1.3 GB for a full batch). A batch world gets it for min(batch, its chunks); a
+    // streaming session for the most chunks one tick can fill under its action-time budget (mmgen_stream_set_costs) - cudaMalloc /
+    // cudaFree of these sizes take tens of milliseconds (measured on BASELINE config 3), so it is sized once, not grown step by step
+    const size_t hint = w->fillHint ? w->fillHint : std::min<size_t>((size_t)kFillBatch, (size_t)w->n);
+    const size_t need = w->reserving ? hint : std::min<size_t>((size_t)kFillBatch, list.size());
+    if (need > w->fillCap)
+    {
+        const size_t cap = std::min<size_t>((size_t)kFillBatch, std::max(need, hint));
+        MMG_CUDA(cudaStreamSynchronize(w->stream));
+        cudaFree(w->d_gF); cudaFree(w->d_gCF); cudaFree(w->d_info); cudaFree(w->d_prepF); cudaFree(w->d_prepC); cudaFree(w->d_rockQueue);
+        w->d_gF = nullptr; w->d_gCF = nullptr; w->d_info = nullptr; w->d_prepF = nullptr; w->d_prepC = nullptr; w->d_rockQueue = nullptr;
+        w->fillCap = 0;
+        MMG_CUDA(cudaMalloc(&w->d_gF, cap * MAX_FEATURES * sizeof(FeaturePlacement)));
+        MMG_CUDA(cudaMalloc(&w->d_gCF, cap * MAX_CAVE_FEATURES * sizeof(CaveFeaturePlacement)));
+        MMG_CUDA(cudaMalloc(&w->d_info, cap * sizeof(GatherInfo)));
+        MMG_CUDA(cudaMalloc(&w->d_prepF, cap * MAX_FEATURES * sizeof(Prep)));
+        MMG_CUDA(cudaMalloc(&w->d_prepC, cap * MAX_CAVE_FEATURES * sizeof(Prep)));
+        MMG_CUDA(cudaMalloc(&w->d_rockQueue, cap * kRockQueuePerChunk * sizeof(uint2)));
+        w->fillCap = cap;
+    }
     if (!w->d_lushQueue) MMG_CUDA(cudaMalloc(&w->d_lushQueue, (size_t)kLushQueueCap * sizeof(uint2)));
     if (!w->d_lushCount) MMG_CUDA(cudaMalloc(&w->d_lushCount, 4 * sizeof(int)));
-    if (!w->d_rockQueue) MMG_CUDA(cudaMalloc(&w->d_rockQueue, cap * kRockQueuePerChunk * sizeof(uint2)));
+    if (w->reserving) return 0;
     if (worldUploadList(w, list)) return 1;
     for (size_t b0 = 0; b0 < list.size(); b0 += kFillBatch)
     {
@@ -847,6 +869,19 @@ static int worldFill(MmgenWorld* w, const std::vector<int>& list, uint8_t* hostB
     if (enc && codecDeliver(w, nBatches, enc->bytes, enc)) return 1;
     for (int i : list) w->stage[i] = 6;
     return 0;
+}
+
+// every device buffer the stage runners would otherwise allocate at their first call, now (a streaming session reserves at set-up, as
+// Terrain::initCuda does, terrain.cpp:154-185: cudaMalloc inside a tick costs the tick tens of milliseconds)
+static int worldReserve(MmgenWorld* w)
+{
+    const std::vector<int> none;
+    const std::vector<int2> noZones;
+    w->reserving = true;
+    const int rc = worldHeightfields(w, &none) || worldLayers(w, none) || worldErode(w, noZones) || worldCaves(w, none) || worldPlacements(w, none) ||
+                   worldFill(w, none, nullptr, [](int) { return (size_t)0; });
+    w->reserving = false;
+    return rc;
 }
 
 static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks, EncodedOut* enc = nullptr)
