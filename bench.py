@@ -727,6 +727,9 @@ def run_own(args):
                        "; then moved by feedback from %d untimed passes (per-rank device time)" % rounds if rounds else "")),
                    "halo_variants_ms_per_step": {k: round(v, 2) for k, v in variants.items()},
                    "tiles": [list(t) for t in tiles_final], "chunks_touched_rank0": counts,
+                   "stage_overlap": "layers + erosion (S2, S3) run on a high-priority side stream while the caves (S4, stage-1 inputs only) run on the "
+                                    "main stream; they join before S5. stages.S3.ms / S4.ms are elapsed times of overlapping stages and do not add up to "
+                                    "ms_per_step; the kernel times under `kernels` and the S4 roofline are measured with both streams sharing the SMs",
                    "l2": "working set per step (>= %.1f GB written) far exceeds the 126 MB L2; no flush needed" % (n_target * 98304 / 1e9)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * max(e2e_wall, e2e_dev) / args.steps, "host_checksum": host_sum,

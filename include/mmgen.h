@@ -305,6 +305,10 @@ int mmgen_work_counters(uint64_t* out32, int reset);
 /* tuning knob: queue slots per chunk for the rock voxels that k_fill_terrain hands to k_fill_rock (default and maximum 49 152;
  * <= 0 restores the default). Voxels that do not fit are finished in place: results never depend on this value. */
 int mmgen_set_rock_queue_per_chunk(int slots);
+/* measurement knob: a generate call that runs layers, erosion and caves together overlaps layers + erosion (side stream) with the
+ * caves, which only read stage-1 products; serial != 0 runs them one after the other, as the reference's state machine does. The
+ * products are identical either way (tests/test_gpu_parity.py::test_stage_overlap_is_result_neutral). */
+int mmgen_set_serial_stages(int serial);
 /* achieved FP32 FMA rate of this device (TFLOP/s, 8 independent FFMA chains per thread on every SM): roofline denominator */
 int mmgen_measure_fp32_peak(float* out_tflops);
 

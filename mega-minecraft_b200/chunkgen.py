@@ -99,6 +99,10 @@ class ChunkGen:
         self._check(self.L.mmgen_chunk_costs(origins.shape[0], _ptr(origins), _ptr(out)))
         return out
 
+    def set_serial_stages(self, serial):
+        """Measurement knob (mmgen_set_serial_stages): run layers + erosion and the caves one after the other instead of overlapped."""
+        self._check(self.L.mmgen_set_serial_stages(1 if serial else 0))
+
     def work_counters(self, reset=True):
         """mmgen_work_counters: 32 uint64 counters of the cheap stages (see include/mmgen.h)."""
         out = np.zeros(32, np.uint64)

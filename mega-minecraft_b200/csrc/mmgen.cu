@@ -175,6 +175,8 @@ struct MmgenWorld
     std::vector<uint8_t> stage;
     cudaStream_t stream = nullptr;
     cudaStream_t copyStream = nullptr;   // device->host block copies overlapped with the fill (generate_to_host)
+    cudaStream_t sideStream = nullptr;   // layers + erosion of a full generate, while the caves (which only need stage 1) run on `stream`
+    cudaEvent_t evSide[2] = {};          // fork / join of the side stream
     cudaEvent_t ev[14] = {};             // [2s-2, 2s-1] bracket stage s; [12, 13] bracket the whole generate
     cudaEvent_t evMesh[2] = {};          // bracket mmgen_world_mesh (its own pair: total_ms keeps the last generate's time)
     cudaEvent_t evBatch[2] = {};
@@ -411,6 +413,7 @@ extern "C" int mmgen_caves(int n, const int32_t* origins, const float* heightfie
 #define MMG_FILL_BATCH 2048
 #endif
 constexpr int kFillBatch = MMG_FILL_BATCH;
+static bool g_serialStages = false;                    // mmgen_set_serial_stages: no overlap of layers + erosion with the caves (measurement knob)
 static int g_rockQueuePerChunk = kRockQueuePerChunk;   // mmgen_set_rock_queue_per_chunk (tuning / test knob, <= kRockQueuePerChunk)
 
 // the kernel sequence of Chunk::fill for one batch of m chunks (lists indexed by batch position)
@@ -602,6 +605,13 @@ int mmgen_world_create(int cx0, int cz0, int nx, int nz, MmgenWorld** out)
     w->stage.assign(w->n, 0);
     MMG_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     MMG_CUDA(cudaStreamCreateWithFlags(&w->copyStream, cudaStreamNonBlocking));
+    {
+        // erosion is hundreds of short dependent launches: its blocks go first whenever the cave kernel frees an SM slot
+        int prLow = 0, prHigh = 0;
+        MMG_CUDA(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
+        MMG_CUDA(cudaStreamCreateWithPriority(&w->sideStream, cudaStreamNonBlocking, prHigh));
+    }
+    for (auto& e : w->evSide) MMG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : w->ev) MMG_CUDA(cudaEventCreate(&e));
     for (auto& e : w->evMesh) MMG_CUDA(cudaEventCreate(&e));
     for (auto& e : w->evBatch) MMG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -657,6 +667,8 @@ int mmgen_world_destroy(MmgenWorld* w)
     for (auto& e : w->evBatch) if (e) cudaEventDestroy(e);
     if (w->stream) cudaStreamDestroy(w->stream);
     if (w->copyStream) cudaStreamDestroy(w->copyStream);
+    if (w->sideStream) cudaStreamDestroy(w->sideStream);
+    for (auto& e : w->evSide) if (e) cudaEventDestroy(e);
     delete w;
     return 0;
 }
@@ -897,6 +909,23 @@ static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks, Enco
         if (worldHeightfields(w, nullptr)) return 1;
         MMG_CUDA(cudaEventRecord(w->ev[1], w->stream));
     }
+    // A generate that runs layers, erosion and caves in one call overlaps them: the cave stage reads stage-1 products only
+    // (heightfield, biome weights: chunk.cu:755-937), so it runs on `stream` while layers + erosion - 1 600 short dependent launches
+    // that leave most of the GPU idle - run on the high-priority side stream; both join before the placements. The reference's
+    // state machine orders them one after the other (terrain.cpp:587-960); the products are the same either way.
+    constexpr int kOverlapMask = MMGEN_STAGE_LAYERS | MMGEN_STAGE_EROSION | MMGEN_STAGE_CAVES;
+    const bool overlap = (stageMask & kOverlapMask) == kOverlapMask && !g_serialStages;
+    struct StreamRoles      // whatever path leaves this function, the world's streams keep their roles
+    {
+        MmgenWorld* w; cudaStream_t main, side;
+        ~StreamRoles() { w->stream = main; w->sideStream = side; }
+    } roles{w, w->stream, w->sideStream};
+    if (overlap)
+    {
+        MMG_CUDA(cudaEventRecord(w->evSide[0], w->stream));
+        MMG_CUDA(cudaStreamWaitEvent(w->sideStream, w->evSide[0], 0));
+        std::swap(w->stream, w->sideStream);      // the stage runners below enqueue on w->stream
+    }
     if (stageMask & MMGEN_STAGE_LAYERS)
     {
         // chunks whose 3x3 neighbourhood lies inside the window (gatherHeightfield's condition)
@@ -938,10 +967,33 @@ static int worldGenerate(MmgenWorld* w, int stageMask, uint8_t* hostBlocks, Enco
                     for (int x = 0; x < 24 && ok; ++x) ok = w->stage[(lz0 + z) * nx + lx0 + x] >= 2;
                 if (ok) corners.push_back(make_int2(lx0, lz0));
             }
+        std::vector<int> caved;
+        if (overlap)
+        {
+            // the caves of every chunk that is eroded already or is about to be, queued on the main stream first
+            std::vector<uint8_t> will(w->n, 0);
+            for (const int2& c : corners)
+                for (int z = 6; z < 18; ++z)
+                    for (int x = 6; x < 18; ++x) will[(c.y + z) * nx + c.x + x] = 1;
+            for (int i = 0; i < w->n; ++i)
+                if ((w->stage[i] == 3 || (will[i] && w->stage[i] < 3)) && w->ownsPlacements(i % nx, i / nx)) caved.push_back(i);
+            std::swap(w->stream, w->sideStream);      // main stream
+            MMG_CUDA(cudaEventRecord(w->ev[6], w->stream));
+            if (worldCaves(w, caved)) return 1;
+            MMG_CUDA(cudaEventRecord(w->ev[7], w->stream));
+            std::swap(w->stream, w->sideStream);      // side stream again
+        }
         if (worldErode(w, corners)) return 1;
         MMG_CUDA(cudaEventRecord(w->ev[5], w->stream));
+        if (overlap)
+        {
+            for (int i : caved) w->stage[i] = 4;      // worldErode marked its zones' chunks 3
+            MMG_CUDA(cudaEventRecord(w->evSide[1], w->stream));
+            std::swap(w->stream, w->sideStream);
+            MMG_CUDA(cudaStreamWaitEvent(w->stream, w->evSide[1], 0));
+        }
     }
-    if (stageMask & MMGEN_STAGE_CAVES)
+    if ((stageMask & MMGEN_STAGE_CAVES) && !overlap)
     {
         std::vector<int> list;
         for (int i = 0; i < w->n; ++i)
@@ -1445,6 +1497,12 @@ int mmgen_measure_fp32_peak(float* out_tflops)
     cudaEventDestroy(b);
     cudaFree(d);
     *out_tflops = best;
+    return 0;
+}
+
+int mmgen_set_serial_stages(int serial)
+{
+    g_serialStages = serial != 0;
     return 0;
 }
 

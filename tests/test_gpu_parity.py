@@ -381,6 +381,32 @@ def test_c4_cave_and_fill_stress_32x32(gen, mm, oracle):
     world.close()
 
 
+def test_stage_overlap_is_result_neutral(gen, mm, golden):
+    """A full generate runs layers + erosion on a side stream while the caves (stage-1 inputs only) run on the main stream. Serial
+    and overlapped runs must give the same world - the reference's blocks for the golden window, and identical per-chunk hashes,
+    eroded layers and cave layers for a region that spans several erosion zones."""
+    hashes = {}
+    for serial in (1, 0):
+        try:
+            gen.L.mmgen_set_serial_stages(serial)
+            world = gen.region_world(3, 3, 6, 6)
+            world.generate(mm.STAGE_ALL)
+            assert np.array_equal(world.download_region_blocks(), golden["g"]["blocks"])
+            world.close()
+            world = gen.region_world(-20, 5, 40, 30)
+            world.generate(mm.STAGE_ALL)
+            d = world.download(layers=True, cave_layers=True)
+            hashes[serial] = (world.chunk_hashes(), d["layers"].copy(), d["cave_layers"].copy(), world.stages().copy())
+            world.close()
+        finally:
+            gen.L.mmgen_set_serial_stages(0)
+    assert hashes[0][0] == hashes[1][0] and len(hashes[0][0]) == 40 * 30
+    assert np.array_equal(hashes[0][3], hashes[1][3])
+    done = hashes[0][3].ravel() >= 4      # eroded and caved (chunks outside that hold no product)
+    assert done.sum() >= 40 * 30
+    assert np.array_equal(hashes[0][1][done], hashes[1][1][done]) and np.array_equal(hashes[0][2][done], hashes[1][2][done])
+
+
 def test_rock_queue_overflow_is_result_neutral(gen, mm, golden):
     """k_fill_terrain queues rock voxels for the dense kernel k_fill_rock; voxels that do not fit in the queue are
     finished in place. With a queue far too small the blocks must still equal the reference's."""
