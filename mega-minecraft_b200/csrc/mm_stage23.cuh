@@ -154,11 +154,13 @@ constexpr int kMaxZoneBatch = 32;
 constexpr int kZoneTiles = 144;      // 12 x 12 tiles of 32 x 32 cells
 // (A persistent variant - two 1024-thread CTAs per SM walking the tiles - was measured and is slower: 54.7 vs 39.4 ms per
 // 256x256 world; with one tile per CTA the block scheduler overlaps the staging of one tile with the arithmetic of others.)
-// One CTA of 32 x 8 threads per tile, four rows per thread: a quiet tile costs the launch of 8 warps, not 32.
+// One CTA of 32 x 4 threads per tile, eight rows per thread: a quiet tile costs the launch of 4 warps, not 32, and a tile CTA
+// (4 096 registers) fits next to the five resident CTAs of k_caves, with which erosion shares the SMs in a full generate
+// (profiles/r02_erode_rows.txt: 256x256 world, overlapped: 2 / 4 / 8 / 16 rows of threads 457.9 / 457.0 / 460.5 / 467.4 ms).
 // (2 / 3 / 4 / 6 tiles per CTA, so that the mostly quiet late sweeps launch fewer blocks, measured in round 2: 7.3 / 7.4 / 8.1 /
 // 8.4 ms against 6.1 per 128x128 region - the live tiles of a CTA run one after the other.)
 #ifndef MMG_ERODE_ROWS
-#define MMG_ERODE_ROWS 8
+#define MMG_ERODE_ROWS 4
 #endif
 constexpr int kErodeRows = MMG_ERODE_ROWS;
 __global__ void __launch_bounds__(32 * kErodeRows) k_erode_sweep(float* __restrict__ zones, int pIn, int pOut, int pUp, int pAccIn, int pAccOut,
