@@ -695,7 +695,10 @@ def run_own(args):
                     "that were neither claimed by an earlier placement nor excluded by the air test"})
     stages = {
         "S1": dict(r1, ms=float(stage_ms[1])), "S2": dict(r2, ms=float(stage_ms[2])),
-        "S3": dict(r3, ms=float(stage_ms[3]), sweeps=world.erosion_sweeps(), issue_slot_utilisation_pct=NCU_ISSUE["k_erode_sweep"][0]),
+        "S3": dict(r3, ms=float(stage_ms[3]), sweeps=world.erosion_sweeps(), issue_slot_utilisation_pct=NCU_ISSUE["k_erode_sweep"][0],
+                   note="runs on the side stream concurrently with S4 (config.stage_overlap): its kernel and stage times are stretched by the sharing "
+                        "and are not what the stage costs the step - serial it takes 27 ms per 256x256 world (profiles/r02_stage_overlap.txt), "
+                        "overlapped the step grows by about 12 ms over a step without erosion"),
         "S4": {"ms": float(stage_ms[4]), "bound": "fp32", "fp32_tflops": ach4, "fp32_frac": ach4 / (fp32_peak * world_size),
                "executed_fp32_frac": ach4 / (fp32_peak * world_size) * EXECUTED_OVER_ALGORITHMIC_CAVES,
                "hbm_gbs": sum_over_ranks(int((st >= 4).sum()) * BYTES_CAVES_CHUNK) / 1e9 / max(max_over_ranks(stage_ms[4] / 1e3), 1e-9),
