@@ -1,5 +1,5 @@
-# round 2, call 3K (GPU box): the round's evidence run - GPU suite, default bench (with the CPU leg), reference arm, BASELINE configs 3 and 4, smoke, mesh
-OUT=gpurun_out/r3k; mkdir -p $OUT
+# round 2, (GPU box): the round's evidence run - GPU suite, default bench (with the CPU leg), reference arm, BASELINE configs 3 and 4, smoke, mesh
+OUT=gpurun_out/evidence; mkdir -p $OUT
 timeout 1200 python -m pytest tests -m gpu -x -q > $OUT/pytest.log 2>&1; echo "pytest rc=$?"; tail -2 $OUT/pytest.log
 timeout 1200 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; tail -c 300 $OUT/bench.err
 timeout 900 python bench.py --impl reference > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref rc=$?"
@@ -11,7 +11,7 @@ python - <<'PY'
 import json
 for f in ('bench','bench_ref','bench_c3','bench_c4'):
     try:
-        d=json.loads(open('gpurun_out/r3k/%s.json'%f).read().strip().splitlines()[-1])
+        d=json.loads(open('gpurun_out/evidence/%s.json'%f).read().strip().splitlines()[-1])
         print(f, d.get('value'), d.get('ms_per_step'), (d.get('e2e') or {}).get('value'), (d.get('cpu_baseline') or {}).get('value'))
     except Exception as e: print(f, 'ERR', e)
 PY

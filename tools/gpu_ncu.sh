@@ -1,5 +1,5 @@
-# round 2, call 3J (GPU box): final ncu evidence - launch list of the bench command, --set full captures of the five hot kernels, census
-OUT=gpurun_out/r3j; mkdir -p $OUT
+# round 2, (GPU box): final ncu evidence - launch list of the bench command, --set full captures of the five hot kernels, census
+OUT=gpurun_out/ncu; mkdir -p $OUT
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv python bench.py --world 48 --steps 1 --warmup 1 --no-cpu > $OUT/ncu_bench.log 2>&1; echo "ncu launch list rc=$?"
 # one launch from the middle of a 128x128-chunk world (launch 2 of 5 for the cave kernel, 4 of 8 for the fill kernels)
 for K in k_caves:2 k_fill_features:4 k_fill_rock:4 k_fill_terrain:4 k_erode_sweep:300; do
