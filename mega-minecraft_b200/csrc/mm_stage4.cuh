@@ -192,7 +192,7 @@ __device__ __forceinline__ float special_cave_noise_cached(float px, float py, f
         q3 = fminf(q3, q);
     };
     const int ux0 = ix - 1 - bx, uy0 = iy - 1 - by, uz0 = iz - 1 - bz;
-    // the table holds cells [box, box + (ex, ey, ez)) (ex, ey, ez in 3..kCaveBox: what the slab's voxels touch)
+    // the table holds cells [box, box + (ex, ey, ez)) (k_caves: a fixed kCaveBox^3 block placed around the expected sample positions)
     if ((unsigned)ux0 <= (unsigned)(ex - 3) && (unsigned)uy0 <= (unsigned)(ey - 3) && (unsigned)uz0 <= (unsigned)(ez - 3))
     {
         // the whole 3x3x3 neighbourhood is in the table (nearly always): no per-cell bounds tests

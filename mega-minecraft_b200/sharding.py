@@ -145,25 +145,42 @@ class HaloExchange:
 COST_WEIGHTS = (0.0, 8.842e-4, 2.056e-3, 4.005e-3)      # ms: x cave voxels / 1e4, x fill voxels / 1e4, x land columns / 256, per chunk
 
 
-def chunk_cost_map(gen, region, rank=0, world_size=1, weights=COST_WEIGHTS):
+_cost_buffers = {}      # (shape, device) -> tensors reused by chunk_cost_map: it runs inside every timed step
+
+
+def chunk_cost_map(gen, region, rank=0, world_size=1, weights=COST_WEIGHTS, stride=2):
     """(rnz, rnx) predicted cost per chunk of `region`, from stage 1 alone: every rank evaluates the features of a strip of
-    rows (mmgen_chunk_costs), the strips are all-gathered, every rank ends up with the same map."""
+    rows (mmgen_chunk_costs), the strips are all-gathered, every rank ends up with the same map. The features are taken at every
+    `stride`-th chunk in x and z and repeated over the chunks in between: terrain height and land fraction vary over hundreds of
+    blocks, a quarter of the stage-1 evaluations place the cuts as well as all of them."""
     rx0, rz0, rnx, rnz = region
-    rows = tiling.split_points(rz0, rnz, world_size) if rnz >= world_size else [rz0] + [rz0 + rnz] * world_size
+    snx, snz = -(-rnx // stride), -(-rnz // stride)      # sampled grid
+    rows = tiling.split_points(0, snz, world_size) if snz >= world_size else [0] + [snz] * world_size
     z0, z1 = rows[rank], rows[rank + 1]
-    zz, xx = np.meshgrid(np.arange(z0, z1, dtype=np.int32), np.arange(rx0, rx0 + rnx, dtype=np.int32), indexing="ij")
+    zz, xx = np.meshgrid(rz0 + stride * np.arange(z0, z1, dtype=np.int32), rx0 + stride * np.arange(snx, dtype=np.int32), indexing="ij")
     origins = np.ascontiguousarray(np.stack([xx.ravel() * 16, zz.ravel() * 16], axis=1), np.int32)
-    f = gen.chunk_costs(origins).reshape(z1 - z0, rnx, 3) if len(origins) else np.zeros((0, rnx, 3), np.float32)
+    f = gen.chunk_costs(origins).reshape(z1 - z0, snx, 3) if len(origins) else np.zeros((0, snx, 3), np.float32)
     if dist.is_initialized() and dist.get_world_size() > 1:
         most = max(b - a for a, b in zip(rows, rows[1:]))
-        t = torch.zeros((most, rnx, 3), dtype=torch.float32)
-        t[:z1 - z0] = torch.from_numpy(f)
-        t = t.to(_dev(), non_blocking=True)
-        out = torch.empty((world_size * most, rnx, 3), dtype=torch.float32, device=t.device)
-        dist.all_gather_into_tensor(out, t)          # one collective, one read-back
-        out = out.cpu().numpy().reshape(world_size, most, rnx, 3)
+        dev = _dev()
+        key = (most, snx, world_size, str(dev))
+        if key not in _cost_buffers:
+            pin = dev.type == "cuda"
+            _cost_buffers[key] = (torch.zeros((most, snx, 3), dtype=torch.float32, pin_memory=pin),
+                                  torch.empty((most, snx, 3), dtype=torch.float32, device=dev),
+                                  torch.empty((world_size * most, snx, 3), dtype=torch.float32, device=dev),
+                                  torch.empty((world_size * most, snx, 3), dtype=torch.float32, pin_memory=pin))
+        h_in, d_in, d_out, h_out = _cost_buffers[key]
+        h_in[:z1 - z0] = torch.from_numpy(f)
+        d_in.copy_(h_in, non_blocking=True)
+        dist.all_gather_into_tensor(d_out, d_in)          # one collective, one read-back
+        h_out.copy_(d_out)
+        out = h_out.numpy().reshape(world_size, most, snx, 3)
         f = np.concatenate([out[r, :b - a] for r, (a, b) in enumerate(zip(rows, rows[1:]))], axis=0)
-    return weights[0] * f[:, :, 0] / 1e4 + weights[1] * f[:, :, 1] / 1e4 + weights[2] * f[:, :, 2] / 256.0 + weights[3]
+    c = weights[0] * f[:, :, 0] / 1e4 + weights[1] * f[:, :, 1] / 1e4 + weights[2] * f[:, :, 2] / 256.0 + weights[3]
+    if stride > 1:
+        c = np.repeat(np.repeat(c, stride, axis=0), stride, axis=1)[:rnz, :rnx]
+    return c
 
 
 class Balancer:
