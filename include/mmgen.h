@@ -311,6 +311,9 @@ int mmgen_set_rock_queue_per_chunk(int slots);
 int mmgen_set_serial_stages(int serial);
 /* achieved FP32 FMA rate of this device (TFLOP/s, 8 independent FFMA chains per thread on every SM): roofline denominator */
 int mmgen_measure_fp32_peak(float* out_tflops);
+/* self-test: the packed-fp32 noise routines (two samples per call on sm_100's FFMA2 / FADD2 / FMUL2) against the scalar routines they
+ * replace, at n pseudo-random positions; *out_mismatches = results that differ in any bit (must be 0) */
+int mmgen_selftest_packed_noise(int n, uint32_t seed, uint64_t* out_mismatches);
 
 #ifdef __cplusplus
 }

@@ -99,6 +99,12 @@ class ChunkGen:
         self._check(self.L.mmgen_chunk_costs(origins.shape[0], _ptr(origins), _ptr(out)))
         return out
 
+    def selftest_packed_noise(self, n=1 << 22, seed=1):
+        """mmgen_selftest_packed_noise: number of packed-noise results that differ from the scalar routines in any bit (must be 0)."""
+        v = ctypes.c_uint64(0)
+        self._check(self.L.mmgen_selftest_packed_noise(int(n), ctypes.c_uint32(int(seed)), ctypes.byref(v)))
+        return v.value
+
     def set_serial_stages(self, serial):
         """Measurement knob (mmgen_set_serial_stages): run layers + erosion and the caves one after the other instead of overlapped."""
         self._check(self.L.mmgen_set_serial_stages(1 if serial else 0))

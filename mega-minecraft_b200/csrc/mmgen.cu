@@ -1472,6 +1472,62 @@ int mmgen_work_counters(uint64_t* out32, int reset)
 
 const char* mmgen_kernel_name(int slot) { return (slot >= 0 && slot < K_NUM) ? kKernelNames[slot] : ""; }
 
+// self-test of the packed-fp32 noise routines (mm_arith.cuh): every pair evaluation against the two scalar evaluations it stands
+// for, bit for bit, at n pseudo-random positions of the magnitudes the pipeline uses (offsets of thousands, steps of 1e-3 .. 1)
+__global__ void k_selftest_packed_noise(int n, unsigned seed, unsigned long long* mismatches)
+{
+    noise_tab_stage();
+    unsigned long long bad = 0ull;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        Minstd rng = make_rng3(i, (int)(seed & 0x3ff), (int)(seed >> 10));
+        const float sc = (i & 1) ? 6000.f : ((i & 2) ? 40.f : 2.f);
+        const float ax = rng.u11() * sc, ay = rng.u11() * sc, az = rng.u11() * sc;
+        const float bx = ax + 5923.45f, by = ay + 4129.42f, bz = az + 5790.48f;
+        auto ne = [](float p, float q) { return __float_as_uint(p) != __float_as_uint(q); };
+        {
+            const f32x2 r = simplex3x2_raw<false>(f2_make(ax, bx), f2_make(ay, by), f2_make(az, bz));
+            bad += ne(f2_lo(r), simplex3_raw<false>(ax, ay, az)) + ne(f2_hi(r), simplex3_raw<false>(bx, by, bz));
+            const f32x2 t = simplex3x2_raw<true>(f2_make(ax, bx), f2_make(ay, by), f2_make(az, bz));
+            bad += ne(f2_lo(t), simplex3_raw<true>(ax, ay, az)) + ne(f2_hi(t), simplex3_raw<true>(bx, by, bz));
+        }
+        {
+            const f32x2 r = simplex2x2_raw<false>(f2_make(ax, bx), f2_make(az, bz));
+            bad += ne(f2_lo(r), simplex2_raw<false>(ax, az)) + ne(f2_hi(r), simplex2_raw<false>(bx, bz));
+            const f32x2 t = simplex2x2_raw<true>(f2_make(ax, bx), f2_make(az, bz));
+            bad += ne(f2_lo(t), simplex2_raw<true>(ax, az)) + ne(f2_hi(t), simplex2_raw<true>(bx, bz));
+        }
+        {
+            const float px = ax * 0.004f, py = ay * 0.004f, pz = az * 0.004f;
+            bad += ne(fbm3_paired<5>(px, py, pz), fbm3<5>(px, py, pz)) + ne(fbm3_paired<4, true>(px, py, pz), fbm3<4, true>(px, py, pz)) +
+                   ne(fbm3_paired<3>(px, py, pz), fbm3<3>(px, py, pz));
+            float o1, o2, o3;
+            fbm3_from3<5>(px, py, pz, &o1, &o2, &o3);
+            bad += ne(o1, fbm3<5>(px, py, pz)) + ne(o2, fbm3<5>(px + 5923.45f, py + 4129.42f, pz + 5790.48f)) +
+                   ne(o3, fbm3<5>(px + 1765.68f, py + 4704.36f, pz + 5692.12f));
+            const f32x2 q = fbm2x2<4>(f2_make(px, bx * 0.01f), f2_make(pz, bz * 0.01f));
+            bad += ne(f2_lo(q), fbm2<4>(px, pz)) + ne(f2_hi(q), fbm2<4>(bx * 0.01f, bz * 0.01f));
+        }
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+int mmgen_selftest_packed_noise(int n, uint32_t seed, uint64_t* out_mismatches)
+{
+    if (requireReady()) return 1;
+    if (n <= 0 || !out_mismatches) { g_lastError = "mmgen_selftest_packed_noise: bad arguments"; return 1; }
+    unsigned long long* d = nullptr;
+    MMG_CUDA(cudaMalloc(&d, sizeof(unsigned long long)));
+    MMG_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), g_stream));
+    MMG_LAUNCH(k_selftest_packed_noise, kNumSMs * 4, 256, kNoiseSmemBytes, g_stream, n, (unsigned)seed, d);
+    unsigned long long h = 0ull;
+    MMG_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, g_stream));
+    MMG_CUDA(cudaStreamSynchronize(g_stream));
+    cudaFree(d);
+    *out_mismatches = (uint64_t)h;
+    return 0;
+}
+
 int mmgen_measure_fp32_peak(float* out_tflops)
 {
     if (requireReady()) return 1;

@@ -381,6 +381,13 @@ def test_c4_cave_and_fill_stress_32x32(gen, mm, oracle):
     world.close()
 
 
+def test_packed_noise_equals_scalar_noise(gen):
+    """The noise kernels evaluate simplex samples two at a time on the packed fp32 instructions of sm_100 (mm_arith.cuh). Every
+    pair routine must return, bit for bit, what the two scalar evaluations return - 4 M positions x 21 comparisons each."""
+    for seed in (1, 77):
+        assert gen.selftest_packed_noise(1 << 22, seed) == 0
+
+
 def test_stage_overlap_is_result_neutral(gen, mm, golden):
     """A full generate runs layers + erosion on a side stream while the caves (stage-1 inputs only) run on the main stream. Serial
     and overlapped runs must give the same world - the reference's blocks for the golden window, and identical per-chunk hashes,
