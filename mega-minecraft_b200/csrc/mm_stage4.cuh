@@ -333,26 +333,24 @@ __device__ __forceinline__ int cave_threshold_noise(int wx, int y, int wz, bool 
 // The "huge caves" term of the threshold, smoothstep(0.2, 0.4, fbm3<4>(pos * 0.00035)), is exactly 0 wherever the fbm is
 // <= 0.2 - most of the world - yet the reference pays its four simplex3 at every voxel. The fbm is Lipschitz: one octave is
 // 42 * simplex3_raw, whose gradient norm stays below 7.6 (20 M finite-difference samples of the oracle's restatement;
-// kSimplex3Lipschitz = 10 is used), so along y the fbm moves by at most sum_i 2^-(i+1) * 2^i * 0.00035 * 10 = 0.007 per
-// voxel. One sample at the middle of each 16-voxel run (y = 16 s + 8, s = 0..8: every voxel the threshold is evaluated
-// for has y < 142) that is <= 0.2 - 8 * 0.007 - 0.004 (rounding, sample position) proves huge == 0 for the whole run.
-// Bit s of the mask = proved for y in [16 s, 16 s + 16). Validated over the 256x256-chunk world by the census build
-// (-DMMG_FEATURE_STATS evaluates the term anyway and counts disagreements: none) and by the unchanged world hash.
+// kSimplex3Lipschitz = 10 is used), so the fbm moves by at most sum_i 2^-(i+1) * 2^i * 0.00035 * 10 = 0.007 per voxel of
+// distance, in any direction. One sample at the middle of each 16-voxel run (y = 16 s + 8, s = 0..8: every voxel the threshold
+// is evaluated for has y < 142) that is <= 0.2 - (distance to the farthest voxel it speaks for) * 0.007 - 0.004 (rounding) proves
+// huge == 0 there. Validated by the census build (-DMMG_FEATURE_STATS evaluates the term anyway and counts disagreements: none),
+// by tests/test_exact_shortcuts.py on the oracle's fbm and by the unchanged world hash.
 constexpr float kSimplex3Lipschitz = 10.f;
 constexpr int kHugeRun = 16, kHugeSamples = 9;
-__device__ __forceinline__ unsigned huge_zero_mask(int wx, int wz)
+// The bound holds in every direction, so one sample serves a 4 x 4 block of columns: taken at the block's centre (x0 + 1.5, z0 + 1.5)
+// and the middle of the run, it is at most sqrt(1.5^2 + 1.5^2 + 8^2) = 8.28 voxels from any voxel of the 4 x 4 x 16 box - the margin
+// grows from 8 to 8.3 voxels' worth and the chunk needs 144 evaluations of the fbm instead of 2 304.
+// Bit s of the result = proved for y in [16 s, 16 s + 16) of every column x0 .. x0 + 3, z0 .. z0 + 3.
+__device__ __forceinline__ bool huge_zero_sample(int wx0, int wz0, int s)
 {
     constexpr float perVoxel = 4.f * 0.5f * (0.0050f * 0.0700f) * kSimplex3Lipschitz;
-    constexpr float limit = 0.2f - (kHugeRun / 2) * perVoxel - 0.004f;
-    const float npx = (float)wx * 0.0050f, npz = (float)wz * 0.0050f;
-    unsigned mask = 0u;
-#pragma unroll 1
-    for (int s = 0; s < kHugeSamples; ++s)
-    {
-        const float npy = (float)(kHugeRun * s + kHugeRun / 2) * 0.0050f;
-        if (fbm3_paired<4>(npx * 0.0700f, npy * 0.0700f, npz * 0.0700f) <= limit) mask |= 1u << s;
-    }
-    return mask;
+    constexpr float limit = 0.2f - 8.3f * perVoxel - 0.004f;
+    const float npx = ((float)wx0 + 1.5f) * 0.0050f, npz = ((float)wz0 + 1.5f) * 0.0050f;
+    const float npy = (float)(kHugeRun * s + kHugeRun / 2) * 0.0050f;
+    return fbm3_paired<4>(npx * 0.0700f, npy * 0.0700f, npz * 0.0700f) <= limit;
 }
 
 struct CaveColumn { float obw, ravTop, ravDepth; int ravActive; unsigned hugeZeroMask; };
@@ -360,10 +358,18 @@ struct CaveColumn { float obw, ravTop, ravDepth; int ravActive; unsigned hugeZer
 __global__ void __launch_bounds__(256) k_cave_columns(const int* __restrict__ chunkList, const int2* __restrict__ origins,
                                                       const float* __restrict__ biomeWeights, CaveColumn* __restrict__ cols)
 {
+    __shared__ unsigned shHuge[16];      // per 4 x 4 block of columns: huge-caves term proved 0 for run s
+    const int idx = threadIdx.x;
+    if (idx < 16) shHuge[idx] = 0u;
     noise_tab_stage();
     const int li = blockIdx.x, chunk = chunkList ? chunkList[li] : li;
-    const int idx = threadIdx.x;
     const int2 o = origins[chunk];
+    if (idx < 16 * kHugeSamples)
+    {
+        const int b = idx / kHugeSamples, sRun = idx % kHugeSamples;
+        if (huge_zero_sample(o.x + 4 * (b & 3), o.y + 4 * (b >> 2), sRun)) atomicOr(&shHuge[b], 1u << sRun);
+    }
+    __syncthreads();
     const float* cw = biomeWeights + (size_t)chunk * (NUM_BIOMES * 256) + idx;
     float obw = 0.f;
 #pragma unroll
@@ -371,7 +377,7 @@ __global__ void __launch_bounds__(256) k_cave_columns(const int* __restrict__ ch
     const Ravine r = ravine_column(o.x + (idx & 15), o.y + (idx >> 4), obw);
     CaveColumn c;
     c.obw = obw; c.ravTop = r.top; c.ravDepth = r.depth; c.ravActive = r.active ? 1 : 0;
-    c.hugeZeroMask = huge_zero_mask(o.x + (idx & 15), o.y + (idx >> 4));
+    c.hugeZeroMask = shHuge[((idx & 15) >> 2) + 4 * (idx >> 6)];
     cols[(size_t)li * 256 + idx] = c;
 }
 
