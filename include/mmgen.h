@@ -192,7 +192,9 @@ int mmgen_region_close(MmgenRegionFile* r);
 int mmgen_world_sync(MmgenWorld* w);
 /* furthest completed stage per chunk (0..6), raster order i = (cz-cz0)*nx + (cx-cx0) */
 int mmgen_world_stages(MmgenWorld* w, uint8_t* out);
-/* device time of the last mmgen_world_generate per stage (ms, CUDA events), stage 1..6 */
+/* device time of the last mmgen_world_generate per stage (ms, CUDA events), stage 1..6. When one call runs layers, erosion and
+ * caves, stages 2-3 run on a side stream concurrently with stage 4 (mmgen_set_serial_stages): their elapsed times overlap and do
+ * not add up to mmgen_world_total_ms. */
 int mmgen_world_stage_ms(MmgenWorld* w, float* out7);
 /* device time of the whole last mmgen_world_generate[_to_host] call (ms, CUDA events on the world's stream) */
 int mmgen_world_total_ms(MmgenWorld* w, float* out);
