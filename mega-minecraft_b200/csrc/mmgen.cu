@@ -156,6 +156,10 @@ struct MmgenWorld
     int* d_lushCount = nullptr;                      // [0] lush queue length, [2] near-rock, [3] bulk-rock queue lengths
     uint2* d_rockQueue = nullptr;                    // rock voxels of one fill batch waiting for getCaveBiome (k_fill_rock)
     size_t fillCap = 0;                              // chunks per fill batch the scratch above (d_gF .. d_rockQueue) is sized for
+    // second set of gathered lists + Prep records: a call that fills several batches gathers and prepares batch b + 1 on the side
+    // stream while batch b's terrain / rock passes run (allocated by the first such call)
+    FeaturePlacement* d_gF2 = nullptr; CaveFeaturePlacement* d_gCF2 = nullptr; GatherInfo* d_info2 = nullptr; Prep* d_prepF2 = nullptr; Prep* d_prepC2 = nullptr;
+    cudaEvent_t evGather[2] = {}, evScan[2] = {};    // per set: gathered + prepared (side stream); the placement scan is done with it (main stream)
     size_t fillHint = 0;                             // streaming sessions: the most chunks a tick can fill (0 = a batch world)
     bool reserving = false;                          // worldReserve: the stage runners allocate their buffers and return
     uint8_t* d_blocks = nullptr;                     // [chunk][16][16][384]
@@ -417,10 +421,11 @@ static bool g_serialStages = false;                    // mmgen_set_serial_stage
 static int g_rockQueuePerChunk = kRockQueuePerChunk;   // mmgen_set_rock_queue_per_chunk (tuning / test knob, <= kRockQueuePerChunk)
 
 // the kernel sequence of Chunk::fill for one batch of m chunks (lists indexed by batch position)
-static int launchFill(int m, const int* d_list, const int2* d_origins, const float* d_height, const float* d_weights, const float* d_layers,
-                      const CaveLayer* d_caves, const FeaturePlacement* d_gF, const CaveFeaturePlacement* d_gCF, GatherInfo* d_info,
-                      Prep* d_prepF, Prep* d_prepC, int strideF, int strideCF, uint8_t* d_blocks, uint2* d_rockQueue, uint2* d_lushQueue,
-                      int* d_counters, cudaStream_t stream)
+// the fill of one batch in three parts, so that the world path can run the placement preparation of the NEXT batch on its side
+// stream while this batch's terrain / rock passes run: (1) terrain, rock, lush; (2) Prep records of the gathered lists;
+// (3) the placement scan and the decorators
+static int launchFillTerrain(int m, const int* d_list, const int2* d_origins, const float* d_height, const float* d_weights, const float* d_layers,
+                             const CaveLayer* d_caves, uint8_t* d_blocks, uint2* d_rockQueue, uint2* d_lushQueue, int* d_counters, cudaStream_t stream)
 {
     const int rockCap = (int)std::min<size_t>((size_t)m * g_rockQueuePerChunk, (size_t)kFillBatch * kRockQueuePerChunk);
     MMG_CUDA(cudaMemsetAsync(d_counters, 0, 4 * sizeof(int), stream));
@@ -430,12 +435,32 @@ static int launchFill(int m, const int* d_list, const int2* d_origins, const flo
                                                  (const uint2*)d_rockQueue, rockCap, d_blocks, d_lushQueue, d_counters));
     MMG_TIMED(K_FILL_LUSH, stream, 1, MMG_LAUNCH(k_fill_lush, kNumSMs * 8, 128, kNoiseSmemBytes, stream, d_origins, (const uint2*)d_lushQueue,
                                                  (const int*)d_counters, d_blocks));
+    return 0;
+}
+static int launchFillPrepare(int m, const int* d_list, const int2* d_origins, const FeaturePlacement* d_gF, const CaveFeaturePlacement* d_gCF,
+                             GatherInfo* d_info, Prep* d_prepF, Prep* d_prepC, int strideF, int strideCF, cudaStream_t stream)
+{
     MMG_TIMED(K_PREPARE, stream, 1, MMG_LAUNCH(k_prepare_placements, m, 256, 0, stream, d_list, d_origins, d_gF, d_gCF, d_info, strideF, strideCF,
                                                d_prepF, d_prepC));
+    return 0;
+}
+static int launchFillFeatures(int m, const int* d_list, const int2* d_origins, const float* d_height, const float* d_weights, const CaveLayer* d_caves,
+                              const FeaturePlacement* d_gF, const CaveFeaturePlacement* d_gCF, const GatherInfo* d_info, const Prep* d_prepF,
+                              const Prep* d_prepC, int strideF, int strideCF, uint8_t* d_blocks, cudaStream_t stream)
+{
     MMG_TIMED(K_FILL_FEATURES, stream, 1, MMG_LAUNCH(k_fill_features, m * 12, kFeatThreads, kNoiseSmemBytes, stream, d_list, d_origins, d_gF, d_gCF,
-                                                     (const Prep*)d_prepF, (const Prep*)d_prepC, (const GatherInfo*)d_info, strideF, strideCF, d_blocks));
+                                                     d_prepF, d_prepC, d_info, strideF, strideCF, d_blocks));
     MMG_TIMED(K_DECORATORS, stream, 1, MMG_LAUNCH(k_decorators, m, 256, 0, stream, d_list, m, d_origins, d_height, d_weights, d_caves, d_blocks));
     return 0;
+}
+static int launchFill(int m, const int* d_list, const int2* d_origins, const float* d_height, const float* d_weights, const float* d_layers,
+                      const CaveLayer* d_caves, const FeaturePlacement* d_gF, const CaveFeaturePlacement* d_gCF, GatherInfo* d_info,
+                      Prep* d_prepF, Prep* d_prepC, int strideF, int strideCF, uint8_t* d_blocks, uint2* d_rockQueue, uint2* d_lushQueue,
+                      int* d_counters, cudaStream_t stream)
+{
+    return launchFillTerrain(m, d_list, d_origins, d_height, d_weights, d_layers, d_caves, d_blocks, d_rockQueue, d_lushQueue, d_counters, stream) ||
+           launchFillPrepare(m, d_list, d_origins, d_gF, d_gCF, d_info, d_prepF, d_prepC, strideF, strideCF, stream) ||
+           launchFillFeatures(m, d_list, d_origins, d_height, d_weights, d_caves, d_gF, d_gCF, d_info, d_prepF, d_prepC, strideF, strideCF, d_blocks, stream);
 }   // chunks gathered + filled per launch group (bounds the gathered-list buffers)
 
 extern "C" int mmgen_feature_placements(int n, const int32_t* origins, const float* heightfield, const float* biomeWeights,
@@ -612,6 +637,8 @@ int mmgen_world_create(int cx0, int cz0, int nx, int nz, MmgenWorld** out)
         MMG_CUDA(cudaStreamCreateWithPriority(&w->sideStream, cudaStreamNonBlocking, prHigh));
     }
     for (auto& e : w->evSide) MMG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : w->evGather) MMG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : w->evScan) MMG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : w->ev) MMG_CUDA(cudaEventCreate(&e));
     for (auto& e : w->evMesh) MMG_CUDA(cudaEventCreate(&e));
     for (auto& e : w->evBatch) MMG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -669,6 +696,9 @@ int mmgen_world_destroy(MmgenWorld* w)
     if (w->copyStream) cudaStreamDestroy(w->copyStream);
     if (w->sideStream) cudaStreamDestroy(w->sideStream);
     for (auto& e : w->evSide) if (e) cudaEventDestroy(e);
+    for (auto& e : w->evGather) if (e) cudaEventDestroy(e);
+    for (auto& e : w->evScan) if (e) cudaEventDestroy(e);
+    cudaFree(w->d_gF2); cudaFree(w->d_gCF2); cudaFree(w->d_info2); cudaFree(w->d_prepF2); cudaFree(w->d_prepC2);
     delete w;
     return 0;
 }
@@ -828,7 +858,9 @@ static int worldFill(MmgenWorld* w, const std::vector<int>& list, uint8_t* hostB
         const size_t cap = std::min<size_t>((size_t)kFillBatch, std::max(need, hint));
         MMG_CUDA(cudaStreamSynchronize(w->stream));
         cudaFree(w->d_gF); cudaFree(w->d_gCF); cudaFree(w->d_info); cudaFree(w->d_prepF); cudaFree(w->d_prepC); cudaFree(w->d_rockQueue);
+        cudaFree(w->d_gF2); cudaFree(w->d_gCF2); cudaFree(w->d_info2); cudaFree(w->d_prepF2); cudaFree(w->d_prepC2);
         w->d_gF = nullptr; w->d_gCF = nullptr; w->d_info = nullptr; w->d_prepF = nullptr; w->d_prepC = nullptr; w->d_rockQueue = nullptr;
+        w->d_gF2 = nullptr; w->d_gCF2 = nullptr; w->d_info2 = nullptr; w->d_prepF2 = nullptr; w->d_prepC2 = nullptr;
         w->fillCap = 0;
         MMG_CUDA(cudaMalloc(&w->d_gF, cap * MAX_FEATURES * sizeof(FeaturePlacement)));
         MMG_CUDA(cudaMalloc(&w->d_gCF, cap * MAX_CAVE_FEATURES * sizeof(CaveFeaturePlacement)));
@@ -842,18 +874,61 @@ static int worldFill(MmgenWorld* w, const std::vector<int>& list, uint8_t* hostB
     if (!w->d_lushCount) MMG_CUDA(cudaMalloc(&w->d_lushCount, 4 * sizeof(int)));
     if (w->reserving) return 0;
     if (worldUploadList(w, list)) return 1;
+    const bool pipelined = nBatches > 1;
+    if (pipelined && !w->d_gF2)
+    {
+        MMG_CUDA(cudaMalloc(&w->d_gF2, w->fillCap * MAX_FEATURES * sizeof(FeaturePlacement)));
+        MMG_CUDA(cudaMalloc(&w->d_gCF2, w->fillCap * MAX_CAVE_FEATURES * sizeof(CaveFeaturePlacement)));
+        MMG_CUDA(cudaMalloc(&w->d_info2, w->fillCap * sizeof(GatherInfo)));
+        MMG_CUDA(cudaMalloc(&w->d_prepF2, w->fillCap * MAX_FEATURES * sizeof(Prep)));
+        MMG_CUDA(cudaMalloc(&w->d_prepC2, w->fillCap * MAX_CAVE_FEATURES * sizeof(Prep)));
+    }
+    FeaturePlacement* const gF[2] = {w->d_gF, w->d_gF2};
+    CaveFeaturePlacement* const gCF[2] = {w->d_gCF, w->d_gCF2};
+    GatherInfo* const info[2] = {w->d_info, w->d_info2};
+    Prep* const prepF[2] = {w->d_prepF, w->d_prepF2};
+    Prep* const prepC[2] = {w->d_prepC, w->d_prepC2};
+    // gathered lists + Prep records of batch b into set b & 1, on stream st
+    auto gather = [&](size_t b, cudaStream_t st) -> int {
+        const size_t b0 = b * (size_t)kFillBatch;
+        const int m = (int)std::min<size_t>(kFillBatch, list.size() - b0), set = pipelined ? (int)(b & 1) : 0;
+        const int* dl = w->d_list + b0;
+        MMG_TIMED(K_GATHER, st, 1, MMG_LAUNCH(k_gather_features, m, 256, 0, st, dl, (const int2*)w->d_origins,
+                                              (const FeaturePlacement*)w->d_features, (const CaveFeaturePlacement*)w->d_caveFeatures,
+                                              (const int*)w->d_counts, nx, gF[set], gCF[set], info[set]));
+        return launchFillPrepare(m, dl, (const int2*)w->d_origins, gF[set], gCF[set], info[set], prepF[set], prepC[set], MAX_FEATURES, MAX_CAVE_FEATURES, st);
+    };
+    if (pipelined)
+    {
+        // the side stream starts where the main stream is now (placements done, list uploaded) with batch 0
+        MMG_CUDA(cudaEventRecord(w->evSide[0], w->stream));
+        MMG_CUDA(cudaStreamWaitEvent(w->sideStream, w->evSide[0], 0));
+        if (gather(0, w->sideStream)) return 1;
+        MMG_CUDA(cudaEventRecord(w->evGather[0], w->sideStream));
+    }
     for (size_t b0 = 0; b0 < list.size(); b0 += kFillBatch)
     {
         const int m = (int)std::min<size_t>(kFillBatch, list.size() - b0);
         const int* dl = w->d_list + b0;
-        MMG_TIMED(K_GATHER, w->stream, 1, MMG_LAUNCH(k_gather_features, m, 256, 0, w->stream, dl, (const int2*)w->d_origins,
-                                                     (const FeaturePlacement*)w->d_features, (const CaveFeaturePlacement*)w->d_caveFeatures,
-                                                     (const int*)w->d_counts, nx, w->d_gF, w->d_gCF, w->d_info));
-        if (launchFill(m, dl, (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights, (const float*)w->d_eroded,
-                       (const CaveLayer*)w->d_caves, (const FeaturePlacement*)w->d_gF, (const CaveFeaturePlacement*)w->d_gCF,
-                       w->d_info, w->d_prepF, w->d_prepC, MAX_FEATURES, MAX_CAVE_FEATURES, w->d_blocks, w->d_rockQueue, w->d_lushQueue,
-                       w->d_lushCount, w->stream))
+        const size_t b = b0 / kFillBatch;
+        const int set = pipelined ? (int)(b & 1) : 0;
+        if (pipelined && b + 1 < (size_t)nBatches)
+        {
+            // batch b + 1 is gathered and prepared on the side stream while this batch's terrain / rock passes run; its set was last read
+            // by the placement scan of batch b - 1
+            if (b >= 1) MMG_CUDA(cudaStreamWaitEvent(w->sideStream, w->evScan[set ^ 1], 0));
+            if (gather(b + 1, w->sideStream)) return 1;
+            MMG_CUDA(cudaEventRecord(w->evGather[set ^ 1], w->sideStream));
+        }
+        if (!pipelined && gather(b, w->stream)) return 1;
+        if (launchFillTerrain(m, dl, (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights, (const float*)w->d_eroded,
+                              (const CaveLayer*)w->d_caves, w->d_blocks, w->d_rockQueue, w->d_lushQueue, w->d_lushCount, w->stream))
             return 1;
+        if (pipelined) MMG_CUDA(cudaStreamWaitEvent(w->stream, w->evGather[set], 0));
+        if (launchFillFeatures(m, dl, (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights, (const CaveLayer*)w->d_caves,
+                               gF[set], gCF[set], info[set], prepF[set], prepC[set], MAX_FEATURES, MAX_CAVE_FEATURES, w->d_blocks, w->stream))
+            return 1;
+        if (pipelined) MMG_CUDA(cudaEventRecord(w->evScan[set], w->stream));
         if (enc)
         {
             slots.resize(m);
