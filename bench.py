@@ -13,7 +13,9 @@ region (BASELINE.json metric), its roofline reading and two measured baselines.
       `e2e`    = the same through mmgen_world_generate_to_host: chunk origins come from host memory and the raw block
                  volumes are delivered into pinned HOST memory inside the timed region.
       `e2e_encoded` = the same with the volumes run-length coded on the device (wire format MMCH1) - an extra, not the headline.
-      `roofline`, `stages` = per-stage algorithmic FLOPs / bytes over device time; S1-S3 from device work counters.
+      `roofline`, `stages` = per-stage algorithmic FLOPs / bytes over device time; S1-S3 and the placement scan from
+                 device work counters; ncu pipe figures of the committed captures next to the canonical-FLOP rates. Layers + erosion
+                 run on a side stream concurrently with the caves (config.stage_overlap): stage times overlap.
   python bench.py --config c4      BASELINE config 4: cave + fill stress on 32x32 chunks, S4 and S6 timed in isolation.
   python bench.py --config c3      BASELINE config 3: 64x64-chunk streaming region at the reference's tick pattern (mmgen_stream_*).
   python bench.py --impl reference [...]

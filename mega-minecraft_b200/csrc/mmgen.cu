@@ -361,7 +361,10 @@ extern "C" int mmgen_erode_zone(const float* gathered, float* out_eroded, int* o
     return 0;
 }
 
-constexpr int kCaveBatch = 4096;                       // chunks per cave launch group
+#ifndef MMG_CAVE_BATCH
+#define MMG_CAVE_BATCH 4096
+#endif
+constexpr int kCaveBatch = MMG_CAVE_BATCH;             // chunks per cave launch group
 constexpr int kCaveBiomeQueueCap = kCaveBatch * 256 * 8;  // cave-biome lookups queued per group (avg ~5.4 per column)
 
 // the kernel sequence of Chunk::generateCaves for m chunks (d_list: chunk indices or null; column terms indexed by batch position)
