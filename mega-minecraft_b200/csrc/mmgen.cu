@@ -361,6 +361,7 @@ extern "C" int mmgen_erode_zone(const float* gathered, float* out_eroded, int* o
     return 0;
 }
 
+// (8192 / 16384 chunks per group measured: 453.3 / 452.4 ms per 256x256 world against 454.0 - not worth 2x / 4x the queue memory)
 #ifndef MMG_CAVE_BATCH
 #define MMG_CAVE_BATCH 4096
 #endif
