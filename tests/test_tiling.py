@@ -160,3 +160,38 @@ def test_feedback_balancer_converges_and_partitions(pkg):
             first = imb if first is None else first
         final = [cost(t) for t in b.tiles()]
         assert max(final) / (sum(final) / len(final)) < 1.03 <= first
+
+
+def test_cost_map_samples_every_second_chunk_and_cuts_balance(pkg):
+    """chunk_cost_map evaluates the stage-1 features at every `stride`-th chunk (the sampled chunk's value stands for its stride x
+    stride block) and Balancer.cut_by_cost places the cuts of the 4 x 2 grid so that every tile carries about the same predicted
+    cost: for a smooth synthetic cost field the heaviest tile stays within a few per cent of the mean, where equal tiles do not."""
+    tiling, sharding = pkg
+    region = (-7, 3, 101, 64)
+    seen = []
+
+    class FakeGen:
+        def chunk_costs(self, origins):
+            seen.append(origins.copy())
+            x, z = origins[:, 0].astype(np.float64) / 16.0, origins[:, 1].astype(np.float64) / 16.0
+            f = 1.0 + 0.8 * np.sin(x / 23.0) * np.cos(z / 17.0) + 0.004 * (x + z)
+            return np.stack([f * 1e4, f * 2e4, 256.0 * np.ones_like(f)], axis=1).astype(np.float32)
+
+    w = (1.0, 0.5, 0.25, 0.1)
+    full = sharding.chunk_cost_map(FakeGen(), region, weights=w, stride=1)
+    half = sharding.chunk_cost_map(FakeGen(), region, weights=w, stride=2)
+    assert full.shape == half.shape == (region[3], region[2])
+    assert len(seen[0]) == region[2] * region[3] and len(seen[1]) == 51 * 32      # a quarter of the evaluations
+    assert np.array_equal(half[::2, ::2], full[::2, ::2])                          # sampled chunks carry their own value ...
+    assert np.array_equal(half[1::2, 1::2], full[0:-1:2, 0:-1:2][:half[1::2, 1::2].shape[0], :half[1::2, 1::2].shape[1]])   # ... and lend it to their block
+    for cost in (full, half):
+        tiles = sharding.Balancer(region, 8).cut_by_cost(cost)
+        cover = np.zeros((region[3], region[2]), np.int32)
+        loads = []
+        for (x0, z0, nx, nz) in tiles:
+            cover[z0 - region[1]:z0 - region[1] + nz, x0 - region[0]:x0 - region[0] + nx] += 1
+            loads.append(full[z0 - region[1]:z0 - region[1] + nz, x0 - region[0]:x0 - region[0] + nx].sum())
+        assert (cover == 1).all()
+        assert max(loads) / (sum(loads) / 8) < 1.06
+    equal = [full[z0 - region[1]:z0 - region[1] + nz, x0 - region[0]:x0 - region[0] + nx].sum() for (x0, z0, nx, nz) in tiling.tiles(*region, 8)]
+    assert max(equal) / (sum(equal) / 8) > 1.10
