@@ -446,6 +446,8 @@ def run_own(args):
 
     S = args.world
     gen = mm.ChunkGen(local_rank)
+    fill_overlap = mm.FILL_OVERLAP_DEFAULT if args.fill_overlap is None else args.fill_overlap
+    gen.set_fill_overlap(fill_overlap)
     region = (0, 0, S, S)
     # Tiling (N > 1): the cuts are placed by a cost PREDICTOR that needs stage 1 only - every rank evaluates the stage-1 cost
     # features of a strip of the region (mmgen_chunk_costs, < 1 ms), the strips are all-gathered and every rank derives the same
@@ -782,6 +784,7 @@ def main():
     ap.add_argument("--ref-zones", type=int, default=3, help="the reference CUDA arm generates ZxZ erosion zones (+ apron) per step")
     ap.add_argument("--cpu-cave-chunks", type=int, default=0, help="bound the CPU baseline's S4 sample (0 = the whole zone)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--fill-overlap", type=int, default=None, help="mmgen_set_fill_overlap mode (default: the library's)")
     ap.add_argument("--config", default="c5", choices=["c5", "c3", "c4"],
                     help="c5 (default): the 256x256-chunk world the metric is quoted on; c3: 64x64 streaming region at the reference's tick pattern; "
                          "c4: cave + fill stress on 32x32 chunks, S4 and S6 timed in isolation (BASELINE.json configs 3 and 4; one GPU)")

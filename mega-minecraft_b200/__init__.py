@@ -5,5 +5,5 @@ The directory name is not a Python identifier; load it with `mmgen_loader.load()
 """
 from .chunkgen import (  # noqa: F401
     ChunkGen, World, Terrain, TickStats, Vertex, RegionFile, decode_chunk, save_region, REFERENCE_COSTS, MmgenError, lib_path, build, CaveLayer, FeaturePlacement, CaveFeaturePlacement,
-    STAGE_HEIGHTFIELD, STAGE_LAYERS, STAGE_EROSION, STAGE_CAVES, STAGE_FEATURES, STAGE_FILL, STAGE_ALL,
+    STAGE_HEIGHTFIELD, STAGE_LAYERS, STAGE_EROSION, STAGE_CAVES, STAGE_FEATURES, STAGE_FILL, STAGE_ALL, FILL_OVERLAP_DEFAULT,
 )

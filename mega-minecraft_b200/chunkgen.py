@@ -15,6 +15,7 @@ _LIB = os.environ.get("MMGEN_LIB") or os.path.join(_HERE, "libmmgen.so")      # 
 
 STAGE_HEIGHTFIELD, STAGE_LAYERS, STAGE_EROSION, STAGE_CAVES, STAGE_FEATURES, STAGE_FILL = 1, 2, 4, 8, 16, 32
 STAGE_ALL = 63
+FILL_OVERLAP_DEFAULT = 8      # mmgen_set_fill_overlap mode the library starts in
 
 CaveLayer = np.dtype([("start", "<i4"), ("end", "<i4"), ("bottomBiome", "u1"), ("topBiome", "u1"), ("pad", "u1", (2,))])
 FeaturePlacement = np.dtype([("feature", "u1"), ("pad0", "u1", (3,)), ("x", "<i4"), ("y", "<i4"), ("z", "<i4"),
@@ -104,6 +105,11 @@ class ChunkGen:
         v = ctypes.c_uint64(0)
         self._check(self.L.mmgen_selftest_packed_noise(int(n), ctypes.c_uint32(int(seed)), ctypes.byref(v)))
         return v.value
+
+    def set_fill_overlap(self, mode):
+        """Scheduling knob (mmgen_set_fill_overlap): 0 = fill passes of a batch in sequence; g = overlap the next batch's terrain / rock
+        passes with this batch's placement scan, k_fill_rock at g CTAs per SM (+16: on the high-priority stream)."""
+        self._check(self.L.mmgen_set_fill_overlap(int(mode)))
 
     def set_serial_stages(self, serial):
         """Measurement knob (mmgen_set_serial_stages): run layers + erosion and the caves one after the other instead of overlapped."""

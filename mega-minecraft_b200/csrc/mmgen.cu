@@ -180,6 +180,7 @@ struct MmgenWorld
     cudaStream_t stream = nullptr;
     cudaStream_t copyStream = nullptr;   // device->host block copies overlapped with the fill (generate_to_host)
     cudaStream_t sideStream = nullptr;   // layers + erosion of a full generate, while the caves (which only need stage 1) run on `stream`
+    cudaStream_t fillStream = nullptr;   // terrain / rock / lush passes of the next fill batch under mmgen_set_fill_overlap (default priority)
     cudaEvent_t evSide[2] = {};          // fork / join of the side stream
     cudaEvent_t ev[14] = {};             // [2s-2, 2s-1] bracket stage s; [12, 13] bracket the whole generate
     cudaEvent_t evMesh[2] = {};          // bracket mmgen_world_mesh (its own pair: total_ms keeps the last generate's time)
@@ -423,6 +424,11 @@ extern "C" int mmgen_caves(int n, const int32_t* origins, const float* heightfie
 constexpr int kFillBatch = MMG_FILL_BATCH;
 static bool g_serialStages = false;                    // mmgen_set_serial_stages: no overlap of layers + erosion with the caves (measurement knob)
 static int g_rockQueuePerChunk = kRockQueuePerChunk;   // mmgen_set_rock_queue_per_chunk (tuning / test knob, <= kRockQueuePerChunk)
+// mmgen_set_fill_overlap: 0 = a batch's terrain / rock / lush passes and its placement scan run one after the other on the world's
+// stream; g > 0 = the terrain / rock / lush passes of batch b + 1 run on the side stream while the placement scan of batch b runs on
+// the main stream (they touch different chunks' volumes), with k_fill_rock's persistent grid at g CTAs per SM
+static int g_fillOverlap = 8;                          // 256x256 world on a B200: 454.2 ms off, 446.7 ms at 8 (profiles/r02_fill_overlap.txt)
+static int g_rockGridPerSM = MMG_ROCK_MINBLOCKS;
 
 // the kernel sequence of Chunk::fill for one batch of m chunks (lists indexed by batch position)
 // the fill of one batch in three parts, so that the world path can run the placement preparation of the NEXT batch on its side
@@ -435,7 +441,7 @@ static int launchFillTerrain(int m, const int* d_list, const int2* d_origins, co
     MMG_CUDA(cudaMemsetAsync(d_counters, 0, 4 * sizeof(int), stream));
     MMG_TIMED(K_FILL_TERRAIN, stream, 1, MMG_LAUNCH(k_fill_terrain, m * 16, kRowThreads, kNoiseSmemBytes, stream, d_list, d_origins, d_height,
                                                     d_weights, d_layers, d_caves, d_blocks, d_rockQueue, rockCap, d_counters));
-    MMG_TIMED(K_FILL_ROCK, stream, 1, MMG_LAUNCH(k_fill_rock, kNumSMs * MMG_ROCK_MINBLOCKS, 128, kNoiseSmemBytes, stream, d_origins, d_height,
+    MMG_TIMED(K_FILL_ROCK, stream, 1, MMG_LAUNCH(k_fill_rock, kNumSMs * g_rockGridPerSM, 128, kNoiseSmemBytes, stream, d_origins, d_height,
                                                  (const uint2*)d_rockQueue, rockCap, d_blocks, d_lushQueue, d_counters));
     MMG_TIMED(K_FILL_LUSH, stream, 1, MMG_LAUNCH(k_fill_lush, kNumSMs * 8, 128, kNoiseSmemBytes, stream, d_origins, (const uint2*)d_lushQueue,
                                                  (const int*)d_counters, d_blocks));
@@ -634,6 +640,7 @@ int mmgen_world_create(int cx0, int cz0, int nx, int nz, MmgenWorld** out)
     w->stage.assign(w->n, 0);
     MMG_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     MMG_CUDA(cudaStreamCreateWithFlags(&w->copyStream, cudaStreamNonBlocking));
+    MMG_CUDA(cudaStreamCreateWithFlags(&w->fillStream, cudaStreamNonBlocking));
     {
         // erosion is hundreds of short dependent launches: its blocks go first whenever the cave kernel frees an SM slot
         int prLow = 0, prHigh = 0;
@@ -699,6 +706,7 @@ int mmgen_world_destroy(MmgenWorld* w)
     if (w->stream) cudaStreamDestroy(w->stream);
     if (w->copyStream) cudaStreamDestroy(w->copyStream);
     if (w->sideStream) cudaStreamDestroy(w->sideStream);
+    if (w->fillStream) cudaStreamDestroy(w->fillStream);
     for (auto& e : w->evSide) if (e) cudaEventDestroy(e);
     for (auto& e : w->evGather) if (e) cudaEventDestroy(e);
     for (auto& e : w->evScan) if (e) cudaEventDestroy(e);
@@ -902,13 +910,20 @@ static int worldFill(MmgenWorld* w, const std::vector<int>& list, uint8_t* hostB
                                               (const int*)w->d_counts, nx, gF[set], gCF[set], info[set]));
         return launchFillPrepare(m, dl, (const int2*)w->d_origins, gF[set], gCF[set], info[set], prepF[set], prepC[set], MAX_FEATURES, MAX_CAVE_FEATURES, st);
     };
+    const bool overlapFill = pipelined && (g_fillOverlap & 15) > 0 && !g_serialStages;
+    g_rockGridPerSM = overlapFill ? std::min(g_fillOverlap & 15, (int)MMG_ROCK_MINBLOCKS) : (int)MMG_ROCK_MINBLOCKS;
+    // bit 4 of the knob: the overlapped passes go to the high-priority side stream instead of the default-priority fill stream
+    cudaStream_t const side = (overlapFill && !(g_fillOverlap & 16)) ? w->fillStream : w->sideStream;
     if (pipelined)
     {
         // the side stream starts where the main stream is now (placements done, list uploaded) with batch 0
         MMG_CUDA(cudaEventRecord(w->evSide[0], w->stream));
-        MMG_CUDA(cudaStreamWaitEvent(w->sideStream, w->evSide[0], 0));
-        if (gather(0, w->sideStream)) return 1;
-        MMG_CUDA(cudaEventRecord(w->evGather[0], w->sideStream));
+        MMG_CUDA(cudaStreamWaitEvent(side, w->evSide[0], 0));
+        if (!overlapFill)
+        {
+            if (gather(0, w->sideStream)) return 1;
+            MMG_CUDA(cudaEventRecord(w->evGather[0], w->sideStream));
+        }
     }
     for (size_t b0 = 0; b0 < list.size(); b0 += kFillBatch)
     {
@@ -916,18 +931,34 @@ static int worldFill(MmgenWorld* w, const std::vector<int>& list, uint8_t* hostB
         const int* dl = w->d_list + b0;
         const size_t b = b0 / kFillBatch;
         const int set = pipelined ? (int)(b & 1) : 0;
-        if (pipelined && b + 1 < (size_t)nBatches)
+        if (overlapFill)
         {
-            // batch b + 1 is gathered and prepared on the side stream while this batch's terrain / rock passes run; its set was last read
-            // by the placement scan of batch b - 1
-            if (b >= 1) MMG_CUDA(cudaStreamWaitEvent(w->sideStream, w->evScan[set ^ 1], 0));
-            if (gather(b + 1, w->sideStream)) return 1;
-            MMG_CUDA(cudaEventRecord(w->evGather[set ^ 1], w->sideStream));
+            // side stream: lists + Prep records of batch b into set b & 1 (last read by the placement scan of batch b - 2), then the
+            // batch's terrain / rock / lush passes (the rock and lush queues are only ever touched on this stream, in batch order).
+            // Main stream: the placement scan + decorators of batch b once the side stream has finished the batch - while the side
+            // stream is already in batch b + 1, whose chunks are different chunks.
+            if (b >= 2) MMG_CUDA(cudaStreamWaitEvent(side, w->evScan[set], 0));
+            if (gather(b, side)) return 1;
+            if (launchFillTerrain(m, dl, (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights, (const float*)w->d_eroded,
+                                  (const CaveLayer*)w->d_caves, w->d_blocks, w->d_rockQueue, w->d_lushQueue, w->d_lushCount, side))
+                return 1;
+            MMG_CUDA(cudaEventRecord(w->evGather[set], side));
         }
-        if (!pipelined && gather(b, w->stream)) return 1;
-        if (launchFillTerrain(m, dl, (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights, (const float*)w->d_eroded,
-                              (const CaveLayer*)w->d_caves, w->d_blocks, w->d_rockQueue, w->d_lushQueue, w->d_lushCount, w->stream))
-            return 1;
+        else
+        {
+            if (pipelined && b + 1 < (size_t)nBatches)
+            {
+                // batch b + 1 is gathered and prepared on the side stream while this batch's terrain / rock passes run; its set was last read
+                // by the placement scan of batch b - 1
+                if (b >= 1) MMG_CUDA(cudaStreamWaitEvent(w->sideStream, w->evScan[set ^ 1], 0));
+                if (gather(b + 1, w->sideStream)) return 1;
+                MMG_CUDA(cudaEventRecord(w->evGather[set ^ 1], w->sideStream));
+            }
+            if (!pipelined && gather(b, w->stream)) return 1;
+            if (launchFillTerrain(m, dl, (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights, (const float*)w->d_eroded,
+                                  (const CaveLayer*)w->d_caves, w->d_blocks, w->d_rockQueue, w->d_lushQueue, w->d_lushCount, w->stream))
+                return 1;
+        }
         if (pipelined) MMG_CUDA(cudaStreamWaitEvent(w->stream, w->evGather[set], 0));
         if (launchFillFeatures(m, dl, (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights, (const CaveLayer*)w->d_caves,
                                gF[set], gCF[set], info[set], prepF[set], prepC[set], MAX_FEATURES, MAX_CAVE_FEATURES, w->d_blocks, w->stream))
@@ -1638,6 +1669,12 @@ int mmgen_measure_fp32_peak(float* out_tflops)
 int mmgen_set_serial_stages(int serial)
 {
     g_serialStages = serial != 0;
+    return 0;
+}
+
+int mmgen_set_fill_overlap(int rockCtasPerSM)
+{
+    g_fillOverlap = rockCtasPerSM < 0 ? 0 : rockCtasPerSM;
     return 0;
 }
 

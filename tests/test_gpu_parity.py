@@ -414,6 +414,33 @@ def test_stage_overlap_is_result_neutral(gen, mm, golden):
     assert np.array_equal(hashes[0][1][done], hashes[1][1][done]) and np.array_equal(hashes[0][2][done], hashes[1][2][done])
 
 
+def test_fill_overlap_is_result_neutral(gen, mm, golden):
+    """A fill that spans several 2048-chunk batches can run the terrain / rock / lush passes of batch b + 1 on a second stream while the
+    placement scan of batch b runs (mmgen_set_fill_overlap). Every mode must give the same chunks: identical per-chunk hashes over a
+    region of four batches, twice per mode (the second run reuses the first run's buffers and events), and the reference's blocks for
+    the golden window."""
+    ref = None
+    try:
+        for mode in (0, 8, 4, 16 + 8):
+            gen.set_fill_overlap(mode)
+            world = gen.region_world(-30, 40, 96, 72)
+            for rep in range(2):
+                world.reset()
+                world.generate(mm.STAGE_ALL)
+                hs = world.chunk_hashes()
+                assert len(hs) == 96 * 72
+                if ref is None:
+                    ref = hs
+                assert hs == ref, "fill overlap mode %d changes the world (run %d)" % (mode, rep)
+            world.close()
+            world = gen.region_world(3, 3, 6, 6)
+            world.generate(mm.STAGE_ALL)
+            assert np.array_equal(world.download_region_blocks(), golden["g"]["blocks"])
+            world.close()
+    finally:
+        gen.set_fill_overlap(mm.FILL_OVERLAP_DEFAULT)
+
+
 def test_rock_queue_overflow_is_result_neutral(gen, mm, golden):
     """k_fill_terrain queues rock voxels for the dense kernel k_fill_rock; voxels that do not fit in the queue are
     finished in place. With a queue far too small the blocks must still equal the reference's."""
