@@ -597,6 +597,17 @@ def run_own(args):
     total_chunks = S * S
     value = total_chunks * args.steps / dev_s
 
+    # ---- S6 kernel times without the cross-batch overlap (one extra untimed step): with mmgen_set_fill_overlap on, the event pairs of the
+    # timed steps bracket kernels that share the SMs with another stream's kernels (or wait behind them), so their elapsed times overlap
+    ktimes_s6 = {}
+    if fill_overlap:
+        gen.set_fill_overlap(0)
+        gen.kernel_timing(True)
+        step(variant)
+        ktimes_s6 = {k: v[0] for k, v in gen.kernel_times().items() if v[1]}
+        gen.kernel_timing(False)
+        gen.set_fill_overlap(fill_overlap)
+
     # ---- end-to-end leg: origins from host memory, block volumes into pinned host memory
     step(variant, to_host=True)
     barrier()
@@ -682,7 +693,9 @@ def run_own(args):
                     "algorithmic FLOPs = noise-primitive calls of the reference algorithm x canonical cost (SURVEY.md 8d), evaluations this "
                     "implementation proves unnecessary still count; k_fill_features (placement rasterisation) has no FLOP model and is reported by time" % hbm6}
     r1, r2, r3 = cheap_stage_rooflines(wcount, args.steps, kernels, fp32_peak, pk["hbm_gbs"])      # this rank's counters and kernel times
-    s6k = {k: {"ms": kernels[k]["ms_per_step"], "share_of_S6": kernels[k]["ms_per_step"] / max(float(stage_ms[6]), 1e-9),
+    s6_serial_ms = {k: ktimes_s6.get(k, kernels[k]["ms_per_step"]) for k in kernels}      # = the timed steps' figures when the overlap is off
+    s6_sum = sum(s6_serial_ms.get(k, 0.0) for k in ("k_fill_terrain", "k_fill_rock", "k_fill_lush", "k_prepare_placements", "k_fill_features", "k_decorators"))
+    s6k = {k: {"ms": s6_serial_ms[k], "share_of_S6": s6_serial_ms[k] / max(s6_sum, 1e-9),
                "issue_slot_utilisation_pct": NCU_ISSUE[k][0], "fma_pipe_pct": NCU_PIPES[k][0], "alu_pipe_pct": NCU_PIPES[k][1],
                "active_lanes_of_32": NCU_PIPES[k][2], "src": NCU_ISSUE[k][1]}
            for k in ("k_fill_terrain", "k_fill_rock", "k_fill_features") if k in kernels}
@@ -736,7 +749,11 @@ def run_own(args):
                    "tiles": [list(t) for t in tiles_final], "chunks_touched_rank0": counts,
                    "stage_overlap": "layers + erosion (S2, S3) run on a high-priority side stream while the caves (S4, stage-1 inputs only) run on the "
                                     "main stream; they join before S5. stages.S3.ms / S4.ms are elapsed times of overlapping stages and do not add up to "
-                                    "ms_per_step; the kernel times under `kernels` and the S4 roofline are measured with both streams sharing the SMs",
+                                    "ms_per_step; the kernel times under `kernels` and the S4 roofline are measured with both streams sharing the SMs. "
+                                    "S6 (mmgen_set_fill_overlap %d): %s" % (fill_overlap, "the terrain / rock / lush passes of fill batch b + 1 run on a second stream "
+                                    "while the placement scan + decorators of batch b run on the main stream (different chunks' volumes); the S6 entries of "
+                                    "`kernels` are elapsed times of kernels that share the SMs or wait behind the other stream, stages.S6.kernels has their "
+                                    "times from one extra untimed step with the overlap off" if fill_overlap else "fill passes in sequence"),
                    "l2": "working set per step (>= %.1f GB written) far exceeds the 126 MB L2; no flush needed" % (n_target * 98304 / 1e9)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * max(e2e_wall, e2e_dev) / args.steps, "host_checksum": host_sum,

@@ -428,20 +428,20 @@ static int g_rockQueuePerChunk = kRockQueuePerChunk;   // mmgen_set_rock_queue_p
 // stream; g > 0 = the terrain / rock / lush passes of batch b + 1 run on the side stream while the placement scan of batch b runs on
 // the main stream (they touch different chunks' volumes), with k_fill_rock's persistent grid at g CTAs per SM
 static int g_fillOverlap = 8;                          // 256x256 world on a B200: 454.2 ms off, 446.7 ms at 8 (profiles/r02_fill_overlap.txt)
-static int g_rockGridPerSM = MMG_ROCK_MINBLOCKS;
 
 // the kernel sequence of Chunk::fill for one batch of m chunks (lists indexed by batch position)
 // the fill of one batch in three parts, so that the world path can run the placement preparation of the NEXT batch on its side
 // stream while this batch's terrain / rock passes run: (1) terrain, rock, lush; (2) Prep records of the gathered lists;
 // (3) the placement scan and the decorators
 static int launchFillTerrain(int m, const int* d_list, const int2* d_origins, const float* d_height, const float* d_weights, const float* d_layers,
-                             const CaveLayer* d_caves, uint8_t* d_blocks, uint2* d_rockQueue, uint2* d_lushQueue, int* d_counters, cudaStream_t stream)
+                             const CaveLayer* d_caves, uint8_t* d_blocks, uint2* d_rockQueue, uint2* d_lushQueue, int* d_counters, cudaStream_t stream,
+                             int rockCtasPerSM = MMG_ROCK_MINBLOCKS)
 {
     const int rockCap = (int)std::min<size_t>((size_t)m * g_rockQueuePerChunk, (size_t)kFillBatch * kRockQueuePerChunk);
     MMG_CUDA(cudaMemsetAsync(d_counters, 0, 4 * sizeof(int), stream));
     MMG_TIMED(K_FILL_TERRAIN, stream, 1, MMG_LAUNCH(k_fill_terrain, m * 16, kRowThreads, kNoiseSmemBytes, stream, d_list, d_origins, d_height,
                                                     d_weights, d_layers, d_caves, d_blocks, d_rockQueue, rockCap, d_counters));
-    MMG_TIMED(K_FILL_ROCK, stream, 1, MMG_LAUNCH(k_fill_rock, kNumSMs * g_rockGridPerSM, 128, kNoiseSmemBytes, stream, d_origins, d_height,
+    MMG_TIMED(K_FILL_ROCK, stream, 1, MMG_LAUNCH(k_fill_rock, kNumSMs * rockCtasPerSM, 128, kNoiseSmemBytes, stream, d_origins, d_height,
                                                  (const uint2*)d_rockQueue, rockCap, d_blocks, d_lushQueue, d_counters));
     MMG_TIMED(K_FILL_LUSH, stream, 1, MMG_LAUNCH(k_fill_lush, kNumSMs * 8, 128, kNoiseSmemBytes, stream, d_origins, (const uint2*)d_lushQueue,
                                                  (const int*)d_counters, d_blocks));
@@ -911,7 +911,7 @@ static int worldFill(MmgenWorld* w, const std::vector<int>& list, uint8_t* hostB
         return launchFillPrepare(m, dl, (const int2*)w->d_origins, gF[set], gCF[set], info[set], prepF[set], prepC[set], MAX_FEATURES, MAX_CAVE_FEATURES, st);
     };
     const bool overlapFill = pipelined && (g_fillOverlap & 15) > 0 && !g_serialStages;
-    g_rockGridPerSM = overlapFill ? std::min(g_fillOverlap & 15, (int)MMG_ROCK_MINBLOCKS) : (int)MMG_ROCK_MINBLOCKS;
+    const int rockCtasPerSM = overlapFill ? std::min(g_fillOverlap & 15, (int)MMG_ROCK_MINBLOCKS) : (int)MMG_ROCK_MINBLOCKS;
     // bit 4 of the knob: the overlapped passes go to the high-priority side stream instead of the default-priority fill stream
     cudaStream_t const side = (overlapFill && !(g_fillOverlap & 16)) ? w->fillStream : w->sideStream;
     if (pipelined)
@@ -940,7 +940,7 @@ static int worldFill(MmgenWorld* w, const std::vector<int>& list, uint8_t* hostB
             if (b >= 2) MMG_CUDA(cudaStreamWaitEvent(side, w->evScan[set], 0));
             if (gather(b, side)) return 1;
             if (launchFillTerrain(m, dl, (const int2*)w->d_origins, (const float*)w->d_height, (const float*)w->d_weights, (const float*)w->d_eroded,
-                                  (const CaveLayer*)w->d_caves, w->d_blocks, w->d_rockQueue, w->d_lushQueue, w->d_lushCount, side))
+                                  (const CaveLayer*)w->d_caves, w->d_blocks, w->d_rockQueue, w->d_lushQueue, w->d_lushCount, side, rockCtasPerSM))
                 return 1;
             MMG_CUDA(cudaEventRecord(w->evGather[set], side));
         }
