@@ -694,6 +694,13 @@ def run_own(args):
                     "implementation proves unnecessary still count; k_fill_features (placement rasterisation) has no FLOP model and is reported by time" % hbm6}
     r1, r2, r3 = cheap_stage_rooflines(wcount, args.steps, kernels, fp32_peak, pk["hbm_gbs"])      # this rank's counters and kernel times
     s6_serial_ms = {k: ktimes_s6.get(k, kernels[k]["ms_per_step"]) for k in kernels}      # = the timed steps' figures when the overlap is off
+    if ktimes_s6:
+        # the S6 kernels' entries carry the time the kernel takes by itself (extra step, overlap off); what the event pair of the timed
+        # steps spans - the kernel sharing the SMs with the other stream's kernels, or queued behind them - is kept next to it
+        for k in ("k_gather_features", "k_fill_terrain", "k_fill_rock", "k_fill_lush", "k_prepare_placements", "k_fill_features", "k_decorators"):
+            if k in kernels and k in ktimes_s6:
+                kernels[k] = {"ms_per_step": ktimes_s6[k], "launches_per_step": kernels[k]["launches_per_step"],
+                              "elapsed_ms_in_timed_steps": kernels[k]["ms_per_step"], "src": "extra untimed step with mmgen_set_fill_overlap(0)"}
     s6_sum = sum(s6_serial_ms.get(k, 0.0) for k in ("k_fill_terrain", "k_fill_rock", "k_fill_lush", "k_prepare_placements", "k_fill_features", "k_decorators"))
     s6k = {k: {"ms": s6_serial_ms[k], "share_of_S6": s6_serial_ms[k] / max(s6_sum, 1e-9),
                "issue_slot_utilisation_pct": NCU_ISSUE[k][0], "fma_pipe_pct": NCU_PIPES[k][0], "alu_pipe_pct": NCU_PIPES[k][1],
@@ -752,8 +759,9 @@ def run_own(args):
                                     "ms_per_step; the kernel times under `kernels` and the S4 roofline are measured with both streams sharing the SMs. "
                                     "S6 (mmgen_set_fill_overlap %d): %s" % (fill_overlap, "the terrain / rock / lush passes of fill batch b + 1 run on a second stream "
                                     "while the placement scan + decorators of batch b run on the main stream (different chunks' volumes); the S6 entries of "
-                                    "`kernels` are elapsed times of kernels that share the SMs or wait behind the other stream, stages.S6.kernels has their "
-                                    "times from one extra untimed step with the overlap off" if fill_overlap else "fill passes in sequence"),
+                                    "`kernels` give ms_per_step from one extra untimed step with the overlap off (each kernel by itself) and, as "
+                                    "elapsed_ms_in_timed_steps, what their event pairs span in the timed steps, where they share the SMs with the other "
+                                    "stream's kernels or queue behind them" if fill_overlap else "fill passes in sequence"),
                    "l2": "working set per step (>= %.1f GB written) far exceeds the 126 MB L2; no flush needed" % (n_target * 98304 / 1e9)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * max(e2e_wall, e2e_dev) / args.steps, "host_checksum": host_sum,

@@ -71,25 +71,48 @@ __device__ __forceinline__ void mesh_stage_block_data(uint32_t* shBD)
     __syncthreads();
 }
 
-// Visible faces of voxel (x, y, z) of the chunk as a 6-bit mask (chunk.cu:1879-1936); self = its block (not AIR, not X-shaped).
-__device__ __forceinline__ unsigned mesh_face_mask(const uint8_t* __restrict__ blocks, const MeshChunk& mc, int x, int y, int z, uint32_t selfData,
-                                                   const uint32_t* shBD)
+// Visible faces of a voxel as a 6-bit mask (chunk.cu:1879-1936): mesh_face_mask_strip below; self = its block (not AIR, not X-shaped).
+// The column a warp works on and its four horizontal neighbour columns (+z, +x, -z, -x; from the neighbour chunk at the rim), 384 bytes
+// each, staged in shared memory by coalesced word loads (15 independent loads per lane) before the column is walked: the face tests then
+// read shared memory instead of chasing six dependent global byte loads per voxel (ncu, profiles/r02_k_mesh_{count,emit}.txt: 34 % / 21 %
+// of the stall samples sat on those loads). Returns the mask of horizontal directions whose neighbour chunk does not exist.
+struct MeshStrip { uint32_t w[5][96]; };
+__device__ __forceinline__ unsigned mesh_stage_strip(MeshStrip& S, const uint8_t* __restrict__ blocks, const MeshChunk& mc, int x, int z, int lane)
+{
+    unsigned missing = 0u;
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+    {
+        int nchunk = mc.chunk, nx = x, nz = z;
+        if (k > 0)
+        {
+            const int d = k - 1;
+            nx += mesh_dx(d); nz += mesh_dz(d);
+            if (nx < 0) { nchunk = mc.nb[3]; nx += 16; }
+            else if (nx >= 16) { nchunk = mc.nb[1]; nx -= 16; }
+            else if (nz < 0) { nchunk = mc.nb[2]; nz += 16; }
+            else if (nz >= 16) { nchunk = mc.nb[0]; nz -= 16; }
+            if (nchunk < 0) { missing |= 1u << d; continue; }      // warp-uniform
+        }
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(blocks + (size_t)nchunk * 98304 + 384 * (nx + 16 * nz));
+        S.w[k][lane] = src[lane]; S.w[k][lane + 32] = src[lane + 32]; S.w[k][lane + 64] = src[lane + 64];
+    }
+    __syncwarp();
+    return missing;
+}
+// mesh_face_mask on a staged strip: same tests, same mask
+__device__ __forceinline__ unsigned mesh_face_mask_strip(const MeshStrip& S, unsigned missing, int y, uint32_t selfData, const uint32_t* shBD)
 {
     const unsigned selfTrans = selfData & 3u;
     unsigned mask = 0u;
 #pragma unroll
     for (int d = 0; d < 6; ++d)
     {
-        int nx = x + mesh_dx(d), ny = y + mesh_dy(d), nz = z + mesh_dz(d);
+        const int ny = y + mesh_dy(d);
         if (ny >= 0 && ny < 384)
         {
-            int nchunk = mc.chunk;
-            if (nx < 0) { nchunk = mc.nb[3]; nx += 16; }
-            else if (nx >= 16) { nchunk = mc.nb[1]; nx -= 16; }
-            else if (nz < 0) { nchunk = mc.nb[2]; nz += 16; }
-            else if (nz >= 16) { nchunk = mc.nb[0]; nz -= 16; }
-            if (nchunk < 0) continue;                                  // no neighbour chunk: the face is not emitted (chunk.cu:1908-1911)
-            const uint8_t nb = blocks[(size_t)nchunk * 98304 + ny + 384 * (nx + 16 * nz)];
+            if (d < 4 && ((missing >> d) & 1u)) continue;             // no neighbour chunk: the face is not emitted (chunk.cu:1908-1911)
+            const uint8_t nb = reinterpret_cast<const uint8_t*>(S.w[d < 4 ? d + 1 : 0])[ny];
             const unsigned nTrans = shBD[nb] & 3u;
             const bool show = (selfTrans == 2u) ? (nb == B_AIR || nTrans == 1u) : (nTrans != 0u);
             if (!show) continue;
@@ -99,9 +122,10 @@ __device__ __forceinline__ unsigned mesh_face_mask(const uint8_t* __restrict__ b
     return mask;
 }
 
-// Both kernels: one CTA (12 warps) per chunk; a warp takes columns warp, warp + 12, ... and its lanes take 32 consecutive
-// voxels of the column at a time, so block IDs are read as coalesced runs and the faces of 32 voxels are known together.
+// Both kernels: one CTA (12 warps) per chunk; a warp takes columns warp, warp + 12, ..., stages the column and its four neighbours, and
+// its lanes take 32 consecutive voxels of the column at a time, so the faces of 32 voxels are known together.
 constexpr int kMeshWarps = 12;
+constexpr int kMeshStripBytes = kMeshWarps * (int)sizeof(MeshStrip);
 
 // per chunk: colOff[256] = exclusive scan of the columns' vertex counts, totals[li] = vertices of the chunk
 __global__ void __launch_bounds__(32 * kMeshWarps) k_mesh_count(const MeshChunk* __restrict__ list, const uint8_t* __restrict__ blocks,
@@ -109,20 +133,24 @@ __global__ void __launch_bounds__(32 * kMeshWarps) k_mesh_count(const MeshChunk*
 {
     __shared__ int sh[256];
     __shared__ uint32_t shBD[NUM_BLOCKS];
+    __shared__ MeshStrip shStrip[kMeshWarps];
     const int li = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const MeshChunk mc = list[li];
     mesh_stage_block_data(shBD);
+    MeshStrip& S = shStrip[warp];
     for (int c = warp; c < 256; c += kMeshWarps)
     {
         const int x = c & 15, z = c >> 4;
-        const uint8_t* col = blocks + (size_t)mc.chunk * 98304 + (size_t)c * 384;
+        __syncwarp();                                                      // the previous column's strip has been read
+        const unsigned missing = mesh_stage_strip(S, blocks, mc, x, z, lane);
+        const uint8_t* col = reinterpret_cast<const uint8_t*>(S.w[0]);
         int n = 0;
         for (int y0 = 0; y0 < 384; y0 += 32)
         {
             const uint8_t b = col[y0 + lane];
             if (b == B_AIR) continue;
             const uint32_t data = shBD[b];
-            n += ((data & 3u) == 3u) ? 8 : 4 * __popc(mesh_face_mask(blocks, mc, x, y0 + lane, z, data, shBD));
+            n += ((data & 3u) == 3u) ? 8 : 4 * __popc(mesh_face_mask_strip(S, missing, y0 + lane, data, shBD));
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
@@ -156,8 +184,9 @@ __global__ void __launch_bounds__(32 * kMeshWarps) k_mesh_emit(const MeshChunk* 
                                                                MeshVertex* __restrict__ verts, uint32_t* __restrict__ idx)
 {
     __shared__ MeshQuad shQ[kMeshWarps][kMeshWarpQuads];
-    __shared__ uint2 shStage[kMeshWarps][32 * 5];
+    __shared__ __align__(16) uint2 shStage[kMeshWarps][32 * 5];
     __shared__ uint32_t shBD[NUM_BLOCKS];
+    MeshStrip* shStrip = reinterpret_cast<MeshStrip*>(mmg_dyn_smem);      // kMeshStripBytes of dynamic shared memory (the static arrays take 44 KB)
     const int li = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const MeshChunk mc = list[li];
     mesh_stage_block_data(shBD);
@@ -165,10 +194,13 @@ __global__ void __launch_bounds__(32 * kMeshWarps) k_mesh_emit(const MeshChunk* 
     uint2* iout = reinterpret_cast<uint2*>(idx + (vertBase[li] / 4) * 6);     // 6 indices per 4 vertices throughout; 8-byte aligned
     MeshQuad* Q = shQ[warp];
     uint2* stage = shStage[warp];
+    MeshStrip& S = shStrip[warp];
     for (int c = warp; c < 256; c += kMeshWarps)
     {
         const int x = c & 15, z = c >> 4;
-        const uint8_t* col = blocks + (size_t)mc.chunk * 98304 + (size_t)c * 384;
+        __syncwarp();                                                      // the previous column's strip has been read
+        const unsigned missing = mesh_stage_strip(S, blocks, mc, x, z, lane);
+        const uint8_t* col = reinterpret_cast<const uint8_t*>(S.w[0]);
         int quadBase = colOff[li * 256 + c] / 4;                           // quad index inside the chunk
         for (int y0 = 0; y0 < 384; y0 += 32)
         {
@@ -181,8 +213,9 @@ __global__ void __launch_bounds__(32 * kMeshWarps) k_mesh_emit(const MeshChunk* 
             {
                 data = shBD[b];
                 if ((data & 3u) == 3u) nq = 2;
-                else { mask = mesh_face_mask(blocks, mc, x, y, z, data, shBD); nq = __popc(mask); }
+                else { mask = mesh_face_mask_strip(S, missing, y, data, shBD); nq = __popc(mask); }
             }
+            if (!__ballot_sync(0xffffffffu, nq != 0)) continue;            // air above the terrain, rock below it: most words hold no quad
             int incl = nq;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1)
@@ -272,11 +305,13 @@ __global__ void __launch_bounds__(32 * kMeshWarps) k_mesh_emit(const MeshChunk* 
                     o[4] = make_uint2(q.code >> 25, 0u);
                 }
                 __syncwarp();
-                const int words = min(8, total - f0) * 20;
-                uint2* vo = vout + (size_t)(quadBase + f0) * 20;
+                // a quad is 160 bytes and a chunk's vertices start on a quad boundary of the arena: 16-byte words throughout
+                const int words = min(8, total - f0) * 10;
+                uint4* vo = reinterpret_cast<uint4*>(vout + (size_t)(quadBase + f0) * 20);
+                const uint4* st4 = reinterpret_cast<const uint4*>(stage);
 #pragma unroll
-                for (int r = 0; r < 5; ++r)
-                    if (r * 32 + lane < words) vo[r * 32 + lane] = stage[r * 32 + lane];
+                for (int r = 0; r < 3; ++r)
+                    if (r * 32 + lane < words) vo[r * 32 + lane] = st4[r * 32 + lane];
                 __syncwarp();
             }
             // indices: total quads x 3 words: (f, f+1) (f+2, f) (f+2, f+3) with f = first vertex of the quad

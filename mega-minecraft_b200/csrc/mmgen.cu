@@ -240,6 +240,7 @@ int mmgen_init(int device)
     if (!g_stream) MMG_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     // k_fill_features: 40 KB static + the 10 KB noise tables exceed the 48 KB default
     MMG_CUDA(cudaFuncSetAttribute(k_fill_features, cudaFuncAttributeMaxDynamicSharedMemorySize, kNoiseSmemBytes));
+    MMG_CUDA(cudaFuncSetAttribute(k_mesh_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, kMeshStripBytes));
     MMG_LAUNCH(k_init_noise_tables, 3, 256, 0, g_stream);     // simplex lattice tables (mm_arith.cuh)
     MMG_CUDA(cudaStreamSynchronize(g_stream));
     g_device = device;
@@ -1734,7 +1735,7 @@ int mmgen_world_mesh(MmgenWorld* w, int n, const int32_t* chunkCoords, int32_t* 
         w->meshVertCap = cap;
     }
     MMG_CUDA(cudaMemcpyAsync(w->d_meshBase, w->h_meshBase.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, w->stream));
-    MMG_LAUNCH(k_mesh_emit, n, 32 * kMeshWarps, 0, w->stream, (const MeshChunk*)w->d_meshList, (const uint8_t*)w->d_blocks, (const int*)w->d_meshColOff,
+    MMG_LAUNCH(k_mesh_emit, n, 32 * kMeshWarps, kMeshStripBytes, w->stream, (const MeshChunk*)w->d_meshList, (const uint8_t*)w->d_blocks, (const int*)w->d_meshColOff,
                (const long long*)w->d_meshBase, w->d_meshVerts, w->d_meshIdx);
     MMG_CUDA(cudaEventRecord(e1, w->stream));
     MMG_CUDA(cudaStreamSynchronize(w->stream));
