@@ -287,7 +287,10 @@ int mmgen_heightfields(int n, const int32_t* origins, float* out_heightfield, fl
 // (chunk.cu:682-705) for all zones of the batch in lockstep, with the convergence test on the device.
 static const float kTanRepose[NUM_ERODED] = {1.42814791f, 0.839099586f, 1.0f, 0.839099586f,
                                              0.577350318f, 0.700207531f, 2.14450693f, 1.0f};
-constexpr int kSweepGroup = 8;     // sweeps between two convergence polls
+#ifndef MMG_SWEEP_GROUP
+#define MMG_SWEEP_GROUP 8
+#endif
+constexpr int kSweepGroup = MMG_SWEEP_GROUP;     // sweeps between two convergence polls (even)
 constexpr int kZoneBatch = kMaxZoneBatch;     // zones per launch: 32 x 4 live planes x 590 KB = 75 MB, L2-resident
 
 static int erodeZonesDevice(float* d_zones, int nZones, int* d_flags, cudaStream_t stream, int* sweepsOut)
