@@ -57,6 +57,9 @@ __device__ unsigned long long g_work[W_NUM];
 #ifndef MMG_TERRAIN_MINBLOCKS
 #define MMG_TERRAIN_MINBLOCKS 5
 #endif
+#ifndef MMG_ROCK_TWO_LEVEL
+#define MMG_ROCK_TWO_LEVEL 1
+#endif
 #ifndef MMG_ROCK_MINBLOCKS
 #define MMG_ROCK_MINBLOCKS 8
 #endif

@@ -107,6 +107,48 @@ __device__ MMG_NOISE_INLINE bool cave_biome_is_crystal(int x, int y, int z, floa
     return rand <= 0.f;
 }
 
+// cave_biome_is_crystal in two steps, for callers that regroup their voxels in between (k_fill_rock): the first step stops where
+// `rocky` is exactly 0 (nearly half of the voxels), the second carries on from the warped position with the 2-D noises and the draw.
+// The same operations in the same order as above: rocky(...) && decide(...) == cave_biome_is_crystal(...).
+__device__ MMG_NOISE_INLINE bool cave_crystal_rocky(int x, int y, int z, float4* warped)      // *warped = (cx, cy, cz, rocky)
+{
+    const float px = (float)x, py = (float)y, pz = (float)z;
+    const float qx = px * 0.0470f, qy = py * 0.0470f, qz = pz * 0.0470f;
+    float o1, o2, o3;
+    fbm3_from3<3>(qx, qy, qz, &o1, &o2, &o3);
+    const float cx = fmaf(o1, 30.f, px);
+    const float cy = fmaf(o2, 24.f, py);
+    const float cz = fmaf(o3, 30.f, pz);
+    const float rocky = ss_t(fmaf(simplex3_raw<true>(fmaf(cx, 0.0022f, -9193.23f), fmaf(cy, 0.0022f, -6813.39f), fmaf(cz, 0.0022f, (float)-2171.23)), 42.f, 0.05f) / (0.05f - -0.05f));
+    *warped = make_float4(cx, cy, cz, rocky);
+    return !(rocky == 0.f);
+}
+__device__ MMG_NOISE_INLINE bool cave_crystal_decide(int x, int y, int z, float maxHeight, int seed, float4 warped)
+{
+    const float cx = warped.x, cy = warped.y, cz = warped.z, rocky = warped.w;
+    const float nx = cx * 0.2000f, nz = cz * 0.2000f;
+    const float top = fmaf(maxHeight + -128.f, 0.15f, 128.f);
+    const f32x2 sd = fbm2x2<3>(f2_make(nx + -4921.34f, nx + 9411.32f), f2_make(nz + 8402.13f, nz + -3921.34f));
+    const float sdStart = fmaf(f2_lo(sd), 18.f, top + -72.f);
+    const float sdEnd = fmaf(f2_hi(sd), 7.f, sdStart + -10.f);
+    const float shallow = ss_t((cy - sdEnd) / (sdStart - sdEnd));
+    if (shallow == 0.f) return false;
+    const f32x2 ns = fbm2x2<3>(f2_make(nx, nx + 3821.34f), f2_make(nz, nz + 4920.32f));
+    const float nsStart = fmaf(f2_lo(ns), 23.f, top + -19.f);
+    const float nsEnd = fmaf(f2_hi(ns), 3.f, nsStart + -5.f);
+    const float none = ss_t((cy - nsEnd) / (nsStart - nsEnd));
+    Minstd rng = make_rng4(x, y, z, seed);
+    float rand = rng.u01();
+    rand -= none;                                   // biome 0: NONE
+    if (rand <= 0.f) return false;
+    float w = 1.0f;                                 // biome 1: c_caveBiomeNoiseWeights[1] = {2, 1, 0, 1}
+    w *= 1.0f - none;
+    w *= shallow;
+    w *= rocky;
+    rand -= w;
+    return rand <= 0.f;
+}
+
 // ---------------------------------------------------------------- specialCaveNoise (rng.hpp:282-320)
 // hash (rng.hpp:148-155) at this call site: fma(z, Kz, fma(x, Kx, y*Ky))
 __device__ MMG_NOISE_INLINE float special_cave_noise(float px, float py, float pz)

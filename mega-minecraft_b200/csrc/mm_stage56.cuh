@@ -643,12 +643,55 @@ __global__ void __launch_bounds__(128, MMG_ROCK_MINBLOCKS) k_fill_rock(const int
     const int lane = threadIdx.x & 31;
     uint2* wq = shPending + (threadIdx.x >> 5) * 64;
     int qn = 0;
+#if MMG_ROCK_TWO_LEVEL
+    // second level: the voxels whose `rocky` noise is not 0 (the biome question stops there for the others) wait for a full warp again
+    // before the 2-D noises and the draw
+    __shared__ uint2 shPend2[4 * 64];
+    __shared__ float4 shWarped2[4 * 64];
+    uint2* wq2 = shPend2 + (threadIdx.x >> 5) * 64;
+    float4* ww2 = shWarped2 + (threadIdx.x >> 5) * 64;
+    int qn2 = 0;
+    auto drain2 = [&]() {
+        const int cnt = min(qn2, 32);
+        qn2 -= cnt;
+        const int slot = qn2 + (lane < cnt ? lane : 0);
+        const uint2 e = wq2[slot];
+        const float4 wp = ww2[slot];
+        __syncwarp();
+        if (lane < cnt)
+        {
+            const int chunk = (int)e.x, voxel = (int)(e.y & 0x1ffffu), idx = voxel / 384, y = voxel - idx * 384;
+            const int2 o = origins[chunk];
+            if (cave_crystal_decide(o.x + (idx & 15), y, o.y + (idx >> 4), heightfield[(size_t)chunk * 256 + idx], 190249401, wp))
+                blocks[(size_t)chunk * 98304 + voxel] = ((e.y >> 19) & 1u) ? B_QUARTZ : ((((e.y >> 17) & 3u) == 0u) ? B_COBBLESTONE : B_COBBLED_DEEPSLATE);
+        }
+    };
+#endif
     // pops up to 32 pending bulk voxels: x = chunk, y = voxel | kind << 17 | (quartz ? 1 << 19 : 0)
     auto drain = [&]() {
         const int cnt = min(qn, 32);
         qn -= cnt;
         const uint2 e = wq[qn + (lane < cnt ? lane : 0)];
         __syncwarp();
+#if MMG_ROCK_TWO_LEVEL
+        bool rocky = false;
+        float4 wp = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < cnt)
+        {
+            const int chunk = (int)e.x, voxel = (int)(e.y & 0x1ffffu), idx = voxel / 384, y = voxel - idx * 384;
+            const int2 o = origins[chunk];
+            rocky = cave_crystal_rocky(o.x + (idx & 15), y, o.y + (idx >> 4), &wp);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, rocky);
+        if (rocky)
+        {
+            const int slot = qn2 + __popc(m & ((1u << lane) - 1u));
+            wq2[slot] = e; ww2[slot] = wp;
+        }
+        qn2 += __popc(m);
+        __syncwarp();
+        if (qn2 >= 32) drain2();
+#else
         if (lane < cnt)
         {
             const int chunk = (int)e.x, voxel = (int)(e.y & 0x1ffffu), idx = voxel / 384, y = voxel - idx * 384;
@@ -656,6 +699,7 @@ __global__ void __launch_bounds__(128, MMG_ROCK_MINBLOCKS) k_fill_rock(const int
             if (cave_biome_is_crystal(o.x + (idx & 15), y, o.y + (idx >> 4), heightfield[(size_t)chunk * 256 + idx], 190249401))
                 blocks[(size_t)chunk * 98304 + voxel] = ((e.y >> 19) & 1u) ? B_QUARTZ : ((((e.y >> 17) & 3u) == 0u) ? B_COBBLESTONE : B_COBBLED_DEEPSLATE);
         }
+#endif
     };
     for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x)
     {
@@ -720,6 +764,9 @@ __global__ void __launch_bounds__(128, MMG_ROCK_MINBLOCKS) k_fill_rock(const int
         }
     }
     if (qn > 0) drain();
+#if MMG_ROCK_TWO_LEVEL
+    if (qn2 > 0) drain2();
+#endif
 }
 
 __global__ void __launch_bounds__(128) k_fill_lush(const int2* __restrict__ origins, const uint2* __restrict__ lushQueue,
