@@ -66,7 +66,9 @@ FLOP_BIOME_NOISE = 11 * F_S2                                      # getBiomeNois
 FLOP_FBM5 = 5 * F_S2                                              # one stratified layer's thickness noise (S2)
 # issue-slot utilisation of the S6 kernels from the committed ncu captures (the placement scan has no noise-primitive FLOP model:
 # SURVEY.md 8(d) counts weights, smoothsteps and layer / list logic as 0 FLOP)
-NCU_ISSUE = {"k_caves": (83.7, "profiles/r02_k_caves_final.txt"), "k_fill_rock": (70.6, "profiles/r02_k_fill_rock_final.txt"),
+NCU_ISSUE = {"k_caves": (83.7, "profiles/r02_k_caves_final.txt"),
+             "k_fill_rock": (70.6, "profiles/r02_k_fill_rock_final.txt (captured before the kernel's second regrouping level, DESIGN.md 5 item 30: "
+                                   "the kernel is 7 % faster since and its later noise calls run on fuller warps than the 27.7 lanes listed)"),
              "k_fill_terrain": (80.8, "profiles/r02_k_fill_terrain_final.txt"), "k_fill_features": (75.6, "profiles/r02_k_fill_features_final.txt"),
              "k_erode_sweep": (38.3, "profiles/r02_k_erode_sweep_final.txt")}
 # the same captures: FMA-pipe and ALU-pipe cycles active (% of peak), active lanes per executed warp instruction
