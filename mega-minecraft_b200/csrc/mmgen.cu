@@ -29,7 +29,6 @@ static bool g_ready = false;
 // their buffers; one world must not be driven from two threads at once.
 static std::mutex g_batchMutex;
 #define MMG_BATCH_LOCK() std::lock_guard<std::mutex> mmg_batch_lock_(g_batchMutex)
-static int g_device = -1;
 
 // grow-only device scratch for the batch operators (the reference's Terrain owns fixed staging
 // buffers sized for one tick, terrain.cpp:111-185; here the callee owns them)
@@ -243,7 +242,6 @@ int mmgen_init(int device)
     MMG_CUDA(cudaFuncSetAttribute(k_mesh_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, kMeshStripBytes));
     MMG_LAUNCH(k_init_noise_tables, 3, 256, 0, g_stream);     // simplex lattice tables (mm_arith.cuh)
     MMG_CUDA(cudaStreamSynchronize(g_stream));
-    g_device = device;
     g_ready = true;
     return 0;
 }
