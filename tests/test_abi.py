@@ -53,3 +53,13 @@ def test_product_does_not_reference_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle/" not in text.replace("oracle/tools", "") or f.endswith(".py") is False or "import oracle" not in text, f
                 assert "#include \"../../oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_scheduling_knob_defaults_agree(mm):
+    """The Python binding restores `FILL_OVERLAP_DEFAULT` after tests and bench runs that change mmgen_set_fill_overlap: it has to be
+    the mode the library starts in (csrc/mmgen.cu), and every knob of the header has a binding method."""
+    src = open(os.path.join(ROOT, "mega-minecraft_b200", "csrc", "mmgen.cu")).read()
+    m = re.search(r"static int g_fillOverlap = (\d+);", src)
+    assert m and int(m.group(1)) == mm.FILL_OVERLAP_DEFAULT
+    for method in ("set_fill_overlap", "set_serial_stages"):
+        assert callable(getattr(mm.ChunkGen, method))
