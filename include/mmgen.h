@@ -316,7 +316,7 @@ int mmgen_set_serial_stages(int serial);
  * second stream while the placement scan of batch b runs (they write different chunks' volumes), k_fill_rock's persistent grid sized g
  * CTAs per SM; g + 16: the same on the high-priority side stream. The products are identical in every mode
  * (tests/test_gpu_parity.py::test_fill_overlap_is_result_neutral). */
-int mmgen_set_fill_overlap(int rockCtasPerSM);
+int mmgen_set_fill_overlap(int mode);
 /* achieved FP32 FMA rate of this device (TFLOP/s, 8 independent FFMA chains per thread on every SM): roofline denominator */
 int mmgen_measure_fp32_peak(float* out_tflops);
 /* self-test: the packed-fp32 noise routines (two samples per call on sm_100's FFMA2 / FADD2 / FMUL2) against the scalar routines they

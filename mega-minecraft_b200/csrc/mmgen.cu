@@ -1674,9 +1674,9 @@ int mmgen_set_serial_stages(int serial)
     return 0;
 }
 
-int mmgen_set_fill_overlap(int rockCtasPerSM)
+int mmgen_set_fill_overlap(int mode)
 {
-    g_fillOverlap = rockCtasPerSM < 0 ? 0 : rockCtasPerSM;
+    g_fillOverlap = mode < 0 ? 0 : mode;
     return 0;
 }
 
