@@ -314,7 +314,7 @@ int mmgen_set_serial_stages(int serial);
 /* scheduling knob of a fill that spans several batches (2048 chunks each). 0: a batch's terrain / rock / lush passes and its placement
  * scan + decorators run one after the other on the world's stream. g in 1..8: the terrain / rock / lush passes of batch b + 1 run on a
  * second stream while the placement scan of batch b runs (they write different chunks' volumes), k_fill_rock's persistent grid sized g
- * CTAs per SM; g + 16: the same on the high-priority side stream. The products are identical in every mode
+ * CTAs per SM (the library starts with 8); g + 16: the same on the high-priority side stream. The products are identical in every mode
  * (tests/test_gpu_parity.py::test_fill_overlap_is_result_neutral). */
 int mmgen_set_fill_overlap(int mode);
 /* achieved FP32 FMA rate of this device (TFLOP/s, 8 independent FFMA chains per thread on every SM): roofline denominator */
